@@ -1,0 +1,444 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+// Replaces the cuDNN calls behind BasicBlock.forward (ref: models/backbones/residuals.py:100-120),
+// the 1x1 stride-2 downsample path (:259-263), makeDeconvLayer (:286-310) and the three
+// heads of makeResnetTerminal (ref: models/centerNetOffset.py:103-122), BatchNorm folded.
+//
+// GEMM view: D[m, n] = sum_k A[m, k] * W[n, k];  m = output pixel (8x16 patch of one image),
+// n = output channel, k = (filter tap, input channel).  Activations are NHWC bf16, so for a
+// fixed tap the A tile of 128 pixels x 64 channels is ONE 4-D TMA box {64 ch, 16 x, 8 y, 1 n}
+// of the input tensor shifted by the tap offset; out-of-image coordinates are zero-filled by
+// the TMA unit, which implements the conv padding for free.  The box lands in shared memory
+// as 128 rows of 128 B with the 128-byte swizzle = the canonical K-major UMMA operand.
+//   * stride-2 convs read through four "parity" views (y%2, x%2) of the same NHWC tensor
+//     (strides doubled, base shifted), so every tap is again a dense box: no im2col copy;
+//   * ConvTranspose 4x4 s2 p1 is computed as four output-parity 2x2 convolutions (K = 4*Cin,
+//     no zero insertion), the epilogue scatters to (2y+py, 2x+px).
+//
+// Kernel: persistent, one CTA per SM, 6 warps: warp 0 = TMA producer, warp 1 = MMA issuer
+// (one thread issues tcgen05.mma for the CTA; accumulators live in TMEM, double-buffered when
+// 2*BN <= 512 columns), warps 2-5 = epilogue (tcgen05.ld -> bias/residual/ReLU -> bf16 NHWC,
+// or for the heads: ReLU + block-diagonal 1x1 -> fp32 NCHW planes).
+#include "tc.cuh"
+
+namespace scd {
+
+constexpr int IG_BM = 128;          // pixels per tile = TMEM lanes
+constexpr int IG_BK = 64;           // channels per k-block = one 128 B swizzle row
+constexpr int IG_TW = 16, IG_TH = 8;
+constexpr int IG_THREADS = 192;
+constexpr int IG_A_BYTES = IG_BM * IG_BK * 2;
+
+enum { EPI_STORE = 0, EPI_HEADS = 1 };
+
+struct alignas(64) IgemmParams {
+    CUtensorMap tmA[4];
+    CUtensorMap tmB;
+    int n_taps, cin_blocks, tiles_x, tiles_y, n_par, n_tiles_n, batch, total_tiles;
+    int cout, out_mul, hout, wout, relu;
+    int8_t tap_map[4][9], tap_dy[4][9], tap_dx[4][9];
+    const float* bias;
+    const __nv_bfloat16* residual;
+    __nv_bfloat16* out;
+    // heads epilogue
+    const float* w1;
+    const float* b1;
+    float* heat;
+    float* regr;
+    float* off;
+};
+
+template <int BN> struct IgemmCfg {
+    static constexpr int B_BYTES = BN * IG_BK * 2;
+    static constexpr int STAGE_BYTES = IG_A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN <= 128) ? 6 : (BN == 256 ? 4 : 3);
+    static constexpr int ACC_STAGES = (2 * BN <= 512) ? 2 : 1;
+    static constexpr int TMEM_COLS = (BN * ACC_STAGES <= 128) ? 128 : (BN * ACC_STAGES <= 256 ? 256 : 512);
+    static constexpr int B_BOX_ROWS = (BN > 256) ? BN / 2 : BN;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
+                                      (384 + 7 * 128 + 8) * 4 /*head constants*/;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(IG_THREADS, 1)
+igemm_kernel(const __grid_constant__ IgemmParams p)
+{
+    using Cfg = IgemmCfg<BN>;
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t smem_base = (tc::smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* smem_gen = smem_dyn + (smem_base - tc::smem_u32(smem_dyn));
+    const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+    // barrier slots (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem ptr
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+    uint32_t* tmem_slot_gen = reinterpret_cast<uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES +
+                                                           8 * (2 * Cfg::STAGES + 4));
+    float* head_const = reinterpret_cast<float*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&p.tmB);
+        tc::tma_prefetch_desc(&p.tmA[0]);
+        for (int s = 0; s < Cfg::STAGES; ++s) { tc::mbar_init(full_bar(s), 1); tc::mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(tfull_bar(s), 1); tc::mbar_init(tempty_bar(s), 128); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    if (EPI == EPI_HEADS) {
+        for (int i = threadIdx.x; i < 384 + 7 * 128 + 7; i += IG_THREADS) {
+            float v;
+            if (i < 384) v = p.bias[i];
+            else if (i < 384 + 7 * 128) v = p.w1[i - 384];
+            else v = p.b1[i - 384 - 7 * 128];
+            head_const[i] = v;
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    const int k_blocks = p.n_taps * p.cin_blocks;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const int nt = t % p.n_tiles_n;
+                int m = t / p.n_tiles_n;
+                const int tx = m % p.tiles_x; m /= p.tiles_x;
+                const int ty = m % p.tiles_y; m /= p.tiles_y;
+                const int par = m % p.n_par;
+                const int img = m / p.n_par;
+                const int brow = par * p.cout + nt * BN;
+                for (int tap = 0; tap < p.n_taps; ++tap) {
+                    const CUtensorMap* ma = &p.tmA[p.tap_map[par][tap]];
+                    const int ax = tx * IG_TW + p.tap_dx[par][tap];
+                    const int ay = ty * IG_TH + p.tap_dy[par][tap];
+                    for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                        tc::mbar_wait(empty_bar(stage), phase ^ 1u);
+                        const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                        const uint32_t sb = sa + IG_A_BYTES;
+                        tc::mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+                        tc::tma_load_4d(ma, full_bar(stage), sa, cb * IG_BK, ax, ay, img);
+                        const int kcol = (tap * p.cin_blocks + cb) * IG_BK;
+                        tc::tma_load_2d(&p.tmB, full_bar(stage), sb, kcol, brow);
+                        if (BN > 256)
+                            tc::tma_load_2d(&p.tmB, full_bar(stage), sb + Cfg::B_BOX_ROWS * IG_BK * 2, kcol,
+                                            brow + Cfg::B_BOX_ROWS);
+                        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc_main = tc::umma_idesc_bf16(IG_BM, BN > 256 ? 256 : BN);
+            constexpr uint32_t idesc_tail = tc::umma_idesc_bf16(IG_BM, BN > 256 ? BN - 256 : 16);
+            int stage = 0; uint32_t phase = 0;
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+                const uint32_t as = (Cfg::ACC_STAGES == 2) ? (it & 1u) : 0u;
+                const uint32_t aphase = (Cfg::ACC_STAGES == 2) ? ((it >> 1) & 1u) : (it & 1u);
+                tc::mbar_wait(tempty_bar(as), aphase ^ 1u);
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    tc::mbar_wait(full_bar(stage), phase);
+                    tc::tc_fence_after();
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t sb = sa + IG_A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < IG_BK / 16; ++k) {
+                        const uint64_t adesc = tc::umma_desc_sw128(sa + k * 32);
+                        const uint64_t bdesc = tc::umma_desc_sw128(sb + k * 32);
+                        const uint32_t acc = (kb | k) ? 1u : 0u;
+                        tc::umma_bf16(d_tmem, adesc, bdesc, idesc_main, acc);
+                        if (BN > 256) {
+                            const uint64_t bdesc2 = tc::umma_desc_sw128(sb + 256 * IG_BK * 2 + k * 32);
+                            tc::umma_bf16(d_tmem + 256, adesc, bdesc2, idesc_tail, acc);
+                        }
+                    }
+                    tc::umma_commit(empty_bar(stage));           // frees the smem slot when the MMAs retire
+                    if (kb == k_blocks - 1) tc::umma_commit(tfull_bar(as));
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue warps (TMEM lanes 32*(warp%4) ..) =================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                      // pixel inside the 8x16 patch
+        const int ly = row >> 4, lx = row & 15;
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+            const int nt = t % p.n_tiles_n;
+            int m = t / p.n_tiles_n;
+            const int tx = m % p.tiles_x; m /= p.tiles_x;
+            const int ty = m % p.tiles_y; m /= p.tiles_y;
+            const int par = m % p.n_par;
+            const int img = m / p.n_par;
+            const int oy = (ty * IG_TH + ly) * p.out_mul + (par >> 1);
+            const int ox = (tx * IG_TW + lx) * p.out_mul + (par & 1);
+            const uint32_t as = (Cfg::ACC_STAGES == 2) ? (it & 1u) : 0u;
+            const uint32_t aphase = (Cfg::ACC_STAGES == 2) ? ((it >> 1) & 1u) : (it & 1u);
+            tc::mbar_wait(tfull_bar(as), aphase);
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+
+            if (EPI == EPI_STORE) {
+                const size_t pix = ((size_t)img * p.hout + oy) * p.wout + ox;
+                __nv_bfloat16* optr = p.out + pix * p.cout + nt * BN;
+                const __nv_bfloat16* rptr = p.residual ? p.residual + pix * p.cout + nt * BN : nullptr;
+                const float* bptr = p.bias + nt * BN;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t r[32];
+                    tc::tmem_ld32(taddr + c0, r);
+                    tc::tmem_ld_wait();
+                    __align__(16) __nv_bfloat162 o[16];
+                    uint4 resv[4];
+                    if (rptr) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) resv[i] = reinterpret_cast<const uint4*>(rptr + c0)[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float a = __uint_as_float(r[2 * i]) + __ldg(bptr + c0 + 2 * i);
+                        float b = __uint_as_float(r[2 * i + 1]) + __ldg(bptr + c0 + 2 * i + 1);
+                        if (rptr) {
+                            const __nv_bfloat162 rr = reinterpret_cast<const __nv_bfloat162*>(resv)[i];
+                            a += __low2float(rr);
+                            b += __high2float(rr);
+                        }
+                        if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                        o[i] = __floats2bfloat162_rn(a, b);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        reinterpret_cast<uint4*>(optr + c0)[i] = reinterpret_cast<const uint4*>(o)[i];
+                }
+            } else {
+                // heads: hidden = ReLU(acc + b3); out_j = b1_j + sum_c hidden[head(j), c] * w1[j, c]
+                const float* b3 = head_const;
+                const float* w1 = head_const + 384;
+                const float* b1 = head_const + 384 + 7 * 128;
+                float o[7];
+#pragma unroll
+                for (int j = 0; j < 7; ++j) o[j] = b1[j];
+#pragma unroll 1
+                for (int c0 = 0; c0 < 384; c0 += 32) {
+                    uint32_t r[32];
+                    tc::tmem_ld32(taddr + c0, r);
+                    tc::tmem_ld_wait();
+                    const int head = c0 >> 7, hc = c0 & 127;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float h = fmaxf(__uint_as_float(r[i]) + b3[c0 + i], 0.f);
+                        if (head == 0) {
+                            o[0] = fmaf(h, w1[hc + i], o[0]);
+                        } else if (head == 1) {
+                            o[1] = fmaf(h, w1[1 * 128 + hc + i], o[1]);
+                            o[2] = fmaf(h, w1[2 * 128 + hc + i], o[2]);
+                            o[3] = fmaf(h, w1[3 * 128 + hc + i], o[3]);
+                            o[4] = fmaf(h, w1[4 * 128 + hc + i], o[4]);
+                        } else {
+                            o[5] = fmaf(h, w1[5 * 128 + hc + i], o[5]);
+                            o[6] = fmaf(h, w1[6 * 128 + hc + i], o[6]);
+                        }
+                    }
+                }
+                const size_t hw = (size_t)p.hout * p.wout;
+                const size_t pix = (size_t)oy * p.wout + ox;
+                p.heat[(size_t)img * hw + pix] = o[0];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) p.regr[((size_t)img * 4 + j) * hw + pix] = o[1 + j];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) p.off[((size_t)img * 2 + j) * hw + pix] = o[5 + j];
+            }
+            tc::tc_fence_before();
+            tc::mbar_arrive(tempty_bar(as));                 // 128 arrivals release the accumulator
+        }
+    }
+
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// NHWC bf16 activation viewed as a 4-D tensor {C, W/sub, H/sub, N}; sub = 2 selects the
+// (py, px) parity view used by stride-2 convolutions.
+static int make_act_map(CUtensorMap* m, const void* base, int n, int h, int w, int c, int sub, int py, int px)
+{
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return fail(SCD_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const char* b = static_cast<const char*>(base) + ((size_t)py * w + px) * c * 2;
+    cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)(w / sub), (cuuint64_t)(h / sub), (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)sub * c * 2, (cuuint64_t)sub * w * c * 2, (cuuint64_t)h * w * c * 2};
+    cuuint32_t box[4] = {IG_BK, IG_TW, IG_TH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(b), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SCD_ECUDA, "cuTensorMapEncodeTiled(activation) failed: %d", (int)r);
+    return SCD_OK;
+}
+
+// weights: 2-D {K, rows} bf16, K contiguous
+static int make_w_map(CUtensorMap* m, const void* base, int k_total, int rows, int box_rows)
+{
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return fail(SCD_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
+    cuuint32_t box[2] = {IG_BK, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SCD_ECUDA, "cuTensorMapEncodeTiled(weight) failed: %d", (int)r);
+    return SCD_OK;
+}
+
+template <int BN, int EPI>
+static int launch_igemm(const IgemmParams& p, cudaStream_t st)
+{
+    using Cfg = IgemmCfg<BN>;
+    static bool attr_done = false;     // idempotent per-process kernel attribute
+    if (!attr_done) {
+        SCD_CUDA_CHECK(cudaFuncSetAttribute(igemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            Cfg::SMEM_BYTES));
+        attr_done = true;
+    }
+    const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+    igemm_kernel<BN, EPI><<<grid, IG_THREADS, Cfg::SMEM_BYTES, st>>>(p);
+    SCD_LAUNCH_CHECK("igemm_kernel");
+    return SCD_OK;
+}
+
+// kind: 0 = 3x3 s1 p1, 1 = 3x3 s2 p1, 2 = 1x1 s2, 3 = deconv 4x4 s2 p1
+static int fill_geometry(IgemmParams& p, int kind, const void* x, int batch, int hin, int win, int cin)
+{
+    int gh, gw;        // output grid the tiles cover (per parity class for the deconv)
+    p.n_par = 1; p.out_mul = 1;
+    for (int a = 0; a < 4; ++a) for (int t = 0; t < 9; ++t) { p.tap_map[a][t] = 0; p.tap_dy[a][t] = 0; p.tap_dx[a][t] = 0; }
+    if (kind == 0) {
+        gh = hin; gw = win; p.n_taps = 9; p.hout = hin; p.wout = win;
+        int rc = make_act_map(&p.tmA[0], x, batch, hin, win, cin, 1, 0, 0); if (rc) return rc;
+        for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
+        for (int r = 0; r < 3; ++r) for (int s = 0; s < 3; ++s) { p.tap_dy[0][r * 3 + s] = (int8_t)(r - 1); p.tap_dx[0][r * 3 + s] = (int8_t)(s - 1); }
+    } else if (kind == 1 || kind == 2) {
+        if (hin % 2 || win % 2) return fail(SCD_EINVAL, "stride-2 conv needs even input size");
+        gh = hin / 2; gw = win / 2; p.hout = gh; p.wout = gw;
+        for (int py = 0; py < 2; ++py) for (int px = 0; px < 2; ++px) {
+            int rc = make_act_map(&p.tmA[py * 2 + px], x, batch, hin, win, cin, 2, py, px); if (rc) return rc;
+        }
+        if (kind == 2) { p.n_taps = 1; }
+        else {
+            p.n_taps = 9;
+            // input row 2*oy + r - 1: r=0 -> odd row of block oy-1, r=1 -> even row of block oy, r=2 -> odd row of block oy
+            const int par_of[3] = {1, 0, 1}, off_of[3] = {-1, 0, 0};
+            for (int r = 0; r < 3; ++r) for (int s = 0; s < 3; ++s) {
+                p.tap_map[0][r * 3 + s] = (int8_t)(par_of[r] * 2 + par_of[s]);
+                p.tap_dy[0][r * 3 + s] = (int8_t)off_of[r];
+                p.tap_dx[0][r * 3 + s] = (int8_t)off_of[s];
+            }
+        }
+    } else if (kind == 3) {
+        gh = hin; gw = win; p.hout = 2 * hin; p.wout = 2 * win; p.n_par = 4; p.out_mul = 2; p.n_taps = 4;
+        int rc = make_act_map(&p.tmA[0], x, batch, hin, win, cin, 1, 0, 0); if (rc) return rc;
+        for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
+        // oy = 2*iy - 1 + kh.  even oy=2j: kh=1 -> iy=j, kh=3 -> iy=j-1;  odd oy=2j+1: kh=0 -> iy=j+1, kh=2 -> iy=j.
+        // tap order inside a parity class = (a, b) with a, b in {0,1}: the host packs weights the same way
+        const int dy_of[2][2] = {{0, -1}, {1, 0}};
+        for (int qy = 0; qy < 2; ++qy) for (int qx = 0; qx < 2; ++qx)
+            for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) {
+                p.tap_dy[qy * 2 + qx][a * 2 + b] = (int8_t)dy_of[qy][a];
+                p.tap_dx[qy * 2 + qx][a * 2 + b] = (int8_t)dy_of[qx][b];
+            }
+    } else {
+        return fail(SCD_EINVAL, "unknown conv kind %d", kind);
+    }
+    if (gh % IG_TH || gw % IG_TW)
+        return fail(SCD_EINVAL, "output grid %dx%d is not a multiple of the %dx%d pixel tile", gh, gw, IG_TH, IG_TW);
+    if (cin % IG_BK) return fail(SCD_EINVAL, "Cin = %d is not a multiple of %d", cin, IG_BK);
+    p.cin_blocks = cin / IG_BK;
+    p.tiles_x = gw / IG_TW; p.tiles_y = gh / IG_TH; p.batch = batch;
+    return SCD_OK;
+}
+
+static int pick_bn(int cout) { return cout >= 256 ? 256 : (cout >= 128 ? 128 : 64); }
+
+}  // namespace scd
+
+extern "C" int scd_conv_igemm_fwd(int kind, const void* x, const void* weight, const float* bias,
+                                  const void* residual, int relu, int batch, int hin, int win,
+                                  int cin, int cout, void* y, void* stream)
+{
+    using namespace scd;
+    if (batch <= 0) return SCD_OK;
+    if (!x || !weight || !bias || !y) return fail(SCD_EINVAL, "scd_conv_igemm_fwd: null pointer");
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = fill_geometry(p, kind, x, batch, hin, win, cin);
+    if (rc) return rc;
+    const int bn = pick_bn(cout);
+    if (cout % bn) return fail(SCD_EINVAL, "Cout = %d unsupported", cout);
+    p.cout = cout; p.n_tiles_n = cout / bn; p.relu = relu;
+    p.total_tiles = batch * p.n_par * p.tiles_y * p.tiles_x * p.n_tiles_n;
+    p.bias = bias; p.residual = static_cast<const __nv_bfloat16*>(residual); p.out = static_cast<__nv_bfloat16*>(y);
+    rc = make_w_map(&p.tmB, weight, p.n_taps * cin, p.n_par * cout, bn);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bn == 256) return launch_igemm<256, EPI_STORE>(p, st);
+    if (bn == 128) return launch_igemm<128, EPI_STORE>(p, st);
+    return launch_igemm<64, EPI_STORE>(p, st);
+}
+
+extern "C" int scd_heads_fwd(const void* x, const void* w3, const float* b3, const float* w1,
+                             const float* b1, int batch, int height, int width,
+                             float* heat, float* regr, float* offset, void* stream)
+{
+    using namespace scd;
+    if (batch <= 0) return SCD_OK;
+    if (!x || !w3 || !b3 || !w1 || !b1 || !heat || !regr || !offset)
+        return fail(SCD_EINVAL, "scd_heads_fwd: null pointer");
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = fill_geometry(p, 0, x, batch, height, width, 256);
+    if (rc) return rc;
+    p.cout = 384; p.n_tiles_n = 1; p.relu = 1;
+    p.total_tiles = batch * p.tiles_y * p.tiles_x;
+    p.bias = b3; p.w1 = w1; p.b1 = b1; p.heat = heat; p.regr = regr; p.off = offset;
+    rc = make_w_map(&p.tmB, w3, 9 * 256, 384, IgemmCfg<384>::B_BOX_ROWS);
+    if (rc) return rc;
+    return launch_igemm<384, EPI_HEADS>(p, (cudaStream_t)stream);
+}

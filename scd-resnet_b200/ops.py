@@ -1,0 +1,215 @@
+"""Tensor-facing wrappers of the C ABI (include/scd_b200.h).
+
+PyTorch is used for device memory and streams only; every function launches hand-written
+sm_100a kernels from libscd_b200.so on torch's current stream.  Inputs must be CUDA tensors;
+there is no CPU path.
+"""
+import ctypes
+
+import torch
+
+from ._lib import lib, check, ScdError
+
+MAXTAGLEN = 30      # ref: datasets/scds/scdx16p100.py:46
+HEATMAPSIZE = 128   # ref: datasets/scds/scdx16p100.py:50
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t, dtype, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ScdError("%s must be a CUDA tensor (scd_b200 has no CPU path)" % name)
+    if t.dtype != dtype:
+        raise ScdError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t.contiguous()
+
+
+def decode_topk(heat, regr, offset, K=100, planes=False):
+    """decodeCenterNet (ref: models/centerNetOffset.py:219-251) on LOGITS.
+
+    Returns (scores f32 (B,K), idx i64, ys i64, xs i64, offset (B,K,2), regr (B,K,4)) and, when
+    `planes`, also the (10,B,K) f32 stack of trainer/wrappers/centerOffsetResidual.py:11-22.
+    """
+    heat = _req(heat, torch.float32, "heatmap")
+    regr = _req(regr, torch.float32, "regr")
+    offset = _req(offset, torch.float32, "offset")
+    b, c, h, w = heat.shape
+    dev = heat.device
+    scores = torch.empty(b, K, dtype=torch.float32, device=dev)
+    idx = torch.empty(b, K, dtype=torch.int64, device=dev)
+    ys = torch.empty(b, K, dtype=torch.int64, device=dev)
+    xs = torch.empty(b, K, dtype=torch.int64, device=dev)
+    off_out = torch.empty(b, K, 2, dtype=torch.float32, device=dev)
+    regr_out = torch.empty(b, K, 4, dtype=torch.float32, device=dev)
+    pl = torch.empty(10, b, K, dtype=torch.float32, device=dev) if planes else None
+    with torch.cuda.device(dev):
+        check(lib.scd_decode_topk(_ptr(heat), _ptr(regr), _ptr(offset), b, c, h, w, K, _ptr(scores), _ptr(idx),
+                                  _ptr(ys), _ptr(xs), _ptr(off_out), _ptr(regr_out), _ptr(pl), _stream()),
+              "scd_decode_topk")
+    out = (scores, idx, ys, xs, off_out, regr_out)
+    return out + (pl,) if planes else out
+
+
+def render_targets(locs, counts):
+    """Gaussian target rendering + batch contract (ref: datasets/scds/scdx16p100.py:328-356,514-536,575-591).
+
+    locs (B,30,8) f32, counts (B,) i32 -> heat (B,1,128,128) f32, mask (B,30) bool, regr6 (B,30,6) f32,
+    idx (B,30) i64.
+    """
+    locs = _req(locs, torch.float32, "locs")
+    counts = _req(counts, torch.int32, "counts")
+    b = locs.shape[0]
+    if tuple(locs.shape[1:]) != (MAXTAGLEN, 8):
+        raise ScdError("locs must be (B,30,8)")
+    dev = locs.device
+    heat = torch.empty(b, 1, HEATMAPSIZE, HEATMAPSIZE, dtype=torch.float32, device=dev)
+    mask = torch.empty(b, MAXTAGLEN, dtype=torch.bool, device=dev)
+    regr6 = torch.empty(b, MAXTAGLEN, 6, dtype=torch.float32, device=dev)
+    idx = torch.empty(b, MAXTAGLEN, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.scd_render_targets(_ptr(locs), _ptr(counts), b, _ptr(heat), _ptr(mask), _ptr(regr6), _ptr(idx),
+                                     _stream()), "scd_render_targets")
+    return heat, mask, regr6, idx
+
+
+def centernet_loss(heat, regr, offset, gt_heat, mask, regr6, idx, regr_w=0.1, off_w=0.1, with_grad=True,
+                   sigmoid_inplace=True):
+    """CenterNetLoss fwd+bwd (ref: models/centerNetOffset.py:182-217).
+
+    Returns (losses f32[4] = total, focal, size, offset; d_heat, d_regr, d_off or None).  With
+    `sigmoid_inplace` `heat` is overwritten by sigmoid(heat) like the reference's sigmoid_ (utility.py:121).
+    """
+    heat = _req(heat, torch.float32, "heatmap")
+    regr = _req(regr, torch.float32, "regr")
+    offset = _req(offset, torch.float32, "offset")
+    gt_heat = _req(gt_heat, torch.float32, "gt heat")
+    regr6 = _req(regr6, torch.float32, "gt regr")
+    idx = _req(idx, torch.int64, "gt idx")
+    if mask.dtype == torch.bool:
+        mask = mask.contiguous().view(torch.uint8)
+    mask = _req(mask, torch.uint8, "mask")
+    b, c, h, w = heat.shape
+    if c != 1:
+        raise ScdError("heatmap must have one class")
+    dev = heat.device
+    losses = torch.empty(4, dtype=torch.float32, device=dev)
+    if with_grad:
+        d_heat, d_regr, d_off = torch.empty_like(heat), torch.empty_like(regr), torch.empty_like(offset)
+    else:
+        d_heat = d_regr = d_off = None
+    nbytes = lib.scd_centernet_loss_workspace_bytes(b, h, w)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.scd_centernet_loss(_ptr(heat), _ptr(heat if sigmoid_inplace else None), _ptr(regr), _ptr(offset),
+                                     _ptr(gt_heat), _ptr(mask), _ptr(regr6), _ptr(idx), b, h, w, mask.shape[1],
+                                     regr_w, off_w, _ptr(losses), _ptr(d_heat), _ptr(d_regr), _ptr(d_off),
+                                     _ptr(ws), nbytes, _stream()), "scd_centernet_loss")
+    return losses, d_heat, d_regr, d_off
+
+
+def stem_fwd(x, weight, bias):
+    """ResNet.preprocess (ref: models/backbones/residuals.py:210-215), BN folded. -> (B,H/4,W/4,64) bf16 NHWC."""
+    x = _req(x, torch.float32, "x")
+    weight = _req(weight, torch.float32, "stem weight")
+    bias = _req(bias, torch.float32, "stem bias")
+    b, c, h, w = x.shape
+    y = torch.empty(b, h // 4, w // 4, 64, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.scd_stem_fwd(_ptr(x), _ptr(weight), _ptr(bias), b, h, w, _ptr(y), _stream()), "scd_stem_fwd")
+    return y
+
+
+def conv_igemm_fwd(kind, x, weight, bias, residual=None, relu=True):
+    """One implicit-GEMM stage. x (B,H,W,Cin) bf16 NHWC; weight packed by weights.pack_conv; -> NHWC bf16."""
+    x = _req(x, torch.bfloat16, "x")
+    weight = _req(weight, torch.bfloat16, "weight")
+    bias = _req(bias, torch.float32, "bias")
+    b, h, w, cin = x.shape
+    cout = bias.numel()
+    if kind == 0:
+        ho, wo = h, w
+    elif kind in (1, 2):
+        ho, wo = h // 2, w // 2
+    else:
+        ho, wo = 2 * h, 2 * w
+    y = torch.empty(b, ho, wo, cout, dtype=torch.bfloat16, device=x.device)
+    if residual is not None:
+        residual = _req(residual, torch.bfloat16, "residual")
+        if residual.shape != y.shape:
+            raise ScdError("residual shape mismatch")
+    with torch.cuda.device(x.device):
+        check(lib.scd_conv_igemm_fwd(kind, _ptr(x), _ptr(weight), _ptr(bias), _ptr(residual), int(relu), b, h, w,
+                                     cin, cout, _ptr(y), _stream()), "scd_conv_igemm_fwd")
+    return y
+
+
+def heads_fwd(x, w3, b3, w1, b1):
+    """The three heads fused (ref: models/centerNetOffset.py:103-122). x (B,H,W,256) bf16 -> NCHW f32 maps."""
+    x = _req(x, torch.bfloat16, "x")
+    b, h, w, c = x.shape
+    heat = torch.empty(b, 1, h, w, dtype=torch.float32, device=x.device)
+    regr = torch.empty(b, 4, h, w, dtype=torch.float32, device=x.device)
+    off = torch.empty(b, 2, h, w, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.scd_heads_fwd(_ptr(x), _ptr(_req(w3, torch.bfloat16, "w3")), _ptr(_req(b3, torch.float32, "b3")),
+                                _ptr(_req(w1, torch.float32, "w1")), _ptr(_req(b1, torch.float32, "b1")), b, h, w,
+                                _ptr(heat), _ptr(regr), _ptr(off), _stream()), "scd_heads_fwd")
+    return heat, regr, off
+
+
+def infer_weights_layout():
+    n = 34
+    offs = (ctypes.c_size_t * n)()
+    sizes = (ctypes.c_size_t * n)()
+    check(lib.scd_infer_weights_layout(offs, sizes, n), "scd_infer_weights_layout")
+    return list(offs), list(sizes), lib.scd_infer_weights_bytes()
+
+
+def resnet10_infer(x, blob, workspace=None, out=None):
+    """ResNet.forward, eval, decode=False (ref: models/backbones/residuals.py:312-334) as one native call.
+
+    x (B,1,H,W) f32; blob = packed BN-folded weights (weights.pack_infer_blob).  Returns heat, regr, offset
+    (NCHW f32) and the workspace (reusable).
+    """
+    x = _req(x, torch.float32, "x")
+    b, c, h, w = x.shape
+    dev = x.device
+    nbytes = lib.scd_infer_workspace_bytes(b, h, w)
+    if workspace is None or workspace.numel() < nbytes:
+        workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    if out is None:
+        out = (torch.empty(b, 1, h // 4, w // 4, dtype=torch.float32, device=dev),
+               torch.empty(b, 4, h // 4, w // 4, dtype=torch.float32, device=dev),
+               torch.empty(b, 2, h // 4, w // 4, dtype=torch.float32, device=dev))
+    heat, regr, off = out
+    with torch.cuda.device(dev):
+        check(lib.scd_resnet10_infer(_ptr(x), _ptr(blob), b, h, w, _ptr(heat), _ptr(regr), _ptr(off),
+                                     _ptr(workspace), workspace.numel(), _stream()), "scd_resnet10_infer")
+    return heat, regr, off, workspace
+
+
+def slide_geometry(height, width):
+    """ref: test.py:48-57 -> (clipH, clipV, resizeH, resizeW, padTB, padLR)."""
+    g = (ctypes.c_int * 6)()
+    check(lib.scd_slide_geometry(height, width, g), "scd_slide_geometry")
+    return tuple(g)
+
+
+def slide_tiles(gray, tile_begin=0, tile_end=None):
+    """Reflect pad + stride-384 tiling + per-tile fp64 normalise (ref: test.py:48-90). gray (H,W) f32 CUDA."""
+    gray = _req(gray, torch.float32, "gray")
+    h, w = gray.shape
+    g = slide_geometry(h, w)
+    total = g[0] * g[1]
+    if tile_end is None:
+        tile_end = total
+    tiles = torch.empty(tile_end - tile_begin, 1, 512, 512, dtype=torch.float32, device=gray.device)
+    with torch.cuda.device(gray.device):
+        check(lib.scd_slide_tiles(_ptr(gray), h, w, tile_begin, tile_end, _ptr(tiles), _stream()), "scd_slide_tiles")
+    return tiles

@@ -1,0 +1,89 @@
+"""Host-side weight preparation: BatchNorm folding and GEMM-operand packing.
+
+Runs once per set of parameters (not on the hot path).  Works on whatever device the
+state_dict lives on; the packed blob is what scd_resnet10_infer consumes.
+"""
+import torch
+
+from . import ops
+
+BN_EPS = 1e-5      # torch.nn.BatchNorm2d default (ref: models/backbones/residuals.py:212)
+
+# igemm stages in blob order: (conv key, bn prefix, kind)
+STAGES = [
+    ("layer1.0.conv1", "layer1.0.bn1", 0), ("layer1.0.conv2", "layer1.0.bn2", 0),
+    ("layer2.0.downsample.0", "layer2.0.downsample.1", 2), ("layer2.0.conv1", "layer2.0.bn1", 1),
+    ("layer2.0.conv2", "layer2.0.bn2", 0),
+    ("layer3.0.downsample.0", "layer3.0.downsample.1", 2), ("layer3.0.conv1", "layer3.0.bn1", 1),
+    ("layer3.0.conv2", "layer3.0.bn2", 0),
+    ("layer4.0.downsample.0", "layer4.0.downsample.1", 2), ("layer4.0.conv1", "layer4.0.bn1", 1),
+    ("layer4.0.conv2", "layer4.0.bn2", 0),
+    ("deconvolutionLayers.0", "deconvolutionLayers.1", 3), ("deconvolutionLayers.3", "deconvolutionLayers.4", 3),
+    ("deconvolutionLayers.6", "deconvolutionLayers.7", 3),
+]
+HEADS = ("heatmap", "regr", "offset")     # dict order (ref: models/centerNetOffset.py:165)
+
+
+def bn_scale_shift(sd, prefix):
+    """Eval-mode BN as y = x * scale + shift."""
+    scale = sd[prefix + ".weight"].float() / torch.sqrt(sd[prefix + ".running_var"].float() + BN_EPS)
+    shift = sd[prefix + ".bias"].float() - sd[prefix + ".running_mean"].float() * scale
+    return scale, shift
+
+
+def pack_conv(weight, kind, scale=None):
+    """Conv2d weight (Cout,Cin,R,S) -> (Cout, R*S*Cin) bf16, k = (r*S + s)*Cin + c (kinds 0-2);
+    ConvTranspose2d weight (Cin,Cout,4,4) -> (4, Cout, 4*Cin) bf16 by output parity (kind 3):
+    class (qy,qx), tap (a,b): kh = KH[qy][a], kw = KH[qx][b], KH = [[1,3],[0,2]]
+    (oy = 2*iy - 1 + kh; see csrc/igemm.cu fill_geometry)."""
+    w = weight.float()
+    if kind != 3:
+        if scale is not None:
+            w = w * scale.view(-1, 1, 1, 1)
+        return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
+    if scale is not None:
+        w = w * scale.view(1, -1, 1, 1)
+    kh_of = ((1, 3), (0, 2))
+    cin, cout = w.shape[0], w.shape[1]
+    out = torch.empty(4, cout, 4 * cin, dtype=torch.float32, device=w.device)
+    for qy in range(2):
+        for qx in range(2):
+            for a in range(2):
+                for b in range(2):
+                    t = a * 2 + b
+                    out[qy * 2 + qx, :, t * cin:(t + 1) * cin] = w[:, :, kh_of[qy][a], kh_of[qx][b]].t()
+    return out.to(torch.bfloat16).contiguous()
+
+
+def fold(sd):
+    """BN-folded, packed tensors of every stage (dict of name -> tensor), for eval-mode inference."""
+    out = {}
+    s, b = bn_scale_shift(sd, "preprocess.1")
+    out["stem_w"] = (sd["preprocess.0.weight"].float() * s.view(-1, 1, 1, 1)).reshape(64, 49).contiguous()
+    out["stem_b"] = b.contiguous()
+    for i, (ck, bk, kind) in enumerate(STAGES):
+        s, b = bn_scale_shift(sd, bk)
+        out["w%d" % i] = pack_conv(sd[ck + ".weight"], kind, s)
+        out["b%d" % i] = b.contiguous()
+    out["w3"] = torch.cat([pack_conv(sd[h + ".0.weight"], 0) for h in HEADS], 0).contiguous()
+    out["b3"] = torch.cat([sd[h + ".0.bias"].float() for h in HEADS], 0).contiguous()
+    out["w1"] = torch.cat([sd[h + ".2.weight"].float().reshape(-1, 128) for h in HEADS], 0).contiguous()
+    out["b1"] = torch.cat([sd[h + ".2.bias"].float() for h in HEADS], 0).contiguous()
+    return out
+
+
+def pack_infer_blob(sd, device):
+    """The packed parameter blob of scd_resnet10_infer (layout: include/scd_b200.h)."""
+    f = fold(sd)
+    offs, sizes, total = ops.infer_weights_layout()
+    entries = [f["stem_w"], f["stem_b"]]
+    for i in range(len(STAGES)):
+        entries += [f["w%d" % i], f["b%d" % i]]
+    entries += [f["w3"], f["b3"], f["w1"], f["b1"]]
+    blob = torch.zeros(total, dtype=torch.uint8, device=device)
+    for e, o, n in zip(entries, offs, sizes):
+        raw = e.contiguous().view(torch.uint8).reshape(-1)
+        if raw.numel() != n:
+            raise ops.ScdError("blob entry size mismatch: %d vs %d" % (raw.numel(), n))
+        blob[o:o + n] = raw.to(device)
+    return blob

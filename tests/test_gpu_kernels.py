@@ -1,0 +1,289 @@
+"""Parity of every CUDA kernel (through the C ABI) against the CPU oracle.  Needs a B200."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import centernet_cpu as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def S():
+    import scd_resnet_b200 as s
+    return s
+
+
+def dev(t):
+    return t.cuda()
+
+
+def relmax(a, b):
+    a = a.detach().double().cpu(); b = b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+# ------------------------------------------------------------------------------ decode
+def _check_decode(S, heat, regr, off, K=100, exact=True):
+    out = S.ops.decode_topk(dev(heat), dev(regr), dev(off), K=K, planes=True)
+    sc, idx, ys, xs, o, r, planes = [t.cpu() for t in out]
+    esc, eidx, eys, exs, eo, er = O.decode_centernet({"heatmap": heat, "regr": regr, "offset": off}, K=K)
+    if exact:
+        assert torch.equal(idx, eidx)
+        assert torch.equal(ys, eys) and torch.equal(xs, exs)
+        assert torch.equal(o, eo) and torch.equal(r, er)          # gathers are copies: bit exact
+    assert relmax(sc, esc) < 1e-5                                  # sigmoid: 1e-5 rel (fp32)
+    assert relmax(planes, O.wrapper_stack(esc, eidx, eys, exs, eo, er)) < 1e-5 or not exact
+    # structural invariants, independent of the oracle
+    assert (sc[:, :-1] >= sc[:, 1:]).all()
+    assert torch.equal(ys * 128 + xs, idx)
+    for b in range(idx.shape[0]):
+        assert len(set(idx[b].tolist())) == K
+    return sc, idx
+
+
+def test_decode_kat_ties(S, golden):
+    """SURVEY 8c KAT: exact score ties; our order is (score desc, idx asc) like the oracle's."""
+    i = np.arange(2 * 128 * 128, dtype=np.float64)
+    heat = torch.from_numpy((3 * np.sin(0.37 * i) - 2).astype(np.float32)).reshape(2, 1, 128, 128)
+    j4 = np.arange(2 * 4 * 128 * 128, dtype=np.float64)
+    j2 = np.arange(2 * 2 * 128 * 128, dtype=np.float64)
+    regr = torch.from_numpy((0.5 * np.cos(0.11 * j4)).astype(np.float32)).reshape(2, 4, 128, 128)
+    off = torch.from_numpy((2 + 2 * np.sin(0.23 * j2)).astype(np.float32)).reshape(2, 2, 128, 128)
+    sc, idx = _check_decode(S, heat, regr, off, exact=False)
+    g = golden("kat")
+    assert int(idx.sum()) == 1645770
+    for b in range(2):
+        assert sorted(idx[b].tolist()) == sorted(g["dec_idx"][b].tolist())
+    assert relmax(sc, torch.from_numpy(g["dec_scores"])) < 1e-5
+
+
+def test_decode_random_maps(S):
+    rng = np.random.default_rng(5)
+    heat = torch.from_numpy(rng.standard_normal((8, 1, 128, 128)).astype(np.float32) * 1.5 - 2)
+    regr = torch.from_numpy(rng.standard_normal((8, 4, 128, 128)).astype(np.float32))
+    off = torch.from_numpy(rng.standard_normal((8, 2, 128, 128)).astype(np.float32))
+    _check_decode(S, heat, regr, off)
+    _check_decode(S, heat, regr, off, K=1)
+    _check_decode(S, heat, regr, off, K=128)
+
+
+def test_decode_few_peaks_and_plateaus(S):
+    """Fewer than K peaks -> zero-score fill by ascending index; constant map -> all ties."""
+    yy, xx = torch.meshgrid(torch.arange(128.), torch.arange(128.), indexing="ij")
+    bump = lambda cy, cx, a: a * torch.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / 18.0)
+    h0 = bump(20, 30, 6.0) + bump(90, 100, 4.0) + bump(64, 0, 5.0) + bump(127, 127, 3.0) - 4.0
+    h1 = torch.full((128, 128), -1.25)                     # plateau: every pixel is a peak
+    h2 = torch.full((128, 128), 40.0)                      # saturated sigmoid == 1.0 everywhere
+    h3 = torch.full((128, 128), -200.0)                    # sigmoid underflows to 0: all zeros
+    heat = torch.stack([h0, h1, h2, h3]).unsqueeze(1).contiguous()
+    rng = np.random.default_rng(6)
+    regr = torch.from_numpy(rng.standard_normal((4, 4, 128, 128)).astype(np.float32))
+    off = torch.from_numpy(rng.standard_normal((4, 2, 128, 128)).astype(np.float32))
+    sc, idx = _check_decode(S, heat, regr, off)
+    assert idx[1].tolist() == list(range(100)) and idx[2].tolist() == list(range(100))
+    assert idx[3].tolist() == list(range(100)) and float(sc[3].max()) == 0.0
+    assert (sc[0] > 0).sum() == 4
+
+
+def test_decode_rejects_bad_shapes(S):
+    z = torch.zeros(1, 1, 64, 64, device="cuda")
+    with pytest.raises(S.ScdError):
+        S.ops.decode_topk(z, torch.zeros(1, 4, 64, 64, device="cuda"), torch.zeros(1, 2, 64, 64, device="cuda"))
+    with pytest.raises(S.ScdError):
+        S.ops.decode_topk(torch.zeros(1, 1, 128, 128), torch.zeros(1, 4, 128, 128), torch.zeros(1, 2, 128, 128))
+
+
+# ------------------------------------------------------------------------------ render
+def test_render_targets_golden(S, golden):
+    g = golden("targets")
+    locs, counts = torch.from_numpy(g["locs"]), torch.from_numpy(g["counts"])
+    heat, mask, regr6, idx = [t.cpu() for t in S.ops.render_targets(dev(locs), dev(counts))]
+    assert np.array_equal(mask.numpy(), g["mask"])
+    assert np.array_equal(idx.numpy(), g["idx"])
+    assert np.array_equal(regr6.numpy(), g["regr6"])
+    ref = torch.from_numpy(g["heat"])
+    assert torch.equal(heat == 1, ref == 1)                 # focal positives are exactly the same pixels
+    assert torch.equal(heat == 0, ref == 0)                 # identical windows (radius is bit exact)
+    assert relmax(heat, ref) < 1e-6                         # fp64 exp may differ from numpy's in the last ulp
+    assert (heat != ref).float().mean() < 1e-3
+
+
+def test_render_targets_large_batch(S):
+    locs, counts = O.make_objects(64, seed=9)
+    heat, mask, regr6, idx = [t.cpu() for t in S.ops.render_targets(dev(locs), dev(counts))]
+    eh, em, er, ei = O.render_targets(locs, counts)
+    assert torch.equal(mask, em) and torch.equal(idx, ei) and torch.equal(regr6, er)
+    assert torch.equal(heat == 1, eh == 1) and relmax(heat, eh) < 1e-6
+
+
+# ------------------------------------------------------------------------------ loss
+def _loss_case(S, batch, seed, empty=False):
+    rng = np.random.default_rng(seed)
+    locs, counts = O.make_objects(batch, seed=seed)
+    if empty:
+        counts.zero_()
+    gt = O.render_targets(locs, counts)
+    heat = torch.from_numpy((2.0 * rng.standard_normal((batch, 1, 128, 128)) - 2).astype(np.float32))
+    heat[0, 0, 0, :8] = torch.tensor([-30., 30., -9.3, 9.3, 0., 1e-3, -15., 15.])      # clamp edges
+    regr = torch.from_numpy(rng.standard_normal((batch, 4, 128, 128)).astype(np.float32))
+    off = torch.from_numpy(rng.standard_normal((batch, 2, 128, 128)).astype(np.float32))
+    th, tr, to = [t.clone().requires_grad_(True) for t in (heat, regr, off)]
+    tot, fo, sz, of = O.centernet_loss({"heatmap": th, "regr": tr, "offset": to}, gt)
+    tot.backward()
+    hd = dev(heat)
+    losses, dh, dr, do = S.ops.centernet_loss(hd, dev(regr), dev(off), *[dev(t) for t in gt])
+    exp = torch.stack([tot, fo, sz, of]).detach()
+    assert relmax(losses, exp) < 1e-5, (losses, exp)
+    assert relmax(hd, torch.sigmoid(heat)) < 1e-5            # in-place sigmoid_ side effect (utility.py:121)
+    assert relmax(dh, th.grad) < 1e-5
+    assert relmax(dr, tr.grad) < 1e-5 and relmax(do, to.grad) < 1e-5
+    assert torch.equal(dr.cpu() != 0, tr.grad != 0)
+
+
+def test_centernet_loss(S):
+    _loss_case(S, 4, 21)
+    _loss_case(S, 32, 22)
+
+
+def test_centernet_loss_no_positives(S):
+    _loss_case(S, 2, 23, empty=True)                         # focal.py:47-48 branch, L1 denominators 1e-4
+
+
+def test_centernet_loss_kat(S, golden):
+    g = golden("kat")
+    i = np.arange(2 * 128 * 128, dtype=np.float64)
+    heat = torch.from_numpy((3 * np.sin(0.37 * i) - 2).astype(np.float32)).reshape(2, 1, 128, 128)
+    j4 = np.arange(2 * 4 * 128 * 128, dtype=np.float64)
+    j2 = np.arange(2 * 2 * 128 * 128, dtype=np.float64)
+    regr = torch.from_numpy((0.5 * np.cos(0.11 * j4)).astype(np.float32)).reshape(2, 4, 128, 128)
+    off = torch.from_numpy((2 + 2 * np.sin(0.23 * j2)).astype(np.float32)).reshape(2, 2, 128, 128)
+    losses, _, _, _ = S.ops.centernet_loss(dev(heat), dev(regr), dev(off), dev(torch.from_numpy(g["draw_heat"])),
+                                           dev(torch.from_numpy(g["kat_mask"])), dev(torch.from_numpy(g["kat_gt6"])),
+                                           dev(torch.from_numpy(g["kat_idx"])), with_grad=False)
+    exp = torch.tensor([933.2405395507812, 931.3619995117188, 1.6251022815704346, 0.2534022033214569])
+    assert relmax(losses, exp) < 1e-5
+
+
+# ------------------------------------------------------------------------------ slide front end
+def test_slide_tiles(S, golden):
+    g = golden("slide")
+    rng = np.random.default_rng(int(g["gray_seed"]))
+    h, w = [int(v) for v in g["shape"]]
+    gray = np.round(rng.uniform(0, 255, size=(h, w)))
+    assert list(S.ops.slide_geometry(h, w)) == list(g["geometry"])
+    tiles = S.ops.slide_tiles(dev(torch.from_numpy(gray).float())).cpu()
+    exp = O.slide_tiles(gray)
+    assert tiles.shape == exp.shape
+    assert relmax(tiles, exp) < 1e-6
+    assert (tiles != exp).float().mean() < 1e-3
+    part = S.ops.slide_tiles(dev(torch.from_numpy(gray).float()), 3, 7).cpu()
+    assert torch.equal(part, tiles[3:7])
+    assert np.allclose(tiles[0, 0, ::16, ::16].numpy(), g["tile0_sub"], rtol=1e-6, atol=1e-7)
+
+
+def test_slide_tiles_opencv_fixup_width(S):
+    """Padded width 3200 (3072-wide slide): the reference's hard-coded mirror fix-up (test.py:79-82)."""
+    rng = np.random.default_rng(12)
+    gray = np.round(rng.uniform(0, 255, size=(600, 3072)))
+    assert S.ops.slide_geometry(600, 3072)[3] == 3200
+    tiles = S.ops.slide_tiles(dev(torch.from_numpy(gray).float())).cpu()
+    assert relmax(tiles, O.slide_tiles(gray)) < 1e-6
+
+
+# ------------------------------------------------------------------------------ stem
+def test_stem(S):
+    sd = O.make_state_dict(1234)
+    f = S.weights.fold(sd)
+    x = O.make_tiles(2, seed=3)
+    y = S.ops.stem_fwd(dev(x), dev(f["stem_w"]), dev(f["stem_b"])).float().cpu().permute(0, 3, 1, 2)
+    t = F.conv2d(x, sd["preprocess.0.weight"], None, stride=2, padding=3)
+    t = F.relu(F.batch_norm(t, sd["preprocess.1.running_mean"], sd["preprocess.1.running_var"],
+                            sd["preprocess.1.weight"], sd["preprocess.1.bias"], False, 0.1, 1e-5))
+    t = F.max_pool2d(t, 3, 2, 1)
+    assert y.shape == t.shape
+    assert relmax(y, t) < 1e-2                               # bf16 output: 1e-2 rel (north star)
+    assert ((y - t).abs() <= 0.004 * t.abs() + 1e-3).all()   # per element: bf16 rounding only
+
+
+# ------------------------------------------------------------------------------ implicit GEMM convs
+def _bf16(t):
+    return t.to(torch.bfloat16).float()
+
+
+def _conv_case(S, kind, b, h, w, cin, cout, residual, relu, seed):
+    rng = np.random.default_rng(seed)
+    x = _bf16(torch.from_numpy(rng.standard_normal((b, cin, h, w)).astype(np.float32)))
+    bias = torch.from_numpy(rng.standard_normal(cout).astype(np.float32))
+    if kind == 3:
+        wt = _bf16(torch.from_numpy((rng.standard_normal((cin, cout, 4, 4)) / np.sqrt(4 * cin)).astype(np.float32)))
+        ref = F.conv_transpose2d(x, wt, bias, stride=2, padding=1)
+    else:
+        k = 1 if kind == 2 else 3
+        wt = _bf16(torch.from_numpy((rng.standard_normal((cout, cin, k, k)) / np.sqrt(k * k * cin)).astype(np.float32)))
+        ref = F.conv2d(x, wt, bias, stride=1 if kind == 0 else 2, padding=0 if kind == 2 else 1)
+    res = None
+    if residual:
+        res = _bf16(torch.from_numpy(rng.standard_normal(tuple(ref.shape)).astype(np.float32)))
+        ref = ref + res
+    if relu:
+        ref = F.relu(ref)
+    xg = dev(x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))
+    rg = dev(res.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)) if residual else None
+    y = S.ops.conv_igemm_fwd(kind, xg, dev(S.weights.pack_conv(wt, kind)), dev(bias), rg, relu)
+    torch.cuda.synchronize()
+    y = y.float().cpu().permute(0, 3, 1, 2)
+    assert y.shape == ref.shape
+    err = (y - ref).abs()
+    assert (err <= 0.008 * ref.abs() + 0.02).all(), (kind, err.max().item(), ref.abs().max().item())
+    assert relmax(y, ref) < 1e-2
+
+
+@pytest.mark.parametrize("case", [
+    (0, 2, 128, 128, 64, 64, False, True),      # layer1.conv1
+    (0, 1, 128, 128, 64, 64, True, True),       # layer1.conv2 + residual
+    (0, 2, 64, 64, 128, 128, True, True),       # layer2.conv2
+    (0, 3, 32, 32, 256, 256, True, True),       # layer3.conv2
+    (0, 3, 16, 16, 512, 512, True, True),       # layer4.conv2 (two N tiles)
+    (1, 2, 128, 128, 64, 128, False, True),     # layer2.conv1 (stride 2)
+    (1, 2, 32, 32, 256, 512, False, True),      # layer4.conv1
+    (2, 2, 128, 128, 64, 128, False, False),    # layer2.downsample
+    (2, 2, 32, 32, 256, 512, False, False),     # layer4.downsample
+    (3, 2, 16, 16, 512, 256, False, True),      # deconv 1
+    (3, 1, 64, 64, 256, 256, False, True),      # deconv 3
+])
+def test_conv_igemm(S, case):
+    _conv_case(S, *case, seed=hash(case) % 1000)
+
+
+def test_heads(S):
+    rng = np.random.default_rng(31)
+    sd = O.make_state_dict(1234)
+    f = S.weights.fold(sd)
+    x = _bf16(torch.from_numpy(np.abs(rng.standard_normal((2, 256, 128, 128))).astype(np.float32)))
+    heat, regr, off = S.ops.heads_fwd(dev(x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)),
+                                      dev(f["w3"]), dev(f["b3"]), dev(f["w1"]), dev(f["b1"]))
+    for name, got in (("heatmap", heat), ("regr", regr), ("offset", off)):
+        hmid = F.relu(F.conv2d(x, _bf16(sd[name + ".0.weight"]), sd[name + ".0.bias"], padding=1))
+        ref = F.conv2d(hmid, sd[name + ".2.weight"], sd[name + ".2.bias"])
+        assert relmax(got, ref) < 1e-2, name
+        assert ((got.cpu() - ref).abs() <= 0.01 * ref.abs() + 0.02 * ref.abs().max()).all()
+
+
+# ------------------------------------------------------------------------------ whole network
+def test_infer_vs_oracle(S, golden):
+    """heatmap / regr / offset of the bf16 tensor-core path vs the fp32 oracle: 1e-2 rel (north star)."""
+    sd = O.make_state_dict(1234)
+    x = O.make_tiles(2, seed=0)
+    blob = S.weights.pack_infer_blob(sd, "cuda")
+    heat, regr, off, _ = S.ops.resnet10_infer(dev(x), blob)
+    with torch.no_grad():
+        ref = O.resnet10_forward(sd, x)[0]
+    for name, got in (("heatmap", heat), ("regr", regr), ("offset", off)):
+        r = ref[name]
+        e = (got.cpu() - r).abs()
+        assert e.max() <= 1e-2 * r.abs().max() * 3, (name, e.max().item(), r.abs().max().item())
+        assert (e.double().pow(2).mean().sqrt() / r.double().pow(2).mean().sqrt()) < 1e-2, name
+    g = golden("model_eval")
+    assert relmax(heat[:, :, ::4, ::4], torch.from_numpy(g["heat_sub"])) < 3e-2
