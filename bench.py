@@ -1,0 +1,257 @@
+"""Benchmark of the centerOffsetRes10 hot path (BASELINE.json metric, config[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A step = one pass of the hot path over one batch of 64 synthetic 512x512 tiles on each GPU:
+stem -> 14 tcgen05 implicit-GEMM stages -> fused heads -> decode (17 kernel launches).
+Prints ONE JSON line (rank 0).  `value` = tiles/s over all GPUs with inputs resident in HBM;
+`e2e` = the same through TileDetector.detect_host with pinned HOST tiles (H2D + D2H inside the timed
+region); `roofline` = the dominant kernel (fused heads igemm) against the measured bf16 peak;
+`cpu_baseline` = the CPU oracle (a port of the reference's PyTorch path) on this box's host cores.
+`--impl reference` times that CPU path alone.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "512x512 tiles/sec centerOffsetRes10 infer+decode"
+FLOPS_PER_TILE = 49.2957e9               # SURVEY.md 8a (18 convs + 3 deconvs, deconv without zero insertion)
+HEADS_FLOPS_PER_TILE = 2.0 * 16384 * (384 * 2304 + 7 * 128)
+WORKLOAD = "configs[1]: centerOffsetRes10 batched inference+decode, batch 64 of 512x512 tiles per GPU, bf16"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_oracle_rate(tiles_per_iter, min_seconds, warmup=1, max_iters=1000, fixed_iters=None):
+    """tiles/s of the CPU oracle (reference port: ATen fp32 on host cores) for infer + decode."""
+    import torch
+    from oracle import centernet_cpu as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = O.make_state_dict(1234)
+    x = O.make_tiles(tiles_per_iter, seed=0)
+
+    def step():
+        with torch.no_grad():
+            out = O.resnet10_forward(sd, x)[0]
+            O.decode_centernet(out, K=100)
+
+    for _ in range(warmup):
+        step()
+    times = []
+    t0 = time.perf_counter()
+    while True:
+        t1 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t1)
+        if fixed_iters is not None:
+            if len(times) >= fixed_iters:
+                break
+        elif time.perf_counter() - t0 >= min_seconds or len(times) >= max_iters:
+            break
+    total = sum(times)
+    return tiles_per_iter * len(times) / total, total / len(times), len(times), torch.get_num_threads()
+
+
+def run_reference(args, rank):
+    """The reference arm: the reference's own CPU implementation of the path.  The reference is pure
+    Python/PyTorch (nothing to compile), and /root/reference does not exist on the GPU box, so this runs
+    the oracle port (oracle/centernet_cpu.py, pinned to the reference by tests/golden) on all host cores."""
+    if rank != 0:
+        return
+    sample = 8
+    rate, sec_per_iter, iters, cores = cpu_oracle_rate(sample, 0, warmup=max(1, min(args.warmup, 2)),
+                                                       fixed_iters=args.steps)
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "tiles/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_iter * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": "%d tiles per step on the host CPU" % sample},
+            "cpu_baseline": {"value": rate, "unit": "tiles/s", "cores": cores, "kind": "port",
+                             "sample": "%d steps x %d tiles, infer+decode, fp32 ATen on %d threads"
+                                       % (iters, sample, cores)},
+            "e2e": {"value": rate, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="tiles per GPU per step (config[1] = 64)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    import scd_resnet_b200 as S           # raises if libscd_b200.so is missing: no fallback
+    from scd_resnet_b200 import synthetic
+    from scd_resnet_b200.centerNetOffset import CenterNetResidual
+    from scd_resnet_b200.inference import TileDetector
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B, K, W = args.batch, args.steps, args.warmup
+    model = CenterNetResidual(10)
+    model.load_state_dict(synthetic.make_state_dict(model, 1234))
+    model.eval()
+    det = TileDetector(model, B, dev)
+    # three rotating input batches (3 x 64 MB) and 1.4 GB of activations: far beyond the 126 MB L2
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    xs = [torch.randn(B, 1, 512, 512, device=dev, generator=g) for _ in range(3)]
+
+    # ---- device-resident throughput --------------------------------------------------------------
+    for i in range(W):
+        det.detect_device(xs[i % 3])
+    stage_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(17)] for _ in range(K)]
+    dec_ev = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    for evs in stage_ev:
+        for e in evs:
+            e.record()                    # materialise the cudaEvent_t handles
+    for e in dec_ev:
+        e.record()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    barrier()
+    t_start.record()
+    for i in range(K):
+        det.detect_device(xs[i % 3], stage_ev[i])
+        dec_ev[i].record()
+    t_end.record()
+    barrier()
+    ms = t_start.elapsed_time(t_end)
+    clk = clocks.stop() if rank == 0 else None
+    stage_ms = [statistics.mean(stage_ev[i][j].elapsed_time(stage_ev[i][j + 1]) for i in range(K)) for j in range(16)]
+    decode_ms = statistics.mean(stage_ev[i][16].elapsed_time(dec_ev[i]) for i in range(K))
+
+    # ---- end to end: pinned host tiles in, host detections out ---------------------------------------
+    host = [torch.randn(B, 1, 512, 512).pin_memory() for _ in range(3)]
+    det.detect_host([host[i % 3] for i in range(3)])
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = det.detect_host([host[i % 3] for i in range(K)])
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e2e_ms, e2e_wall_ms) if world == 1 else e2e_ms
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = t.tolist()
+
+    if rank == 0:
+        peaks = measured_peaks()
+        heads_ms = stage_ms[15]
+        ach = HEADS_FLOPS_PER_TILE * B / (heads_ms * 1e-3) / 1e12
+        names = ["stem", "l1c1", "l1c2", "l2ds", "l2c1", "l2c2", "l3ds", "l3c1", "l3c2", "l4ds", "l4c1", "l4c2",
+                 "dc1", "dc2", "dc3", "heads"]
+        line = {
+            "metric": METRIC, "value": world * B * K / (ms * 1e-3), "unit": "tiles/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "tile": 512, "K": 100,
+                       "weights": "synthetic He-init, BN folded (seed 1234)",
+                       "l2": "3 rotating input batches (3x64 MB) + 1.4 GB activations per step > 126 MB L2"},
+            "e2e": {"value": world * B * K / (e2e_ms * 1e-3), "unit": "tiles/s",
+                    "h2d_bytes_per_step": B * 512 * 512 * 4, "d2h_bytes_per_step": 10 * B * 100 * 4,
+                    "api": "TileDetector.detect_host (pinned host tiles -> host detections, copies overlapped)"},
+            "gpu_launches": 17 * K,
+            "roofline": {"kernel": "igemm_kernel<384, EPI_HEADS> (fused heads)", "bound": "tensor",
+                         "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                         "peak_source": peaks["source"] + " sustained bf16 (kernel timed inside a long step)",
+                         "ms_per_launch": heads_ms},
+            "step_tflops": FLOPS_PER_TILE * B / (ms / K * 1e-3) / 1e12,
+            "stage_ms": {n: round(v, 4) for n, v in zip(names, stage_ms)}, "decode_ms": round(decode_ms, 4),
+            "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rate, spi, iters, cores = cpu_oracle_rate(8, 10.0)
+            line["cpu_baseline"] = {"value": rate, "unit": "tiles/s", "cores": cores, "kind": "port",
+                                    "sample": "%d iterations x 8 tiles, infer+decode, fp32 ATen on %d threads"
+                                              % (iters, cores)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -134,19 +134,27 @@ int scd_heads_fwd(const void* x, const void* w3, const float* b3, const float* w
  * ResNet.forward (residuals.py:312-334) with decode=False, as one native call that
  * chains the kernels above on `stream`.
  *
- * `weights` is the packed, BN-folded parameter blob built by the host side
- * (layout: scd_infer_weights_layout), `workspace` holds the NHWC activations.
+ * `weights` is the packed, BN-folded parameter blob built by the host side, `workspace`
+ * holds the NHWC bf16 activations.  Blob entries (byte offsets / sizes from
+ * scd_infer_weights_layout, each 256-byte aligned):
+ *   0 stem w f32 (64,49) | 1 stem b f32 (64) |
+ *   2+2i, 3+2i : weight bf16 / bias f32 of igemm stage i, in the order
+ *                l1c1 l1c2 l2ds l2c1 l2c2 l3ds l3c1 l3c2 l4ds l4c1 l4c2 dc1 dc2 dc3 |
+ *   30 heads w3 bf16 (384,2304) | 31 b3 f32 (384) | 32 w1 f32 (7,128) | 33 b1 f32 (7)
+ *
+ * `h_stage_events` (nullable) is a HOST array of 17 cudaEvent_t recorded on `stream`
+ * before the stem, after the stem, after each of the 14 igemm stages and after the heads,
+ * so that a caller can time every kernel of a step without a profiler.
  * ---------------------------------------------------------------------------------- */
-/* blob entries: 0 stem w f32 (64,49) | 1 stem b f32 (64) | 2+2i, 3+2i: weight bf16 / bias f32 of
- * igemm stage i in the order l1c1 l1c2 l2ds l2c1 l2c2 l3ds l3c1 l3c2 l4ds l4c1 l4c2 dc1 dc2 dc3 |
- * 30 heads w3 bf16 (384,2304) | 31 b3 f32 (384) | 32 w1 f32 (7,128) | 33 b1 f32 (7) */
 #define SCD_INFER_WEIGHT_ENTRIES 34
+#define SCD_INFER_STAGE_EVENTS 17
 size_t scd_infer_weights_bytes(void);
 int    scd_infer_weights_layout(size_t* h_offsets, size_t* h_sizes, int n);   /* host arrays, n = 34 */
 size_t scd_infer_workspace_bytes(int batch, int height, int width);
 int scd_resnet10_infer(const float* x, const void* weights, int batch, int height, int width,
                        float* heat, float* regr, float* offset,
-                       void* workspace, size_t workspace_bytes, void* stream);
+                       void* workspace, size_t workspace_bytes, void* const* h_stage_events,
+                       void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Slide front-end: per-tile normalisation.  Replaces normalize

@@ -25,7 +25,8 @@ PROTOTYPES = {
     "scd_infer_weights_bytes": (c_size_t, []),
     "scd_infer_weights_layout": (c_int, [c_void_p, c_void_p, c_int]),
     "scd_infer_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "scd_resnet10_infer": (c_int, [c_void_p, c_void_p] + [c_int] * 3 + [c_void_p] * 3 + [c_void_p, c_size_t, c_void_p]),
+    "scd_resnet10_infer": (c_int, [c_void_p, c_void_p] + [c_int] * 3 + [c_void_p] * 3
+                           + [c_void_p, c_size_t, c_void_p, c_void_p]),
     "scd_slide_geometry": (c_int, [c_int, c_int, c_void_p]),
     "scd_slide_tiles": (c_int, [c_void_p] + [c_int] * 4 + [c_void_p, c_void_p]),
 }

@@ -69,7 +69,8 @@ extern "C" size_t scd_infer_workspace_bytes(int batch, int height, int width)
 
 extern "C" int scd_resnet10_infer(const float* x, const void* weights, int batch, int height, int width,
                                   float* heat, float* regr, float* offset,
-                                  void* workspace, size_t workspace_bytes, void* stream)
+                                  void* workspace, size_t workspace_bytes, void* const* h_stage_events,
+                                  void* stream)
 {
     using namespace scd;
     if (batch <= 0) return SCD_OK;
@@ -97,8 +98,15 @@ extern "C" int scd_resnet10_infer(const float* x, const void* weights, int batch
     void *d4 = take(512 * px / 64), *b4 = take(512 * px / 64), *c4 = take(512 * px / 64);
     void *e1 = take(256 * px / 16), *e2 = take(256 * px / 4), *e3 = take(256 * px);
 
-    int rc = scd_stem_fwd(x, Bf(0), Bf(1), batch, height, width, a0, stream);
+    auto mark = [&](int i) -> int {
+        if (h_stage_events) SCD_CUDA_CHECK(cudaEventRecord((cudaEvent_t)h_stage_events[i], (cudaStream_t)stream));
+        return SCD_OK;
+    };
+    int rc = mark(0);
     if (rc) return rc;
+    rc = scd_stem_fwd(x, Bf(0), Bf(1), batch, height, width, a0, stream);
+    if (rc) return rc;
+    if ((rc = mark(1))) return rc;
     struct Step { int conv; const void* in; const void* res; void* out; int hin, win; };
     const Step steps[14] = {
         {0, a0, nullptr, a1, h1, w1},         {1, a1, a0, a2, h1, w1},
@@ -113,6 +121,9 @@ extern "C" int scd_resnet10_infer(const float* x, const void* weights, int batch
         rc = scd_conv_igemm_fwd(c.kind, s.in, W(2 + 2 * s.conv), Bf(3 + 2 * s.conv), s.res, c.relu, batch, s.hin,
                                 s.win, c.cin, c.cout, s.out, stream);
         if (rc) return rc;
+        if ((rc = mark(2 + i))) return rc;
     }
-    return scd_heads_fwd(e3, W(30), Bf(31), Bf(32), Bf(33), batch, h1, w1, heat, regr, offset, stream);
+    rc = scd_heads_fwd(e3, W(30), Bf(31), Bf(32), Bf(33), batch, h1, w1, heat, regr, offset, stream);
+    if (rc) return rc;
+    return mark(16);
 }

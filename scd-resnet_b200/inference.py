@@ -1,0 +1,72 @@
+"""Batched tile inference + decode, the path BASELINE config 2 measures (test.py:95-112 per batch).
+
+TileDetector keeps the packed weights, the activation workspace and the output buffers resident, and
+runs   H2D copy -> scd_resnet10_infer -> scd_decode_topk -> D2H copy   with the copies on a side stream so
+that the transfer of batch i+1 overlaps the kernels of batch i.
+"""
+import torch
+
+from . import ops, weights
+
+
+class TileDetector:
+    """model: a CenterNetResidual in eval mode (or a state_dict).  batch: tiles per launch."""
+
+    def __init__(self, model_or_sd, batch, device=None, K=100, height=512, width=512):
+        sd = model_or_sd.state_dict() if hasattr(model_or_sd, "state_dict") else model_or_sd
+        sd = {k.replace("module.", "", 1) if k.startswith("module.") else k: v for k, v in sd.items()}
+        self.device = torch.device(device if device is not None else "cuda")
+        self.batch, self.K, self.h, self.w = batch, K, height, width
+        with torch.cuda.device(self.device):
+            self.blob = weights.pack_infer_blob(sd, self.device)
+            self.workspace = torch.empty(ops.lib.scd_infer_workspace_bytes(batch, height, width), dtype=torch.uint8,
+                                         device=self.device)
+            hw = (height // 4, width // 4)
+            self.maps = (torch.empty(batch, 1, *hw, device=self.device), torch.empty(batch, 4, *hw, device=self.device),
+                         torch.empty(batch, 2, *hw, device=self.device))
+            self.copy_stream = torch.cuda.Stream(self.device)
+            self.compute_stream = torch.cuda.Stream(self.device)
+            self.dev_in = [torch.empty(batch, 1, height, width, device=self.device) for _ in range(2)]
+            self.in_ready = [torch.cuda.Event() for _ in range(2)]
+            self.in_free = [torch.cuda.Event() for _ in range(2)]
+            self.out_ready = [torch.cuda.Event() for _ in range(2)]
+            self._host_ring = None
+        self.launches_per_batch = 17      # stem + 14 igemm + heads + decode
+
+    def detect_device(self, x, stage_events=None):
+        """x (B,1,H,W) f32 on the device -> (10,B,K) f32 planes on the device (current stream)."""
+        b = x.shape[0]
+        heat, regr, off = [m[:b] for m in self.maps]
+        ops.resnet10_infer(x, self.blob, self.workspace, (heat, regr, off), stage_events)
+        return ops.decode_topk(heat, regr, off, K=self.K, planes=True)[6]
+
+    def detect_host(self, host_batches):
+        """host_batches: list of pinned (B,1,H,W) f32 host tensors.  Returns a list of (10,B,K) host tensors.
+
+        Copies run on copy_stream, kernels on compute_stream, two buffers each way."""
+        n = len(host_batches)
+        if self._host_ring is None or self._host_ring.shape[0] < n:
+            self._host_ring = torch.empty(n, 10, self.batch, self.K, pin_memory=True)
+        results = []
+        with torch.cuda.device(self.device):
+            for i, hb in enumerate(host_batches):
+                s = i & 1
+                b = hb.shape[0]
+                with torch.cuda.stream(self.copy_stream):
+                    if i >= 2:
+                        self.copy_stream.wait_event(self.in_free[s])      # batch i-2 has consumed this buffer
+                    self.dev_in[s][:b].copy_(hb, non_blocking=True)
+                    self.in_ready[s].record(self.copy_stream)
+                with torch.cuda.stream(self.compute_stream):
+                    self.compute_stream.wait_event(self.in_ready[s])
+                    planes = self.detect_device(self.dev_in[s][:b])
+                    self.in_free[s].record(self.compute_stream)
+                    self.out_ready[s].record(self.compute_stream)
+                with torch.cuda.stream(self.copy_stream):
+                    self.copy_stream.wait_event(self.out_ready[s])
+                    out = self._host_ring[i, :, :b]
+                    out.copy_(planes, non_blocking=True)
+                    planes.record_stream(self.copy_stream)
+                    results.append(out)
+            self.copy_stream.synchronize()
+        return results

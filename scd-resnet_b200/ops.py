@@ -171,7 +171,7 @@ def infer_weights_layout():
     return list(offs), list(sizes), lib.scd_infer_weights_bytes()
 
 
-def resnet10_infer(x, blob, workspace=None, out=None):
+def resnet10_infer(x, blob, workspace=None, out=None, stage_events=None):
     """ResNet.forward, eval, decode=False (ref: models/backbones/residuals.py:312-334) as one native call.
 
     x (B,1,H,W) f32; blob = packed BN-folded weights (weights.pack_infer_blob).  Returns heat, regr, offset
@@ -188,9 +188,14 @@ def resnet10_infer(x, blob, workspace=None, out=None):
                torch.empty(b, 4, h // 4, w // 4, dtype=torch.float32, device=dev),
                torch.empty(b, 2, h // 4, w // 4, dtype=torch.float32, device=dev))
     heat, regr, off = out
+    ev = None
+    if stage_events is not None:       # 17 torch.cuda.Event(enable_timing=True), each recorded once before
+        if len(stage_events) != 17:
+            raise ScdError("stage_events must hold 17 events")
+        ev = (ctypes.c_void_p * 17)(*[e.cuda_event for e in stage_events])
     with torch.cuda.device(dev):
         check(lib.scd_resnet10_infer(_ptr(x), _ptr(blob), b, h, w, _ptr(heat), _ptr(regr), _ptr(off),
-                                     _ptr(workspace), workspace.numel(), _stream()), "scd_resnet10_infer")
+                                     _ptr(workspace), workspace.numel(), ev, _stream()), "scd_resnet10_infer")
     return heat, regr, off, workspace
 
 

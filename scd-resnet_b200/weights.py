@@ -65,10 +65,10 @@ def fold(sd):
         s, b = bn_scale_shift(sd, bk)
         out["w%d" % i] = pack_conv(sd[ck + ".weight"], kind, s)
         out["b%d" % i] = b.contiguous()
-    out["w3"] = torch.cat([pack_conv(sd[h + ".0.weight"], 0) for h in HEADS], 0).contiguous()
-    out["b3"] = torch.cat([sd[h + ".0.bias"].float() for h in HEADS], 0).contiguous()
-    out["w1"] = torch.cat([sd[h + ".2.weight"].float().reshape(-1, 128) for h in HEADS], 0).contiguous()
-    out["b1"] = torch.cat([sd[h + ".2.bias"].float() for h in HEADS], 0).contiguous()
+    out["head_w3"] = torch.cat([pack_conv(sd[h + ".0.weight"], 0) for h in HEADS], 0).contiguous()
+    out["head_b3"] = torch.cat([sd[h + ".0.bias"].float() for h in HEADS], 0).contiguous()
+    out["head_w1"] = torch.cat([sd[h + ".2.weight"].float().reshape(-1, 128) for h in HEADS], 0).contiguous()
+    out["head_b1"] = torch.cat([sd[h + ".2.bias"].float() for h in HEADS], 0).contiguous()
     return out
 
 
@@ -79,7 +79,7 @@ def pack_infer_blob(sd, device):
     entries = [f["stem_w"], f["stem_b"]]
     for i in range(len(STAGES)):
         entries += [f["w%d" % i], f["b%d" % i]]
-    entries += [f["w3"], f["b3"], f["w1"], f["b1"]]
+    entries += [f["head_w3"], f["head_b3"], f["head_w1"], f["head_b1"]]
     blob = torch.zeros(total, dtype=torch.uint8, device=device)
     for e, o, n in zip(entries, offs, sizes):
         raw = e.contiguous().view(torch.uint8).reshape(-1)

@@ -73,18 +73,20 @@ def test_decode_few_peaks_and_plateaus(S):
     """Fewer than K peaks -> zero-score fill by ascending index; constant map -> all ties."""
     yy, xx = torch.meshgrid(torch.arange(128.), torch.arange(128.), indexing="ij")
     bump = lambda cy, cx, a: a * torch.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / 18.0)
-    h0 = bump(20, 30, 6.0) + bump(90, 100, 4.0) + bump(64, 0, 5.0) + bump(127, 127, 3.0) - 4.0
+    ramp = 1e-3 * (xx + 1.5 * yy) - 4.0                    # strictly increasing: one peak, bottom right
+    h0 = bump(20, 30, 6.0) + bump(90, 100, 4.0) + bump(64, 0, 5.0) + ramp
     h1 = torch.full((128, 128), -1.25)                     # plateau: every pixel is a peak
     h2 = torch.full((128, 128), 40.0)                      # saturated sigmoid == 1.0 everywhere
     h3 = torch.full((128, 128), -200.0)                    # sigmoid underflows to 0: all zeros
-    heat = torch.stack([h0, h1, h2, h3]).unsqueeze(1).contiguous()
+    heat = torch.stack([h0, h1, h2, h3, ramp]).unsqueeze(1).contiguous()
     rng = np.random.default_rng(6)
-    regr = torch.from_numpy(rng.standard_normal((4, 4, 128, 128)).astype(np.float32))
-    off = torch.from_numpy(rng.standard_normal((4, 2, 128, 128)).astype(np.float32))
+    regr = torch.from_numpy(rng.standard_normal((5, 4, 128, 128)).astype(np.float32))
+    off = torch.from_numpy(rng.standard_normal((5, 2, 128, 128)).astype(np.float32))
     sc, idx = _check_decode(S, heat, regr, off)
     assert idx[1].tolist() == list(range(100)) and idx[2].tolist() == list(range(100))
     assert idx[3].tolist() == list(range(100)) and float(sc[3].max()) == 0.0
-    assert (sc[0] > 0).sum() == 4
+    assert (sc[0] > 0).sum() == 4 and idx[0, :3].tolist() == [20 * 128 + 30, 64 * 128, 90 * 128 + 100]
+    assert idx[4].tolist() == [128 * 128 - 1] + list(range(99)) and (sc[4] > 0).sum() == 1
 
 
 def test_decode_rejects_bad_shapes(S):
@@ -263,7 +265,7 @@ def test_heads(S):
     f = S.weights.fold(sd)
     x = _bf16(torch.from_numpy(np.abs(rng.standard_normal((2, 256, 128, 128))).astype(np.float32)))
     heat, regr, off = S.ops.heads_fwd(dev(x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)),
-                                      dev(f["w3"]), dev(f["b3"]), dev(f["w1"]), dev(f["b1"]))
+                                      dev(f["head_w3"]), dev(f["head_b3"]), dev(f["head_w1"]), dev(f["head_b1"]))
     for name, got in (("heatmap", heat), ("regr", regr), ("offset", off)):
         hmid = F.relu(F.conv2d(x, _bf16(sd[name + ".0.weight"]), sd[name + ".0.bias"], padding=1))
         ref = F.conv2d(hmid, sd[name + ".2.weight"], sd[name + ".2.bias"])
