@@ -92,10 +92,12 @@ int scd_centernet_loss(const float* heat, float* prob_out, const float* regr, co
 
 /* ------------------------------------------------------------------------------------
  * Stem.  Replaces ResNet.preprocess (models/backbones/residuals.py:210-215):
- * Conv2d 1->64 7x7 s2 p3 (BN folded: weight (64,49) f32, bias (64) f32) -> ReLU
- * -> MaxPool 3x3 s2 p1.   x (B,1,H,W) f32 NCHW -> y (B,H/4,W/4,64) bf16 NHWC.
+ * Conv2d 1->64 7x7 s2 p3 (BN folded) -> ReLU -> MaxPool 3x3 s2 p1, as a 4x4 conv over the
+ * 2x2 space-to-depth image on tcgen05 (K = 64).  weight (64,64) bf16, K-major,
+ * k = (dy*4+dx)*4 + py*2+px  <->  (ky,kx) = (2dy+py-1, 2dx+px-1), zero where ky or kx is -1;
+ * bias (64) f32.   x (B,1,H,W) f32 NCHW -> y (B,H/4,W/4,64) bf16 NHWC.
  * ---------------------------------------------------------------------------------- */
-int scd_stem_fwd(const float* x, const float* weight, const float* bias, int batch,
+int scd_stem_fwd(const float* x, const void* weight, const float* bias, int batch,
                  int height, int width, void* y, void* stream);
 
 /* ------------------------------------------------------------------------------------
@@ -137,7 +139,7 @@ int scd_heads_fwd(const void* x, const void* w3, const float* b3, const float* w
  * `weights` is the packed, BN-folded parameter blob built by the host side, `workspace`
  * holds the NHWC bf16 activations.  Blob entries (byte offsets / sizes from
  * scd_infer_weights_layout, each 256-byte aligned):
- *   0 stem w f32 (64,49) | 1 stem b f32 (64) |
+ *   0 stem w bf16 (64,64) | 1 stem b f32 (64) |
  *   2+2i, 3+2i : weight bf16 / bias f32 of igemm stage i, in the order
  *                l1c1 l1c2 l2ds l2c1 l2c2 l3ds l3c1 l3c2 l4ds l4c1 l4c2 dc1 dc2 dc3 |
  *   30 heads w3 bf16 (384,2304) | 31 b3 f32 (384) | 32 w1 f32 (7,128) | 33 b1 f32 (7)

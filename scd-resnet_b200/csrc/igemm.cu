@@ -328,6 +328,11 @@ static int make_w_map(CUtensorMap* m, const void* base, int k_total, int rows, i
     return SCD_OK;
 }
 
+int make_w_map_2d(CUtensorMap* m, const void* base, int k_total, int rows, int box_rows)
+{
+    return make_w_map(m, base, k_total, rows, box_rows);
+}
+
 template <int BN, int EPI>
 static int launch_igemm(const IgemmParams& p, cudaStream_t st)
 {

@@ -16,13 +16,13 @@ static const ConvSpec kConvs[14] = {
 };
 static int conv_taps(int kind) { return kind == 2 ? 1 : (kind == 3 ? 16 : 9); }
 
-// blob entries: 0 stem_w f32 (64,49) | 1 stem_b f32 (64) | 2+2i conv_i w bf16 | 3+2i conv_i b f32 |
+// blob entries: 0 stem_w bf16 (64,64) | 1 stem_b f32 (64) | 2+2i conv_i w bf16 | 3+2i conv_i b f32 |
 //               30 heads w3 bf16 (384, 2304) | 31 b3 f32 (384) | 32 w1 f32 (7,128) | 33 b1 f32 (7)
 constexpr int kNumEntries = 34;
 static void weights_layout(size_t* off, size_t* size)
 {
     size_t sz[kNumEntries];
-    sz[0] = 64 * 49 * 4; sz[1] = 64 * 4;
+    sz[0] = 64 * 64 * 2; sz[1] = 64 * 4;
     for (int i = 0; i < 14; ++i) {
         sz[2 + 2 * i] = (size_t)kConvs[i].cout * conv_taps(kConvs[i].kind) * kConvs[i].cin * 2;
         sz[3 + 2 * i] = (size_t)kConvs[i].cout * 4;
@@ -104,7 +104,7 @@ extern "C" int scd_resnet10_infer(const float* x, const void* weights, int batch
     };
     int rc = mark(0);
     if (rc) return rc;
-    rc = scd_stem_fwd(x, Bf(0), Bf(1), batch, height, width, a0, stream);
+    rc = scd_stem_fwd(x, W(0), Bf(1), batch, height, width, a0, stream);
     if (rc) return rc;
     if ((rc = mark(1))) return rc;
     struct Step { int conv; const void* in; const void* res; void* out; int hin, win; };

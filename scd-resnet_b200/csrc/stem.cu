@@ -1,164 +1,208 @@
-// Stem: Conv2d 1->64 7x7 s2 p3 (BN folded) -> ReLU -> MaxPool 3x3 s2 p1, fused.
+// Stem: Conv2d 1->64 7x7 s2 p3 (BN folded) -> ReLU -> MaxPool 3x3 s2 p1, fused, on tensor cores.
 //
 // Replaces ResNet.preprocess (ref: models/backbones/residuals.py:210-215).  The 64x256x256
 // conv output (the largest activation of the net, 16.8 MB fp32 per tile in the reference)
-// never reaches HBM: a CTA computes the (2*8+1) x (2*16+1) conv outputs under an 8x16 pool
-// tile into shared memory and writes only the pooled 64x128x128 map, NHWC bf16.
+// never reaches HBM: a CTA computes the 17x17 conv outputs under an 8x8 pool tile and writes
+// only the pooled 64x128x128 map, NHWC bf16.
 //
-// K = 49 with a single input channel is tensor-core-hostile, so this stage runs on the FP32
-// pipes: a thread owns 4 neighbouring conv outputs x 16 channels (64 accumulators), weights
-// come from shared memory as broadcast LDS.128.
-#include "common.cuh"
+// The 7x7 stride-2 conv on one channel is rewritten as a 4x4 stride-1 conv on the 2x2
+// space-to-depth image (4 "parity" channels): K = 4*4*4 = 64 exactly, 15 of the 64 weights
+// are structural zeros.  In that layout the 8 K-values of a 16-byte operand chunk are two
+// neighbouring s2d pixels, contiguous in the staged input patch, so the im2col A tile is
+// built in shared memory with 2 x LDS.64 + 1 x STS.128 per chunk (128-byte swizzle applied by
+// hand), and 289 conv outputs x 64 channels take 12 tcgen05.mma (M=128, N=64, K=16) into TMEM.
+// The CUDA-core version of this stage cost 1.34 ms per 64-tile batch (32 % of the step).
+#include "tc.cuh"
 
 namespace scd {
 
-constexpr int ST_PH = 8, ST_PW = 16;                 // pool tile
-constexpr int ST_CH = 2 * ST_PH + 1;                 // 17 conv rows
-constexpr int ST_CW = 2 * ST_PW + 1;                 // 33 conv cols
-constexpr int ST_XG = (ST_CW + 3) / 4;               // 9 groups of 4 conv cols
-constexpr int ST_IH = 2 * ST_CH + 5;                 // 39 input rows
-constexpr int ST_IW = 80;                            // 2*33+5 = 71 used, padded so 8*xg+12 stays inside
+constexpr int ST_P = 8;                      // pool tile 8x8
+constexpr int ST_C = 2 * ST_P + 1;           // 17x17 conv outputs under it
+constexpr int ST_NPOS = ST_C * ST_C;         // 289
+constexpr int ST_MT = 3;                     // M tiles of 128 rows
+constexpr int ST_PS = ST_C + 3;              // 20x20 s2d pixels of input under the conv tile
 constexpr int ST_THREADS = 256;
 constexpr int ST_CO = 64;
+constexpr int ST_TMEM_COLS = 256;            // 3 x 64 accumulator columns, power of two
 
-struct StemSmem {
-    float patch[ST_IH][ST_IW];
-    float w[49][ST_CO];
-    float bias[ST_CO];
-    __nv_bfloat16 conv[ST_CH * ST_XG * 4][ST_CO];    // (row, col) -> 64 channels, post bias+ReLU
-};
+// shared memory map (byte offsets from a 1024-aligned base)
+constexpr int ST_OFF_A = 0;                                   // 3 x 16 KB im2col tiles; later the conv tile
+constexpr int ST_OFF_B = ST_MT * 16384;                       // 8 KB weights (64 x 64 bf16, swizzled by TMA)
+constexpr int ST_OFF_PATCH = ST_OFF_B + 8192;                 // 20 x 20 x 4 bf16
+constexpr int ST_OFF_BAR = ST_OFF_PATCH + ST_PS * ST_PS * 8 + 64;   // +64: chunk reads run 8 B past the end
+constexpr int ST_SMEM = ST_OFF_BAR + 64 + 1024;
 
 __global__ void __launch_bounds__(ST_THREADS, 2)
-stem_kernel(const float* __restrict__ x, const float* __restrict__ weight, const float* __restrict__ bias,
-            int height, int width, __nv_bfloat16* __restrict__ y)
+stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ x,
+               const float* __restrict__ bias, int height, int width, __nv_bfloat16* __restrict__ y)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    StemSmem& s = *reinterpret_cast<StemSmem*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int hc = height / 2, wc = width / 2;       // conv output size
-    const int hp = height / 4, wp = width / 4;       // pooled output size
-    const int tiles_x = wp / ST_PW;
-    const int b = blockIdx.y;
-    const int py0 = (blockIdx.x / tiles_x) * ST_PH, px0 = (blockIdx.x % tiles_x) * ST_PW;
-    const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;  // first conv row/col under the pool tile
-    const int iy0 = 2 * cy0 - 3, ix0 = 2 * cx0 - 3;  // first input row/col under that
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t sbase = (tc::smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* sgen = smem_dyn + (sbase - tc::smem_u32(smem_dyn));
+    const uint32_t bar_w = sbase + ST_OFF_BAR, bar_mma = bar_w + 8, tmem_slot = bar_w + 16;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    for (int i = tid; i < 49 * ST_CO; i += ST_THREADS) {
-        // weight arrives as (64, 49); shared copy is (49, 64) so 16 channels of a tap are contiguous
-        const int c = i / 49, t = i % 49;
-        s.w[t][c] = weight[i];
+    const int hp = height / 4, wp = width / 4, hc = height / 2, wc = width / 2;
+    const int tiles_x = wp / ST_P;
+    const int b = blockIdx.y;
+    const int py0 = (blockIdx.x / tiles_x) * ST_P, px0 = (blockIdx.x % tiles_x) * ST_P;
+    const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;      // first conv row / col under the pool tile
+    const int Y0 = cy0 - 2, X0 = cx0 - 2;                // first s2d row / col under that (iy = 2Y + py)
+
+    if (tid == 0) {
+        tc::mbar_init(bar_w, 1);
+        tc::mbar_init(bar_mma, 1);
+        tc::fence_barrier_init();
+        tc::mbar_arrive_expect_tx(bar_w, 8192);
+        tc::tma_load_2d(&tmW, bar_w, sbase + ST_OFF_B, 0, 0);
     }
-    if (tid < ST_CO) s.bias[tid] = bias[tid];
-    const float* xb = x + (size_t)b * height * width;
-    for (int i = tid; i < ST_IH * ST_IW; i += ST_THREADS) {
-        const int r = i / ST_IW, c = i % ST_IW;
-        const int iy = iy0 + r, ix = ix0 + c;
-        float v = 0.f;                               // zero padding (p3) and the unused pad columns
-        if (iy >= 0 && iy < height && ix >= 0 && ix < width) v = xb[(size_t)iy * width + ix];
-        s.patch[r][c] = v;
+    if (warp == 1) tc::tmem_alloc<ST_TMEM_COLS>(tmem_slot);
+
+    // ---- stage the input patch as s2d bf16: patch[Y][X][py][px] -------------------------------
+    {
+        const float* xb = x + (size_t)b * height * width;
+        uint32_t* patch = reinterpret_cast<uint32_t*>(sgen + ST_OFF_PATCH);
+        for (int i = tid; i < 2 * ST_PS * ST_PS; i += ST_THREADS) {      // one (iy, X) pixel pair each
+            const int X = i % ST_PS, ry = i / ST_PS;                      // ry = 2*Ylocal + py
+            const int iy = 2 * Y0 + ry, ix = 2 * (X0 + X);
+            float2 v = make_float2(0.f, 0.f);                             // conv zero padding
+            if (iy >= 0 && iy < height && ix >= 0 && ix < width)
+                v = *reinterpret_cast<const float2*>(xb + (size_t)iy * width + ix);
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+            patch[((ry >> 1) * ST_PS + X) * 2 + (ry & 1)] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        if (tid < 16) patch[ST_PS * ST_PS * 2 + tid] = 0u;               // slack read by the last chunk
     }
     __syncthreads();
 
-    // ---- conv + bias + ReLU into shared memory -------------------------------------------
-    for (int item = tid; item < ST_CH * ST_XG * 4; item += ST_THREADS) {
-        const int cg = item & 3;                     // 16-channel group
-        const int g = item >> 2;
-        const int xg = g % ST_XG, row = g / ST_XG;
-        float acc[4][16];
+    // ---- im2col: A[row][k], k = (dy*4 + dx)*4 + py*2 + px, 128 B rows, 128-byte swizzle --------
+    {
+        const unsigned char* patch = sgen + ST_OFF_PATCH;
+        for (int it = tid; it < ST_MT * 128 * 8; it += ST_THREADS) {
+            const int j = it & 7, row = it >> 3;
+            const int pos = row < ST_NPOS ? row : ST_NPOS - 1;           // padded rows: any in-bounds source
+            const int r = pos / ST_C, c = pos % ST_C;
+            const int dy = j >> 1, dx0 = (j & 1) * 2;
+            const unsigned char* src = patch + ((r + dy) * ST_PS + c + dx0) * 8;
+            const uint2 lo = *reinterpret_cast<const uint2*>(src);
+            const uint2 hi = *reinterpret_cast<const uint2*>(src + 8);
+            uint4 v = make_uint4(lo.x, lo.y, hi.x, hi.y);
+            *reinterpret_cast<uint4*>(sgen + ST_OFF_A + row * 128 + ((j ^ (row & 7)) << 4)) = v;
+        }
+    }
+    // generic-proxy writes above must be visible to the tensor core (async proxy)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<const uint32_t*>(sgen + ST_OFF_BAR + 16);
+
+    if (tid == 0) {
+        tc::mbar_wait(bar_w, 0);                                          // weights landed
+        tc::tc_fence_after();
+        constexpr uint32_t idesc = tc::umma_idesc_bf16(128, ST_CO);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int m = 0; m < ST_MT; ++m)
 #pragma unroll
-            for (int c = 0; c < 16; ++c) acc[j][c] = s.bias[cg * 16 + c];
-#pragma unroll 1
-        for (int ky = 0; ky < 7; ++ky) {
-            float in[13];
-            const float* pr = &s.patch[2 * row + ky][8 * xg];
+            for (int k = 0; k < 4; ++k)
+                tc::umma_bf16(tmem_base + m * ST_CO, tc::umma_desc_sw128(sbase + ST_OFF_A + m * 16384 + k * 32),
+                              tc::umma_desc_sw128(sbase + ST_OFF_B + k * 32), idesc, k ? 1u : 0u);
+        tc::umma_commit(bar_mma);
+    }
+    __syncwarp();
+    tc::mbar_wait(bar_mma, 0);                                            // all 12 MMAs retired: A is dead
+    tc::tc_fence_after();
+
+    // ---- epilogue: TMEM -> +bias, ReLU -> bf16 conv tile in smem (over the A tiles) ------------
+    // warp w reads TMEM lanes 32*(w%4)..; warps 0-3 take M tiles 0 and 2, warps 4-7 take M tile 1
+    {
+        const int q = warp & 3;
+        for (int m = (warp >> 2); m < ST_MT; m += 2) {
+            const int row = m * 128 + q * 32 + lane;
+            uint32_t r0[32], r1[32];
+            const uint32_t taddr = tmem_base + m * ST_CO + ((uint32_t)(q * 32) << 16);
+            tc::tmem_ld32(taddr, r0);
+            tc::tmem_ld32(taddr + 32, r1);
+            tc::tmem_ld_wait();
+            if (row < ST_NPOS) {
+                const int cy = cy0 + row / ST_C, cx = cx0 + row % ST_C;
+                // conv positions outside the map are max-pool padding; post-ReLU values are >= 0 so 0 == -inf
+                const bool valid = cy >= 0 && cy < hc && cx >= 0 && cx < wc;
+                unsigned char* dst = sgen + ST_OFF_A + row * 128;
 #pragma unroll
-            for (int i = 0; i < 13; ++i) in[i] = pr[i];
+                for (int ch = 0; ch < 8; ++ch) {
+                    __align__(16) __nv_bfloat162 o[4];
 #pragma unroll
-            for (int kx = 0; kx < 7; ++kx) {
-                const float4* wp4 = reinterpret_cast<const float4*>(&s.w[ky * 7 + kx][cg * 16]);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 w4 = wp4[q];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float v = in[2 * j + kx];
-                        acc[j][q * 4 + 0] = fmaf(v, w4.x, acc[j][q * 4 + 0]);
-                        acc[j][q * 4 + 1] = fmaf(v, w4.y, acc[j][q * 4 + 1]);
-                        acc[j][q * 4 + 2] = fmaf(v, w4.z, acc[j][q * 4 + 2]);
-                        acc[j][q * 4 + 3] = fmaf(v, w4.w, acc[j][q * 4 + 3]);
+                    for (int i = 0; i < 4; ++i) {
+                        const int cidx = ch * 8 + 2 * i;
+                        const float a = __uint_as_float(cidx < 32 ? r0[cidx] : r1[cidx - 32]) + __ldg(bias + cidx);
+                        const float d = __uint_as_float(cidx < 32 ? r0[cidx + 1] : r1[cidx - 31]) + __ldg(bias + cidx + 1);
+                        o[i] = valid ? __floats2bfloat162_rn(fmaxf(a, 0.f), fmaxf(d, 0.f)) : __floats2bfloat162_rn(0.f, 0.f);
                     }
+                    *reinterpret_cast<uint4*>(dst + ((ch ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(o);
                 }
             }
         }
-        const int cy = cy0 + row;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int col = xg * 4 + j;
-            const int cx = cx0 + col;
-            // conv positions outside the map are max-pool padding; post-ReLU values are >= 0,
-            // so 0 stands in for -inf
-            const bool valid = cy >= 0 && cy < hc && cx >= 0 && cx < wc && col < ST_CW;
-            __align__(16) __nv_bfloat162 o[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float a = valid ? fmaxf(acc[j][2 * c], 0.f) : 0.f;
-                const float d = valid ? fmaxf(acc[j][2 * c + 1], 0.f) : 0.f;
-                o[c] = __floats2bfloat162_rn(a, d);
-            }
-            uint4* dst = reinterpret_cast<uint4*>(&s.conv[row * (ST_XG * 4) + col][cg * 16]);
-            dst[0] = reinterpret_cast<const uint4*>(o)[0];
-            dst[1] = reinterpret_cast<const uint4*>(o)[1];
-        }
     }
+    tc::tc_fence_before();
     __syncthreads();
 
-    // ---- 3x3 s2 max pool, NHWC bf16 store: thread = (pool pixel, half of the channels) ----
+    // ---- 3x3 s2 max pool, NHWC bf16 store: thread = (pool pixel, 16-channel quarter) -----------
     {
-        const int half = tid & 1, pos = tid >> 1;    // 128 pool pixels x 2 halves = 256 threads
-        const int pyl = pos / ST_PW, pxl = pos % ST_PW;
-        __nv_bfloat162 m[16];
+        const int quarter = tid & 3, pos = tid >> 2;                      // 64 pool pixels x 4 quarters
+        const int pyl = pos / ST_P, pxl = pos % ST_P;
+        __nv_bfloat162 m[8];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) m[c] = __floats2bfloat162_rn(0.f, 0.f);
+        for (int c = 0; c < 8; ++c) m[c] = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
-                const uint4* src = reinterpret_cast<const uint4*>(
-                    &s.conv[(2 * pyl + dy) * (ST_XG * 4) + 2 * pxl + dx][half * 32]);
+                const int row = (2 * pyl + dy) * ST_C + 2 * pxl + dx;
+                const unsigned char* src = sgen + ST_OFF_A + row * 128;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint4 u = src[q];
+                for (int hch = 0; hch < 2; ++hch) {
+                    const int ch = quarter * 2 + hch;
+                    const uint4 u = *reinterpret_cast<const uint4*>(src + ((ch ^ (row & 7)) << 4));
                     const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) m[q * 4 + c] = __hmax2(m[q * 4 + c], h2[c]);
+                    for (int c = 0; c < 4; ++c) m[hch * 4 + c] = __hmax2(m[hch * 4 + c], h2[c]);
                 }
             }
-        const int py = py0 + pyl, px = px0 + pxl;
-        uint4* dst = reinterpret_cast<uint4*>(y + (((size_t)b * hp + py) * wp + px) * ST_CO + half * 32);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q] = reinterpret_cast<const uint4*>(m)[q];
+        uint4* dst = reinterpret_cast<uint4*>(y + (((size_t)b * hp + py0 + pyl) * wp + px0 + pxl) * ST_CO + quarter * 16);
+        dst[0] = reinterpret_cast<const uint4*>(m)[0];
+        dst[1] = reinterpret_cast<const uint4*>(m)[1];
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc<ST_TMEM_COLS>(tmem_base);
     }
 }
 
+int make_w_map_2d(CUtensorMap* m, const void* base, int k_total, int rows, int box_rows);   // igemm.cu
+
 }  // namespace scd
 
-extern "C" int scd_stem_fwd(const float* x, const float* weight, const float* bias, int batch,
+extern "C" int scd_stem_fwd(const float* x, const void* weight, const float* bias, int batch,
                             int height, int width, void* y, void* stream)
 {
     using namespace scd;
     if (batch <= 0) return SCD_OK;
     if (!x || !weight || !bias || !y) return fail(SCD_EINVAL, "scd_stem_fwd: null pointer");
-    if (height % (4 * ST_PH) != 0 || width % (4 * ST_PW) != 0)
-        return fail(SCD_EINVAL, "scd_stem_fwd: H must be a multiple of %d and W of %d (got %dx%d)", 4 * ST_PH,
-                    4 * ST_PW, height, width);
-    static_assert(sizeof(StemSmem) <= 110 * 1024, "two stem CTAs must fit one SM");
-    SCD_CUDA_CHECK(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)sizeof(StemSmem)));
-    dim3 grid((height / 4 / ST_PH) * (width / 4 / ST_PW), batch);
-    stem_kernel<<<grid, ST_THREADS, sizeof(StemSmem), (cudaStream_t)stream>>>(
-        x, weight, bias, height, width, reinterpret_cast<__nv_bfloat16*>(y));
-    SCD_LAUNCH_CHECK("stem_kernel");
+    if (height % (4 * ST_P) != 0 || width % (4 * ST_P) != 0)
+        return fail(SCD_EINVAL, "scd_stem_fwd: H and W must be multiples of %d (got %dx%d)", 4 * ST_P, height, width);
+    CUtensorMap tmW;
+    int rc = make_w_map_2d(&tmW, weight, 64, 64, 64);
+    if (rc) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SCD_CUDA_CHECK(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+        attr_done = true;
+    }
+    dim3 grid((height / 4 / ST_P) * (width / 4 / ST_P), batch);
+    stem_tc_kernel<<<grid, ST_THREADS, ST_SMEM, (cudaStream_t)stream>>>(
+        tmW, x, bias, height, width, reinterpret_cast<__nv_bfloat16*>(y));
+    SCD_LAUNCH_CHECK("stem_tc_kernel");
     return SCD_OK;
 }

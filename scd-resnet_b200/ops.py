@@ -116,7 +116,7 @@ def centernet_loss(heat, regr, offset, gt_heat, mask, regr6, idx, regr_w=0.1, of
 def stem_fwd(x, weight, bias):
     """ResNet.preprocess (ref: models/backbones/residuals.py:210-215), BN folded. -> (B,H/4,W/4,64) bf16 NHWC."""
     x = _req(x, torch.float32, "x")
-    weight = _req(weight, torch.float32, "stem weight")
+    weight = _req(weight, torch.bfloat16, "stem weight")
     bias = _req(bias, torch.float32, "stem bias")
     b, c, h, w = x.shape
     y = torch.empty(b, h // 4, w // 4, 64, dtype=torch.bfloat16, device=x.device)

@@ -55,11 +55,25 @@ def pack_conv(weight, kind, scale=None):
     return out.to(torch.bfloat16).contiguous()
 
 
+def pack_stem(weight, scale=None):
+    """Conv2d 1->64 7x7 s2 weight (64,1,7,7) -> (64, 64) bf16 for the space-to-depth stem GEMM:
+    k = (dy*4 + dx)*4 + py*2 + px  <->  (ky, kx) = (2*dy + py - 1, 2*dx + px - 1); the 15 entries
+    with ky == -1 or kx == -1 are structural zeros (csrc/stem.cu)."""
+    w = weight.float().reshape(64, 7, 7)
+    if scale is not None:
+        w = w * scale.view(-1, 1, 1)
+    full = torch.zeros(64, 8, 8, dtype=torch.float32, device=w.device)
+    full[:, 1:, 1:] = w                                   # index t = k + 1 in 0..7, t = 0 is the zero tap
+    # t_y = 2*dy + py, t_x = 2*dx + px  ->  (dy, py, dx, px) -> order (dy, dx, py, px)
+    full = full.reshape(64, 4, 2, 4, 2).permute(0, 1, 3, 2, 4).reshape(64, 64)
+    return full.to(torch.bfloat16).contiguous()
+
+
 def fold(sd):
     """BN-folded, packed tensors of every stage (dict of name -> tensor), for eval-mode inference."""
     out = {}
     s, b = bn_scale_shift(sd, "preprocess.1")
-    out["stem_w"] = (sd["preprocess.0.weight"].float() * s.view(-1, 1, 1, 1)).reshape(64, 49).contiguous()
+    out["stem_w"] = pack_stem(sd["preprocess.0.weight"], s)
     out["stem_b"] = b.contiguous()
     for i, (ck, bk, kind) in enumerate(STAGES):
         s, b = bn_scale_shift(sd, bk)

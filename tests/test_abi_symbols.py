@@ -31,7 +31,7 @@ def test_abi_version_and_layout_queries():
     assert s.lib.scd_abi_version() == 1
     offs, sizes, total = s.ops.infer_weights_layout()
     assert len(offs) == 34 and total == s.lib.scd_infer_weights_bytes()
-    assert sizes[0] == 64 * 49 * 4 and sizes[30] == 384 * 2304 * 2
+    assert sizes[0] == 64 * 64 * 2 and sizes[30] == 384 * 2304 * 2
     assert all(o % 256 == 0 for o in offs)
     assert s.ops.slide_geometry(16384, 16384) == (43, 43, 16640, 16640, 128, 128)   # BASELINE config 5
     assert s.lib.scd_infer_workspace_bytes(64, 512, 512) > 64 * 20 * 2 ** 20
