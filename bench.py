@@ -41,7 +41,8 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons.  The sampler runs from before the warm-up to after the timed
+    region (nvidia-smi needs a few hundred ms to start); samples are matched to the timed window by time."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -51,7 +52,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -59,19 +60,24 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        ok = [(t, r) for t, r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        win = [r for t, r in ok if t0 - 0.02 <= t <= t1 + 0.05]
+        window = "timed region"
+        if not win:                       # timed region shorter than the sampling period
+            win, window = [r for t, r in ok if t >= t0 - 2.0], "warm-up + timed region"
+        sm = [float(r[0]) for r in win]
+        mx = [float(r[1]) for r in win]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i] == "Active" for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i] == "Active" for r in win)]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 def cpu_oracle_rate(tiles_per_iter, min_seconds, warmup=1, max_iters=1000, fixed_iters=None):
@@ -128,8 +134,8 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="tiles per GPU per step (config[1] = 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -172,6 +178,9 @@ def main():
     xs = [torch.randn(B, 1, 512, 512, device=dev, generator=g) for _ in range(3)]
 
     # ---- device-resident throughput --------------------------------------------------------------
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     for i in range(W):
         det.detect_device(xs[i % 3])
     stage_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(17)] for _ in range(K)]
@@ -182,11 +191,8 @@ def main():
     for e in dec_ev:
         e.record()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clocks = ClockSampler(local)
     barrier()
-    if rank == 0:
-        clocks.start()
-    barrier()
+    wall0 = time.time()
     t_start.record()
     for i in range(K):
         det.detect_device(xs[i % 3], stage_ev[i])
@@ -194,7 +200,7 @@ def main():
     t_end.record()
     barrier()
     ms = t_start.elapsed_time(t_end)
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(wall0, time.time()) if rank == 0 else None
     stage_ms = [statistics.mean(stage_ev[i][j].elapsed_time(stage_ev[i][j + 1]) for i in range(K)) for j in range(16)]
     decode_ms = statistics.mean(stage_ev[i][16].elapsed_time(dec_ev[i]) for i in range(K))
 

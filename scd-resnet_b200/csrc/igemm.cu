@@ -34,6 +34,7 @@ enum { EPI_STORE = 0, EPI_HEADS = 1 };
 struct alignas(64) IgemmParams {
     CUtensorMap tmA[4];
     CUtensorMap tmB;
+    CUtensorMap tmOut[4];           // output views (one per output parity for the deconv), box {64 ch, 16 x, 2 y}
     int n_taps, cin_blocks, tiles_x, tiles_y, n_par, n_tiles_n, batch, total_tiles;
     int cout, out_mul, hout, wout, relu;
     int8_t tap_map[4][9], tap_dy[4][9], tap_dx[4][9];
@@ -55,8 +56,12 @@ template <int BN> struct IgemmCfg {
     static constexpr int ACC_STAGES = (2 * BN <= 512) ? 2 : 1;
     static constexpr int TMEM_COLS = (BN * ACC_STAGES <= 128) ? 128 : (BN * ACC_STAGES <= 256 ? 256 : 512);
     static constexpr int B_BOX_ROWS = (BN > 256) ? BN / 2 : BN;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                      (384 + 7 * 128 + 8) * 4 /*head constants*/;
+    // [pipeline stages][4 x 4 KB store staging][barriers 256 B][per-warp bias copies | head constants]
+    static constexpr int OFF_STG = STAGES * STAGE_BYTES;
+    static constexpr int OFF_BAR = OFF_STG + 4 * 4096;
+    static constexpr int OFF_CONST = OFF_BAR + 256;
+    static constexpr int CONST_BYTES = (BN > 256) ? (384 + 7 * 128 + 8) * 4 : 4 * BN * 4;
+    static constexpr int SMEM_BYTES = OFF_CONST + CONST_BYTES + 1024 /*align slack*/;
 };
 
 template <int BN, int EPI>
@@ -67,16 +72,15 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t smem_base = (tc::smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* smem_gen = smem_dyn + (smem_base - tc::smem_u32(smem_dyn));
-    const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+    const uint32_t bar_base = smem_base + Cfg::OFF_BAR;
     // barrier slots (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem ptr
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
-    uint32_t* tmem_slot_gen = reinterpret_cast<uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES +
-                                                           8 * (2 * Cfg::STAGES + 4));
-    float* head_const = reinterpret_cast<float*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
+    uint32_t* tmem_slot_gen = reinterpret_cast<uint32_t*>(smem_gen + Cfg::OFF_BAR + 8 * (2 * Cfg::STAGES + 4));
+    float* head_const = reinterpret_cast<float*>(smem_gen + Cfg::OFF_CONST);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -195,36 +199,65 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
             const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
 
             if (EPI == EPI_STORE) {
+                // TMEM -> regs -> (+bias, +residual, ReLU) -> bf16 -> swizzled smem tile -> TMA store.
+                // Each warp owns 2 rows of the 8x16 pixel patch = one {64 ch, 16 x, 2 y} box per 64 channels.
+                unsigned char* stg_gen = smem_gen + Cfg::OFF_STG + q * 4096;
+                const uint32_t stg = smem_base + Cfg::OFF_STG + q * 4096;
+                float* bias_s = head_const + q * BN;
+                __syncwarp();
+                for (int i = lane; i < BN; i += 32) bias_s[i] = __ldg(p.bias + nt * BN + i);
+                __syncwarp();
                 const size_t pix = ((size_t)img * p.hout + oy) * p.wout + ox;
-                __nv_bfloat16* optr = p.out + pix * p.cout + nt * BN;
                 const __nv_bfloat16* rptr = p.residual ? p.residual + pix * p.cout + nt * BN : nullptr;
-                const float* bptr = p.bias + nt * BN;
+                const CUtensorMap* mo = &p.tmOut[par];
+                const int gx = tx * IG_TW, gy = ty * IG_TH + 2 * q;
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    uint32_t r[32];
-                    tc::tmem_ld32(taddr + c0, r);
-                    tc::tmem_ld_wait();
-                    __align__(16) __nv_bfloat162 o[16];
-                    uint4 resv[4];
+                for (int c0 = 0; c0 < BN; c0 += 64) {
+                    uint4 resv[8];
                     if (rptr) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) resv[i] = reinterpret_cast<const uint4*>(rptr + c0)[i];
+                        for (int i = 0; i < 8; ++i) resv[i] = __ldg(reinterpret_cast<const uint4*>(rptr + c0) + i);
                     }
+                    uint32_t r[64];
+                    tc::tmem_ld32(taddr + c0, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+                    tc::tmem_ld32(taddr + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+                    tc::tmem_ld_wait();
+                    if (c0 + 64 >= BN) {                     // last TMEM read of this tile: release the accumulator
+                        tc::tc_fence_before();
+                        tc::mbar_arrive(tempty_bar(as));
+                    }
+                    if (lane == 0) tc::bulk_wait_read0();    // previous store has finished reading the staging tile
+                    __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float a = __uint_as_float(r[2 * i]) + __ldg(bptr + c0 + 2 * i);
-                        float b = __uint_as_float(r[2 * i + 1]) + __ldg(bptr + c0 + 2 * i + 1);
+                    for (int ch = 0; ch < 8; ++ch) {
+                        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c0 + ch * 8);
+                        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c0 + ch * 8 + 4);
+                        float v[8];
+                        v[0] = __uint_as_float(r[ch * 8 + 0]) + b0.x; v[1] = __uint_as_float(r[ch * 8 + 1]) + b0.y;
+                        v[2] = __uint_as_float(r[ch * 8 + 2]) + b0.z; v[3] = __uint_as_float(r[ch * 8 + 3]) + b0.w;
+                        v[4] = __uint_as_float(r[ch * 8 + 4]) + b1.x; v[5] = __uint_as_float(r[ch * 8 + 5]) + b1.y;
+                        v[6] = __uint_as_float(r[ch * 8 + 6]) + b1.z; v[7] = __uint_as_float(r[ch * 8 + 7]) + b1.w;
                         if (rptr) {
-                            const __nv_bfloat162 rr = reinterpret_cast<const __nv_bfloat162*>(resv)[i];
-                            a += __low2float(rr);
-                            b += __high2float(rr);
-                        }
-                        if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                        o[i] = __floats2bfloat162_rn(a, b);
-                    }
+                            const __nv_bfloat162* rr = reinterpret_cast<const __nv_bfloat162*>(&resv[ch]);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        reinterpret_cast<uint4*>(optr + c0)[i] = reinterpret_cast<const uint4*>(o)[i];
+                            for (int i = 0; i < 4; ++i) { v[2 * i] += __low2float(rr[i]); v[2 * i + 1] += __high2float(rr[i]); }
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                        }
+                        __align__(16) __nv_bfloat162 o[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) o[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                        *reinterpret_cast<uint4*>(stg_gen + lane * 128 + ((ch ^ (lane & 7)) << 4)) =
+                            *reinterpret_cast<const uint4*>(o);
+                    }
+                    tc::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tc::tma_store_4d(mo, stg, nt * BN + c0, gx, gy, img);
+                        tc::bulk_commit();
+                    }
                 }
             } else {
                 // heads: hidden = ReLU(acc + b3); out_j = b1_j + sum_c hidden[head(j), c] * w1[j, c]
@@ -264,9 +297,13 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
 #pragma unroll
                 for (int j = 0; j < 2; ++j) p.off[((size_t)img * 2 + j) * hw + pix] = o[5 + j];
             }
-            tc::tc_fence_before();
-            tc::mbar_arrive(tempty_bar(as));                 // 128 arrivals release the accumulator
+            if (EPI == EPI_HEADS) {
+                tc::tc_fence_before();
+                tc::mbar_arrive(tempty_bar(as));             // 128 arrivals release the accumulator
+            }
         }
+        if (EPI == EPI_STORE && lane == 0) tc::bulk_wait0(); // all TMA stores of this warp have completed
+        __syncwarp();
     }
 
     tc::tc_fence_before();
@@ -296,14 +333,15 @@ static EncodeTiledFn encode_fn() {
 
 // NHWC bf16 activation viewed as a 4-D tensor {C, W/sub, H/sub, N}; sub = 2 selects the
 // (py, px) parity view used by stride-2 convolutions.
-static int make_act_map(CUtensorMap* m, const void* base, int n, int h, int w, int c, int sub, int py, int px)
+static int make_act_map(CUtensorMap* m, const void* base, int n, int h, int w, int c, int sub, int py, int px,
+                        int box_h = IG_TH)
 {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return fail(SCD_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
     const char* b = static_cast<const char*>(base) + ((size_t)py * w + px) * c * 2;
     cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)(w / sub), (cuuint64_t)(h / sub), (cuuint64_t)n};
     cuuint64_t strides[3] = {(cuuint64_t)sub * c * 2, (cuuint64_t)sub * w * c * 2, (cuuint64_t)h * w * c * 2};
-    cuuint32_t box[4] = {IG_BK, IG_TW, IG_TH, 1};
+    cuuint32_t box[4] = {IG_BK, IG_TW, (cuuint32_t)box_h, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(b), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -422,6 +460,10 @@ extern "C" int scd_conv_igemm_fwd(int kind, const void* x, const void* weight, c
     p.bias = bias; p.residual = static_cast<const __nv_bfloat16*>(residual); p.out = static_cast<__nv_bfloat16*>(y);
     rc = make_w_map(&p.tmB, weight, p.n_taps * cin, p.n_par * cout, bn);
     if (rc) return rc;
+    for (int par = 0; par < p.n_par; ++par) {
+        rc = make_act_map(&p.tmOut[par], y, batch, p.hout, p.wout, cout, p.out_mul, par >> 1, par & 1, 2);
+        if (rc) return rc;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (bn == 256) return launch_igemm<256, EPI_STORE>(p, st);
     if (bn == 128) return launch_igemm<128, EPI_STORE>(p, st);
