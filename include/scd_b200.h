@@ -158,6 +158,77 @@ int scd_resnet10_infer(const float* x, const void* weights, int batch, int heigh
                        void* workspace, size_t workspace_bytes, void* const* h_stage_events,
                        void* stream);
 
+/* ====================================================================================
+ * Training path (NetworkFactory.train, models/networkFactory.py:257-263: forward with
+ * batch-statistics BatchNorm -> CenterNetLoss -> backward -> Adam).
+ * Activations and their gradients are NHWC bf16, BN statistics and all reductions fp32/fp64,
+ * master weights fp32.
+ * ==================================================================================== */
+
+/* Train-mode BatchNorm2d (eps 1e-5, momentum 0.1, residuals.py:30) over z (pixels, C) bf16:
+ *   scd_bn_stats     sums[0..C) = sum z, sums[C..2C) = sum z^2   (fp64; all-reduce them for SyncBatchNorm)
+ *   scd_bn_finalize  scale = gamma*invstd, shift = beta - mean*scale, mean, invstd; updates running_mean /
+ *                    running_var (unbiased) / num_batches_tracked when given.  `count` = elements per channel.
+ *   scd_bn_apply     out = [relu](z*scale + shift [+ residual])
+ *   scd_bn_bwd       phase 0: sums = (sum dy, sum dy*xhat) with dy = da * (a > 0) (a == NULL: no ReLU mask);
+ *                    phase 1: dz = scale*(dy - sums0/count - xhat*sums1/count), optional dy_out (the gradient
+ *                    entering the residual branch), dgamma, dbeta. */
+int scd_bn_stats(const void* z, size_t pixels, int C, double* sums, void* stream);
+int scd_bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, long long* num_batches, int C, double count, float momentum,
+                    float eps, float* scale, float* shift, float* mean, float* invstd, void* stream);
+int scd_bn_apply(const void* z, const float* scale, const float* shift, const void* residual, int relu,
+                 size_t pixels, int C, void* out, void* stream);
+int scd_bn_bwd(const void* da, const void* a, const void* z, const float* scale, const float* mean,
+               const float* invstd, size_t pixels, int C, double count, double* sums, void* dz,
+               void* dy_out, float* dgamma, float* dbeta, int phase, void* stream);
+
+/* Data gradient of a forward stage of kind 0 (3x3 s1), 1 (3x3 s2, optionally fused with the gradient of the
+ * parallel 1x1 s2 downsample conv: dz2) or 3 (ConvTranspose 4x4 s2), as an implicit GEMM over dz
+ * (B,hin,win,cin).  `weight` is the data-gradient packing of the layer's weight (weights.py), `add`
+ * (nullable, dx's layout) is added: the gradient arriving through another branch. */
+int scd_conv_igemm_dgrad(int kind, const void* dz, const void* dz2, const void* weight, const float* bias,
+                         const void* add, int batch, int hin, int win, int cin, int cout, void* dx,
+                         void* stream);
+
+/* Weight gradient as a pixel-contraction GEMM with MN-major tcgen05 operands and split-K.
+ * kind 0/1/2: a_in = layer input (B,hin,win,cin), dz = output gradient, out[(t*cin/64 + ci/64)][co][ci%64];
+ * kind 3 (ConvTranspose): a_in = layer input (B,hin,win,cin), dz (B,2hin,2win,cout),
+ *                         out[(t*cout/64 + co/64)][ci][co%64], t = kh*4 + kw;
+ * kind 4 (stem): a_in = im2col operand col0 (B,hin,win,64), dz = dz0, out[0][co][k].
+ * `out` (fp32, scd_conv_wgrad_out_floats elements) must be zero on entry; partial tiles are accumulated. */
+size_t scd_conv_wgrad_out_floats(int kind, int cin, int cout);
+int scd_conv_wgrad(int kind, const void* a_in, const void* dz, int batch, int hin, int win,
+                   int cin, int cout, float* out, void* stream);
+
+/* Stem in training: raw conv output z0 (B,H/2,W/2,64) bf16 + its im2col operand col0 (same shape);
+ * a0 = maxpool3x3s2(relu(z0*scale + shift)); and the gradient back to relu(bn(z0)) (ReLU mask applied). */
+int scd_stem_conv_train(const float* x, const void* weight, int batch, int height, int width,
+                        void* z0, void* col0, void* stream);
+int scd_stem_bn_relu_pool(const void* z0, const float* scale, const float* shift, int batch, int hp, int wp,
+                          void* a0, void* stream);
+int scd_stem_pool_bwd(const void* z0, const float* scale, const float* shift, const void* da0, int batch,
+                      int hp, int wp, void* dy0, void* stream);
+
+/* Heads in training: scd_heads_fwd + hidden = ReLU(conv3x3 + b3) stored as (B,H,W,384) bf16;
+ * scd_heads_bwd: d_hidden = (w1^T d_out) * (hidden > 0), and the gradients of w1 (7,128), b1 (7), b3 (384). */
+int scd_heads_fwd_train(const void* x, const void* w3, const float* b3, const float* w1,
+                        const float* b1, int batch, int height, int width,
+                        float* heat, float* regr, float* offset, void* hidden, void* stream);
+int scd_heads_bwd(const float* d_heat, const float* d_regr, const float* d_off, const void* hidden,
+                  const float* w1, int batch, int height, int width, void* d_hidden, float* g_w1,
+                  float* g_b1, float* g_b3, void* stream);
+
+/* Fused Adam (torch.optim.Adam defaults, networkFactory.py:80-82) over the flat fp32 parameter buffer.
+ * The gradient of parameter i is grad_scale * grads[gmap ? gmap[i] : i] (the wgrad kernels write their own
+ * layout).  scd_gather_cast_bf16 refreshes the bf16 GEMM-operand copies: dst[i] = bf16(src[idx[i]]), 0 if
+ * idx[i] < 0.  scd_scale_inplace: x *= *d_scale. */
+int scd_adam_step(float* params, float* exp_avg, float* exp_avg_sq, const float* grads, const int* gmap,
+                  size_t n, int step, float lr, float beta1, float beta2, float eps, float grad_scale,
+                  void* stream);
+int scd_gather_cast_bf16(const float* src, const int* idx, size_t n, void* dst, void* stream);
+int scd_scale_inplace(float* x, size_t n, const float* d_scale, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Slide front-end: per-tile normalisation.  Replaces normalize
  * (datasets/argumentations.py:39-44) as applied per 512x512 tile in test.py:86-90,

@@ -27,6 +27,21 @@ PROTOTYPES = {
     "scd_infer_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "scd_resnet10_infer": (c_int, [c_void_p, c_void_p] + [c_int] * 3 + [c_void_p] * 3
                            + [c_void_p, c_size_t, c_void_p, c_void_p]),
+    "scd_bn_stats": (c_int, [c_void_p, c_size_t, c_int, c_void_p, c_void_p]),
+    "scd_bn_finalize": (c_int, [c_void_p] * 6 + [c_int, ctypes.c_double, c_float, c_float] + [c_void_p] * 4 + [c_void_p]),
+    "scd_bn_apply": (c_int, [c_void_p] * 4 + [c_int, c_size_t, c_int, c_void_p, c_void_p]),
+    "scd_bn_bwd": (c_int, [c_void_p] * 6 + [c_size_t, c_int, ctypes.c_double] + [c_void_p] * 5 + [c_int, c_void_p]),
+    "scd_conv_igemm_dgrad": (c_int, [c_int] + [c_void_p] * 5 + [c_int] * 5 + [c_void_p, c_void_p]),
+    "scd_conv_wgrad_out_floats": (c_size_t, [c_int, c_int, c_int]),
+    "scd_conv_wgrad": (c_int, [c_int, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p, c_void_p]),
+    "scd_stem_conv_train": (c_int, [c_void_p, c_void_p] + [c_int] * 3 + [c_void_p] * 3),
+    "scd_stem_bn_relu_pool": (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p, c_void_p]),
+    "scd_stem_pool_bwd": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p, c_void_p]),
+    "scd_heads_fwd_train": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p] * 4 + [c_void_p]),
+    "scd_heads_bwd": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p] * 4 + [c_void_p]),
+    "scd_adam_step": (c_int, [c_void_p] * 5 + [c_size_t, c_int] + [c_float] * 5 + [c_void_p]),
+    "scd_gather_cast_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "scd_scale_inplace": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "scd_slide_geometry": (c_int, [c_int, c_int, c_void_p]),
     "scd_slide_tiles": (c_int, [c_void_p] + [c_int] * 4 + [c_void_p, c_void_p]),
 }

@@ -1,0 +1,265 @@
+// Train-mode BatchNorm (+ReLU, +residual) forward and backward on NHWC bf16 activations.
+//
+// Replaces the torch.nn.BatchNorm2d / ReLU / `out += residual` calls of the reference in training
+// (ref: models/backbones/residuals.py:100-120 BasicBlock.forward, :210-213 stem, :298-307 deconv
+// stack; BN momentum 0.1 :30, eps 1e-5) and their autograd.  All kernels are HBM-bound streaming
+// passes over [pixels][C] with 128-bit accesses; per-channel reductions are accumulated per thread
+// in fp32, per CTA in shared memory and across CTAs with fp64 atomics.
+//
+//   bn_stats      z                      -> sum[c], sumsq[c]                       (fp64)
+//   bn_finalize   sums, gamma, beta      -> scale, shift, mean, invstd; running stats (momentum, unbiased var)
+//   bn_apply      z, scale, shift, res?  -> a = [relu](z*scale + shift [+ res])     (bf16)
+//   bn_bwd_reduce da, a?, z              -> sum(dy), sum(dy * xhat)                 (fp64), dy = da * (a > 0)
+//   bn_bwd_apply  da, a?, z, sums        -> dz = scale*(dy - mean(dy) - xhat*mean(dy*xhat)) (bf16) [, dy]
+#include "common.cuh"
+
+namespace scd {
+
+constexpr int BN_THREADS = 256;
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { f[2 * i] = __low2float(h[i]); f[2 * i + 1] = __high2float(h[i]); }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    __align__(16) __nv_bfloat162 h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return *reinterpret_cast<const uint4*>(h);
+}
+
+// Threads are laid out so that thread t always handles channel group (t % (C/8)); a CTA strides over
+// pixels.  Requires BN_THREADS % (C/8) == 0, true for C in {64,128,256,384(no!),512}: 384/8 = 48 does not
+// divide 256, so the launch picks a block size that is a multiple of C/8.
+template <int MODE>   // 0: stats of z   1: backward sums
+__global__ void __launch_bounds__(384)
+bn_reduce_kernel(const uint4* __restrict__ z, const uint4* __restrict__ da, const uint4* __restrict__ a,
+                 const float* __restrict__ mean, const float* __restrict__ invstd,
+                 size_t pixels, int cgroups, double* __restrict__ sums /* [2][C] */)
+{
+    extern __shared__ float red[];                       // [2][blockDim.x][8]
+    const int g = threadIdx.x % cgroups;                 // channel group of 8
+    const int lanes = blockDim.x / cgroups;              // pixel lanes per CTA
+    const int pl = threadIdx.x / cgroups;
+    float s0[8], s1[8], mu[8], is[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s0[i] = 0.f; s1[i] = 0.f; mu[i] = 0.f; is[i] = 1.f; }
+    if (MODE == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { mu[i] = mean[g * 8 + i]; is[i] = invstd[g * 8 + i]; }
+    }
+    for (size_t p = (size_t)blockIdx.x * lanes + pl; p < pixels; p += (size_t)gridDim.x * lanes) {
+        float zf[8];
+        unpack8(__ldg(z + p * cgroups + g), zf);
+        if (MODE == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s0[i] += zf[i]; s1[i] = fmaf(zf[i], zf[i], s1[i]); }
+        } else {
+            float df[8];
+            unpack8(__ldg(da + p * cgroups + g), df);
+            if (a != nullptr) {
+                float af[8];
+                unpack8(__ldg(a + p * cgroups + g), af);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) df[i] = af[i] > 0.f ? df[i] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s0[i] += df[i]; s1[i] = fmaf(df[i], (zf[i] - mu[i]) * is[i], s1[i]); }
+        }
+    }
+    float* r0 = red + (size_t)threadIdx.x * 8;
+    float* r1 = red + (size_t)(blockDim.x + threadIdx.x) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { r0[i] = s0[i]; r1[i] = s1[i]; }
+    __syncthreads();
+    const int C = cgroups * 8;
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+        const int which = c / C, ch = c % C;
+        const float* base = red + (size_t)which * blockDim.x * 8;
+        double t = 0.0;
+        for (int l = 0; l < lanes; ++l) t += (double)base[(size_t)(l * cgroups + ch / 8) * 8 + (ch & 7)];
+        atomicAdd(sums + which * C + ch, t);
+    }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, long long* __restrict__ num_batches,
+                                   int C, double count, float momentum, float eps,
+                                   float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ invstd_out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && num_batches) *num_batches += 1;
+    if (c >= C) return;
+    const double m = sums[c] / count;
+    double var = sums[C + c] / count - m * m;            // biased (what normalises the batch)
+    if (var < 0.0) var = 0.0;
+    const float inv = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * inv;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)m * sc;
+    mean_out[c] = (float)m;
+    invstd_out[c] = inv;
+    if (running_mean) {
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+
+__global__ void __launch_bounds__(BN_THREADS)
+bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
+                const uint4* __restrict__ residual, int relu, size_t n8, int cgroups, uint4* __restrict__ out)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i % cgroups);
+        float zf[8], o[8];
+        unpack8(__ldg(z + i), zf);
+        const float4 sa = __ldg(reinterpret_cast<const float4*>(scale) + 2 * g);
+        const float4 sb = __ldg(reinterpret_cast<const float4*>(scale) + 2 * g + 1);
+        const float4 ha = __ldg(reinterpret_cast<const float4*>(shift) + 2 * g);
+        const float4 hb = __ldg(reinterpret_cast<const float4*>(shift) + 2 * g + 1);
+        o[0] = fmaf(zf[0], sa.x, ha.x); o[1] = fmaf(zf[1], sa.y, ha.y);
+        o[2] = fmaf(zf[2], sa.z, ha.z); o[3] = fmaf(zf[3], sa.w, ha.w);
+        o[4] = fmaf(zf[4], sb.x, hb.x); o[5] = fmaf(zf[5], sb.y, hb.y);
+        o[6] = fmaf(zf[6], sb.z, hb.z); o[7] = fmaf(zf[7], sb.w, hb.w);
+        if (residual) {
+            float rf[8];
+            unpack8(__ldg(residual + i), rf);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] += rf[k];
+        }
+        if (relu) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k], 0.f);
+        }
+        out[i] = pack8(o);
+    }
+}
+
+// dz = scale * (dy - sum_dy/n - xhat * sum_dyx/n); dy = da * (a > 0).  Optionally also writes dy (the
+// gradient that flows into the residual branch).  Thread 0..C-1 of CTA 0 also emit dgamma, dbeta.
+__global__ void __launch_bounds__(BN_THREADS)
+bn_bwd_apply_kernel(const uint4* __restrict__ da, const uint4* __restrict__ a, const uint4* __restrict__ z,
+                    const float* __restrict__ scale, const float* __restrict__ mean,
+                    const float* __restrict__ invstd, const double* __restrict__ sums, double count,
+                    size_t n8, int cgroups, uint4* __restrict__ dz, uint4* __restrict__ dy_out,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta)
+{
+    const int C = cgroups * 8;
+    if (blockIdx.x == 0) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            if (dbeta) dbeta[c] = (float)sums[c];
+            if (dgamma) dgamma[c] = (float)sums[C + c];
+        }
+    }
+    const float inv_n = (float)(1.0 / count);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i % cgroups);
+        float df[8], zf[8], o[8];
+        unpack8(__ldg(da + i), df);
+        unpack8(__ldg(z + i), zf);
+        if (a != nullptr) {
+            float af[8];
+            unpack8(__ldg(a + i), af);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) df[k] = af[k] > 0.f ? df[k] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = g * 8 + k;
+            const float xh = (zf[k] - __ldg(mean + c)) * __ldg(invstd + c);
+            const float m1 = (float)sums[c] * inv_n, m2 = (float)sums[C + c] * inv_n;
+            o[k] = __ldg(scale + c) * (df[k] - m1 - xh * m2);
+        }
+        dz[i] = pack8(o);
+        if (dy_out) dy_out[i] = pack8(df);
+    }
+}
+
+static inline int stream_grid(size_t items, int per_block) {
+    size_t want = (items + per_block - 1) / per_block;
+    const size_t cap = (size_t)kNumSMs * 8;
+    if (want > cap) want = cap;
+    return (int)(want < 1 ? 1 : want);
+}
+
+static int reduce_block(int C) {            // largest multiple of C/8 that is <= 384 and a multiple of 32
+    const int cg = C / 8;
+    for (int b = 384; b >= cg; b -= 32)
+        if (b % cg == 0) return b;
+    return 0;
+}
+
+}  // namespace scd
+
+extern "C" int scd_bn_stats(const void* z, size_t pixels, int C, double* sums, void* stream)
+{
+    using namespace scd;
+    if (!z || !sums || C % 8) return fail(SCD_EINVAL, "scd_bn_stats: bad arguments");
+    const int block = reduce_block(C);
+    if (!block) return fail(SCD_EINVAL, "scd_bn_stats: unsupported channel count %d", C);
+    SCD_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, (cudaStream_t)stream));
+    const int lanes = block / (C / 8);
+    const int grid = stream_grid(pixels, lanes * 16);
+    bn_reduce_kernel<0><<<grid, block, (size_t)2 * block * 8 * sizeof(float), (cudaStream_t)stream>>>(
+        static_cast<const uint4*>(z), nullptr, nullptr, nullptr, nullptr, pixels, C / 8, sums);
+    SCD_LAUNCH_CHECK("bn_reduce_kernel<0>");
+    return SCD_OK;
+}
+
+extern "C" int scd_bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean,
+                               float* running_var, long long* num_batches, int C, double count, float momentum,
+                               float eps, float* scale, float* shift, float* mean, float* invstd, void* stream)
+{
+    using namespace scd;
+    if (!sums || !gamma || !beta || !scale || !shift || !mean || !invstd)
+        return fail(SCD_EINVAL, "scd_bn_finalize: null pointer");
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        sums, gamma, beta, running_mean, running_var, num_batches, C, count, momentum, eps, scale, shift, mean, invstd);
+    SCD_LAUNCH_CHECK("bn_finalize_kernel");
+    return SCD_OK;
+}
+
+extern "C" int scd_bn_apply(const void* z, const float* scale, const float* shift, const void* residual, int relu,
+                            size_t pixels, int C, void* out, void* stream)
+{
+    using namespace scd;
+    if (!z || !scale || !shift || !out || C % 8) return fail(SCD_EINVAL, "scd_bn_apply: bad arguments");
+    const size_t n8 = pixels * (size_t)(C / 8);
+    bn_apply_kernel<<<stream_grid(n8, BN_THREADS * 4), BN_THREADS, 0, (cudaStream_t)stream>>>(
+        static_cast<const uint4*>(z), scale, shift, static_cast<const uint4*>(residual), relu, n8, C / 8,
+        static_cast<uint4*>(out));
+    SCD_LAUNCH_CHECK("bn_apply_kernel");
+    return SCD_OK;
+}
+
+extern "C" int scd_bn_bwd(const void* da, const void* a, const void* z, const float* scale, const float* mean,
+                          const float* invstd, size_t pixels, int C, double count, double* sums, void* dz,
+                          void* dy_out, float* dgamma, float* dbeta, int phase, void* stream)
+{
+    // phase 0: reduce (sums <- sum dy, sum dy*xhat); phase 1: apply (uses sums, possibly all-reduced in between)
+    using namespace scd;
+    if (!da || !z || !scale || !mean || !invstd || !sums || C % 8) return fail(SCD_EINVAL, "scd_bn_bwd: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (phase == 0) {
+        const int block = reduce_block(C);
+        if (!block) return fail(SCD_EINVAL, "scd_bn_bwd: unsupported channel count %d", C);
+        SCD_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+        const int lanes = block / (C / 8);
+        bn_reduce_kernel<1><<<stream_grid(pixels, lanes * 16), block, (size_t)2 * block * 8 * sizeof(float), st>>>(
+            static_cast<const uint4*>(z), static_cast<const uint4*>(da), static_cast<const uint4*>(a), mean, invstd,
+            pixels, C / 8, sums);
+        SCD_LAUNCH_CHECK("bn_reduce_kernel<1>");
+    } else {
+        if (!dz) return fail(SCD_EINVAL, "scd_bn_bwd: dz is null");
+        const size_t n8 = pixels * (size_t)(C / 8);
+        bn_bwd_apply_kernel<<<stream_grid(n8, BN_THREADS * 4), BN_THREADS, 0, st>>>(
+            static_cast<const uint4*>(da), static_cast<const uint4*>(a), static_cast<const uint4*>(z), scale, mean,
+            invstd, sums, count, n8, C / 8, static_cast<uint4*>(dz), static_cast<uint4*>(dy_out), dgamma, dbeta);
+        SCD_LAUNCH_CHECK("bn_bwd_apply_kernel");
+    }
+    return SCD_OK;
+}

@@ -20,6 +20,7 @@
 // 2*BN <= 512 columns), warps 2-5 = epilogue (tcgen05.ld -> bias/residual/ReLU -> bf16 NHWC,
 // or for the heads: ReLU + block-diagonal 1x1 -> fp32 NCHW planes).
 #include "tc.cuh"
+#include "tmap.cuh"
 
 namespace scd {
 
@@ -29,15 +30,15 @@ constexpr int IG_TW = 16, IG_TH = 8;
 constexpr int IG_THREADS = 192;
 constexpr int IG_A_BYTES = IG_BM * IG_BK * 2;
 
-enum { EPI_STORE = 0, EPI_HEADS = 1 };
+enum { EPI_STORE = 0, EPI_HEADS = 1, EPI_HEADS_TRAIN = 2 };   // TRAIN also stores the hidden activations
 
 struct alignas(64) IgemmParams {
     CUtensorMap tmA[4];
     CUtensorMap tmB;
     CUtensorMap tmOut[4];           // output views (one per output parity for the deconv), box {64 ch, 16 x, 2 y}
-    int n_taps, cin_blocks, tiles_x, tiles_y, n_par, n_tiles_n, batch, total_tiles;
+    int n_taps[4], cin_blocks, tiles_x, tiles_y, n_par, n_tiles_n, batch, total_tiles;
     int cout, out_mul, hout, wout, relu;
-    int8_t tap_map[4][9], tap_dy[4][9], tap_dx[4][9];
+    int8_t tap_map[4][16], tap_dy[4][16], tap_dx[4][16];   // per output-parity class: A view, y / x offset
     const float* bias;
     const __nv_bfloat16* residual;
     __nv_bfloat16* out;
@@ -92,7 +93,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
-    if (EPI == EPI_HEADS) {
+    if (EPI != EPI_STORE) {
         for (int i = threadIdx.x; i < 384 + 7 * 128 + 7; i += IG_THREADS) {
             float v;
             if (i < 384) v = p.bias[i];
@@ -106,7 +107,6 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
 
-    const int k_blocks = p.n_taps * p.cin_blocks;
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -120,7 +120,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
                 const int par = m % p.n_par;
                 const int img = m / p.n_par;
                 const int brow = par * p.cout + nt * BN;
-                for (int tap = 0; tap < p.n_taps; ++tap) {
+                for (int tap = 0; tap < p.n_taps[par]; ++tap) {
                     const CUtensorMap* ma = &p.tmA[p.tap_map[par][tap]];
                     const int ax = tx * IG_TW + p.tap_dx[par][tap];
                     const int ay = ty * IG_TH + p.tap_dy[par][tap];
@@ -149,6 +149,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
             int stage = 0; uint32_t phase = 0;
             uint32_t it = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+                const int k_blocks = p.n_taps[(t / (p.n_tiles_n * p.tiles_x * p.tiles_y)) % p.n_par] * p.cin_blocks;
                 const uint32_t as = (Cfg::ACC_STAGES == 2) ? (it & 1u) : 0u;
                 const uint32_t aphase = (Cfg::ACC_STAGES == 2) ? ((it >> 1) & 1u) : (it & 1u);
                 tc::mbar_wait(tempty_bar(as), aphase ^ 1u);
@@ -267,15 +268,22 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
                 float o[7];
 #pragma unroll
                 for (int j = 0; j < 7; ++j) o[j] = b1[j];
+                unsigned char* stg_gen = smem_gen + Cfg::OFF_STG + q * 4096;
+                const uint32_t stg = smem_base + Cfg::OFF_STG + q * 4096;
 #pragma unroll 1
                 for (int c0 = 0; c0 < 384; c0 += 32) {
                     uint32_t r[32];
                     tc::tmem_ld32(taddr + c0, r);
                     tc::tmem_ld_wait();
                     const int head = c0 >> 7, hc = c0 & 127;
+                    if (EPI == EPI_HEADS_TRAIN && (c0 & 32) == 0) {
+                        if (lane == 0) tc::bulk_wait_read0();     // previous hidden store has read the staging tile
+                        __syncwarp();
+                    }
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const float h = fmaxf(__uint_as_float(r[i]) + b3[c0 + i], 0.f);
+                        if (EPI == EPI_HEADS_TRAIN) r[i] = __float_as_uint(h);
                         if (head == 0) {
                             o[0] = fmaf(h, w1[hc + i], o[0]);
                         } else if (head == 1) {
@@ -288,6 +296,27 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
                             o[6] = fmaf(h, w1[6 * 128 + hc + i], o[6]);
                         }
                     }
+                    if (EPI == EPI_HEADS_TRAIN) {
+                        // hidden = ReLU(conv3x3 + b3) as bf16 NHWC (B,H,W,384): needed by the backward pass
+                        const int half = (c0 >> 5) & 1;
+#pragma unroll
+                        for (int ch = 0; ch < 4; ++ch) {
+                            __align__(16) __nv_bfloat162 hb[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                hb[i] = __floats2bfloat162_rn(__uint_as_float(r[ch * 8 + 2 * i]), __uint_as_float(r[ch * 8 + 2 * i + 1]));
+                            *reinterpret_cast<uint4*>(stg_gen + lane * 128 + (((half * 4 + ch) ^ (lane & 7)) << 4)) =
+                                *reinterpret_cast<const uint4*>(hb);
+                        }
+                        if (half == 1) {
+                            tc::fence_proxy_async();
+                            __syncwarp();
+                            if (lane == 0) {
+                                tc::tma_store_4d(&p.tmOut[0], stg, c0 - 32, tx * IG_TW, ty * IG_TH + 2 * q, img);
+                                tc::bulk_commit();
+                            }
+                        }
+                    }
                 }
                 const size_t hw = (size_t)p.hout * p.wout;
                 const size_t pix = (size_t)oy * p.wout + ox;
@@ -297,12 +326,12 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
 #pragma unroll
                 for (int j = 0; j < 2; ++j) p.off[((size_t)img * 2 + j) * hw + pix] = o[5 + j];
             }
-            if (EPI == EPI_HEADS) {
+            if (EPI != EPI_STORE) {
                 tc::tc_fence_before();
                 tc::mbar_arrive(tempty_bar(as));             // 128 arrivals release the accumulator
             }
         }
-        if (EPI == EPI_STORE && lane == 0) tc::bulk_wait0(); // all TMA stores of this warp have completed
+        if (EPI != EPI_HEADS && lane == 0) tc::bulk_wait0(); // all TMA stores of this warp have completed
         __syncwarp();
     }
 
@@ -315,62 +344,6 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
 }
 
 // ---------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
-    return fn;
-}
-
-// NHWC bf16 activation viewed as a 4-D tensor {C, W/sub, H/sub, N}; sub = 2 selects the
-// (py, px) parity view used by stride-2 convolutions.
-static int make_act_map(CUtensorMap* m, const void* base, int n, int h, int w, int c, int sub, int py, int px,
-                        int box_h = IG_TH)
-{
-    EncodeTiledFn enc = encode_fn();
-    if (!enc) return fail(SCD_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    const char* b = static_cast<const char*>(base) + ((size_t)py * w + px) * c * 2;
-    cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)(w / sub), (cuuint64_t)(h / sub), (cuuint64_t)n};
-    cuuint64_t strides[3] = {(cuuint64_t)sub * c * 2, (cuuint64_t)sub * w * c * 2, (cuuint64_t)h * w * c * 2};
-    cuuint32_t box[4] = {IG_BK, IG_TW, (cuuint32_t)box_h, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(b), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(SCD_ECUDA, "cuTensorMapEncodeTiled(activation) failed: %d", (int)r);
-    return SCD_OK;
-}
-
-// weights: 2-D {K, rows} bf16, K contiguous
-static int make_w_map(CUtensorMap* m, const void* base, int k_total, int rows, int box_rows)
-{
-    EncodeTiledFn enc = encode_fn();
-    if (!enc) return fail(SCD_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
-    cuuint32_t box[2] = {IG_BK, (cuuint32_t)box_rows};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(SCD_ECUDA, "cuTensorMapEncodeTiled(weight) failed: %d", (int)r);
-    return SCD_OK;
-}
-
-int make_w_map_2d(CUtensorMap* m, const void* base, int k_total, int rows, int box_rows)
-{
-    return make_w_map(m, base, k_total, rows, box_rows);
-}
-
 template <int BN, int EPI>
 static int launch_igemm(const IgemmParams& p, cudaStream_t st)
 {
@@ -387,26 +360,33 @@ static int launch_igemm(const IgemmParams& p, cudaStream_t st)
     return SCD_OK;
 }
 
-// kind: 0 = 3x3 s1 p1, 1 = 3x3 s2 p1, 2 = 1x1 s2, 3 = deconv 4x4 s2 p1
-static int fill_geometry(IgemmParams& p, int kind, const void* x, int batch, int hin, int win, int cin)
+// kind: 0 = conv 3x3 s1 p1          1 = conv 3x3 s2 p1         2 = conv 1x1 s2      3 = deconv 4x4 s2 p1
+//       5 = data-gradient of kind 1 (+ of a kind-2 downsample when x2 != null): a transposed 3x3 s2 conv,
+//           x = dz of the 3x3 conv, x2 = dz of the 1x1 conv, output at twice the resolution
+//       7 = data-gradient of kind 3: a 4x4 s2 p1 conv of dz (at twice the resolution) -> input resolution
+//   (the data-gradient of kind 0 is kind 0 with flipped, transposed weights)
+static int fill_geometry(IgemmParams& p, int kind, const void* x, const void* x2, int batch, int hin, int win, int cin)
 {
-    int gh, gw;        // output grid the tiles cover (per parity class for the deconv)
+    int gh, gw;        // grid the pixel tiles cover (per output-parity class when n_par = 4)
     p.n_par = 1; p.out_mul = 1;
-    for (int a = 0; a < 4; ++a) for (int t = 0; t < 9; ++t) { p.tap_map[a][t] = 0; p.tap_dy[a][t] = 0; p.tap_dx[a][t] = 0; }
+    for (int a = 0; a < 4; ++a) {
+        p.n_taps[a] = 0;
+        for (int t = 0; t < 16; ++t) { p.tap_map[a][t] = 0; p.tap_dy[a][t] = 0; p.tap_dx[a][t] = 0; }
+    }
+    int rc;
     if (kind == 0) {
-        gh = hin; gw = win; p.n_taps = 9; p.hout = hin; p.wout = win;
-        int rc = make_act_map(&p.tmA[0], x, batch, hin, win, cin, 1, 0, 0); if (rc) return rc;
+        gh = hin; gw = win; p.n_taps[0] = 9; p.hout = hin; p.wout = win;
+        if ((rc = make_act_map(&p.tmA[0], x, batch, hin, win, cin, 1, 0, 0))) return rc;
         for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
         for (int r = 0; r < 3; ++r) for (int s = 0; s < 3; ++s) { p.tap_dy[0][r * 3 + s] = (int8_t)(r - 1); p.tap_dx[0][r * 3 + s] = (int8_t)(s - 1); }
     } else if (kind == 1 || kind == 2) {
         if (hin % 2 || win % 2) return fail(SCD_EINVAL, "stride-2 conv needs even input size");
         gh = hin / 2; gw = win / 2; p.hout = gh; p.wout = gw;
-        for (int py = 0; py < 2; ++py) for (int px = 0; px < 2; ++px) {
-            int rc = make_act_map(&p.tmA[py * 2 + px], x, batch, hin, win, cin, 2, py, px); if (rc) return rc;
-        }
-        if (kind == 2) { p.n_taps = 1; }
+        for (int py = 0; py < 2; ++py) for (int px = 0; px < 2; ++px)
+            if ((rc = make_act_map(&p.tmA[py * 2 + px], x, batch, hin, win, cin, 2, py, px))) return rc;
+        if (kind == 2) { p.n_taps[0] = 1; }
         else {
-            p.n_taps = 9;
+            p.n_taps[0] = 9;
             // input row 2*oy + r - 1: r=0 -> odd row of block oy-1, r=1 -> even row of block oy, r=2 -> odd row of block oy
             const int par_of[3] = {1, 0, 1}, off_of[3] = {-1, 0, 0};
             for (int r = 0; r < 3; ++r) for (int s = 0; s < 3; ++s) {
@@ -416,17 +396,55 @@ static int fill_geometry(IgemmParams& p, int kind, const void* x, int batch, int
             }
         }
     } else if (kind == 3) {
-        gh = hin; gw = win; p.hout = 2 * hin; p.wout = 2 * win; p.n_par = 4; p.out_mul = 2; p.n_taps = 4;
-        int rc = make_act_map(&p.tmA[0], x, batch, hin, win, cin, 1, 0, 0); if (rc) return rc;
+        gh = hin; gw = win; p.hout = 2 * hin; p.wout = 2 * win; p.n_par = 4; p.out_mul = 2;
+        if ((rc = make_act_map(&p.tmA[0], x, batch, hin, win, cin, 1, 0, 0))) return rc;
         for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
         // oy = 2*iy - 1 + kh.  even oy=2j: kh=1 -> iy=j, kh=3 -> iy=j-1;  odd oy=2j+1: kh=0 -> iy=j+1, kh=2 -> iy=j.
         // tap order inside a parity class = (a, b) with a, b in {0,1}: the host packs weights the same way
         const int dy_of[2][2] = {{0, -1}, {1, 0}};
-        for (int qy = 0; qy < 2; ++qy) for (int qx = 0; qx < 2; ++qx)
+        for (int qy = 0; qy < 2; ++qy) for (int qx = 0; qx < 2; ++qx) {
+            p.n_taps[qy * 2 + qx] = 4;
             for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) {
                 p.tap_dy[qy * 2 + qx][a * 2 + b] = (int8_t)dy_of[qy][a];
                 p.tap_dx[qy * 2 + qx][a * 2 + b] = (int8_t)dy_of[qx][b];
             }
+        }
+    } else if (kind == 5) {
+        // x = dz (B,hin,win,cin) of a 3x3 s2 conv; output (B,2hin,2win,cout) = gradient of that conv's input.
+        // iy = 2*oy + r - 1:  even iy=2j: r=1 -> oy=j;   odd iy=2j+1: r=0 -> oy=j+1, r=2 -> oy=j.
+        // class (qy,qx) taps = (a over y choices) x (b over x choices); class (0,0) gets one extra tap that
+        // reads x2 = dz of the parallel 1x1 s2 downsample conv (same resolution, same channel count).
+        gh = hin; gw = win; p.hout = 2 * hin; p.wout = 2 * win; p.n_par = 4; p.out_mul = 2;
+        if ((rc = make_act_map(&p.tmA[0], x, batch, hin, win, cin, 1, 0, 0))) return rc;
+        p.tmA[1] = p.tmA[0];
+        if (x2 && (rc = make_act_map(&p.tmA[1], x2, batch, hin, win, cin, 1, 0, 0))) return rc;
+        p.tmA[2] = p.tmA[0]; p.tmA[3] = p.tmA[0];
+        const int cnt[2] = {1, 2};
+        const int dyo[2][2] = {{0, 0}, {1, 0}};
+        for (int qy = 0; qy < 2; ++qy) for (int qx = 0; qx < 2; ++qx) {
+            const int c = qy * 2 + qx;
+            int t = 0;
+            for (int a = 0; a < cnt[qy]; ++a) for (int b = 0; b < cnt[qx]; ++b, ++t) {
+                p.tap_dy[c][t] = (int8_t)dyo[qy][a];
+                p.tap_dx[c][t] = (int8_t)dyo[qx][b];
+            }
+            if (c == 0 && x2) { p.tap_map[0][t] = 1; ++t; }
+            p.n_taps[c] = t;
+        }
+    } else if (kind == 7) {
+        // x = dz (B,hin,win,cin) at the deconv's OUTPUT resolution; output (B,hin/2,win/2,cout).
+        // dz row 2*iy - 1 + kh: kh=0 -> odd row of block iy-1, 1 -> even row of block iy, 2 -> odd row of block iy,
+        // 3 -> even row of block iy+1
+        if (hin % 2 || win % 2) return fail(SCD_EINVAL, "kind 7 needs even input size");
+        gh = hin / 2; gw = win / 2; p.hout = gh; p.wout = gw; p.n_taps[0] = 16;
+        const int par_of[4] = {1, 0, 1, 0}, off_of[4] = {-1, 0, 0, 1};
+        for (int py = 0; py < 2; ++py) for (int px = 0; px < 2; ++px)
+            if ((rc = make_act_map(&p.tmA[py * 2 + px], x, batch, hin, win, cin, 2, py, px))) return rc;
+        for (int kh = 0; kh < 4; ++kh) for (int kw = 0; kw < 4; ++kw) {
+            p.tap_map[0][kh * 4 + kw] = (int8_t)(par_of[kh] * 2 + par_of[kw]);
+            p.tap_dy[0][kh * 4 + kw] = (int8_t)off_of[kh];
+            p.tap_dx[0][kh * 4 + kw] = (int8_t)off_of[kw];
+        }
     } else {
         return fail(SCD_EINVAL, "unknown conv kind %d", kind);
     }
@@ -442,23 +460,25 @@ static int pick_bn(int cout) { return cout >= 256 ? 256 : (cout >= 128 ? 128 : 6
 
 }  // namespace scd
 
-extern "C" int scd_conv_igemm_fwd(int kind, const void* x, const void* weight, const float* bias,
-                                  const void* residual, int relu, int batch, int hin, int win,
-                                  int cin, int cout, void* y, void* stream)
+static int conv_igemm(int kind, const void* x, const void* x2, const void* weight, const float* bias,
+                      const void* residual, int relu, int batch, int hin, int win, int cin, int cout, void* y,
+                      void* stream)
 {
     using namespace scd;
     if (batch <= 0) return SCD_OK;
-    if (!x || !weight || !bias || !y) return fail(SCD_EINVAL, "scd_conv_igemm_fwd: null pointer");
+    if (!x || !weight || !bias || !y) return fail(SCD_EINVAL, "scd_conv_igemm: null pointer");
     IgemmParams p;
     memset(&p, 0, sizeof(p));
-    int rc = fill_geometry(p, kind, x, batch, hin, win, cin);
+    int rc = fill_geometry(p, kind, x, x2, batch, hin, win, cin);
     if (rc) return rc;
     const int bn = pick_bn(cout);
     if (cout % bn) return fail(SCD_EINVAL, "Cout = %d unsupported", cout);
     p.cout = cout; p.n_tiles_n = cout / bn; p.relu = relu;
     p.total_tiles = batch * p.n_par * p.tiles_y * p.tiles_x * p.n_tiles_n;
     p.bias = bias; p.residual = static_cast<const __nv_bfloat16*>(residual); p.out = static_cast<__nv_bfloat16*>(y);
-    rc = make_w_map(&p.tmB, weight, p.n_taps * cin, p.n_par * cout, bn);
+    int max_taps = 0;
+    for (int a = 0; a < p.n_par; ++a) max_taps = p.n_taps[a] > max_taps ? p.n_taps[a] : max_taps;
+    rc = make_w_map(&p.tmB, weight, max_taps * cin, p.n_par * cout, bn);   // rows = (class, cout), K = taps * cin
     if (rc) return rc;
     for (int par = 0; par < p.n_par; ++par) {
         rc = make_act_map(&p.tmOut[par], y, batch, p.hout, p.wout, cout, p.out_mul, par >> 1, par & 1, 2);
@@ -470,9 +490,27 @@ extern "C" int scd_conv_igemm_fwd(int kind, const void* x, const void* weight, c
     return launch_igemm<64, EPI_STORE>(p, st);
 }
 
-extern "C" int scd_heads_fwd(const void* x, const void* w3, const float* b3, const float* w1,
-                             const float* b1, int batch, int height, int width,
-                             float* heat, float* regr, float* offset, void* stream)
+extern "C" int scd_conv_igemm_fwd(int kind, const void* x, const void* weight, const float* bias,
+                                  const void* residual, int relu, int batch, int hin, int win,
+                                  int cin, int cout, void* y, void* stream)
+{
+    if (kind < 0 || kind > 3) return scd::fail(SCD_EINVAL, "scd_conv_igemm_fwd: kind must be 0..3");
+    return conv_igemm(kind, x, nullptr, weight, bias, residual, relu, batch, hin, win, cin, cout, y, stream);
+}
+
+extern "C" int scd_conv_igemm_dgrad(int kind, const void* dz, const void* dz2, const void* weight, const float* bias,
+                                    const void* add, int batch, int hin, int win, int cin, int cout, void* dx,
+                                    void* stream)
+{
+    // data gradient of forward kind `kind`; (hin, win, cin) describe dz, cout the channels of dx
+    const int k = kind == 0 ? 0 : (kind == 1 ? 5 : (kind == 3 ? 7 : -1));
+    if (k < 0) return scd::fail(SCD_EINVAL, "scd_conv_igemm_dgrad: kind must be 0, 1 or 3");
+    return conv_igemm(k, dz, dz2, weight, bias, add, 0, batch, hin, win, cin, cout, dx, stream);
+}
+
+static int heads_fwd(const void* x, const void* w3, const float* b3, const float* w1,
+                     const float* b1, int batch, int height, int width,
+                     float* heat, float* regr, float* offset, void* hidden, void* stream)
 {
     using namespace scd;
     if (batch <= 0) return SCD_OK;
@@ -480,12 +518,32 @@ extern "C" int scd_heads_fwd(const void* x, const void* w3, const float* b3, con
         return fail(SCD_EINVAL, "scd_heads_fwd: null pointer");
     IgemmParams p;
     memset(&p, 0, sizeof(p));
-    int rc = fill_geometry(p, 0, x, batch, height, width, 256);
+    int rc = fill_geometry(p, 0, x, nullptr, batch, height, width, 256);
     if (rc) return rc;
     p.cout = 384; p.n_tiles_n = 1; p.relu = 1;
     p.total_tiles = batch * p.tiles_y * p.tiles_x;
     p.bias = b3; p.w1 = w1; p.b1 = b1; p.heat = heat; p.regr = regr; p.off = offset;
     rc = make_w_map(&p.tmB, w3, 9 * 256, 384, IgemmCfg<384>::B_BOX_ROWS);
     if (rc) return rc;
+    if (hidden) {
+        if ((rc = make_act_map(&p.tmOut[0], hidden, batch, height, width, 384, 1, 0, 0, 2))) return rc;
+        return launch_igemm<384, EPI_HEADS_TRAIN>(p, (cudaStream_t)stream);
+    }
     return launch_igemm<384, EPI_HEADS>(p, (cudaStream_t)stream);
+}
+
+extern "C" int scd_heads_fwd(const void* x, const void* w3, const float* b3, const float* w1,
+                             const float* b1, int batch, int height, int width,
+                             float* heat, float* regr, float* offset, void* stream)
+{
+    return heads_fwd(x, w3, b3, w1, b1, batch, height, width, heat, regr, offset, nullptr, stream);
+}
+
+// training forward of the heads: additionally stores hidden = ReLU(conv3x3 + b3), (B,H,W,384) bf16 NHWC
+extern "C" int scd_heads_fwd_train(const void* x, const void* w3, const float* b3, const float* w1,
+                                   const float* b1, int batch, int height, int width,
+                                   float* heat, float* regr, float* offset, void* hidden, void* stream)
+{
+    if (!hidden) return scd::fail(SCD_EINVAL, "scd_heads_fwd_train: hidden is null");
+    return heads_fwd(x, w3, b3, w1, b1, batch, height, width, heat, regr, offset, hidden, stream);
 }

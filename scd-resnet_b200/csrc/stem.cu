@@ -13,6 +13,7 @@
 // hand), and 289 conv outputs x 64 channels take 12 tcgen05.mma (M=128, N=64, K=16) into TMEM.
 // The CUDA-core version of this stage cost 1.34 ms per 64-tile batch (32 % of the step).
 #include "tc.cuh"
+#include "tmap.cuh"
 
 namespace scd {
 
@@ -180,7 +181,132 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict_
     }
 }
 
-int make_w_map_2d(CUtensorMap* m, const void* base, int k_total, int rows, int box_rows);   // igemm.cu
+// ------------------------------------------------------------------------------------------------
+// Training variant: raw conv output z0 (B, H/2, W/2, 64) bf16 NHWC (BatchNorm needs batch statistics
+// before the ReLU / pool), plus the im2col operand itself, col0 (B, H/2, W/2, 64) bf16, so that the stem's
+// weight gradient is a plain pixel-contraction GEMM (wgrad.cu kind 4) with no second im2col pass.
+// CTA = 16 x 16 conv positions = two 8 x 16 M tiles; both outputs leave through TMA stores of the
+// swizzled shared-memory tiles (box {64, 16, 8, 1}).
+constexpr int SV_T = 16;
+constexpr int SV_PS = SV_T + 3;                               // 19 x 19 s2d pixels
+constexpr int SV_OFF_B = 2 * 16384;
+constexpr int SV_OFF_PATCH = SV_OFF_B + 8192;
+constexpr int SV_OFF_BAR = SV_OFF_PATCH + SV_PS * SV_PS * 8 + 64;
+constexpr int SV_SMEM = SV_OFF_BAR + 64 + 1024;
+
+__global__ void __launch_bounds__(ST_THREADS, 3)
+stem_conv_train_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmZ,
+                       const __grid_constant__ CUtensorMap tmCol, const float* __restrict__ x, int height, int width)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t sbase = (tc::smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* sgen = smem_dyn + (sbase - tc::smem_u32(smem_dyn));
+    const uint32_t bar_w = sbase + SV_OFF_BAR, bar_mma = bar_w + 8, bar_st = bar_w + 16, tmem_slot = bar_w + 24;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wc = width / 2;
+    const int tiles_x = wc / SV_T;
+    const int b = blockIdx.y;
+    const int cy0 = (blockIdx.x / tiles_x) * SV_T, cx0 = (blockIdx.x % tiles_x) * SV_T;
+    const int Y0 = cy0 - 2, X0 = cx0 - 2;
+
+    if (tid == 0) {
+        tc::mbar_init(bar_w, 1);
+        tc::mbar_init(bar_mma, 1);
+        tc::mbar_init(bar_st, 1);
+        tc::fence_barrier_init();
+        tc::mbar_arrive_expect_tx(bar_w, 8192);
+        tc::tma_load_2d(&tmW, bar_w, sbase + SV_OFF_B, 0, 0);
+    }
+    if (warp == 1) tc::tmem_alloc<128>(tmem_slot);
+    {
+        const float* xb = x + (size_t)b * height * width;
+        uint32_t* patch = reinterpret_cast<uint32_t*>(sgen + SV_OFF_PATCH);
+        for (int i = tid; i < 2 * SV_PS * SV_PS; i += ST_THREADS) {
+            const int X = i % SV_PS, ry = i / SV_PS;
+            const int iy = 2 * Y0 + ry, ix = 2 * (X0 + X);
+            float2 v = make_float2(0.f, 0.f);
+            if (iy >= 0 && iy < height && ix >= 0 && ix < width)
+                v = *reinterpret_cast<const float2*>(xb + (size_t)iy * width + ix);
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+            patch[((ry >> 1) * SV_PS + X) * 2 + (ry & 1)] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        if (tid < 16) patch[SV_PS * SV_PS * 2 + tid] = 0u;
+    }
+    __syncthreads();
+    {
+        const unsigned char* patch = sgen + SV_OFF_PATCH;
+        for (int it = tid; it < 256 * 8; it += ST_THREADS) {
+            const int j = it & 7, row = it >> 3;                      // row = r * 16 + c: M tile = rows 8m..8m+7
+            const int r = row >> 4, c = row & 15;
+            const int dy = j >> 1, dx0 = (j & 1) * 2;
+            const unsigned char* src = patch + ((r + dy) * SV_PS + c + dx0) * 8;
+            const uint2 lo = *reinterpret_cast<const uint2*>(src);
+            const uint2 hi = *reinterpret_cast<const uint2*>(src + 8);
+            *reinterpret_cast<uint4*>(sgen + row * 128 + ((j ^ (row & 7)) << 4)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+        }
+    }
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<const uint32_t*>(sgen + SV_OFF_BAR + 24);
+
+    if (tid == 0) {
+        tc::tma_store_4d(&tmCol, sbase, 0, cx0, cy0, b);              // the im2col operand, for the weight gradient
+        tc::tma_store_4d(&tmCol, sbase + 16384, 0, cx0, cy0 + 8, b);
+        tc::bulk_commit();
+        tc::mbar_wait(bar_w, 0);
+        tc::tc_fence_after();
+        constexpr uint32_t idesc = tc::umma_idesc_bf16(128, ST_CO);
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                tc::umma_bf16(tmem_base + m * ST_CO, tc::umma_desc_sw128(sbase + m * 16384 + k * 32),
+                              tc::umma_desc_sw128(sbase + SV_OFF_B + k * 32), idesc, k ? 1u : 0u);
+        tc::umma_commit(bar_mma);
+        tc::bulk_wait_read0();                                         // the col0 stores have read the tiles
+        tc::mbar_arrive(bar_st);
+    }
+    __syncwarp();
+    tc::mbar_wait(bar_mma, 0);
+    tc::mbar_wait(bar_st, 0);
+    tc::tc_fence_after();
+    {
+        const int q = warp & 3, m = warp >> 2;
+        const int row = m * 128 + q * 32 + lane;
+        uint32_t r0[32], r1[32];
+        const uint32_t taddr = tmem_base + m * ST_CO + ((uint32_t)(q * 32) << 16);
+        tc::tmem_ld32(taddr, r0);
+        tc::tmem_ld32(taddr + 32, r1);
+        tc::tmem_ld_wait();
+        unsigned char* dst = sgen + row * 128;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+            __align__(16) __nv_bfloat162 o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int cidx = ch * 8 + 2 * i;
+                o[i] = __floats2bfloat162_rn(__uint_as_float(cidx < 32 ? r0[cidx] : r1[cidx - 32]),
+                                             __uint_as_float(cidx < 32 ? r0[cidx + 1] : r1[cidx - 31]));
+            }
+            *reinterpret_cast<uint4*>(dst + ((ch ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(o);
+        }
+    }
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        tc::tma_store_4d(&tmZ, sbase, 0, cx0, cy0, b);
+        tc::tma_store_4d(&tmZ, sbase + 16384, 0, cx0, cy0 + 8, b);
+        tc::bulk_commit();
+        tc::bulk_wait0();
+    }
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc<128>(tmem_base);
+    }
+}
 
 }  // namespace scd
 
@@ -193,7 +319,7 @@ extern "C" int scd_stem_fwd(const float* x, const void* weight, const float* bia
     if (height % (4 * ST_P) != 0 || width % (4 * ST_P) != 0)
         return fail(SCD_EINVAL, "scd_stem_fwd: H and W must be multiples of %d (got %dx%d)", 4 * ST_P, height, width);
     CUtensorMap tmW;
-    int rc = make_w_map_2d(&tmW, weight, 64, 64, 64);
+    int rc = make_w_map(&tmW, weight, 64, 64, 64);
     if (rc) return rc;
     static bool attr_done = false;
     if (!attr_done) {
@@ -204,5 +330,29 @@ extern "C" int scd_stem_fwd(const float* x, const void* weight, const float* bia
     stem_tc_kernel<<<grid, ST_THREADS, ST_SMEM, (cudaStream_t)stream>>>(
         tmW, x, bias, height, width, reinterpret_cast<__nv_bfloat16*>(y));
     SCD_LAUNCH_CHECK("stem_tc_kernel");
+    return SCD_OK;
+}
+
+extern "C" int scd_stem_conv_train(const float* x, const void* weight, int batch, int height, int width,
+                                   void* z0, void* col0, void* stream)
+{
+    using namespace scd;
+    if (batch <= 0) return SCD_OK;
+    if (!x || !weight || !z0 || !col0) return fail(SCD_EINVAL, "scd_stem_conv_train: null pointer");
+    if (height % (2 * SV_T) != 0 || width % (2 * SV_T) != 0)
+        return fail(SCD_EINVAL, "scd_stem_conv_train: H and W must be multiples of %d", 2 * SV_T);
+    CUtensorMap tmW, tmZ, tmCol;
+    int rc;
+    if ((rc = make_w_map(&tmW, weight, 64, 64, 64))) return rc;
+    if ((rc = make_act_map(&tmZ, z0, batch, height / 2, width / 2, 64, 1, 0, 0, 8))) return rc;
+    if ((rc = make_act_map(&tmCol, col0, batch, height / 2, width / 2, 64, 1, 0, 0, 8))) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SCD_CUDA_CHECK(cudaFuncSetAttribute(stem_conv_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SV_SMEM));
+        attr_done = true;
+    }
+    dim3 grid((height / 2 / SV_T) * (width / 2 / SV_T), batch);
+    stem_conv_train_kernel<<<grid, ST_THREADS, SV_SMEM, (cudaStream_t)stream>>>(tmW, tmZ, tmCol, x, height, width);
+    SCD_LAUNCH_CHECK("stem_conv_train_kernel");
     return SCD_OK;
 }

@@ -1,0 +1,311 @@
+// Training-only bandwidth kernels around the tensor-core GEMMs.
+//
+//   stem_bn_relu_pool      z0 (B,256,256,64) -> a0 = maxpool3x3s2(relu(bn(z0)))          (residuals.py:212-214)
+//   stem_pool_bwd          d a0 -> dy0 = gradient at relu(bn(z0)), ReLU mask applied       (their autograd)
+//   heads_bwd              d heat/regr/offset + hidden -> d hidden, d w1, d b1, d b3       (centerNetOffset.py:106-110)
+//   adam_step              fused Adam over the flat parameter buffer (torch.optim.Adam defaults, networkFactory.py:80-82)
+//   gather_cast            bf16 GEMM-operand copies of the fp32 master weights
+//   scale_inplace          x *= s (upstream-gradient scaling of the fused loss gradients)
+#include "common.cuh"
+
+namespace scd {
+
+__device__ __forceinline__ void unpack8f(const uint4& u, float (&f)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { f[2 * i] = __low2float(h[i]); f[2 * i + 1] = __high2float(h[i]); }
+}
+__device__ __forceinline__ uint4 pack8f(const float (&f)[8]) {
+    __align__(16) __nv_bfloat162 h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return *reinterpret_cast<const uint4*>(h);
+}
+
+// thread = (pool pixel, 8 channels); z0 is NHWC with 64 channels at (hc, wc) = 2 x (hp, wp)
+__global__ void __launch_bounds__(256)
+stem_bn_relu_pool_kernel(const uint4* __restrict__ z0, const float* __restrict__ scale,
+                         const float* __restrict__ shift, int batch, int hp, int wp, uint4* __restrict__ a0)
+{
+    const size_t total = (size_t)batch * hp * wp * 8;
+    const int hc = 2 * hp, wc = 2 * wp;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i & 7);
+        size_t r = i >> 3;
+        const int px = (int)(r % wp); r /= wp;
+        const int py = (int)(r % hp);
+        const int b = (int)(r / hp);
+        float sc[8], sh[8], m[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { sc[k] = __ldg(scale + g * 8 + k); sh[k] = __ldg(shift + g * 8 + k); m[k] = 0.f; }
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int cy = 2 * py + dy, cx = 2 * px + dx;
+                if (cy < 0 || cy >= hc || cx < 0 || cx >= wc) continue;      // -inf padding; relu output >= 0
+                float zf[8];
+                unpack8f(__ldg(z0 + (((size_t)b * hc + cy) * wc + cx) * 8 + g), zf);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], fmaf(zf[k], sc[k], sh[k]));
+            }
+        a0[i] = pack8f(m);
+    }
+}
+
+// thread = (conv pixel, 8 channels).  A conv position receives the gradient of every pool window in which it
+// is the first maximum in row-major window order (PyTorch's max_pool2d rule); positions with y <= 0 get 0
+// (ReLU).  Even rows/cols sit in one window, odd ones in two.
+__global__ void __launch_bounds__(256)
+stem_pool_bwd_kernel(const uint4* __restrict__ z0, const float* __restrict__ scale, const float* __restrict__ shift,
+                     const uint4* __restrict__ da0, int batch, int hp, int wp, uint4* __restrict__ dy0)
+{
+    const int hc = 2 * hp, wc = 2 * wp;
+    const size_t total = (size_t)batch * hc * wc * 8;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i & 7);
+        size_t r = i >> 3;
+        const int cx = (int)(r % wc); r /= wc;
+        const int cy = (int)(r % hc);
+        const int b = (int)(r / hc);
+        float sc[8], sh[8], self[8], out[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { sc[k] = __ldg(scale + g * 8 + k); sh[k] = __ldg(shift + g * 8 + k); out[k] = 0.f; }
+        {
+            float zf[8];
+            unpack8f(__ldg(z0 + i), zf);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) self[k] = fmaf(zf[k], sc[k], sh[k]);
+        }
+        const int py_lo = cy >> 1, py_hi = (cy + 1) >> 1;       // equal when cy is even
+        const int px_lo = cx >> 1, px_hi = (cx + 1) >> 1;
+        for (int py = py_lo; py <= py_hi; ++py) {
+            if (py >= hp) continue;
+            for (int px = px_lo; px <= px_hi; ++px) {
+                if (px >= wp) continue;
+                bool win[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) win[k] = self[k] > 0.f;
+                for (int dy = -1; dy <= 1; ++dy)
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        const int y = 2 * py + dy, x = 2 * px + dx;
+                        if (y < 0 || y >= hc || x < 0 || x >= wc || (y == cy && x == cx)) continue;
+                        const bool earlier = (y < cy) || (y == cy && x < cx);
+                        float zf[8];
+                        unpack8f(__ldg(z0 + (((size_t)b * hc + y) * wc + x) * 8 + g), zf);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const float v = fmaf(zf[k], sc[k], sh[k]);
+                            if (v > self[k] || (earlier && v == self[k])) win[k] = false;
+                        }
+                    }
+                float df[8];
+                unpack8f(__ldg(da0 + (((size_t)b * hp + py) * wp + px) * 8 + g), df);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) out[k] += win[k] ? df[k] : 0.f;
+            }
+        }
+        dy0[i] = pack8f(out);
+    }
+}
+
+// heads backward through Conv1x1 and the hidden ReLU.  block = 8 pixels x 48 channel groups (8 channels each).
+// hidden [pix][384] bf16; heads own channels [0,128) heatmap, [128,256) regr, [256,384) offset;
+// w1 (7,128) f32 rows: heatmap, regr x4, offset x2.
+__global__ void __launch_bounds__(384)
+heads_bwd_kernel(const float* __restrict__ d_heat, const float* __restrict__ d_regr, const float* __restrict__ d_off,
+                 const uint4* __restrict__ hidden, const float* __restrict__ w1, size_t pixels, size_t hw,
+                 uint4* __restrict__ d_hidden, float* __restrict__ g_w1, float* __restrict__ g_b1,
+                 float* __restrict__ g_b3)
+{
+    __shared__ float s_red[8][48][8];            // one 8-channel quantity at a time across the 8 pixel lanes
+    __shared__ float s_db1[8][8];
+    const int g = threadIdx.x % 48, pl = threadIdx.x / 48;
+    const int head = g / 16;                     // 0: heatmap, 1: regr, 2: offset
+    const int j0 = head == 0 ? 0 : (head == 1 ? 1 : 5), nj = head == 0 ? 1 : (head == 1 ? 4 : 2);
+    const int hc = (g % 16) * 8;                 // channel inside the head
+    float w[4][8], acc_b3[8], acc_w[4][8], acc_b1[7];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { w[j][k] = j < nj ? __ldg(w1 + (j0 + j) * 128 + hc + k) : 0.f; acc_w[j][k] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc_b3[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) acc_b1[j] = 0.f;
+    for (size_t p = (size_t)blockIdx.x * 8 + pl; p < pixels; p += (size_t)gridDim.x * 8) {
+        const size_t b = p / hw, s = p % hw;
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        if (head == 0) d[0] = __ldg(d_heat + p);
+        else if (head == 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[j] = __ldg(d_regr + (b * 4 + j) * hw + s);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) d[j] = __ldg(d_off + (b * 2 + j) * hw + s);
+        }
+        if (g % 16 == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (j < nj) acc_b1[j0 + j] += d[j];
+        }
+        float hf[8], o[8];
+        unpack8f(__ldg(hidden + p * 48 + g), hf);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float t = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) t = fmaf(d[j], w[j][k], t);
+            o[k] = hf[k] > 0.f ? t : 0.f;                       // ReLU mask of the hidden activation
+            acc_b3[k] += o[k];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc_w[j][k] = fmaf(d[j], hf[k], acc_w[j][k]);
+        }
+        d_hidden[p * 48 + g] = pack8f(o);
+    }
+    if (g % 16 == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (j < nj) s_db1[pl][j0 + j] = acc_b1[j0 + j];
+    }
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {                // c = 0: d b3, c = 1..4: d w1 rows j0 + c - 1
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s_red[pl][g][k] = (c == 0) ? acc_b3[k] : acc_w[c == 0 ? 0 : c - 1][k];
+        __syncthreads();
+        if (pl == 0 && (c == 0 || c - 1 < nj)) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float t = 0.f;
+#pragma unroll
+                for (int l = 0; l < 8; ++l) t += s_red[l][g][k];
+                if (c == 0) atomicAdd(g_b3 + g * 8 + k, t);
+                else atomicAdd(g_w1 + (j0 + c - 1) * 128 + hc + k, t);
+            }
+        }
+        __syncthreads();
+    }
+    if (pl == 0 && g % 16 == 0) {
+        for (int j = 0; j < nj; ++j) {
+            float v = 0.f;
+            for (int l = 0; l < 8; ++l) v += s_db1[l][j0 + j];
+            atomicAdd(g_b1 + j0 + j, v);
+        }
+    }
+}
+
+// torch.optim.Adam (defaults: betas (0.9, 0.999), eps 1e-8, no weight decay, no amsgrad), one fused pass.
+// grad index: g = gmap ? G[gmap[i]] : G[i]  (the wgrad kernels write their own layout)
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ G,
+            const int* __restrict__ gmap, size_t n, float lr, float beta1, float beta2, float eps,
+            float bc1, float bc2_sqrt, float gscale)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float g = (gmap ? G[gmap[i]] : G[i]) * gscale;
+        const float mi = beta1 * m[i] + (1.f - beta1) * g;
+        const float vi = beta2 * v[i] + (1.f - beta2) * g * g;
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] -= (lr / bc1) * (mi / denom);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gather_cast_kernel(const float* __restrict__ src, const int* __restrict__ idx, size_t n, __nv_bfloat16* __restrict__ dst)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int j = idx[i];
+        dst[i] = __float2bfloat16_rn(j >= 0 ? src[j] : 0.f);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+scale_kernel(float* __restrict__ x, size_t n, const float* __restrict__ s)
+{
+    const float f = *s;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] *= f;
+}
+
+static inline int sgrid(size_t items, int per_block) {
+    size_t want = (items + per_block - 1) / per_block;
+    const size_t cap = (size_t)kNumSMs * 8;
+    if (want > cap) want = cap;
+    return (int)(want < 1 ? 1 : want);
+}
+
+}  // namespace scd
+
+extern "C" int scd_stem_bn_relu_pool(const void* z0, const float* scale, const float* shift, int batch, int hp, int wp,
+                                     void* a0, void* stream)
+{
+    using namespace scd;
+    if (!z0 || !scale || !shift || !a0) return fail(SCD_EINVAL, "scd_stem_bn_relu_pool: null pointer");
+    const size_t total = (size_t)batch * hp * wp * 8;
+    stem_bn_relu_pool_kernel<<<sgrid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const uint4*>(z0), scale, shift, batch, hp, wp, static_cast<uint4*>(a0));
+    SCD_LAUNCH_CHECK("stem_bn_relu_pool_kernel");
+    return SCD_OK;
+}
+
+extern "C" int scd_stem_pool_bwd(const void* z0, const float* scale, const float* shift, const void* da0, int batch,
+                                 int hp, int wp, void* dy0, void* stream)
+{
+    using namespace scd;
+    if (!z0 || !scale || !shift || !da0 || !dy0) return fail(SCD_EINVAL, "scd_stem_pool_bwd: null pointer");
+    const size_t total = (size_t)batch * hp * wp * 4 * 8;
+    stem_pool_bwd_kernel<<<sgrid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const uint4*>(z0), scale, shift, static_cast<const uint4*>(da0), batch, hp, wp,
+        static_cast<uint4*>(dy0));
+    SCD_LAUNCH_CHECK("stem_pool_bwd_kernel");
+    return SCD_OK;
+}
+
+extern "C" int scd_heads_bwd(const float* d_heat, const float* d_regr, const float* d_off, const void* hidden,
+                             const float* w1, int batch, int height, int width, void* d_hidden, float* g_w1,
+                             float* g_b1, float* g_b3, void* stream)
+{
+    using namespace scd;
+    if (!d_heat || !d_regr || !d_off || !hidden || !w1 || !d_hidden || !g_w1 || !g_b1 || !g_b3)
+        return fail(SCD_EINVAL, "scd_heads_bwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    SCD_CUDA_CHECK(cudaMemsetAsync(g_w1, 0, 7 * 128 * sizeof(float), st));
+    SCD_CUDA_CHECK(cudaMemsetAsync(g_b1, 0, 7 * sizeof(float), st));
+    SCD_CUDA_CHECK(cudaMemsetAsync(g_b3, 0, 384 * sizeof(float), st));
+    const size_t pixels = (size_t)batch * height * width;
+    heads_bwd_kernel<<<sgrid(pixels, 8 * 8), 384, 0, st>>>(d_heat, d_regr, d_off, static_cast<const uint4*>(hidden), w1,
+                                                          pixels, (size_t)height * width, static_cast<uint4*>(d_hidden),
+                                                          g_w1, g_b1, g_b3);
+    SCD_LAUNCH_CHECK("heads_bwd_kernel");
+    return SCD_OK;
+}
+
+extern "C" int scd_adam_step(float* params, float* exp_avg, float* exp_avg_sq, const float* grads, const int* gmap,
+                             size_t n, int step, float lr, float beta1, float beta2, float eps, float grad_scale,
+                             void* stream)
+{
+    using namespace scd;
+    if (!params || !exp_avg || !exp_avg_sq || !grads || step < 1) return fail(SCD_EINVAL, "scd_adam_step: bad arguments");
+    const float bc1 = 1.f - powf(beta1, (float)step);
+    const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+    adam_kernel<<<sgrid(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(params, exp_avg, exp_avg_sq, grads, gmap, n, lr,
+                                                                     beta1, beta2, eps, bc1, bc2s, grad_scale);
+    SCD_LAUNCH_CHECK("adam_kernel");
+    return SCD_OK;
+}
+
+extern "C" int scd_gather_cast_bf16(const float* src, const int* idx, size_t n, void* dst, void* stream)
+{
+    using namespace scd;
+    if (!src || !idx || !dst) return fail(SCD_EINVAL, "scd_gather_cast_bf16: null pointer");
+    gather_cast_kernel<<<sgrid(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(src, idx, n, static_cast<__nv_bfloat16*>(dst));
+    SCD_LAUNCH_CHECK("gather_cast_kernel");
+    return SCD_OK;
+}
+
+extern "C" int scd_scale_inplace(float* x, size_t n, const float* d_scale, void* stream)
+{
+    using namespace scd;
+    if (!x || !d_scale) return fail(SCD_EINVAL, "scd_scale_inplace: null pointer");
+    scale_kernel<<<sgrid(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(x, n, d_scale);
+    SCD_LAUNCH_CHECK("scale_kernel");
+    return SCD_OK;
+}

@@ -1,0 +1,271 @@
+// Weight-gradient GEMM on tcgen05 tensor cores (sm_100a).
+//
+// Replaces the autograd wgrad of every Conv2d / ConvTranspose2d on the training path (the
+// backward of ref: models/backbones/residuals.py:100-120,259-263,298-307 and
+// models/centerNetOffset.py:103-110, reached through loss.backward() at models/networkFactory.py:261).
+//
+//   D[(tap, cs), cp] = sum over pixels (n, y, x) of  S_tap[n, y + dy_tap, x + dx_tap, cs] * P[n, y, x, cp]
+//
+// S is the tensor that is read shifted per filter tap (the layer input for a conv, the output gradient
+// for a transposed conv), P the one read in place.  The contraction runs over PIXELS, and both tensors
+// are NHWC bf16, i.e. channel-contiguous: both UMMA operands are MN-major.  A TMA box {64 ch, 16 x, 4 y}
+// lands as 64 pixel rows of 128 B (128-byte swizzle) = the canonical MN-major tile with K = 64 pixels;
+// 64-channel blocks sit 8 KB apart (descriptor LBO), 8-pixel groups 1 KB apart (SBO).  The tap shift
+// and the conv zero padding are again just TMA coordinates.
+//
+// M tile = two (tap, 64-channel) chunks of S, N tile = up to 256 channels of P, the pixel range of a
+// work unit is one of `splits` interleaved slices (split-K); partial tiles are accumulated into the fp32
+// gradient buffer with coalesced red.global.add.  Same warp roles as igemm.cu.
+#include "tc.cuh"
+#include "tmap.cuh"
+
+namespace scd {
+
+constexpr int WG_THREADS = 192;
+constexpr int WG_KPIX = 64;                    // pixels per k-tile: 4 rows x 16 cols
+constexpr int WG_TH = 4;
+constexpr int WG_CHUNK_BYTES = WG_KPIX * 128;  // 8 KB: 64 pixel rows x 64 channels bf16
+constexpr int WG_STAGES = 4;
+constexpr int WG_STAGE_BYTES = 6 * WG_CHUNK_BYTES;      // 2 S chunks + up to 4 P chunks
+constexpr int WG_OFF_BAR = WG_STAGES * WG_STAGE_BYTES;
+constexpr int WG_SMEM = WG_OFF_BAR + 256 + 1024;
+
+struct alignas(64) WgradParams {
+    CUtensorMap tmS[4];
+    CUtensorMap tmP;
+    int n_taps, cs_blocks, n_chunks, m_tiles, n_tiles, bn_chunks;
+    int tiles_x, tiles_y, batch, splits, cp, total_units;
+    int8_t tap_map[16], tap_dy[16], tap_dx[16];
+    float* out;                                // [2 * m_tiles][cp][64] fp32
+};
+
+// MN-major operand, 128-byte swizzle: LBO = distance between 64-element MN blocks, SBO = 1024 B between
+// 8-row K groups (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
+           ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_kernel(const __grid_constant__ WgradParams p)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t smem_base = (tc::smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* smem_gen = smem_dyn + (smem_base - tc::smem_u32(smem_dyn));
+    const uint32_t bar_base = smem_base + WG_OFF_BAR;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (WG_STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * WG_STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * WG_STAGES + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * WG_STAGES + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < WG_STAGES; ++s) { tc::mbar_init(full_bar(s), 1); tc::mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(tfull_bar(s), 1); tc::mbar_init(tempty_bar(s), 128); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc<512>(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<const uint32_t*>(smem_gen + WG_OFF_BAR + 8 * (2 * WG_STAGES + 4));
+
+    const int bn = p.bn_chunks * 64;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const int k_tiles = p.batch * tiles_per_img;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t bytes = (uint32_t)(2 + p.bn_chunks) * WG_CHUNK_BYTES;
+            for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+                const int split = u % p.splits;
+                const int rest = u / p.splits;
+                const int nt = rest % p.n_tiles, mt = rest / p.n_tiles;
+                int c0 = 2 * mt, c1 = 2 * mt + 1;
+                if (c1 >= p.n_chunks) c1 = p.n_chunks - 1;          // padded chunk: any valid source
+                const int tap0 = c0 / p.cs_blocks, csb0 = c0 % p.cs_blocks;
+                const int tap1 = c1 / p.cs_blocks, csb1 = c1 % p.cs_blocks;
+                for (int kt = split; kt < k_tiles; kt += p.splits) {
+                    const int img = kt / tiles_per_img;
+                    const int r = kt % tiles_per_img;
+                    const int ty = r / p.tiles_x, tx = r % p.tiles_x;
+                    tc::mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sa = smem_base + stage * WG_STAGE_BYTES;
+                    const uint32_t sb = sa + 2 * WG_CHUNK_BYTES;
+                    tc::mbar_arrive_expect_tx(full_bar(stage), bytes);
+                    tc::tma_load_4d(&p.tmS[p.tap_map[tap0]], full_bar(stage), sa, csb0 * 64,
+                                    tx * TM_TW + p.tap_dx[tap0], ty * WG_TH + p.tap_dy[tap0], img);
+                    tc::tma_load_4d(&p.tmS[p.tap_map[tap1]], full_bar(stage), sa + WG_CHUNK_BYTES, csb1 * 64,
+                                    tx * TM_TW + p.tap_dx[tap1], ty * WG_TH + p.tap_dy[tap1], img);
+                    for (int i = 0; i < p.bn_chunks; ++i)
+                        tc::tma_load_4d(&p.tmP, full_bar(stage), sb + i * WG_CHUNK_BYTES,
+                                        (nt * p.bn_chunks + i) * 64, tx * TM_TW, ty * WG_TH, img);
+                    if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // kind::f16, bf16 x bf16 -> fp32, A and B MN-major (bits 15, 16), M = 128, N = bn
+            const uint32_t idesc = tc::umma_idesc_bf16(128, bn) | (1u << 15) | (1u << 16);
+            int stage = 0; uint32_t phase = 0, it = 0;
+            for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
+                const int split = u % p.splits;
+                const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+                tc::mbar_wait(tempty_bar(as), aphase ^ 1u);
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 256;
+                uint32_t first = 1;
+                for (int kt = split; kt < k_tiles; kt += p.splits) {
+                    tc::mbar_wait(full_bar(stage), phase);
+                    tc::tc_fence_after();
+                    const uint32_t sa = smem_base + stage * WG_STAGE_BYTES;
+                    const uint32_t sb = sa + 2 * WG_CHUNK_BYTES;
+#pragma unroll
+                    for (int k = 0; k < WG_KPIX / 16; ++k) {
+                        tc::umma_bf16(d_tmem, umma_desc_mn_sw128(sa + k * 2048, WG_CHUNK_BYTES),
+                                      umma_desc_mn_sw128(sb + k * 2048, WG_CHUNK_BYTES), idesc, (first && k == 0) ? 0u : 1u);
+                    }
+                    first = 0;
+                    tc::umma_commit(empty_bar(stage));
+                    if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+                }
+                tc::umma_commit(tfull_bar(as));
+            }
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                   // row of the M tile: chunk = row / 64, channel = row % 64
+        uint32_t it = 0;
+        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
+            const int rest = u / p.splits;
+            const int nt = rest % p.n_tiles, mt = rest / p.n_tiles;
+            const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+            tc::mbar_wait(tfull_bar(as), aphase);
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
+            const int chunk = 2 * mt + (row >> 6);
+            // out[chunk][cp][64]: the 32 lanes of a warp hit 32 consecutive floats per column
+            float* obase = p.out + ((size_t)chunk * p.cp + (size_t)nt * bn) * 64 + (row & 63);
+            const bool live = chunk < p.n_chunks;
+#pragma unroll 1
+            for (int c0 = 0; c0 < bn; c0 += 32) {
+                uint32_t r[32];
+                tc::tmem_ld32(taddr + c0, r);
+                tc::tmem_ld_wait();
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(obase + (size_t)(c0 + i) * 64),
+                                     "f"(__uint_as_float(r[i])) : "memory");
+                }
+            }
+            tc::tc_fence_before();
+            tc::mbar_arrive(tempty_bar(as));
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace scd
+
+// kind: 0 = conv3x3 s1 p1, 1 = conv3x3 s2 p1, 2 = conv1x1 s2, 3 = ConvTranspose 4x4 s2 p1, 4 = 1x1 s1 (stem im2col).
+// conv (0-2): S = layer input a (B,Hin,Win,Cin), P = output gradient dz (B,Ho,Wo,Cout); taps as in the forward.
+//             out[(t*Cin/64 + ci/64)][co][ci%64]
+// deconv (3): S = output gradient dz (B,2Hin,2Win,Cout) read through parity views, P = layer input a
+//             (B,Hin,Win,Cin); 16 taps t = kh*4 + kw.   out[(t*Cout/64 + co/64)][ci][co%64]
+extern "C" size_t scd_conv_wgrad_out_floats(int kind, int cin, int cout)
+{
+    const int taps = (kind == 2 || kind == 4) ? 1 : (kind == 3 ? 16 : 9);
+    const int cs = kind == 3 ? cout : cin, cp = kind == 3 ? cin : cout;
+    const int chunks = taps * (cs / 64);
+    return (size_t)((chunks + 1) / 2 * 2) * cp * 64;
+}
+
+extern "C" int scd_conv_wgrad(int kind, const void* a_in, const void* dz, int batch, int hin, int win,
+                              int cin, int cout, float* out, void* stream)
+{
+    using namespace scd;
+    if (batch <= 0) return SCD_OK;
+    if (!a_in || !dz || !out) return fail(SCD_EINVAL, "scd_conv_wgrad: null pointer");
+    if (cin % 64 || cout % 64) return fail(SCD_EINVAL, "scd_conv_wgrad: channels must be multiples of 64");
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    int gh, gw, rc;
+    if (kind == 0) {
+        gh = hin; gw = win; p.n_taps = 9;
+        if ((rc = make_act_map(&p.tmS[0], a_in, batch, hin, win, cin, 1, 0, 0, WG_TH))) return rc;
+        for (int r = 0; r < 3; ++r) for (int s = 0; s < 3; ++s) { p.tap_dy[r * 3 + s] = (int8_t)(r - 1); p.tap_dx[r * 3 + s] = (int8_t)(s - 1); }
+        if ((rc = make_act_map(&p.tmP, dz, batch, gh, gw, cout, 1, 0, 0, WG_TH))) return rc;
+    } else if (kind == 1 || kind == 2) {
+        gh = hin / 2; gw = win / 2;
+        for (int py = 0; py < 2; ++py) for (int px = 0; px < 2; ++px)
+            if ((rc = make_act_map(&p.tmS[py * 2 + px], a_in, batch, hin, win, cin, 2, py, px, WG_TH))) return rc;
+        if (kind == 2) p.n_taps = 1;
+        else {
+            p.n_taps = 9;
+            const int par_of[3] = {1, 0, 1}, off_of[3] = {-1, 0, 0};
+            for (int r = 0; r < 3; ++r) for (int s = 0; s < 3; ++s) {
+                p.tap_map[r * 3 + s] = (int8_t)(par_of[r] * 2 + par_of[s]);
+                p.tap_dy[r * 3 + s] = (int8_t)off_of[r];
+                p.tap_dx[r * 3 + s] = (int8_t)off_of[s];
+            }
+        }
+        if ((rc = make_act_map(&p.tmP, dz, batch, gh, gw, cout, 1, 0, 0, WG_TH))) return rc;
+    } else if (kind == 3) {
+        gh = hin; gw = win; p.n_taps = 16;
+        // dz row 2*iy - 1 + kh:  kh=0 -> odd row of block iy-1, 1 -> even row of block iy, 2 -> odd row of block iy,
+        // 3 -> even row of block iy+1
+        const int par_of[4] = {1, 0, 1, 0}, off_of[4] = {-1, 0, 0, 1};
+        for (int py = 0; py < 2; ++py) for (int px = 0; px < 2; ++px)
+            if ((rc = make_act_map(&p.tmS[py * 2 + px], dz, batch, 2 * hin, 2 * win, cout, 2, py, px, WG_TH))) return rc;
+        for (int kh = 0; kh < 4; ++kh) for (int kw = 0; kw < 4; ++kw) {
+            p.tap_map[kh * 4 + kw] = (int8_t)(par_of[kh] * 2 + par_of[kw]);
+            p.tap_dy[kh * 4 + kw] = (int8_t)off_of[kh];
+            p.tap_dx[kh * 4 + kw] = (int8_t)off_of[kw];
+        }
+        if ((rc = make_act_map(&p.tmP, a_in, batch, hin, win, cin, 1, 0, 0, WG_TH))) return rc;
+    } else if (kind == 4) {
+        // plain pixel contraction, one tap, no shift: the stem (S = im2col operand col0, P = dz0)
+        gh = hin; gw = win; p.n_taps = 1;
+        if ((rc = make_act_map(&p.tmS[0], a_in, batch, hin, win, cin, 1, 0, 0, WG_TH))) return rc;
+        if ((rc = make_act_map(&p.tmP, dz, batch, hin, win, cout, 1, 0, 0, WG_TH))) return rc;
+    } else {
+        return fail(SCD_EINVAL, "scd_conv_wgrad: unknown kind %d", kind);
+    }
+    if (gh % WG_TH || gw % TM_TW) return fail(SCD_EINVAL, "scd_conv_wgrad: grid %dx%d not a multiple of 4x16", gh, gw);
+    const int cs = kind == 3 ? cout : cin, cp = kind == 3 ? cin : cout;
+    p.cs_blocks = cs / 64;
+    p.n_chunks = p.n_taps * p.cs_blocks;
+    p.m_tiles = (p.n_chunks + 1) / 2;
+    p.cp = cp;
+    p.bn_chunks = cp % 256 == 0 ? 4 : (cp % 192 == 0 ? 3 : (cp % 128 == 0 ? 2 : 1));
+    p.n_tiles = cp / (p.bn_chunks * 64);
+    p.tiles_x = gw / TM_TW; p.tiles_y = gh / WG_TH; p.batch = batch;
+    const int k_tiles = batch * p.tiles_x * p.tiles_y;
+    const int out_tiles = p.m_tiles * p.n_tiles;
+    int splits = (kNumSMs + out_tiles - 1) / out_tiles;          // about one work unit per SM ...
+    if (splits > k_tiles / 8) splits = k_tiles / 8;              // ... but at least 8 k-tiles per unit
+    if (splits < 1) splits = 1;
+    p.splits = splits;
+    p.total_units = out_tiles * splits;
+    p.out = out;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SCD_CUDA_CHECK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+        attr_done = true;
+    }
+    const int grid = p.total_units < kNumSMs ? p.total_units : kNumSMs;
+    wgrad_kernel<<<grid, WG_THREADS, WG_SMEM, (cudaStream_t)stream>>>(p);
+    SCD_LAUNCH_CHECK("wgrad_kernel");
+    return SCD_OK;
+}

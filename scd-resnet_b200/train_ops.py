@@ -1,0 +1,151 @@
+"""Tensor-facing wrappers of the training entry points of the C ABI (include/scd_b200.h, second half)."""
+import ctypes
+
+import torch
+
+from ._lib import lib, check, ScdError
+from .ops import _ptr, _stream, _req
+
+BN_EPS, BN_MOMENTUM = 1e-5, 0.1     # ref: torch BatchNorm2d default eps; models/backbones/residuals.py:30
+
+
+def bn_forward(z, gamma, beta, running_mean=None, running_var=None, num_batches=None, residual=None, relu=True,
+               out=None, all_reduce=None):
+    """Train-mode BN (+residual)(+ReLU) on z (B,H,W,C) bf16 NHWC.  Returns (a, ctx); ctx is what the backward
+    needs.  `all_reduce(t)` (optional) sums the fp64 statistics across ranks = SyncBatchNorm."""
+    z = _req(z, torch.bfloat16, "z")
+    C = z.shape[-1]
+    pixels = z.numel() // C
+    dev = z.device
+    sums = torch.empty(2 * C, dtype=torch.float64, device=dev)
+    stat = torch.empty(4, C, dtype=torch.float32, device=dev)          # scale, shift, mean, invstd
+    with torch.cuda.device(dev):
+        check(lib.scd_bn_stats(_ptr(z), pixels, C, _ptr(sums), _stream()), "scd_bn_stats")
+        count = float(pixels)
+        if all_reduce is not None:
+            count = all_reduce(sums, pixels)
+        check(lib.scd_bn_finalize(_ptr(sums), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
+                                  _ptr(num_batches), C, count, BN_MOMENTUM, BN_EPS, _ptr(stat[0]), _ptr(stat[1]),
+                                  _ptr(stat[2]), _ptr(stat[3]), _stream()), "scd_bn_finalize")
+        if out is None:
+            out = torch.empty_like(z)
+        check(lib.scd_bn_apply(_ptr(z), _ptr(stat[0]), _ptr(stat[1]), _ptr(residual), int(relu), pixels, C, _ptr(out),
+                               _stream()), "scd_bn_apply")
+    return out, {"stat": stat, "count": count, "sums": sums}
+
+
+def bn_backward(da, a, z, ctx, want_dy=False, dgamma=None, dbeta=None, all_reduce=None):
+    """Backward of bn_forward.  a = the post-ReLU output (ReLU mask) or None.  Returns (dz, dy or None)."""
+    C = z.shape[-1]
+    pixels = z.numel() // C
+    dev = z.device
+    stat, count = ctx["stat"], ctx["count"]
+    sums = ctx["sums"]
+    dz = torch.empty_like(z)
+    dy = torch.empty_like(z) if want_dy else None
+    with torch.cuda.device(dev):
+        args = (_ptr(da), _ptr(a), _ptr(z), _ptr(stat[0]), _ptr(stat[2]), _ptr(stat[3]), pixels, C, count, _ptr(sums))
+        check(lib.scd_bn_bwd(*args, None, None, None, None, 0, _stream()), "scd_bn_bwd(reduce)")
+        if all_reduce is not None:
+            all_reduce(sums, None)
+        check(lib.scd_bn_bwd(*args, _ptr(dz), _ptr(dy), _ptr(dgamma), _ptr(dbeta), 1, _stream()), "scd_bn_bwd(apply)")
+    return dz, dy
+
+
+def conv_dgrad(kind, dz, weight, zero_bias, cout, add=None, dz2=None, out=None):
+    """Data gradient of a forward stage (kind 0, 1 or 3).  dz (B,h,w,cin) bf16 -> dx NHWC bf16."""
+    dz = _req(dz, torch.bfloat16, "dz")
+    b, h, w, cin = dz.shape
+    if kind == 0:
+        ho, wo = h, w
+    elif kind == 1:
+        ho, wo = 2 * h, 2 * w
+    else:
+        ho, wo = h // 2, w // 2
+    if out is None:
+        out = torch.empty(b, ho, wo, cout, dtype=torch.bfloat16, device=dz.device)
+    with torch.cuda.device(dz.device):
+        check(lib.scd_conv_igemm_dgrad(kind, _ptr(dz), _ptr(dz2), _ptr(weight), _ptr(zero_bias), _ptr(add), b, h, w, cin,
+                                       cout, _ptr(out), _stream()), "scd_conv_igemm_dgrad")
+    return out
+
+
+def conv_wgrad_floats(kind, cin, cout):
+    return lib.scd_conv_wgrad_out_floats(kind, cin, cout)
+
+
+def conv_wgrad(kind, a_in, dz, cin, cout, out):
+    """Weight gradient into `out` (fp32, zeroed by the caller, layout of include/scd_b200.h)."""
+    a_in = _req(a_in, torch.bfloat16, "a_in")
+    b, h, w = a_in.shape[0], a_in.shape[1], a_in.shape[2]
+    with torch.cuda.device(a_in.device):
+        check(lib.scd_conv_wgrad(kind, _ptr(a_in), _ptr(_req(dz, torch.bfloat16, "dz")), b, h, w, cin, cout, _ptr(out),
+                                 _stream()), "scd_conv_wgrad")
+    return out
+
+
+def stem_conv_train(x, weight):
+    x = _req(x, torch.float32, "x")
+    b, _, h, w = x.shape
+    z0 = torch.empty(b, h // 2, w // 2, 64, dtype=torch.bfloat16, device=x.device)
+    col0 = torch.empty_like(z0)
+    with torch.cuda.device(x.device):
+        check(lib.scd_stem_conv_train(_ptr(x), _ptr(weight), b, h, w, _ptr(z0), _ptr(col0), _stream()),
+              "scd_stem_conv_train")
+    return z0, col0
+
+
+def stem_bn_relu_pool(z0, stat):
+    b, hc, wc, _ = z0.shape
+    a0 = torch.empty(b, hc // 2, wc // 2, 64, dtype=torch.bfloat16, device=z0.device)
+    with torch.cuda.device(z0.device):
+        check(lib.scd_stem_bn_relu_pool(_ptr(z0), _ptr(stat[0]), _ptr(stat[1]), b, hc // 2, wc // 2, _ptr(a0), _stream()),
+              "scd_stem_bn_relu_pool")
+    return a0
+
+
+def stem_pool_bwd(z0, stat, da0):
+    b, hc, wc, _ = z0.shape
+    dy0 = torch.empty_like(z0)
+    with torch.cuda.device(z0.device):
+        check(lib.scd_stem_pool_bwd(_ptr(z0), _ptr(stat[0]), _ptr(stat[1]), _ptr(da0), b, hc // 2, wc // 2, _ptr(dy0),
+                                    _stream()), "scd_stem_pool_bwd")
+    return dy0
+
+
+def heads_fwd_train(x, w3, b3, w1, b1):
+    b, h, w, _ = x.shape
+    dev = x.device
+    heat = torch.empty(b, 1, h, w, dtype=torch.float32, device=dev)
+    regr = torch.empty(b, 4, h, w, dtype=torch.float32, device=dev)
+    off = torch.empty(b, 2, h, w, dtype=torch.float32, device=dev)
+    hidden = torch.empty(b, h, w, 384, dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.scd_heads_fwd_train(_ptr(x), _ptr(w3), _ptr(b3), _ptr(w1), _ptr(b1), b, h, w, _ptr(heat), _ptr(regr),
+                                      _ptr(off), _ptr(hidden), _stream()), "scd_heads_fwd_train")
+    return heat, regr, off, hidden
+
+
+def heads_bwd(d_heat, d_regr, d_off, hidden, w1, g_w1, g_b1, g_b3):
+    b, h, w, _ = hidden.shape
+    d_hidden = torch.empty_like(hidden)
+    with torch.cuda.device(hidden.device):
+        check(lib.scd_heads_bwd(_ptr(d_heat), _ptr(d_regr), _ptr(d_off), _ptr(hidden), _ptr(w1), b, h, w, _ptr(d_hidden),
+                                _ptr(g_w1), _ptr(g_b1), _ptr(g_b3), _stream()), "scd_heads_bwd")
+    return d_hidden
+
+
+def adam_step(params, exp_avg, exp_avg_sq, grads, gmap, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
+    with torch.cuda.device(params.device):
+        check(lib.scd_adam_step(_ptr(params), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(grads), _ptr(gmap), params.numel(),
+                                step, lr, betas[0], betas[1], eps, grad_scale, _stream()), "scd_adam_step")
+
+
+def gather_cast_bf16(src, idx, dst):
+    with torch.cuda.device(src.device):
+        check(lib.scd_gather_cast_bf16(_ptr(src), _ptr(idx), idx.numel(), _ptr(dst), _stream()), "scd_gather_cast_bf16")
+
+
+def scale_inplace(x, d_scale):
+    with torch.cuda.device(x.device):
+        check(lib.scd_scale_inplace(_ptr(x), x.numel(), _ptr(d_scale), _stream()), "scd_scale_inplace")

@@ -101,3 +101,78 @@ def pack_infer_blob(sd, device):
             raise ops.ScdError("blob entry size mismatch: %d vs %d" % (raw.numel(), n))
         blob[o:o + n] = raw.to(device)
     return blob
+
+
+# ----------------------------------------------------------------------------------------------------
+# Training-side layouts.  The functions below are pure index permutations (no dtype change), so the same
+# code packs weights and, applied to an index tensor, yields the gather maps used by scd_gather_cast_bf16.
+# ----------------------------------------------------------------------------------------------------
+def layout_fwd(w, kind):
+    """Forward GEMM-operand layout of a weight (any dtype): see pack_conv."""
+    if kind != 3:
+        return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+    kh_of = ((1, 3), (0, 2))
+    cin, cout = w.shape[0], w.shape[1]
+    out = w.new_zeros(4, cout, 4 * cin)
+    for qy in range(2):
+        for qx in range(2):
+            for a in range(2):
+                for b in range(2):
+                    t = a * 2 + b
+                    out[qy * 2 + qx, :, t * cin:(t + 1) * cin] = w[:, :, kh_of[qy][a], kh_of[qx][b]].t()
+    return out
+
+
+def layout_dgrad(w, kind, w_ds=None):
+    """Data-gradient GEMM-operand layout (csrc/igemm.cu kinds 0 / 5 / 7).
+
+    kind 0: W (Co,Ci,3,3) -> (Ci, 9*Co), tap t' = (r', s') reads W[co, ci, 2-r', 2-s'] (flipped kernel).
+    kind 1: W (Co,Ci,3,3) [+ downsample W_ds (Co,Ci,1,1)] -> (4, Ci, 4*Co): transposed 3x3 s2 conv by output
+            parity class (qy,qx); y choices R[0] = [1], R[1] = [0, 2]; class (0,0) has W_ds as a second tap.
+    kind 3: W (Ci,Co,4,4) -> (Ci, 16*Co), tap t = kh*4 + kw reads W[ci, co, kh, kw]."""
+    if kind == 0:
+        co, ci = w.shape[0], w.shape[1]
+        return w.flip(2, 3).permute(1, 2, 3, 0).reshape(ci, 9 * co)
+    if kind == 1:
+        co, ci = w.shape[0], w.shape[1]
+        out = w.new_zeros(4, ci, 4 * co)
+        R = ((1,), (0, 2))
+        for qy in range(2):
+            for qx in range(2):
+                t = 0
+                for r in R[qy]:
+                    for s in R[qx]:
+                        out[qy * 2 + qx, :, t * co:(t + 1) * co] = w[:, :, r, s].t()
+                        t += 1
+                if qy == 0 and qx == 0 and w_ds is not None:
+                    out[0, :, t * co:(t + 1) * co] = w_ds[:, :, 0, 0].t()
+        return out
+    if kind == 3:
+        ci, co = w.shape[0], w.shape[1]
+        return w.permute(0, 2, 3, 1).reshape(ci, 16 * co)
+    raise ValueError(kind)
+
+
+def layout_stem(w):
+    """(64,1,7,7) -> (64,64) space-to-depth K order (see pack_stem), any dtype."""
+    full = w.new_zeros(64, 8, 8)
+    full[:, 1:, 1:] = w.reshape(64, 7, 7)
+    return full.reshape(64, 4, 2, 4, 2).permute(0, 1, 3, 2, 4).reshape(64, 64)
+
+
+def wgrad_index(shape, kind):
+    """For a weight of `shape` (reference layout) the index of each element inside the buffer that
+    scd_conv_wgrad fills (see include/scd_b200.h), as an int64 tensor of that shape."""
+    if kind == 4:                                           # stem: out[0][co][k]
+        k = layout_stem(torch.arange(1, 64 * 49 + 1, dtype=torch.int64).reshape(64, 1, 7, 7))   # (co, k) -> ref+1
+        idx = torch.zeros(64 * 49, dtype=torch.int64)
+        co, kk = torch.nonzero(k, as_tuple=True)
+        idx[k[co, kk] - 1] = co * 64 + kk
+        return idx.reshape(shape)
+    if kind == 3:
+        ci, co, kh, kw = torch.meshgrid(*[torch.arange(s) for s in shape], indexing="ij")
+        t = kh * 4 + kw
+        return ((t * (shape[1] // 64) + co // 64) * shape[0] + ci) * 64 + co % 64
+    co, ci, r, s = torch.meshgrid(*[torch.arange(s) for s in shape], indexing="ij")
+    t = r * shape[3] + s
+    return ((t * (shape[1] // 64) + ci // 64) * shape[0] + co) * 64 + ci % 64
