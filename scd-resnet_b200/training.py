@@ -1,11 +1,299 @@
-"""Train-mode forward/backward of CenterNetResidual (SURVEY.md 8a rows a1-a9 with batch-statistics BN, a20).
+"""Training step of centerOffsetRes10 on hand-written sm_100a kernels.
 
-Not built yet in this round: inference, decode, loss and target rendering are.  Fails loudly instead of
-falling back to PyTorch ops.
+Mirrors NetworkFactory.train (ref: models/networkFactory.py:257-263): zero_grad -> forward with
+batch-statistics BatchNorm (ref: models/backbones/residuals.py:312-334) -> CenterNetLoss
+(ref: models/centerNetOffset.py:182-217) -> backward -> Adam (torch defaults, :80-82).
+
+TrainEngine owns four flat fp32 buffers: P (master parameters; the module's nn.Parameters are re-bound as
+views into it, so state_dict / checkpoints / DDP-style broadcasts keep working), G (gradients, in the layouts
+the wgrad kernels produce), M and V (Adam moments), plus WB, the bf16 GEMM-operand copies of the weights
+(forward and data-gradient layouts) that one gather kernel refreshes after every optimiser step.
+Orchestration is host Python over the C ABI; every device operation is one of this repo's kernels
+(besides memsets and, for more than one rank, NCCL all-reduces).
 """
+import torch
+
+from . import ops, weights
+from . import train_ops as T
 from ._lib import ScdError
+
+# (name, conv param prefix, bn prefix, kind, cin, cout)
+_BLOCKS = [("layer1", 64, 64, 1), ("layer2", 64, 128, 2), ("layer3", 128, 256, 2), ("layer4", 256, 512, 2)]
+_DECONV = [("deconvolutionLayers.0", "deconvolutionLayers.1", 512, 256),
+           ("deconvolutionLayers.3", "deconvolutionLayers.4", 256, 256),
+           ("deconvolutionLayers.6", "deconvolutionLayers.7", 256, 256)]
+_HEADS = (("heatmap", 0, 1), ("regr", 1, 4), ("offset", 5, 2))
+
+
+class TrainEngine:
+    def __init__(self, module, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, regr_w=0.1, off_w=0.1, process_group=None):
+        self.module = module
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.regr_w, self.off_w = regr_w, off_w
+        self.group = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.step_count = 0
+        named = dict(module.named_parameters())
+        dev = next(module.parameters()).device
+        if dev.type != "cuda":
+            raise ScdError("TrainEngine needs the module on a CUDA device")
+        self.dev = dev
+        # ---- flat parameter buffer; head 1x1 weights / biases grouped so the kernels see (7,128), (7), (384)
+        order = [k for k in named if not (k.split(".")[0] in ("heatmap", "regr", "offset"))]
+        order += [h + ".0.weight" for h, _, _ in _HEADS] + [h + ".0.bias" for h, _, _ in _HEADS]
+        order += [h + ".2.weight" for h, _, _ in _HEADS] + [h + ".2.bias" for h, _, _ in _HEADS]
+        assert sorted(order) == sorted(named)
+        self.off, n = {}, 0
+        for k in order:
+            self.off[k] = n
+            n += named[k].numel()
+        self.n_params = n
+        self.P = torch.empty(n, dtype=torch.float32, device=dev)
+        for k in order:
+            p = named[k]
+            view = self.P[self.off[k]:self.off[k] + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view                                  # the module now lives in the flat buffer
+        self.M = torch.zeros_like(self.P)
+        self.V = torch.zeros_like(self.P)
+        self._build_layouts(named)
+        self.zero_bias = torch.zeros(512, dtype=torch.float32, device=dev)
+        self.refresh_operands()
+
+    # ------------------------------------------------------------------ layouts
+    def _build_layouts(self, named):
+        """gmap: parameter element -> index in G;  wmap: element of WB -> index in P (or -1)."""
+        gmap = torch.empty(self.n_params, dtype=torch.int64)
+        self.g_off, g_n = {}, 0
+        wparts, self.wb_off, w_n = [], {}, 0
+
+        def g_alloc(key, floats):
+            nonlocal g_n
+            self.g_off[key] = g_n
+            g_n += (floats + 63) // 64 * 64
+            return self.g_off[key]
+
+        def pidx(key):                                    # 1-based indices of a parameter inside P
+            p = named[key]
+            return (torch.arange(p.numel(), dtype=torch.int64) + self.off[key] + 1).view(p.shape)
+
+        def w_alloc(key, index_tensor):
+            nonlocal w_n
+            flat = index_tensor.reshape(-1) - 1           # zeros (structural) -> -1
+            self.wb_off[key] = (w_n, tuple(index_tensor.shape))
+            w_n += (flat.numel() + 127) // 128 * 128
+            wparts.append((self.wb_off[key][0], flat))
+
+        def plain(key):
+            base = g_alloc(key, named[key].numel())
+            gmap[self.off[key]:self.off[key] + named[key].numel()] = base + torch.arange(named[key].numel())
+
+        def conv(key, kind, cin, cout, fwd=True):
+            shape = tuple(named[key].shape)
+            base = g_alloc(key, T.conv_wgrad_floats(kind, cin, cout))
+            gmap[self.off[key]:self.off[key] + named[key].numel()] = (base + weights.wgrad_index(shape, kind)).reshape(-1)
+            if fwd:
+                w_alloc(key + ":fwd", weights.layout_fwd(pidx(key), kind))
+
+        def bn(prefix):
+            plain(prefix + ".weight")
+            plain(prefix + ".bias")
+
+        # stem
+        base = g_alloc("preprocess.0.weight", T.conv_wgrad_floats(4, 64, 64))
+        gmap[self.off["preprocess.0.weight"]:self.off["preprocess.0.weight"] + 64 * 49] = \
+            (base + weights.wgrad_index((64, 1, 7, 7), 4)).reshape(-1)
+        w_alloc("preprocess.0.weight:fwd", weights.layout_stem(pidx("preprocess.0.weight")))
+        bn("preprocess.1")
+        for name, cin, cout, stride in _BLOCKS:
+            p = name + ".0"
+            conv(p + ".conv1.weight", 0 if stride == 1 else 1, cin, cout)
+            bn(p + ".bn1")
+            conv(p + ".conv2.weight", 0, cout, cout)
+            bn(p + ".bn2")
+            w_alloc(p + ".conv2.weight:dgrad", weights.layout_dgrad(pidx(p + ".conv2.weight"), 0))
+            if stride == 1:
+                w_alloc(p + ".conv1.weight:dgrad", weights.layout_dgrad(pidx(p + ".conv1.weight"), 0))
+            else:
+                conv(p + ".downsample.0.weight", 2, cin, cout)
+                bn(p + ".downsample.1")
+                w_alloc(p + ".conv1.weight:dgrad",
+                        weights.layout_dgrad(pidx(p + ".conv1.weight"), 1, pidx(p + ".downsample.0.weight")))
+        for ck, bk, cin, cout in _DECONV:
+            conv(ck + ".weight", 3, cin, cout)
+            bn(bk)
+            w_alloc(ck + ".weight:dgrad", weights.layout_dgrad(pidx(ck + ".weight"), 3))
+        # heads: the three 3x3 convs run as one conv with 384 output channels
+        base = g_alloc("heads.w3", T.conv_wgrad_floats(0, 256, 384))
+        idx384 = weights.wgrad_index((384, 256, 3, 3), 0)
+        w3_idx = torch.cat([pidx(h + ".0.weight") for h, _, _ in _HEADS], 0)          # (384,256,3,3) of P indices
+        for i, (h, _, _) in enumerate(_HEADS):
+            k = h + ".0.weight"
+            gmap[self.off[k]:self.off[k] + named[k].numel()] = (base + idx384[i * 128:(i + 1) * 128]).reshape(-1)
+        w_alloc("heads.w3:fwd", weights.layout_fwd(w3_idx, 0))
+        w_alloc("heads.w3:dgrad", weights.layout_dgrad(w3_idx, 0))
+        b3 = g_alloc("heads.b3", 384)
+        w1 = g_alloc("heads.w1", 7 * 128)
+        b1 = g_alloc("heads.b1", 7)
+        for i, (h, j0, nj) in enumerate(_HEADS):
+            gmap[self.off[h + ".0.bias"]:self.off[h + ".0.bias"] + 128] = b3 + i * 128 + torch.arange(128)
+            gmap[self.off[h + ".2.weight"]:self.off[h + ".2.weight"] + nj * 128] = w1 + j0 * 128 + torch.arange(nj * 128)
+            gmap[self.off[h + ".2.bias"]:self.off[h + ".2.bias"] + nj] = b1 + j0 + torch.arange(nj)
+        self.n_grads = g_n
+        self.G = torch.zeros(g_n, dtype=torch.float32, device=self.dev)
+        self.gmap = gmap.to(torch.int32).to(self.dev)
+        wmap = torch.full((w_n,), -1, dtype=torch.int64)
+        for o, flat in wparts:
+            wmap[o:o + flat.numel()] = flat
+        self.wmap = wmap.to(torch.int32).to(self.dev)
+        self.WB = torch.empty(w_n, dtype=torch.bfloat16, device=self.dev)
+
+    def wb(self, key):
+        o, shape = self.wb_off[key]
+        n = 1
+        for s in shape:
+            n *= s
+        return self.WB[o:o + n]
+
+    def g(self, key, n=None):
+        o = self.g_off[key]
+        return self.G[o:o + n] if n is not None else self.G[o:]
+
+    def p(self, key):
+        return dict(self.module.named_parameters())[key].data
+
+    def refresh_operands(self):
+        T.gather_cast_bf16(self.P, self.wmap, self.WB)
+
+    # ------------------------------------------------------------------ SyncBatchNorm hooks
+    def _allreduce_stats(self, sums, pixels):
+        if self.world == 1:
+            return float(pixels) if pixels is not None else None
+        torch.distributed.all_reduce(sums, group=self.group)
+        return float(pixels) * self.world if pixels is not None else None
+
+    # ------------------------------------------------------------------ forward + backward
+    def _bn(self, z, prefix, residual=None, relu=True):
+        m = self.module.get_submodule(prefix)
+        return T.bn_forward(z, m.weight.data, m.bias.data, m.running_mean, m.running_var, m.num_batches_tracked,
+                            residual, relu, all_reduce=self._allreduce_stats if self.world > 1 else None)
+
+    def _bn_bwd(self, da, a, z, ctx, prefix, want_dy=False):
+        return T.bn_backward(da, a, z, ctx, want_dy, self.g(prefix + ".weight"), self.g(prefix + ".bias"),
+                             all_reduce=self._allreduce_stats if self.world > 1 else None)
+
+    def _conv(self, kind, x, key, cout):
+        return ops.conv_igemm_fwd(kind, x, self.wb(key + ":fwd"), self.zero_bias[:cout], None, False)
+
+    def forward_backward(self, x, targets, sigmoid_inplace=False):
+        """x (B,1,H,W) f32 CUDA; targets = [heat (B,1,128,128), mask (B,30), regr6 (B,30,6), idx (B,30)].
+        Returns (losses f32[4] on the device, outputs dict); gradients land in self.G."""
+        mod = self.module
+        self.G.zero_()
+        tape = []
+        # ---- forward -----------------------------------------------------------------------------------
+        z0, col0 = T.stem_conv_train(x, self.wb("preprocess.0.weight:fwd"))
+        _, ctx0 = self._stem_bn(z0, mod.preprocess[1])
+        a = T.stem_bn_relu_pool(z0, ctx0["stat"])
+        a0 = a
+        for name, cin, cout, stride in _BLOCKS:
+            p = name + ".0"
+            a_in = a
+            z1 = self._conv(0 if stride == 1 else 1, a_in, p + ".conv1.weight", cout)
+            a1, c1 = self._bn(z1, p + ".bn1")
+            z2 = self._conv(0, a1, p + ".conv2.weight", cout)
+            if stride == 1:
+                skip, zd, cd = a_in, None, None
+            else:
+                zd = self._conv(2, a_in, p + ".downsample.0.weight", cout)
+                skip, cd = self._bn(zd, p + ".downsample.1", relu=False)
+            a, c2 = self._bn(z2, p + ".bn2", residual=skip)
+            tape.append((p, cin, cout, stride, a_in, z1, a1, c1, z2, c2, zd, cd, a))
+        dtape = []
+        for ck, bk, cin, cout in _DECONV:
+            a_in = a
+            z = self._conv(3, a_in, ck + ".weight", cout)
+            a, c = self._bn(z, bk)
+            dtape.append((ck, bk, cin, cout, a_in, z, c, a))
+        e3 = a
+        b3 = self.P[self.off["heatmap.0.bias"]:self.off["heatmap.0.bias"] + 384]
+        w1 = self.P[self.off["heatmap.2.weight"]:self.off["heatmap.2.weight"] + 7 * 128]
+        b1 = self.P[self.off["heatmap.2.bias"]:self.off["heatmap.2.bias"] + 7]
+        heat, regr, off, hidden = T.heads_fwd_train(e3, self.wb("heads.w3:fwd"), b3, w1, b1)
+        # ---- loss (forward + its own backward in one pass) -------------------------------------------
+        heat_logits = heat
+        losses, d_heat, d_regr, d_off = ops.centernet_loss(heat_logits, regr, off, targets[0], targets[1], targets[2],
+                                                           targets[3], self.regr_w, self.off_w, with_grad=True,
+                                                           sigmoid_inplace=sigmoid_inplace)
+        # ---- backward ----------------------------------------------------------------------------------
+        d_hidden = T.heads_bwd(d_heat, d_regr, d_off, hidden, w1, self.g("heads.w1"), self.g("heads.b1"),
+                               self.g("heads.b3"))
+        T.conv_wgrad(0, e3, d_hidden, 256, 384, self.g("heads.w3"))
+        da = T.conv_dgrad(0, d_hidden, self.wb("heads.w3:dgrad"), self.zero_bias[:256], 256)
+        for ck, bk, cin, cout, a_in, z, c, a_out in reversed(dtape):
+            dz, _ = self._bn_bwd(da, a_out, z, c, bk)
+            T.conv_wgrad(3, a_in, dz, cin, cout, self.g(ck + ".weight"))
+            da = T.conv_dgrad(3, dz, self.wb(ck + ".weight:dgrad"), self.zero_bias[:cin], cin)
+        for p, cin, cout, stride, a_in, z1, a1, c1, z2, c2, zd, cd, a_out in reversed(tape):
+            dz2, dy = self._bn_bwd(da, a_out, z2, c2, p + ".bn2", want_dy=True)
+            T.conv_wgrad(0, a1, dz2, cout, cout, self.g(p + ".conv2.weight"))
+            da1 = T.conv_dgrad(0, dz2, self.wb(p + ".conv2.weight:dgrad"), self.zero_bias[:cout], cout)
+            dz1, _ = self._bn_bwd(da1, a1, z1, c1, p + ".bn1")
+            if stride == 1:
+                T.conv_wgrad(0, a_in, dz1, cin, cout, self.g(p + ".conv1.weight"))
+                da = T.conv_dgrad(0, dz1, self.wb(p + ".conv1.weight:dgrad"), self.zero_bias[:cin], cin, add=dy)
+            else:
+                dzd, _ = self._bn_bwd(dy, None, zd, cd, p + ".downsample.1")
+                T.conv_wgrad(1, a_in, dz1, cin, cout, self.g(p + ".conv1.weight"))
+                T.conv_wgrad(2, a_in, dzd, cin, cout, self.g(p + ".downsample.0.weight"))
+                da = T.conv_dgrad(1, dz1, self.wb(p + ".conv1.weight:dgrad"), self.zero_bias[:cin], cin, dz2=dzd)
+        dy0 = T.stem_pool_bwd(z0, ctx0["stat"], da)
+        dz0, _ = T.bn_backward(dy0, None, z0, ctx0, False, self.g("preprocess.1.weight"), self.g("preprocess.1.bias"),
+                               all_reduce=self._allreduce_stats if self.world > 1 else None)
+        T.conv_wgrad(4, col0, dz0, 64, 64, self.g("preprocess.0.weight"))
+        return losses, {"heatmap": heat_logits, "regr": regr, "offset": off}
+
+    def _stem_bn(self, z0, bn0):
+        """Batch statistics of the stem conv output; the normalisation itself is fused with ReLU + max-pool."""
+        C = 64
+        pixels = z0.numel() // C
+        sums = torch.empty(2 * C, dtype=torch.float64, device=self.dev)
+        stat = torch.empty(4, C, dtype=torch.float32, device=self.dev)
+        ops.check(ops.lib.scd_bn_stats(ops._ptr(z0), pixels, C, ops._ptr(sums), ops._stream()), "scd_bn_stats")
+        count = self._allreduce_stats(sums, pixels)
+        ops.check(ops.lib.scd_bn_finalize(ops._ptr(sums), ops._ptr(bn0.weight.data), ops._ptr(bn0.bias.data),
+                                          ops._ptr(bn0.running_mean), ops._ptr(bn0.running_var),
+                                          ops._ptr(bn0.num_batches_tracked), C, count, T.BN_MOMENTUM, T.BN_EPS,
+                                          ops._ptr(stat[0]), ops._ptr(stat[1]), ops._ptr(stat[2]), ops._ptr(stat[3]),
+                                          ops._stream()), "scd_bn_finalize")
+        return None, {"stat": stat, "count": count, "sums": sums}
+
+    # ------------------------------------------------------------------ optimiser
+    def optimizer_step(self):
+        """DDP semantics (ref: models/networkFactory.py:134): gradients are averaged over ranks, then Adam."""
+        if self.world > 1:
+            torch.distributed.all_reduce(self.G, group=self.group)
+        self.step_count += 1
+        T.adam_step(self.P, self.M, self.V, self.G, self.gmap, self.step_count, self.lr, self.betas, self.eps,
+                    1.0 / self.world)
+        self.refresh_operands()
+
+    def train_step(self, x, targets):
+        """NetworkFactory.train: returns the device tensor (total, focal, size, offset)."""
+        losses, _ = self.forward_backward(x, targets)
+        self.optimizer_step()
+        return losses
+
+    def set_learning_rate(self, lr):
+        self.lr = lr
+
+    def grads_reference_layout(self):
+        """{name: gradient tensor in the parameter's own layout} (diagnostics / interop; not on the hot path)."""
+        g = self.G[self.gmap.long()]
+        return {k: g[self.off[k]:self.off[k] + p.numel()].view_as(p) for k, p in self.module.named_parameters()}
 
 
 def forward_train(module, x):
-    raise ScdError("CenterNetResidual.train() forward is not built yet in scd_b200 (inference/decode/loss/"
-                   "target-render kernels are); call .eval() for inference. There is no PyTorch fallback.")
+    raise ScdError("CenterNetResidual.forward in train mode has no stand-alone autograd graph in scd_b200: training "
+                   "runs through scd_resnet_b200.training.TrainEngine (forward + loss + backward + Adam on native "
+                   "kernels), which networkFactory.NetworkFactory.train uses. Call .eval() for inference.")
