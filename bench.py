@@ -139,6 +139,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="tiles per GPU per step (config[1] = 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=10, help="timed training steps (configs[2]/[3]); 0 = skip")
+    ap.add_argument("--train-batch", type=int, default=32, help="samples per GPU per training step (exp.json)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -218,10 +220,41 @@ def main():
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3
     e2e_ms = max(e2e_ms, e2e_wall_ms) if world == 1 else e2e_ms
 
+    # ---- training step (configs[2] / [3]): render targets + forward + loss + backward + Adam ---------------
+    train_ms = None
+    if args.train_steps > 0:
+        from scd_resnet_b200.training import TrainEngine
+        del det, xs
+        torch.cuda.empty_cache()
+        TB = args.train_batch
+        tmodel = CenterNetResidual(10)
+        tmodel.load_state_dict(synthetic.make_state_dict(tmodel, 1234))
+        tmodel.to(dev).train()
+        eng = TrainEngine(tmodel, process_group=dist.group.WORLD if world > 1 else None)
+        txs = [torch.randn(TB, 1, 512, 512, device=dev, generator=g) for _ in range(3)]
+        tlocs = [tuple(t.to(dev) for t in synthetic.make_objects(TB, seed=50 + 3 * rank + i)) for i in range(3)]
+
+        def train_once(i):
+            ys = S.ops.render_targets(*tlocs[i % 3])
+            return eng.train_step(txs[i % 3], ys)
+
+        for i in range(3):
+            train_once(i)
+        barrier()
+        ts, te = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ts.record()
+        for i in range(args.train_steps):
+            last = train_once(i)
+        te.record()
+        barrier()
+        train_ms = ts.elapsed_time(te)
+        train_loss = float(last[0])
+
     if world > 1:
-        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, e2e_ms, train_ms or 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = t.tolist()
+        ms, e2e_ms, tm = t.tolist()
+        train_ms = tm if train_ms is not None else None
 
     if rank == 0:
         peaks = measured_peaks()
@@ -249,6 +282,15 @@ def main():
             "stage_ms": {n: round(v, 4) for n, v in zip(names, stage_ms)}, "decode_ms": round(decode_ms, 4),
             "clocks": clk,
         }
+        if train_ms is not None:
+            sps = world * args.train_batch * args.train_steps / (train_ms * 1e-3)
+            line["train"] = {"metric": "training samples/sec, centerOffsetRes10, batch 32 per GPU (exp.json)",
+                             "value": sps, "unit": "samples/s", "ms_per_step": train_ms / args.train_steps,
+                             "steps": args.train_steps, "batch_per_gpu": args.train_batch,
+                             "step": "render targets + fwd (batch-stat BN) + focal/L1 loss + bwd + Adam",
+                             "grad_sync": "NCCL all-reduce of the flat fp32 gradient + BN statistics" if world > 1 else "none",
+                             "tflops": 147.5e9 * args.train_batch / (train_ms / args.train_steps * 1e-3) / 1e12,
+                             "last_loss": train_loss}
         if world == 1 and not args.no_cpu_baseline:
             rate, spi, iters, cores = cpu_oracle_rate(8, 10.0)
             line["cpu_baseline"] = {"value": rate, "unit": "tiles/s", "cores": cores, "kind": "port",
