@@ -8,10 +8,9 @@
 // offset, and a host sync (focal.py:47).  Here:
 //
 //   1. count_pos      reads gt once                      (N_pos is batch-wide, focal.py:42)
-//   2. focal_fused    reads logits + gt, writes d_heat (and sigmoid, and zeroes d_regr /
-//                     d_off), per-CTA partial sums in fp64
-//   3. l1_finalize    one CTA: 30 x B gathers, masked L1 x2 and their sparse gradients,
-//                     deterministic final reduction of the partials, writes losses[4]
+//   2. focal_fused    reads logits + gt, writes d_heat (and sigmoid), per-CTA partial sums in fp64
+//   3. l1_finalize    30 x B gathers, masked L1 x2 and their sparse gradients (scattered into planes
+//                     cleared by a memset); the last CTA reduces all partials in fixed order -> losses[4]
 //
 // HBM-bound; algorithmic traffic per sample (fp32, 128x128): 64 KB logits + 64 KB gt read,
 // 64 KB d_heat written (+ 64 KB gt for the count pass).
@@ -22,14 +21,22 @@ namespace scd {
 constexpr int LOSS_THREADS = 256;
 
 struct LossWs {            // workspace header; partial sums follow
-    unsigned n_pos;
-    unsigned n_blocks;
-    unsigned pad[2];
+    unsigned n_pos;        // count(gt == 1) over the batch
+    unsigned n_blocks;     // CTAs of the focal pass
+    unsigned n_mask;       // mask.sum() over the batch
+    unsigned l1_done;      // CTAs of the L1 pass that have finished
 };
 
 __global__ void __launch_bounds__(LOSS_THREADS)
-count_pos_kernel(const float4* __restrict__ gt, size_t n4, LossWs* __restrict__ ws)
+count_pos_kernel(const float4* __restrict__ gt, size_t n4, const uint8_t* __restrict__ mask, int n_obj,
+                 LossWs* __restrict__ ws)
 {
+    if (blockIdx.x == 0) {                                           // mask.float().sum() (regression.py:38)
+        int m = 0;
+        for (int i = threadIdx.x; i < n_obj; i += blockDim.x) m += mask[i] ? 1 : 0;
+        m = warp_sum(m);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&ws->n_mask, (unsigned)m);
+    }
     int c = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         const float4 g = ld_stream(gt + i);
@@ -64,14 +71,12 @@ __device__ __forceinline__ void focal_elem(float x, float g, float& prob, float&
 __global__ void __launch_bounds__(LOSS_THREADS)
 focal_fused_kernel(const float4* __restrict__ logits, const float4* __restrict__ gt, size_t n4,
                    float4* __restrict__ prob_out, float4* __restrict__ d_heat,
-                   float4* __restrict__ d_regr, float4* __restrict__ d_off,
                    LossWs* __restrict__ ws, double* __restrict__ partials)
 {
     const unsigned npos = ws->n_pos;
     // loss = -(pos + neg) / N_pos, or -neg when there is no positive (focal.py:47-51)
     const float scale = npos > 0 ? -1.f / (float)npos : -1.f;
     float ps = 0.f, ns = 0.f;
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         const float4 x = logits[i];            // plain load: prob_out may alias logits
@@ -84,12 +89,6 @@ focal_fused_kernel(const float4* __restrict__ logits, const float4* __restrict__
         focal_elem(x.w, g.w, pr.w, a, c, d.w); ps += a; ns += c;
         if (prob_out) prob_out[i] = pr;
         if (d_heat) d_heat[i] = make_float4(d.x * scale, d.y * scale, d.z * scale, d.w * scale);
-        if (d_regr) {          // dense zero fill of the sparse L1 gradients: 4 + 2 planes per heat plane
-            // element i of the heat map of sample b covers d_regr[b][0..3][i'] and d_off[b][0..1][i']
-            // the planes are contiguous, so sample b's regr block is 4x and off block 2x the heat block
-            d_regr[4 * i] = zero; d_regr[4 * i + 1] = zero; d_regr[4 * i + 2] = zero; d_regr[4 * i + 3] = zero;
-            d_off[2 * i] = zero; d_off[2 * i + 1] = zero;
-        }
     }
     // CTA reduction in fp64, one partial pair per CTA (combined in fixed order later)
     __shared__ double sp[LOSS_THREADS / 32], sn[LOSS_THREADS / 32];
@@ -106,37 +105,26 @@ focal_fused_kernel(const float4* __restrict__ logits, const float4* __restrict__
     }
 }
 
-__global__ void __launch_bounds__(1024)
+// Masked L1 terms over the B x 30 object list, their sparse gradients, and (last CTA to finish) the
+// deterministic final reduction of every partial sum into losses[4].
+constexpr int L1_THREADS = 256;
+__global__ void __launch_bounds__(L1_THREADS)
 l1_finalize_kernel(const float* __restrict__ regr, const float* __restrict__ offset,
                    const uint8_t* __restrict__ mask, const float* __restrict__ regr6,
                    const int64_t* __restrict__ idx, int batch, int hw, int max_tags,
                    float regr_w, float off_w, float* __restrict__ losses,
                    float* __restrict__ d_regr, float* __restrict__ d_off,
-                   const LossWs* __restrict__ ws, const double* __restrict__ partials)
+                   LossWs* __restrict__ ws, const double* __restrict__ focal_partials, double* __restrict__ l1_partials)
 {
-    __shared__ double red[3][32];
-    __shared__ float s_num;
+    __shared__ double red[3][L1_THREADS / 32];
+    __shared__ bool is_last;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_obj = batch * max_tags;
-
-    // num = mask.float().sum() over the whole batch (regression.py:38)
-    int cnt = 0;
-    for (int i = tid; i < n_obj; i += blockDim.x) cnt += mask[i] ? 1 : 0;
-    cnt = warp_sum(cnt);
-    if (lane == 0) red[0][warp] = (double)cnt;
-    __syncthreads();
-    if (tid == 0) {
-        double t = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[0][w];
-        s_num = (float)t;
-    }
-    __syncthreads();
-    const float denom = s_num + 1e-4f;                              // regression.py:43
+    const float denom = (float)ws->n_mask + 1e-4f;                  // regression.py:43
     const float gr = regr_w / denom, go = off_w / denom;
-
     float sr = 0.f, so = 0.f;
-    for (int i = tid; i < n_obj; i += blockDim.x) {
-        if (!mask[i]) continue;
+    const int i = blockIdx.x * L1_THREADS + tid;
+    if (i < n_obj && mask[i]) {
         const int b = i / max_tags;
         const int64_t p = idx[i];
         const float* t6 = regr6 + (size_t)i * 6;
@@ -155,21 +143,36 @@ l1_finalize_kernel(const float* __restrict__ regr, const float* __restrict__ off
             if (d_off && d != 0.f) atomicAdd(d_off + a, d > 0.f ? go : -go);
         }
     }
-    // focal partials, fixed order per thread -> deterministic
-    double fp = 0.0, fn = 0.0;
-    const unsigned nb = ws->n_blocks;
-    for (unsigned i = tid; i < nb; i += blockDim.x) { fp += partials[2 * i]; fn += partials[2 * i + 1]; }
-    double a0 = warp_sum((double)sr), a1 = warp_sum((double)so), a2 = warp_sum(fp + fn);
+    double a0 = warp_sum((double)sr), a1 = warp_sum((double)so);
+    if (lane == 0) { red[0][warp] = a0; red[1][warp] = a1; }
     __syncthreads();
-    if (lane == 0) { red[0][warp] = a0; red[1][warp] = a1; red[2][warp] = a2; }
+    if (tid == 0) {
+        double t0 = 0.0, t1 = 0.0;
+        for (int w = 0; w < L1_THREADS / 32; ++w) { t0 += red[0][w]; t1 += red[1][w]; }
+        l1_partials[2 * blockIdx.x] = t0;
+        l1_partials[2 * blockIdx.x + 1] = t1;
+        __threadfence();
+        is_last = atomicAdd(&ws->l1_done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // fixed-order reduction of all partials -> deterministic
+    double f = 0.0, r = 0.0, o = 0.0;
+    const unsigned nb = ws->n_blocks;
+    for (unsigned k = tid; k < nb; k += L1_THREADS) f += focal_partials[2 * k] + focal_partials[2 * k + 1];
+    for (unsigned k = tid; k < gridDim.x; k += L1_THREADS) { r += l1_partials[2 * k]; o += l1_partials[2 * k + 1]; }
+    f = warp_sum(f); r = warp_sum(r); o = warp_sum(o);
+    __syncthreads();
+    if (lane == 0) { red[0][warp] = f; red[1][warp] = r; red[2][warp] = o; }
     __syncthreads();
     if (tid == 0) {
         double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { t0 += red[0][w]; t1 += red[1][w]; t2 += red[2][w]; }
+        for (int w = 0; w < L1_THREADS / 32; ++w) { t0 += red[0][w]; t1 += red[1][w]; t2 += red[2][w]; }
         const unsigned npos = ws->n_pos;
-        const float focal = npos > 0 ? (float)(-t2 / (double)npos) : (float)(-t2);   // t2 holds only neg terms when npos == 0
-        const float size_l = regr_w * ((float)t0 / denom);
-        const float off_l = off_w * ((float)t1 / denom);
+        const float focal = npos > 0 ? (float)(-t0 / (double)npos) : (float)(-t0);   // only neg terms when npos == 0
+        const float size_l = regr_w * ((float)t1 / denom);
+        const float off_l = off_w * ((float)t2 / denom);
         losses[0] = focal + size_l + off_l;                          // centerNetOffset.py:213 (len(heats) == 1)
         losses[1] = focal;
         losses[2] = size_l;
@@ -177,7 +180,7 @@ l1_finalize_kernel(const float* __restrict__ regr, const float* __restrict__ off
     }
 }
 
-__global__ void loss_ws_init_kernel(LossWs* ws) { ws->n_pos = 0u; ws->n_blocks = 0u; }
+__global__ void loss_ws_init_kernel(LossWs* ws) { ws->n_pos = 0u; ws->n_blocks = 0u; ws->n_mask = 0u; ws->l1_done = 0u; }
 
 static inline int loss_grid(size_t n4) {
     size_t want = (n4 + LOSS_THREADS - 1) / LOSS_THREADS;
@@ -191,8 +194,9 @@ static inline int loss_grid(size_t n4) {
 
 extern "C" size_t scd_centernet_loss_workspace_bytes(int batch, int height, int width)
 {
-    (void)batch; (void)height; (void)width;
-    return sizeof(scd::LossWs) + sizeof(double) * 2 * (size_t)scd::kNumSMs * 8;
+    (void)height; (void)width;
+    const size_t l1_ctas = ((size_t)(batch > 0 ? batch : 1) * 64 + scd::L1_THREADS - 1) / scd::L1_THREADS + 1;
+    return sizeof(scd::LossWs) + sizeof(double) * 2 * ((size_t)scd::kNumSMs * 8 + l1_ctas);
 }
 
 extern "C" int scd_centernet_loss(const float* heat, float* prob_out, const float* regr, const float* offset,
@@ -214,16 +218,23 @@ extern "C" int scd_centernet_loss(const float* heat, float* prob_out, const floa
     cudaStream_t st = (cudaStream_t)stream;
     LossWs* ws = reinterpret_cast<LossWs*>(workspace);
     double* partials = reinterpret_cast<double*>(ws + 1);
+    if (max_tags > 64) return fail(SCD_EINVAL, "scd_centernet_loss: max_tags must be <= 64");
     const size_t n4 = (size_t)batch * height * width / 4;
     const int grid = loss_grid(n4);
+    const int n_obj = batch * max_tags;
+    const int l1_grid = (n_obj + L1_THREADS - 1) / L1_THREADS;
+    double* l1_partials = partials + 2 * (size_t)kNumSMs * 8;
     loss_ws_init_kernel<<<1, 1, 0, st>>>(ws);
-    count_pos_kernel<<<grid, LOSS_THREADS, 0, st>>>(reinterpret_cast<const float4*>(gt_heat), n4, ws);
+    count_pos_kernel<<<grid, LOSS_THREADS, 0, st>>>(reinterpret_cast<const float4*>(gt_heat), n4, mask, n_obj, ws);
+    if (d_regr) {      // the L1 gradients are sparse (<= 30 points per sample): clear, then scatter
+        SCD_CUDA_CHECK(cudaMemsetAsync(d_regr, 0, sizeof(float) * 4 * (size_t)batch * height * width, st));
+        SCD_CUDA_CHECK(cudaMemsetAsync(d_off, 0, sizeof(float) * 2 * (size_t)batch * height * width, st));
+    }
     focal_fused_kernel<<<grid, LOSS_THREADS, 0, st>>>(
         reinterpret_cast<const float4*>(heat), reinterpret_cast<const float4*>(gt_heat), n4,
-        reinterpret_cast<float4*>(prob_out), reinterpret_cast<float4*>(d_heat),
-        reinterpret_cast<float4*>(d_regr), reinterpret_cast<float4*>(d_off), ws, partials);
-    l1_finalize_kernel<<<1, 1024, 0, st>>>(regr, offset, mask, regr6, idx, batch, height * width, max_tags,
-                                          regr_w, off_w, losses, d_regr, d_off, ws, partials);
+        reinterpret_cast<float4*>(prob_out), reinterpret_cast<float4*>(d_heat), ws, partials);
+    l1_finalize_kernel<<<l1_grid, L1_THREADS, 0, st>>>(regr, offset, mask, regr6, idx, batch, height * width, max_tags,
+                                                       regr_w, off_w, losses, d_regr, d_off, ws, partials, l1_partials);
     SCD_LAUNCH_CHECK("centernet_loss kernels");
     return SCD_OK;
 }

@@ -6,7 +6,9 @@
 // (ref: datasets/utility.py:11-16) and the mask / index / regression packing of
 // SCD.__getitem__ (:328-356).  In the reference this is a Python loop per object per
 // sample on the host; here it is one pass that writes every heat-map pixel once
-// (HBM-bound: 64 KB written per sample, <= 30 x 32 B read).
+// (HBM-bound: 64 KB written per sample, <= 30 x 32 B read): one CTA per sample keeps the 128x128 map in
+// shared memory; the object table (radius, window, 2 sigma^2) is built once by one warp, then the CTA's
+// threads split each object's window so that no lane evaluates a Gaussian outside a window.
 //
 // Numerics follow the reference to the bit where IEEE allows it: the radius is computed
 // in fp64 with explicitly rounded operations (no FMA contraction) so that the window
@@ -20,8 +22,7 @@ namespace scd {
 
 constexpr int RT_HW = 128;        // HEATMAPSIZE, ref: scdx16p100.py:50
 constexpr int RT_MAXTAG = 30;     // MAXTAGLEN,   ref: scdx16p100.py:46
-constexpr int RT_BANDS = 8;       // CTAs per sample, 16 rows each
-constexpr int RT_THREADS = 512;   // 16 rows x 128 cols / 4 px per thread
+constexpr int RT_THREADS = 256;   // one CTA per sample; the 64 KB heat map lives in shared memory
 
 struct RenderObj {
     int cx, cy, roi;
@@ -56,12 +57,15 @@ render_targets_kernel(const float* __restrict__ locs, const int32_t* __restrict_
                       float* __restrict__ heat, uint8_t* __restrict__ mask,
                       float* __restrict__ regr6, int64_t* __restrict__ idx)
 {
+    extern __shared__ float tile[];                    // [128][128] fp32
     __shared__ RenderObj objs[RT_MAXTAG];
     __shared__ int n_draw;
-    const int b = blockIdx.x / RT_BANDS, band = blockIdx.x % RT_BANDS;
+    const int b = blockIdx.x;
     const int tid = threadIdx.x;
     int count = counts[b];
     count = count < 0 ? 0 : (count > RT_MAXTAG ? RT_MAXTAG : count);
+    for (int i = tid; i < RT_HW * RT_HW / 4; i += RT_THREADS)
+        reinterpret_cast<float4*>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     // one warp prepares the object table (in list order, compacted to the drawn ones)
     if (tid < 32) {
@@ -73,7 +77,7 @@ render_targets_kernel(const float* __restrict__ locs, const int32_t* __restrict_
             const float fx = live ? truncf(l[0]) : 0.f;          // loc[0] = int(loc[0]), :515-516
             const float fy = live ? truncf(l[1]) : 0.f;
             const bool inside = live && fx >= 0.f && fx < (float)RT_HW && fy >= 0.f && fy < (float)RT_HW;
-            if (band == 0) {
+            {
                 mask[(size_t)b * RT_MAXTAG + tid] = inside ? 1 : 0;                      // :330-336
                 idx[(size_t)b * RT_MAXTAG + tid] = inside ? (int64_t)((int)fy * RT_HW + (int)fx) : 0;  // :338-344
                 float* r = regr6 + ((size_t)b * RT_MAXTAG + tid) * 6;                    // :346-351
@@ -99,29 +103,33 @@ render_targets_kernel(const float* __restrict__ locs, const int32_t* __restrict_
     }
     __syncthreads();
 
-    const int y = band * (RT_HW / RT_BANDS) + tid / 32;
-    const int x0 = (tid % 32) * 4;
-    float hv[4] = {0.f, 0.f, 0.f, 0.f};
+    // Object after object, in list order (the fp32 rounding after every object is part of the reference's
+    // result): the threads of the CTA split the object's clipped window, so every lane evaluates a Gaussian
+    // that is actually needed; a pixel is touched by exactly one thread per object.
     const int n = n_draw;
     for (int k = 0; k < n; ++k) {
         const RenderObj o = objs[k];
-        const int dy = y - o.cy;
-        if (dy < -o.roi || dy > o.roi) continue;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int dx = x0 + c - o.cx;
-            if (dx >= -o.roi && dx <= o.roi) {
-                const double g = exp(__ddiv_rn(-(double)(dx * dx + dy * dy), o.den));
-                hv[c] = (float)__dadd_rn(g, (double)hv[c]);
-            }
+        const int xa = max(o.cx - o.roi, 0), xb = min(o.cx + o.roi, RT_HW - 1);          // :579-583 window clipping
+        const int ya = max(o.cy - o.roi, 0), yb = min(o.cy + o.roi, RT_HW - 1);
+        const int w = xb - xa + 1, area = w * (yb - ya + 1);
+        for (int i = tid; i < area; i += RT_THREADS) {
+            const int yy = ya + i / w, xx = xa + i % w;
+            const int dx = xx - o.cx, dy = yy - o.cy;
+            const double g = exp(__ddiv_rn(-(double)(dx * dx + dy * dy), o.den));
+            float* hp = tile + yy * RT_HW + xx;
+            *hp = (float)__dadd_rn(g, (double)*hp);
         }
+        __syncthreads();
     }
-    float4 out;
-    out.x = hv[0] > 1.f ? 1.f : hv[0];                                                   // heat[heat > 1] = 1
-    out.y = hv[1] > 1.f ? 1.f : hv[1];
-    out.z = hv[2] > 1.f ? 1.f : hv[2];
-    out.w = hv[3] > 1.f ? 1.f : hv[3];
-    reinterpret_cast<float4*>(heat + ((size_t)b * RT_HW + y) * RT_HW)[tid % 32] = out;
+    float4* dst = reinterpret_cast<float4*>(heat + (size_t)b * RT_HW * RT_HW);
+    for (int i = tid; i < RT_HW * RT_HW / 4; i += RT_THREADS) {
+        float4 v = reinterpret_cast<const float4*>(tile)[i];
+        v.x = v.x > 1.f ? 1.f : v.x;                                                     // heat[heat > 1] = 1
+        v.y = v.y > 1.f ? 1.f : v.y;
+        v.z = v.z > 1.f ? 1.f : v.z;
+        v.w = v.w > 1.f ? 1.f : v.w;
+        dst[i] = v;
+    }
 }
 
 }  // namespace scd
@@ -132,7 +140,13 @@ extern "C" int scd_render_targets(const float* locs, const int32_t* counts, int 
     if (batch <= 0) return SCD_OK;
     if (!locs || !counts || !heat || !mask || !regr6 || !idx)
         return scd::fail(SCD_EINVAL, "scd_render_targets: null pointer");
-    scd::render_targets_kernel<<<batch * scd::RT_BANDS, scd::RT_THREADS, 0, (cudaStream_t)stream>>>(
+    static bool attr_done = false;
+    if (!attr_done) {
+        SCD_CUDA_CHECK(cudaFuncSetAttribute(scd::render_targets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            scd::RT_HW * scd::RT_HW * 4));
+        attr_done = true;
+    }
+    scd::render_targets_kernel<<<batch, scd::RT_THREADS, scd::RT_HW * scd::RT_HW * 4, (cudaStream_t)stream>>>(
         locs, counts, heat, mask, regr6, idx);
     SCD_LAUNCH_CHECK("render_targets_kernel");
     return SCD_OK;

@@ -1,8 +1,8 @@
 """Batched tile inference + decode, the path BASELINE config 2 measures (test.py:95-112 per batch).
 
 TileDetector keeps the packed weights, the activation workspace and the output buffers resident, and
-runs   H2D copy -> scd_resnet10_infer -> scd_decode_topk -> D2H copy   with the copies on a side stream so
-that the transfer of batch i+1 overlaps the kernels of batch i.
+runs   H2D copy -> scd_resnet10_infer -> scd_decode_topk -> D2H copy   with uploads, kernels and downloads on
+three streams so that the transfer of batch i+1 overlaps the kernels of batch i.
 """
 import torch
 
@@ -24,8 +24,9 @@ class TileDetector:
             hw = (height // 4, width // 4)
             self.maps = (torch.empty(batch, 1, *hw, device=self.device), torch.empty(batch, 4, *hw, device=self.device),
                          torch.empty(batch, 2, *hw, device=self.device))
-            self.copy_stream = torch.cuda.Stream(self.device)
-            self.compute_stream = torch.cuda.Stream(self.device)
+            self.copy_stream = torch.cuda.Stream(self.device)        # host -> device
+            self.d2h_stream = torch.cuda.Stream(self.device)         # device -> host (own stream: a result copy that
+            self.compute_stream = torch.cuda.Stream(self.device)     # waits for batch i must not block the upload of i+1)
             self.dev_in = [torch.empty(batch, 1, height, width, device=self.device) for _ in range(2)]
             self.in_ready = [torch.cuda.Event() for _ in range(2)]
             self.in_free = [torch.cuda.Event() for _ in range(2)]
@@ -49,6 +50,9 @@ class TileDetector:
             self._host_ring = torch.empty(n, 10, self.batch, self.K, pin_memory=True)
         results = []
         with torch.cuda.device(self.device):
+            self.t_first = torch.cuda.Event(enable_timing=True)
+            self.t_last = torch.cuda.Event(enable_timing=True)
+            self.t_first.record(self.copy_stream)             # device-side bracket of the whole call
             for i, hb in enumerate(host_batches):
                 s = i & 1
                 b = hb.shape[0]
@@ -62,11 +66,12 @@ class TileDetector:
                     planes = self.detect_device(self.dev_in[s][:b])
                     self.in_free[s].record(self.compute_stream)
                     self.out_ready[s].record(self.compute_stream)
-                with torch.cuda.stream(self.copy_stream):
-                    self.copy_stream.wait_event(self.out_ready[s])
+                with torch.cuda.stream(self.d2h_stream):
+                    self.d2h_stream.wait_event(self.out_ready[s])
                     out = self._host_ring[i, :, :b]
                     out.copy_(planes, non_blocking=True)
-                    planes.record_stream(self.copy_stream)
+                    planes.record_stream(self.d2h_stream)
                     results.append(out)
-            self.copy_stream.synchronize()
+            self.t_last.record(self.d2h_stream)
+            self.d2h_stream.synchronize()
         return results

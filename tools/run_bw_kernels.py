@@ -1,0 +1,19 @@
+"""Runs decode / render / loss a few times at 2048 tiles (profiling target). GPU box only."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import scd_resnet_b200 as S
+from scd_resnet_b200 import synthetic
+dev = torch.device("cuda"); N = 2048
+g = torch.Generator(device=dev).manual_seed(0)
+heat = torch.randn(N, 1, 128, 128, device=dev, generator=g) * 1.5 - 2
+regr = torch.randn(N, 4, 128, 128, device=dev, generator=g)
+off = torch.randn(N, 2, 128, 128, device=dev, generator=g)
+locs, counts = synthetic.make_objects(N, seed=1)
+locs, counts = locs.to(dev), counts.to(dev)
+for _ in range(3):
+    S.ops.decode_topk(heat, regr, off, K=100)
+    gt = S.ops.render_targets(locs, counts)
+    S.ops.centernet_loss(heat.clone(), regr, off, *gt, sigmoid_inplace=False)
+torch.cuda.synchronize()
+print("ok")
