@@ -57,6 +57,11 @@ int scd_decode_topk(const float* heat, const float* regr, const float* offset,
                     float* scores, int64_t* idx, int64_t* ys, int64_t* xs,
                     float* off_out, float* regr_out, float* planes, void* stream);
 
+/* Exhaustive device-side check (all 2^32 fp32 patterns) of the arithmetic facts the decode kernel's
+ * logit-space peak test relies on; d_counts3[0..2] receive the number of violations of
+ * (0) monotonicity of the fp32 sigmoid, (1) the collapse screen, (2) the logit bound.  Test hook. */
+int scd_selftest_decode_math(unsigned long long* d_counts3, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Target rendering.  Replaces the target part of SCD.argumentation
  * (datasets/scds/scdx16p100.py:514-536), SCD.drawGaussian (:575-591),
@@ -70,6 +75,11 @@ int scd_decode_topk(const float* heat, const float* regr, const float* offset,
  * ---------------------------------------------------------------------------------- */
 int scd_render_targets(const float* locs, const int32_t* counts, int batch,
                        float* heat, uint8_t* mask, float* regr6, int64_t* idx, void* stream);
+/* Same, and *d_npos = count(heat == 1) over the batch: the N_pos of focalLoss (models/losses/focal.py:42),
+ * counted while the heat map is written so that scd_centernet_loss_sparse need not read gt twice. */
+int scd_render_targets_npos(const float* locs, const int32_t* counts, int batch,
+                            float* heat, uint8_t* mask, float* regr6, int64_t* idx,
+                            unsigned int* d_npos, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * CenterNetLoss forward + backward in one pass.  Replaces CenterNetLoss.forward
@@ -89,6 +99,18 @@ int scd_centernet_loss(const float* heat, float* prob_out, const float* regr, co
                        float regr_w, float off_w, float* losses,
                        float* d_heat, float* d_regr, float* d_off,
                        void* workspace, size_t workspace_bytes, void* stream);
+/* Sparse form, what the training step uses.  The two masked-L1 terms touch regr / offset at the <= max_tags
+ * object pixels only, so their gradients are returned as d_obj (B,max_tags,6) f32 =
+ * d total / d (regr[0..3], offset[0..1]) at pixel idx[b,k] (zero where mask is 0; objects sharing a pixel
+ * add up) instead of six dense planes.  d_npos (nullable) = count(gt_heat == 1) over the batch if the
+ * caller already knows it (scd_render_targets_npos): the counting pass over gt_heat is then skipped and the
+ * call moves the algorithmic minimum of HBM traffic (logits + gt read once, d_heat written once). */
+int scd_centernet_loss_sparse(const float* heat, float* prob_out, const float* regr, const float* offset,
+                              const float* gt_heat, const uint8_t* mask, const float* regr6,
+                              const int64_t* idx, int batch, int height, int width, int max_tags,
+                              float regr_w, float off_w, const unsigned int* d_npos, float* losses,
+                              float* d_heat, float* d_obj,
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Stem.  Replaces ResNet.preprocess (models/backbones/residuals.py:210-215):

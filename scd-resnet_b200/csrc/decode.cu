@@ -1,41 +1,71 @@
 // Heat-map decode: sigmoid -> 3x3 peak NMS -> per-image top-K -> gather.
 //
 // Replaces decodeCenterNet (ref: models/centerNetOffset.py:219-251) and the helpers it
-// calls (ref: models/backbones/utility.py:76-118).  HBM-bound: the heat map is read once
-// (10 row loads per 8 rows, the two halo rows come from L2), regr/offset are touched at K
-// points only.  One CTA per image, 16 warps; a warp owns 8 full rows (one row = 32 lanes x
-// float4 = one coalesced 512 B request) and keeps its 8x128 NMS-ed scores in registers for
-// the whole selection, so nothing but histograms lives in shared memory.
+// calls (ref: models/backbones/utility.py:76-118).  HBM-bound: the heat map is read exactly
+// once (one coalesced 512 B request per row), regr/offset are touched at K points only.
 //
-// Selection is exact and deterministic: (score desc, flat index asc).  The K-th largest
-// score T is found by a 4-pass 8-bit radix select over the float bit patterns (scores are
-// >= 0, so the unsigned order is the float order); ties at T are resolved by taking the
-// smallest flat indices via per-row counts; the K survivors are bitonic-sorted.
+// One WARP per image, no block-level barrier anywhere:
+//
+//   * the peak test runs on the LOGITS.  fp32 sigmoid is monotone non-decreasing, so
+//     max3x3(sigmoid(x)) == sigmoid(max3x3(x)) and the reference's keep mask
+//     (maxpool(p) == p, utility.py:87-92) is  sigmoid(m) == sigmoid(x)  with m = max3x3(x).
+//     That holds trivially at logit peaks (x == m); for x < m it needs the two sigmoids to
+//     round to the same float, which is only possible when m - x is tiny or the sigmoid is
+//     saturated.  Pixels are therefore screened with  m - x < thr(x)  (a bound far above the
+//     largest collapsing gap, checked exhaustively over all floats by scd_selftest_decode_math)
+//     and the sigmoid is evaluated only for the screened candidates, compacted 32 at a time
+//     so every lane does useful work;
+//   * selection is a streaming exact top-K: candidates are appended, in ascending flat-index
+//     order, to a 512-entry buffer in shared memory; when it fills, an exact 4 x 8-bit radix
+//     select finds the K-th largest score T, the buffer is compacted (stably) to the K best and
+//     from then on only scores > T are admitted (a later pixel that ties with T loses to the
+//     earlier ones).  A logit-space bound tau_x with sigmoid(x <= tau_x) <= T lets whole rows be
+//     skipped with one vote.  Expected appends for K = 100 on white noise: ~1.3 k of 16 k pixels;
+//   * the K survivors are bitonic-sorted in registers: (score desc, flat index asc), the
+//     deterministic order of SURVEY 8c; fewer than K positive peaks -> zero scores at the
+//     smallest flat indices.
 #include "common.cuh"
 #include <math_constants.h>
 
 namespace scd {
 
-constexpr int DEC_THREADS = 512;
-constexpr int DEC_WARPS = DEC_THREADS / 32;
 constexpr int DEC_HW = 128;
-constexpr int DEC_ROWS = DEC_HW / DEC_WARPS;   // rows per warp = 8
 constexpr int DEC_MAXK = 128;
+constexpr int DEC_BUF = 512;            // survivor buffer entries per image
+constexpr int DEC_Q = 256;              // candidate ring entries (>= 31 pending + 128 of one row)
+constexpr unsigned FULL = 0xffffffffu;
 
-struct DecodeSmem {
-    unsigned hist[DEC_WARPS][256];
-    unsigned warp_tot[DEC_WARPS];
-    int rowcnt[DEC_HW];
-    unsigned long long keys[DEC_MAXK];
-    unsigned bcast[8];
-    unsigned count;
+struct alignas(16) DecWarp {
+    unsigned buf_s[DEC_BUF];            // sigmoid bit patterns of the survivors, ascending flat-index order
+    unsigned short buf_i[DEC_BUF];      // their flat indices
+    float q_x[DEC_Q], q_m[DEC_Q];       // candidate ring: logit, 3x3 max logit   (reused as 128 x u64 sort keys)
+    unsigned short q_i[DEC_Q];          //                 flat index
+    unsigned hist[256];
+    unsigned head, nbuf, tau;           // warp-uniform state: ring head, buffer fill, admission threshold (bits)
+    float tau_x;                        // logits <= tau_x cannot beat tau
 };
 
+// Collapse screen: sigmoid(m) == sigmoid(x) with m > x requires m - x below this bound (x <= 8; above that the
+// sigmoid is close to saturation and the pixel is always evaluated).  The largest collapsing gap is about
+// 2^-22 (1 + e^x): 2.4e-7 at x <= 0, 7e-4 at x = 8; the bound 1e-5 + 1e-2 max(x, 0) is 40x .. 100x above it.
+__device__ __forceinline__ float collapse_bound(float x) { return fmaf(1e-2f, fmaxf(x, 0.f), 1e-5f); }
+constexpr float DEC_SAT = 8.f;
+
+// A logit bound for a score threshold: every x <= logit_bound(T) has sigmoid(x) <= T.
+// logit(T) minus a margin that covers 8 ulp of error in the sigmoid and the rounding of this inverse.
+__device__ __forceinline__ float logit_bound(unsigned t_bits) {
+    const float t = __uint_as_float(t_bits);
+    if (t >= 1.f) return CUDART_INF_F;               // K scores are already 1.0: nothing can be larger
+    const float om = 1.f - t;
+    const float x = logf(t / om);
+    return x - (1e-3f * (1.f + fabsf(x)) + 9.5367431640625e-7f / om);
+}
+
 __device__ __forceinline__ float4 hmax3(float4 p, int lane) {
-    float left = __shfl_up_sync(0xffffffffu, p.w, 1);
-    float right = __shfl_down_sync(0xffffffffu, p.x, 1);
-    if (lane == 0) left = -CUDART_INF_F;       // max_pool2d pads with -inf
-    if (lane == 31) right = -CUDART_INF_F;
+    float left = __shfl_up_sync(FULL, p.w, 1);
+    float right = __shfl_down_sync(FULL, p.x, 1);
+    if (lane == 0) left = p.x;          // max_pool2d pads with -inf: repeating an in-window value is equivalent
+    if (lane == 31) right = p.w;
     float4 m;
     m.x = fmaxf(fmaxf(left, p.x), p.y);
     m.y = fmaxf(fmaxf(p.x, p.y), p.z);
@@ -44,22 +74,119 @@ __device__ __forceinline__ float4 hmax3(float4 p, int lane) {
     return m;
 }
 
-__device__ __forceinline__ float4 sigmoid4(float4 x) {
-    return make_float4(sigmoidf_ref(x.x), sigmoidf_ref(x.y), sigmoidf_ref(x.z), sigmoidf_ref(x.w));
-}
-
-__device__ __forceinline__ int block_sum(int v, DecodeSmem& s, int warp, int lane) {
-    v = warp_sum(v);
-    __syncthreads();
-    if (lane == 0) s.warp_tot[warp] = (unsigned)v;
-    __syncthreads();
-    int t = 0;
+// Exact K-th largest of buf_s[0, nbuf) (nbuf > K) by radix select, then stable compaction to the K best:
+// scores > T, and the first need_eq (smallest flat index) of those == T.  Returns the new fill (= K).
+__device__ __forceinline__ unsigned dec_prune(DecWarp& w, unsigned nbuf, int K)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned prefix = 0u, known = 0u, k_rem = (unsigned)K;
+#pragma unroll 1
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
 #pragma unroll
-    for (int w = 0; w < DEC_WARPS; ++w) t += (int)s.warp_tot[w];
-    return t;
+        for (int i = 0; i < 8; ++i) w.hist[i * 32 + lane] = 0u;
+        __syncwarp();
+        for (unsigned j = lane; j < nbuf; j += 32) {
+            const unsigned u = w.buf_s[j];
+            if ((u & known) == prefix) atomicAdd(&w.hist[(u >> shift) & 255u], 1u);
+        }
+        __syncwarp();
+        const uint4 a = *reinterpret_cast<const uint4*>(&w.hist[8 * lane]);       // lane owns digits [8 lane, 8 lane + 8)
+        const uint4 c = *reinterpret_cast<const uint4*>(&w.hist[8 * lane + 4]);
+        const unsigned t = a.x + a.y + a.z + a.w + c.x + c.y + c.z + c.w;
+        unsigned incl = t;                                                         // suffix sum: digits >= 8 lane
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned n = __shfl_down_sync(FULL, incl, o);
+            if (lane + o < 32) incl += n;
+        }
+        const unsigned above = incl - t;
+        const bool mine = above < k_rem && incl >= k_rem;
+        unsigned digit = 0u, newk = 0u;
+        if (mine) {
+            const unsigned cnt[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+            unsigned acc = above;
+#pragma unroll
+            for (int i = 7; i >= 0; --i) {
+                if (acc < k_rem && acc + cnt[i] >= k_rem) { digit = 8u * lane + i; newk = k_rem - acc; }
+                acc += cnt[i];
+            }
+        }
+        const int src = __ffs(__ballot_sync(FULL, mine)) - 1;
+        digit = __shfl_sync(FULL, digit, src);
+        newk = __shfl_sync(FULL, newk, src);
+        prefix |= digit << shift;
+        known |= 0xFFu << shift;
+        k_rem = newk;
+    }
+    const unsigned T = prefix, need_eq = k_rem;
+    unsigned out = 0u, eq_seen = 0u;
+    for (unsigned j0 = 0; j0 < nbuf; j0 += 32) {
+        const unsigned j = j0 + lane;
+        const bool valid = j < nbuf;
+        const unsigned u = valid ? w.buf_s[j] : 0u;
+        const unsigned short fi = valid ? w.buf_i[j] : (unsigned short)0;
+        const bool eq = valid && u == T;
+        const unsigned beq = __ballot_sync(FULL, eq);
+        const bool keep = valid && (u > T || (eq && eq_seen + __popc(beq & lt) < need_eq));
+        const unsigned bk = __ballot_sync(FULL, keep);       // also orders this chunk's reads before its writes
+        if (keep) {
+            const unsigned pos = out + __popc(bk & lt);      // pos <= j: never overwrites an unread entry
+            w.buf_s[pos] = u;
+            w.buf_i[pos] = fi;
+        }
+        out += __popc(bk);
+        eq_seen += __popc(beq);
+        __syncwarp();
+    }
+    if (lane == 0) { w.tau = T; w.tau_x = logit_bound(T); }
+    __syncwarp();
+    return out;
 }
 
-__global__ void __launch_bounds__(DEC_THREADS, 2)
+// Evaluates queued candidates 32 at a time (all of them when flush): sigmoid, collapse check, admission
+// against tau, append to the survivor buffer; prunes when the buffer is nearly full.
+__device__ __noinline__ void dec_drain(DecWarp& w, unsigned tail, int K, bool flush)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned head = w.head, nbuf = w.nbuf, tau = w.tau;
+    for (;;) {
+        const unsigned avail = tail - head;
+        if (avail == 0u || (avail < 32u && !flush)) break;
+        const unsigned n = avail < 32u ? avail : 32u;
+        bool ok = false;
+        unsigned bits = 0u;
+        unsigned short fi = 0;
+        if ((unsigned)lane < n) {
+            const unsigned e = (head + lane) & (DEC_Q - 1);
+            const float x = w.q_x[e], m = w.q_m[e];
+            fi = w.q_i[e];
+            const float s = sigmoidf_ref(x);
+            bits = __float_as_uint(s);                       // s >= 0: unsigned order == float order
+            ok = bits > tau && (x == m || sigmoidf_ref(m) == s);
+        }
+        const unsigned bal = __ballot_sync(FULL, ok);
+        if (ok) {
+            const unsigned pos = nbuf + __popc(bal & lt);
+            w.buf_s[pos] = bits;
+            w.buf_i[pos] = fi;
+        }
+        nbuf += __popc(bal);
+        head += n;
+        __syncwarp();
+        if (nbuf > DEC_BUF - 32) {
+            nbuf = dec_prune(w, nbuf, K);
+            tau = w.tau;
+        }
+    }
+    if (lane == 0) { w.head = head; w.nbuf = nbuf; }
+    __syncwarp();
+}
+
+template <int WPC>
+__global__ void __launch_bounds__(WPC * 32)
 decode_kernel(const float* __restrict__ heat, const float* __restrict__ regr,
               const float* __restrict__ offset, int batch, int K,
               float* __restrict__ scores, int64_t* __restrict__ idx_out,
@@ -67,198 +194,154 @@ decode_kernel(const float* __restrict__ heat, const float* __restrict__ regr,
               float* __restrict__ off_out, float* __restrict__ regr_out,
               float* __restrict__ planes)
 {
-    __shared__ DecodeSmem s;
-    const int b = blockIdx.x;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int r0 = warp * DEC_ROWS;
+    __shared__ DecWarp sm[WPC];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * WPC + warp;
+    if (b >= batch) return;                                  // warps are independent: no block barrier below
+    DecWarp& w = sm[warp];
+    if (lane == 0) { w.head = 0u; w.nbuf = 0u; w.tau = 0u; w.tau_x = -CUDART_INF_F; }
+    __syncwarp();
+
+    // ---- stream the heat map: rolling 3-row window on logits, loads 8 rows ahead ----------------
     const float4* hp = reinterpret_cast<const float4*>(heat + (size_t)b * DEC_HW * DEC_HW) + lane;
     const float4 ninf = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+    float4 ring[8];
+    float4 x_cur = ld_stream(hp);
+#pragma unroll
+    for (int j = 1; j <= 8; ++j) ring[j & 7] = ld_stream(hp + j * (DEC_HW / 4));
+    float4 hm_prev = ninf, hm_cur = hmax3(x_cur, lane);
+    unsigned tail = 0u, pending = 0u;
+    float tau_x = -CUDART_INF_F;
 
-    if (tid < DEC_MAXK) s.keys[tid] = 0ull;
-    if (tid == 0) s.count = 0u;
+#pragma unroll 1
+    for (int r8 = 0; r8 < DEC_HW; r8 += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int r = r8 + u;
+            const int slot = (u + 1) & 7;
+            const float4 x_next = ring[slot];
+            if (r + 9 < DEC_HW) ring[slot] = ld_stream(hp + (r + 9) * (DEC_HW / 4));
+            const float4 hm_next = (r + 1 < DEC_HW) ? hmax3(x_next, lane) : ninf;
+            {
+                const float xv[4] = {x_cur.x, x_cur.y, x_cur.z, x_cur.w};
+                const float mv[4] = {fmaxf(fmaxf(hm_prev.x, hm_cur.x), hm_next.x), fmaxf(fmaxf(hm_prev.y, hm_cur.y), hm_next.y),
+                                     fmaxf(fmaxf(hm_prev.z, hm_cur.z), hm_next.z), fmaxf(fmaxf(hm_prev.w, hm_cur.w), hm_next.w)};
+                // branch-free screen: above the running bound, and (saturating, or not separated from the window
+                // max); written with !(>=) so that inf - inf = NaN counts as "not separated"
+                bool cand[4];
+                unsigned bal[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    cand[c] = (xv[c] > tau_x) & ((xv[c] > DEC_SAT) | !(mv[c] - xv[c] >= collapse_bound(xv[c])));
+                    bal[c] = __ballot_sync(FULL, cand[c]);
+                }
+                if ((bal[0] | bal[1] | bal[2] | bal[3]) != 0u) {
+                    const unsigned ltm = (1u << lane) - 1u;
+                    // queue order = ascending flat index: lanes first, then the lane's four columns
+                    unsigned pos = tail + __popc(bal[0] & ltm) + __popc(bal[1] & ltm) + __popc(bal[2] & ltm) + __popc(bal[3] & ltm);
+                    const unsigned total = __popc(bal[0]) + __popc(bal[1]) + __popc(bal[2]) + __popc(bal[3]);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (cand[c]) {
+                            const unsigned e = pos & (DEC_Q - 1);
+                            w.q_x[e] = xv[c];
+                            w.q_m[e] = mv[c];
+                            w.q_i[e] = (unsigned short)(r * DEC_HW + lane * 4 + c);
+                            ++pos;
+                        }
+                    }
+                    tail += total;
+                    pending += total;
+                    __syncwarp();
+                    if (pending >= 32u) {
+                        dec_drain(w, tail, K, false);
+                        pending &= 31u;
+                        tau_x = w.tau_x;
+                    }
+                }
+            }
+            hm_prev = hm_cur; hm_cur = hm_next; x_cur = x_next;
+        }
+    }
+    if (pending) dec_drain(w, tail, K, true);
+    unsigned nb = w.nbuf;
+    if (nb > (unsigned)K) nb = dec_prune(w, nb, K);
 
-    // ---- sigmoid + 3x3 peak test, rolling 3-row window ---------------------------------
-    unsigned v[DEC_ROWS * 4];
+    // ---- sort keys: (score bits << 32) | ~flat, padded with zero-score pixels at the smallest indices ------
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(w.q_x);       // 128 slots over q_x | q_m
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const unsigned t = i * 32 + lane;
+        keys[t] = t < nb ? ((unsigned long long)w.buf_s[t] << 32) | (unsigned long long)(0xFFFFFFFFu - w.buf_i[t]) : 0ull;
+    }
+    __syncwarp();
+    if (nb < (unsigned)K) {
+        // every pixel outside the buffer scores 0; the K - nb smallest such flat indices lie in [0, K)
+        const unsigned Z = (unsigned)K - nb;
+        unsigned zseen = 0u;
+        for (unsigned j0 = 0; j0 < (unsigned)K; j0 += 32) {
+            const unsigned j = j0 + lane;
+            int lo = 0, hi = (int)nb;                        // buf_i is ascending: binary search
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (w.buf_i[mid] < j) lo = mid + 1; else hi = mid; }
+            const bool z = j < (unsigned)K && !(lo < (int)nb && w.buf_i[lo] == j);
+            const unsigned bz = __ballot_sync(FULL, z);
+            const unsigned rank = zseen + __popc(bz & lt);
+            if (z && rank < Z) keys[nb + rank] = (unsigned long long)(0xFFFFFFFFu - j);
+            zseen += __popc(bz);
+        }
+        __syncwarp();
+    }
+
+    // ---- bitonic sort of 128 keys, descending; key i lives in lane i / 4, register i % 4 -----------------
+    unsigned long long key[4];
     {
-        // loads run DEC_AHEAD rows ahead of the row being finished: enough bytes in flight to
-        // cover HBM latency without holding all 10 rows in registers at once
-        constexpr int DEC_AHEAD = 4;
-        float4 raw[DEC_ROWS + 2];
-#pragma unroll
-        for (int j = 0; j < DEC_AHEAD + 2; ++j) {
-            const int r = r0 - 1 + j;
-            if (r >= 0 && r < DEC_HW) raw[j] = ld_stream(hp + r * (DEC_HW / 4));
-        }
-        float4 p_cur, hm_prev, hm_cur;
-        hm_prev = (r0 - 1 >= 0) ? hmax3(sigmoid4(raw[0]), lane) : ninf;
-        p_cur = sigmoid4(raw[1]);
-        hm_cur = hmax3(p_cur, lane);
-#pragma unroll
-        for (int j = 0; j < DEC_ROWS; ++j) {
-            if (j + 2 + DEC_AHEAD < DEC_ROWS + 2) {
-                const int r = r0 + 1 + j + DEC_AHEAD;
-                if (r < DEC_HW) raw[j + 2 + DEC_AHEAD] = ld_stream(hp + r * (DEC_HW / 4));
-            }
-            float4 p_next = ninf, hm_next = ninf;
-            if (r0 + j + 1 < DEC_HW) {                 // warp-uniform
-                p_next = sigmoid4(raw[j + 2]);
-                hm_next = hmax3(p_next, lane);
-            }
-            const float mx = fmaxf(fmaxf(hm_prev.x, hm_cur.x), hm_next.x);
-            const float my = fmaxf(fmaxf(hm_prev.y, hm_cur.y), hm_next.y);
-            const float mz = fmaxf(fmaxf(hm_prev.z, hm_cur.z), hm_next.z);
-            const float mw = fmaxf(fmaxf(hm_prev.w, hm_cur.w), hm_next.w);
-            // heat * keep: p * 1.0f = p, p * 0.0f = 0.0f (utility.py:91-92)
-            v[j * 4 + 0] = (mx == p_cur.x) ? __float_as_uint(p_cur.x) : 0u;
-            v[j * 4 + 1] = (my == p_cur.y) ? __float_as_uint(p_cur.y) : 0u;
-            v[j * 4 + 2] = (mz == p_cur.z) ? __float_as_uint(p_cur.z) : 0u;
-            v[j * 4 + 3] = (mw == p_cur.w) ? __float_as_uint(p_cur.w) : 0u;
-            hm_prev = hm_cur; hm_cur = hm_next; p_cur = p_next;
-        }
+        const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(keys + lane * 4);
+        const ulonglong2 k23 = *reinterpret_cast<const ulonglong2*>(keys + lane * 4 + 2);
+        key[0] = k01.x; key[1] = k01.y; key[2] = k23.x; key[3] = k23.y;
     }
-
-    // ---- threshold T = K-th largest score ----------------------------------------------
-    int nz = 0;
 #pragma unroll
-    for (int e = 0; e < DEC_ROWS * 4; ++e) nz += (v[e] != 0u);
-    const int nnz = block_sum(nz, s, warp, lane);
-
-    unsigned T = 0u;
-    unsigned need_eq;
-    if (nnz >= K) {
-        unsigned prefix = 0u, known = 0u, k_rem = (unsigned)K;
-#pragma unroll 1
-        for (int pass = 0; pass < 4; ++pass) {
-            const int shift = 24 - 8 * pass;
-            __syncthreads();
-            for (int i = tid; i < DEC_WARPS * 256; i += DEC_THREADS) (&s.hist[0][0])[i] = 0u;
-            __syncthreads();
-#pragma unroll
-            for (int e = 0; e < DEC_ROWS * 4; ++e) {
-                const unsigned u = v[e];
-                if (u != 0u && (u & known) == prefix) atomicAdd(&s.hist[warp][(u >> shift) & 255u], 1u);
-            }
-            __syncthreads();
-            unsigned t = 0u, incl = 0u;
-            if (tid < 256) {
-#pragma unroll
-                for (int w = 0; w < DEC_WARPS; ++w) t += s.hist[w][tid];
-                incl = t;                                   // suffix-inclusive sum inside the warp
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned n = __shfl_down_sync(0xffffffffu, incl, o);
-                    if (lane + o < 32) incl += n;
-                }
-                if (lane == 0) s.warp_tot[warp] = incl;
-            }
-            __syncthreads();
-            if (tid < 256) {
-                unsigned higher = 0u;
-                for (int w = warp + 1; w < 8; ++w) higher += s.warp_tot[w];
-                const unsigned S = incl + higher;           // #candidates with digit >= tid
-                const unsigned S_next = S - t;              // #candidates with digit >  tid
-                if (S >= k_rem && S_next < k_rem) { s.bcast[0] = (unsigned)tid; s.bcast[1] = k_rem - S_next; }
-            }
-            __syncthreads();
-            prefix |= s.bcast[0] << shift;
-            known |= 0xFFu << shift;
-            k_rem = s.bcast[1];
-        }
-        T = prefix;
-        need_eq = k_rem;
-    } else {
-        need_eq = (unsigned)(K - nnz);      // fill with zeros, smallest flat indices first
-    }
-
-    // ---- among scores == T keep the need_eq smallest flat indices ----------------------
-#pragma unroll
-    for (int j = 0; j < DEC_ROWS; ++j) {
-        int c = (v[j * 4] == T) + (v[j * 4 + 1] == T) + (v[j * 4 + 2] == T) + (v[j * 4 + 3] == T);
-        c = warp_sum(c);
-        if (lane == 0) s.rowcnt[r0 + j] = c;
-    }
-    __syncthreads();
-    if (warp == 0) {
-        const int a0 = s.rowcnt[4 * lane], a1 = s.rowcnt[4 * lane + 1];
-        const int a2 = s.rowcnt[4 * lane + 2], a3 = s.rowcnt[4 * lane + 3];
-        const int tot = a0 + a1 + a2 + a3;
-        int incl = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += n;
-        }
-        int before = incl - tot;
-        const int a[4] = {a0, a1, a2, a3};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int after = before + a[i];
-            if (before < (int)need_eq && after >= (int)need_eq) {
-                s.bcast[2] = (unsigned)(4 * lane + i);
-                s.bcast[3] = need_eq - (unsigned)before;
-            }
-            before = after;
-        }
-    }
-    __syncthreads();
-    const int R = (int)s.bcast[2];
-    const int need_in_row = (int)s.bcast[3];
-
-#pragma unroll
-    for (int j = 0; j < DEC_ROWS; ++j) {
-        const int row = r0 + j;
-        int rank = 0;
-        if (row == R) {                      // warp-uniform
-            const int c = (v[j * 4] == T) + (v[j * 4 + 1] == T) + (v[j * 4 + 2] == T) + (v[j * 4 + 3] == T);
-            int incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int n = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += n;
-            }
-            rank = incl - c;
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const unsigned u = v[j * 4 + c];
-            bool take = u > T;
-            if (u == T) {
-                take = (row < R) || (row == R && rank < need_in_row);
-                ++rank;
-            }
-            if (take) {
-                const unsigned flat = (unsigned)(row * DEC_HW + lane * 4 + c);
-                const unsigned pos = atomicAdd(&s.count, 1u);
-                if (pos < DEC_MAXK) s.keys[pos] = ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
-            }
-        }
-    }
-
-    // ---- bitonic sort of the <=128 survivors, descending --------------------------------
-#pragma unroll 1
     for (int k = 2; k <= DEC_MAXK; k <<= 1) {
-#pragma unroll 1
+#pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
-            __syncthreads();
-            if (tid < DEC_MAXK) {
-                const int o = tid ^ j;
-                if (o > tid) {
-                    const unsigned long long a = s.keys[tid], c = s.keys[o];
-                    const bool desc = (tid & k) == 0;
-                    if (desc ? (a < c) : (a > c)) { s.keys[tid] = c; s.keys[o] = a; }
+            if (j >= 4) {
+                const int lj = j >> 2;
+                const bool desc = (lane & (k >> 2)) == 0;
+                const bool keep_max = desc == ((lane & lj) == 0);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const unsigned long long o = __shfl_xor_sync(FULL, key[r], lj);
+                    key[r] = keep_max ? (key[r] > o ? key[r] : o) : (key[r] < o ? key[r] : o);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if ((r & j) == 0) {
+                        const bool desc = k >= 4 ? (lane & (k >> 2)) == 0 : (r & k) == 0;
+                        const unsigned long long a = key[r], c = key[r | j];
+                        const bool sw = desc ? (a < c) : (a > c);
+                        key[r] = sw ? c : a;
+                        key[r | j] = sw ? a : c;
+                    }
                 }
             }
         }
     }
-    __syncthreads();
+    __syncwarp();
+    *reinterpret_cast<ulonglong2*>(keys + lane * 4) = make_ulonglong2(key[0], key[1]);
+    *reinterpret_cast<ulonglong2*>(keys + lane * 4 + 2) = make_ulonglong2(key[2], key[3]);
+    __syncwarp();
 
-    // ---- outputs -------------------------------------------------------------------------
-    if (tid < K) {
-        const unsigned long long key = s.keys[tid];
-        const float sc = __uint_as_float((unsigned)(key >> 32));
-        const unsigned flat = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
-        const int y = (int)(flat / DEC_HW), x = (int)(flat % DEC_HW);     // utility.py:115-117
-        const size_t o = (size_t)b * K + tid;
+    // ---- outputs (rank t = i * 32 + lane: coalesced) ----------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int t = i * 32 + lane;
+        if (t >= K) break;
+        const unsigned long long kk = keys[t];
+        const float sc = __uint_as_float((unsigned)(kk >> 32));
+        const unsigned flat = 0xFFFFFFFFu - (unsigned)(kk & 0xFFFFFFFFull);
+        const int y = (int)(flat / DEC_HW), x = (int)(flat % DEC_HW);             // utility.py:115-117
+        const size_t o = (size_t)b * K + t;
         scores[o] = sc;
         idx_out[o] = (int64_t)flat;
         ys[o] = (int64_t)y;
@@ -286,7 +369,40 @@ decode_kernel(const float* __restrict__ heat, const float* __restrict__ regr,
     }
 }
 
+// Exhaustive check, over every fp32 bit pattern, of the three properties decode_kernel relies on:
+//   counts[0]: sigmoid is monotone:            sigmoid(x) <= sigmoid(next float above x)
+//   counts[1]: the collapse screen is safe:    sigmoid(x + bound(x) / 2) > sigmoid(x)   whenever sigmoid(x) > 0
+//   counts[2]: the logit bound is safe:        sigmoid(logit_bound(T)) <= T   for T = sigmoid(x)
+__global__ void decode_math_selftest_kernel(unsigned long long* counts)
+{
+    unsigned bad0 = 0, bad1 = 0, bad2 = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32);
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((unsigned)i);
+        if (!(fabsf(x) <= CUDART_MAX_NORMAL_F)) continue;                        // skip inf / nan
+        const float s = sigmoidf_ref(x);
+        const float xn = nextafterf(x, CUDART_INF_F);
+        if (fabsf(xn) <= CUDART_MAX_NORMAL_F && sigmoidf_ref(xn) < s) ++bad0;
+        const float bnd = collapse_bound(x);
+        if (s > 0.f && x <= DEC_SAT && !(sigmoidf_ref(x + 0.5f * bnd) > s)) ++bad1;
+        const float lb = logit_bound(__float_as_uint(s));
+        if (lb > -CUDART_INF_F && lb < CUDART_INF_F && sigmoidf_ref(lb) > s) ++bad2;
+    }
+    if (bad0) atomicAdd(counts + 0, (unsigned long long)bad0);
+    if (bad1) atomicAdd(counts + 1, (unsigned long long)bad1);
+    if (bad2) atomicAdd(counts + 2, (unsigned long long)bad2);
+}
+
 }  // namespace scd
+
+extern "C" int scd_selftest_decode_math(unsigned long long* counts3, void* stream)
+{
+    if (!counts3) return scd::fail(SCD_EINVAL, "scd_selftest_decode_math: null pointer");
+    SCD_CUDA_CHECK(cudaMemsetAsync(counts3, 0, 3 * sizeof(unsigned long long), (cudaStream_t)stream));
+    scd::decode_math_selftest_kernel<<<scd::kNumSMs * 16, 256, 0, (cudaStream_t)stream>>>(counts3);
+    SCD_LAUNCH_CHECK("decode_math_selftest_kernel");
+    return SCD_OK;
+}
 
 extern "C" int scd_decode_topk(const float* heat, const float* regr, const float* offset,
                                int batch, int classes, int height, int width, int K,
@@ -300,8 +416,13 @@ extern "C" int scd_decode_topk(const float* heat, const float* regr, const float
     if (K < 1 || K > scd::DEC_MAXK) return scd::fail(SCD_EINVAL, "scd_decode_topk: K must be in [1,128] (got %d)", K);
     if (!heat || !regr || !offset || !scores || !idx || !ys || !xs || !off_out || !regr_out)
         return scd::fail(SCD_EINVAL, "scd_decode_topk: null pointer");
-    scd::decode_kernel<<<batch, scd::DEC_THREADS, 0, (cudaStream_t)stream>>>(
-        heat, regr, offset, batch, K, scores, idx, ys, xs, off_out, regr_out, planes);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (batch <= 2 * scd::kNumSMs)          // few images: one warp per CTA so that they spread over the SMs
+        scd::decode_kernel<1><<<batch, 32, 0, st>>>(heat, regr, offset, batch, K, scores, idx, ys, xs, off_out,
+                                                    regr_out, planes);
+    else
+        scd::decode_kernel<2><<<(batch + 1) / 2, 64, 0, st>>>(heat, regr, offset, batch, K, scores, idx, ys, xs,
+                                                              off_out, regr_out, planes);
     SCD_LAUNCH_CHECK("decode_kernel");
     return SCD_OK;
 }

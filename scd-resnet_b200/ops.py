@@ -56,11 +56,12 @@ def decode_topk(heat, regr, offset, K=100, planes=False):
     return out + (pl,) if planes else out
 
 
-def render_targets(locs, counts):
+def render_targets(locs, counts, with_npos=False):
     """Gaussian target rendering + batch contract (ref: datasets/scds/scdx16p100.py:328-356,514-536,575-591).
 
     locs (B,30,8) f32, counts (B,) i32 -> heat (B,1,128,128) f32, mask (B,30) bool, regr6 (B,30,6) f32,
-    idx (B,30) i64.
+    idx (B,30) i64.  With `with_npos` a fifth element is returned: count(heat == 1) over the batch, a u32
+    device scalar (stored as int32) that centernet_loss_sparse accepts as the focal loss's N_pos.
     """
     locs = _req(locs, torch.float32, "locs")
     counts = _req(counts, torch.int32, "counts")
@@ -73,6 +74,11 @@ def render_targets(locs, counts):
     regr6 = torch.empty(b, MAXTAGLEN, 6, dtype=torch.float32, device=dev)
     idx = torch.empty(b, MAXTAGLEN, dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
+        if with_npos:
+            npos = torch.empty(1, dtype=torch.int32, device=dev)
+            check(lib.scd_render_targets_npos(_ptr(locs), _ptr(counts), b, _ptr(heat), _ptr(mask), _ptr(regr6),
+                                              _ptr(idx), _ptr(npos), _stream()), "scd_render_targets_npos")
+            return heat, mask, regr6, idx, npos
         check(lib.scd_render_targets(_ptr(locs), _ptr(counts), b, _ptr(heat), _ptr(mask), _ptr(regr6), _ptr(idx),
                                      _stream()), "scd_render_targets")
     return heat, mask, regr6, idx
@@ -111,6 +117,47 @@ def centernet_loss(heat, regr, offset, gt_heat, mask, regr6, idx, regr_w=0.1, of
                                      regr_w, off_w, _ptr(losses), _ptr(d_heat), _ptr(d_regr), _ptr(d_off),
                                      _ptr(ws), nbytes, _stream()), "scd_centernet_loss")
     return losses, d_heat, d_regr, d_off
+
+
+_loss_ws = {}
+
+
+def centernet_loss_sparse(heat, regr, offset, gt_heat, mask, regr6, idx, regr_w=0.1, off_w=0.1, npos=None,
+                          sigmoid_inplace=False):
+    """CenterNetLoss fwd+bwd with the masked-L1 gradients in sparse form (what TrainEngine consumes).
+
+    Returns (losses f32[4], d_heat (B,1,H,W), d_obj (B,30,6) = d total / d (regr0..3, off0..1) at idx[b,k]).
+    `npos`: the device scalar of render_targets(with_npos=True); when given, gt_heat is read only once.
+    """
+    heat = _req(heat, torch.float32, "heatmap")
+    regr = _req(regr, torch.float32, "regr")
+    offset = _req(offset, torch.float32, "offset")
+    gt_heat = _req(gt_heat, torch.float32, "gt heat")
+    regr6 = _req(regr6, torch.float32, "gt regr")
+    idx = _req(idx, torch.int64, "gt idx")
+    if mask.dtype == torch.bool:
+        mask = mask.contiguous().view(torch.uint8)
+    mask = _req(mask, torch.uint8, "mask")
+    if npos is not None:
+        npos = _req(npos, torch.int32, "npos")
+    b, c, h, w = heat.shape
+    if c != 1:
+        raise ScdError("heatmap must have one class")
+    dev = heat.device
+    losses = torch.empty(4, dtype=torch.float32, device=dev)
+    d_heat = torch.empty_like(heat)
+    d_obj = torch.empty(b, mask.shape[1], 6, dtype=torch.float32, device=dev)
+    nbytes = lib.scd_centernet_loss_workspace_bytes(b, h, w)
+    key = (dev, nbytes)
+    ws = _loss_ws.get(key)                       # stream-ordered reuse: the workspace is reset by the call itself
+    if ws is None:
+        ws = _loss_ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.scd_centernet_loss_sparse(_ptr(heat), _ptr(heat if sigmoid_inplace else None), _ptr(regr),
+                                            _ptr(offset), _ptr(gt_heat), _ptr(mask), _ptr(regr6), _ptr(idx), b, h, w,
+                                            mask.shape[1], regr_w, off_w, _ptr(npos), _ptr(losses), _ptr(d_heat),
+                                            _ptr(d_obj), _ptr(ws), nbytes, _stream()), "scd_centernet_loss_sparse")
+    return losses, d_heat, d_obj
 
 
 def stem_fwd(x, weight, bias):

@@ -89,6 +89,57 @@ def test_decode_few_peaks_and_plateaus(S):
     assert idx[4].tolist() == [128 * 128 - 1] + list(range(99)) and (sc[4] > 0).sum() == 1
 
 
+def _gpu_topk_reference(heat, K):
+    """Same arithmetic as the reference on the GPU (ATen CUDA sigmoid = 1/(1+expf(-x)), max_pool2d, stable sort)."""
+    p = torch.sigmoid(heat.cuda())
+    v = (p * (F.max_pool2d(p, 3, 1, 1) == p).float()).view(p.shape[0], -1)
+    sc, idx = torch.sort(v, dim=1, descending=True, stable=True)      # ties: ascending flat index
+    return sc[:, :K].cpu(), idx[:, :K].cpu()
+
+
+def test_decode_math_selftest(S):
+    """All 2^32 floats: sigmoid monotone, collapse screen and logit bound safe (the decode kernel's premises)."""
+    counts = torch.zeros(3, dtype=torch.int64, device="cuda")
+    S.check(S.lib.scd_selftest_decode_math(counts.data_ptr(), torch.cuda.current_stream().cuda_stream), "selftest")
+    torch.cuda.synchronize()
+    assert counts.tolist() == [0, 0, 0]
+
+
+def test_decode_adversarial_maps(S):
+    """Selection logic under stress, bit exact against the same arithmetic run through ATen on the GPU:
+    ascending ramps (every pixel beats the running threshold), saturating logits (distinct logits collapse
+    to one sigmoid), quantised maps (mass ties), near-equal neighbours, a 301-image batch (2 warps / CTA)."""
+    g = torch.Generator().manual_seed(11)
+    yy, xx = torch.meshgrid(torch.arange(128.), torch.arange(128.), indexing="ij")
+    maps = [
+        1e-3 * (xx + 128 * yy) - 8.0,                                   # strictly ascending in flat index
+        -(1e-3 * (xx + 128 * yy)) + 8.0,                                # strictly descending
+        17.0 + 0.5 * torch.randn(128, 128, generator=g),                # straddles the 1 - 2^-24 / 1.0 collapse
+        12.0 + torch.randn(128, 128, generator=g),                      # near saturation: neighbours collapse
+        torch.round(4 * torch.randn(128, 128, generator=g)) / 4 - 1,    # quantised: exact ties everywhere
+        -95.0 + 8 * torch.rand(128, 128, generator=g),                  # around the exp overflow / denormal edge
+        1e-7 * torch.randn(128, 128, generator=g),                      # sigmoid ~ 0.5: sub-ulp neighbours
+        torch.where(torch.rand(128, 128, generator=g) < 0.004, 3.0 + torch.randn(128, 128, generator=g),
+                    torch.full((128, 128), -30.0)),                     # ~65 isolated peaks < K on a flat floor
+        (torch.arange(128 * 128) % 7).float().reshape(128, 128) * 0.3 - 2,   # periodic plateaus
+    ]
+    heat = torch.stack(maps).unsqueeze(1).contiguous()
+    heat = torch.cat([heat, 1.5 * torch.randn(301 - len(maps), 1, 128, 128, generator=g) - 2])
+    B = heat.shape[0]
+    regr = torch.randn(B, 4, 128, 128, generator=g)
+    off = torch.randn(B, 2, 128, 128, generator=g)
+    for K in (100, 128, 7):
+        out = S.ops.decode_topk(dev(heat), dev(regr), dev(off), K=K, planes=True)
+        sc, idx, ys, xs, o, r, planes = [t.cpu() for t in out]
+        esc, eidx = _gpu_topk_reference(heat, K)
+        assert torch.equal(idx, eidx), [b for b in range(B) if not torch.equal(idx[b], eidx[b])][:10]
+        assert torch.equal(sc, esc)
+        assert torch.equal(r, regr.view(B, 4, -1).gather(2, idx.unsqueeze(1).expand(B, 4, K)).permute(0, 2, 1))
+        assert torch.equal(o, off.view(B, 2, -1).gather(2, idx.unsqueeze(1).expand(B, 2, K)).permute(0, 2, 1))
+        assert torch.equal(ys * 128 + xs, idx)
+        assert torch.equal(planes[0], sc) and torch.equal(planes[1], idx.float())
+
+
 def test_decode_rejects_bad_shapes(S):
     z = torch.zeros(1, 1, 64, 64, device="cuda")
     with pytest.raises(S.ScdError):
@@ -120,7 +171,58 @@ def test_render_targets_large_batch(S):
     assert torch.equal(heat == 1, eh == 1) and relmax(heat, eh) < 1e-6
 
 
+def test_render_targets_overlapping_objects_and_npos(S):
+    """Objects piled on top of each other: the kernel draws non-overlapping objects concurrently and must keep
+    the list order (fp32 rounding after every object) wherever windows overlap.  Also the N_pos by-product."""
+    rng = np.random.default_rng(17)
+    B = 48
+    locs = torch.zeros(B, 30, 8)
+    counts = torch.full((B,), 30, dtype=torch.int32)
+    for b in range(B):
+        spread = [2.0, 6.0, 20.0, 64.0][b % 4]                       # tight pile ... whole map
+        c = 64 + spread * rng.standard_normal((30, 2))
+        locs[b, :, 0:2] = torch.from_numpy(c).float()
+        locs[b, :, 2:4] = torch.from_numpy(rng.uniform(0, 4, (30, 2))).float()
+        locs[b, :, 4:6] = torch.from_numpy(3 * rng.standard_normal((30, 2))).float()
+        locs[b, :, 6] = torch.from_numpy(rng.uniform(1, 3, 30)).float()
+        locs[b, :, 7] = torch.from_numpy(rng.uniform(3, 7, 30)).float()
+    counts[5] = 0
+    counts[6] = 1
+    heat, mask, regr6, idx, npos = S.ops.render_targets(dev(locs), dev(counts), with_npos=True)
+    eh, em, er, ei = O.render_targets(locs, counts)
+    assert torch.equal(mask.cpu(), em) and torch.equal(idx.cpu(), ei) and torch.equal(regr6.cpu(), er)
+    assert torch.equal(heat.cpu() == 1, eh == 1) and torch.equal(heat.cpu() == 0, eh == 0)
+    assert relmax(heat, eh) < 1e-6
+    assert int(npos.item()) == int((heat == 1).sum().item()) == int((eh == 1).sum().item())
+    h2 = S.ops.render_targets(dev(locs), dev(counts))[0]
+    assert torch.equal(h2, heat)                                       # deterministic, with or without the counter
+
+
 # ------------------------------------------------------------------------------ loss
+def test_centernet_loss_sparse_matches_dense(S):
+    rng = np.random.default_rng(31)
+    B = 16
+    locs, counts = O.make_objects(B, seed=31)
+    locs[3, 1, 0:2] = locs[3, 0, 0:2]                                  # two objects on one pixel: gradients add
+    counts[3] = max(int(counts[3]), 2)
+    gt = S.ops.render_targets(dev(locs), dev(counts), with_npos=True)
+    heat = dev(torch.from_numpy((2.0 * rng.standard_normal((B, 1, 128, 128)) - 2).astype(np.float32)))
+    regr = dev(torch.from_numpy(rng.standard_normal((B, 4, 128, 128)).astype(np.float32)))
+    off = dev(torch.from_numpy(rng.standard_normal((B, 2, 128, 128)).astype(np.float32)))
+    l0, dh0, dr0, do0 = S.ops.centernet_loss(heat, regr, off, *gt[:4], sigmoid_inplace=False)
+    for npos in (None, gt[4]):
+        l1, dh1, dobj = S.ops.centernet_loss_sparse(heat, regr, off, *gt[:4], npos=npos)
+        assert torch.equal(l0, l1) and torch.equal(dh0, dh1)
+        dr = torch.zeros_like(dr0).view(B, 4, -1)
+        do = torch.zeros_like(do0).view(B, 2, -1)
+        ii = gt[3].unsqueeze(1)
+        dr.scatter_add_(2, ii.expand(B, 4, 30), dobj[:, :, 0:4].permute(0, 2, 1).contiguous())
+        do.scatter_add_(2, ii.expand(B, 2, 30), dobj[:, :, 4:6].permute(0, 2, 1).contiguous())
+        assert torch.allclose(dr.view_as(dr0), dr0, rtol=0, atol=1e-9)
+        assert torch.allclose(do.view_as(do0), do0, rtol=0, atol=1e-9)
+        assert (dobj[~gt[1]] == 0).all()
+
+
 def _loss_case(S, batch, seed, empty=False):
     rng = np.random.default_rng(seed)
     locs, counts = O.make_objects(batch, seed=seed)

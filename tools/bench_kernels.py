@@ -42,12 +42,18 @@ locs, counts = synthetic.make_objects(N, seed=1)
 locs, counts = locs.to(dev), counts.to(dev)
 ms = timeit(lambda: S.ops.render_targets(locs, counts))
 out["render"] = {"samples": N, "ms": ms, "alg_bytes_per_sample": 65536 + 960, "gbs": 66496 * N / ms / 1e6, "frac": 66496 * N / ms / 1e6 / HBM}
-gt = S.ops.render_targets(locs, counts)
+gt = S.ops.render_targets(locs, counts, with_npos=True)
+ms = timeit(lambda: S.ops.render_targets(locs, counts, with_npos=True))
+out["render_npos"] = {"ms": ms, "frac": 66496 * N / ms / 1e6 / HBM}
 hl = heat.clone()
-ms = timeit(lambda: S.ops.centernet_loss(hl, regr, off, *gt, sigmoid_inplace=False))
 alg = 3 * 65536 + 30 * 6 * 4 * 2
+ms = timeit(lambda: S.ops.centernet_loss_sparse(hl, regr, off, *gt[:4], npos=gt[4]))
 out["loss_fwd_bwd"] = {"samples": N, "ms": ms, "alg_bytes_per_sample": alg, "gbs": alg * N / ms / 1e6, "frac": alg * N / ms / 1e6 / HBM,
-                       "note": "kernel also reads gt once more (count pass) and zero-fills d_regr/d_off (6 planes): ~656 KB/sample real traffic"}
+                       "note": "scd_centernet_loss_sparse with N_pos from the render kernel: logits + gt read once, d_heat written once"}
+ms = timeit(lambda: S.ops.centernet_loss_sparse(hl, regr, off, *gt[:4]))
+out["loss_fwd_bwd_count_pass"] = {"ms": ms, "frac": alg * N / ms / 1e6 / HBM, "note": "same, N_pos counted by an extra pass over gt"}
+ms = timeit(lambda: S.ops.centernet_loss(hl, regr, off, *gt[:4], sigmoid_inplace=False))
+out["loss_fwd_bwd_dense_grads"] = {"ms": ms, "frac": alg * N / ms / 1e6 / HBM, "note": "scd_centernet_loss: six dense zero-filled L1 gradient planes (autograd form)"}
 # slide front end: 1849 tiles of a 16384^2 slide
 gray = torch.round(torch.rand(16384, 16384, device=dev, generator=g) * 255)
 ms = timeit(lambda: S.ops.slide_tiles(gray, 0, 512), iters=5)

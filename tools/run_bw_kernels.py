@@ -13,7 +13,7 @@ locs, counts = synthetic.make_objects(N, seed=1)
 locs, counts = locs.to(dev), counts.to(dev)
 for _ in range(3):
     S.ops.decode_topk(heat, regr, off, K=100)
-    gt = S.ops.render_targets(locs, counts)
-    S.ops.centernet_loss(heat.clone(), regr, off, *gt, sigmoid_inplace=False)
+    gt = S.ops.render_targets(locs, counts, with_npos=True)
+    S.ops.centernet_loss_sparse(heat, regr, off, *gt[:4], npos=gt[4])
 torch.cuda.synchronize()
 print("ok")
