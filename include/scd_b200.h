@@ -75,11 +75,12 @@ int scd_selftest_decode_math(unsigned long long* d_counts3, void* stream);
  * ---------------------------------------------------------------------------------- */
 int scd_render_targets(const float* locs, const int32_t* counts, int batch,
                        float* heat, uint8_t* mask, float* regr6, int64_t* idx, void* stream);
-/* Same, and *d_npos = count(heat == 1) over the batch: the N_pos of focalLoss (models/losses/focal.py:42),
- * counted while the heat map is written so that scd_centernet_loss_sparse need not read gt twice. */
+/* Same, and d_counts[0] = count(heat == 1) over the batch (the N_pos of focalLoss, models/losses/focal.py:42),
+ * d_counts[1] = mask.sum() (models/losses/regression.py:38), counted while the targets are written so that
+ * scd_centernet_loss_sparse need not read gt and mask a second time. */
 int scd_render_targets_npos(const float* locs, const int32_t* counts, int batch,
                             float* heat, uint8_t* mask, float* regr6, int64_t* idx,
-                            unsigned int* d_npos, void* stream);
+                            unsigned int* d_counts, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * CenterNetLoss forward + backward in one pass.  Replaces CenterNetLoss.forward
@@ -102,13 +103,13 @@ int scd_centernet_loss(const float* heat, float* prob_out, const float* regr, co
 /* Sparse form, what the training step uses.  The two masked-L1 terms touch regr / offset at the <= max_tags
  * object pixels only, so their gradients are returned as d_obj (B,max_tags,6) f32 =
  * d total / d (regr[0..3], offset[0..1]) at pixel idx[b,k] (zero where mask is 0; objects sharing a pixel
- * add up) instead of six dense planes.  d_npos (nullable) = count(gt_heat == 1) over the batch if the
- * caller already knows it (scd_render_targets_npos): the counting pass over gt_heat is then skipped and the
- * call moves the algorithmic minimum of HBM traffic (logits + gt read once, d_heat written once). */
+ * add up) instead of six dense planes.  d_counts (nullable) = {count(gt_heat == 1), mask.sum()} if the caller
+ * already knows them (scd_render_targets_npos): the counting pass is then skipped and the whole loss is ONE
+ * kernel that moves the algorithmic minimum of HBM traffic (logits + gt read once, d_heat written once). */
 int scd_centernet_loss_sparse(const float* heat, float* prob_out, const float* regr, const float* offset,
                               const float* gt_heat, const uint8_t* mask, const float* regr6,
                               const int64_t* idx, int batch, int height, int width, int max_tags,
-                              float regr_w, float off_w, const unsigned int* d_npos, float* losses,
+                              float regr_w, float off_w, const unsigned int* d_counts, float* losses,
                               float* d_heat, float* d_obj,
                               void* workspace, size_t workspace_bytes, void* stream);
 

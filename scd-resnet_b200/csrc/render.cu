@@ -105,6 +105,7 @@ render_targets_kernel(const float* __restrict__ locs, const int32_t* __restrict_
         }
         const unsigned m = __ballot_sync(0xffffffffu, draw);
         const int n = __popc(m);
+        if (n_pos != nullptr && tid == 0 && n) atomicAdd(n_pos + 1, (unsigned)n);        // mask.sum() (drawn == masked)
         const int slot = __popc(m & ((1u << tid) - 1u));
         if (draw) objs[slot] = o;
         // table offsets: (roi + 1)^2 entries each, in compacted order; objects that do not fit get -1
@@ -176,43 +177,53 @@ render_targets_kernel(const float* __restrict__ locs, const int32_t* __restrict_
     }
     __syncthreads();
 
-    // ---- draw: a 16 x 16 thread patch sweeps each object's clipped window; a pixel is touched by exactly one
-    // thread per object, barriers only where the overlap level changes.
-    const int n = n_draw;
-    int cur_level = n > 0 ? level_of[0] : 0;
-    for (int s2 = 0; s2 < n; ++s2) {
-        if (level_of[s2] != cur_level) { __syncthreads(); cur_level = level_of[s2]; }
-        const int k = order[s2];
-        const RenderObj o = objs[k];
-        const int off = tab_off[k], side = o.roi + 1;
-        const int xa = max(o.cx - o.roi, 0), xb = min(o.cx + o.roi, RT_HW - 1);          // :579-583 window clipping
-        const int ya = max(o.cy - o.roi, 0), yb = min(o.cy + o.roi, RT_HW - 1);
-        const int ty = ((tid >> 4) + 5 * s2) & 15, tx = tid & 15;                        // rotate rows over the warps
-        for (int yy = ya + ty; yy <= yb; yy += 16) {
-            const int dy = abs(yy - o.cy);
-            for (int xx = xa + tx; xx <= xb; xx += 16) {
-                const int dx = abs(xx - o.cx);
-                const double g = off >= 0 ? tab[off + dy * side + dx]
-                                          : exp(__ddiv_rn(-(double)(dx * dx + dy * dy), o.den));
-                float* hp = tile + yy * RT_HW + xx;
-                *hp = (float)__dadd_rn(g, (double)*hp);
+    // ---- draw: the objects of one overlap level are pairwise disjoint, so each warp takes its own object and
+    // sweeps the clipped window with a 2 x 16 lane patch; a block barrier only where the level changes.
+    {
+        const int n = n_draw, warp = tid >> 5, lane = tid & 31;
+        const int ly = lane >> 4, lx = lane & 15;
+        int s0 = 0;
+        while (s0 < n) {
+            const int lv = level_of[s0];
+            int s1 = s0 + 1;
+            while (s1 < n && level_of[s1] == lv) ++s1;
+            for (int s2 = s0 + warp; s2 < s1; s2 += RT_THREADS / 32) {
+                const int k = order[s2];
+                const RenderObj o = objs[k];
+                const int off = tab_off[k], side = o.roi + 1;
+                const int xa = max(o.cx - o.roi, 0), xb = min(o.cx + o.roi, RT_HW - 1);  // :579-583 window clipping
+                const int ya = max(o.cy - o.roi, 0), yb = min(o.cy + o.roi, RT_HW - 1);
+                for (int yy = ya + ly; yy <= yb; yy += 2) {
+                    const int dy = abs(yy - o.cy);
+                    for (int xx = xa + lx; xx <= xb; xx += 16) {
+                        const int dx = abs(xx - o.cx);
+                        const double g = off >= 0 ? tab[off + dy * side + dx]
+                                                  : exp(__ddiv_rn(-(double)(dx * dx + dy * dy), o.den));
+                        float* hp = tile + yy * RT_HW + xx;
+                        *hp = (float)__dadd_rn(g, (double)*hp);
+                    }
+                }
             }
+            s0 = s1;
+            __syncthreads();
         }
+        if (n == 0) __syncthreads();
     }
-    __syncthreads();
 
     float4* dst = reinterpret_cast<float4*>(heat + (size_t)b * RT_HW * RT_HW);
     int c1 = 0;
+#pragma unroll 4
     for (int i = tid; i < RT_HW * RT_HW / 4; i += RT_THREADS) {
         float4 v = reinterpret_cast<const float4*>(tile)[i];
-        v.x = v.x > 1.f ? 1.f : v.x;                                                     // heat[heat > 1] = 1
-        v.y = v.y > 1.f ? 1.f : v.y;
-        v.z = v.z > 1.f ? 1.f : v.z;
-        v.w = v.w > 1.f ? 1.f : v.w;
-        c1 += (v.x == 1.f) + (v.y == 1.f) + (v.z == 1.f) + (v.w == 1.f);
-        dst[i] = v;
+        const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+        if (mx >= 1.f) {                                                                 // rare: object centres
+            v.x = fminf(v.x, 1.f); v.y = fminf(v.y, 1.f);                                // heat[heat > 1] = 1
+            v.z = fminf(v.z, 1.f); v.w = fminf(v.w, 1.f);
+            c1 += (v.x == 1.f) + (v.y == 1.f) + (v.z == 1.f) + (v.w == 1.f);
+        }
+        __stcs(dst + i, v);
     }
-    if (n_pos != nullptr) {              // count(gt == 1), the N_pos of focalLoss (focal.py:42), as a by-product
+    if (n_pos != nullptr) {              // n_pos[0] = count(gt == 1), the N_pos of focalLoss (focal.py:42); n_pos[1] = mask.sum()
         c1 = warp_sum(c1);
         if ((tid & 31) == 0 && c1) atomicAdd(&ones, (unsigned)c1);
         __syncthreads();
@@ -234,7 +245,7 @@ static int render_targets_impl(const float* locs, const int32_t* counts, int bat
                                             scd::RT_HW * scd::RT_HW * 4));
         attr_done = true;
     }
-    if (d_npos) SCD_CUDA_CHECK(cudaMemsetAsync(d_npos, 0, sizeof(unsigned), (cudaStream_t)stream));
+    if (d_npos) SCD_CUDA_CHECK(cudaMemsetAsync(d_npos, 0, 2 * sizeof(unsigned), (cudaStream_t)stream));
     scd::render_targets_kernel<<<batch, scd::RT_THREADS, scd::RT_HW * scd::RT_HW * 4, (cudaStream_t)stream>>>(
         locs, counts, heat, mask, regr6, idx, d_npos);
     SCD_LAUNCH_CHECK("render_targets_kernel");

@@ -60,8 +60,8 @@ def render_targets(locs, counts, with_npos=False):
     """Gaussian target rendering + batch contract (ref: datasets/scds/scdx16p100.py:328-356,514-536,575-591).
 
     locs (B,30,8) f32, counts (B,) i32 -> heat (B,1,128,128) f32, mask (B,30) bool, regr6 (B,30,6) f32,
-    idx (B,30) i64.  With `with_npos` a fifth element is returned: count(heat == 1) over the batch, a u32
-    device scalar (stored as int32) that centernet_loss_sparse accepts as the focal loss's N_pos.
+    idx (B,30) i64.  With `with_npos` a fifth element is returned: [count(heat == 1), mask.sum()] over the batch,
+    two u32 device counters (stored as int32) that centernet_loss_sparse accepts instead of counting itself.
     """
     locs = _req(locs, torch.float32, "locs")
     counts = _req(counts, torch.int32, "counts")
@@ -75,7 +75,7 @@ def render_targets(locs, counts, with_npos=False):
     idx = torch.empty(b, MAXTAGLEN, dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         if with_npos:
-            npos = torch.empty(1, dtype=torch.int32, device=dev)
+            npos = torch.empty(2, dtype=torch.int32, device=dev)
             check(lib.scd_render_targets_npos(_ptr(locs), _ptr(counts), b, _ptr(heat), _ptr(mask), _ptr(regr6),
                                               _ptr(idx), _ptr(npos), _stream()), "scd_render_targets_npos")
             return heat, mask, regr6, idx, npos

@@ -193,7 +193,8 @@ def test_render_targets_overlapping_objects_and_npos(S):
     assert torch.equal(mask.cpu(), em) and torch.equal(idx.cpu(), ei) and torch.equal(regr6.cpu(), er)
     assert torch.equal(heat.cpu() == 1, eh == 1) and torch.equal(heat.cpu() == 0, eh == 0)
     assert relmax(heat, eh) < 1e-6
-    assert int(npos.item()) == int((heat == 1).sum().item()) == int((eh == 1).sum().item())
+    assert int(npos[0].item()) == int((heat == 1).sum().item()) == int((eh == 1).sum().item())
+    assert int(npos[1].item()) == int(em.sum().item())
     h2 = S.ops.render_targets(dev(locs), dev(counts))[0]
     assert torch.equal(h2, heat)                                       # deterministic, with or without the counter
 
