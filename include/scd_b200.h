@@ -225,13 +225,14 @@ int scd_conv_wgrad(int kind, const void* a_in, const void* dz, int batch, int hi
                    int cin, int cout, float* out, void* stream);
 
 /* Stem in training: raw conv output z0 (B,H/2,W/2,64) bf16 + its im2col operand col0 (same shape);
- * a0 = maxpool3x3s2(relu(z0*scale + shift)); and the gradient back to relu(bn(z0)) (ReLU mask applied). */
+ * a0 = maxpool3x3s2(relu(z0*scale + shift)), with argmax (nullable, (B,H/4,W/4,64) u8) recording per pooled
+ * element the window position dy*3+dx of the first maximum (PyTorch's rule) or 9 when the ReLU passes nothing;
+ * scd_stem_pool_bwd routes d a0 through that record to dy0, the gradient at relu(bn(z0)) (ReLU mask applied). */
 int scd_stem_conv_train(const float* x, const void* weight, int batch, int height, int width,
                         void* z0, void* col0, void* stream);
 int scd_stem_bn_relu_pool(const void* z0, const float* scale, const float* shift, int batch, int hp, int wp,
-                          void* a0, void* stream);
-int scd_stem_pool_bwd(const void* z0, const float* scale, const float* shift, const void* da0, int batch,
-                      int hp, int wp, void* dy0, void* stream);
+                          void* a0, uint8_t* argmax, void* stream);
+int scd_stem_pool_bwd(const uint8_t* argmax, const void* da0, int batch, int hp, int wp, void* dy0, void* stream);
 
 /* Heads in training: scd_heads_fwd + hidden = ReLU(conv3x3 + b3) stored as (B,H,W,384) bf16;
  * scd_heads_bwd: d_hidden = (w1^T d_out) * (hidden > 0), and the gradients of w1 (7,128), b1 (7), b3 (384). */

@@ -29,6 +29,13 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     return *reinterpret_cast<const uint4*>(h);
 }
 
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
 // Threads are laid out so that thread t always handles channel group (t % (C/8)); a CTA strides over
 // pixels.  Requires BN_THREADS % (C/8) == 0, true for C in {64,128,256,384(no!),512}: 384/8 = 48 does not
 // divide 256, so the launch picks a block size that is a multiple of C/8.
@@ -113,21 +120,19 @@ __global__ void __launch_bounds__(BN_THREADS)
 bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
                 const uint4* __restrict__ residual, int relu, size_t n8, int cgroups, uint4* __restrict__ out)
 {
+    // grid stride is a multiple of cgroups: a thread keeps its channel group (see bn_bwd_apply_kernel)
+    const int g = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) % cgroups);
+    float sc[8], sh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sc[k] = __ldg(scale + g * 8 + k); sh[k] = __ldg(shift + g * 8 + k); }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
-        const int g = (int)(i % cgroups);
         float zf[8], o[8];
-        unpack8(__ldg(z + i), zf);
-        const float4 sa = __ldg(reinterpret_cast<const float4*>(scale) + 2 * g);
-        const float4 sb = __ldg(reinterpret_cast<const float4*>(scale) + 2 * g + 1);
-        const float4 ha = __ldg(reinterpret_cast<const float4*>(shift) + 2 * g);
-        const float4 hb = __ldg(reinterpret_cast<const float4*>(shift) + 2 * g + 1);
-        o[0] = fmaf(zf[0], sa.x, ha.x); o[1] = fmaf(zf[1], sa.y, ha.y);
-        o[2] = fmaf(zf[2], sa.z, ha.z); o[3] = fmaf(zf[3], sa.w, ha.w);
-        o[4] = fmaf(zf[4], sb.x, hb.x); o[5] = fmaf(zf[5], sb.y, hb.y);
-        o[6] = fmaf(zf[6], sb.z, hb.z); o[7] = fmaf(zf[7], sb.w, hb.w);
+        unpack8(ld_stream_u4(z + i), zf);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = fmaf(zf[k], sc[k], sh[k]);
         if (residual) {
             float rf[8];
-            unpack8(__ldg(residual + i), rf);
+            unpack8(ld_stream_u4(residual + i), rf);
 #pragma unroll
             for (int k = 0; k < 8; ++k) o[k] += rf[k];
         }
@@ -155,25 +160,33 @@ bn_bwd_apply_kernel(const uint4* __restrict__ da, const uint4* __restrict__ a, c
             if (dgamma) dgamma[c] = (float)sums[C + c];
         }
     }
+    // The block size, hence the grid stride, is a multiple of cgroups (apply_block), so a thread
+    // keeps its channel group: dz = A dy + B z + D with per-channel A = scale, B = -scale m2 invstd,
+    // D = scale (m2 invstd mean - m1), m1 = sum(dy)/n, m2 = sum(dy xhat)/n, hoisted out of the loop.
     const float inv_n = (float)(1.0 / count);
+    const int g = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) % cgroups);
+    float cA[8], cB[8], cD[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = g * 8 + k;
+        const float m1 = (float)sums[c] * inv_n, m2 = (float)sums[C + c] * inv_n;
+        const float sc = __ldg(scale + c), is = __ldg(invstd + c), mu = __ldg(mean + c);
+        cA[k] = sc;
+        cB[k] = -sc * m2 * is;
+        cD[k] = sc * (m2 * is * mu - m1);
+    }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
-        const int g = (int)(i % cgroups);
         float df[8], zf[8], o[8];
-        unpack8(__ldg(da + i), df);
-        unpack8(__ldg(z + i), zf);
+        unpack8(ld_stream_u4(da + i), df);
+        unpack8(ld_stream_u4(z + i), zf);
         if (a != nullptr) {
             float af[8];
-            unpack8(__ldg(a + i), af);
+            unpack8(ld_stream_u4(a + i), af);
 #pragma unroll
             for (int k = 0; k < 8; ++k) df[k] = af[k] > 0.f ? df[k] : 0.f;
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int c = g * 8 + k;
-            const float xh = (zf[k] - __ldg(mean + c)) * __ldg(invstd + c);
-            const float m1 = (float)sums[c] * inv_n, m2 = (float)sums[C + c] * inv_n;
-            o[k] = __ldg(scale + c) * (df[k] - m1 - xh * m2);
-        }
+        for (int k = 0; k < 8; ++k) o[k] = fmaf(cA[k], df[k], fmaf(cB[k], zf[k], cD[k]));
         dz[i] = pack8(o);
         if (dy_out) dy_out[i] = pack8(df);
     }
@@ -184,6 +197,13 @@ static inline int stream_grid(size_t items, int per_block) {
     const size_t cap = (size_t)kNumSMs * 8;
     if (want > cap) want = cap;
     return (int)(want < 1 ? 1 : want);
+}
+
+static int apply_block(int C) {             // largest multiple of C/8 and of 32 that is <= BN_THREADS
+    const int cg = C / 8;
+    for (int b = BN_THREADS; b >= cg; b -= 32)
+        if (b % cg == 0) return b;
+    return 0;
 }
 
 static int reduce_block(int C) {            // largest multiple of C/8 that is <= 384 and a multiple of 32
@@ -228,8 +248,10 @@ extern "C" int scd_bn_apply(const void* z, const float* scale, const float* shif
 {
     using namespace scd;
     if (!z || !scale || !shift || !out || C % 8) return fail(SCD_EINVAL, "scd_bn_apply: bad arguments");
+    const int block = apply_block(C);
+    if (!block) return fail(SCD_EINVAL, "scd_bn_apply: unsupported channel count %d", C);
     const size_t n8 = pixels * (size_t)(C / 8);
-    bn_apply_kernel<<<stream_grid(n8, BN_THREADS * 4), BN_THREADS, 0, (cudaStream_t)stream>>>(
+    bn_apply_kernel<<<stream_grid(n8, block * 4), block, 0, (cudaStream_t)stream>>>(
         static_cast<const uint4*>(z), scale, shift, static_cast<const uint4*>(residual), relu, n8, C / 8,
         static_cast<uint4*>(out));
     SCD_LAUNCH_CHECK("bn_apply_kernel");
@@ -255,8 +277,10 @@ extern "C" int scd_bn_bwd(const void* da, const void* a, const void* z, const fl
         SCD_LAUNCH_CHECK("bn_reduce_kernel<1>");
     } else {
         if (!dz) return fail(SCD_EINVAL, "scd_bn_bwd: dz is null");
+        const int ablock = apply_block(C);
+        if (!ablock) return fail(SCD_EINVAL, "scd_bn_bwd: unsupported channel count %d", C);
         const size_t n8 = pixels * (size_t)(C / 8);
-        bn_bwd_apply_kernel<<<stream_grid(n8, BN_THREADS * 4), BN_THREADS, 0, st>>>(
+        bn_bwd_apply_kernel<<<stream_grid(n8, ablock * 4), ablock, 0, st>>>(
             static_cast<const uint4*>(da), static_cast<const uint4*>(a), static_cast<const uint4*>(z), scale, mean,
             invstd, sums, count, n8, C / 8, static_cast<uint4*>(dz), static_cast<uint4*>(dy_out), dgamma, dbeta);
         SCD_LAUNCH_CHECK("bn_bwd_apply_kernel");

@@ -165,9 +165,7 @@ centernet_loss_kernel(const float4* __restrict__ logits, const float4* __restric
     // ---- focal term: loss = -(pos + neg) / N_pos, or -neg when there is no positive (focal.py:47-51) -------
     const float scale = npos > 0 ? -1.f / (float)npos : -1.f;
     float ps = 0.f, ns = 0.f;
-    for (size_t i = t0; i < n4; i += stride) {
-        const float4 x = kExactProb ? logits[i] : ld_stream(logits + i);   // plain load: prob_out may alias logits
-        const float4 g = ld_stream(gt + i);
+    auto body = [&](size_t i, const float4 x, const float4 g) {
         float4 pr, d;
         float a, c;
         focal_elem<kExactProb>(x.x, g.x, pr.x, a, c, d.x); ps += a; ns += c;
@@ -175,8 +173,18 @@ centernet_loss_kernel(const float4* __restrict__ logits, const float4* __restric
         focal_elem<kExactProb>(x.z, g.z, pr.z, a, c, d.z); ps += a; ns += c;
         focal_elem<kExactProb>(x.w, g.w, pr.w, a, c, d.w); ps += a; ns += c;
         if (kExactProb) prob_out[i] = pr;
-        if (d_heat) d_heat[i] = make_float4(d.x * scale, d.y * scale, d.z * scale, d.w * scale);
+        if (d_heat) __stcs(d_heat + i, make_float4(d.x * scale, d.y * scale, d.z * scale, d.w * scale));
+    };
+    size_t i = t0;
+    for (; i + stride < n4; i += 2 * stride) {            // two independent load pairs in flight per thread
+        const float4 x0 = kExactProb ? logits[i] : ld_stream(logits + i);   // plain load: prob_out may alias logits
+        const float4 g0 = ld_stream(gt + i);
+        const float4 x1 = kExactProb ? logits[i + stride] : ld_stream(logits + i + stride);
+        const float4 g1 = ld_stream(gt + i + stride);
+        body(i, x0, g0);
+        body(i + stride, x1, g1);
     }
+    if (i < n4) body(i, kExactProb ? logits[i] : ld_stream(logits + i), ld_stream(gt + i));
 
     // ---- CTA reduction in fp64: (focal, size, offset) per CTA; the last CTA combines them in fixed order ----
     __shared__ double red[3][LOSS_THREADS / 32];
@@ -218,9 +226,18 @@ centernet_loss_kernel(const float4* __restrict__ logits, const float4* __restric
     }
 }
 
+// whole waves only: resident CTAs per SM (occupancy API, per kernel variant) x 148 SMs
+template <bool kExactProb>
 static inline int loss_grid(size_t n4) {
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, centernet_loss_kernel<kExactProb>, LOSS_THREADS, 0) != cudaSuccess || n < 1)
+            n = 4;
+        per_sm = n;
+    }
     size_t want = (n4 + LOSS_THREADS - 1) / LOSS_THREADS;
-    const size_t cap = (size_t)kNumSMs * 8;      // 8 CTAs of 256 threads per SM, whole waves
+    const size_t cap = (size_t)kNumSMs * per_sm;
     if (want > cap) want = cap;
     if (want < 1) want = 1;
     return (int)want;
@@ -253,7 +270,7 @@ static int centernet_loss_impl(const float* heat, float* prob_out, const float* 
     LossWs* ws = reinterpret_cast<LossWs*>(workspace);
     double* partials = reinterpret_cast<double*>(ws + 1);
     const size_t n4 = (size_t)batch * height * width / 4;
-    const int grid = loss_grid(n4);
+    const int grid = prob_out ? loss_grid<true>(n4) : loss_grid<false>(n4);
     const int n_obj = batch * max_tags;
     SCD_CUDA_CHECK(cudaMemsetAsync(ws, 0, sizeof(LossWs), st));
     if (!d_counts)

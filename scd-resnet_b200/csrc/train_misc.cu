@@ -22,10 +22,14 @@ __device__ __forceinline__ uint4 pack8f(const float (&f)[8]) {
     return *reinterpret_cast<const uint4*>(h);
 }
 
-// thread = (pool pixel, 8 channels); z0 is NHWC with 64 channels at (hc, wc) = 2 x (hp, wp)
+// thread = (pool pixel, 8 channels); z0 is NHWC with 64 channels at (hc, wc) = 2 x (hp, wp).
+// argmax (nullable) receives, per pooled element, the window position dy * 3 + dx of the first maximum in
+// row-major order (PyTorch's max_pool2d rule), or 9 when the maximum is not positive (the ReLU passes no
+// gradient): everything the backward pass needs, in one byte instead of a second read of nine z0 values.
 __global__ void __launch_bounds__(256)
 stem_bn_relu_pool_kernel(const uint4* __restrict__ z0, const float* __restrict__ scale,
-                         const float* __restrict__ shift, int batch, int hp, int wp, uint4* __restrict__ a0)
+                         const float* __restrict__ shift, int batch, int hp, int wp, uint4* __restrict__ a0,
+                         uint2* __restrict__ argmax)
 {
     const size_t total = (size_t)batch * hp * wp * 8;
     const int hc = 2 * hp, wc = 2 * wp;
@@ -36,8 +40,9 @@ stem_bn_relu_pool_kernel(const uint4* __restrict__ z0, const float* __restrict__
         const int py = (int)(r % hp);
         const int b = (int)(r / hp);
         float sc[8], sh[8], m[8];
+        unsigned code[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { sc[k] = __ldg(scale + g * 8 + k); sh[k] = __ldg(shift + g * 8 + k); m[k] = 0.f; }
+        for (int k = 0; k < 8; ++k) { sc[k] = __ldg(scale + g * 8 + k); sh[k] = __ldg(shift + g * 8 + k); m[k] = 0.f; code[k] = 9u; }
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
@@ -47,18 +52,24 @@ stem_bn_relu_pool_kernel(const uint4* __restrict__ z0, const float* __restrict__
                 float zf[8];
                 unpack8f(__ldg(z0 + (((size_t)b * hc + cy) * wc + cx) * 8 + g), zf);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], fmaf(zf[k], sc[k], sh[k]));
+                for (int k = 0; k < 8; ++k) {
+                    const float v = fmaf(zf[k], sc[k], sh[k]);
+                    if (v > m[k]) { m[k] = v; code[k] = (unsigned)((dy + 1) * 3 + dx + 1); }   // strict: first maximum wins
+                }
             }
         a0[i] = pack8f(m);
+        if (argmax != nullptr)
+            argmax[i] = make_uint2(code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24),
+                                   code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24));
     }
 }
 
-// thread = (conv pixel, 8 channels).  A conv position receives the gradient of every pool window in which it
-// is the first maximum in row-major window order (PyTorch's max_pool2d rule); positions with y <= 0 get 0
-// (ReLU).  Even rows/cols sit in one window, odd ones in two.
+// thread = (conv pixel, 8 channels).  A conv position receives the gradient of every pool window whose recorded
+// argmax is this position (even rows / cols sit in one window, odd ones in two); the ReLU mask is part of the
+// record (code 9).  Reads 1 byte + 2 bytes per (window, channel), writes dy0 once.
 __global__ void __launch_bounds__(256)
-stem_pool_bwd_kernel(const uint4* __restrict__ z0, const float* __restrict__ scale, const float* __restrict__ shift,
-                     const uint4* __restrict__ da0, int batch, int hp, int wp, uint4* __restrict__ dy0)
+stem_pool_bwd_kernel(const uint2* __restrict__ argmax, const uint4* __restrict__ da0, int batch, int hp, int wp,
+                     uint4* __restrict__ dy0)
 {
     const int hc = 2 * hp, wc = 2 * wp;
     const size_t total = (size_t)batch * hc * wc * 8;
@@ -68,44 +79,28 @@ stem_pool_bwd_kernel(const uint4* __restrict__ z0, const float* __restrict__ sca
         const int cx = (int)(r % wc); r /= wc;
         const int cy = (int)(r % hc);
         const int b = (int)(r / hc);
-        float sc[8], sh[8], self[8], out[8];
+        float out[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { sc[k] = __ldg(scale + g * 8 + k); sh[k] = __ldg(shift + g * 8 + k); out[k] = 0.f; }
-        {
-            float zf[8];
-            unpack8f(__ldg(z0 + i), zf);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) self[k] = fmaf(zf[k], sc[k], sh[k]);
-        }
+        for (int k = 0; k < 8; ++k) out[k] = 0.f;
         const int py_lo = cy >> 1, py_hi = (cy + 1) >> 1;       // equal when cy is even
         const int px_lo = cx >> 1, px_hi = (cx + 1) >> 1;
         for (int py = py_lo; py <= py_hi; ++py) {
             if (py >= hp) continue;
             for (int px = px_lo; px <= px_hi; ++px) {
                 if (px >= wp) continue;
-                bool win[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) win[k] = self[k] > 0.f;
-                for (int dy = -1; dy <= 1; ++dy)
-                    for (int dx = -1; dx <= 1; ++dx) {
-                        const int y = 2 * py + dy, x = 2 * px + dx;
-                        if (y < 0 || y >= hc || x < 0 || x >= wc || (y == cy && x == cx)) continue;
-                        const bool earlier = (y < cy) || (y == cy && x < cx);
-                        float zf[8];
-                        unpack8f(__ldg(z0 + (((size_t)b * hc + y) * wc + x) * 8 + g), zf);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const float v = fmaf(zf[k], sc[k], sh[k]);
-                            if (v > self[k] || (earlier && v == self[k])) win[k] = false;
-                        }
-                    }
+                const unsigned want = (unsigned)((cy - 2 * py + 1) * 3 + (cx - 2 * px + 1));
+                const size_t w = (((size_t)b * hp + py) * wp + px) * 8 + g;
+                const uint2 code = __ldg(argmax + w);
                 float df[8];
-                unpack8f(__ldg(da0 + (((size_t)b * hp + py) * wp + px) * 8 + g), df);
+                unpack8f(__ldg(da0 + w), df);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) out[k] += win[k] ? df[k] : 0.f;
+                for (int k = 0; k < 4; ++k) {
+                    out[k] += ((code.x >> (8 * k)) & 0xFFu) == want ? df[k] : 0.f;
+                    out[4 + k] += ((code.y >> (8 * k)) & 0xFFu) == want ? df[4 + k] : 0.f;
+                }
             }
         }
-        dy0[i] = pack8f(out);
+        __stcs(dy0 + i, pack8f(out));
     }
 }
 
@@ -235,26 +230,26 @@ static inline int sgrid(size_t items, int per_block) {
 }  // namespace scd
 
 extern "C" int scd_stem_bn_relu_pool(const void* z0, const float* scale, const float* shift, int batch, int hp, int wp,
-                                     void* a0, void* stream)
+                                     void* a0, uint8_t* argmax, void* stream)
 {
     using namespace scd;
     if (!z0 || !scale || !shift || !a0) return fail(SCD_EINVAL, "scd_stem_bn_relu_pool: null pointer");
     const size_t total = (size_t)batch * hp * wp * 8;
     stem_bn_relu_pool_kernel<<<sgrid(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        static_cast<const uint4*>(z0), scale, shift, batch, hp, wp, static_cast<uint4*>(a0));
+        static_cast<const uint4*>(z0), scale, shift, batch, hp, wp, static_cast<uint4*>(a0),
+        reinterpret_cast<uint2*>(argmax));
     SCD_LAUNCH_CHECK("stem_bn_relu_pool_kernel");
     return SCD_OK;
 }
 
-extern "C" int scd_stem_pool_bwd(const void* z0, const float* scale, const float* shift, const void* da0, int batch,
-                                 int hp, int wp, void* dy0, void* stream)
+extern "C" int scd_stem_pool_bwd(const uint8_t* argmax, const void* da0, int batch, int hp, int wp, void* dy0,
+                                 void* stream)
 {
     using namespace scd;
-    if (!z0 || !scale || !shift || !da0 || !dy0) return fail(SCD_EINVAL, "scd_stem_pool_bwd: null pointer");
+    if (!argmax || !da0 || !dy0) return fail(SCD_EINVAL, "scd_stem_pool_bwd: null pointer");
     const size_t total = (size_t)batch * hp * wp * 4 * 8;
     stem_pool_bwd_kernel<<<sgrid(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        static_cast<const uint4*>(z0), scale, shift, static_cast<const uint4*>(da0), batch, hp, wp,
-        static_cast<uint4*>(dy0));
+        reinterpret_cast<const uint2*>(argmax), static_cast<const uint4*>(da0), batch, hp, wp, static_cast<uint4*>(dy0));
     SCD_LAUNCH_CHECK("stem_pool_bwd_kernel");
     return SCD_OK;
 }

@@ -95,21 +95,22 @@ def stem_conv_train(x, weight):
     return z0, col0
 
 
-def stem_bn_relu_pool(z0, stat):
+def stem_bn_relu_pool(z0, stat, want_argmax=True):
+    """-> (a0, argmax): a0 = maxpool3x3s2(relu(bn(z0))), argmax (B,H/4,W/4,64) u8 window positions for the backward."""
     b, hc, wc, _ = z0.shape
     a0 = torch.empty(b, hc // 2, wc // 2, 64, dtype=torch.bfloat16, device=z0.device)
+    am = torch.empty(b, hc // 2, wc // 2, 64, dtype=torch.uint8, device=z0.device) if want_argmax else None
     with torch.cuda.device(z0.device):
-        check(lib.scd_stem_bn_relu_pool(_ptr(z0), _ptr(stat[0]), _ptr(stat[1]), b, hc // 2, wc // 2, _ptr(a0), _stream()),
-              "scd_stem_bn_relu_pool")
-    return a0
+        check(lib.scd_stem_bn_relu_pool(_ptr(z0), _ptr(stat[0]), _ptr(stat[1]), b, hc // 2, wc // 2, _ptr(a0), _ptr(am),
+                                        _stream()), "scd_stem_bn_relu_pool")
+    return a0, am
 
 
-def stem_pool_bwd(z0, stat, da0):
-    b, hc, wc, _ = z0.shape
-    dy0 = torch.empty_like(z0)
-    with torch.cuda.device(z0.device):
-        check(lib.scd_stem_pool_bwd(_ptr(z0), _ptr(stat[0]), _ptr(stat[1]), _ptr(da0), b, hc // 2, wc // 2, _ptr(dy0),
-                                    _stream()), "scd_stem_pool_bwd")
+def stem_pool_bwd(argmax, da0):
+    b, hp, wp, _ = argmax.shape
+    dy0 = torch.empty(b, 2 * hp, 2 * wp, 64, dtype=torch.bfloat16, device=da0.device)
+    with torch.cuda.device(da0.device):
+        check(lib.scd_stem_pool_bwd(_ptr(argmax), _ptr(da0), b, hp, wp, _ptr(dy0), _stream()), "scd_stem_pool_bwd")
     return dy0
 
 

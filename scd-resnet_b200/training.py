@@ -194,7 +194,7 @@ class TrainEngine:
         # ---- forward -----------------------------------------------------------------------------------
         z0, col0 = T.stem_conv_train(x, self.wb("preprocess.0.weight:fwd"))
         _, ctx0 = self._stem_bn(z0, mod.preprocess[1])
-        a = T.stem_bn_relu_pool(z0, ctx0["stat"])
+        a, argmax0 = T.stem_bn_relu_pool(z0, ctx0["stat"])
         a0 = a
         for name, cin, cout, stride in _BLOCKS:
             p = name + ".0"
@@ -247,7 +247,7 @@ class TrainEngine:
                 T.conv_wgrad(1, a_in, dz1, cin, cout, self.g(p + ".conv1.weight"))
                 T.conv_wgrad(2, a_in, dzd, cin, cout, self.g(p + ".downsample.0.weight"))
                 da = T.conv_dgrad(1, dz1, self.wb(p + ".conv1.weight:dgrad"), self.zero_bias[:cin], cin, dz2=dzd)
-        dy0 = T.stem_pool_bwd(z0, ctx0["stat"], da)
+        dy0 = T.stem_pool_bwd(argmax0, da)
         dz0, _ = T.bn_backward(dy0, None, z0, ctx0, False, self.g("preprocess.1.weight"), self.g("preprocess.1.bias"),
                                all_reduce=self._allreduce_stats if self.world > 1 else None)
         T.conv_wgrad(4, col0, dz0, 64, 64, self.g("preprocess.0.weight"))

@@ -159,9 +159,10 @@ def test_stem_train(S):
     da0 = rnd(rng, *y.shape)
     y.backward(da0)
     _, ctx = T.bn_forward(z0, gamma.cuda(), beta.cuda(), relu=True)
-    a0 = T.stem_bn_relu_pool(z0, ctx["stat"])
+    a0, argmax = T.stem_bn_relu_pool(z0, ctx["stat"])
     close(nchw(a0), y.detach())
-    dy0 = T.stem_pool_bwd(z0, ctx["stat"], nhwc(da0))
+    assert int(argmax.max()) <= 9
+    dy0 = T.stem_pool_bwd(argmax, nhwc(da0))
     dz0, _ = T.bn_backward(dy0, None, z0, ctx)
     close(nchw(dz0), zt.grad)
     # weight gradient from the im2col operand written by the forward
