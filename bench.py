@@ -234,7 +234,7 @@ def main():
         tlocs = [tuple(t.to(dev) for t in synthetic.make_objects(TB, seed=50 + 3 * rank + i)) for i in range(3)]
 
         def train_once(i):
-            ys = S.ops.render_targets(*tlocs[i % 3])
+            ys = S.ops.render_targets(*tlocs[i % 3], with_npos=True)
             return eng.train_step(txs[i % 3], ys)
 
         for i in range(3):

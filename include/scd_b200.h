@@ -243,6 +243,25 @@ int scd_heads_bwd(const float* d_heat, const float* d_regr, const float* d_off, 
                   const float* w1, int batch, int height, int width, void* d_hidden, float* g_w1,
                   float* g_b1, float* g_b3, void* stream);
 
+/* Heads backward in the sparse form the loss produces (scd_centernet_loss_sparse): d_heat is dense, the regr /
+ * offset gradients exist at the B x max_tags object pixels only, so the 256 hidden channels of those two heads
+ * have a gradient at those pixels only.
+ *   scd_heads_bwd_sparse    d_hidden_heat (B,H,W,128) bf16 = hidden gradient of the heat head (dense; feed it to
+ *                           scd_conv_wgrad / scd_conv_igemm_dgrad with 128 channels), dh_objects (B*max_tags,256)
+ *                           f32 = hidden gradient of the regr (0..127) and offset (128..255) heads per object,
+ *                           and the gradients of w1 (7,128), b1 (7), b3 (384);
+ *   scd_heads_wgrad_sparse  out[tap][co][ci] (9,256,256) f32 = gradient of w3 rows 128..383 (regr, offset heads),
+ *                           x = the heads' input (B,H,W,256) bf16;
+ *   scd_heads_dgrad_sparse  dx (B,H,W,256) bf16 += dh_objects . w3[128:384] around every object pixel
+ *                           (w3 = the (384, 9*256) bf16 forward operand); call after the dense data gradient. */
+int scd_heads_bwd_sparse(const float* d_heat, const float* d_obj, const uint8_t* mask, const int64_t* idx,
+                         const void* hidden, const float* w1, int batch, int height, int width, int max_tags,
+                         void* d_hidden_heat, float* dh_objects, float* g_w1, float* g_b1, float* g_b3, void* stream);
+int scd_heads_wgrad_sparse(const void* x, const float* dh_objects, const uint8_t* mask, const int64_t* idx,
+                           int batch, int height, int width, int max_tags, float* out, void* stream);
+int scd_heads_dgrad_sparse(const float* dh_objects, const uint8_t* mask, const int64_t* idx, const void* w3,
+                           int batch, int height, int width, int max_tags, void* dx, void* stream);
+
 /* Fused Adam (torch.optim.Adam defaults, networkFactory.py:80-82) over the flat fp32 parameter buffer.
  * The gradient of parameter i is grad_scale * grads[gmap ? gmap[i] : i] (the wgrad kernels write their own
  * layout).  scd_gather_cast_bf16 refreshes the bf16 GEMM-operand copies: dst[i] = bf16(src[idx[i]]), 0 if

@@ -136,6 +136,41 @@ def heads_bwd(d_heat, d_regr, d_off, hidden, w1, g_w1, g_b1, g_b3):
     return d_hidden
 
 
+def heads_bwd_sparse(d_heat, d_obj, mask, idx, hidden, w1, g_w1, g_b1, g_b3):
+    """-> (d_hidden_heat (B,H,W,128) bf16, dh_objects (B*max_tags,256) f32); see include/scd_b200.h."""
+    b, h, w, _ = hidden.shape
+    if mask.dtype == torch.bool:
+        mask = mask.contiguous().view(torch.uint8)
+    tags = mask.shape[1]
+    d_hh = torch.empty(b, h, w, 128, dtype=torch.bfloat16, device=hidden.device)
+    dh = torch.empty(b * tags, 256, dtype=torch.float32, device=hidden.device)
+    with torch.cuda.device(hidden.device):
+        check(lib.scd_heads_bwd_sparse(_ptr(d_heat), _ptr(d_obj), _ptr(mask), _ptr(idx), _ptr(hidden), _ptr(w1), b, h, w,
+                                       tags, _ptr(d_hh), _ptr(dh), _ptr(g_w1), _ptr(g_b1), _ptr(g_b3), _stream()),
+              "scd_heads_bwd_sparse")
+    return d_hh, dh
+
+
+def heads_wgrad_sparse(x, dh, mask, idx, out):
+    """out (9,256,256) f32 [tap][co][ci] = gradient of the regr / offset heads' 3x3 weights."""
+    b, h, w, _ = x.shape
+    if mask.dtype == torch.bool:
+        mask = mask.contiguous().view(torch.uint8)
+    with torch.cuda.device(x.device):
+        check(lib.scd_heads_wgrad_sparse(_ptr(x), _ptr(dh), _ptr(mask), _ptr(idx), b, h, w, mask.shape[1], _ptr(out),
+                                         _stream()), "scd_heads_wgrad_sparse")
+
+
+def heads_dgrad_sparse(dh, mask, idx, w3, dx):
+    """dx (B,H,W,256) bf16 += the regr / offset heads' contribution around every object pixel."""
+    b, h, w, _ = dx.shape
+    if mask.dtype == torch.bool:
+        mask = mask.contiguous().view(torch.uint8)
+    with torch.cuda.device(dx.device):
+        check(lib.scd_heads_dgrad_sparse(_ptr(dh), _ptr(mask), _ptr(idx), _ptr(w3), b, h, w, mask.shape[1], _ptr(dx),
+                                         _stream()), "scd_heads_dgrad_sparse")
+
+
 def adam_step(params, exp_avg, exp_avg_sq, grads, gmap, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
     with torch.cuda.device(params.device):
         check(lib.scd_adam_step(_ptr(params), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(grads), _ptr(gmap), params.numel(),

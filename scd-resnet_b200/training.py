@@ -123,15 +123,21 @@ class TrainEngine:
             conv(ck + ".weight", 3, cin, cout)
             bn(bk)
             w_alloc(ck + ".weight:dgrad", weights.layout_dgrad(pidx(ck + ".weight"), 3))
-        # heads: the three 3x3 convs run as one conv with 384 output channels
-        base = g_alloc("heads.w3", T.conv_wgrad_floats(0, 256, 384))
-        idx384 = weights.wgrad_index((384, 256, 3, 3), 0)
+        # heads: the three 3x3 convs run as one conv with 384 output channels in the forward pass.  Backward: the
+        # heat head (dense gradient) goes through the tensor-core wgrad / dgrad with 128 channels; the regr and
+        # offset heads have a hidden gradient at the object pixels only (csrc/heads_sparse.cu), their weight
+        # gradient is laid out [tap][co][ci] with co = 0..127 regr, 128..255 offset.
         w3_idx = torch.cat([pidx(h + ".0.weight") for h, _, _ in _HEADS], 0)          # (384,256,3,3) of P indices
-        for i, (h, _, _) in enumerate(_HEADS):
-            k = h + ".0.weight"
-            gmap[self.off[k]:self.off[k] + named[k].numel()] = (base + idx384[i * 128:(i + 1) * 128]).reshape(-1)
+        base = g_alloc("heads.w3h", T.conv_wgrad_floats(0, 256, 128))
+        k = "heatmap.0.weight"
+        gmap[self.off[k]:self.off[k] + named[k].numel()] = (base + weights.wgrad_index((128, 256, 3, 3), 0)).reshape(-1)
+        base = g_alloc("heads.w3s", 9 * 256 * 256)
+        co, ci, r, s_ = torch.meshgrid(torch.arange(128), torch.arange(256), torch.arange(3), torch.arange(3), indexing="ij")
+        for i, k in enumerate(("regr.0.weight", "offset.0.weight")):
+            gmap[self.off[k]:self.off[k] + named[k].numel()] = \
+                (base + ((r * 3 + s_) * 256 + (co + 128 * i)) * 256 + ci).reshape(-1)
         w_alloc("heads.w3:fwd", weights.layout_fwd(w3_idx, 0))
-        w_alloc("heads.w3:dgrad", weights.layout_dgrad(w3_idx, 0))
+        w_alloc("heads.w3h:dgrad", weights.layout_dgrad(w3_idx[:128], 0))
         b3 = g_alloc("heads.b3", 384)
         w1 = g_alloc("heads.w1", 7 * 128)
         b1 = g_alloc("heads.b1", 7)
@@ -186,7 +192,8 @@ class TrainEngine:
         return ops.conv_igemm_fwd(kind, x, self.wb(key + ":fwd"), self.zero_bias[:cout], None, False)
 
     def forward_backward(self, x, targets, sigmoid_inplace=False):
-        """x (B,1,H,W) f32 CUDA; targets = [heat (B,1,128,128), mask (B,30), regr6 (B,30,6), idx (B,30)].
+        """x (B,1,H,W) f32 CUDA; targets = [heat (B,1,128,128), mask (B,30), regr6 (B,30,6), idx (B,30)]
+        (+ optionally the two device counters of ops.render_targets(with_npos=True)).
         Returns (losses f32[4] on the device, outputs dict); gradients land in self.G."""
         mod = self.module
         self.G.zero_()
@@ -220,16 +227,20 @@ class TrainEngine:
         w1 = self.P[self.off["heatmap.2.weight"]:self.off["heatmap.2.weight"] + 7 * 128]
         b1 = self.P[self.off["heatmap.2.bias"]:self.off["heatmap.2.bias"] + 7]
         heat, regr, off, hidden = T.heads_fwd_train(e3, self.wb("heads.w3:fwd"), b3, w1, b1)
-        # ---- loss (forward + its own backward in one pass) -------------------------------------------
+        # ---- loss (forward + its own backward in one pass; L1 gradients in sparse, per-object form) -----------
         heat_logits = heat
-        losses, d_heat, d_regr, d_off = ops.centernet_loss(heat_logits, regr, off, targets[0], targets[1], targets[2],
-                                                           targets[3], self.regr_w, self.off_w, with_grad=True,
-                                                           sigmoid_inplace=sigmoid_inplace)
+        gt_heat, mask, regr6, gidx = targets[0], targets[1], targets[2], targets[3]
+        counts = targets[4] if len(targets) > 4 else None          # [N_pos, mask.sum()] from render_targets(with_npos)
+        losses, d_heat, d_obj = ops.centernet_loss_sparse(heat_logits, regr, off, gt_heat, mask, regr6, gidx,
+                                                          self.regr_w, self.off_w, npos=counts,
+                                                          sigmoid_inplace=sigmoid_inplace)
         # ---- backward ----------------------------------------------------------------------------------
-        d_hidden = T.heads_bwd(d_heat, d_regr, d_off, hidden, w1, self.g("heads.w1"), self.g("heads.b1"),
-                               self.g("heads.b3"))
-        T.conv_wgrad(0, e3, d_hidden, 256, 384, self.g("heads.w3"))
-        da = T.conv_dgrad(0, d_hidden, self.wb("heads.w3:dgrad"), self.zero_bias[:256], 256)
+        d_hh, dh_obj = T.heads_bwd_sparse(d_heat, d_obj, mask, gidx, hidden, w1, self.g("heads.w1"), self.g("heads.b1"),
+                                          self.g("heads.b3"))
+        T.conv_wgrad(0, e3, d_hh, 256, 128, self.g("heads.w3h"))
+        T.heads_wgrad_sparse(e3, dh_obj, mask, gidx, self.g("heads.w3s"))
+        da = T.conv_dgrad(0, d_hh, self.wb("heads.w3h:dgrad"), self.zero_bias[:256], 256)
+        T.heads_dgrad_sparse(dh_obj, mask, gidx, self.wb("heads.w3:fwd"), da)
         for ck, bk, cin, cout, a_in, z, c, a_out in reversed(dtape):
             dz, _ = self._bn_bwd(da, a_out, z, c, bk)
             T.conv_wgrad(3, a_in, dz, cin, cout, self.g(ck + ".weight"))

@@ -216,6 +216,50 @@ def test_heads_train(S):
     close(g_b3, dh_ref.sum(dim=(0, 2, 3)), 5e-3)
 
 
+def test_heads_backward_sparse_matches_dense(S):
+    """The object-list form of the heads backward (csrc/heads_sparse.cu) against the dense kernels and autograd:
+    same hidden gradient, same w1 / b1 / b3 gradients, and w3 / input gradients equal to a dense conv backward."""
+    from scd_resnet_b200 import train_ops as T
+    rng = np.random.default_rng(12)
+    B, H, W, TAGS = 3, 32, 48, 30
+    hidden = nhwc(rnd(rng, B, 384, H, W))                                  # ~half of it <= 0: a real ReLU mask
+    x = rnd(rng, B, 256, H, W)
+    w3 = rnd(rng, 384, 256, 3, 3, s=0.05)
+    w1 = torch.from_numpy(rng.standard_normal((7, 128)).astype(np.float32)).cuda()
+    d_heat = torch.from_numpy(rng.standard_normal((B, 1, H, W)).astype(np.float32)).cuda()
+    mask = torch.from_numpy(rng.random((B, TAGS)) < 0.6)
+    idx = torch.from_numpy(rng.integers(0, H * W, size=(B, TAGS)))
+    idx[0, 0] = 0; idx[0, 1] = W - 1; idx[0, 2] = H * W - 1; idx[0, 3] = (H - 1) * W        # corners: taps leave the map
+    idx[1, 5] = idx[1, 4]; mask[1, 4] = mask[1, 5] = True                   # two objects on one pixel
+    mask[0, :4] = True
+    mask[2] = False                                                          # a sample without objects
+    d_obj = torch.from_numpy(rng.standard_normal((B, TAGS, 6)).astype(np.float32)) * mask.unsqueeze(-1)
+    # dense form of the same gradients
+    d_regr = torch.zeros(B, 4, H * W).scatter_add_(2, idx.unsqueeze(1).expand(B, 4, TAGS), d_obj[:, :, 0:4].permute(0, 2, 1).contiguous())
+    d_off = torch.zeros(B, 2, H * W).scatter_add_(2, idx.unsqueeze(1).expand(B, 2, TAGS), d_obj[:, :, 4:6].permute(0, 2, 1).contiguous())
+    g = [(torch.empty(7, 128, device="cuda"), torch.empty(7, device="cuda"), torch.empty(384, device="cuda")) for _ in range(2)]
+    dh_dense = T.heads_bwd(d_heat, d_regr.view(B, 4, H, W).cuda(), d_off.view(B, 2, H, W).cuda(), hidden, w1, *g[0])
+    d_hh, dh_obj = T.heads_bwd_sparse(d_heat, d_obj.cuda(), mask.cuda(), idx.cuda(), hidden, w1, *g[1])
+    assert torch.equal(d_hh, dh_dense[..., :128])
+    for a, b_ in zip(g[0], g[1]):
+        close(b_, a, 1e-4)
+    # scatter the per-object rows back: must reproduce the dense hidden gradient of the regr / offset heads
+    rows = (torch.arange(B).view(B, 1) * H * W + idx).view(-1).cuda()
+    dense_so = torch.zeros(B * H * W, 256, device="cuda").index_add_(0, rows, dh_obj)
+    close(dense_so.view(B, H, W, 256), dh_dense[..., 128:].float(), 1e-2)
+    assert (dh_obj[~mask.view(-1).cuda()] == 0).all()
+    # weight / input gradients of the 3x3 conv for channels 128..383 against autograd on the same fp32 rows
+    xt = x.clone().requires_grad_(True)
+    wt = w3[128:].clone().requires_grad_(True)
+    F.conv2d(xt, wt, padding=1).backward(dense_so.view(B, H, W, 256).permute(0, 3, 1, 2).cpu())
+    out = torch.full((9, 256, 256), float("nan"), device="cuda")
+    T.heads_wgrad_sparse(nhwc(x), dh_obj, mask.cuda(), idx.cuda(), out)
+    close(out.view(3, 3, 256, 256).permute(2, 3, 0, 1), wt.grad, 1e-4)
+    dx = torch.zeros(B, H, W, 256, dtype=torch.bfloat16, device="cuda")
+    T.heads_dgrad_sparse(dh_obj, mask.cuda(), idx.cuda(), S.weights.layout_fwd(w3, 0).to(torch.bfloat16).cuda(), dx)
+    close(nchw(dx), xt.grad, 1e-2)
+
+
 # ------------------------------------------------------------------------------ optimiser
 def test_adam_and_gather(S):
     from scd_resnet_b200 import train_ops as T

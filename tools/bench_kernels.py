@@ -73,7 +73,7 @@ x = torch.randn(32, 1, 512, 512, device=dev, generator=g)
 l32, c32 = synthetic.make_objects(32, seed=3)
 l32, c32 = l32.to(dev), c32.to(dev)
 def step():
-    ys = S.ops.render_targets(l32, c32)
+    ys = S.ops.render_targets(l32, c32, with_npos=True)
     return eng.train_step(x, ys)
 for _ in range(3): step()
 torch.cuda.synchronize()
@@ -87,7 +87,7 @@ torch.cuda.synchronize()
 out["train_step"] = {"device_ms": a.elapsed_time(b) / 10, "host_issue_ms": host}
 # phases with events (forward / backward split is inside forward_backward; measure fwd_bwd vs optimizer)
 a, b, c = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-ys = S.ops.render_targets(l32, c32)
+ys = S.ops.render_targets(l32, c32, with_npos=True)
 torch.cuda.synchronize()
 a.record(); eng.forward_backward(x, ys); b.record(); eng.optimizer_step(); c.record(); torch.cuda.synchronize()
 out["train_step"]["fwd_bwd_ms"] = a.elapsed_time(b); out["train_step"]["adam_refresh_ms"] = b.elapsed_time(c)

@@ -15,7 +15,7 @@ l, c = synthetic.make_objects(32, seed=3)
 l, c = l.to(dev), c.to(dev)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 for _ in range(n):
-    ys = S.ops.render_targets(l, c)
+    ys = S.ops.render_targets(l, c, with_npos=True)
     loss = eng.train_step(x, ys)
 torch.cuda.synchronize()
 print("ok", loss.tolist())
