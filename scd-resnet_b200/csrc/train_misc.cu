@@ -64,43 +64,59 @@ stem_bn_relu_pool_kernel(const uint4* __restrict__ z0, const float* __restrict__
     }
 }
 
-// thread = (conv pixel, 8 channels).  A conv position receives the gradient of every pool window whose recorded
-// argmax is this position (even rows / cols sit in one window, odd ones in two); the ReLU mask is part of the
-// record (code 9).  Reads 1 byte + 2 bytes per (window, channel), writes dy0 once.
+// thread = (2 x 2 block of conv pixels, 8 channels).  A conv position receives the gradient of every pool window
+// whose recorded argmax is this position; the ReLU mask is part of the record (code 9).  The block (2a..2a+1,
+// 2b..2b+1) lies in the windows (a..a+1, b..b+1): four window reads (8 B of codes + 16 B of gradient each) serve
+// four outputs.  Window position codes: dy * 3 + dx with (dy, dx) = conv - (2 * window - 1).
 __global__ void __launch_bounds__(256)
 stem_pool_bwd_kernel(const uint2* __restrict__ argmax, const uint4* __restrict__ da0, int batch, int hp, int wp,
                      uint4* __restrict__ dy0)
 {
-    const int hc = 2 * hp, wc = 2 * wp;
-    const size_t total = (size_t)batch * hc * wc * 8;
+    const int wc = 2 * wp;
+    const size_t total = (size_t)batch * hp * wp * 8;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int g = (int)(i & 7);
         size_t r = i >> 3;
-        const int cx = (int)(r % wc); r /= wc;
-        const int cy = (int)(r % hc);
-        const int b = (int)(r / hc);
-        float out[8];
+        const int b0 = (int)(r % wp); r /= wp;
+        const int a0 = (int)(r % hp);
+        const size_t img = r / hp;
+        uint2 code[2][2];
+        float df[2][2][8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) out[k] = 0.f;
-        const int py_lo = cy >> 1, py_hi = (cy + 1) >> 1;       // equal when cy is even
-        const int px_lo = cx >> 1, px_hi = (cx + 1) >> 1;
-        for (int py = py_lo; py <= py_hi; ++py) {
-            if (py >= hp) continue;
-            for (int px = px_lo; px <= px_hi; ++px) {
-                if (px >= wp) continue;
-                const unsigned want = (unsigned)((cy - 2 * py + 1) * 3 + (cx - 2 * px + 1));
-                const size_t w = (((size_t)b * hp + py) * wp + px) * 8 + g;
-                const uint2 code = __ldg(argmax + w);
-                float df[8];
-                unpack8f(__ldg(da0 + w), df);
+        for (int wy = 0; wy < 2; ++wy)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    out[k] += ((code.x >> (8 * k)) & 0xFFu) == want ? df[k] : 0.f;
-                    out[4 + k] += ((code.y >> (8 * k)) & 0xFFu) == want ? df[4 + k] : 0.f;
+            for (int wx = 0; wx < 2; ++wx) {
+                const bool in = a0 + wy < hp && b0 + wx < wp;
+                code[wy][wx] = make_uint2(0x09090909u, 0x09090909u);
+                uint4 d = make_uint4(0u, 0u, 0u, 0u);
+                if (in) {
+                    const size_t w = ((img * hp + a0 + wy) * wp + b0 + wx) * 8 + g;
+                    code[wy][wx] = __ldg(argmax + w);
+                    d = __ldg(da0 + w);
                 }
+                unpack8f(d, df[wy][wx]);
             }
-        }
-        __stcs(dy0 + i, pack8f(out));
+        // out(ry, rx), ry, rx in {0, 1}: windows (wy <= ry, wx <= rx); code = (ry + 1 - 2 wy) * 3 + (rx + 1 - 2 wx)
+#pragma unroll
+        for (int ry = 0; ry < 2; ++ry)
+#pragma unroll
+            for (int rx = 0; rx < 2; ++rx) {
+                float out[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) out[k] = 0.f;
+#pragma unroll
+                for (int wy = 0; wy <= ry; ++wy)
+#pragma unroll
+                    for (int wx = 0; wx <= rx; ++wx) {
+                        const unsigned want = (unsigned)((ry + 1 - 2 * wy) * 3 + (rx + 1 - 2 * wx));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            out[k] += ((code[wy][wx].x >> (8 * k)) & 0xFFu) == want ? df[wy][wx][k] : 0.f;
+                            out[4 + k] += ((code[wy][wx].y >> (8 * k)) & 0xFFu) == want ? df[wy][wx][4 + k] : 0.f;
+                        }
+                    }
+                __stcs(dy0 + ((img * 2 * hp + 2 * a0 + ry) * wc + 2 * b0 + rx) * 8 + g, pack8f(out));
+            }
     }
 }
 
@@ -247,7 +263,7 @@ extern "C" int scd_stem_pool_bwd(const uint8_t* argmax, const void* da0, int bat
 {
     using namespace scd;
     if (!argmax || !da0 || !dy0) return fail(SCD_EINVAL, "scd_stem_pool_bwd: null pointer");
-    const size_t total = (size_t)batch * hp * wp * 4 * 8;
+    const size_t total = (size_t)batch * hp * wp * 8;
     stem_pool_bwd_kernel<<<sgrid(total, 256), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const uint2*>(argmax), static_cast<const uint4*>(da0), batch, hp, wp, static_cast<uint4*>(dy0));
     SCD_LAUNCH_CHECK("stem_pool_bwd_kernel");

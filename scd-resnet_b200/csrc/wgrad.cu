@@ -253,9 +253,19 @@ extern "C" int scd_conv_wgrad(int kind, const void* a_in, const void* dz, int ba
     p.tiles_x = gw / TM_TW; p.tiles_y = gh / WG_TH; p.batch = batch;
     const int k_tiles = batch * p.tiles_x * p.tiles_y;
     const int out_tiles = p.m_tiles * p.n_tiles;
-    int splits = (kNumSMs + out_tiles - 1) / out_tiles;          // about one work unit per SM ...
-    if (splits > k_tiles / 8) splits = k_tiles / 8;              // ... but at least 8 k-tiles per unit
-    if (splits < 1) splits = 1;
+    // split-K: the persistent grid runs the units in waves of 148, so the makespan is
+    // waves * (k-tiles per unit); pick the split count that minimises it (fewest splits on ties: less
+    // accumulation traffic), with at least 8 k-tiles per unit.  (ceil(148 / tiles) would often give 150-160 units:
+    // a second wave with a dozen busy SMs.)
+    int splits = 1;
+    long best = -1;
+    const int max_splits = k_tiles / 8 < 1 ? 1 : (k_tiles / 8 > 4 * kNumSMs ? 4 * kNumSMs : k_tiles / 8);
+    for (int sp = 1; sp <= max_splits; ++sp) {
+        const long units = (long)out_tiles * sp;
+        const long waves = (units + kNumSMs - 1) / kNumSMs;
+        const long cost = waves * ((k_tiles + sp - 1) / sp + 16);    // + fixed cost per unit (prologue, epilogue)
+        if (best < 0 || cost < best) { best = cost; splits = sp; }
+    }
     p.splits = splits;
     p.total_units = out_tiles * splits;
     p.out = out;
