@@ -57,6 +57,14 @@ int scd_decode_topk(const float* heat, const float* regr, const float* offset,
                     float* scores, int64_t* idx, int64_t* ys, int64_t* xs,
                     float* off_out, float* regr_out, float* planes, void* stream);
 
+/* Same with an explicit kernel choice: impl 0 = by batch size (what scd_decode_topk does), 1 = one CTA per
+ * image (lowest latency, for a few hundred images or fewer), 2 = one warp per image (highest throughput).
+ * Both kernels produce identical results. */
+int scd_decode_topk_impl(const float* heat, const float* regr, const float* offset,
+                         int batch, int classes, int height, int width, int K,
+                         float* scores, int64_t* idx, int64_t* ys, int64_t* xs,
+                         float* off_out, float* regr_out, float* planes, int impl, void* stream);
+
 /* Exhaustive device-side check (all 2^32 fp32 patterns) of the arithmetic facts the decode kernel's
  * logit-space peak test relies on; d_counts3[0..2] receive the number of violations of
  * (0) monotonicity of the fp32 sigmoid, (1) the collapse screen, (2) the logit bound.  Test hook. */
@@ -193,7 +201,9 @@ int scd_resnet10_infer(const float* x, const void* weights, int batch, int heigh
  *   scd_bn_finalize  scale = gamma*invstd, shift = beta - mean*scale, mean, invstd; updates running_mean /
  *                    running_var (unbiased) / num_batches_tracked when given.  `count` = elements per channel.
  *   scd_bn_apply     out = [relu](z*scale + shift [+ residual])
- *   scd_bn_bwd       phase 0: sums = (sum dy, sum dy*xhat) with dy = da * (a > 0) (a == NULL: no ReLU mask);
+ *   scd_bn_bwd       phase 0: sums = (sum dy, sum dy*xhat) with dy = da * (a > 0); a == NULL and shift != NULL:
+ *                    the mask is recomputed as z*scale + shift > 0 (valid when the forward had no residual: one
+ *                    tensor less to read); a == NULL and shift == NULL: no ReLU mask;
  *                    phase 1: dz = scale*(dy - sums0/count - xhat*sums1/count), optional dy_out (the gradient
  *                    entering the residual branch), dgamma, dbeta. */
 int scd_bn_stats(const void* z, size_t pixels, int C, double* sums, void* stream);
@@ -202,8 +212,8 @@ int scd_bn_finalize(const double* sums, const float* gamma, const float* beta, f
                     float eps, float* scale, float* shift, float* mean, float* invstd, void* stream);
 int scd_bn_apply(const void* z, const float* scale, const float* shift, const void* residual, int relu,
                  size_t pixels, int C, void* out, void* stream);
-int scd_bn_bwd(const void* da, const void* a, const void* z, const float* scale, const float* mean,
-               const float* invstd, size_t pixels, int C, double count, double* sums, void* dz,
+int scd_bn_bwd(const void* da, const void* a, const void* z, const float* scale, const float* shift,
+               const float* mean, const float* invstd, size_t pixels, int C, double count, double* sums, void* dz,
                void* dy_out, float* dgamma, float* dbeta, int phase, void* stream);
 
 /* Data gradient of a forward stage of kind 0 (3x3 s1), 1 (3x3 s2, optionally fused with the gradient of the

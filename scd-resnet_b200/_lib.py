@@ -15,6 +15,7 @@ PROTOTYPES = {
     "scd_abi_version": (c_int, []),
     "scd_last_error": (ctypes.c_char_p, []),
     "scd_decode_topk": (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p] * 7 + [c_void_p]),
+    "scd_decode_topk_impl": (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p] * 7 + [c_int, c_void_p]),
     "scd_selftest_decode_math": (c_int, [c_void_p, c_void_p]),
     "scd_render_targets": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 4 + [c_void_p]),
     "scd_render_targets_npos": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 5 + [c_void_p]),
@@ -34,7 +35,7 @@ PROTOTYPES = {
     "scd_bn_stats": (c_int, [c_void_p, c_size_t, c_int, c_void_p, c_void_p]),
     "scd_bn_finalize": (c_int, [c_void_p] * 6 + [c_int, ctypes.c_double, c_float, c_float] + [c_void_p] * 4 + [c_void_p]),
     "scd_bn_apply": (c_int, [c_void_p] * 4 + [c_int, c_size_t, c_int, c_void_p, c_void_p]),
-    "scd_bn_bwd": (c_int, [c_void_p] * 6 + [c_size_t, c_int, ctypes.c_double] + [c_void_p] * 5 + [c_int, c_void_p]),
+    "scd_bn_bwd": (c_int, [c_void_p] * 7 + [c_size_t, c_int, ctypes.c_double] + [c_void_p] * 5 + [c_int, c_void_p]),
     "scd_conv_igemm_dgrad": (c_int, [c_int] + [c_void_p] * 5 + [c_int] * 5 + [c_void_p, c_void_p]),
     "scd_conv_wgrad_out_floats": (c_size_t, [c_int, c_int, c_int]),
     "scd_conv_wgrad": (c_int, [c_int, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p, c_void_p]),

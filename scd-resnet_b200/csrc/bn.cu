@@ -43,6 +43,7 @@ template <int MODE>   // 0: stats of z   1: backward sums
 __global__ void __launch_bounds__(384)
 bn_reduce_kernel(const uint4* __restrict__ z, const uint4* __restrict__ da, const uint4* __restrict__ a,
                  const float* __restrict__ mean, const float* __restrict__ invstd,
+                 const float* __restrict__ scale, const float* __restrict__ shift,    // ReLU mask from z when a == NULL
                  size_t pixels, int cgroups, double* __restrict__ sums /* [2][C] */)
 {
     extern __shared__ float red[];                       // [2][blockDim.x][8]
@@ -52,9 +53,14 @@ bn_reduce_kernel(const uint4* __restrict__ z, const uint4* __restrict__ da, cons
     float s0[8], s1[8], mu[8], is[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s0[i] = 0.f; s1[i] = 0.f; mu[i] = 0.f; is[i] = 1.f; }
+    float sc[8], sh[8];
+    const bool zmask = MODE == 1 && a == nullptr && shift != nullptr;
     if (MODE == 1) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { mu[i] = mean[g * 8 + i]; is[i] = invstd[g * 8 + i]; }
+        for (int i = 0; i < 8; ++i) {
+            mu[i] = mean[g * 8 + i]; is[i] = invstd[g * 8 + i];
+            sc[i] = zmask ? scale[g * 8 + i] : 0.f; sh[i] = zmask ? shift[g * 8 + i] : 0.f;
+        }
     }
     for (size_t p = (size_t)blockIdx.x * lanes + pl; p < pixels; p += (size_t)gridDim.x * lanes) {
         float zf[8];
@@ -70,6 +76,9 @@ bn_reduce_kernel(const uint4* __restrict__ z, const uint4* __restrict__ da, cons
                 unpack8(__ldg(a + p * cgroups + g), af);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) df[i] = af[i] > 0.f ? df[i] : 0.f;
+            } else if (zmask) {             // a = relu(z * scale + shift): the same fma as the forward, same sign
+#pragma unroll
+                for (int i = 0; i < 8; ++i) df[i] = fmaf(zf[i], sc[i], sh[i]) > 0.f ? df[i] : 0.f;
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) { s0[i] += df[i]; s1[i] = fmaf(df[i], (zf[i] - mu[i]) * is[i], s1[i]); }
@@ -148,7 +157,7 @@ bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, co
 // gradient that flows into the residual branch).  Thread 0..C-1 of CTA 0 also emit dgamma, dbeta.
 __global__ void __launch_bounds__(BN_THREADS)
 bn_bwd_apply_kernel(const uint4* __restrict__ da, const uint4* __restrict__ a, const uint4* __restrict__ z,
-                    const float* __restrict__ scale, const float* __restrict__ mean,
+                    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                     const float* __restrict__ invstd, const double* __restrict__ sums, double count,
                     size_t n8, int cgroups, uint4* __restrict__ dz, uint4* __restrict__ dy_out,
                     float* __restrict__ dgamma, float* __restrict__ dbeta)
@@ -165,10 +174,12 @@ bn_bwd_apply_kernel(const uint4* __restrict__ da, const uint4* __restrict__ a, c
     // D = scale (m2 invstd mean - m1), m1 = sum(dy)/n, m2 = sum(dy xhat)/n, hoisted out of the loop.
     const float inv_n = (float)(1.0 / count);
     const int g = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) % cgroups);
-    float cA[8], cB[8], cD[8];
+    float cA[8], cB[8], cD[8], cS[8];
+    const bool zmask = a == nullptr && shift != nullptr;       // ReLU mask recomputed from z (saves reading a)
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int c = g * 8 + k;
+        cS[k] = zmask ? __ldg(shift + c) : 0.f;
         const float m1 = (float)sums[c] * inv_n, m2 = (float)sums[C + c] * inv_n;
         const float sc = __ldg(scale + c), is = __ldg(invstd + c), mu = __ldg(mean + c);
         cA[k] = sc;
@@ -184,6 +195,9 @@ bn_bwd_apply_kernel(const uint4* __restrict__ da, const uint4* __restrict__ a, c
             unpack8(ld_stream_u4(a + i), af);
 #pragma unroll
             for (int k = 0; k < 8; ++k) df[k] = af[k] > 0.f ? df[k] : 0.f;
+        } else if (zmask) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) df[k] = fmaf(zf[k], cA[k], cS[k]) > 0.f ? df[k] : 0.f;
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) o[k] = fmaf(cA[k], df[k], fmaf(cB[k], zf[k], cD[k]));
@@ -225,7 +239,7 @@ extern "C" int scd_bn_stats(const void* z, size_t pixels, int C, double* sums, v
     const int lanes = block / (C / 8);
     const int grid = stream_grid(pixels, lanes * 16);
     bn_reduce_kernel<0><<<grid, block, (size_t)2 * block * 8 * sizeof(float), (cudaStream_t)stream>>>(
-        static_cast<const uint4*>(z), nullptr, nullptr, nullptr, nullptr, pixels, C / 8, sums);
+        static_cast<const uint4*>(z), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, pixels, C / 8, sums);
     SCD_LAUNCH_CHECK("bn_reduce_kernel<0>");
     return SCD_OK;
 }
@@ -258,8 +272,8 @@ extern "C" int scd_bn_apply(const void* z, const float* scale, const float* shif
     return SCD_OK;
 }
 
-extern "C" int scd_bn_bwd(const void* da, const void* a, const void* z, const float* scale, const float* mean,
-                          const float* invstd, size_t pixels, int C, double count, double* sums, void* dz,
+extern "C" int scd_bn_bwd(const void* da, const void* a, const void* z, const float* scale, const float* shift,
+                          const float* mean, const float* invstd, size_t pixels, int C, double count, double* sums, void* dz,
                           void* dy_out, float* dgamma, float* dbeta, int phase, void* stream)
 {
     // phase 0: reduce (sums <- sum dy, sum dy*xhat); phase 1: apply (uses sums, possibly all-reduced in between)
@@ -273,7 +287,7 @@ extern "C" int scd_bn_bwd(const void* da, const void* a, const void* z, const fl
         const int lanes = block / (C / 8);
         bn_reduce_kernel<1><<<stream_grid(pixels, lanes * 16), block, (size_t)2 * block * 8 * sizeof(float), st>>>(
             static_cast<const uint4*>(z), static_cast<const uint4*>(da), static_cast<const uint4*>(a), mean, invstd,
-            pixels, C / 8, sums);
+            scale, shift, pixels, C / 8, sums);
         SCD_LAUNCH_CHECK("bn_reduce_kernel<1>");
     } else {
         if (!dz) return fail(SCD_EINVAL, "scd_bn_bwd: dz is null");
@@ -281,7 +295,7 @@ extern "C" int scd_bn_bwd(const void* da, const void* a, const void* z, const fl
         if (!ablock) return fail(SCD_EINVAL, "scd_bn_bwd: unsupported channel count %d", C);
         const size_t n8 = pixels * (size_t)(C / 8);
         bn_bwd_apply_kernel<<<stream_grid(n8, ablock * 4), ablock, 0, st>>>(
-            static_cast<const uint4*>(da), static_cast<const uint4*>(a), static_cast<const uint4*>(z), scale, mean,
+            static_cast<const uint4*>(da), static_cast<const uint4*>(a), static_cast<const uint4*>(z), scale, shift, mean,
             invstd, sums, count, n8, C / 8, static_cast<uint4*>(dz), static_cast<uint4*>(dy_out), dgamma, dbeta);
         SCD_LAUNCH_CHECK("bn_bwd_apply_kernel");
     }

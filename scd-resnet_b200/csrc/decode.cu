@@ -29,6 +29,11 @@
 
 namespace scd {
 
+// decode_cta.cu: one CTA per image, lower latency per image, lower throughput
+int launch_decode_cta(const float* heat, const float* regr, const float* offset, int batch, int K,
+                      float* scores, int64_t* idx, int64_t* ys, int64_t* xs, float* off_out, float* regr_out,
+                      float* planes, cudaStream_t st);
+
 constexpr int DEC_HW = 128;
 constexpr int DEC_MAXK = 128;
 constexpr int DEC_BUF = 512;            // survivor buffer entries per image
@@ -404,10 +409,11 @@ extern "C" int scd_selftest_decode_math(unsigned long long* counts3, void* strea
     return SCD_OK;
 }
 
-extern "C" int scd_decode_topk(const float* heat, const float* regr, const float* offset,
-                               int batch, int classes, int height, int width, int K,
-                               float* scores, int64_t* idx, int64_t* ys, int64_t* xs,
-                               float* off_out, float* regr_out, float* planes, void* stream)
+// impl: 0 = choose by batch size, 1 = CTA per image (decode_cta.cu), 2 = warp per image (this file)
+extern "C" int scd_decode_topk_impl(const float* heat, const float* regr, const float* offset,
+                                    int batch, int classes, int height, int width, int K,
+                                    float* scores, int64_t* idx, int64_t* ys, int64_t* xs,
+                                    float* off_out, float* regr_out, float* planes, int impl, void* stream)
 {
     if (batch <= 0) return SCD_OK;
     if (classes != 1) return scd::fail(SCD_EINVAL, "scd_decode_topk: classes must be 1 (got %d)", classes);
@@ -416,7 +422,12 @@ extern "C" int scd_decode_topk(const float* heat, const float* regr, const float
     if (K < 1 || K > scd::DEC_MAXK) return scd::fail(SCD_EINVAL, "scd_decode_topk: K must be in [1,128] (got %d)", K);
     if (!heat || !regr || !offset || !scores || !idx || !ys || !xs || !off_out || !regr_out)
         return scd::fail(SCD_EINVAL, "scd_decode_topk: null pointer");
+    if (impl < 0 || impl > 2) return scd::fail(SCD_EINVAL, "scd_decode_topk_impl: impl must be 0, 1 or 2");
     cudaStream_t st = (cudaStream_t)stream;
+    // Measured on B200: the CTA-per-image kernel takes ~37 us per wave of 296 images (2 CTAs / SM), the
+    // warp-per-image kernel 85 us (one image) to 127 us (2048 images): the latter wins from three waves on.
+    if (impl == 1 || (impl == 0 && batch <= 4 * scd::kNumSMs))
+        return scd::launch_decode_cta(heat, regr, offset, batch, K, scores, idx, ys, xs, off_out, regr_out, planes, st);
     if (batch <= 2 * scd::kNumSMs)          // few images: one warp per CTA so that they spread over the SMs
         scd::decode_kernel<1><<<batch, 32, 0, st>>>(heat, regr, offset, batch, K, scores, idx, ys, xs, off_out,
                                                     regr_out, planes);
@@ -425,4 +436,13 @@ extern "C" int scd_decode_topk(const float* heat, const float* regr, const float
                                                               off_out, regr_out, planes);
     SCD_LAUNCH_CHECK("decode_kernel");
     return SCD_OK;
+}
+
+extern "C" int scd_decode_topk(const float* heat, const float* regr, const float* offset,
+                               int batch, int classes, int height, int width, int K,
+                               float* scores, int64_t* idx, int64_t* ys, int64_t* xs,
+                               float* off_out, float* regr_out, float* planes, void* stream)
+{
+    return scd_decode_topk_impl(heat, regr, offset, batch, classes, height, width, K, scores, idx, ys, xs, off_out,
+                                regr_out, planes, 0, stream);
 }

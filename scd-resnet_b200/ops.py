@@ -30,11 +30,12 @@ def _req(t, dtype, name):
     return t.contiguous()
 
 
-def decode_topk(heat, regr, offset, K=100, planes=False):
+def decode_topk(heat, regr, offset, K=100, planes=False, impl=0):
     """decodeCenterNet (ref: models/centerNetOffset.py:219-251) on LOGITS.
 
     Returns (scores f32 (B,K), idx i64, ys i64, xs i64, offset (B,K,2), regr (B,K,4)) and, when
     `planes`, also the (10,B,K) f32 stack of trainer/wrappers/centerOffsetResidual.py:11-22.
+    impl: 0 = kernel chosen by batch size, 1 = CTA per image, 2 = warp per image (identical results).
     """
     heat = _req(heat, torch.float32, "heatmap")
     regr = _req(regr, torch.float32, "regr")
@@ -49,8 +50,8 @@ def decode_topk(heat, regr, offset, K=100, planes=False):
     regr_out = torch.empty(b, K, 4, dtype=torch.float32, device=dev)
     pl = torch.empty(10, b, K, dtype=torch.float32, device=dev) if planes else None
     with torch.cuda.device(dev):
-        check(lib.scd_decode_topk(_ptr(heat), _ptr(regr), _ptr(offset), b, c, h, w, K, _ptr(scores), _ptr(idx),
-                                  _ptr(ys), _ptr(xs), _ptr(off_out), _ptr(regr_out), _ptr(pl), _stream()),
+        check(lib.scd_decode_topk_impl(_ptr(heat), _ptr(regr), _ptr(offset), b, c, h, w, K, _ptr(scores), _ptr(idx),
+                                       _ptr(ys), _ptr(xs), _ptr(off_out), _ptr(regr_out), _ptr(pl), impl, _stream()),
               "scd_decode_topk")
     out = (scores, idx, ys, xs, off_out, regr_out)
     return out + (pl,) if planes else out

@@ -34,8 +34,9 @@ def bn_forward(z, gamma, beta, running_mean=None, running_var=None, num_batches=
     return out, {"stat": stat, "count": count, "sums": sums}
 
 
-def bn_backward(da, a, z, ctx, want_dy=False, dgamma=None, dbeta=None, all_reduce=None):
-    """Backward of bn_forward.  a = the post-ReLU output (ReLU mask) or None.  Returns (dz, dy or None)."""
+def bn_backward(da, a, z, ctx, want_dy=False, dgamma=None, dbeta=None, all_reduce=None, relu_from_z=False):
+    """Backward of bn_forward.  a = the post-ReLU output (ReLU mask) or None; relu_from_z: there was a ReLU and no
+    residual, so the mask is recomputed from z instead of reading a.  Returns (dz, dy or None)."""
     C = z.shape[-1]
     pixels = z.numel() // C
     dev = z.device
@@ -44,7 +45,10 @@ def bn_backward(da, a, z, ctx, want_dy=False, dgamma=None, dbeta=None, all_reduc
     dz = torch.empty_like(z)
     dy = torch.empty_like(z) if want_dy else None
     with torch.cuda.device(dev):
-        args = (_ptr(da), _ptr(a), _ptr(z), _ptr(stat[0]), _ptr(stat[2]), _ptr(stat[3]), pixels, C, count, _ptr(sums))
+        if relu_from_z:
+            a = None
+        args = (_ptr(da), _ptr(a), _ptr(z), _ptr(stat[0]), _ptr(stat[1] if relu_from_z else None), _ptr(stat[2]),
+                _ptr(stat[3]), pixels, C, count, _ptr(sums))
         check(lib.scd_bn_bwd(*args, None, None, None, None, 0, _stream()), "scd_bn_bwd(reduce)")
         if all_reduce is not None:
             all_reduce(sums, None)

@@ -184,9 +184,9 @@ class TrainEngine:
         return T.bn_forward(z, m.weight.data, m.bias.data, m.running_mean, m.running_var, m.num_batches_tracked,
                             residual, relu, all_reduce=self._allreduce_stats if self.world > 1 else None)
 
-    def _bn_bwd(self, da, a, z, ctx, prefix, want_dy=False):
+    def _bn_bwd(self, da, a, z, ctx, prefix, want_dy=False, relu_from_z=False):
         return T.bn_backward(da, a, z, ctx, want_dy, self.g(prefix + ".weight"), self.g(prefix + ".bias"),
-                             all_reduce=self._allreduce_stats if self.world > 1 else None)
+                             all_reduce=self._allreduce_stats if self.world > 1 else None, relu_from_z=relu_from_z)
 
     def _conv(self, kind, x, key, cout):
         return ops.conv_igemm_fwd(kind, x, self.wb(key + ":fwd"), self.zero_bias[:cout], None, False)
@@ -242,14 +242,14 @@ class TrainEngine:
         da = T.conv_dgrad(0, d_hh, self.wb("heads.w3h:dgrad"), self.zero_bias[:256], 256)
         T.heads_dgrad_sparse(dh_obj, mask, gidx, self.wb("heads.w3:fwd"), da)
         for ck, bk, cin, cout, a_in, z, c, a_out in reversed(dtape):
-            dz, _ = self._bn_bwd(da, a_out, z, c, bk)
+            dz, _ = self._bn_bwd(da, None, z, c, bk, relu_from_z=True)       # conv -> BN -> ReLU, no residual
             T.conv_wgrad(3, a_in, dz, cin, cout, self.g(ck + ".weight"))
             da = T.conv_dgrad(3, dz, self.wb(ck + ".weight:dgrad"), self.zero_bias[:cin], cin)
         for p, cin, cout, stride, a_in, z1, a1, c1, z2, c2, zd, cd, a_out in reversed(tape):
             dz2, dy = self._bn_bwd(da, a_out, z2, c2, p + ".bn2", want_dy=True)
             T.conv_wgrad(0, a1, dz2, cout, cout, self.g(p + ".conv2.weight"))
             da1 = T.conv_dgrad(0, dz2, self.wb(p + ".conv2.weight:dgrad"), self.zero_bias[:cout], cout)
-            dz1, _ = self._bn_bwd(da1, a1, z1, c1, p + ".bn1")
+            dz1, _ = self._bn_bwd(da1, None, z1, c1, p + ".bn1", relu_from_z=True)
             if stride == 1:
                 T.conv_wgrad(0, a_in, dz1, cin, cout, self.g(p + ".conv1.weight"))
                 da = T.conv_dgrad(0, dz1, self.wb(p + ".conv1.weight:dgrad"), self.zero_bias[:cin], cin, add=dy)
