@@ -189,6 +189,25 @@ int scd_resnet10_infer(const float* x, const void* weights, int batch, int heigh
                        void* workspace, size_t workspace_bytes, void* const* h_stage_events,
                        void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * fp16 variants of the inference entry points: identical contracts with fp16 in place of bf16 for the NHWC
+ * activations, the GEMM-operand weights and the 16-bit entries of the parameter blob.  tcgen05 kind::f16 runs
+ * both formats at the same rate; fp16's 11-bit mantissa keeps the end-to-end error of the 18-layer network near
+ * 1e-3 (bf16: 0.6-1.3e-2, profiles/accuracy_*.json).  Stores saturate at +-65504.
+ * ---------------------------------------------------------------------------------- */
+int scd_stem_fwd_f16(const float* x, const void* weight, const float* bias, int batch,
+                     int height, int width, void* y, void* stream);
+int scd_conv_igemm_fwd_f16(int kind, const void* x, const void* weight, const float* bias,
+                           const void* residual, int relu, int batch, int hin, int win,
+                           int cin, int cout, void* y, void* stream);
+int scd_heads_fwd_f16(const void* x, const void* w3, const float* b3, const float* w1,
+                      const float* b1, int batch, int height, int width,
+                      float* heat, float* regr, float* offset, void* stream);
+int scd_resnet10_infer_f16(const float* x, const void* weights, int batch, int height, int width,
+                           float* heat, float* regr, float* offset,
+                           void* workspace, size_t workspace_bytes, void* const* h_stage_events,
+                           void* stream);
+
 /* ====================================================================================
  * Training path (NetworkFactory.train, models/networkFactory.py:257-263: forward with
  * batch-statistics BatchNorm -> CenterNetLoss -> backward -> Adam).

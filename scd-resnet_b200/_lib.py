@@ -32,6 +32,11 @@ PROTOTYPES = {
     "scd_infer_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "scd_resnet10_infer": (c_int, [c_void_p, c_void_p] + [c_int] * 3 + [c_void_p] * 3
                            + [c_void_p, c_size_t, c_void_p, c_void_p]),
+    "scd_stem_fwd_f16": (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p, c_void_p]),
+    "scd_conv_igemm_fwd_f16": (c_int, [c_int] + [c_void_p] * 4 + [c_int] * 6 + [c_void_p, c_void_p]),
+    "scd_heads_fwd_f16": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p] * 3 + [c_void_p]),
+    "scd_resnet10_infer_f16": (c_int, [c_void_p, c_void_p] + [c_int] * 3 + [c_void_p] * 3
+                               + [c_void_p, c_size_t, c_void_p, c_void_p]),
     "scd_bn_stats": (c_int, [c_void_p, c_size_t, c_int, c_void_p, c_void_p]),
     "scd_bn_finalize": (c_int, [c_void_p] * 6 + [c_int, ctypes.c_double, c_float, c_float] + [c_void_p] * 4 + [c_void_p]),
     "scd_bn_apply": (c_int, [c_void_p] * 4 + [c_int, c_size_t, c_int, c_void_p, c_void_p]),

@@ -65,10 +65,11 @@ template <int BN> struct IgemmCfg {
     static constexpr int SMEM_BYTES = OFF_CONST + CONST_BYTES + 1024 /*align slack*/;
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool F16>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_kernel(const __grid_constant__ IgemmParams p)
 {
+    using A16 = tc::Act<F16>;
     using Cfg = IgemmCfg<BN>;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t smem_base = (tc::smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -144,8 +145,8 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            constexpr uint32_t idesc_main = tc::umma_idesc_bf16(IG_BM, BN > 256 ? 256 : BN);
-            constexpr uint32_t idesc_tail = tc::umma_idesc_bf16(IG_BM, BN > 256 ? BN - 256 : 16);
+            constexpr uint32_t idesc_main = tc::umma_idesc_16(IG_BM, BN > 256 ? 256 : BN, A16::kFmt);
+            constexpr uint32_t idesc_tail = tc::umma_idesc_16(IG_BM, BN > 256 ? BN - 256 : 16, A16::kFmt);
             int stage = 0; uint32_t phase = 0;
             uint32_t it = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
@@ -239,19 +240,18 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
                         v[4] = __uint_as_float(r[ch * 8 + 4]) + b1.x; v[5] = __uint_as_float(r[ch * 8 + 5]) + b1.y;
                         v[6] = __uint_as_float(r[ch * 8 + 6]) + b1.z; v[7] = __uint_as_float(r[ch * 8 + 7]) + b1.w;
                         if (rptr) {
-                            const __nv_bfloat162* rr = reinterpret_cast<const __nv_bfloat162*>(&resv[ch]);
+                            const uint32_t* rr = reinterpret_cast<const uint32_t*>(&resv[ch]);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) { v[2 * i] += __low2float(rr[i]); v[2 * i + 1] += __high2float(rr[i]); }
+                            for (int i = 0; i < 4; ++i) { v[2 * i] += A16::lo(rr[i]); v[2 * i + 1] += A16::hi(rr[i]); }
                         }
                         if (p.relu) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
                         }
-                        __align__(16) __nv_bfloat162 o[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) o[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                        *reinterpret_cast<uint4*>(stg_gen + lane * 128 + ((ch ^ (lane & 7)) << 4)) =
-                            *reinterpret_cast<const uint4*>(o);
+                        uint4 o;
+                        o.x = A16::pack(v[0], v[1]); o.y = A16::pack(v[2], v[3]);
+                        o.z = A16::pack(v[4], v[5]); o.w = A16::pack(v[6], v[7]);
+                        *reinterpret_cast<uint4*>(stg_gen + lane * 128 + ((ch ^ (lane & 7)) << 4)) = o;
                     }
                     tc::fence_proxy_async();
                     __syncwarp();
@@ -301,12 +301,12 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
                         const int half = (c0 >> 5) & 1;
 #pragma unroll
                         for (int ch = 0; ch < 4; ++ch) {
-                            __align__(16) __nv_bfloat162 hb[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                hb[i] = __floats2bfloat162_rn(__uint_as_float(r[ch * 8 + 2 * i]), __uint_as_float(r[ch * 8 + 2 * i + 1]));
-                            *reinterpret_cast<uint4*>(stg_gen + lane * 128 + (((half * 4 + ch) ^ (lane & 7)) << 4)) =
-                                *reinterpret_cast<const uint4*>(hb);
+                            uint4 hb;
+                            hb.x = A16::pack(__uint_as_float(r[ch * 8 + 0]), __uint_as_float(r[ch * 8 + 1]));
+                            hb.y = A16::pack(__uint_as_float(r[ch * 8 + 2]), __uint_as_float(r[ch * 8 + 3]));
+                            hb.z = A16::pack(__uint_as_float(r[ch * 8 + 4]), __uint_as_float(r[ch * 8 + 5]));
+                            hb.w = A16::pack(__uint_as_float(r[ch * 8 + 6]), __uint_as_float(r[ch * 8 + 7]));
+                            *reinterpret_cast<uint4*>(stg_gen + lane * 128 + (((half * 4 + ch) ^ (lane & 7)) << 4)) = hb;
                         }
                         if (half == 1) {
                             tc::fence_proxy_async();
@@ -344,18 +344,18 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
 }
 
 // ---------------------------------------------------------------------------- host side
-template <int BN, int EPI>
+template <int BN, int EPI, bool F16 = false>
 static int launch_igemm(const IgemmParams& p, cudaStream_t st)
 {
     using Cfg = IgemmCfg<BN>;
     static bool attr_done = false;     // idempotent per-process kernel attribute
     if (!attr_done) {
-        SCD_CUDA_CHECK(cudaFuncSetAttribute(igemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SCD_CUDA_CHECK(cudaFuncSetAttribute(igemm_kernel<BN, EPI, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             Cfg::SMEM_BYTES));
         attr_done = true;
     }
     const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-    igemm_kernel<BN, EPI><<<grid, IG_THREADS, Cfg::SMEM_BYTES, st>>>(p);
+    igemm_kernel<BN, EPI, F16><<<grid, IG_THREADS, Cfg::SMEM_BYTES, st>>>(p);
     SCD_LAUNCH_CHECK("igemm_kernel");
     return SCD_OK;
 }
@@ -365,7 +365,8 @@ static int launch_igemm(const IgemmParams& p, cudaStream_t st)
 //           x = dz of the 3x3 conv, x2 = dz of the 1x1 conv, output at twice the resolution
 //       7 = data-gradient of kind 3: a 4x4 s2 p1 conv of dz (at twice the resolution) -> input resolution
 //   (the data-gradient of kind 0 is kind 0 with flipped, transposed weights)
-static int fill_geometry(IgemmParams& p, int kind, const void* x, const void* x2, int batch, int hin, int win, int cin)
+static int fill_geometry(IgemmParams& p, int kind, const void* x, const void* x2, int batch, int hin, int win, int cin,
+                         bool f16 = false)
 {
     int gh, gw;        // grid the pixel tiles cover (per output-parity class when n_par = 4)
     p.n_par = 1; p.out_mul = 1;
@@ -376,14 +377,14 @@ static int fill_geometry(IgemmParams& p, int kind, const void* x, const void* x2
     int rc;
     if (kind == 0) {
         gh = hin; gw = win; p.n_taps[0] = 9; p.hout = hin; p.wout = win;
-        if ((rc = make_act_map(&p.tmA[0], x, batch, hin, win, cin, 1, 0, 0))) return rc;
+        if ((rc = make_act_map(&p.tmA[0], x, batch, hin, win, cin, 1, 0, 0, 8, f16))) return rc;
         for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
         for (int r = 0; r < 3; ++r) for (int s = 0; s < 3; ++s) { p.tap_dy[0][r * 3 + s] = (int8_t)(r - 1); p.tap_dx[0][r * 3 + s] = (int8_t)(s - 1); }
     } else if (kind == 1 || kind == 2) {
         if (hin % 2 || win % 2) return fail(SCD_EINVAL, "stride-2 conv needs even input size");
         gh = hin / 2; gw = win / 2; p.hout = gh; p.wout = gw;
         for (int py = 0; py < 2; ++py) for (int px = 0; px < 2; ++px)
-            if ((rc = make_act_map(&p.tmA[py * 2 + px], x, batch, hin, win, cin, 2, py, px))) return rc;
+            if ((rc = make_act_map(&p.tmA[py * 2 + px], x, batch, hin, win, cin, 2, py, px, 8, f16))) return rc;
         if (kind == 2) { p.n_taps[0] = 1; }
         else {
             p.n_taps[0] = 9;
@@ -397,7 +398,7 @@ static int fill_geometry(IgemmParams& p, int kind, const void* x, const void* x2
         }
     } else if (kind == 3) {
         gh = hin; gw = win; p.hout = 2 * hin; p.wout = 2 * win; p.n_par = 4; p.out_mul = 2;
-        if ((rc = make_act_map(&p.tmA[0], x, batch, hin, win, cin, 1, 0, 0))) return rc;
+        if ((rc = make_act_map(&p.tmA[0], x, batch, hin, win, cin, 1, 0, 0, 8, f16))) return rc;
         for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
         // oy = 2*iy - 1 + kh.  even oy=2j: kh=1 -> iy=j, kh=3 -> iy=j-1;  odd oy=2j+1: kh=0 -> iy=j+1, kh=2 -> iy=j.
         // tap order inside a parity class = (a, b) with a, b in {0,1}: the host packs weights the same way
@@ -415,9 +416,9 @@ static int fill_geometry(IgemmParams& p, int kind, const void* x, const void* x2
         // class (qy,qx) taps = (a over y choices) x (b over x choices); class (0,0) gets one extra tap that
         // reads x2 = dz of the parallel 1x1 s2 downsample conv (same resolution, same channel count).
         gh = hin; gw = win; p.hout = 2 * hin; p.wout = 2 * win; p.n_par = 4; p.out_mul = 2;
-        if ((rc = make_act_map(&p.tmA[0], x, batch, hin, win, cin, 1, 0, 0))) return rc;
+        if ((rc = make_act_map(&p.tmA[0], x, batch, hin, win, cin, 1, 0, 0, 8, f16))) return rc;
         p.tmA[1] = p.tmA[0];
-        if (x2 && (rc = make_act_map(&p.tmA[1], x2, batch, hin, win, cin, 1, 0, 0))) return rc;
+        if (x2 && (rc = make_act_map(&p.tmA[1], x2, batch, hin, win, cin, 1, 0, 0, 8, f16))) return rc;
         p.tmA[2] = p.tmA[0]; p.tmA[3] = p.tmA[0];
         const int cnt[2] = {1, 2};
         const int dyo[2][2] = {{0, 0}, {1, 0}};
@@ -439,7 +440,7 @@ static int fill_geometry(IgemmParams& p, int kind, const void* x, const void* x2
         gh = hin / 2; gw = win / 2; p.hout = gh; p.wout = gw; p.n_taps[0] = 16;
         const int par_of[4] = {1, 0, 1, 0}, off_of[4] = {-1, 0, 0, 1};
         for (int py = 0; py < 2; ++py) for (int px = 0; px < 2; ++px)
-            if ((rc = make_act_map(&p.tmA[py * 2 + px], x, batch, hin, win, cin, 2, py, px))) return rc;
+            if ((rc = make_act_map(&p.tmA[py * 2 + px], x, batch, hin, win, cin, 2, py, px, 8, f16))) return rc;
         for (int kh = 0; kh < 4; ++kh) for (int kw = 0; kw < 4; ++kw) {
             p.tap_map[0][kh * 4 + kw] = (int8_t)(par_of[kh] * 2 + par_of[kw]);
             p.tap_dy[0][kh * 4 + kw] = (int8_t)off_of[kh];
@@ -462,14 +463,14 @@ static int pick_bn(int cout) { return cout >= 256 ? 256 : (cout >= 128 ? 128 : 6
 
 static int conv_igemm(int kind, const void* x, const void* x2, const void* weight, const float* bias,
                       const void* residual, int relu, int batch, int hin, int win, int cin, int cout, void* y,
-                      void* stream)
+                      void* stream, bool f16 = false)
 {
     using namespace scd;
     if (batch <= 0) return SCD_OK;
     if (!x || !weight || !bias || !y) return fail(SCD_EINVAL, "scd_conv_igemm: null pointer");
     IgemmParams p;
     memset(&p, 0, sizeof(p));
-    int rc = fill_geometry(p, kind, x, x2, batch, hin, win, cin);
+    int rc = fill_geometry(p, kind, x, x2, batch, hin, win, cin, f16);
     if (rc) return rc;
     const int bn = pick_bn(cout);
     if (cout % bn) return fail(SCD_EINVAL, "Cout = %d unsupported", cout);
@@ -478,13 +479,18 @@ static int conv_igemm(int kind, const void* x, const void* x2, const void* weigh
     p.bias = bias; p.residual = static_cast<const __nv_bfloat16*>(residual); p.out = static_cast<__nv_bfloat16*>(y);
     int max_taps = 0;
     for (int a = 0; a < p.n_par; ++a) max_taps = p.n_taps[a] > max_taps ? p.n_taps[a] : max_taps;
-    rc = make_w_map(&p.tmB, weight, max_taps * cin, p.n_par * cout, bn);   // rows = (class, cout), K = taps * cin
+    rc = make_w_map(&p.tmB, weight, max_taps * cin, p.n_par * cout, bn, f16);   // rows = (class, cout), K = taps * cin
     if (rc) return rc;
     for (int par = 0; par < p.n_par; ++par) {
-        rc = make_act_map(&p.tmOut[par], y, batch, p.hout, p.wout, cout, p.out_mul, par >> 1, par & 1, 2);
+        rc = make_act_map(&p.tmOut[par], y, batch, p.hout, p.wout, cout, p.out_mul, par >> 1, par & 1, 2, f16);
         if (rc) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (f16) {
+        if (bn == 256) return launch_igemm<256, EPI_STORE, true>(p, st);
+        if (bn == 128) return launch_igemm<128, EPI_STORE, true>(p, st);
+        return launch_igemm<64, EPI_STORE, true>(p, st);
+    }
     if (bn == 256) return launch_igemm<256, EPI_STORE>(p, st);
     if (bn == 128) return launch_igemm<128, EPI_STORE>(p, st);
     return launch_igemm<64, EPI_STORE>(p, st);
@@ -496,6 +502,14 @@ extern "C" int scd_conv_igemm_fwd(int kind, const void* x, const void* weight, c
 {
     if (kind < 0 || kind > 3) return scd::fail(SCD_EINVAL, "scd_conv_igemm_fwd: kind must be 0..3");
     return conv_igemm(kind, x, nullptr, weight, bias, residual, relu, batch, hin, win, cin, cout, y, stream);
+}
+
+extern "C" int scd_conv_igemm_fwd_f16(int kind, const void* x, const void* weight, const float* bias,
+                                      const void* residual, int relu, int batch, int hin, int win,
+                                      int cin, int cout, void* y, void* stream)
+{
+    if (kind < 0 || kind > 3) return scd::fail(SCD_EINVAL, "scd_conv_igemm_fwd_f16: kind must be 0..3");
+    return conv_igemm(kind, x, nullptr, weight, bias, residual, relu, batch, hin, win, cin, cout, y, stream, true);
 }
 
 extern "C" int scd_conv_igemm_dgrad(int kind, const void* dz, const void* dz2, const void* weight, const float* bias,
@@ -510,7 +524,7 @@ extern "C" int scd_conv_igemm_dgrad(int kind, const void* dz, const void* dz2, c
 
 static int heads_fwd(const void* x, const void* w3, const float* b3, const float* w1,
                      const float* b1, int batch, int height, int width,
-                     float* heat, float* regr, float* offset, void* hidden, void* stream)
+                     float* heat, float* regr, float* offset, void* hidden, void* stream, bool f16 = false)
 {
     using namespace scd;
     if (batch <= 0) return SCD_OK;
@@ -518,17 +532,18 @@ static int heads_fwd(const void* x, const void* w3, const float* b3, const float
         return fail(SCD_EINVAL, "scd_heads_fwd: null pointer");
     IgemmParams p;
     memset(&p, 0, sizeof(p));
-    int rc = fill_geometry(p, 0, x, nullptr, batch, height, width, 256);
+    int rc = fill_geometry(p, 0, x, nullptr, batch, height, width, 256, f16);
     if (rc) return rc;
     p.cout = 384; p.n_tiles_n = 1; p.relu = 1;
     p.total_tiles = batch * p.tiles_y * p.tiles_x;
     p.bias = b3; p.w1 = w1; p.b1 = b1; p.heat = heat; p.regr = regr; p.off = offset;
-    rc = make_w_map(&p.tmB, w3, 9 * 256, 384, IgemmCfg<384>::B_BOX_ROWS);
+    rc = make_w_map(&p.tmB, w3, 9 * 256, 384, IgemmCfg<384>::B_BOX_ROWS, f16);
     if (rc) return rc;
     if (hidden) {
         if ((rc = make_act_map(&p.tmOut[0], hidden, batch, height, width, 384, 1, 0, 0, 2))) return rc;
         return launch_igemm<384, EPI_HEADS_TRAIN>(p, (cudaStream_t)stream);
     }
+    if (f16) return launch_igemm<384, EPI_HEADS, true>(p, (cudaStream_t)stream);
     return launch_igemm<384, EPI_HEADS>(p, (cudaStream_t)stream);
 }
 
@@ -537,6 +552,13 @@ extern "C" int scd_heads_fwd(const void* x, const void* w3, const float* b3, con
                              float* heat, float* regr, float* offset, void* stream)
 {
     return heads_fwd(x, w3, b3, w1, b1, batch, height, width, heat, regr, offset, nullptr, stream);
+}
+
+extern "C" int scd_heads_fwd_f16(const void* x, const void* w3, const float* b3, const float* w1,
+                                 const float* b1, int batch, int height, int width,
+                                 float* heat, float* regr, float* offset, void* stream)
+{
+    return heads_fwd(x, w3, b3, w1, b1, batch, height, width, heat, regr, offset, nullptr, stream, true);
 }
 
 // training forward of the heads: additionally stores hidden = ReLU(conv3x3 + b3), (B,H,W,384) bf16 NHWC

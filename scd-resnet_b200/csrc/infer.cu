@@ -67,10 +67,10 @@ extern "C" size_t scd_infer_workspace_bytes(int batch, int height, int width)
     return per_img * (size_t)batch + 4096;
 }
 
-extern "C" int scd_resnet10_infer(const float* x, const void* weights, int batch, int height, int width,
-                                  float* heat, float* regr, float* offset,
-                                  void* workspace, size_t workspace_bytes, void* const* h_stage_events,
-                                  void* stream)
+static int resnet10_infer_impl(const float* x, const void* weights, int batch, int height, int width,
+                               float* heat, float* regr, float* offset,
+                               void* workspace, size_t workspace_bytes, void* const* h_stage_events,
+                               void* stream, bool f16)
 {
     using namespace scd;
     if (batch <= 0) return SCD_OK;
@@ -104,7 +104,8 @@ extern "C" int scd_resnet10_infer(const float* x, const void* weights, int batch
     };
     int rc = mark(0);
     if (rc) return rc;
-    rc = scd_stem_fwd(x, W(0), Bf(1), batch, height, width, a0, stream);
+    rc = f16 ? scd_stem_fwd_f16(x, W(0), Bf(1), batch, height, width, a0, stream)
+             : scd_stem_fwd(x, W(0), Bf(1), batch, height, width, a0, stream);
     if (rc) return rc;
     if ((rc = mark(1))) return rc;
     struct Step { int conv; const void* in; const void* res; void* out; int hin, win; };
@@ -118,12 +119,31 @@ extern "C" int scd_resnet10_infer(const float* x, const void* weights, int batch
     for (int i = 0; i < 14; ++i) {
         const Step& s = steps[i];
         const ConvSpec& c = kConvs[s.conv];
-        rc = scd_conv_igemm_fwd(c.kind, s.in, W(2 + 2 * s.conv), Bf(3 + 2 * s.conv), s.res, c.relu, batch, s.hin,
-                                s.win, c.cin, c.cout, s.out, stream);
+        rc = (f16 ? scd_conv_igemm_fwd_f16 : scd_conv_igemm_fwd)(c.kind, s.in, W(2 + 2 * s.conv), Bf(3 + 2 * s.conv), s.res,
+                                                                 c.relu, batch, s.hin, s.win, c.cin, c.cout, s.out, stream);
         if (rc) return rc;
         if ((rc = mark(2 + i))) return rc;
     }
-    rc = scd_heads_fwd(e3, W(30), Bf(31), Bf(32), Bf(33), batch, h1, w1, heat, regr, offset, stream);
+    rc = (f16 ? scd_heads_fwd_f16 : scd_heads_fwd)(e3, W(30), Bf(31), Bf(32), Bf(33), batch, h1, w1, heat, regr, offset, stream);
     if (rc) return rc;
     return mark(16);
+}
+
+extern "C" int scd_resnet10_infer(const float* x, const void* weights, int batch, int height, int width,
+                                  float* heat, float* regr, float* offset,
+                                  void* workspace, size_t workspace_bytes, void* const* h_stage_events,
+                                  void* stream)
+{
+    return resnet10_infer_impl(x, weights, batch, height, width, heat, regr, offset, workspace, workspace_bytes,
+                               h_stage_events, stream, false);
+}
+
+// Same pass with fp16 instead of bf16 activations and GEMM operands (the blob's 16-bit entries are fp16).
+extern "C" int scd_resnet10_infer_f16(const float* x, const void* weights, int batch, int height, int width,
+                                      float* heat, float* regr, float* offset,
+                                      void* workspace, size_t workspace_bytes, void* const* h_stage_events,
+                                      void* stream)
+{
+    return resnet10_infer_impl(x, weights, batch, height, width, heat, regr, offset, workspace, workspace_bytes,
+                               h_stage_events, stream, true);
 }

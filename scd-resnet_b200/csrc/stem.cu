@@ -33,10 +33,12 @@ constexpr int ST_OFF_PATCH = ST_OFF_B + 8192;                 // 20 x 20 x 4 bf1
 constexpr int ST_OFF_BAR = ST_OFF_PATCH + ST_PS * ST_PS * 8 + 64;   // +64: chunk reads run 8 B past the end
 constexpr int ST_SMEM = ST_OFF_BAR + 64 + 1024;
 
+template <bool F16>
 __global__ void __launch_bounds__(ST_THREADS, 2)
 stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ x,
                const float* __restrict__ bias, int height, int width, __nv_bfloat16* __restrict__ y)
 {
+    using A16 = tc::Act<F16>;        // y is bf16 or fp16 (same size); the pointer type is nominal
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t sbase = (tc::smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* sgen = smem_dyn + (sbase - tc::smem_u32(smem_dyn));
@@ -69,8 +71,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict_
             float2 v = make_float2(0.f, 0.f);                             // conv zero padding
             if (iy >= 0 && iy < height && ix >= 0 && ix < width)
                 v = *reinterpret_cast<const float2*>(xb + (size_t)iy * width + ix);
-            const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
-            patch[((ry >> 1) * ST_PS + X) * 2 + (ry & 1)] = *reinterpret_cast<const uint32_t*>(&h);
+            patch[((ry >> 1) * ST_PS + X) * 2 + (ry & 1)] = A16::pack(v.x, v.y);
         }
         if (tid < 16) patch[ST_PS * ST_PS * 2 + tid] = 0u;               // slack read by the last chunk
     }
@@ -101,7 +102,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict_
     if (tid == 0) {
         tc::mbar_wait(bar_w, 0);                                          // weights landed
         tc::tc_fence_after();
-        constexpr uint32_t idesc = tc::umma_idesc_bf16(128, ST_CO);
+        constexpr uint32_t idesc = tc::umma_idesc_16(128, ST_CO, A16::kFmt);
 #pragma unroll
         for (int m = 0; m < ST_MT; ++m)
 #pragma unroll
@@ -132,15 +133,15 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict_
                 unsigned char* dst = sgen + ST_OFF_A + row * 128;
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) {
-                    __align__(16) __nv_bfloat162 o[4];
+                    uint32_t o[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int cidx = ch * 8 + 2 * i;
                         const float a = __uint_as_float(cidx < 32 ? r0[cidx] : r1[cidx - 32]) + __ldg(bias + cidx);
                         const float d = __uint_as_float(cidx < 32 ? r0[cidx + 1] : r1[cidx - 31]) + __ldg(bias + cidx + 1);
-                        o[i] = valid ? __floats2bfloat162_rn(fmaxf(a, 0.f), fmaxf(d, 0.f)) : __floats2bfloat162_rn(0.f, 0.f);
+                        o[i] = valid ? A16::pack(fmaxf(a, 0.f), fmaxf(d, 0.f)) : 0u;
                     }
-                    *reinterpret_cast<uint4*>(dst + ((ch ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(o);
+                    *reinterpret_cast<uint4*>(dst + ((ch ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
             }
         }
@@ -152,9 +153,9 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict_
     {
         const int quarter = tid & 3, pos = tid >> 2;                      // 64 pool pixels x 4 quarters
         const int pyl = pos / ST_P, pxl = pos % ST_P;
-        __nv_bfloat162 m[8];
+        uint32_t m[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) m[c] = __floats2bfloat162_rn(0.f, 0.f);
+        for (int c = 0; c < 8; ++c) m[c] = 0u;                            // +0.0 in either format
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
@@ -165,14 +166,14 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict_
                 for (int hch = 0; hch < 2; ++hch) {
                     const int ch = quarter * 2 + hch;
                     const uint4 u = *reinterpret_cast<const uint4*>(src + ((ch ^ (row & 7)) << 4));
-                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+                    const uint32_t h2[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) m[hch * 4 + c] = __hmax2(m[hch * 4 + c], h2[c]);
+                    for (int c = 0; c < 4; ++c) m[hch * 4 + c] = A16::max2(m[hch * 4 + c], h2[c]);
                 }
             }
         uint4* dst = reinterpret_cast<uint4*>(y + (((size_t)b * hp + py0 + pyl) * wp + px0 + pxl) * ST_CO + quarter * 16);
-        dst[0] = reinterpret_cast<const uint4*>(m)[0];
-        dst[1] = reinterpret_cast<const uint4*>(m)[1];
+        dst[0] = make_uint4(m[0], m[1], m[2], m[3]);
+        dst[1] = make_uint4(m[4], m[5], m[6], m[7]);
     }
     __syncthreads();
     if (warp == 1) {
@@ -310,8 +311,9 @@ stem_conv_train_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
 
 }  // namespace scd
 
-extern "C" int scd_stem_fwd(const float* x, const void* weight, const float* bias, int batch,
-                            int height, int width, void* y, void* stream)
+template <bool F16>
+static int stem_fwd_impl(const float* x, const void* weight, const float* bias, int batch,
+                         int height, int width, void* y, void* stream)
 {
     using namespace scd;
     if (batch <= 0) return SCD_OK;
@@ -319,18 +321,30 @@ extern "C" int scd_stem_fwd(const float* x, const void* weight, const float* bia
     if (height % (4 * ST_P) != 0 || width % (4 * ST_P) != 0)
         return fail(SCD_EINVAL, "scd_stem_fwd: H and W must be multiples of %d (got %dx%d)", 4 * ST_P, height, width);
     CUtensorMap tmW;
-    int rc = make_w_map(&tmW, weight, 64, 64, 64);
+    int rc = make_w_map(&tmW, weight, 64, 64, 64, F16);
     if (rc) return rc;
     static bool attr_done = false;
     if (!attr_done) {
-        SCD_CUDA_CHECK(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+        SCD_CUDA_CHECK(cudaFuncSetAttribute(stem_tc_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
         attr_done = true;
     }
     dim3 grid((height / 4 / ST_P) * (width / 4 / ST_P), batch);
-    stem_tc_kernel<<<grid, ST_THREADS, ST_SMEM, (cudaStream_t)stream>>>(
+    stem_tc_kernel<F16><<<grid, ST_THREADS, ST_SMEM, (cudaStream_t)stream>>>(
         tmW, x, bias, height, width, reinterpret_cast<__nv_bfloat16*>(y));
     SCD_LAUNCH_CHECK("stem_tc_kernel");
     return SCD_OK;
+}
+
+extern "C" int scd_stem_fwd(const float* x, const void* weight, const float* bias, int batch,
+                            int height, int width, void* y, void* stream)
+{
+    return stem_fwd_impl<false>(x, weight, bias, batch, height, width, y, stream);
+}
+
+extern "C" int scd_stem_fwd_f16(const float* x, const void* weight, const float* bias, int batch,
+                                int height, int width, void* y, void* stream)
+{
+    return stem_fwd_impl<true>(x, weight, bias, batch, height, width, y, stream);
 }
 
 extern "C" int scd_stem_conv_train(const float* x, const void* weight, int batch, int height, int width,

@@ -2,6 +2,7 @@
 // tcgen05 (UMMA) with TMEM accumulators.  Inline PTX only; no CUTLASS.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace scd {
@@ -120,6 +121,42 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// Same for either 16-bit operand format of kind::f16: fmt 0 = fp16, 1 = bf16 (A at bits [7,10), B at [10,13)).
+__host__ __device__ constexpr uint32_t umma_idesc_16(int m, int n, uint32_t fmt) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// Element type of the inference activations / GEMM operands.  bf16 is the configuration BASELINE names; fp16
+// runs at the same tensor-core rate with an 8x finer mantissa (the network's values are O(1..100): BatchNorm is
+// folded and the tiles are normalised) and saturates at +-65504 instead of producing inf.
+template <bool F16> struct Act;
+template <> struct Act<false> {
+    static constexpr uint32_t kFmt = 1u;
+    __device__ static __forceinline__ uint32_t pack(float a, float b) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<const uint32_t*>(&h);
+    }
+    __device__ static __forceinline__ float lo(uint32_t u) { return __low2float(*reinterpret_cast<const __nv_bfloat162*>(&u)); }
+    __device__ static __forceinline__ float hi(uint32_t u) { return __high2float(*reinterpret_cast<const __nv_bfloat162*>(&u)); }
+    __device__ static __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
+        const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+        return *reinterpret_cast<const uint32_t*>(&r);
+    }
+};
+template <> struct Act<true> {
+    static constexpr uint32_t kFmt = 0u;
+    __device__ static __forceinline__ uint32_t pack(float a, float b) {
+        const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+        return *reinterpret_cast<const uint32_t*>(&h);
+    }
+    __device__ static __forceinline__ float lo(uint32_t u) { return __low2float(*reinterpret_cast<const __half2*>(&u)); }
+    __device__ static __forceinline__ float hi(uint32_t u) { return __high2float(*reinterpret_cast<const __half2*>(&u)); }
+    __device__ static __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
+        const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+        return *reinterpret_cast<const uint32_t*>(&r);
+    }
+};
+
 // D[tmem] (+)= A[smem] * B[smem]^T, issued by one thread for the CTA
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {

@@ -28,7 +28,7 @@ static inline EncodeTiledFn encode_fn() {
 // NHWC bf16 activation viewed as a 4-D tensor {C, W/sub, H/sub, N}; sub = 2 selects the
 // (py, px) parity view used by stride-2 convolutions.
 static inline int make_act_map(CUtensorMap* m, const void* base, int n, int h, int w, int c, int sub, int py, int px,
-                        int box_h = 8)
+                        int box_h = 8, bool f16 = false)
 {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return fail(SCD_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
@@ -37,7 +37,8 @@ static inline int make_act_map(CUtensorMap* m, const void* base, int n, int h, i
     cuuint64_t strides[3] = {(cuuint64_t)sub * c * 2, (cuuint64_t)sub * w * c * 2, (cuuint64_t)h * w * c * 2};
     cuuint32_t box[4] = {TM_BK, TM_TW, (cuuint32_t)box_h, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(b), dims, strides, box, es,
+    CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                     const_cast<char*>(b), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(SCD_ECUDA, "cuTensorMapEncodeTiled(activation) failed: %d", (int)r);
@@ -45,7 +46,7 @@ static inline int make_act_map(CUtensorMap* m, const void* base, int n, int h, i
 }
 
 // weights: 2-D {K, rows} bf16, K contiguous
-static inline int make_w_map(CUtensorMap* m, const void* base, int k_total, int rows, int box_rows)
+static inline int make_w_map(CUtensorMap* m, const void* base, int k_total, int rows, int box_rows, bool f16 = false)
 {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return fail(SCD_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
@@ -53,7 +54,8 @@ static inline int make_w_map(CUtensorMap* m, const void* base, int k_total, int 
     cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
     cuuint32_t box[2] = {TM_BK, (cuuint32_t)box_rows};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+    CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                     const_cast<void*>(base), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(SCD_ECUDA, "cuTensorMapEncodeTiled(weight) failed: %d", (int)r);

@@ -10,15 +10,19 @@ from . import ops, weights
 
 
 class TileDetector:
-    """model: a CenterNetResidual in eval mode (or a state_dict).  batch: tiles per launch."""
+    """model: a CenterNetResidual in eval mode (or a state_dict).  batch: tiles per launch.
+    precision: "bf16" (the configuration BASELINE names) or "fp16" (same speed, ~8x smaller rounding error)."""
 
-    def __init__(self, model_or_sd, batch, device=None, K=100, height=512, width=512):
+    def __init__(self, model_or_sd, batch, device=None, K=100, height=512, width=512, precision="bf16"):
+        if precision not in ("bf16", "fp16"):
+            raise ops.ScdError("precision must be 'bf16' or 'fp16'")
+        self.fp16 = precision == "fp16"
         sd = model_or_sd.state_dict() if hasattr(model_or_sd, "state_dict") else model_or_sd
         sd = {k.replace("module.", "", 1) if k.startswith("module.") else k: v for k, v in sd.items()}
         self.device = torch.device(device if device is not None else "cuda")
         self.batch, self.K, self.h, self.w = batch, K, height, width
         with torch.cuda.device(self.device):
-            self.blob = weights.pack_infer_blob(sd, self.device)
+            self.blob = weights.pack_infer_blob(sd, self.device, torch.float16 if self.fp16 else torch.bfloat16)
             self.workspace = torch.empty(ops.lib.scd_infer_workspace_bytes(batch, height, width), dtype=torch.uint8,
                                          device=self.device)
             hw = (height // 4, width // 4)
@@ -38,7 +42,7 @@ class TileDetector:
         """x (B,1,H,W) f32 on the device -> (10,B,K) f32 planes on the device (current stream)."""
         b = x.shape[0]
         heat, regr, off = [m[:b] for m in self.maps]
-        ops.resnet10_infer(x, self.blob, self.workspace, (heat, regr, off), stage_events)
+        ops.resnet10_infer(x, self.blob, self.workspace, (heat, regr, off), stage_events, fp16=self.fp16)
         return ops.decode_topk(heat, regr, off, K=self.K, planes=True)[6]
 
     def detect_host(self, host_batches):

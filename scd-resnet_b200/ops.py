@@ -161,22 +161,34 @@ def centernet_loss_sparse(heat, regr, offset, gt_heat, mask, regr6, idx, regr_w=
     return losses, d_heat, d_obj
 
 
+def _act_dtype(weight):
+    """Inference activations take the dtype of the packed weights: bf16 (default) or fp16."""
+    if weight.dtype not in (torch.bfloat16, torch.float16):
+        raise ScdError("packed weights must be bfloat16 or float16, got %s" % weight.dtype)
+    return weight.dtype
+
+
 def stem_fwd(x, weight, bias):
-    """ResNet.preprocess (ref: models/backbones/residuals.py:210-215), BN folded. -> (B,H/4,W/4,64) bf16 NHWC."""
+    """ResNet.preprocess (ref: models/backbones/residuals.py:210-215), BN folded. -> (B,H/4,W/4,64) NHWC in the
+    dtype of `weight` (bf16 or fp16)."""
     x = _req(x, torch.float32, "x")
-    weight = _req(weight, torch.bfloat16, "stem weight")
+    dt = _act_dtype(weight)
+    weight = _req(weight, dt, "stem weight")
     bias = _req(bias, torch.float32, "stem bias")
     b, c, h, w = x.shape
-    y = torch.empty(b, h // 4, w // 4, 64, dtype=torch.bfloat16, device=x.device)
+    y = torch.empty(b, h // 4, w // 4, 64, dtype=dt, device=x.device)
+    fn = lib.scd_stem_fwd_f16 if dt == torch.float16 else lib.scd_stem_fwd
     with torch.cuda.device(x.device):
-        check(lib.scd_stem_fwd(_ptr(x), _ptr(weight), _ptr(bias), b, h, w, _ptr(y), _stream()), "scd_stem_fwd")
+        check(fn(_ptr(x), _ptr(weight), _ptr(bias), b, h, w, _ptr(y), _stream()), "scd_stem_fwd")
     return y
 
 
 def conv_igemm_fwd(kind, x, weight, bias, residual=None, relu=True):
-    """One implicit-GEMM stage. x (B,H,W,Cin) bf16 NHWC; weight packed by weights.pack_conv; -> NHWC bf16."""
-    x = _req(x, torch.bfloat16, "x")
-    weight = _req(weight, torch.bfloat16, "weight")
+    """One implicit-GEMM stage. x (B,H,W,Cin) NHWC bf16 or fp16 (= the dtype of `weight`, packed by
+    weights.pack_conv); -> NHWC of the same dtype."""
+    dt = _act_dtype(weight)
+    x = _req(x, dt, "x")
+    weight = _req(weight, dt, "weight")
     bias = _req(bias, torch.float32, "bias")
     b, h, w, cin = x.shape
     cout = bias.numel()
@@ -186,26 +198,29 @@ def conv_igemm_fwd(kind, x, weight, bias, residual=None, relu=True):
         ho, wo = h // 2, w // 2
     else:
         ho, wo = 2 * h, 2 * w
-    y = torch.empty(b, ho, wo, cout, dtype=torch.bfloat16, device=x.device)
+    y = torch.empty(b, ho, wo, cout, dtype=dt, device=x.device)
     if residual is not None:
-        residual = _req(residual, torch.bfloat16, "residual")
+        residual = _req(residual, dt, "residual")
         if residual.shape != y.shape:
             raise ScdError("residual shape mismatch")
+    fn = lib.scd_conv_igemm_fwd_f16 if dt == torch.float16 else lib.scd_conv_igemm_fwd
     with torch.cuda.device(x.device):
-        check(lib.scd_conv_igemm_fwd(kind, _ptr(x), _ptr(weight), _ptr(bias), _ptr(residual), int(relu), b, h, w,
+        check(fn(kind, _ptr(x), _ptr(weight), _ptr(bias), _ptr(residual), int(relu), b, h, w,
                                      cin, cout, _ptr(y), _stream()), "scd_conv_igemm_fwd")
     return y
 
 
 def heads_fwd(x, w3, b3, w1, b1):
-    """The three heads fused (ref: models/centerNetOffset.py:103-122). x (B,H,W,256) bf16 -> NCHW f32 maps."""
-    x = _req(x, torch.bfloat16, "x")
+    """The three heads fused (ref: models/centerNetOffset.py:103-122). x (B,H,W,256) bf16 / fp16 -> NCHW f32 maps."""
+    dt = _act_dtype(w3)
+    x = _req(x, dt, "x")
+    fn = lib.scd_heads_fwd_f16 if dt == torch.float16 else lib.scd_heads_fwd
     b, h, w, c = x.shape
     heat = torch.empty(b, 1, h, w, dtype=torch.float32, device=x.device)
     regr = torch.empty(b, 4, h, w, dtype=torch.float32, device=x.device)
     off = torch.empty(b, 2, h, w, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        check(lib.scd_heads_fwd(_ptr(x), _ptr(_req(w3, torch.bfloat16, "w3")), _ptr(_req(b3, torch.float32, "b3")),
+        check(fn(_ptr(x), _ptr(_req(w3, dt, "w3")), _ptr(_req(b3, torch.float32, "b3")),
                                 _ptr(_req(w1, torch.float32, "w1")), _ptr(_req(b1, torch.float32, "b1")), b, h, w,
                                 _ptr(heat), _ptr(regr), _ptr(off), _stream()), "scd_heads_fwd")
     return heat, regr, off
@@ -219,11 +234,11 @@ def infer_weights_layout():
     return list(offs), list(sizes), lib.scd_infer_weights_bytes()
 
 
-def resnet10_infer(x, blob, workspace=None, out=None, stage_events=None):
+def resnet10_infer(x, blob, workspace=None, out=None, stage_events=None, fp16=False):
     """ResNet.forward, eval, decode=False (ref: models/backbones/residuals.py:312-334) as one native call.
 
-    x (B,1,H,W) f32; blob = packed BN-folded weights (weights.pack_infer_blob).  Returns heat, regr, offset
-    (NCHW f32) and the workspace (reusable).
+    x (B,1,H,W) f32; blob = packed BN-folded weights (weights.pack_infer_blob; `fp16` must match the dtype it was
+    packed with).  Returns heat, regr, offset (NCHW f32) and the workspace (reusable).
     """
     x = _req(x, torch.float32, "x")
     b, c, h, w = x.shape
@@ -242,8 +257,9 @@ def resnet10_infer(x, blob, workspace=None, out=None, stage_events=None):
             raise ScdError("stage_events must hold 17 events")
         ev = (ctypes.c_void_p * 17)(*[e.cuda_event for e in stage_events])
     with torch.cuda.device(dev):
-        check(lib.scd_resnet10_infer(_ptr(x), _ptr(blob), b, h, w, _ptr(heat), _ptr(regr), _ptr(off),
-                                     _ptr(workspace), workspace.numel(), ev, _stream()), "scd_resnet10_infer")
+        fn = lib.scd_resnet10_infer_f16 if fp16 else lib.scd_resnet10_infer
+        check(fn(_ptr(x), _ptr(blob), b, h, w, _ptr(heat), _ptr(regr), _ptr(off),
+                 _ptr(workspace), workspace.numel(), ev, _stream()), "scd_resnet10_infer")
     return heat, regr, off, workspace
 
 

@@ -31,7 +31,7 @@ def bn_scale_shift(sd, prefix):
     return scale, shift
 
 
-def pack_conv(weight, kind, scale=None):
+def pack_conv(weight, kind, scale=None, dtype=torch.bfloat16):
     """Conv2d weight (Cout,Cin,R,S) -> (Cout, R*S*Cin) bf16, k = (r*S + s)*Cin + c (kinds 0-2);
     ConvTranspose2d weight (Cin,Cout,4,4) -> (4, Cout, 4*Cin) bf16 by output parity (kind 3):
     class (qy,qx), tap (a,b): kh = KH[qy][a], kw = KH[qx][b], KH = [[1,3],[0,2]]
@@ -40,7 +40,7 @@ def pack_conv(weight, kind, scale=None):
     if kind != 3:
         if scale is not None:
             w = w * scale.view(-1, 1, 1, 1)
-        return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
+        return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(dtype).contiguous()
     if scale is not None:
         w = w * scale.view(1, -1, 1, 1)
     kh_of = ((1, 3), (0, 2))
@@ -52,10 +52,10 @@ def pack_conv(weight, kind, scale=None):
                 for b in range(2):
                     t = a * 2 + b
                     out[qy * 2 + qx, :, t * cin:(t + 1) * cin] = w[:, :, kh_of[qy][a], kh_of[qx][b]].t()
-    return out.to(torch.bfloat16).contiguous()
+    return out.to(dtype).contiguous()
 
 
-def pack_stem(weight, scale=None):
+def pack_stem(weight, scale=None, dtype=torch.bfloat16):
     """Conv2d 1->64 7x7 s2 weight (64,1,7,7) -> (64, 64) bf16 for the space-to-depth stem GEMM:
     k = (dy*4 + dx)*4 + py*2 + px  <->  (ky, kx) = (2*dy + py - 1, 2*dx + px - 1); the 15 entries
     with ky == -1 or kx == -1 are structural zeros (csrc/stem.cu)."""
@@ -66,29 +66,30 @@ def pack_stem(weight, scale=None):
     full[:, 1:, 1:] = w                                   # index t = k + 1 in 0..7, t = 0 is the zero tap
     # t_y = 2*dy + py, t_x = 2*dx + px  ->  (dy, py, dx, px) -> order (dy, dx, py, px)
     full = full.reshape(64, 4, 2, 4, 2).permute(0, 1, 3, 2, 4).reshape(64, 64)
-    return full.to(torch.bfloat16).contiguous()
+    return full.to(dtype).contiguous()
 
 
-def fold(sd):
-    """BN-folded, packed tensors of every stage (dict of name -> tensor), for eval-mode inference."""
+def fold(sd, dtype=torch.bfloat16):
+    """BN-folded, packed tensors of every stage (dict of name -> tensor), for eval-mode inference.
+    dtype: the 16-bit format of the GEMM operands and activations, torch.bfloat16 or torch.float16."""
     out = {}
     s, b = bn_scale_shift(sd, "preprocess.1")
-    out["stem_w"] = pack_stem(sd["preprocess.0.weight"], s)
+    out["stem_w"] = pack_stem(sd["preprocess.0.weight"], s, dtype)
     out["stem_b"] = b.contiguous()
     for i, (ck, bk, kind) in enumerate(STAGES):
         s, b = bn_scale_shift(sd, bk)
-        out["w%d" % i] = pack_conv(sd[ck + ".weight"], kind, s)
+        out["w%d" % i] = pack_conv(sd[ck + ".weight"], kind, s, dtype)
         out["b%d" % i] = b.contiguous()
-    out["head_w3"] = torch.cat([pack_conv(sd[h + ".0.weight"], 0) for h in HEADS], 0).contiguous()
+    out["head_w3"] = torch.cat([pack_conv(sd[h + ".0.weight"], 0, None, dtype) for h in HEADS], 0).contiguous()
     out["head_b3"] = torch.cat([sd[h + ".0.bias"].float() for h in HEADS], 0).contiguous()
     out["head_w1"] = torch.cat([sd[h + ".2.weight"].float().reshape(-1, 128) for h in HEADS], 0).contiguous()
     out["head_b1"] = torch.cat([sd[h + ".2.bias"].float() for h in HEADS], 0).contiguous()
     return out
 
 
-def pack_infer_blob(sd, device):
-    """The packed parameter blob of scd_resnet10_infer (layout: include/scd_b200.h)."""
-    f = fold(sd)
+def pack_infer_blob(sd, device, dtype=torch.bfloat16):
+    """The packed parameter blob of scd_resnet10_infer / scd_resnet10_infer_f16 (layout: include/scd_b200.h)."""
+    f = fold(sd, dtype)
     offs, sizes, total = ops.infer_weights_layout()
     entries = [f["stem_w"], f["stem_b"]]
     for i in range(len(STAGES)):

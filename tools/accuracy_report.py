@@ -24,6 +24,9 @@ with torch.no_grad():
 blob = S.weights.pack_infer_blob(sd, "cuda")
 heat, regr, off, _ = S.ops.resnet10_infer(x.cuda(), blob)
 rep = {"ours_bf16_vs_fp32_oracle": {k: metrics(v, ref[k]) for k, v in (("heatmap", heat), ("regr", regr), ("offset", off))}}
+blob16 = S.weights.pack_infer_blob(sd, "cuda", torch.float16)
+h16, r16, o16, _ = S.ops.resnet10_infer(x.cuda(), blob16, fp16=True)
+rep["ours_fp16_vs_fp32_oracle"] = {k: metrics(v, ref[k]) for k, v in (("heatmap", h16), ("regr", r16), ("offset", o16))}
 sdg = {k: v.cuda() for k, v in sd.items()}
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
@@ -35,4 +38,5 @@ rep["torch_cuda_fp32_vs_fp32_oracle"] = {k: metrics(g32[k], ref[k]) for k in ref
 rep["torch_cuda_bf16_autocast_vs_fp32_oracle"] = {k: metrics(g16[k].float(), ref[k]) for k in ref}
 # probabilities (what decode and the loss consume)
 rep["ours_sigmoid_heat"] = metrics(torch.sigmoid(heat), torch.sigmoid(ref["heatmap"]))
+rep["ours_fp16_sigmoid_heat"] = metrics(torch.sigmoid(h16), torch.sigmoid(ref["heatmap"]))
 print(json.dumps(rep, indent=1))
