@@ -313,6 +313,9 @@ int scd_scale_inplace(float* x, size_t n, const float* d_scale, void* stream);
 int scd_slide_geometry(int height, int width, int* h_geom6);  /* clipH, clipV, resizeH, resizeW, padTB, padLR */
 int scd_slide_tiles(const float* gray, int height, int width, int tile_begin, int tile_end,
                     float* tiles, void* stream);
+/* Same for a uint8 grey image (the rounded grey values of test.py:31 are integers in [0, 255]). */
+int scd_slide_tiles_u8(const uint8_t* gray, int height, int width, int tile_begin, int tile_end,
+                       float* tiles, void* stream);
 
 #ifdef __cplusplus
 }

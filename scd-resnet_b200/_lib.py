@@ -57,6 +57,7 @@ PROTOTYPES = {
     "scd_scale_inplace": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "scd_slide_geometry": (c_int, [c_int, c_int, c_void_p]),
     "scd_slide_tiles": (c_int, [c_void_p] + [c_int] * 4 + [c_void_p, c_void_p]),
+    "scd_slide_tiles_u8": (c_int, [c_void_p] + [c_int] * 4 + [c_void_p, c_void_p]),
 }
 
 

@@ -50,8 +50,14 @@ class CenterNetResidual(torch.nn.Module):
     """ResNet-10 CenterNet with heatmap / regr / offset heads (ref: models/centerNetOffset.py:150-168,
     models/backbones/residuals.py:184-353).  Only numLayers=10 with the default dims is built here."""
 
-    def __init__(self, numLayers=10, dims=(64, 64, 128, 256, 512, 256, 256, 256)):
+    def __init__(self, numLayers=10, dims=(64, 64, 128, 256, 512, 256, 256, 256), precision="bf16"):
+        """precision: 16-bit format of the eval-mode tensor-core path, "bf16" (BASELINE's configuration) or "fp16"
+        (same speed, ~8x smaller rounding error: 1e-3 instead of 1e-2 against the fp32 reference).  It can also be
+        switched later through the `precision` attribute."""
         super().__init__()
+        if precision not in ("bf16", "fp16"):
+            raise ScdError("precision must be 'bf16' or 'fp16'")
+        self.precision = precision
         dims = list(dims)
         if numLayers != 10 or dims != [64, 64, 128, 256, 512, 256, 256, 256]:
             raise ScdError("scd_b200 builds centerOffsetRes10 only (numLayers=10, default dims); got %r %r"
@@ -103,10 +109,11 @@ class CenterNetResidual(torch.nn.Module):
     # ------------------------------------------------------------------ eval-mode parameters
     def _infer_blob(self):
         """BN-folded, GEMM-packed parameters; rebuilt whenever a parameter or buffer changed."""
-        key = tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        key = (self.precision,) + tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
         if self._blob is None or self._blob_key != key:
             sd = {k: v.detach() for k, v in self.state_dict().items()}
-            self._blob = weights.pack_infer_blob(sd, next(self.parameters()).device)
+            self._blob = weights.pack_infer_blob(sd, next(self.parameters()).device,
+                                                 torch.float16 if self.precision == "fp16" else torch.bfloat16)
             self._blob_key = key
         return self._blob
 
@@ -122,7 +129,7 @@ class CenterNetResidual(torch.nn.Module):
         else:
             with torch.no_grad():
                 heat, regr, off, self._workspace = ops.resnet10_infer(inp.float(), self._infer_blob(),
-                                                                      self._workspace)
+                                                                      self._workspace, fp16=self.precision == "fp16")
             ret = {"heatmap": heat, "regr": regr, "offset": off}
         return [ret] if not decode else self.decoder(ret)
 

@@ -47,8 +47,9 @@ __device__ __forceinline__ double block_sum_f64(double v, double* sh) {
     return t;
 }
 
+template <typename T>        // grey values as float (what test.py holds) or uint8 (what the scanner wrote: 4x less to upload)
 __global__ void __launch_bounds__(SL_THREADS)
-slide_tiles_kernel(const float* __restrict__ gray, int height, int width, SlideGeom g,
+slide_tiles_kernel(const T* __restrict__ gray, int height, int width, SlideGeom g,
                    int tile_begin, float* __restrict__ tiles)
 {
     __shared__ double sh[SL_THREADS / 32];
@@ -72,21 +73,21 @@ slide_tiles_kernel(const float* __restrict__ gray, int height, int width, SlideG
     (void)ox;
     double sum = 0.0;
     for (int r = rbase; r < SL_TILE; r += SL_THREADS / 128) {
-        const float* row = gray + (size_t)reflect(oy + r, height) * width;
+        const T* row = gray + (size_t)reflect(oy + r, height) * width;
         sum += (double)row[sx[0]] + (double)row[sx[1]] + (double)row[sx[2]] + (double)row[sx[3]];
     }
     const double n = (double)SL_TILE * SL_TILE;
     const double mean = block_sum_f64(sum, sh) / n;            // torch.mean
     double ss = 0.0;
     for (int r = rbase; r < SL_TILE; r += SL_THREADS / 128) {
-        const float* row = gray + (size_t)reflect(oy + r, height) * width;
+        const T* row = gray + (size_t)reflect(oy + r, height) * width;
 #pragma unroll
         for (int c = 0; c < 4; ++c) { const double d = (double)row[sx[c]] - mean; ss += d * d; }
     }
     const double sd = sqrt(block_sum_f64(ss, sh) / n);         // sqrt(mean(square(t - mean)))
     float* out = tiles + (size_t)blockIdx.x * SL_TILE * SL_TILE;
     for (int r = rbase; r < SL_TILE; r += SL_THREADS / 128) {
-        const float* row = gray + (size_t)reflect(oy + r, height) * width;
+        const T* row = gray + (size_t)reflect(oy + r, height) * width;
         float4 o;
         o.x = (float)(((double)row[sx[0]] - mean) / sd);
         o.y = (float)(((double)row[sx[1]] - mean) / sd);
@@ -108,8 +109,8 @@ extern "C" int scd_slide_geometry(int height, int width, int* h_geom6)
     return SCD_OK;
 }
 
-extern "C" int scd_slide_tiles(const float* gray, int height, int width, int tile_begin, int tile_end,
-                               float* tiles, void* stream)
+template <typename T>
+static int slide_tiles_impl(const T* gray, int height, int width, int tile_begin, int tile_end, float* tiles, void* stream)
 {
     if (!gray || !tiles) return scd::fail(SCD_EINVAL, "scd_slide_tiles: null pointer");
     if (height <= 2 * scd::SL_PAD || width <= 2 * scd::SL_PAD)
@@ -121,8 +122,20 @@ extern "C" int scd_slide_tiles(const float* gray, int height, int width, int til
         return scd::fail(SCD_EINVAL, "scd_slide_tiles: tile range [%d,%d) outside [0,%d)", tile_begin, tile_end,
                          g.clip_h * g.clip_v);
     if (tile_begin == tile_end) return SCD_OK;
-    scd::slide_tiles_kernel<<<tile_end - tile_begin, scd::SL_THREADS, 0, (cudaStream_t)stream>>>(
+    scd::slide_tiles_kernel<T><<<tile_end - tile_begin, scd::SL_THREADS, 0, (cudaStream_t)stream>>>(
         gray, height, width, g, tile_begin, tiles);
     SCD_LAUNCH_CHECK("slide_tiles_kernel");
     return SCD_OK;
+}
+
+extern "C" int scd_slide_tiles(const float* gray, int height, int width, int tile_begin, int tile_end,
+                               float* tiles, void* stream)
+{
+    return slide_tiles_impl<float>(gray, height, width, tile_begin, tile_end, tiles, stream);
+}
+
+extern "C" int scd_slide_tiles_u8(const uint8_t* gray, int height, int width, int tile_begin, int tile_end,
+                                  float* tiles, void* stream)
+{
+    return slide_tiles_impl<uint8_t>(gray, height, width, tile_begin, tile_end, tiles, stream);
 }

@@ -271,8 +271,12 @@ def slide_geometry(height, width):
 
 
 def slide_tiles(gray, tile_begin=0, tile_end=None):
-    """Reflect pad + stride-384 tiling + per-tile fp64 normalise (ref: test.py:48-90). gray (H,W) f32 CUDA."""
-    gray = _req(gray, torch.float32, "gray")
+    """Reflect pad + stride-384 tiling + per-tile fp64 normalise (ref: test.py:48-90).
+    gray (H,W) CUDA tensor of grey values, float32 or uint8."""
+    if gray.dtype == torch.uint8:
+        gray, fn = _req(gray, torch.uint8, "gray"), lib.scd_slide_tiles_u8
+    else:
+        gray, fn = _req(gray, torch.float32, "gray"), lib.scd_slide_tiles
     h, w = gray.shape
     g = slide_geometry(h, w)
     total = g[0] * g[1]
@@ -280,5 +284,5 @@ def slide_tiles(gray, tile_begin=0, tile_end=None):
         tile_end = total
     tiles = torch.empty(tile_end - tile_begin, 1, 512, 512, dtype=torch.float32, device=gray.device)
     with torch.cuda.device(gray.device):
-        check(lib.scd_slide_tiles(_ptr(gray), h, w, tile_begin, tile_end, _ptr(tiles), _stream()), "scd_slide_tiles")
+        check(fn(_ptr(gray), h, w, tile_begin, tile_end, _ptr(tiles), _stream()), "scd_slide_tiles")
     return tiles

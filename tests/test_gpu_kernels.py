@@ -286,6 +286,8 @@ def test_slide_tiles(S, golden):
     assert tiles.shape == exp.shape
     assert relmax(tiles, exp) < 1e-6
     assert (tiles != exp).float().mean() < 1e-3
+    u8 = S.ops.slide_tiles(dev(torch.from_numpy(gray).to(torch.uint8))).cpu()       # integer grey values: same tiles
+    assert torch.equal(u8, tiles)
     part = S.ops.slide_tiles(dev(torch.from_numpy(gray).float()), 3, 7).cpu()
     assert torch.equal(part, tiles[3:7])
     assert np.allclose(tiles[0, 0, ::16, ::16].numpy(), g["tile0_sub"], rtol=1e-6, atol=1e-7)
