@@ -302,6 +302,26 @@ int scd_gather_cast_bf16(const float* src, const int* idx, size_t n, void* dst, 
 int scd_scale_inplace(float* x, size_t n, const float* d_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Detection metrics of the validation loop.  Replaces centerNetEvaluation
+ * (models/centerNetOffset.py:253-353) with IoU / IoUConfidence / Orthogonity / MAE
+ * (evaluations/detection.py:12-205): all K x L detection / object pairs of every sample in one pass, the
+ * reference's ~20 masked_select compactions as five ordered streams.
+ *
+ * Inputs: the decode outputs scores (B,K) f32, ys / xs (B,K) i64, offset (B,K,2), regr (B,K,4) and the targets
+ * regr6 (B,L,6), gt_idx (B,L) i64, mask (B,L) u8.  K <= 128, L <= 64.
+ * out: 9 rows of B*K*L floats, each compacted in the reference's (n, k, l) order:
+ *   0 iou, 1 score (counts5[0] entries) | 2 sine between major axes, 6 / 7 / 8 absolute errors of major length,
+ *   minor length, radius (counts5[1]) | 3 ioucenter (counts5[2]) | 4 iouoffsetwo (counts5[3]) | 5 iouoffset
+ *   (counts5[4]).  obj_num (B) i32 = mask.sum() per sample.  Bit-identical to the ATen arithmetic.
+ * ---------------------------------------------------------------------------------- */
+size_t scd_centernet_eval_workspace_bytes(int batch, int K, int L);
+int scd_centernet_eval(const float* scores, const int64_t* ys, const int64_t* xs, const float* offset,
+                       const float* regr, const float* regr6, const int64_t* gt_idx, const uint8_t* mask,
+                       int batch, int K, int L, int heatmap_size, float score_thr,
+                       float* out, int* counts5, int* obj_num,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Slide front-end: per-tile normalisation.  Replaces normalize
  * (datasets/argumentations.py:39-44) as applied per 512x512 tile in test.py:86-90,
  * including the reflect padding of test.py:59-60 and the stride-384 tiling (:48-57).

@@ -225,6 +225,25 @@ def main():
          "tile_abs": tiles.double().abs().sum(dim=(1, 2, 3)).numpy(),
          "tile0_sub": tiles[0, 0, ::16, ::16].numpy(), "tileL_sub": tiles[-1, 0, ::16, ::16].numpy()}
     np.savez_compressed(os.path.join(OUT, "slide.npz"), **s)
+    # ---------------- evaluation: centerNetEvaluation + AP -----------------
+    from models.centerNetOffset import centerNetEvaluation
+    from evaluations.detection import averagePrecisionPlots, averagePrecisionAll
+    from configuration import defaultConfig
+    defaultConfig.useGPU = False
+    tg_e, sc_e, ys_e, xs_e, off_e, regr_e = O.make_eval_case(6, seed=5)
+    ev, _ = centerNetEvaluation(None, tg_e, sc_e, None, ys_e, xs_e, off_e, regr_e, None)
+    e = {"seed": np.int64(5), "batch": np.int64(6),
+         "iou": ev["iouscore"][0].numpy(), "score": ev["iouscore"][1].numpy(), "ortho": ev["ortho"].numpy(),
+         "ioucenter": ev["ioucenter"].numpy(), "iouoffsetwo": ev["iouoffsetwo"].numpy(),
+         "iouoffset": ev["iouoffset"].numpy(), "mae_maj": ev["maes"][0].numpy(), "mae_min": ev["maes"][1].numpy(),
+         "mae_rad": ev["maes"][2].numpy(), "objs": np.array(ev["objs"], np.int64)}
+    obj_num = max(int(sum(ev["objs"])), len(ev["iouscore"][0]))
+    for thr in (0.3, 0.5, 0.7, 0.9):
+        plots = averagePrecisionPlots(ev["iouscore"][0], ev["iouscore"][1], obj_num, thr)
+        e["plots%d" % int(thr * 100)] = np.array(plots, np.float64).reshape(-1, 2)
+        e["ap%d" % int(thr * 100)] = np.float64(averagePrecisionAll(plots))
+    e["expression"] = np.array(plugin.expression([ev]))
+    np.savez_compressed(os.path.join(OUT, "evaluation.npz"), **e)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

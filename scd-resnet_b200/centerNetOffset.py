@@ -144,6 +144,23 @@ def decodeCenterNet(outputDictionary, K=100, nmsKernelSize=3, **kwargs):
     return [sc, idx, ys, xs, off, regr, outputDictionary]
 
 
+def centerNetEvaluation(xs, ys, ctScores, ctIndices, ctY, ctX, offset, regression, outputDictionary):
+    """ref: centerNetEvaluation models/centerNetOffset.py:253-353 (the plugin's `evaluation` export, called as
+    evaluation(xs, ys, *decodeResult), networkFactory.py:271).  Same dictionary, same element order; the tensors
+    stay on the device like the reference's do when useGPU is set."""
+    with torch.no_grad():
+        out, counts, obj = ops.centernet_eval(ctScores, ctY, ctX, offset, regression, ys[2], ys[3], ys[1])
+        n = counts.tolist()                                   # one host sync (the reference has ~25: masked_select, .item())
+    row = lambda r, m: out[r, :n[m]]
+    return {'iouscore': [row(0, 0), row(1, 0)],
+            'ortho': row(2, 1),
+            'ioucenter': row(3, 2),
+            'iouoffsetwo': row(4, 3),
+            'iouoffset': row(5, 4),
+            'maes': [row(6, 1), row(7, 1), row(8, 1)],
+            'objs': obj.tolist()}, outputDictionary
+
+
 class _CenterNetLossFn(torch.autograd.Function):
     """Fused loss forward+backward (scd_centernet_loss); gradients are produced in the forward pass."""
 

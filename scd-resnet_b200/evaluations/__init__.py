@@ -1,0 +1,1 @@
+"""Mirror of the reference's `evaluations` package for the centerOffsetRes10 path."""

@@ -102,7 +102,7 @@ class NetworkFactory(object):
                 result = self.model(*xs, decode=True)
         finally:
             self.model.train(was)
-        if self.evaluation is None:
+        if self.evaluation is None or ys is None:
             return result
         return self.evaluation(xs, ys, *result)
 

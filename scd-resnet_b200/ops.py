@@ -168,6 +168,37 @@ def _act_dtype(weight):
     return weight.dtype
 
 
+def centernet_eval(scores, ys, xs, offset, regr, regr6, gt_idx, mask, threshold=0.3):
+    """Pair metrics of centerNetEvaluation (ref: models/centerNetOffset.py:253-353) in one native call.
+
+    Returns (out (9, B*K*L) f32 with every row compacted, counts (5,) i32, obj_num (B,) i32), all on the device;
+    row / count layout in include/scd_b200.h.
+    """
+    scores = _req(scores, torch.float32, "scores")
+    ys = _req(ys, torch.int64, "ys")
+    xs = _req(xs, torch.int64, "xs")
+    offset = _req(offset, torch.float32, "offset")
+    regr = _req(regr, torch.float32, "regr")
+    regr6 = _req(regr6, torch.float32, "gt regr")
+    gt_idx = _req(gt_idx, torch.int64, "gt idx")
+    if mask.dtype == torch.bool:
+        mask = mask.contiguous().view(torch.uint8)
+    mask = _req(mask, torch.uint8, "mask")
+    b, k = scores.shape
+    l = regr6.shape[1]
+    dev = scores.device
+    out = torch.empty(9, b * k * l, dtype=torch.float32, device=dev)
+    counts = torch.empty(5, dtype=torch.int32, device=dev)
+    obj = torch.empty(b, dtype=torch.int32, device=dev)
+    nbytes = lib.scd_centernet_eval_workspace_bytes(b, k, l)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.scd_centernet_eval(_ptr(scores), _ptr(ys), _ptr(xs), _ptr(offset), _ptr(regr), _ptr(regr6),
+                                     _ptr(gt_idx), _ptr(mask), b, k, l, HEATMAPSIZE, threshold, _ptr(out), _ptr(counts),
+                                     _ptr(obj), _ptr(ws), nbytes, _stream()), "scd_centernet_eval")
+    return out, counts, obj
+
+
 def stem_fwd(x, weight, bias):
     """ResNet.preprocess (ref: models/backbones/residuals.py:210-215), BN folded. -> (B,H/4,W/4,64) NHWC in the
     dtype of `weight` (bf16 or fp16)."""

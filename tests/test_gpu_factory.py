@@ -36,6 +36,15 @@ def test_network_factory_trains_and_snapshots(tmp_path):
     assert torch.equal(nf.model.state_dict()["layer3.0.conv1.weight"], w)
     out = nf.validate([synthetic.make_tiles(2, seed=9).cuda()], None)
     assert out[0].shape == (2, 100) and out[1].dtype == torch.int64
+    # validation with targets: the plugin's evaluation + expression exports (ref: networkFactory.py:181-211,265-271)
+    locs, counts = synthetic.make_objects(2, seed=4)
+    import scd_resnet_b200 as S
+    ys = S.ops.render_targets(locs.cuda(), counts.cuda())
+    ev, raw = nf.validate([synthetic.make_tiles(2, seed=9).cuda()], list(ys))
+    assert set(ev) == {"iouscore", "ortho", "ioucenter", "iouoffsetwo", "iouoffset", "maes", "objs"}
+    assert ev["objs"] == [int(m.sum()) for m in ys[1]] and "heatmap" in raw
+    line = nf.evalExpr([ev, ev])
+    assert line.startswith("[mIoU] ") and "[AP50]" in line and "[avgS]" in line
 
 
 def test_module_eval_decode_and_wrapper():

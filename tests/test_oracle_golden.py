@@ -164,3 +164,29 @@ def test_slide_geometry_16384():
     # BASELINE config 5: 43 x 43 = 1849 tiles, padded to 16640
     ch, cv, rh, rw, ptb, plr = O.slide_geometry(16384, 16384)
     assert (ch, cv, rh, rw) == (43, 43, 16640, 16640) and ptb == plr == 128
+
+
+def test_evaluation_golden(golden):
+    """Row f2: centerNetEvaluation / IoU / Orthogonity / MAE / AP restated in the oracle vs the reference's own
+    outputs on the seeded case of O.make_eval_case (bit exact: it is element-wise fp32 arithmetic)."""
+    g = golden("evaluation")
+    tg, sc, ys, xs, off, regr = O.make_eval_case(int(g["batch"]), seed=int(g["seed"]))
+    ev = O.centernet_evaluation(tg, sc, ys, xs, off, regr)
+
+    def same(a, b):
+        a = np.asarray(a); b = np.asarray(b)
+        return a.shape == b.shape and np.array_equal(np.nan_to_num(a, nan=-7.0), np.nan_to_num(b, nan=-7.0))
+
+    assert same(ev["iouscore"][0].numpy(), g["iou"]) and same(ev["iouscore"][1].numpy(), g["score"])
+    assert same(ev["ortho"].numpy(), g["ortho"])
+    for k in ("ioucenter", "iouoffsetwo", "iouoffset"):
+        assert same(ev[k].numpy(), g[k]), k
+    for a, k in zip(ev["maes"], ("mae_maj", "mae_min", "mae_rad")):
+        assert same(a.numpy(), g[k]), k
+    assert ev["objs"] == g["objs"].tolist()
+    assert len(g["iou"]) > 50 and len(g["ortho"]) > 50          # the case is not degenerate
+    obj_num = max(sum(ev["objs"]), len(ev["iouscore"][0]))
+    for thr in (30, 50, 70, 90):
+        plots = O.average_precision_plots(ev["iouscore"][0], ev["iouscore"][1], obj_num, thr / 100)
+        np.testing.assert_allclose(plots.numpy(), g["plots%d" % thr], rtol=0, atol=1e-15)
+        assert abs(O.average_precision_all(plots) - float(g["ap%d" % thr])) < 1e-15
