@@ -140,6 +140,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="tiles per GPU per step (config[1] = 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--slide", type=int, default=16384, help="edge of the synthetic whole-slide image (configs[4]); 0 = skip")
+    ap.add_argument("--hbm-kernels", type=int, default=2048, help="tiles for the decode / loss / render roofline leg; 0 = skip")
     ap.add_argument("--train-steps", type=int, default=10, help="timed training steps (configs[2]/[3]); 0 = skip")
     ap.add_argument("--train-batch", type=int, default=32, help="samples per GPU per training step (exp.json)")
     args = ap.parse_args()
@@ -260,6 +261,45 @@ def main():
                       "timing": "host wall clock around analyse_slide (upload, tiling, inference, decode, gather, merge), max over ranks"}
         del gray, planes
 
+    # ---- the HBM-bound kernels of the path at a size where a roofline fraction means something (2048 tiles /
+    # samples; at the batch sizes of configs[1..3] they move 4-8 MB and are launch bound).  L2 flushed between
+    # launches; algorithmic bytes per unit from SURVEY.md 8d. --------------------------------------------
+    hbm_kernels = None
+    if rank == 0 and args.hbm_kernels > 0:
+        N = args.hbm_kernels
+        peaks_ = measured_peaks()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+        def timeit(fn, iters=15):
+            for _ in range(3):
+                fn()
+            ts = []
+            for _ in range(iters):
+                flush.zero_()
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b_.record(); torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b_))
+            return statistics.median(ts)
+
+        hh = torch.randn(N, 1, 128, 128, device=dev, generator=g) * 1.5 - 2
+        rr = torch.randn(N, 4, 128, 128, device=dev, generator=g)
+        oo = torch.randn(N, 2, 128, 128, device=dev, generator=g)
+        ll, cc = synthetic.make_objects(N, seed=1)
+        ll, cc = ll.to(dev), cc.to(dev)
+        gt = S.ops.render_targets(ll, cc, with_npos=True)
+        res = {}
+        for name, unit_bytes, fn in (
+                ("decode", 73136, lambda: S.ops.decode_topk(hh, rr, oo, K=100)),
+                ("loss_fwd_bwd", 3 * 65536 + 30 * 6 * 4 * 2, lambda: S.ops.centernet_loss_sparse(hh, rr, oo, *gt[:4], npos=gt[4])),
+                ("render_targets", 65536 + 960, lambda: S.ops.render_targets(ll, cc, with_npos=True))):
+            t_ms = timeit(fn)
+            gbs = unit_bytes * N / t_ms / 1e6
+            res[name] = {"units": N, "ms": round(t_ms, 4), "alg_bytes_per_unit": unit_bytes, "achieved_gbs": round(gbs, 1),
+                         "frac_of_hbm_peak": round(gbs / peaks_["hbm_gbs"], 4)}
+        hbm_kernels = {"peak_gbs": peaks_["hbm_gbs"], "peak_source": peaks_["source"], "l2": "256 MB flush before every launch",
+                       "timing": "CUDA events around the public op (all its launches and memsets)", **res}
+        del hh, rr, oo, gt, flush
+
     # ---- training step (configs[2] / [3]): render targets + forward + loss + backward + Adam ---------------
     train_ms = None
     if args.train_steps > 0:
@@ -315,7 +355,8 @@ def main():
             "gpu_launches": 17 * K,
             "roofline": {"kernel": "igemm_kernel<384, EPI_HEADS> (fused heads)", "bound": "tensor",
                          "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                         "frac": ach / peaks["bf16_tflops_sustained"],
+                         "traffic": 569620992 * B // 64,    # dram read + write per launch, ncu --set full (profiles/ncu_full_r01_b.json)
                          "peak_source": peaks["source"] + " sustained bf16 (kernel timed inside a long step)",
                          "ms_per_launch": heads_ms},
             "step_tflops": FLOPS_PER_TILE * B / (ms / K * 1e-3) / 1e12,
@@ -326,6 +367,8 @@ def main():
         }
         if slide_info is not None:
             line["slide"] = slide_info
+        if hbm_kernels is not None:
+            line["hbm_kernels"] = hbm_kernels
         if train_ms is not None:
             sps = world * args.train_batch * args.train_steps / (train_ms * 1e-3)
             line["train"] = {"metric": "training samples/sec, centerOffsetRes10, batch 32 per GPU (exp.json)",
