@@ -183,6 +183,232 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Persistent, warp-specialised version of the same computation (the one scd_stem_fwd launches).
+// stem_tc_kernel above runs one 8x8 pool tile per CTA as a chain of phases (stage patch -> im2col -> MMA ->
+// epilogue -> pool) separated by block barriers: 16 k CTAs of ~7 us each, tensor pipe 6 % busy, issue slots 18 %
+// (ncu, profiles/ncu_full_r01_b.json).  Here one CTA per SM walks its tiles with three roles running
+// concurrently on different tiles:
+//   warps 0-3  loaders   global patch (prefetched one tile ahead in registers) -> s2d patch in smem -> im2col A tile
+//   warp  4    MMA       12 x tcgen05.mma per tile into one of two TMEM accumulator stages
+//   warps 5-8  epilogue  TMEM -> +bias, ReLU -> 16-bit conv tile (over the consumed A tile) -> 3x3 s2 max pool -> HBM
+// Two CTAs per SM, each with two A stages (48 KB each) and one TMEM accumulator stage (released as soon as the
+// epilogue has read it), mbarriers between the roles, weights loaded once per CTA.
+constexpr int SP_THREADS = 288;
+constexpr int SP_STAGES = 2;                                                // 2 CTAs per SM: 2 x (96 KB A + 8 KB B + patches)
+constexpr int SP_A_BYTES = ST_MT * 16384;                                   // 48 KB
+constexpr int SP_PATCH_BYTES = ST_PS * ST_PS * 8 + 64;
+constexpr int SP_OFF_B = SP_STAGES * SP_A_BYTES;
+constexpr int SP_OFF_PATCH = SP_OFF_B + 8192;
+constexpr int SP_OFF_BAR = (SP_OFF_PATCH + SP_STAGES * SP_PATCH_BYTES + 63) & ~63;
+constexpr int SP_SMEM = SP_OFF_BAR + 128 + 256 + 1024;       // barriers (128 B) | bias (256 B) | align slack
+constexpr int SP_LD_ITERS = (2 * ST_PS * ST_PS + 127) / 128;                // 7 float2 loads per loader thread
+
+template <bool F16>
+__global__ void __launch_bounds__(SP_THREADS, 2)
+stem_pipe_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ x,
+                 const float* __restrict__ bias, int batch, int height, int width, __nv_bfloat16* __restrict__ y)
+{
+    using A16 = tc::Act<F16>;
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t sbase = (tc::smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* sgen = smem_dyn + (sbase - tc::smem_u32(smem_dyn));
+    const uint32_t bar0 = sbase + SP_OFF_BAR;
+    auto a_full = [&](int s) { return bar0 + 8u * s; };                      // loaders -> MMA        (128 arrivals)
+    auto a_free = [&](int s) { return bar0 + 8u * (3 + s); };                // epilogue -> loaders   (128 arrivals)
+    auto mma_done = [&](int s) { return bar0 + 8u * (6 + s); };              // MMA -> epilogue       (tcgen05.commit)
+    const uint32_t t_free = bar0 + 8u * 9;                                   // epilogue -> MMA       (128 arrivals)
+    const uint32_t bar_w = bar0 + 8u * 11, tmem_slot = bar0 + 8u * 12;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    const int hp = height / 4, wp = width / 4, hc = height / 2, wc = width / 2;
+    const int tiles_x = wp / ST_P, tiles_img = tiles_x * (hp / ST_P);
+    const int total = batch * tiles_img;
+
+    if (tid == 0) {
+        for (int s = 0; s < SP_STAGES; ++s) { tc::mbar_init(a_full(s), 128); tc::mbar_init(a_free(s), 128); tc::mbar_init(mma_done(s), 1); }
+        tc::mbar_init(t_free, 128);
+        tc::mbar_init(bar_w, 1);
+        tc::fence_barrier_init();
+        tc::mbar_arrive_expect_tx(bar_w, 8192);
+        tc::tma_load_2d(&tmW, bar_w, sbase + SP_OFF_B, 0, 0);
+    }
+    if (warp == 4) tc::tmem_alloc<256>(tmem_slot);
+    float* bias_s = reinterpret_cast<float*>(sgen + SP_OFF_BAR + 128);      // 64 floats behind the barriers
+    if (tid < ST_CO) bias_s[tid] = bias[tid];
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<const uint32_t*>(sgen + SP_OFF_BAR + 8 * 12);
+
+    if (warp < 4) {
+        // ===================== loaders =====================
+        float2 pre[SP_LD_ITERS];
+        auto fetch = [&](int t) {                        // the tile's (iy, X) pixel pairs -> registers
+            const int b = t / tiles_img, r = t % tiles_img;
+            const int py0 = (r / tiles_x) * ST_P, px0 = (r % tiles_x) * ST_P;
+            const int Y0 = 2 * py0 - 3, X0 = 2 * px0 - 3;          // first s2d row / col (iy = 2Y + py)
+            const float* xb = x + (size_t)b * height * width;
+#pragma unroll
+            for (int j = 0; j < SP_LD_ITERS; ++j) {
+                const int i = tid + j * 128;
+                float2 v = make_float2(0.f, 0.f);                   // conv zero padding
+                if (i < 2 * ST_PS * ST_PS) {
+                    const int X = i % ST_PS, ry = i / ST_PS;
+                    const int iy = 2 * Y0 + ry, ix = 2 * (X0 + X);
+                    if (iy >= 0 && iy < height && ix >= 0 && ix < width)
+                        v = __ldg(reinterpret_cast<const float2*>(xb + (size_t)iy * width + ix));
+                }
+                pre[j] = v;
+            }
+        };
+        // im2col geometry is the same for every tile: chunk c = tid + 128 i copies 16 B from patch offset src to
+        // A offset dst (k = (dy*4 + dx)*4 + py*2 + px, 128 B rows, 128-byte swizzle); packed (dst << 12) | src
+        uint32_t geo[ST_MT * 128 * 8 / 128];
+#pragma unroll
+        for (int i = 0; i < ST_MT * 128 * 8 / 128; ++i) {
+            const int c = tid + 128 * i;
+            const int j = c & 7, row = c >> 3;
+            const int pos = row < ST_NPOS ? row : ST_NPOS - 1;      // padded rows: any in-bounds source
+            const int r = pos / ST_C, cc = pos % ST_C;
+            const int dy = j >> 1, dx0 = (j & 1) * 2;
+            geo[i] = ((uint32_t)(row * 128 + ((j ^ (row & 7)) << 4)) << 12) | (uint32_t)(((r + dy) * ST_PS + cc + dx0) * 8);
+        }
+        int t = blockIdx.x;
+        if (t < total) fetch(t);
+        uint32_t it = 0;
+        for (; t < total; t += gridDim.x, ++it) {
+            const int s = it % SP_STAGES;
+            const uint32_t par = (it / SP_STAGES) & 1u;
+            tc::mbar_wait(a_free(s), par ^ 1u);                     // the epilogue has finished with A[s] / patch[s]
+            uint32_t* patch = reinterpret_cast<uint32_t*>(sgen + SP_OFF_PATCH + s * SP_PATCH_BYTES);
+#pragma unroll
+            for (int j = 0; j < SP_LD_ITERS; ++j) {
+                const int i = tid + j * 128;
+                if (i < 2 * ST_PS * ST_PS) {
+                    const int X = i % ST_PS, ry = i / ST_PS;
+                    patch[((ry >> 1) * ST_PS + X) * 2 + (ry & 1)] = A16::pack(pre[j].x, pre[j].y);
+                }
+            }
+            if (tid < 16) patch[ST_PS * ST_PS * 2 + tid] = 0u;     // slack read by the last chunk
+            if (t + (int)gridDim.x < total) fetch(t + gridDim.x);  // next tile's loads fly during the im2col below
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const unsigned char* pb = reinterpret_cast<const unsigned char*>(patch);
+            unsigned char* A = sgen + s * SP_A_BYTES;
+#pragma unroll
+            for (int i = 0; i < ST_MT * 128 * 8 / 128; ++i) {
+                const unsigned char* src = pb + (geo[i] & 0xFFFu);
+                const uint2 lo = *reinterpret_cast<const uint2*>(src);
+                const uint2 hi = *reinterpret_cast<const uint2*>(src + 8);
+                *reinterpret_cast<uint4*>(A + (geo[i] >> 12)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+            }
+            tc::fence_proxy_async();                                // generic-proxy writes -> visible to tcgen05.mma
+            tc::mbar_arrive(a_full(s));
+        }
+    } else if (warp == 4) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            tc::mbar_wait(bar_w, 0);
+            constexpr uint32_t idesc = tc::umma_idesc_16(128, ST_CO, A16::kFmt);
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+                const int s = it % SP_STAGES;
+                tc::mbar_wait(t_free, (it & 1u) ^ 1u);              // the accumulators of the previous tile have been read
+                tc::mbar_wait(a_full(s), (it / SP_STAGES) & 1u);
+                tc::tc_fence_after();
+                const uint32_t a0 = sbase + s * SP_A_BYTES;
+#pragma unroll
+                for (int m = 0; m < ST_MT; ++m)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc::umma_bf16(tmem_base + m * ST_CO, tc::umma_desc_sw128(a0 + m * 16384 + k * 32),
+                                      tc::umma_desc_sw128(sbase + SP_OFF_B + k * 32), idesc, k ? 1u : 0u);
+                tc::umma_commit(mma_done(s));
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue + pool (warps 5-8 = TMEM lane quarters 1, 2, 3, 0) =====================
+        const int q = warp & 3, et = tid - 160;                     // et: 0..127
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+            const int s = it % SP_STAGES;
+            const int b = t / tiles_img, r = t % tiles_img;
+            const int py0 = (r / tiles_x) * ST_P, px0 = (r % tiles_x) * ST_P;
+            const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;        // first conv row / col under the pool tile
+            tc::mbar_wait(mma_done(s), (it / SP_STAGES) & 1u);      // the 12 MMAs retired: A[s] is dead, TMEM is full
+            tc::tc_fence_after();
+            unsigned char* C = sgen + s * SP_A_BYTES;               // conv tile, same swizzled 128 B rows
+#pragma unroll 1
+            for (int m = 0; m < ST_MT; ++m) {
+                const int row = m * 128 + q * 32 + lane;
+                uint32_t acc[64];
+                const uint32_t taddr = tmem_base + m * ST_CO + ((uint32_t)(q * 32) << 16);
+                tc::tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
+                tc::tmem_ld32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&acc[32]));
+                tc::tmem_ld_wait();
+                if (row < ST_NPOS) {
+                    const int cy = cy0 + row / ST_C, cx = cx0 + row % ST_C;
+                    // conv positions outside the map are max-pool padding; post-ReLU values are >= 0 so 0 == -inf
+                    const bool valid = cy >= 0 && cy < hc && cx >= 0 && cx < wc;
+                    unsigned char* dst = C + row * 128;
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch) {
+                        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                        if (valid) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch * 8);
+                            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch * 8 + 4);
+                            o.x = A16::pack(fmaxf(__uint_as_float(acc[ch * 8 + 0]) + b0.x, 0.f), fmaxf(__uint_as_float(acc[ch * 8 + 1]) + b0.y, 0.f));
+                            o.y = A16::pack(fmaxf(__uint_as_float(acc[ch * 8 + 2]) + b0.z, 0.f), fmaxf(__uint_as_float(acc[ch * 8 + 3]) + b0.w, 0.f));
+                            o.z = A16::pack(fmaxf(__uint_as_float(acc[ch * 8 + 4]) + b1.x, 0.f), fmaxf(__uint_as_float(acc[ch * 8 + 5]) + b1.y, 0.f));
+                            o.w = A16::pack(fmaxf(__uint_as_float(acc[ch * 8 + 6]) + b1.z, 0.f), fmaxf(__uint_as_float(acc[ch * 8 + 7]) + b1.w, 0.f));
+                        }
+                        *reinterpret_cast<uint4*>(dst + ((ch ^ (row & 7)) << 4)) = o;
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            tc::mbar_arrive(t_free);                                // the accumulators can be overwritten
+            asm volatile("bar.sync 2, 128;" ::: "memory");          // conv tile complete
+            // 3x3 s2 max pool, NHWC store: item = (pool pixel, 16-channel quarter); 256 items, 2 per thread
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int item = et + h * 128;
+                const int quarter = item & 3, pos = item >> 2;
+                const int pyl = pos / ST_P, pxl = pos % ST_P;
+                uint32_t mx[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) mx[c] = 0u;             // +0.0 in either format
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const int row = (2 * pyl + dy) * ST_C + 2 * pxl + dx;
+                        const unsigned char* src = C + row * 128;
+#pragma unroll
+                        for (int hch = 0; hch < 2; ++hch) {
+                            const int ch = quarter * 2 + hch;
+                            const uint4 u = *reinterpret_cast<const uint4*>(src + ((ch ^ (row & 7)) << 4));
+                            const uint32_t h2[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) mx[hch * 4 + c] = A16::max2(mx[hch * 4 + c], h2[c]);
+                        }
+                    }
+                uint4* dst = reinterpret_cast<uint4*>(y + (((size_t)b * hp + py0 + pyl) * wp + px0 + pxl) * ST_CO + quarter * 16);
+                dst[0] = make_uint4(mx[0], mx[1], mx[2], mx[3]);
+                dst[1] = make_uint4(mx[4], mx[5], mx[6], mx[7]);
+            }
+            tc::mbar_arrive(a_free(s));                             // A[s] / patch[s] may be refilled
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc<256>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Training variant: raw conv output z0 (B, H/2, W/2, 64) bf16 NHWC (BatchNorm needs batch statistics
 // before the ReLU / pool), plus the im2col operand itself, col0 (B, H/2, W/2, 64) bf16, so that the stem's
 // weight gradient is a plain pixel-contraction GEMM (wgrad.cu kind 4) with no second im2col pass.
@@ -325,13 +551,13 @@ static int stem_fwd_impl(const float* x, const void* weight, const float* bias, 
     if (rc) return rc;
     static bool attr_done = false;
     if (!attr_done) {
-        SCD_CUDA_CHECK(cudaFuncSetAttribute(stem_tc_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+        SCD_CUDA_CHECK(cudaFuncSetAttribute(stem_pipe_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
         attr_done = true;
     }
-    dim3 grid((height / 4 / ST_P) * (width / 4 / ST_P), batch);
-    stem_tc_kernel<F16><<<grid, ST_THREADS, ST_SMEM, (cudaStream_t)stream>>>(
-        tmW, x, bias, height, width, reinterpret_cast<__nv_bfloat16*>(y));
-    SCD_LAUNCH_CHECK("stem_tc_kernel");
+    const int total = (height / 4 / ST_P) * (width / 4 / ST_P) * batch;
+    stem_pipe_kernel<F16><<<total < 2 * kNumSMs ? total : 2 * kNumSMs, SP_THREADS, SP_SMEM, (cudaStream_t)stream>>>(
+        tmW, x, bias, batch, height, width, reinterpret_cast<__nv_bfloat16*>(y));
+    SCD_LAUNCH_CHECK("stem_pipe_kernel");
     return SCD_OK;
 }
 
