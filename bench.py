@@ -310,7 +310,8 @@ def main():
         tmodel = CenterNetResidual(10)
         tmodel.load_state_dict(synthetic.make_state_dict(tmodel, 1234))
         tmodel.to(dev).train()
-        eng = TrainEngine(tmodel, process_group=dist.group.WORLD if world > 1 else None)
+        eng = TrainEngine(tmodel, process_group=dist.group.WORLD if world > 1 else None,
+                          peer_stats=os.environ.get("SCD_PEER_STATS", "1") != "0")
         txs = [torch.randn(TB, 1, 512, 512, device=dev, generator=g) for _ in range(3)]
         tlocs = [tuple(t.to(dev) for t in synthetic.make_objects(TB, seed=50 + 3 * rank + i)) for i in range(3)]
 
@@ -375,7 +376,9 @@ def main():
                              "value": sps, "unit": "samples/s", "ms_per_step": train_ms / args.train_steps,
                              "steps": args.train_steps, "batch_per_gpu": args.train_batch,
                              "step": "render targets + fwd (batch-stat BN) + focal/L1 loss + bwd + Adam",
-                             "grad_sync": "NCCL all-reduce of the flat fp32 gradient + BN statistics" if world > 1 else "none",
+                             "grad_sync": ("NCCL all-reduce of the flat fp32 gradient; BN statistics: "
+                                           + ("one-shot NVLink peer-memory all-reduce kernel" if eng.peer is not None
+                                              else "NCCL all-reduce (%s)" % eng.peer_reason)) if world > 1 else "none",
                              "tflops": 147.5e9 * args.train_batch / (train_ms / args.train_steps * 1e-3) / 1e12,
                              "last_loss": train_loss}
         if world == 1 and not args.no_cpu_baseline:

@@ -291,6 +291,16 @@ int scd_heads_wgrad_sparse(const void* x, const float* dh_objects, const uint8_t
 int scd_heads_dgrad_sparse(const float* dh_objects, const uint8_t* mask, const int64_t* idx, const void* w3,
                            int batch, int height, int width, int max_tags, void* dx, void* stream);
 
+/* One-shot all-reduce (sum) of a small fp64 vector over NVLink peer memory: the SyncBatchNorm statistics exchange
+ * (models/networkFactory.py:133) without a NCCL launch per BatchNorm.  Every rank owns a symmetric buffer of
+ * scd_peer_allreduce_buffer_bytes(world, cap) bytes, zeroed once; d_peer_buffers is a DEVICE array of `world`
+ * pointers to those buffers (peer-mapped; index = rank).  All ranks call with the same n <= cap and the same
+ * seq = 1, 2, 3, ...; local[0..n) is replaced by the sum over ranks, added in rank order (bit-identical
+ * everywhere).  A peer that never arrives traps the kernel after ~4 s instead of hanging the GPU. */
+size_t scd_peer_allreduce_buffer_bytes(int world, int cap);
+int scd_peer_allreduce_f64(double* local, int n, void* const* d_peer_buffers, int rank, int world, int cap,
+                           unsigned int seq, void* stream);
+
 /* Fused Adam (torch.optim.Adam defaults, networkFactory.py:80-82) over the flat fp32 parameter buffer.
  * The gradient of parameter i is grad_scale * grads[gmap ? gmap[i] : i] (the wgrad kernels write their own
  * layout).  scd_gather_cast_bf16 refreshes the bf16 GEMM-operand copies: dst[i] = bf16(src[idx[i]]), 0 if

@@ -52,6 +52,8 @@ PROTOTYPES = {
     "scd_heads_bwd_sparse": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_void_p] * 5 + [c_void_p]),
     "scd_heads_wgrad_sparse": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p, c_void_p]),
     "scd_heads_dgrad_sparse": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p, c_void_p]),
+    "scd_peer_allreduce_buffer_bytes": (c_size_t, [c_int, c_int]),
+    "scd_peer_allreduce_f64": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, ctypes.c_uint, c_void_p]),
     "scd_adam_step": (c_int, [c_void_p] * 5 + [c_size_t, c_int] + [c_float] * 5 + [c_void_p]),
     "scd_gather_cast_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "scd_scale_inplace": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),

@@ -57,3 +57,65 @@ def broadcast_module(module, src=0, group=None):
         return
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src, group=group)
+
+
+class PeerAllReduce:
+    """One-shot fp64 all-reduce over NVLink peer memory for the SyncBatchNorm statistics (csrc/peer.cu).
+
+    Built on torch's symmetric-memory allocator (CUDA IPC / fabric handles exchanged through the process group);
+    the reduction itself is this repository's kernel.  Construction is collective.  `available` is False when the
+    platform cannot map peer memory (then the caller keeps using NCCL all-reduces)."""
+
+    def __init__(self, group, device, cap=1024):
+        import ctypes
+        from ._lib import lib, check
+        self._lib, self._check, self._ctypes = lib, check, ctypes
+        self.group, self.device, self.cap = group, torch.device(device), cap
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.seq = 0
+        self.available = False
+        self.reason = ""
+        try:
+            import torch.distributed._symmetric_memory as symm
+            nbytes = lib.scd_peer_allreduce_buffer_bytes(self.world, cap)
+            with torch.cuda.device(self.device):
+                self.buf = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+                self.buf.zero_()
+                self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+                ptrs = [int(p) for p in self.handle.buffer_ptrs]
+                self.peers = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+                torch.cuda.synchronize(self.device)
+            dist.barrier(group)                            # every buffer is zeroed before anybody writes into it
+            # self-test against NCCL on a vector that differs per rank
+            probe = torch.arange(cap, dtype=torch.float64, device=self.device) * (self.rank + 1) + 0.25 * self.rank
+            ref = probe.clone()
+            dist.all_reduce(ref, group=group)
+            self(probe)
+            torch.cuda.synchronize(self.device)
+            ok = torch.tensor([1 if torch.equal(probe, ref) else 0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) != 1:
+                raise RuntimeError("peer all-reduce self-test disagrees with NCCL")
+            self.available = True
+        except Exception as e:                             # no peer access, no symmetric memory, old driver, ...
+            self.reason = "%s: %s" % (type(e).__name__, e)
+            flag = torch.zeros(1, device=self.device)
+            try:
+                dist.all_reduce(flag, group=group)         # keep the ranks in step if only some of them failed
+            except Exception:
+                pass
+            self.available = False
+
+    def __call__(self, vec):
+        """In-place sum of a contiguous fp64 CUDA vector (<= cap elements) over the ranks."""
+        if vec.dtype != torch.float64 or not vec.is_contiguous() or vec.numel() > self.cap:
+            raise ValueError("PeerAllReduce takes a contiguous float64 vector of at most %d elements" % self.cap)
+        self.seq += 1
+        c = self._ctypes
+        with torch.cuda.device(self.device):
+            self._check(self._lib.scd_peer_allreduce_f64(c.c_void_p(vec.data_ptr()), vec.numel(),
+                                                         c.c_void_p(self.peers.data_ptr()), self.rank, self.world, self.cap,
+                                                         self.seq & 0xFFFFFFFF or 1,
+                                                         c.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                        "scd_peer_allreduce_f64")
+        return vec

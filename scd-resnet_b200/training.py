@@ -26,7 +26,8 @@ _HEADS = (("heatmap", 0, 1), ("regr", 1, 4), ("offset", 5, 2))
 
 
 class TrainEngine:
-    def __init__(self, module, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, regr_w=0.1, off_w=0.1, process_group=None):
+    def __init__(self, module, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, regr_w=0.1, off_w=0.1, process_group=None,
+                 peer_stats=True):
         self.module = module
         self.lr, self.betas, self.eps = lr, betas, eps
         self.regr_w, self.off_w = regr_w, off_w
@@ -59,6 +60,16 @@ class TrainEngine:
         self._build_layouts(named)
         self.zero_bias = torch.zeros(512, dtype=torch.float32, device=dev)
         self.refresh_operands()
+        # SyncBatchNorm statistics: 2 x C fp64 sums per BatchNorm, forward and backward.  Over NVLink peer memory when
+        # the platform allows it (falls back to NCCL all-reduces otherwise; `peer_reason` says why).
+        self.peer, self.peer_reason = None, ""
+        if self.world > 1 and peer_stats:
+            from .dist import PeerAllReduce
+            pa = PeerAllReduce(process_group, dev, cap=1024)
+            if pa.available:
+                self.peer = pa
+            else:
+                self.peer_reason = pa.reason
 
     # ------------------------------------------------------------------ layouts
     def _build_layouts(self, named):
@@ -175,7 +186,10 @@ class TrainEngine:
     def _allreduce_stats(self, sums, pixels):
         if self.world == 1:
             return float(pixels) if pixels is not None else None
-        torch.distributed.all_reduce(sums, group=self.group)
+        if self.peer is not None:
+            self.peer(sums)                                # one-shot NVLink peer-memory reduction (csrc/peer.cu)
+        else:
+            torch.distributed.all_reduce(sums, group=self.group)
         return float(pixels) * self.world if pixels is not None else None
 
     # ------------------------------------------------------------------ forward + backward
