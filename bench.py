@@ -296,6 +296,20 @@ def main():
             gbs = unit_bytes * N / t_ms / 1e6
             res[name] = {"units": N, "ms": round(t_ms, 4), "alg_bytes_per_unit": unit_bytes, "achieved_gbs": round(gbs, 1),
                          "frac_of_hbm_peak": round(gbs / peaks_["hbm_gbs"], 4)}
+        # data path (row f3): 256 samples of a 512-tile resident dataset; 1 MB tile + 1 MB noise read, 1 MB written
+        NA = 256
+        ds = torch.randint(0, 256, (512, 512, 512), device=dev, generator=g).float()
+        dl, dc = synthetic.make_objects(512, seed=2)
+        dl, dc = dl.to(dev), dc.to(dev)
+        ai = torch.randperm(512, device=dev, generator=g)[:NA]
+        af = torch.rand(NA, 2, device=dev, generator=g) > 0.5
+        aj = torch.randn(NA, device=dev, generator=g)
+        an = torch.randn(NA, 512, 512, device=dev, generator=g)
+        t_ms = timeit(lambda: S.ops.augment_batch(ds, dl, dc, ai, af, aj, an))
+        gbs = 3 * (1 << 20) * NA / t_ms / 1e6
+        res["augment_batch"] = {"units": NA, "ms": round(t_ms, 4), "alg_bytes_per_unit": 3 << 20, "achieved_gbs": round(gbs, 1),
+                                "frac_of_hbm_peak": round(gbs / peaks_["hbm_gbs"], 4)}
+        del ds, an
         hbm_kernels = {"peak_gbs": peaks_["hbm_gbs"], "peak_source": peaks_["source"], "l2": "256 MB flush before every launch",
                        "timing": "CUDA events around the public op (all its launches and memsets)", **res}
         del hh, rr, oo, gt, flush

@@ -312,6 +312,22 @@ int scd_gather_cast_bf16(const float* src, const int* idx, size_t n, void* dst, 
 int scd_scale_inplace(float* x, size_t n, const float* d_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Training data path on the device.  Replaces SCD.argumentation
+ * (datasets/scds/scdx16p100.py:418-440) = flips with their object-coordinate fix-ups + normalize
+ * (datasets/argumentations.py:39-44) + varianceJitter (:62-67) + gaussianNoise (:54-60), and the gather of
+ * SCD.__getitem__ (:304-327), for a whole batch.
+ *
+ * Resident dataset: samples (N,512,512) f32, locs (N,30,8) f32, counts (N) i32.  Batch: index (B) i64 sample
+ * ids (the caller checks 0 <= id < N), flips (B,2) u8 = [flip x, flip y] decisions, jitter (B) f32 and noise
+ * (B,512,512) f32 (nullable) = the N(0,1) draws.  Outputs tiles (B,1,512,512) f32 = ((x - mean)/sqrt(var)) *
+ * (1 + jitter_sv * jitter) + noise * noise_sv, out_locs (B,30,8), out_counts (B): what scd_render_targets takes.
+ * ---------------------------------------------------------------------------------- */
+int scd_augment_batch(const float* samples, const float* locs, const int32_t* counts, int n_samples,
+                      const int64_t* index, const uint8_t* flips, const float* jitter, const float* noise,
+                      int batch, float noise_sv, float jitter_sv,
+                      float* tiles, float* out_locs, int32_t* out_counts, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Detection metrics of the validation loop.  Replaces centerNetEvaluation
  * (models/centerNetOffset.py:253-353) with IoU / IoUConfidence / Orthogonity / MAE
  * (evaluations/detection.py:12-205): all K x L detection / object pairs of every sample in one pass, the

@@ -244,6 +244,38 @@ def main():
         e["ap%d" % int(thr * 100)] = np.float64(averagePrecisionAll(plots))
     e["expression"] = np.array(plugin.expression([ev]))
     np.savez_compressed(os.path.join(OUT, "evaluation.npz"), **e)
+    # ---------------- augmentation: SCD.argumentation replayed with recorded draws ------
+    ds_s, ds_l, ds_c = O.make_dataset(6, seed=3)
+    a = {"seed": np.int64(3), "n": np.int64(6), "rng_seeds": np.arange(100, 106, dtype=np.int64)}
+    flips, jit, tile_sum, tile_abs, tile_sub, out_locs = [], [], [], [], [], []
+    noise_sums, heats = [], []
+    for i in range(6):
+        n_obj = int(ds_c[i])
+        np.random.seed(100 + i)
+        torch.manual_seed(100 + i)
+        tile, heat_i, locs_i = SCD.argumentation(ds_s[i:i + 1].clone(), ds_l[i, :n_obj].clone())
+        locs_i = locs_i.reshape(-1, 8) if n_obj else torch.zeros(0, 8)
+        # replay the draws in the order the reference makes them
+        np.random.seed(100 + i)
+        torch.manual_seed(100 + i)
+        fx, fy = np.random.uniform() > 0.5, np.random.uniform() > 0.5
+        g = torch.randn(1)
+        noise = torch.randn(1, 512, 512)
+        chk, chk_l = O.augment(ds_s[i:i + 1], ds_l[i, :n_obj], fx, fy, g, noise)
+        chk_t = chk_l.clone()
+        chk_t[:, :2] = torch.trunc(chk_t[:, :2])               # the reference truncates the centres in place (:515-516)
+        assert torch.equal(chk, tile) and torch.equal(chk_t, locs_i), "oracle augment != reference"
+        heats.append(heat_i.double().sum().item())
+        flips.append([fx, fy]); jit.append(float(g))
+        tile_sum.append(tile.double().sum().item()); tile_abs.append(tile.double().abs().sum().item())
+        tile_sub.append(tile[0, 0, ::32, ::32].numpy())
+        pad = np.zeros((30, 8), np.float32); pad[:n_obj] = locs_i.numpy()
+        out_locs.append(pad)
+        noise_sums.append(noise.double().sum().item())
+    a.update({"flips": np.array(flips, np.uint8), "jitter": np.array(jit, np.float32), "tile_sum": np.array(tile_sum),
+              "tile_abs": np.array(tile_abs), "tile_sub": np.stack(tile_sub), "out_locs": np.stack(out_locs),
+              "noise_sum": np.array(noise_sums), "heat_sum": np.array(heats)})
+    np.savez_compressed(os.path.join(OUT, "augment.npz"), **a)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -168,6 +168,38 @@ def _act_dtype(weight):
     return weight.dtype
 
 
+def augment_batch(samples, locs, counts, index, flips, jitter, noise=None, noise_sv=0.05, jitter_sv=0.05):
+    """SCD.argumentation for a batch drawn from a device-resident dataset (ref: datasets/scds/scdx16p100.py:418-440).
+
+    samples (N,512,512) f32, locs (N,30,8) f32, counts (N) i32 stay on the device; index (B) i64, flips (B,2) bool /
+    u8, jitter (B) f32, noise (B,512,512) f32 or None are the batch's sample ids and random draws.
+    Returns (tiles (B,1,512,512) f32, out_locs (B,30,8) f32, out_counts (B) i32)."""
+    samples = _req(samples, torch.float32, "samples")
+    locs = _req(locs, torch.float32, "locs")
+    counts = _req(counts, torch.int32, "counts")
+    index = _req(index, torch.int64, "index")
+    if flips.dtype == torch.bool:
+        flips = flips.contiguous().view(torch.uint8)
+    flips = _req(flips, torch.uint8, "flips")
+    jitter = _req(jitter, torch.float32, "jitter")
+    if noise is not None:
+        noise = _req(noise, torch.float32, "noise")
+    n, b = samples.shape[0], index.shape[0]
+    if tuple(samples.shape[1:]) != (512, 512) or tuple(locs.shape) != (n, MAXTAGLEN, 8) or counts.shape[0] != n:
+        raise ScdError("augment_batch: dataset tensors must be (N,512,512), (N,30,8), (N)")
+    if b and (int(index.min()) < 0 or int(index.max()) >= n):
+        raise ScdError("augment_batch: sample index out of range")
+    dev = samples.device
+    tiles = torch.empty(b, 1, 512, 512, dtype=torch.float32, device=dev)
+    out_locs = torch.empty(b, MAXTAGLEN, 8, dtype=torch.float32, device=dev)
+    out_counts = torch.empty(b, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.scd_augment_batch(_ptr(samples), _ptr(locs), _ptr(counts), n, _ptr(index), _ptr(flips), _ptr(jitter),
+                                    _ptr(noise), b, noise_sv, jitter_sv, _ptr(tiles), _ptr(out_locs), _ptr(out_counts),
+                                    _stream()), "scd_augment_batch")
+    return tiles, out_locs, out_counts
+
+
 def centernet_eval(scores, ys, xs, offset, regr, regr6, gt_idx, mask, threshold=0.3):
     """Pair metrics of centerNetEvaluation (ref: models/centerNetOffset.py:253-353) in one native call.
 
