@@ -11,16 +11,19 @@
 //     (maxpool(p) == p, utility.py:87-92) is  sigmoid(m) == sigmoid(x)  with m = max3x3(x).
 //     That holds trivially at logit peaks (x == m); for x < m it needs the two sigmoids to
 //     round to the same float, which is only possible when m - x is tiny or the sigmoid is
-//     saturated.  Pixels are therefore screened with  m - x < thr(x)  (a bound far above the
-//     largest collapsing gap, checked exhaustively over all floats by scd_selftest_decode_math)
-//     and the sigmoid is evaluated only for the screened candidates, compacted 32 at a time
-//     so every lane does useful work;
-//   * selection is a streaming exact top-K: candidates are appended, in ascending flat-index
-//     order, to a 512-entry buffer in shared memory; when it fills, an exact 4 x 8-bit radix
-//     select finds the K-th largest score T, the buffer is compacted (stably) to the K best and
-//     from then on only scores > T are admitted (a later pixel that ties with T loses to the
-//     earlier ones).  A logit-space bound tau_x with sigmoid(x <= tau_x) <= T lets whole rows be
-//     skipped with one vote.  Expected appends for K = 100 on white noise: ~1.3 k of 16 k pixels;
+//     saturated: a screen  m - x < bound(x)  far above the largest collapsing gap (checked
+//     exhaustively over all floats by scd_selftest_decode_math) decides who gets a sigmoid;
+//   * the image is walked in groups of 8 rows staged (with a halo row on either side) in shared memory.  The
+//     only per-pixel work is one compare against a logit bound tau_x (below); the flagged pixels of a group
+//     are listed in flat-index order (one packed warp scan per group) and then processed COMPACTED, 32 per
+//     step with one pixel per lane: 3x3 maximum from the staged rows, screen, sigmoid, admission.  Per-row
+//     collectives and per-pixel NMS arithmetic of the earlier versions are gone: white noise costs ~10 k
+//     warp-instructions per image instead of 25 k;
+//   * selection is a streaming exact top-K: admitted candidates are appended, in ascending flat-index
+//     order, to a 512-entry buffer; when it fills (and after the first groups, to get a bound early) an exact
+//     4 x 8-bit radix select finds the K-th largest score T, the buffer is compacted (stably) to the K best and
+//     from then on only scores > T are admitted (a later pixel that ties with T loses to the earlier ones);
+//     tau_x is a logit with sigmoid(x <= tau_x) <= T;
 //   * the K survivors are bitonic-sorted in registers: (score desc, flat index asc), the
 //     deterministic order of SURVEY 8c; fewer than K positive peaks -> zero scores at the
 //     smallest flat indices.
@@ -37,16 +40,16 @@ int launch_decode_cta(const float* heat, const float* regr, const float* offset,
 constexpr int DEC_HW = 128;
 constexpr int DEC_MAXK = 128;
 constexpr int DEC_BUF = 512;            // survivor buffer entries per image
-constexpr int DEC_Q = 256;              // candidate ring entries (>= 31 pending + 128 of one row)
+constexpr int DEC_G = 8;                // rows per group
 constexpr unsigned FULL = 0xffffffffu;
 
 struct alignas(16) DecWarp {
-    unsigned buf_s[DEC_BUF];            // sigmoid bit patterns of the survivors, ascending flat-index order
-    unsigned short buf_i[DEC_BUF];      // their flat indices
-    float q_x[DEC_Q], q_m[DEC_Q];       // candidate ring: logit, 3x3 max logit   (reused as 128 x u64 sort keys)
-    unsigned short q_i[DEC_Q];          //                 flat index
+    unsigned buf_s[DEC_BUF];            // sigmoid bit patterns of the survivors
+    unsigned short buf_i[DEC_BUF];      // their flat indices (the buffer is in no particular order)
+    float tile[DEC_G + 2][DEC_HW];      // the group's rows with one halo row above and below   (later: 128 x u64 sort keys)
+    unsigned short list[DEC_G * DEC_HW];// flagged pixels of the group: (row in group << 7) | column
     unsigned hist[256];
-    unsigned head, nbuf, tau;           // warp-uniform state: ring head, buffer fill, admission threshold (bits)
+    unsigned tau, tau_i;                // K-th best entry so far: score bits and flat index (set by dec_prune)
     float tau_x;                        // logits <= tau_x cannot beat tau
 };
 
@@ -79,62 +82,102 @@ __device__ __forceinline__ float4 hmax3(float4 p, int lane) {
     return m;
 }
 
-// Exact K-th largest of buf_s[0, nbuf) (nbuf > K) by radix select, then stable compaction to the K best:
-// scores > T, and the first need_eq (smallest flat index) of those == T.  Returns the new fill (= K).
+// One 8-bit radix-select pass over the buffer entries selected by `pred`: finds the digit that holds the k_rem-th
+// largest key (descending) and the rank inside it; returns the count of that digit through cnt_out.
+template <typename KeyFn>
+__device__ __forceinline__ void dec_radix_pass(DecWarp& w, unsigned nbuf, int shift, unsigned& k_rem, unsigned& digit_out,
+                                               unsigned& cnt_out, KeyFn key /* (j, &in_set) -> key bits */)
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w.hist[i * 32 + lane] = 0u;
+    __syncwarp();
+    for (unsigned j = lane; j < nbuf; j += 32) {
+        bool in;
+        const unsigned u = key(j, in);
+        if (in) atomicAdd(&w.hist[(u >> shift) & 255u], 1u);
+    }
+    __syncwarp();
+    const uint4 a = *reinterpret_cast<const uint4*>(&w.hist[8 * lane]);       // lane owns digits [8 lane, 8 lane + 8)
+    const uint4 c = *reinterpret_cast<const uint4*>(&w.hist[8 * lane + 4]);
+    const unsigned t = a.x + a.y + a.z + a.w + c.x + c.y + c.z + c.w;
+    unsigned incl = t;                                                         // suffix sum: digits >= 8 lane
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned n = __shfl_down_sync(FULL, incl, o);
+        if (lane + o < 32) incl += n;
+    }
+    const unsigned above = incl - t;
+    const bool mine = above < k_rem && incl >= k_rem;
+    unsigned digit = 0u, newk = 0u, cnt_d = 0u;
+    if (mine) {
+        const unsigned cnt[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+        unsigned acc = above;
+#pragma unroll
+        for (int i = 7; i >= 0; --i) {
+            if (acc < k_rem && acc + cnt[i] >= k_rem) { digit = 8u * lane + i; newk = k_rem - acc; cnt_d = cnt[i]; }
+            acc += cnt[i];
+        }
+    }
+    const int src = __ffs(__ballot_sync(FULL, mine)) - 1;
+    digit_out = __shfl_sync(FULL, digit, src);
+    k_rem = __shfl_sync(FULL, newk, src);
+    cnt_out = __shfl_sync(FULL, cnt_d, src);
+    __syncwarp();
+}
+
+// Exact K best of buf[0, nbuf) (nbuf >= K) under the order (score desc, flat index asc), whatever the order of the
+// buffer: 4 x 8-bit radix select on the score bits gives the K-th score T and how many entries equal to T are
+// needed; only if more entries tie at T than are needed, two more passes select among them on the (inverted) flat
+// index.  The buffer is compacted to the K best; tau = T, tau_i = flat index of the K-th entry (a later candidate
+// with score T is better only if its index is smaller), tau_x = a logit bound for T.  Returns the new fill (= K).
 __device__ __forceinline__ unsigned dec_prune(DecWarp& w, unsigned nbuf, int K)
 {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    unsigned prefix = 0u, known = 0u, k_rem = (unsigned)K;
+    unsigned prefix = 0u, known = 0u, k_rem = (unsigned)K, cnt_eq = 0u;
 #pragma unroll 1
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 24 - 8 * pass;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) w.hist[i * 32 + lane] = 0u;
-        __syncwarp();
-        for (unsigned j = lane; j < nbuf; j += 32) {
-            const unsigned u = w.buf_s[j];
-            if ((u & known) == prefix) atomicAdd(&w.hist[(u >> shift) & 255u], 1u);
-        }
-        __syncwarp();
-        const uint4 a = *reinterpret_cast<const uint4*>(&w.hist[8 * lane]);       // lane owns digits [8 lane, 8 lane + 8)
-        const uint4 c = *reinterpret_cast<const uint4*>(&w.hist[8 * lane + 4]);
-        const unsigned t = a.x + a.y + a.z + a.w + c.x + c.y + c.z + c.w;
-        unsigned incl = t;                                                         // suffix sum: digits >= 8 lane
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned n = __shfl_down_sync(FULL, incl, o);
-            if (lane + o < 32) incl += n;
-        }
-        const unsigned above = incl - t;
-        const bool mine = above < k_rem && incl >= k_rem;
-        unsigned digit = 0u, newk = 0u;
-        if (mine) {
-            const unsigned cnt[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
-            unsigned acc = above;
-#pragma unroll
-            for (int i = 7; i >= 0; --i) {
-                if (acc < k_rem && acc + cnt[i] >= k_rem) { digit = 8u * lane + i; newk = k_rem - acc; }
-                acc += cnt[i];
-            }
-        }
-        const int src = __ffs(__ballot_sync(FULL, mine)) - 1;
-        digit = __shfl_sync(FULL, digit, src);
-        newk = __shfl_sync(FULL, newk, src);
+        unsigned digit;
+        dec_radix_pass(w, nbuf, shift, k_rem, digit, cnt_eq,
+                       [&](unsigned j, bool& in) { const unsigned u = w.buf_s[j]; in = (u & known) == prefix; return u; });
         prefix |= digit << shift;
         known |= 0xFFu << shift;
-        k_rem = newk;
     }
-    const unsigned T = prefix, need_eq = k_rem;
-    unsigned out = 0u, eq_seen = 0u;
+    const unsigned T = prefix, need_eq = k_rem;          // cnt_eq entries have score T, the need_eq smallest indices stay
+    unsigned I_T;                                        // flat index of the K-th best entry
+    if (cnt_eq > need_eq) {
+        // inverted index as a 16-bit key (descending key = ascending index), 2 passes among the tied entries
+        unsigned ipre = 0u, iknown = 0u, ik = need_eq, dummy;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            const int shift = 8 - 8 * pass;
+            unsigned digit;
+            dec_radix_pass(w, nbuf, shift, ik, digit, dummy, [&](unsigned j, bool& in) {
+                const unsigned v = 0xFFFFu - w.buf_i[j];
+                in = w.buf_s[j] == T && (v & iknown) == ipre;
+                return v;
+            });
+            ipre |= digit << shift;
+            iknown |= 0xFFu << shift;
+        }
+        I_T = 0xFFFFu - ipre;
+    } else {                                             // every tied entry stays: the K-th is the one with the largest index
+        unsigned mx = 0u;
+        for (unsigned j = lane; j < nbuf; j += 32)
+            if (w.buf_s[j] == T) mx = max(mx, (unsigned)w.buf_i[j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+        I_T = mx;
+    }
+    unsigned out = 0u;
     for (unsigned j0 = 0; j0 < nbuf; j0 += 32) {
         const unsigned j = j0 + lane;
         const bool valid = j < nbuf;
         const unsigned u = valid ? w.buf_s[j] : 0u;
         const unsigned short fi = valid ? w.buf_i[j] : (unsigned short)0;
-        const bool eq = valid && u == T;
-        const unsigned beq = __ballot_sync(FULL, eq);
-        const bool keep = valid && (u > T || (eq && eq_seen + __popc(beq & lt) < need_eq));
+        const bool keep = valid && (u > T || (u == T && fi <= I_T));
         const unsigned bk = __ballot_sync(FULL, keep);       // also orders this chunk's reads before its writes
         if (keep) {
             const unsigned pos = out + __popc(bk & lt);      // pos <= j: never overwrites an unread entry
@@ -142,52 +185,11 @@ __device__ __forceinline__ unsigned dec_prune(DecWarp& w, unsigned nbuf, int K)
             w.buf_i[pos] = fi;
         }
         out += __popc(bk);
-        eq_seen += __popc(beq);
         __syncwarp();
     }
-    if (lane == 0) { w.tau = T; w.tau_x = logit_bound(T); }
+    if (lane == 0) { w.tau = T; w.tau_i = I_T; w.tau_x = logit_bound(T); }
     __syncwarp();
     return out;
-}
-
-// Evaluates queued candidates 32 at a time (all of them when flush): sigmoid, collapse check, admission
-// against tau, append to the survivor buffer; prunes when the buffer is nearly full.
-__device__ __noinline__ void dec_drain(DecWarp& w, unsigned tail, int K, bool flush)
-{
-    const int lane = threadIdx.x & 31;
-    const unsigned lt = (1u << lane) - 1u;
-    unsigned head = w.head, nbuf = w.nbuf, tau = w.tau;
-    for (;;) {
-        const unsigned avail = tail - head;
-        if (avail == 0u || (avail < 32u && !flush)) break;
-        const unsigned n = avail < 32u ? avail : 32u;
-        bool ok = false;
-        unsigned bits = 0u;
-        unsigned short fi = 0;
-        if ((unsigned)lane < n) {
-            const unsigned e = (head + lane) & (DEC_Q - 1);
-            const float x = w.q_x[e], m = w.q_m[e];
-            fi = w.q_i[e];
-            const float s = sigmoidf_ref(x);
-            bits = __float_as_uint(s);                       // s >= 0: unsigned order == float order
-            ok = bits > tau && (x == m || sigmoidf_ref(m) == s);
-        }
-        const unsigned bal = __ballot_sync(FULL, ok);
-        if (ok) {
-            const unsigned pos = nbuf + __popc(bal & lt);
-            w.buf_s[pos] = bits;
-            w.buf_i[pos] = fi;
-        }
-        nbuf += __popc(bal);
-        head += n;
-        __syncwarp();
-        if (nbuf > DEC_BUF - 32) {
-            nbuf = dec_prune(w, nbuf, K);
-            tau = w.tau;
-        }
-    }
-    if (lane == 0) { w.head = head; w.nbuf = nbuf; }
-    __syncwarp();
 }
 
 template <int WPC>
@@ -204,77 +206,123 @@ decode_kernel(const float* __restrict__ heat, const float* __restrict__ regr,
     const int b = blockIdx.x * WPC + warp;
     if (b >= batch) return;                                  // warps are independent: no block barrier below
     DecWarp& w = sm[warp];
-    if (lane == 0) { w.head = 0u; w.nbuf = 0u; w.tau = 0u; w.tau_x = -CUDART_INF_F; }
-    __syncwarp();
-
-    // ---- stream the heat map: rolling 3-row window on logits, loads 8 rows ahead ----------------
+    const unsigned lt = (1u << lane) - 1u;
     const float4* hp = reinterpret_cast<const float4*>(heat + (size_t)b * DEC_HW * DEC_HW) + lane;
     const float4 ninf = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
-    float4 ring[8];
-    float4 x_cur = ld_stream(hp);
-#pragma unroll
-    for (int j = 1; j <= 8; ++j) ring[j & 7] = ld_stream(hp + j * (DEC_HW / 4));
-    float4 hm_prev = ninf, hm_cur = hmax3(x_cur, lane);
-    unsigned tail = 0u, pending = 0u;
-    float tau_x = -CUDART_INF_F;
+    unsigned nbuf = 0u, tau = 0u, tau_i = 0u;                // K-th best so far (score bits, flat index); none yet:
+    float tau_x = -CUDART_INF_F;                             //   admit every positive score
+    bool have_tau = false;
+    const unsigned prune_at = (unsigned)(2 * K > 96 ? 2 * K : 96);
 
+    // ---- groups of 8 rows: stage them (+ halo rows) in shared memory, flag pixels, process the flagged ones -----
+    float4 nxt[DEC_G + 2];                                   // next group's rows, loaded while this one is processed
+#pragma unroll
+    for (int u = 0; u < DEC_G + 2; ++u) nxt[u] = (u == 0) ? ninf : ld_stream(hp + (u - 1) * (DEC_HW / 4));
 #pragma unroll 1
-    for (int r8 = 0; r8 < DEC_HW; r8 += 8) {
+    for (int r0 = 0; r0 < DEC_HW; r0 += DEC_G) {
+        unsigned mask = 0u;                                  // bit 4 u + c: pixel (r0 + u, 4 lane + c) is flagged
+        __syncwarp();                                        // the previous group's tile / list reads are done
+        if (!have_tau) {
+            // no bound yet (first group or two): flag what passes the 3x3 screen, tested in registers
+            float4 hm_a = hmax3(nxt[0], lane), hm_b = hmax3(nxt[1], lane);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int r = r8 + u;
-            const int slot = (u + 1) & 7;
-            const float4 x_next = ring[slot];
-            if (r + 9 < DEC_HW) ring[slot] = ld_stream(hp + (r + 9) * (DEC_HW / 4));
-            const float4 hm_next = (r + 1 < DEC_HW) ? hmax3(x_next, lane) : ninf;
-            {
-                const float xv[4] = {x_cur.x, x_cur.y, x_cur.z, x_cur.w};
-                const float mv[4] = {fmaxf(fmaxf(hm_prev.x, hm_cur.x), hm_next.x), fmaxf(fmaxf(hm_prev.y, hm_cur.y), hm_next.y),
-                                     fmaxf(fmaxf(hm_prev.z, hm_cur.z), hm_next.z), fmaxf(fmaxf(hm_prev.w, hm_cur.w), hm_next.w)};
-                // branch-free screen: above the running bound, and (saturating, or not separated from the window
-                // max); written with !(>=) so that inf - inf = NaN counts as "not separated"
-                bool cand[4];
-                unsigned bal[4];
+            for (int u = 1; u <= DEC_G; ++u) {
+                const float4 hm_c = hmax3(nxt[u + 1], lane);
+                const float xv[4] = {nxt[u].x, nxt[u].y, nxt[u].z, nxt[u].w};
+                const float mv[4] = {fmaxf(fmaxf(hm_a.x, hm_b.x), hm_c.x), fmaxf(fmaxf(hm_a.y, hm_b.y), hm_c.y),
+                                     fmaxf(fmaxf(hm_a.z, hm_b.z), hm_c.z), fmaxf(fmaxf(hm_a.w, hm_b.w), hm_c.w)};
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    cand[c] = (xv[c] > tau_x) & ((xv[c] > DEC_SAT) | !(mv[c] - xv[c] >= collapse_bound(xv[c])));
-                    bal[c] = __ballot_sync(FULL, cand[c]);
-                }
-                if ((bal[0] | bal[1] | bal[2] | bal[3]) != 0u) {
-                    const unsigned ltm = (1u << lane) - 1u;
-                    // queue order = ascending flat index: lanes first, then the lane's four columns
-                    unsigned pos = tail + __popc(bal[0] & ltm) + __popc(bal[1] & ltm) + __popc(bal[2] & ltm) + __popc(bal[3] & ltm);
-                    const unsigned total = __popc(bal[0]) + __popc(bal[1]) + __popc(bal[2]) + __popc(bal[3]);
+                for (int c = 0; c < 4; ++c)
+                    mask |= (((xv[c] > DEC_SAT) | !(mv[c] - xv[c] >= collapse_bound(xv[c]))) ? 1u : 0u) << (4 * (u - 1) + c);
+                hm_a = hm_b; hm_b = hm_c;
+            }
+        } else {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        if (cand[c]) {
-                            const unsigned e = pos & (DEC_Q - 1);
-                            w.q_x[e] = xv[c];
-                            w.q_m[e] = mv[c];
-                            w.q_i[e] = (unsigned short)(r * DEC_HW + lane * 4 + c);
-                            ++pos;
-                        }
-                    }
-                    tail += total;
-                    pending += total;
-                    __syncwarp();
-                    if (pending >= 32u) {
-                        dec_drain(w, tail, K, false);
-                        pending &= 31u;
-                        tau_x = w.tau_x;
-                    }
+            for (int u = 1; u <= DEC_G; ++u) {
+                mask |= (nxt[u].x > tau_x ? 1u : 0u) << (4 * (u - 1));
+                mask |= (nxt[u].y > tau_x ? 2u : 0u) << (4 * (u - 1));
+                mask |= (nxt[u].z > tau_x ? 4u : 0u) << (4 * (u - 1));
+                mask |= (nxt[u].w > tau_x ? 8u : 0u) << (4 * (u - 1));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < DEC_G + 2; ++u) *reinterpret_cast<float4*>(&w.tile[u][lane * 4]) = nxt[u];
+        if (r0 + DEC_G < DEC_HW) {                           // prefetch rows r0 + 7 .. r0 + 16 of the next group
+#pragma unroll
+            for (int u = 0; u < DEC_G + 2; ++u) {
+                const int row = r0 + DEC_G - 1 + u;
+                nxt[u] = row < DEC_HW ? ld_stream(hp + row * (DEC_HW / 4)) : ninf;
+            }
+        }
+        if (!__any_sync(FULL, mask != 0u)) continue;
+
+        // list of the flagged pixels (any order: ties are broken on the index when the buffer is pruned)
+        const unsigned n_mine = __popc(mask);
+        unsigned incl = n_mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const unsigned total = __shfl_sync(FULL, incl, 31);
+        {
+            unsigned pos = incl - n_mine;
+            for (unsigned m2 = mask; m2; m2 &= m2 - 1u) {
+                const int bit = __ffs(m2) - 1;
+                w.list[pos++] = (unsigned short)(((bit >> 2) << 7) | (lane * 4 + (bit & 3)));
+            }
+        }
+        __syncwarp();
+
+        // flagged pixels, 32 per step, one per lane: 3x3 maximum from the staged rows, collapse screen, sigmoid,
+        // admission against the K-th best so far
+        for (unsigned j0 = 0; j0 < total; j0 += 32) {
+            const unsigned j = j0 + lane;
+            bool ok = false;
+            unsigned sbits = 0u, flat = 0u;
+            if (j < total) {
+                const unsigned code = w.list[j];
+                const int u = code >> 7, col = code & 127;
+                const int cl = col > 0 ? col - 1 : col, cr = col < DEC_HW - 1 ? col + 1 : col;   // -inf padding: repeat
+                const float x = w.tile[u + 1][col];
+                float m = fmaxf(fmaxf(w.tile[u][cl], w.tile[u][col]), w.tile[u][cr]);
+                m = fmaxf(m, fmaxf(fmaxf(w.tile[u + 1][cl], x), w.tile[u + 1][cr]));
+                m = fmaxf(m, fmaxf(fmaxf(w.tile[u + 2][cl], w.tile[u + 2][col]), w.tile[u + 2][cr]));
+                // the reference's keep mask is sigmoid(m) == sigmoid(x): true at logit peaks, otherwise only inside
+                // the collapse bound (or in saturation); written with !(>=) so that inf - inf = NaN is "not separated"
+                if (x == m || x > DEC_SAT || !(m - x >= collapse_bound(x))) {
+                    const float sg = sigmoidf_ref(x);
+                    sbits = __float_as_uint(sg);                 // sg >= 0: unsigned order == float order
+                    flat = (unsigned)((r0 + u) * DEC_HW + col);
+                    ok = (sbits > tau || (sbits == tau && flat < tau_i)) && (x == m || sigmoidf_ref(m) == sg);
                 }
             }
-            hm_prev = hm_cur; hm_cur = hm_next; x_cur = x_next;
+            const unsigned bal = __ballot_sync(FULL, ok);
+            if (ok) {
+                const unsigned pos = nbuf + __popc(bal & lt);
+                w.buf_s[pos] = sbits;
+                w.buf_i[pos] = (unsigned short)flat;
+            }
+            nbuf += __popc(bal);
+            __syncwarp();
+            if (nbuf > DEC_BUF - 32) {
+                nbuf = dec_prune(w, nbuf, K);
+                tau = w.tau; tau_i = w.tau_i; tau_x = w.tau_x; have_tau = true;
+            }
+        }
+        // tighten the bound as soon as there is enough to select from (every later pixel has a larger index than
+        // everything kept, so the logit bound alone decides who is flagged in the next groups)
+        if (nbuf >= prune_at) {
+            nbuf = dec_prune(w, nbuf, K);
+            tau = w.tau; tau_i = w.tau_i; tau_x = w.tau_x; have_tau = true;
         }
     }
-    if (pending) dec_drain(w, tail, K, true);
-    unsigned nb = w.nbuf;
+    __syncwarp();
+    unsigned nb = nbuf;
     if (nb > (unsigned)K) nb = dec_prune(w, nb, K);
 
     // ---- sort keys: (score bits << 32) | ~flat, padded with zero-score pixels at the smallest indices ------
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(w.q_x);       // 128 slots over q_x | q_m
-    const unsigned lt = (1u << lane) - 1u;
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(&w.tile[0][0]);   // 128 slots over the tile
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const unsigned t = i * 32 + lane;
@@ -287,9 +335,9 @@ decode_kernel(const float* __restrict__ heat, const float* __restrict__ regr,
         unsigned zseen = 0u;
         for (unsigned j0 = 0; j0 < (unsigned)K; j0 += 32) {
             const unsigned j = j0 + lane;
-            int lo = 0, hi = (int)nb;                        // buf_i is ascending: binary search
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (w.buf_i[mid] < j) lo = mid + 1; else hi = mid; }
-            const bool z = j < (unsigned)K && !(lo < (int)nb && w.buf_i[lo] == j);
+            bool inbuf = false;                              // the buffer is unordered: scan it (nb < K <= 128, rare path)
+            for (unsigned i = 0; i < nb; ++i) inbuf |= w.buf_i[i] == j;
+            const bool z = j < (unsigned)K && !inbuf;
             const unsigned bz = __ballot_sync(FULL, z);
             const unsigned rank = zseen + __popc(bz & lt);
             if (z && rank < Z) keys[nb + rank] = (unsigned long long)(0xFFFFFFFFu - j);
@@ -337,39 +385,48 @@ decode_kernel(const float* __restrict__ heat, const float* __restrict__ regr,
     *reinterpret_cast<ulonglong2*>(keys + lane * 4 + 2) = make_ulonglong2(key[2], key[3]);
     __syncwarp();
 
-    // ---- outputs (rank t = i * 32 + lane: coalesced) ----------------------------------------------------
+    // ---- outputs (rank t = i * 32 + lane: coalesced).  All gathers first (24 independent loads per lane in
+    // flight: they are scattered DRAM sectors), then the stores.
+    unsigned flat_[4];
+    float sc_[4], g_[4][6];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int t = i * 32 + lane;
-        if (t >= K) break;
-        const unsigned long long kk = keys[t];
-        const float sc = __uint_as_float((unsigned)(kk >> 32));
-        const unsigned flat = 0xFFFFFFFFu - (unsigned)(kk & 0xFFFFFFFFull);
-        const int y = (int)(flat / DEC_HW), x = (int)(flat % DEC_HW);             // utility.py:115-117
-        const size_t o = (size_t)b * K + t;
-        scores[o] = sc;
-        idx_out[o] = (int64_t)flat;
-        ys[o] = (int64_t)y;
-        xs[o] = (int64_t)x;
-        const float* rp = regr + (size_t)b * 4 * DEC_HW * DEC_HW + flat;
-        const float* op = offset + (size_t)b * 2 * DEC_HW * DEC_HW + flat;
-        const float g0 = __ldg(rp), g1 = __ldg(rp + DEC_HW * DEC_HW);
-        const float g2 = __ldg(rp + 2 * DEC_HW * DEC_HW), g3 = __ldg(rp + 3 * DEC_HW * DEC_HW);
-        const float o0 = __ldg(op), o1 = __ldg(op + DEC_HW * DEC_HW);
-        reinterpret_cast<float4*>(regr_out)[o] = make_float4(g0, g1, g2, g3);
-        reinterpret_cast<float2*>(off_out)[o] = make_float2(o0, o1);
-        if (planes != nullptr) {
-            const size_t ps = (size_t)batch * K;
-            planes[o] = sc;
-            planes[ps + o] = (float)flat;
-            planes[2 * ps + o] = (float)y;
-            planes[3 * ps + o] = (float)x;
-            planes[4 * ps + o] = g0;
-            planes[5 * ps + o] = g1;
-            planes[6 * ps + o] = g2;
-            planes[7 * ps + o] = g3;
-            planes[8 * ps + o] = o0;
-            planes[9 * ps + o] = o1;
+        const unsigned long long kk = keys[t < K ? t : 0];
+        sc_[i] = __uint_as_float((unsigned)(kk >> 32));
+        flat_[i] = 0xFFFFFFFFu - (unsigned)(kk & 0xFFFFFFFFull);
+        const float* rp = regr + (size_t)b * 4 * DEC_HW * DEC_HW + flat_[i];
+        const float* op = offset + (size_t)b * 2 * DEC_HW * DEC_HW + flat_[i];
+        g_[i][0] = __ldg(rp); g_[i][1] = __ldg(rp + DEC_HW * DEC_HW);
+        g_[i][2] = __ldg(rp + 2 * DEC_HW * DEC_HW); g_[i][3] = __ldg(rp + 3 * DEC_HW * DEC_HW);
+        g_[i][4] = __ldg(op); g_[i][5] = __ldg(op + DEC_HW * DEC_HW);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int t = i * 32 + lane;
+        if (t < K) {
+            const unsigned flat = flat_[i];
+            const int y = (int)(flat / DEC_HW), x = (int)(flat % DEC_HW);             // utility.py:115-117
+            const size_t o = (size_t)b * K + t;
+            scores[o] = sc_[i];
+            idx_out[o] = (int64_t)flat;
+            ys[o] = (int64_t)y;
+            xs[o] = (int64_t)x;
+            reinterpret_cast<float4*>(regr_out)[o] = make_float4(g_[i][0], g_[i][1], g_[i][2], g_[i][3]);
+            reinterpret_cast<float2*>(off_out)[o] = make_float2(g_[i][4], g_[i][5]);
+            if (planes != nullptr) {
+                const size_t ps = (size_t)batch * K;
+                planes[o] = sc_[i];
+                planes[ps + o] = (float)flat;
+                planes[2 * ps + o] = (float)y;
+                planes[3 * ps + o] = (float)x;
+                planes[4 * ps + o] = g_[i][0];
+                planes[5 * ps + o] = g_[i][1];
+                planes[6 * ps + o] = g_[i][2];
+                planes[7 * ps + o] = g_[i][3];
+                planes[8 * ps + o] = g_[i][4];
+                planes[9 * ps + o] = g_[i][5];
+            }
         }
     }
 }
