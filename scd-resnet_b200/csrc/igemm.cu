@@ -19,6 +19,7 @@
 // (one thread issues tcgen05.mma for the CTA; accumulators live in TMEM, double-buffered when
 // 2*BN <= 512 columns), warps 2-5 = epilogue (tcgen05.ld -> bias/residual/ReLU -> bf16 NHWC,
 // or for the heads: ReLU + block-diagonal 1x1 -> fp32 NCHW planes).
+#include <cstdlib>
 #include "tc.cuh"
 #include "tmap.cuh"
 
@@ -38,6 +39,11 @@ struct alignas(64) IgemmParams {
     CUtensorMap tmOut[4];           // output views (one per output parity for the deconv), box {64 ch, 16 x, 2 y}
     int n_taps[4], cin_blocks, tiles_x, tiles_y, n_par, n_tiles_n, batch, total_tiles;
     int cout, out_mul, hout, wout, relu;
+    int b_resident;                 // BN = 64 only: the whole weight matrix (<= 9 k-blocks) stays in shared memory
+    int row_mode;                   // BN = 64, 3x3 s1, Cin = 64, W = 128: one image row per tile, A = 3-row halo strip loaded once
+    int bo_mode;                    // row_mode: put (start address >> 7) & 7 into the descriptor's base_offset field
+    CUtensorMap tmHalo;             // box {64 ch, 130 x, 3 y}
+    CUtensorMap tmOutRow;           // box {64 ch, 32 x, 1 y}
     int8_t tap_map[4][16], tap_dy[4][16], tap_dx[4][16];   // per output-parity class: A view, y / x offset
     const float* bias;
     const __nv_bfloat16* residual;
@@ -53,12 +59,16 @@ struct alignas(64) IgemmParams {
 template <int BN> struct IgemmCfg {
     static constexpr int B_BYTES = BN * IG_BK * 2;
     static constexpr int STAGE_BYTES = IG_A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN <= 128) ? 6 : (BN == 256 ? 4 : 3);
+    static constexpr int STAGES = (BN == 64) ? 5 : (BN == 128 ? 6 : (BN == 256 ? 4 : 3));
+    static constexpr int RES_B_BLOCKS = (BN == 64) ? 9 : 0;     // resident weights: 9 k-blocks x 8 KB (layer1: 3x3, Cin 64)
+    static constexpr int HALO_W = 130, HALO_BYTES = 3 * HALO_W * 128;       // row mode: 3 rows x 130 px x 64 ch
+    static constexpr int HALO_STAGE = 50 * 1024, HALO_STAGES = 2;           // fits into the 5 x 24 KB stage area
     static constexpr int ACC_STAGES = (2 * BN <= 512) ? 2 : 1;
     static constexpr int TMEM_COLS = (BN * ACC_STAGES <= 128) ? 128 : (BN * ACC_STAGES <= 256 ? 256 : 512);
     static constexpr int B_BOX_ROWS = (BN > 256) ? BN / 2 : BN;
     // [pipeline stages][4 x 4 KB store staging][barriers 256 B][per-warp bias copies | head constants]
-    static constexpr int OFF_STG = STAGES * STAGE_BYTES;
+    static constexpr int OFF_RESB = STAGES * STAGE_BYTES;
+    static constexpr int OFF_STG = OFF_RESB + RES_B_BLOCKS * B_BYTES;
     static constexpr int OFF_BAR = OFF_STG + 4 * 4096;
     static constexpr int OFF_CONST = OFF_BAR + 256;
     static constexpr int CONST_BYTES = (BN > 256) ? (384 + 7 * 128 + 8) * 4 : 4 * BN * 4;
@@ -81,6 +91,8 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+    const uint32_t resb_bar = bar_base + 8u * (2 * Cfg::STAGES + 5);          // resident weights have landed
+    const bool resb = Cfg::RES_B_BLOCKS > 0 && p.b_resident != 0;
     uint32_t* tmem_slot_gen = reinterpret_cast<uint32_t*>(smem_gen + Cfg::OFF_BAR + 8 * (2 * Cfg::STAGES + 4));
     float* head_const = reinterpret_cast<float*>(smem_gen + Cfg::OFF_CONST);
 
@@ -91,6 +103,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
         tc::tma_prefetch_desc(&p.tmA[0]);
         for (int s = 0; s < Cfg::STAGES; ++s) { tc::mbar_init(full_bar(s), 1); tc::mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < 2; ++s) { tc::mbar_init(tfull_bar(s), 1); tc::mbar_init(tempty_bar(s), 128); }
+        tc::mbar_init(resb_bar, 1);
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -113,6 +126,22 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
         // ================= TMA producer =================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            if (resb) {             // the whole (Cout, K) weight matrix once per CTA: layer1 re-read it for every tile
+                const int kbs = p.n_taps[0] * p.cin_blocks;
+                tc::mbar_arrive_expect_tx(resb_bar, (uint32_t)kbs * Cfg::B_BYTES);
+                for (int kb = 0; kb < kbs; ++kb)
+                    tc::tma_load_2d(&p.tmB, resb_bar, smem_base + Cfg::OFF_RESB + kb * Cfg::B_BYTES, kb * IG_BK, 0);
+            }
+            if (Cfg::RES_B_BLOCKS > 0 && p.row_mode) {
+                // one image row (128 px) per tile: the 3 x 130 px halo strip once, all nine taps read it in place
+                for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                    const int ty = t % p.tiles_y, img = t / p.tiles_y;
+                    tc::mbar_wait(empty_bar(stage), phase ^ 1u);
+                    tc::mbar_arrive_expect_tx(full_bar(stage), Cfg::HALO_BYTES);
+                    tc::tma_load_4d(&p.tmHalo, full_bar(stage), smem_base + stage * Cfg::HALO_STAGE, 0, -1, ty - 1, img);
+                    if (++stage == Cfg::HALO_STAGES) { stage = 0; phase ^= 1u; }
+                }
+            } else
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const int nt = t % p.n_tiles_n;
                 int m = t / p.n_tiles_n;
@@ -129,10 +158,10 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
                         tc::mbar_wait(empty_bar(stage), phase ^ 1u);
                         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                         const uint32_t sb = sa + IG_A_BYTES;
-                        tc::mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+                        tc::mbar_arrive_expect_tx(full_bar(stage), resb ? IG_A_BYTES : Cfg::STAGE_BYTES);
                         tc::tma_load_4d(ma, full_bar(stage), sa, cb * IG_BK, ax, ay, img);
                         const int kcol = (tap * p.cin_blocks + cb) * IG_BK;
-                        tc::tma_load_2d(&p.tmB, full_bar(stage), sb, kcol, brow);
+                        if (!resb) tc::tma_load_2d(&p.tmB, full_bar(stage), sb, kcol, brow);
                         if (BN > 256)
                             tc::tma_load_2d(&p.tmB, full_bar(stage), sb + Cfg::B_BOX_ROWS * IG_BK * 2, kcol,
                                             brow + Cfg::B_BOX_ROWS);
@@ -149,6 +178,34 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
             constexpr uint32_t idesc_tail = tc::umma_idesc_16(IG_BM, BN > 256 ? BN - 256 : 16, A16::kFmt);
             int stage = 0; uint32_t phase = 0;
             uint32_t it = 0;
+            if (resb) { tc::mbar_wait(resb_bar, 0); tc::tc_fence_after(); }
+            if (Cfg::RES_B_BLOCKS > 0 && p.row_mode) {
+                for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+                    const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+                    tc::mbar_wait(tempty_bar(as), aphase ^ 1u);
+                    tc::mbar_wait(full_bar(stage), phase);
+                    tc::tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + as * BN;
+                    const uint32_t halo = smem_base + stage * Cfg::HALO_STAGE;
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        // operand rows = the 128 pixels (x + dx) of halo row dy + 1: a window of the strip that starts
+                        // (tap / 3) * 130 + tap % 3 pixel rows (128 B each) into it, i.e. off the 1024 B swizzle
+                        // pattern.  The tensor core takes the pattern phase from the address bits (as TMA did when it
+                        // wrote the strip), so the plain descriptor is right; bo_mode is the experiment switch.
+                        const uint32_t a0 = halo + (uint32_t)((tap / 3) * Cfg::HALO_W + tap % 3) * 128u;
+                        const uint64_t bo = p.bo_mode ? ((uint64_t)((a0 >> 7) & 7u) << 49) : 0ull;
+                        const uint32_t b0 = smem_base + Cfg::OFF_RESB + tap * Cfg::B_BYTES;
+#pragma unroll
+                        for (int k = 0; k < IG_BK / 16; ++k)
+                            tc::umma_bf16(d_tmem, tc::umma_desc_sw128(a0 + k * 32) | bo, tc::umma_desc_sw128(b0 + k * 32), idesc_main,
+                                          (tap | k) ? 1u : 0u);
+                    }
+                    tc::umma_commit(empty_bar(stage));
+                    tc::umma_commit(tfull_bar(as));
+                    if (++stage == Cfg::HALO_STAGES) { stage = 0; phase ^= 1u; }
+                }
+            } else
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
                 const int k_blocks = p.n_taps[(t / (p.n_tiles_n * p.tiles_x * p.tiles_y)) % p.n_par] * p.cin_blocks;
                 const uint32_t as = (Cfg::ACC_STAGES == 2) ? (it & 1u) : 0u;
@@ -160,7 +217,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
                     tc::mbar_wait(full_bar(stage), phase);
                     tc::tc_fence_after();
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-                    const uint32_t sb = sa + IG_A_BYTES;
+                    const uint32_t sb = resb ? smem_base + Cfg::OFF_RESB + kb * Cfg::B_BYTES : sa + IG_A_BYTES;
 #pragma unroll
                     for (int k = 0; k < IG_BK / 16; ++k) {
                         const uint64_t adesc = tc::umma_desc_sw128(sa + k * 32);
@@ -192,8 +249,9 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
             const int ty = m % p.tiles_y; m /= p.tiles_y;
             const int par = m % p.n_par;
             const int img = m / p.n_par;
-            const int oy = (ty * IG_TH + ly) * p.out_mul + (par >> 1);
-            const int ox = (tx * IG_TW + lx) * p.out_mul + (par & 1);
+            const bool rowm = Cfg::RES_B_BLOCKS > 0 && p.row_mode;                   // tile = image row ty, pixel x = TMEM lane
+            const int oy = rowm ? ty : (ty * IG_TH + ly) * p.out_mul + (par >> 1);
+            const int ox = rowm ? row : (tx * IG_TW + lx) * p.out_mul + (par & 1);
             const uint32_t as = (Cfg::ACC_STAGES == 2) ? (it & 1u) : 0u;
             const uint32_t aphase = (Cfg::ACC_STAGES == 2) ? ((it >> 1) & 1u) : (it & 1u);
             tc::mbar_wait(tfull_bar(as), aphase);
@@ -211,8 +269,8 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
                 __syncwarp();
                 const size_t pix = ((size_t)img * p.hout + oy) * p.wout + ox;
                 const __nv_bfloat16* rptr = p.residual ? p.residual + pix * p.cout + nt * BN : nullptr;
-                const CUtensorMap* mo = &p.tmOut[par];
-                const int gx = tx * IG_TW, gy = ty * IG_TH + 2 * q;
+                const CUtensorMap* mo = rowm ? &p.tmOutRow : &p.tmOut[par];
+                const int gx = rowm ? 32 * q : tx * IG_TW, gy = rowm ? ty : ty * IG_TH + 2 * q;
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 64) {
                     uint4 resv[8];
@@ -475,6 +533,31 @@ static int conv_igemm(int kind, const void* x, const void* x2, const void* weigh
     const int bn = pick_bn(cout);
     if (cout % bn) return fail(SCD_EINVAL, "Cout = %d unsupported", cout);
     p.cout = cout; p.n_tiles_n = cout / bn; p.relu = relu;
+    p.b_resident = (bn == 64 && p.n_par == 1 && p.n_tiles_n == 1 && p.n_taps[0] * p.cin_blocks <= IgemmCfg<64>::RES_B_BLOCKS) ? 1 : 0;
+    // SCD_IGEMM_ROW_MODE: 0 = off, 1 = on (default), 2 = on with the pattern phase in the descriptor's base_offset field.
+    // Measured on B200: tcgen05 derives the 128-byte swizzle phase from the operand's shared-memory ADDRESS bits, so a
+    // window that starts off the 1024 B pattern needs base_offset = 0 (mode 2 gives wrong results; tests/test_gpu_kernels.py).
+    static const int row_env = [] { const char* e = getenv("SCD_IGEMM_ROW_MODE"); return e ? atoi(e) : 1; }();
+    if (row_env && p.b_resident && kind == 0 && cin == 64 && win == IG_BM) {
+        p.row_mode = 1; p.bo_mode = row_env == 2;
+        p.tiles_x = 1; p.tiles_y = hin;
+        EncodeTiledFn enc = encode_fn();
+        if (!enc) return fail(SCD_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+        const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+        cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)win, (cuuint64_t)hin, (cuuint64_t)batch};
+        cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)win * cin * 2, (cuuint64_t)hin * win * cin * 2};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        cuuint32_t box_in[4] = {64, (cuuint32_t)IgemmCfg<64>::HALO_W, 3, 1};
+        CUresult r = enc(&p.tmHalo, dt, 4, const_cast<void*>(x), dims, strides, box_in, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(SCD_ECUDA, "cuTensorMapEncodeTiled(halo) failed: %d", (int)r);
+        cuuint64_t odims[4] = {(cuuint64_t)cout, (cuuint64_t)win, (cuuint64_t)hin, (cuuint64_t)batch};
+        cuuint64_t ostrides[3] = {(cuuint64_t)cout * 2, (cuuint64_t)win * cout * 2, (cuuint64_t)hin * win * cout * 2};
+        cuuint32_t box_out[4] = {64, 32, 1, 1};
+        r = enc(&p.tmOutRow, dt, 4, y, odims, ostrides, box_out, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(SCD_ECUDA, "cuTensorMapEncodeTiled(row out) failed: %d", (int)r);
+    }
     p.total_tiles = batch * p.n_par * p.tiles_y * p.tiles_x * p.n_tiles_n;
     p.bias = bias; p.residual = static_cast<const __nv_bfloat16*>(residual); p.out = static_cast<__nv_bfloat16*>(y);
     int max_taps = 0;
