@@ -44,6 +44,7 @@ struct alignas(64) IgemmParams {
     int bo_mode;                    // row_mode: put (start address >> 7) & 7 into the descriptor's base_offset field
     CUtensorMap tmHalo;             // box {64 ch, 130 x, 3 y}
     CUtensorMap tmOutRow;           // box {64 ch, 32 x, 1 y}
+    CUtensorMap tmRes;              // row mode with a residual: box {64 ch, 128 x, 1 y}, prefetched by the producer
     int8_t tap_map[4][16], tap_dy[4][16], tap_dx[4][16];   // per output-parity class: A view, y / x offset
     const float* bias;
     const __nv_bfloat16* residual;
@@ -67,7 +68,11 @@ template <int BN> struct IgemmCfg {
     static constexpr int TMEM_COLS = (BN * ACC_STAGES <= 128) ? 128 : (BN * ACC_STAGES <= 256 ? 256 : 512);
     static constexpr int B_BOX_ROWS = (BN > 256) ? BN / 2 : BN;
     // [pipeline stages][4 x 4 KB store staging][barriers 256 B][per-warp bias copies | head constants]
-    static constexpr int OFF_RESB = STAGES * STAGE_BYTES;
+    static constexpr int RES_STAGE = IG_BM * 128;                           // row mode: residual row, 16 KB, 2 stages
+    static constexpr int OFF_ROWRES = HALO_STAGES * HALO_STAGE;
+    static constexpr int STAGE_AREA = (BN == 64 && OFF_ROWRES + 2 * RES_STAGE > STAGES * STAGE_BYTES)
+                                          ? OFF_ROWRES + 2 * RES_STAGE : STAGES * STAGE_BYTES;
+    static constexpr int OFF_RESB = STAGE_AREA;
     static constexpr int OFF_STG = OFF_RESB + RES_B_BLOCKS * B_BYTES;
     static constexpr int OFF_BAR = OFF_STG + 4 * 4096;
     static constexpr int OFF_CONST = OFF_BAR + 256;
@@ -92,6 +97,8 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
     const uint32_t resb_bar = bar_base + 8u * (2 * Cfg::STAGES + 5);          // resident weights have landed
+    auto rfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 6 + s); };    // row mode: residual row landed
+    auto rempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 8 + s); };   //           ... and was consumed
     const bool resb = Cfg::RES_B_BLOCKS > 0 && p.b_resident != 0;
     uint32_t* tmem_slot_gen = reinterpret_cast<uint32_t*>(smem_gen + Cfg::OFF_BAR + 8 * (2 * Cfg::STAGES + 4));
     float* head_const = reinterpret_cast<float*>(smem_gen + Cfg::OFF_CONST);
@@ -104,6 +111,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
         for (int s = 0; s < Cfg::STAGES; ++s) { tc::mbar_init(full_bar(s), 1); tc::mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < 2; ++s) { tc::mbar_init(tfull_bar(s), 1); tc::mbar_init(tempty_bar(s), 128); }
         tc::mbar_init(resb_bar, 1);
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(rfull_bar(s), 1); tc::mbar_init(rempty_bar(s), 128); }
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -139,6 +147,11 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
                     tc::mbar_wait(empty_bar(stage), phase ^ 1u);
                     tc::mbar_arrive_expect_tx(full_bar(stage), Cfg::HALO_BYTES);
                     tc::tma_load_4d(&p.tmHalo, full_bar(stage), smem_base + stage * Cfg::HALO_STAGE, 0, -1, ty - 1, img);
+                    if (p.residual) {                       // the epilogue's residual row rides along (same stage index)
+                        tc::mbar_wait(rempty_bar(stage), phase ^ 1u);
+                        tc::mbar_arrive_expect_tx(rfull_bar(stage), Cfg::RES_STAGE);
+                        tc::tma_load_4d(&p.tmRes, rfull_bar(stage), smem_base + Cfg::OFF_ROWRES + stage * Cfg::RES_STAGE, 0, 0, ty, img);
+                    }
                     if (++stage == Cfg::HALO_STAGES) { stage = 0; phase ^= 1u; }
                 }
             } else
@@ -274,7 +287,14 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 64) {
                     uint4 resv[8];
-                    if (rptr) {
+                    if (rptr && rowm) {                      // row mode: the producer's TMA put the residual row in smem
+                        const uint32_t rs = it & 1u, rph = (it >> 1) & 1u;
+                        tc::mbar_wait(rfull_bar(rs), rph);
+                        const unsigned char* rsm = smem_gen + Cfg::OFF_ROWRES + rs * Cfg::RES_STAGE + row * 128;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) resv[i] = *reinterpret_cast<const uint4*>(rsm + ((i ^ (row & 7)) << 4));
+                        tc::mbar_arrive(rempty_bar(rs));
+                    } else if (rptr) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) resv[i] = __ldg(reinterpret_cast<const uint4*>(rptr + c0) + i);
                     }
@@ -557,6 +577,12 @@ static int conv_igemm(int kind, const void* x, const void* x2, const void* weigh
         r = enc(&p.tmOutRow, dt, 4, y, odims, ostrides, box_out, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(SCD_ECUDA, "cuTensorMapEncodeTiled(row out) failed: %d", (int)r);
+        if (residual) {
+            cuuint32_t box_res[4] = {64, (cuuint32_t)IG_BM, 1, 1};
+            r = enc(&p.tmRes, dt, 4, const_cast<void*>(residual), odims, ostrides, box_res, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(SCD_ECUDA, "cuTensorMapEncodeTiled(row residual) failed: %d", (int)r);
+        }
     }
     p.total_tiles = batch * p.n_par * p.tiles_y * p.tiles_x * p.n_tiles_n;
     p.bias = bias; p.residual = static_cast<const __nv_bfloat16*>(residual); p.out = static_cast<__nv_bfloat16*>(y);
