@@ -39,8 +39,8 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
 // Threads are laid out so that thread t always handles channel group (t % (C/8)); a CTA strides over
 // pixels.  Requires BN_THREADS % (C/8) == 0, true for C in {64,128,256,384(no!),512}: 384/8 = 48 does not
 // divide 256, so the launch picks a block size that is a multiple of C/8.
-template <int MODE>   // 0: stats of z   1: backward sums
-__global__ void __launch_bounds__(384)
+template <int MODE>   // 0: stats of z   1: backward sums (mask from a, or none)   2: backward sums, ReLU mask recomputed from z
+__global__ void __launch_bounds__(384, 3)
 bn_reduce_kernel(const uint4* __restrict__ z, const uint4* __restrict__ da, const uint4* __restrict__ a,
                  const float* __restrict__ mean, const float* __restrict__ invstd,
                  const float* __restrict__ scale, const float* __restrict__ shift,    // ReLU mask from z when a == NULL
@@ -53,14 +53,15 @@ bn_reduce_kernel(const uint4* __restrict__ z, const uint4* __restrict__ da, cons
     float s0[8], s1[8], mu[8], is[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s0[i] = 0.f; s1[i] = 0.f; mu[i] = 0.f; is[i] = 1.f; }
-    float sc[8], sh[8];
-    const bool zmask = MODE == 1 && a == nullptr && shift != nullptr;
-    if (MODE == 1) {
+    float sc[MODE == 2 ? 8 : 1], sh[MODE == 2 ? 8 : 1];
+    constexpr bool zmask = MODE == 2;
+    if (MODE >= 1) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            mu[i] = mean[g * 8 + i]; is[i] = invstd[g * 8 + i];
-            sc[i] = zmask ? scale[g * 8 + i] : 0.f; sh[i] = zmask ? shift[g * 8 + i] : 0.f;
-        }
+        for (int i = 0; i < 8; ++i) { mu[i] = mean[g * 8 + i]; is[i] = invstd[g * 8 + i]; }
+    }
+    if (MODE == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sc[i] = scale[g * 8 + i]; sh[i] = shift[g * 8 + i]; }
     }
     for (size_t p = (size_t)blockIdx.x * lanes + pl; p < pixels; p += (size_t)gridDim.x * lanes) {
         float zf[8];
@@ -71,14 +72,14 @@ bn_reduce_kernel(const uint4* __restrict__ z, const uint4* __restrict__ da, cons
         } else {
             float df[8];
             unpack8(__ldg(da + p * cgroups + g), df);
-            if (a != nullptr) {
+            if (zmask) {                    // a = relu(z * scale + shift): the same fma as the forward, same sign
+#pragma unroll
+                for (int i = 0; i < 8; ++i) df[i] = fmaf(zf[i], sc[MODE == 2 ? i : 0], sh[MODE == 2 ? i : 0]) > 0.f ? df[i] : 0.f;
+            } else if (a != nullptr) {
                 float af[8];
                 unpack8(__ldg(a + p * cgroups + g), af);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) df[i] = af[i] > 0.f ? df[i] : 0.f;
-            } else if (zmask) {             // a = relu(z * scale + shift): the same fma as the forward, same sign
-#pragma unroll
-                for (int i = 0; i < 8; ++i) df[i] = fmaf(zf[i], sc[i], sh[i]) > 0.f ? df[i] : 0.f;
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) { s0[i] += df[i]; s1[i] = fmaf(df[i], (zf[i] - mu[i]) * is[i], s1[i]); }
@@ -285,9 +286,14 @@ extern "C" int scd_bn_bwd(const void* da, const void* a, const void* z, const fl
         if (!block) return fail(SCD_EINVAL, "scd_bn_bwd: unsupported channel count %d", C);
         SCD_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
         const int lanes = block / (C / 8);
-        bn_reduce_kernel<1><<<stream_grid(pixels, lanes * 16), block, (size_t)2 * block * 8 * sizeof(float), st>>>(
-            static_cast<const uint4*>(z), static_cast<const uint4*>(da), static_cast<const uint4*>(a), mean, invstd,
-            scale, shift, pixels, C / 8, sums);
+        if (a == nullptr && shift != nullptr)
+            bn_reduce_kernel<2><<<stream_grid(pixels, lanes * 16), block, (size_t)2 * block * 8 * sizeof(float), st>>>(
+                static_cast<const uint4*>(z), static_cast<const uint4*>(da), nullptr, mean, invstd, scale, shift, pixels,
+                C / 8, sums);
+        else
+            bn_reduce_kernel<1><<<stream_grid(pixels, lanes * 16), block, (size_t)2 * block * 8 * sizeof(float), st>>>(
+                static_cast<const uint4*>(z), static_cast<const uint4*>(da), static_cast<const uint4*>(a), mean, invstd,
+                scale, shift, pixels, C / 8, sums);
         SCD_LAUNCH_CHECK("bn_reduce_kernel<1>");
     } else {
         if (!dz) return fail(SCD_EINVAL, "scd_bn_bwd: dz is null");
