@@ -371,7 +371,7 @@ def main():
             "roofline": {"kernel": "igemm_kernel<384, EPI_HEADS> (fused heads)", "bound": "tensor",
                          "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": ach / peaks["bf16_tflops_sustained"],
-                         "traffic": 569620992 * B // 64,    # dram read + write per launch, ncu --set full (profiles/ncu_full_r01_b.json)
+                         "traffic": 569620992 * B // 64,    # dram read + write per launch, ncu --set full (profiles/ncu_full_r01_c.json)
                          "peak_source": peaks["source"] + " sustained bf16 (kernel timed inside a long step)",
                          "ms_per_launch": heads_ms},
             "step_tflops": FLOPS_PER_TILE * B / (ms / K * 1e-3) / 1e12,
