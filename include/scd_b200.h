@@ -190,6 +190,36 @@ int scd_resnet10_infer(const float* x, const void* weights, int batch, int heigh
                        void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * The same pass for the other BasicBlock plugins: depth = numLayers in {10, 18, 34}
+ * (ResNetSpec, models/backbones/residuals.py:20-26), dims8 = the eight `dims` of ResNet.__init__
+ * (residuals.py:195-201; NULL = {64,64,128,256,512,256,256,256}), every entry a supported channel count of the
+ * kernels (64, 128, 256 or 512).  The half / quarter-width plugins (trainer/model/centerOffsetRes10h.py:13-14,
+ * Res10q, Res18h, Res34h; head width 64, models/centerNetOffseth.py:146-148) run zero-padded to these widths:
+ * the host packs zero rows / columns (weights.py), which leaves every real channel's arithmetic unchanged.
+ * The heads always see 3 x 128 hidden channels (w3 (384, 9*dims8[7]), w1 (7,128)).
+ *
+ * Blob: 0 stem w | 1 stem b | 2+2i, 3+2i weight / bias of igemm stage i | then heads w3, b3, w1, b1;
+ * stage order per layer: [downsample, conv1, conv2] for a projection block, [conv1, conv2] otherwise, then the
+ * three deconvs (scd_resnet_conv_specs lists kind / cin / cout).  Stage events: scd_resnet_num_convs + 3.
+ * f16 != 0 selects fp16 operands.  scd_resnet10_infer == scd_resnet_infer(10, NULL, 0, ...).
+ * ---------------------------------------------------------------------------------- */
+int    scd_resnet_num_convs(int depth, const int* dims8);                     /* < 0: unsupported */
+int    scd_resnet_conv_specs(int depth, const int* dims8, int* h_kind, int* h_cin, int* h_cout, int n);
+size_t scd_resnet_weights_bytes(int depth, const int* dims8);
+int    scd_resnet_weights_layout(int depth, const int* dims8, size_t* h_offsets, size_t* h_sizes, int n);
+size_t scd_resnet_workspace_bytes(int depth, const int* dims8, int batch, int height, int width);
+int scd_resnet_infer(int depth, const int* dims8, int f16, const float* x, const void* weights, int batch,
+                     int height, int width, float* heat, float* regr, float* offset, void* workspace,
+                     size_t workspace_bytes, void* const* h_stage_events, int n_events, void* stream);
+/* scd_heads_fwd with `cin` input channels (x (B,H,W,cin), w3 (384, 9*cin)). */
+int scd_heads_fwd_c(const void* x, const void* w3, const float* b3, const float* w1,
+                    const float* b1, int batch, int height, int width, int cin,
+                    float* heat, float* regr, float* offset, void* stream);
+int scd_heads_fwd_c_f16(const void* x, const void* w3, const float* b3, const float* w1,
+                        const float* b1, int batch, int height, int width, int cin,
+                        float* heat, float* regr, float* offset, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * fp16 variants of the inference entry points: identical contracts with fp16 in place of bf16 for the NHWC
  * activations, the GEMM-operand weights and the 16-bit entries of the parameter blob.  tcgen05 kind::f16 runs
  * both formats at the same rate; fp16's 11-bit mantissa keeps the end-to-end error of the 18-layer network near

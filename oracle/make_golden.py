@@ -280,5 +280,49 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+VARIANTS = ("centerOffsetRes18", "centerOffsetRes34", "centerOffsetRes10h", "centerOffsetRes10q", "centerOffsetRes18h",
+            "centerOffsetRes34h")
+
+
+def make_variants():
+    """the width / depth variants of the plugin (trainer/model/centerOffsetRes*.py), each run
+    through the real reference module on one 256 x 512 tile with the oracle's deterministic weights."""
+    sys.path.insert(0, ROOT)
+    from oracle import centernet_cpu as O
+    import_reference()
+    torch.set_num_threads(8)
+    g = {"names": np.array(VARIANTS)}
+    x = O.make_tiles(1, seed=7)[:, :, :256, :]
+    for name in VARIANTS:
+        plugin = importlib.import_module("trainer.model." + name)
+        model = plugin.model(**plugin.modelParams)
+        ref_sd = model.state_dict()
+        depth, dims = plugin.modelParams["numLayers"], plugin.modelParams["dims"]
+        head_dim = ref_sd["heatmap.0.weight"].shape[0]
+        spec = O.state_dict_spec(dims, depth=depth, head_dim=head_dim)
+        assert list(spec) == list(ref_sd), name
+        assert all(tuple(ref_sd[k].shape) == tuple(v) for k, v in spec.items()), name
+        sd = O.make_state_dict(1234, dims, depth, head_dim)
+        model.load_state_dict(sd, strict=True)
+        model.eval()
+        with torch.no_grad():
+            out = model(x, decode=False)[0]
+            dec = model(x, decode=True)
+        for k, short in (("heatmap", "heat"), ("regr", "regr"), ("offset", "off")):
+            g["%s_%s_sub" % (name, short)] = sub(out[k])
+            g["%s_%s_sum" % (name, short)] = np.float64(out[k].double().sum().item())
+            g["%s_%s_abs" % (name, short)] = np.float64(out[k].double().abs().sum().item())
+        g[name + "_dec_scores"] = dec[0].numpy()
+        g[name + "_dec_idx"] = dec[1].numpy()
+        g[name + "_head_dim"] = np.int64(head_dim)
+        print(name, depth, dims, head_dim, "distinct top-100 scores", len(np.unique(dec[0].numpy())))
+    np.savez_compressed(os.path.join(OUT, "variants.npz"), **g)
+    print("variants.npz", os.path.getsize(os.path.join(OUT, "variants.npz")))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "variants":
+        make_variants()
+    else:
+        main()
+        make_variants()

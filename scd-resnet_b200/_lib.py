@@ -37,6 +37,15 @@ PROTOTYPES = {
     "scd_heads_fwd_f16": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p] * 3 + [c_void_p]),
     "scd_resnet10_infer_f16": (c_int, [c_void_p, c_void_p] + [c_int] * 3 + [c_void_p] * 3
                                + [c_void_p, c_size_t, c_void_p, c_void_p]),
+    "scd_resnet_num_convs": (c_int, [c_int, c_void_p]),
+    "scd_resnet_conv_specs": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    "scd_resnet_weights_bytes": (c_size_t, [c_int, c_void_p]),
+    "scd_resnet_weights_layout": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int]),
+    "scd_resnet_workspace_bytes": (c_size_t, [c_int, c_void_p, c_int, c_int, c_int]),
+    "scd_resnet_infer": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p] + [c_int] * 3 + [c_void_p] * 3
+                         + [c_void_p, c_size_t, c_void_p, c_int, c_void_p]),
+    "scd_heads_fwd_c": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p] * 3 + [c_void_p]),
+    "scd_heads_fwd_c_f16": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p] * 3 + [c_void_p]),
     "scd_bn_stats": (c_int, [c_void_p, c_size_t, c_int, c_void_p, c_void_p]),
     "scd_bn_finalize": (c_int, [c_void_p] * 6 + [c_int, ctypes.c_double, c_float, c_float] + [c_void_p] * 4 + [c_void_p]),
     "scd_bn_apply": (c_int, [c_void_p] * 4 + [c_int, c_size_t, c_int, c_void_p, c_void_p]),

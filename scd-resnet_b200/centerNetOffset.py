@@ -47,8 +47,11 @@ def makeResnetTerminal(prediction, current, output):
 
 
 class CenterNetResidual(torch.nn.Module):
-    """ResNet-10 CenterNet with heatmap / regr / offset heads (ref: models/centerNetOffset.py:150-168,
-    models/backbones/residuals.py:184-353).  Only numLayers=10 with the default dims is built here."""
+    """ResNet CenterNet with heatmap / regr / offset heads (ref: models/centerNetOffset.py:150-168,
+    models/backbones/residuals.py:184-353).  numLayers 10 (the headline plugin), 18 and 34 (BasicBlock networks,
+    ResNetSpec residuals.py:20-26); `dims` up to 512 channels (narrower networks run zero-padded to the kernels'
+    64-channel granularity, weights.arch_of).  The Bottleneck depths 50 / 101 are not built."""
+    terminalDimension = 128                                                      # ref: centerNetOffset.py:146-148
 
     def __init__(self, numLayers=10, dims=(64, 64, 128, 256, 512, 256, 256, 256), precision="bf16"):
         """precision: 16-bit format of the eval-mode tensor-core path, "bf16" (BASELINE's configuration) or "fp16"
@@ -59,9 +62,12 @@ class CenterNetResidual(torch.nn.Module):
             raise ScdError("precision must be 'bf16' or 'fp16'")
         self.precision = precision
         dims = list(dims)
-        if numLayers != 10 or dims != [64, 64, 128, 256, 512, 256, 256, 256]:
-            raise ScdError("scd_b200 builds centerOffsetRes10 only (numLayers=10, default dims); got %r %r"
-                           % (numLayers, dims))
+        if numLayers not in weights.BLOCKS:
+            raise ScdError("scd_b200 builds the BasicBlock networks (numLayers %s); got %r"
+                           % (sorted(weights.BLOCKS), numLayers))
+        if len(dims) != 8 or dims[0] != dims[1] or max(dims) > 512 or min(dims) < 1:
+            raise ScdError("scd_b200: dims must be 8 widths <= 512 with dims[0] == dims[1]; got %r" % (dims,))
+        self.numLayers, self.dims = numLayers, dims
         self.decoder = decodeCenterNet
         self.preprocess = torch.nn.Sequential(                                   # ref: residuals.py:210-215
             torch.nn.Conv2d(1, dims[0], kernel_size=7, stride=2, padding=3, bias=False),
@@ -75,7 +81,9 @@ class CenterNetResidual(torch.nn.Module):
             if stride != 1 or cin != c:
                 down = torch.nn.Sequential(torch.nn.Conv2d(cin, c, kernel_size=1, stride=stride, bias=False),
                                            torch.nn.BatchNorm2d(c, momentum=BNMOMENTUM))
-            setattr(self, "layer%d" % li, torch.nn.Sequential(BasicBlock(cin, c, stride, down)))
+            blocks = [BasicBlock(cin, c, stride, down)]
+            blocks += [BasicBlock(c, c) for _ in range(1, weights.BLOCKS[numLayers][li - 1])]
+            setattr(self, "layer%d" % li, torch.nn.Sequential(*blocks))
             cin = c
         layers = []
         for c in (dims[5], dims[6], dims[7]):                                    # ref: residuals.py:286-310
@@ -84,9 +92,10 @@ class CenterNetResidual(torch.nn.Module):
                        torch.nn.BatchNorm2d(c, momentum=BNMOMENTUM), torch.nn.ReLU(inplace=True)]
             cin = c
         self.deconvolutionLayers = torch.nn.Sequential(*layers)
-        self.heatmap = makeResnetTerminal(cin, 128, CLASSDIMENSION)              # ref: centerNetOffset.py:146-148
-        self.regr = makeResnetTerminal(cin, 128, 4)
-        self.offset = makeResnetTerminal(cin, 128, 2)
+        hd = self.terminalDimension
+        self.heatmap = makeResnetTerminal(cin, hd, CLASSDIMENSION)               # ref: centerNetOffset.py:146-148
+        self.regr = makeResnetTerminal(cin, hd, 4)
+        self.offset = makeResnetTerminal(cin, hd, 2)
         self.initialize(numLayers)
         self._blob = None
         self._blob_key = None
@@ -112,6 +121,7 @@ class CenterNetResidual(torch.nn.Module):
         key = (self.precision,) + tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
         if self._blob is None or self._blob_key != key:
             sd = {k: v.detach() for k, v in self.state_dict().items()}
+            self._arch = weights.arch_of(sd)
             self._blob = weights.pack_infer_blob(sd, next(self.parameters()).device,
                                                  torch.float16 if self.precision == "fp16" else torch.bfloat16)
             self._blob_key = key
@@ -128,8 +138,9 @@ class CenterNetResidual(torch.nn.Module):
             ret = training.forward_train(self, inp)
         else:
             with torch.no_grad():
-                heat, regr, off, self._workspace = ops.resnet10_infer(inp.float(), self._infer_blob(),
-                                                                      self._workspace, fp16=self.precision == "fp16")
+                blob = self._infer_blob()
+                heat, regr, off, self._workspace = ops.resnet_infer(inp.float(), blob, self._arch[0], self._arch[2],
+                                                                    self._workspace, fp16=self.precision == "fp16")
             ret = {"heatmap": heat, "regr": regr, "offset": off}
         return [ret] if not decode else self.decoder(ret)
 

@@ -633,7 +633,7 @@ extern "C" int scd_conv_igemm_dgrad(int kind, const void* dz, const void* dz2, c
 
 static int heads_fwd(const void* x, const void* w3, const float* b3, const float* w1,
                      const float* b1, int batch, int height, int width,
-                     float* heat, float* regr, float* offset, void* hidden, void* stream, bool f16 = false)
+                     float* heat, float* regr, float* offset, void* hidden, void* stream, bool f16 = false, int cin = 256)
 {
     using namespace scd;
     if (batch <= 0) return SCD_OK;
@@ -641,12 +641,12 @@ static int heads_fwd(const void* x, const void* w3, const float* b3, const float
         return fail(SCD_EINVAL, "scd_heads_fwd: null pointer");
     IgemmParams p;
     memset(&p, 0, sizeof(p));
-    int rc = fill_geometry(p, 0, x, nullptr, batch, height, width, 256, f16);
+    int rc = fill_geometry(p, 0, x, nullptr, batch, height, width, cin, f16);
     if (rc) return rc;
     p.cout = 384; p.n_tiles_n = 1; p.relu = 1;
     p.total_tiles = batch * p.tiles_y * p.tiles_x;
     p.bias = b3; p.w1 = w1; p.b1 = b1; p.heat = heat; p.regr = regr; p.off = offset;
-    rc = make_w_map(&p.tmB, w3, 9 * 256, 384, IgemmCfg<384>::B_BOX_ROWS, f16);
+    rc = make_w_map(&p.tmB, w3, 9 * cin, 384, IgemmCfg<384>::B_BOX_ROWS, f16);
     if (rc) return rc;
     if (hidden) {
         if ((rc = make_act_map(&p.tmOut[0], hidden, batch, height, width, 384, 1, 0, 0, 2))) return rc;
@@ -671,6 +671,22 @@ extern "C" int scd_heads_fwd_f16(const void* x, const void* w3, const float* b3,
 }
 
 // training forward of the heads: additionally stores hidden = ReLU(conv3x3 + b3), (B,H,W,384) bf16 NHWC
+extern "C" int scd_heads_fwd_c(const void* x, const void* w3, const float* b3, const float* w1,
+                               const float* b1, int batch, int height, int width, int cin,
+                               float* heat, float* regr, float* offset, void* stream)
+{
+    if (cin % 64 || cin < 64 || cin > 512) return scd::fail(SCD_EINVAL, "scd_heads_fwd_c: cin = %d", cin);
+    return heads_fwd(x, w3, b3, w1, b1, batch, height, width, heat, regr, offset, nullptr, stream, false, cin);
+}
+
+extern "C" int scd_heads_fwd_c_f16(const void* x, const void* w3, const float* b3, const float* w1,
+                                   const float* b1, int batch, int height, int width, int cin,
+                                   float* heat, float* regr, float* offset, void* stream)
+{
+    if (cin % 64 || cin < 64 || cin > 512) return scd::fail(SCD_EINVAL, "scd_heads_fwd_c_f16: cin = %d", cin);
+    return heads_fwd(x, w3, b3, w1, b1, batch, height, width, heat, regr, offset, nullptr, stream, true, cin);
+}
+
 extern "C" int scd_heads_fwd_train(const void* x, const void* w3, const float* b3, const float* w1,
                                    const float* b1, int batch, int height, int width,
                                    float* heat, float* regr, float* offset, void* hidden, void* stream)

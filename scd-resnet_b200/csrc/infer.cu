@@ -1,88 +1,189 @@
-// Whole inference pass of CenterNetResidual(numLayers = 10), eval mode, decode=False:
+// Whole inference pass of CenterNetResidual(numLayers in {10, 18, 34}), eval mode, decode=False:
 // ResNet.forward (ref: models/backbones/residuals.py:312-334) as one native call that chains
-// the stem, 14 implicit-GEMM stages and the fused heads on one stream.
+// the stem, the implicit-GEMM stages and the fused heads on one stream.  The stage list is built from the depth
+// (BasicBlock counts of ResNetSpec, ref: models/backbones/residuals.py:20-26 via centerNetOffset.py:152-155) and
+// the eight `dims` of ResNet.__init__ (residuals.py:195-201), rounded up by the host to the 64-channel k-block
+// (the half / quarter-width plugins run zero-padded, scd-resnet_b200/weights.py).
 #include "common.cuh"
 
 namespace scd {
 
 struct ConvSpec { int kind, cin, cout, relu; };
-// order: l1c1 l1c2 | l2ds l2c1 l2c2 | l3ds l3c1 l3c2 | l4ds l4c1 l4c2 | dc1 dc2 dc3
-static const ConvSpec kConvs[14] = {
-    {0, 64, 64, 1},   {0, 64, 64, 1},
-    {2, 64, 128, 0},  {1, 64, 128, 1},  {0, 128, 128, 1},
-    {2, 128, 256, 0}, {1, 128, 256, 1}, {0, 256, 256, 1},
-    {2, 256, 512, 0}, {1, 256, 512, 1}, {0, 512, 512, 1},
-    {3, 512, 256, 1}, {3, 256, 256, 1}, {3, 256, 256, 1},
+struct Step { int conv; int in, res, out; int hin, win; };          // buffer ids; hin = divisor of the INPUT resolution vs (H/4, W/4)
+constexpr int kMaxConvs = 48;                                       // depth 34: 36 + 3 downsamples + 3 deconvs = 39
+
+struct NetPlan {
+    int n_convs;
+    ConvSpec convs[kMaxConvs];
+    Step steps[kMaxConvs];
+    int dims[8];
+    // buffers: 3 per resolution level (levels 0..3 = layer1..4), then e1 e2 e3
+    size_t buf_elems_per_px[15];        // elements per (H/4 * W/4) pixel, times 64 to stay integral
+    int heads_in;                       // buffer id of the heads' input
 };
+
 static int conv_taps(int kind) { return kind == 2 ? 1 : (kind == 3 ? 16 : 9); }
 
-// blob entries: 0 stem_w bf16 (64,64) | 1 stem_b f32 (64) | 2+2i conv_i w bf16 | 3+2i conv_i b f32 |
-//               30 heads w3 bf16 (384, 2304) | 31 b3 f32 (384) | 32 w1 f32 (7,128) | 33 b1 f32 (7)
-constexpr int kNumEntries = 34;
-static void weights_layout(size_t* off, size_t* size)
+static const int kDefaultDims[8] = {64, 64, 128, 256, 512, 256, 256, 256};
+
+static int build_plan(int depth, const int* dims8, NetPlan& pl)
 {
-    size_t sz[kNumEntries];
-    sz[0] = 64 * 64 * 2; sz[1] = 64 * 4;
-    for (int i = 0; i < 14; ++i) {
-        sz[2 + 2 * i] = (size_t)kConvs[i].cout * conv_taps(kConvs[i].kind) * kConvs[i].cin * 2;
-        sz[3 + 2 * i] = (size_t)kConvs[i].cout * 4;
+    int blocks[4];
+    if (depth == 10) { blocks[0] = blocks[1] = blocks[2] = blocks[3] = 1; }
+    else if (depth == 18) { blocks[0] = blocks[1] = blocks[2] = blocks[3] = 2; }
+    else if (depth == 34) { blocks[0] = 3; blocks[1] = 4; blocks[2] = 6; blocks[3] = 3; }
+    else return fail(SCD_EINVAL, "scd_resnet_infer: depth %d is not a BasicBlock network (10, 18 or 34)", depth);
+    const int* d = dims8 ? dims8 : kDefaultDims;
+    for (int i = 0; i < 8; ++i) {
+        if (d[i] <= 0 || d[i] % 64 || d[i] > 512)
+            return fail(SCD_EINVAL, "scd_resnet_infer: dims[%d] = %d must be a multiple of 64 in 64..512 (pad on the host)", i,
+                        d[i]);
+        if (d[i] != 64 && d[i] != 128 && d[i] % 256)
+            return fail(SCD_EINVAL, "scd_resnet_infer: dims[%d] = %d unsupported (64, 128, 256 or 512)", i, d[i]);
+        pl.dims[i] = d[i];
     }
-    sz[30] = (size_t)384 * 2304 * 2; sz[31] = 384 * 4; sz[32] = 7 * 128 * 4; sz[33] = 7 * 4;
+    if (d[0] != 64) return fail(SCD_EINVAL, "scd_resnet_infer: the stem writes 64 channels, dims[0] = %d", d[0]);
+    if (d[1] != d[0]) return fail(SCD_EINVAL, "scd_resnet_infer: layer1 with a projection shortcut (dims[1] != dims[0])");
+    int n = 0;
+    int cin = d[0];
+    int cur = 0;                                                    // buffer holding the running activation (a0)
+    for (int l = 0; l < 4; ++l) {
+        const int c = d[1 + l];
+        const int div = 1 << l;                                     // resolution divisor of this level
+        const int P = 3 * l, T = 3 * l + 1, Q = 3 * l + 2;
+        for (int i = 0; i < 3; ++i) pl.buf_elems_per_px[3 * l + i] = (size_t)c * 64 / ((size_t)div * div);
+        for (int b = 0; b < blocks[l]; ++b) {
+            if (n + 3 > kMaxConvs) return fail(SCD_EINVAL, "scd_resnet_infer: plan overflow");
+            if (b == 0 && l > 0) {
+                // projection block: ds(in) -> P, c1(in) s2 -> T, c2(T) + P -> Q
+                pl.convs[n] = {2, cin, c, 0}; pl.steps[n] = {n, cur, -1, P, div / 2, 0}; ++n;      // read the previous level
+                pl.convs[n] = {1, cin, c, 1}; pl.steps[n] = {n, cur, -1, T, div / 2, 0}; ++n;
+                pl.convs[n] = {0, c, c, 1};   pl.steps[n] = {n, T, P, Q, div, 0}; ++n;
+                cur = Q;
+            } else {
+                // identity block: c1(cur) -> T, c2(T) + cur -> the other of {P, Q}
+                const int in = (b == 0) ? P : cur;                  // layer1 block 0 reads the stem output in P
+                const int out = (in == P) ? Q : P;
+                pl.convs[n] = {0, c, c, 1}; pl.steps[n] = {n, in, -1, T, div, 0}; ++n;
+                pl.convs[n] = {0, c, c, 1}; pl.steps[n] = {n, T, in, out, div, 0}; ++n;
+                cur = out;
+            }
+            cin = c;
+        }
+    }
+    // three deconvs: level 3 -> 2 -> 1 -> 0 resolution
+    for (int i = 0; i < 3; ++i) {
+        const int c = d[5 + i];
+        const int div_in = 8 >> i, div_out = 4 >> i;
+        pl.buf_elems_per_px[12 + i] = (size_t)c * 64 / ((size_t)div_out * div_out);
+        pl.convs[n] = {3, cin, c, 1}; pl.steps[n] = {n, cur, -1, 12 + i, div_in, 0}; ++n;
+        cur = 12 + i; cin = c;
+    }
+    pl.n_convs = n;
+    pl.heads_in = cur;
+    return SCD_OK;
+}
+
+static int n_entries(const NetPlan& pl) { return 2 + 2 * pl.n_convs + 4; }
+
+static void weights_layout(const NetPlan& pl, size_t* off, size_t* size)
+{
+    const int ne = n_entries(pl);
+    size_t sz[2 * kMaxConvs + 6];
+    sz[0] = 64 * 64 * 2; sz[1] = 64 * 4;
+    for (int i = 0; i < pl.n_convs; ++i) {
+        sz[2 + 2 * i] = (size_t)pl.convs[i].cout * conv_taps(pl.convs[i].kind) * pl.convs[i].cin * 2;
+        sz[3 + 2 * i] = (size_t)pl.convs[i].cout * 4;
+    }
+    const int h = 2 + 2 * pl.n_convs;
+    sz[h] = (size_t)384 * 9 * pl.dims[7] * 2; sz[h + 1] = 384 * 4; sz[h + 2] = 7 * 128 * 4; sz[h + 3] = 7 * 4;
     size_t o = 0;
-    for (int i = 0; i < kNumEntries; ++i) {
+    for (int i = 0; i < ne; ++i) {
         if (off) off[i] = o;
         if (size) size[i] = sz[i];
         o += (sz[i] + 255) & ~(size_t)255;
     }
-    if (off) off[kNumEntries] = o;
+    if (off) off[ne] = o;
+}
+
+static size_t workspace_bytes(const NetPlan& pl, int batch, int height, int width)
+{
+    const size_t px = (size_t)(height / 4) * (width / 4);
+    size_t per_img = 0;
+    for (int i = 0; i < 15; ++i) per_img += 2 * (pl.buf_elems_per_px[i] * px / 64);
+    return per_img * (size_t)batch + 4096;
 }
 
 }  // namespace scd
 
-extern "C" size_t scd_infer_weights_bytes(void)
+// ---- plan queries -------------------------------------------------------------------------------------------------
+extern "C" int scd_resnet_num_convs(int depth, const int* dims8)
 {
-    size_t off[scd::kNumEntries + 1];
-    scd::weights_layout(off, nullptr);
-    return off[scd::kNumEntries];
+    scd::NetPlan pl;
+    if (scd::build_plan(depth, dims8, pl)) return -1;
+    return pl.n_convs;
 }
 
-extern "C" int scd_infer_weights_layout(size_t* h_offsets, size_t* h_sizes, int n)
+extern "C" int scd_resnet_conv_specs(int depth, const int* dims8, int* h_kind, int* h_cin, int* h_cout, int n)
 {
-    if (n != scd::kNumEntries || !h_offsets || !h_sizes)
-        return scd::fail(SCD_EINVAL, "scd_infer_weights_layout: expected %d entries", scd::kNumEntries);
-    size_t off[scd::kNumEntries + 1], sz[scd::kNumEntries];
-    scd::weights_layout(off, sz);
+    scd::NetPlan pl;
+    int rc = scd::build_plan(depth, dims8, pl);
+    if (rc) return rc;
+    if (n != pl.n_convs || !h_kind || !h_cin || !h_cout)
+        return scd::fail(SCD_EINVAL, "scd_resnet_conv_specs: expected %d entries", pl.n_convs);
+    for (int i = 0; i < n; ++i) { h_kind[i] = pl.convs[i].kind; h_cin[i] = pl.convs[i].cin; h_cout[i] = pl.convs[i].cout; }
+    return SCD_OK;
+}
+
+extern "C" size_t scd_resnet_weights_bytes(int depth, const int* dims8)
+{
+    scd::NetPlan pl;
+    if (scd::build_plan(depth, dims8, pl)) return 0;
+    size_t off[2 * scd::kMaxConvs + 7];
+    scd::weights_layout(pl, off, nullptr);
+    return off[scd::n_entries(pl)];
+}
+
+extern "C" int scd_resnet_weights_layout(int depth, const int* dims8, size_t* h_offsets, size_t* h_sizes, int n)
+{
+    scd::NetPlan pl;
+    int rc = scd::build_plan(depth, dims8, pl);
+    if (rc) return rc;
+    if (n != scd::n_entries(pl) || !h_offsets || !h_sizes)
+        return scd::fail(SCD_EINVAL, "scd_resnet_weights_layout: expected %d entries", scd::n_entries(pl));
+    size_t off[2 * scd::kMaxConvs + 7], sz[2 * scd::kMaxConvs + 6];
+    scd::weights_layout(pl, off, sz);
     for (int i = 0; i < n; ++i) { h_offsets[i] = off[i]; h_sizes[i] = sz[i]; }
     return SCD_OK;
 }
 
-// activations per image, bf16 NHWC, in units of (H/4 * W/4) pixels:
-//   a0 a1 a2 : 64 ch @ 1     d2 b2 c2 : 128 ch @ 1/4    d3 b3 c3 : 256 ch @ 1/16
-//   d4 b4 c4 : 512 ch @ 1/64 e1 : 256 @ 1/16            e2 : 256 @ 1/4    e3 : 256 @ 1
-extern "C" size_t scd_infer_workspace_bytes(int batch, int height, int width)
+extern "C" size_t scd_resnet_workspace_bytes(int depth, const int* dims8, int batch, int height, int width)
 {
-    const size_t px = (size_t)(height / 4) * (width / 4);
-    const size_t per_img = 2 * (3 * 64 * px + 3 * 128 * px / 4 + 3 * 256 * px / 16 + 3 * 512 * px / 64 +
-                                256 * px / 16 + 256 * px / 4 + 256 * px);
-    return per_img * (size_t)batch + 4096;
+    scd::NetPlan pl;
+    if (scd::build_plan(depth, dims8, pl)) return 0;
+    return scd::workspace_bytes(pl, batch, height, width);
 }
 
-static int resnet10_infer_impl(const float* x, const void* weights, int batch, int height, int width,
-                               float* heat, float* regr, float* offset,
-                               void* workspace, size_t workspace_bytes, void* const* h_stage_events,
-                               void* stream, bool f16)
+// ---- the pass -----------------------------------------------------------------------------------------------------
+extern "C" int scd_resnet_infer(int depth, const int* dims8, int f16, const float* x, const void* weights, int batch,
+                                int height, int width, float* heat, float* regr, float* offset, void* workspace,
+                                size_t workspace_bytes, void* const* h_stage_events, int n_events, void* stream)
 {
     using namespace scd;
+    NetPlan pl;
+    int rc = build_plan(depth, dims8, pl);
+    if (rc) return rc;
     if (batch <= 0) return SCD_OK;
     if (!x || !weights || !heat || !regr || !offset || !workspace)
-        return fail(SCD_EINVAL, "scd_resnet10_infer: null pointer");
+        return fail(SCD_EINVAL, "scd_resnet_infer: null pointer");
     if (height % 256 || width % 512)
-        return fail(SCD_EINVAL, "scd_resnet10_infer: tile must be a multiple of 256 x 512 (H x W), got %dx%d", height,
-                    width);
-    if (workspace_bytes < scd_infer_workspace_bytes(batch, height, width))
-        return fail(SCD_EWORKSPACE, "scd_resnet10_infer: workspace too small");
-    size_t off[kNumEntries + 1];
-    weights_layout(off, nullptr);
+        return fail(SCD_EINVAL, "scd_resnet_infer: tile must be a multiple of 256 x 512 (H x W), got %dx%d", height, width);
+    if (workspace_bytes < scd::workspace_bytes(pl, batch, height, width))
+        return fail(SCD_EWORKSPACE, "scd_resnet_infer: workspace too small");
+    if (h_stage_events && n_events != pl.n_convs + 3)
+        return fail(SCD_EINVAL, "scd_resnet_infer: expected %d stage events", pl.n_convs + 3);
+    size_t off[2 * kMaxConvs + 7];
+    weights_layout(pl, off, nullptr);
     const char* wb = static_cast<const char*>(weights);
     auto W = [&](int e) { return static_cast<const void*>(wb + off[e]); };
     auto Bf = [&](int e) { return reinterpret_cast<const float*>(wb + off[e]); };
@@ -91,42 +192,45 @@ static int resnet10_infer_impl(const float* x, const void* weights, int batch, i
     const size_t px = (size_t)h1 * w1 * batch;
     char* ws = static_cast<char*>(workspace);
     ws = reinterpret_cast<char*>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
-    auto take = [&](size_t elems) { char* r = ws; ws += elems * 2; return static_cast<void*>(r); };
-    void *a0 = take(64 * px), *a1 = take(64 * px), *a2 = take(64 * px);
-    void *d2 = take(128 * px / 4), *b2 = take(128 * px / 4), *c2 = take(128 * px / 4);
-    void *d3 = take(256 * px / 16), *b3 = take(256 * px / 16), *c3 = take(256 * px / 16);
-    void *d4 = take(512 * px / 64), *b4 = take(512 * px / 64), *c4 = take(512 * px / 64);
-    void *e1 = take(256 * px / 16), *e2 = take(256 * px / 4), *e3 = take(256 * px);
+    void* buf[15];
+    for (int i = 0; i < 15; ++i) { buf[i] = ws; ws += 2 * (pl.buf_elems_per_px[i] * px / 64); }
 
     auto mark = [&](int i) -> int {
         if (h_stage_events) SCD_CUDA_CHECK(cudaEventRecord((cudaEvent_t)h_stage_events[i], (cudaStream_t)stream));
         return SCD_OK;
     };
-    int rc = mark(0);
-    if (rc) return rc;
-    rc = f16 ? scd_stem_fwd_f16(x, W(0), Bf(1), batch, height, width, a0, stream)
-             : scd_stem_fwd(x, W(0), Bf(1), batch, height, width, a0, stream);
+    if ((rc = mark(0))) return rc;
+    rc = f16 ? scd_stem_fwd_f16(x, W(0), Bf(1), batch, height, width, buf[0], stream)
+             : scd_stem_fwd(x, W(0), Bf(1), batch, height, width, buf[0], stream);
     if (rc) return rc;
     if ((rc = mark(1))) return rc;
-    struct Step { int conv; const void* in; const void* res; void* out; int hin, win; };
-    const Step steps[14] = {
-        {0, a0, nullptr, a1, h1, w1},         {1, a1, a0, a2, h1, w1},
-        {2, a2, nullptr, d2, h1, w1},         {3, a2, nullptr, b2, h1, w1},         {4, b2, d2, c2, h1 / 2, w1 / 2},
-        {5, c2, nullptr, d3, h1 / 2, w1 / 2}, {6, c2, nullptr, b3, h1 / 2, w1 / 2}, {7, b3, d3, c3, h1 / 4, w1 / 4},
-        {8, c3, nullptr, d4, h1 / 4, w1 / 4}, {9, c3, nullptr, b4, h1 / 4, w1 / 4}, {10, b4, d4, c4, h1 / 8, w1 / 8},
-        {11, c4, nullptr, e1, h1 / 8, w1 / 8}, {12, e1, nullptr, e2, h1 / 4, w1 / 4}, {13, e2, nullptr, e3, h1 / 2, w1 / 2},
-    };
-    for (int i = 0; i < 14; ++i) {
-        const Step& s = steps[i];
-        const ConvSpec& c = kConvs[s.conv];
-        rc = (f16 ? scd_conv_igemm_fwd_f16 : scd_conv_igemm_fwd)(c.kind, s.in, W(2 + 2 * s.conv), Bf(3 + 2 * s.conv), s.res,
-                                                                 c.relu, batch, s.hin, s.win, c.cin, c.cout, s.out, stream);
+    for (int i = 0; i < pl.n_convs; ++i) {
+        const Step& s = pl.steps[i];
+        const ConvSpec& c = pl.convs[s.conv];
+        rc = (f16 ? scd_conv_igemm_fwd_f16 : scd_conv_igemm_fwd)(c.kind, buf[s.in], W(2 + 2 * i), Bf(3 + 2 * i),
+                                                                 s.res >= 0 ? buf[s.res] : nullptr, c.relu, batch,
+                                                                 h1 / s.hin, w1 / s.hin, c.cin, c.cout, buf[s.out], stream);
         if (rc) return rc;
         if ((rc = mark(2 + i))) return rc;
     }
-    rc = (f16 ? scd_heads_fwd_f16 : scd_heads_fwd)(e3, W(30), Bf(31), Bf(32), Bf(33), batch, h1, w1, heat, regr, offset, stream);
+    const int h = 2 + 2 * pl.n_convs;
+    rc = (f16 ? scd_heads_fwd_c_f16 : scd_heads_fwd_c)(buf[pl.heads_in], W(h), Bf(h + 1), Bf(h + 2), Bf(h + 3), batch, h1, w1,
+                                                       pl.dims[7], heat, regr, offset, stream);
     if (rc) return rc;
-    return mark(16);
+    return mark(2 + pl.n_convs);
+}
+
+// ---- CenterNetResidual(numLayers = 10), default widths: the entry points of the headline path ----------------------------
+extern "C" size_t scd_infer_weights_bytes(void) { return scd_resnet_weights_bytes(10, nullptr); }
+
+extern "C" int scd_infer_weights_layout(size_t* h_offsets, size_t* h_sizes, int n)
+{
+    return scd_resnet_weights_layout(10, nullptr, h_offsets, h_sizes, n);
+}
+
+extern "C" size_t scd_infer_workspace_bytes(int batch, int height, int width)
+{
+    return scd_resnet_workspace_bytes(10, nullptr, batch, height, width);
 }
 
 extern "C" int scd_resnet10_infer(const float* x, const void* weights, int batch, int height, int width,
@@ -134,8 +238,8 @@ extern "C" int scd_resnet10_infer(const float* x, const void* weights, int batch
                                   void* workspace, size_t workspace_bytes, void* const* h_stage_events,
                                   void* stream)
 {
-    return resnet10_infer_impl(x, weights, batch, height, width, heat, regr, offset, workspace, workspace_bytes,
-                               h_stage_events, stream, false);
+    return scd_resnet_infer(10, nullptr, 0, x, weights, batch, height, width, heat, regr, offset, workspace, workspace_bytes,
+                            h_stage_events, 17, stream);
 }
 
 // Same pass with fp16 instead of bf16 activations and GEMM operands (the blob's 16-bit entries are fp16).
@@ -144,6 +248,6 @@ extern "C" int scd_resnet10_infer_f16(const float* x, const void* weights, int b
                                       void* workspace, size_t workspace_bytes, void* const* h_stage_events,
                                       void* stream)
 {
-    return resnet10_infer_impl(x, weights, batch, height, width, heat, regr, offset, workspace, workspace_bytes,
-                               h_stage_events, stream, true);
+    return scd_resnet_infer(10, nullptr, 1, x, weights, batch, height, width, heat, regr, offset, workspace, workspace_bytes,
+                            h_stage_events, 17, stream);
 }

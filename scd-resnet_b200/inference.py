@@ -1,7 +1,7 @@
 """Batched tile inference + decode, the path BASELINE config 2 measures (test.py:95-112 per batch).
 
 TileDetector keeps the packed weights, the activation workspace and the output buffers resident, and
-runs   H2D copy -> scd_resnet10_infer -> scd_decode_topk -> D2H copy   with uploads, kernels and downloads on
+runs   H2D copy -> scd_resnet_infer -> scd_decode_topk -> D2H copy   with uploads, kernels and downloads on
 three streams so that the transfer of batch i+1 overlaps the kernels of batch i.
 """
 import torch
@@ -22,9 +22,11 @@ class TileDetector:
         self.device = torch.device(device if device is not None else "cuda")
         self.batch, self.K, self.h, self.w = batch, K, height, width
         with torch.cuda.device(self.device):
+            self.depth, self.dims, self.kdims = weights.arch_of(sd)      # numLayers, widths, kernel-level widths
             self.blob = weights.pack_infer_blob(sd, self.device, torch.float16 if self.fp16 else torch.bfloat16)
-            self.workspace = torch.empty(ops.lib.scd_infer_workspace_bytes(batch, height, width), dtype=torch.uint8,
-                                         device=self.device)
+            self.workspace = torch.empty(ops.lib.scd_resnet_workspace_bytes(self.depth, ops._dims_arg(self.kdims), batch,
+                                                                            height, width),
+                                         dtype=torch.uint8, device=self.device)
             hw = (height // 4, width // 4)
             self.maps = (torch.empty(batch, 1, *hw, device=self.device), torch.empty(batch, 4, *hw, device=self.device),
                          torch.empty(batch, 2, *hw, device=self.device))
@@ -36,13 +38,14 @@ class TileDetector:
             self.in_free = [torch.cuda.Event() for _ in range(2)]
             self.out_ready = [torch.cuda.Event() for _ in range(2)]
             self._host_ring = None
-        self.launches_per_batch = 17      # stem + 14 igemm + heads + decode
+        self.launches_per_batch = len(ops.resnet_conv_specs(self.depth, self.kdims)) + 3     # stem + igemms + heads + decode
 
     def detect_device(self, x, stage_events=None):
         """x (B,1,H,W) f32 on the device -> (10,B,K) f32 planes on the device (current stream)."""
         b = x.shape[0]
         heat, regr, off = [m[:b] for m in self.maps]
-        ops.resnet10_infer(x, self.blob, self.workspace, (heat, regr, off), stage_events, fp16=self.fp16)
+        ops.resnet_infer(x, self.blob, self.depth, self.kdims, self.workspace, (heat, regr, off), stage_events,
+                         fp16=self.fp16)
         return ops.decode_topk(heat, regr, off, K=self.K, planes=True)[6]
 
     def detect_host(self, host_batches):

@@ -289,24 +289,56 @@ def heads_fwd(x, w3, b3, w1, b1):
     return heat, regr, off
 
 
-def infer_weights_layout():
-    n = 34
+def _dims_arg(dims):
+    """Kernel-level channel counts (multiples of 64) as a C int[8], or None for the default widths."""
+    if dims is None:
+        return None
+    if len(dims) != 8:
+        raise ScdError("dims must have 8 entries (ref: models/backbones/residuals.py:195-198)")
+    return (ctypes.c_int * 8)(*[int(d) for d in dims])
+
+
+def resnet_conv_specs(depth=10, dims=None):
+    """[(kind, cin, cout)] of the igemm stages of CenterNetResidual(depth) in blob order (include/scd_b200.h)."""
+    d = _dims_arg(dims)
+    n = lib.scd_resnet_num_convs(depth, d)
+    if n < 0:
+        raise ScdError("unsupported network depth %r / dims %r: %s"
+                       % (depth, dims, lib.scd_last_error().decode("utf-8", "replace")))
+    k, ci, co = (ctypes.c_int * n)(), (ctypes.c_int * n)(), (ctypes.c_int * n)()
+    check(lib.scd_resnet_conv_specs(depth, d, k, ci, co, n), "scd_resnet_conv_specs")
+    return list(zip(k, ci, co))
+
+
+def infer_weights_layout(depth=10, dims=None):
+    d = _dims_arg(dims)
+    nc = lib.scd_resnet_num_convs(depth, d)
+    if nc < 0:
+        raise ScdError("unsupported network depth %r / dims %r: %s"
+                       % (depth, dims, lib.scd_last_error().decode("utf-8", "replace")))
+    n = 2 + 2 * nc + 4
     offs = (ctypes.c_size_t * n)()
     sizes = (ctypes.c_size_t * n)()
-    check(lib.scd_infer_weights_layout(offs, sizes, n), "scd_infer_weights_layout")
-    return list(offs), list(sizes), lib.scd_infer_weights_bytes()
+    check(lib.scd_resnet_weights_layout(depth, d, offs, sizes, n), "scd_resnet_weights_layout")
+    return list(offs), list(sizes), lib.scd_resnet_weights_bytes(depth, d)
 
 
-def resnet10_infer(x, blob, workspace=None, out=None, stage_events=None, fp16=False):
+def resnet_infer(x, blob, depth=10, dims=None, workspace=None, out=None, stage_events=None, fp16=False):
     """ResNet.forward, eval, decode=False (ref: models/backbones/residuals.py:312-334) as one native call.
 
-    x (B,1,H,W) f32; blob = packed BN-folded weights (weights.pack_infer_blob; `fp16` must match the dtype it was
-    packed with).  Returns heat, regr, offset (NCHW f32) and the workspace (reusable).
+    x (B,1,H,W) f32; blob = packed BN-folded weights (weights.pack_infer_blob with the same depth / dims; `fp16`
+    must match the dtype it was packed with).  depth = numLayers (10, 18, 34); dims = kernel-level (padded) widths.
+    Returns heat, regr, offset (NCHW f32) and the workspace (reusable).
     """
     x = _req(x, torch.float32, "x")
     b, c, h, w = x.shape
     dev = x.device
-    nbytes = lib.scd_infer_workspace_bytes(b, h, w)
+    d = _dims_arg(dims)
+    nc = lib.scd_resnet_num_convs(depth, d)
+    if nc < 0:
+        raise ScdError("unsupported network depth %r / dims %r: %s"
+                       % (depth, dims, lib.scd_last_error().decode("utf-8", "replace")))
+    nbytes = lib.scd_resnet_workspace_bytes(depth, d, b, h, w)
     if workspace is None or workspace.numel() < nbytes:
         workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     if out is None:
@@ -314,16 +346,22 @@ def resnet10_infer(x, blob, workspace=None, out=None, stage_events=None, fp16=Fa
                torch.empty(b, 4, h // 4, w // 4, dtype=torch.float32, device=dev),
                torch.empty(b, 2, h // 4, w // 4, dtype=torch.float32, device=dev))
     heat, regr, off = out
-    ev = None
-    if stage_events is not None:       # 17 torch.cuda.Event(enable_timing=True), each recorded once before
-        if len(stage_events) != 17:
-            raise ScdError("stage_events must hold 17 events")
-        ev = (ctypes.c_void_p * 17)(*[e.cuda_event for e in stage_events])
+    ev, n_ev = None, 0
+    if stage_events is not None:       # nc + 3 torch.cuda.Event(enable_timing=True), each recorded once before
+        n_ev = nc + 3
+        if len(stage_events) != n_ev:
+            raise ScdError("stage_events must hold %d events" % n_ev)
+        ev = (ctypes.c_void_p * n_ev)(*[e.cuda_event for e in stage_events])
     with torch.cuda.device(dev):
-        fn = lib.scd_resnet10_infer_f16 if fp16 else lib.scd_resnet10_infer
-        check(fn(_ptr(x), _ptr(blob), b, h, w, _ptr(heat), _ptr(regr), _ptr(off),
-                 _ptr(workspace), workspace.numel(), ev, _stream()), "scd_resnet10_infer")
+        check(lib.scd_resnet_infer(depth, d, 1 if fp16 else 0, _ptr(x), _ptr(blob), b, h, w, _ptr(heat), _ptr(regr),
+                                   _ptr(off), _ptr(workspace), workspace.numel(), ev, n_ev, _stream()),
+              "scd_resnet_infer")
     return heat, regr, off, workspace
+
+
+def resnet10_infer(x, blob, workspace=None, out=None, stage_events=None, fp16=False):
+    """CenterNetResidual(numLayers=10) with the default widths: the headline path (scd_resnet10_infer)."""
+    return resnet_infer(x, blob, 10, None, workspace, out, stage_events, fp16)
 
 
 def slide_geometry(height, width):

@@ -9,19 +9,69 @@ from . import ops
 
 BN_EPS = 1e-5      # torch.nn.BatchNorm2d default (ref: models/backbones/residuals.py:212)
 
-# igemm stages in blob order: (conv key, bn prefix, kind)
-STAGES = [
-    ("layer1.0.conv1", "layer1.0.bn1", 0), ("layer1.0.conv2", "layer1.0.bn2", 0),
-    ("layer2.0.downsample.0", "layer2.0.downsample.1", 2), ("layer2.0.conv1", "layer2.0.bn1", 1),
-    ("layer2.0.conv2", "layer2.0.bn2", 0),
-    ("layer3.0.downsample.0", "layer3.0.downsample.1", 2), ("layer3.0.conv1", "layer3.0.bn1", 1),
-    ("layer3.0.conv2", "layer3.0.bn2", 0),
-    ("layer4.0.downsample.0", "layer4.0.downsample.1", 2), ("layer4.0.conv1", "layer4.0.bn1", 1),
-    ("layer4.0.conv2", "layer4.0.bn2", 0),
-    ("deconvolutionLayers.0", "deconvolutionLayers.1", 3), ("deconvolutionLayers.3", "deconvolutionLayers.4", 3),
-    ("deconvolutionLayers.6", "deconvolutionLayers.7", 3),
-]
+# BasicBlock counts per layer (ref: ResNetSpec, models/backbones/residuals.py:20-26)
+BLOCKS = {10: (1, 1, 1, 1), 18: (2, 2, 2, 2), 34: (3, 4, 6, 3)}
+DEFAULT_DIMS = (64, 64, 128, 256, 512, 256, 256, 256)      # ref: models/backbones/residuals.py:195-201
+
+
+def stages(depth=10):
+    """igemm stages of CenterNetResidual(depth) in blob order: (conv key, bn prefix, kind).  The first block of
+    layers 2-4 has the projection shortcut (ref: ResNet.makeLayer, models/backbones/residuals.py:256-271)."""
+    if depth not in BLOCKS:
+        raise ops.ScdError("numLayers = %r: scd_b200 builds the BasicBlock networks %s (50 / 101 are Bottleneck nets)"
+                           % (depth, sorted(BLOCKS)))
+    out = []
+    for li, nb in enumerate(BLOCKS[depth], 1):
+        for b in range(nb):
+            p = "layer%d.%d" % (li, b)
+            if b == 0 and li > 1:
+                out.append((p + ".downsample.0", p + ".downsample.1", 2))
+                out.append((p + ".conv1", p + ".bn1", 1))
+            else:
+                out.append((p + ".conv1", p + ".bn1", 0))
+            out.append((p + ".conv2", p + ".bn2", 0))
+    for i in range(3):
+        out.append(("deconvolutionLayers.%d" % (3 * i), "deconvolutionLayers.%d" % (3 * i + 1), 3))
+    return out
+
+
+STAGES = stages(10)
 HEADS = ("heatmap", "regr", "offset")     # dict order (ref: models/centerNetOffset.py:165)
+
+
+def pad_width(c):
+    """Channel count the kernels run a `c`-channel tensor at: the 64-channel k-block / N-tile granularity."""
+    for w in (64, 128, 256, 512):
+        if c <= w:
+            return w
+    raise ops.ScdError("%d channels: wider than the kernels' 512" % c)
+
+
+def arch_of(sd):
+    """(depth, dims, padded dims) of a CenterNetResidual state_dict (any of the BasicBlock plugins: Res10 / 18 / 34 and
+    their half / quarter-width versions, ref: trainer/model/centerOffsetRes*.py `modelParams`)."""
+    if any(".conv3." in k for k in sd):
+        raise ops.ScdError("Bottleneck network (numLayers 50 / 101): not built in scd_b200")
+    nb = tuple(len({k.split(".")[1] for k in sd if k.startswith("layer%d." % li)}) for li in range(1, 5))
+    depth = [d for d, b in BLOCKS.items() if b == nb]
+    if not depth:
+        raise ops.ScdError("unrecognised block counts %r" % (nb,))
+    dims = [sd["preprocess.0.weight"].shape[0]] + [sd["layer%d.0.conv1.weight" % li].shape[0] for li in range(1, 5)]
+    dims += [sd["deconvolutionLayers.%d.weight" % (3 * i)].shape[1] for i in range(3)]
+    if sd["heatmap.0.weight"].shape[0] > 128:
+        raise ops.ScdError("head width %d > 128" % sd["heatmap.0.weight"].shape[0])
+    if "layer1.0.downsample.0.weight" in sd:
+        raise ops.ScdError("layer1 with a projection shortcut (dims[1] != dims[0]) is not built")
+    return depth[0], dims, [pad_width(c) for c in dims]
+
+
+def _pad(t, shape):
+    """Zero-pad tensor `t` at the end of every dimension up to `shape`."""
+    if tuple(t.shape) == tuple(shape):
+        return t
+    out = t.new_zeros(shape)
+    out[tuple(slice(0, n) for n in t.shape)] = t
+    return out
 
 
 def bn_scale_shift(sd, prefix):
@@ -71,28 +121,44 @@ def pack_stem(weight, scale=None, dtype=torch.bfloat16):
 
 def fold(sd, dtype=torch.bfloat16):
     """BN-folded, packed tensors of every stage (dict of name -> tensor), for eval-mode inference.
-    dtype: the 16-bit format of the GEMM operands and activations, torch.bfloat16 or torch.float16."""
+    dtype: the 16-bit format of the GEMM operands and activations, torch.bfloat16 or torch.float16.
+    Narrow networks are zero-padded to the kernels' widths (arch_of): a padded output channel has zero weights and a
+    zero bias, hence is exactly 0 after the ReLU, and a padded input channel meets zero weights."""
+    depth, dims, pd = arch_of(sd)
+    specs = ops.resnet_conv_specs(depth, pd)
     out = {}
     s, b = bn_scale_shift(sd, "preprocess.1")
-    out["stem_w"] = pack_stem(sd["preprocess.0.weight"], s, dtype)
-    out["stem_b"] = b.contiguous()
-    for i, (ck, bk, kind) in enumerate(STAGES):
+    out["stem_w"] = pack_stem(_pad(sd["preprocess.0.weight"].float() * s.view(-1, 1, 1, 1), (64, 1, 7, 7)), None, dtype)
+    out["stem_b"] = _pad(b, (64,)).contiguous()
+    for i, ((ck, bk, kind), (skind, cin, cout)) in enumerate(zip(stages(depth), specs)):
+        assert kind == skind
         s, b = bn_scale_shift(sd, bk)
-        out["w%d" % i] = pack_conv(sd[ck + ".weight"], kind, s, dtype)
-        out["b%d" % i] = b.contiguous()
-    out["head_w3"] = torch.cat([pack_conv(sd[h + ".0.weight"], 0, None, dtype) for h in HEADS], 0).contiguous()
-    out["head_b3"] = torch.cat([sd[h + ".0.bias"].float() for h in HEADS], 0).contiguous()
-    out["head_w1"] = torch.cat([sd[h + ".2.weight"].float().reshape(-1, 128) for h in HEADS], 0).contiguous()
+        w = sd[ck + ".weight"].float()
+        if kind == 3:
+            w = _pad(w * s.view(1, -1, 1, 1), (cin, cout, 4, 4))
+        else:
+            w = _pad(w * s.view(-1, 1, 1, 1), (cout, cin) + tuple(w.shape[2:]))
+        out["w%d" % i] = pack_conv(w, kind, None, dtype)
+        out["b%d" % i] = _pad(b, (cout,)).contiguous()
+    cin = pd[7]
+    out["head_w3"] = torch.cat([pack_conv(_pad(sd[h + ".0.weight"].float(), (128, cin, 3, 3)), 0, None, dtype)
+                                for h in HEADS], 0).contiguous()
+    out["head_b3"] = torch.cat([_pad(sd[h + ".0.bias"].float(), (128,)) for h in HEADS], 0).contiguous()
+    out["head_w1"] = torch.cat([_pad(sd[h + ".2.weight"].float().reshape(sd[h + ".2.weight"].shape[0], -1),
+                                     (sd[h + ".2.weight"].shape[0], 128)) for h in HEADS], 0).contiguous()
     out["head_b1"] = torch.cat([sd[h + ".2.bias"].float() for h in HEADS], 0).contiguous()
+    out["n_stages"] = len(specs)
     return out
 
 
 def pack_infer_blob(sd, device, dtype=torch.bfloat16):
-    """The packed parameter blob of scd_resnet10_infer / scd_resnet10_infer_f16 (layout: include/scd_b200.h)."""
+    """The packed parameter blob of scd_resnet_infer (layout: include/scd_b200.h) for the network `sd` describes
+    (depth and widths: arch_of(sd))."""
+    depth, dims, pd = arch_of(sd)
     f = fold(sd, dtype)
-    offs, sizes, total = ops.infer_weights_layout()
+    offs, sizes, total = ops.infer_weights_layout(depth, pd)
     entries = [f["stem_w"], f["stem_b"]]
-    for i in range(len(STAGES)):
+    for i in range(f["n_stages"]):
         entries += [f["w%d" % i], f["b%d" % i]]
     entries += [f["head_w3"], f["head_b3"], f["head_w1"], f["head_b1"]]
     blob = torch.zeros(total, dtype=torch.uint8, device=device)

@@ -124,6 +124,34 @@ def test_model_eval_golden(golden):
     assert w.shape == (10, 2, 100) and rel(w.numpy(), g["wrapper"]) < 1e-5
 
 
+VARIANTS = {"centerOffsetRes18": (18, O.DIMS, 128), "centerOffsetRes34": (34, O.DIMS, 128),
+            "centerOffsetRes10h": (10, [32, 32, 64, 128, 256, 128, 128, 128], 64),
+            "centerOffsetRes10q": (10, [16, 16, 32, 64, 128, 64, 64, 64], 64),
+            "centerOffsetRes18h": (18, [32, 32, 64, 128, 256, 128, 128, 128], 64),
+            "centerOffsetRes34h": (34, [32, 32, 64, 128, 256, 128, 128, 128], 64)}
+
+
+@pytest.mark.parametrize("name", ["centerOffsetRes18", "centerOffsetRes10h", "centerOffsetRes10q", "centerOffsetRes18h",
+                                  "centerOffsetRes34h"])
+def test_variant_forward_golden(golden, name):
+    """the oracle's depth / width generalisation against the reference's own plugin modules
+    (trainer/model/centerOffsetRes*.py run by oracle/make_golden.py)."""
+    g = golden("variants")
+    depth, dims, head_dim = VARIANTS[name]
+    assert int(g[name + "_head_dim"]) == head_dim
+    sd = O.make_state_dict(1234, dims, depth, head_dim)
+    x = O.make_tiles(1, seed=7)[:, :, :256, :]
+    with torch.no_grad():
+        out = O.resnet_forward(sd, x)[0]
+    for key, k in (("heat", "heatmap"), ("regr", "regr"), ("off", "offset")):
+        t = out[k]
+        assert rel(t[:, :, ::4, ::4].numpy(), g["%s_%s_sub" % (name, key)]) < 1e-5
+        assert abs(t.double().sum().item() - g["%s_%s_sum" % (name, key)]) < 1e-5 * g["%s_%s_abs" % (name, key)]
+    if len(np.unique(g[name + "_dec_scores"])) == 100:          # tie-free: indices bit-exact vs the reference's topk
+        sc, idx = O.decode_centernet(out, K=100)[:2]
+        assert np.array_equal(idx.numpy(), g[name + "_dec_idx"])
+
+
 def test_model_train_golden(golden):
     g = golden("model_train")
     sd = O.make_state_dict(1234)
