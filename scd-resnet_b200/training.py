@@ -1,4 +1,4 @@
-"""Training step of centerOffsetRes10 on hand-written sm_100a kernels.
+"""Training step of centerOffsetRes10 (and the full-width Res18 / Res34 plugins) on hand-written sm_100a kernels.
 
 Mirrors NetworkFactory.train (ref: models/networkFactory.py:257-263): zero_grad -> forward with
 batch-statistics BatchNorm (ref: models/backbones/residuals.py:312-334) -> CenterNetLoss
@@ -17,12 +17,26 @@ from . import ops, weights
 from . import train_ops as T
 from ._lib import ScdError
 
-# (name, conv param prefix, bn prefix, kind, cin, cout)
-_BLOCKS = [("layer1", 64, 64, 1), ("layer2", 64, 128, 2), ("layer3", 128, 256, 2), ("layer4", 256, 512, 2)]
-_DECONV = [("deconvolutionLayers.0", "deconvolutionLayers.1", 512, 256),
-           ("deconvolutionLayers.3", "deconvolutionLayers.4", 256, 256),
-           ("deconvolutionLayers.6", "deconvolutionLayers.7", 256, 256)]
 _HEADS = (("heatmap", 0, 1), ("regr", 1, 4), ("offset", 5, 2))
+
+
+def _block_list(depth, dims):
+    """(block prefix, cin, cout, stride) of every BasicBlock (ref: ResNet.makeLayer, residuals.py:256-271)."""
+    out, cin = [], dims[0]
+    for li in range(1, 5):
+        c = dims[li]
+        for b in range(weights.BLOCKS[depth][li - 1]):
+            out.append(("layer%d.%d" % (li, b), cin, c, 2 if (li > 1 and b == 0) else 1))
+            cin = c
+    return out
+
+
+def _deconv_list(dims):
+    out, cin = [], dims[4]
+    for i in range(3):
+        out.append(("deconvolutionLayers.%d" % (3 * i), "deconvolutionLayers.%d" % (3 * i + 1), cin, dims[5 + i]))
+        cin = dims[5 + i]
+    return out
 
 
 class TrainEngine:
@@ -39,6 +53,12 @@ class TrainEngine:
         if dev.type != "cuda":
             raise ScdError("TrainEngine needs the module on a CUDA device")
         self.dev = dev
+        depth, dims, _ = weights.arch_of(module.state_dict())
+        if list(dims) != list(weights.DEFAULT_DIMS) or module.heatmap[0].weight.shape[0] != 128:
+            raise ScdError("TrainEngine: training is built for the full-width networks (Res10 / 18 / 34, dims %r, 128-channel "
+                           "heads); the half / quarter-width plugins run inference only (got dims %r)"
+                           % (list(weights.DEFAULT_DIMS), list(dims)))
+        self.blocks, self.deconvs = _block_list(depth, dims), _deconv_list(dims)
         # ---- flat parameter buffer; head 1x1 weights / biases grouped so the kernels see (7,128), (7), (384)
         order = [k for k in named if not (k.split(".")[0] in ("heatmap", "regr", "offset"))]
         order += [h + ".0.weight" for h, _, _ in _HEADS] + [h + ".0.bias" for h, _, _ in _HEADS]
@@ -116,8 +136,7 @@ class TrainEngine:
             (base + weights.wgrad_index((64, 1, 7, 7), 4)).reshape(-1)
         w_alloc("preprocess.0.weight:fwd", weights.layout_stem(pidx("preprocess.0.weight")))
         bn("preprocess.1")
-        for name, cin, cout, stride in _BLOCKS:
-            p = name + ".0"
+        for p, cin, cout, stride in self.blocks:
             conv(p + ".conv1.weight", 0 if stride == 1 else 1, cin, cout)
             bn(p + ".bn1")
             conv(p + ".conv2.weight", 0, cout, cout)
@@ -130,7 +149,7 @@ class TrainEngine:
                 bn(p + ".downsample.1")
                 w_alloc(p + ".conv1.weight:dgrad",
                         weights.layout_dgrad(pidx(p + ".conv1.weight"), 1, pidx(p + ".downsample.0.weight")))
-        for ck, bk, cin, cout in _DECONV:
+        for ck, bk, cin, cout in self.deconvs:
             conv(ck + ".weight", 3, cin, cout)
             bn(bk)
             w_alloc(ck + ".weight:dgrad", weights.layout_dgrad(pidx(ck + ".weight"), 3))
@@ -217,8 +236,7 @@ class TrainEngine:
         _, ctx0 = self._stem_bn(z0, mod.preprocess[1])
         a, argmax0 = T.stem_bn_relu_pool(z0, ctx0["stat"])
         a0 = a
-        for name, cin, cout, stride in _BLOCKS:
-            p = name + ".0"
+        for p, cin, cout, stride in self.blocks:
             a_in = a
             z1 = self._conv(0 if stride == 1 else 1, a_in, p + ".conv1.weight", cout)
             a1, c1 = self._bn(z1, p + ".bn1")
@@ -231,7 +249,7 @@ class TrainEngine:
             a, c2 = self._bn(z2, p + ".bn2", residual=skip)
             tape.append((p, cin, cout, stride, a_in, z1, a1, c1, z2, c2, zd, cd, a))
         dtape = []
-        for ck, bk, cin, cout in _DECONV:
+        for ck, bk, cin, cout in self.deconvs:
             a_in = a
             z = self._conv(3, a_in, ck + ".weight", cout)
             a, c = self._bn(z, bk)
