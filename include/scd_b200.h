@@ -348,9 +348,11 @@ int scd_scale_inplace(float* x, size_t n, const float* d_scale, void* stream);
  * SCD.__getitem__ (:304-327), for a whole batch.
  *
  * Resident dataset: samples (N,512,512) f32, locs (N,30,8) f32, counts (N) i32.  Batch: index (B) i64 sample
- * ids (the caller checks 0 <= id < N), flips (B,2) u8 = [flip x, flip y] decisions, jitter (B) f32 and noise
+ * ids (an id outside [0, N) is reported in-band: out_counts[b] = -1, tile b untouched), flips (B,2) u8 = [flip x, flip y] decisions, jitter (B) f32 and noise
  * (B,512,512) f32 (nullable) = the N(0,1) draws.  Outputs tiles (B,1,512,512) f32 = ((x - mean)/sqrt(var)) *
  * (1 + jitter_sv * jitter) + noise * noise_sv, out_locs (B,30,8), out_counts (B): what scd_render_targets takes.
+ * One 8-CTA thread-block cluster per sample: the tile is read from HBM once and kept in registers, the statistics
+ * are reduced over the cluster through distributed shared memory.
  * ---------------------------------------------------------------------------------- */
 int scd_augment_batch(const float* samples, const float* locs, const int32_t* counts, int n_samples,
                       const int64_t* index, const uint8_t* flips, const float* jitter, const float* noise,

@@ -4,9 +4,9 @@
 // torch.flip + the object-coordinate fix-ups, normalize (ref: datasets/argumentations.py:39-44), varianceJitter
 // (:62-67) and gaussianNoise (:54-60), and the sample / object-list gather of SCD.__getitem__ (:304-327).
 // In the reference this is host Python per sample (the real bottleneck of its training loop);
-// here the dataset lives in HBM (50 k tiles of 1 MB fit into 180 GB) and one CTA per sample of the batch gathers
-// the tile, takes mean / variance, and writes the flipped, normalised, jittered, noised tile once:
-// HBM-bound, 1 MB read twice (second pass from L2) + 1 MB of noise read + 1 MB written per sample.
+// here the dataset lives in HBM (50 k tiles of 1 MB fit into 180 GB) and one 8-CTA cluster per sample of the batch
+// gathers the tile into registers, takes mean / variance over the cluster, and writes the flipped, normalised, jittered,
+// noised tile once: HBM-bound, 1 MB of tile + 1 MB of noise read + 1 MB written per sample.
 //
 // The random draws are INPUTS (flip decisions, the jitter Gaussian, the noise field), so the result is a pure
 // function that can be checked against the reference replayed with the same draws; tile = ((x - mean) / sqrt(var))
@@ -20,6 +20,8 @@ constexpr int AU_S = 512;             // INPUTSIZE, ref: scdx16p100.py:49
 constexpr int AU_HM = 128;            // HEATMAPSIZE
 constexpr int AU_TAGS = 30;           // MAXTAGLEN
 constexpr int AU_THREADS = 1024;
+constexpr int AU_CL = 8;              // CTAs per sample (one thread-block cluster)
+constexpr int AU_PER = AU_S * AU_S / 4 / AU_CL / AU_THREADS;      // float4 per thread: 8
 
 __device__ __forceinline__ double au_block_sum(double v, double* sh) {
     v = warp_sum(v);
@@ -31,72 +33,116 @@ __device__ __forceinline__ double au_block_sum(double v, double* sh) {
     return t;
 }
 
+// Sum of one double per CTA over the cluster, identical (fixed order) in every CTA: each CTA stores its value into
+// slot `rank` of every peer's shared array through distributed shared memory, then one cluster barrier.
+__device__ __forceinline__ double au_cluster_sum(double v, double* slots, unsigned rank) {
+    if (threadIdx.x < AU_CL) {
+        unsigned local = (unsigned)__cvta_generic_to_shared(slots + rank), remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"((unsigned)threadIdx.x));
+        asm volatile("st.shared::cluster.f64 [%0], %1;" :: "r"(remote), "d"(v) : "memory");
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    double t = 0.0;
+#pragma unroll
+    for (int p = 0; p < AU_CL; ++p) t += slots[p];
+    return t;
+}
+
 // samples (N,512,512) f32, locs (N,30,8) f32, counts (N) i32: the resident dataset.  index (B) i64: the samples of
 // this batch.  flips (B,2) u8: [flip x (dim 2), flip y (dim 1)].  jitter (B) f32: the N(0,1) draw of varianceJitter.
 // noise (B,512,512) f32 N(0,1) draws (nullable: no noise).  -> tiles (B,1,512,512) f32, out_locs (B,30,8), out_counts (B).
-__global__ void __launch_bounds__(AU_THREADS)
+//
+// One cluster of 8 CTAs per sample.  Each CTA keeps its 64 source rows (128 KB) in REGISTERS, 8 float4 per thread, so
+// the tile is read from HBM exactly once; the two statistics (mean, then the variance about that mean, as the
+// reference computes them) are reduced over the cluster through distributed shared memory.
+__global__ void __cluster_dims__(AU_CL, 1, 1) __launch_bounds__(AU_THREADS)
 augment_kernel(const float* __restrict__ samples, const float* __restrict__ locs, const int32_t* __restrict__ counts,
                const int64_t* __restrict__ index, const uint8_t* __restrict__ flips, const float* __restrict__ jitter,
-               const float* __restrict__ noise, float noise_sv, float jitter_sv,
+               const float* __restrict__ noise, float noise_sv, float jitter_sv, int n_samples,
                float* __restrict__ tiles, float* __restrict__ out_locs, int32_t* __restrict__ out_counts)
 {
     __shared__ double sh[AU_THREADS / 32];
-    const int b = blockIdx.x, tid = threadIdx.x;
-    const size_t src_i = (size_t)index[b];
+    __shared__ double slots[2][AU_CL];
+    const int b = blockIdx.x / AU_CL, tid = threadIdx.x;
+    const unsigned rank = blockIdx.x % AU_CL;                // == %cluster_ctarank for a 1-D cluster
+    const int64_t raw_i = index[b];
+    if (raw_i < 0 || raw_i >= (int64_t)n_samples) {          // whole cluster alike: no barrier is left half-joined
+        if (rank == 0 && tid == 0) out_counts[b] = -1;       // reported in-band: the call itself stays asynchronous
+        return;
+    }
+    const size_t src_i = (size_t)raw_i;
     const bool fx = flips[2 * b] != 0, fy = flips[2 * b + 1] != 0;
-    const float4* src = reinterpret_cast<const float4*>(samples + src_i * AU_S * AU_S);
     constexpr int N4 = AU_S * AU_S / 4;
+    const int base = rank * (N4 / AU_CL);                    // this CTA's float4 range of the SOURCE tile
+    const float4* src = reinterpret_cast<const float4*>(samples + src_i * AU_S * AU_S) + base;
+
+    // every CTA of the cluster must be running before its shared memory is written remotely: arrive now, wait below
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    float4 v[AU_PER];
+#pragma unroll
+    for (int k = 0; k < AU_PER; ++k) v[k] = ld_stream(src + k * AU_THREADS + tid);
 
     // object list: gather + flip (scdx16p100.py:424-436); rows beyond the count are passed through (zeros)
-    if (tid < AU_TAGS) {
+    if (rank == 0 && tid < AU_TAGS) {
         const int n = counts[src_i];
         const float* l = locs + (src_i * AU_TAGS + tid) * 8;
-        float v[8];
+        float o[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = l[c];
+        for (int c = 0; c < 8; ++c) o[c] = l[c];
         if (tid < n) {
-            if (fx) { v[0] = (float)(AU_HM - 1) - v[0]; v[2] = -v[2]; v[4] = -v[4]; }
-            if (fy) { v[1] = (float)(AU_HM - 1) - v[1]; v[3] = -v[3]; v[5] = -v[5]; }
+            if (fx) { o[0] = (float)(AU_HM - 1) - o[0]; o[2] = -o[2]; o[4] = -o[4]; }
+            if (fy) { o[1] = (float)(AU_HM - 1) - o[1]; o[3] = -o[3]; o[5] = -o[5]; }
         }
 #pragma unroll
-        for (int c = 0; c < 8; ++c) out_locs[((size_t)b * AU_TAGS + tid) * 8 + c] = v[c];
+        for (int c = 0; c < 8; ++c) out_locs[((size_t)b * AU_TAGS + tid) * 8 + c] = o[c];
         if (tid == 0) out_counts[b] = n;
     }
 
     double s = 0.0;
-    for (int i = tid; i < N4; i += AU_THREADS) {
-        const float4 x = __ldg(src + i);
-        s += ((double)x.x + (double)x.y) + ((double)x.z + (double)x.w);
-    }
-    const float mean = (float)(au_block_sum(s, sh) / (double)(AU_S * AU_S));          // torch.mean
+#pragma unroll
+    for (int k = 0; k < AU_PER; ++k) s += ((double)v[k].x + (double)v[k].y) + ((double)v[k].z + (double)v[k].w);
+    s = au_block_sum(s, sh);
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+    const double s_tile = au_cluster_sum(s, slots[0], rank);
+    const float mean = (float)(s_tile / (double)(AU_S * AU_S));                       // torch.mean
     double q = 0.0;
-    for (int i = tid; i < N4; i += AU_THREADS) {
-        const float4 x = __ldg(src + i);
-        const float d0 = x.x - mean, d1 = x.y - mean, d2 = x.z - mean, d3 = x.w - mean;   // fp32, like tensor - mean
+#pragma unroll
+    for (int k = 0; k < AU_PER; ++k) {
+        const float d0 = v[k].x - mean, d1 = v[k].y - mean, d2 = v[k].z - mean, d3 = v[k].w - mean;   // fp32, like tensor - mean
         q += ((double)(d0 * d0) + (double)(d1 * d1)) + ((double)(d2 * d2) + (double)(d3 * d3));
     }
-    const float var = (float)(au_block_sum(q, sh) / (double)(AU_S * AU_S));            // mean(square(t - mean))
+    const double q_tile = au_cluster_sum(au_block_sum(q, sh), slots[1], rank);
+    const float var = (float)(q_tile / (double)(AU_S * AU_S));                         // mean(square(t - mean))
     const float sd = sqrtf(var);
     const float scale = 1.f + jitter_sv * jitter[b];                                  // varianceJitter
     float4* dst = reinterpret_cast<float4*>(tiles + (size_t)b * AU_S * AU_S);
     const float4* nz = noise ? reinterpret_cast<const float4*>(noise + (size_t)b * AU_S * AU_S) : nullptr;
-    for (int i = tid; i < N4; i += AU_THREADS) {                                       // i = OUTPUT position
-        const int y = i / (AU_S / 4), x4 = i % (AU_S / 4);
-        const int sy = fy ? AU_S - 1 - y : y;
-        const int sx4 = fx ? AU_S / 4 - 1 - x4 : x4;
-        float4 v = __ldg(src + sy * (AU_S / 4) + sx4);
-        if (fx) { const float t0 = v.x, t1 = v.y; v.x = v.w; v.y = v.z; v.z = t1; v.w = t0; }
-        float4 o;
-        o.x = __fmul_rn(__fdiv_rn(v.x - mean, sd), scale);
-        o.y = __fmul_rn(__fdiv_rn(v.y - mean, sd), scale);
-        o.z = __fmul_rn(__fdiv_rn(v.z - mean, sd), scale);
-        o.w = __fmul_rn(__fdiv_rn(v.w - mean, sd), scale);
-        if (nz) {
-            const float4 g = ld_stream(nz + i);
-            o.x = __fadd_rn(o.x, __fmul_rn(g.x, noise_sv)); o.y = __fadd_rn(o.y, __fmul_rn(g.y, noise_sv));
-            o.z = __fadd_rn(o.z, __fmul_rn(g.z, noise_sv)); o.w = __fadd_rn(o.w, __fmul_rn(g.w, noise_sv));
+#pragma unroll
+    for (int h = 0; h < AU_PER; h += 4) {                                              // 4 float4 per step: 64 registers per thread
+        float4 g[4];
+        int di[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                                                  // source position -> output position
+            const int sp = base + (h + k) * AU_THREADS + tid;
+            const int y = sp / (AU_S / 4), x4 = sp % (AU_S / 4);
+            di[k] = (fy ? AU_S - 1 - y : y) * (AU_S / 4) + (fx ? AU_S / 4 - 1 - x4 : x4);
+            if (nz) g[k] = ld_stream(nz + di[k]);
         }
-        __stcs(dst + i, o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float4 x = v[h + k];
+            if (fx) { const float t0 = x.x, t1 = x.y; x.x = x.w; x.y = x.z; x.z = t1; x.w = t0; }
+            float4 o;
+            o.x = __fmul_rn(__fdiv_rn(x.x - mean, sd), scale);
+            o.y = __fmul_rn(__fdiv_rn(x.y - mean, sd), scale);
+            o.z = __fmul_rn(__fdiv_rn(x.z - mean, sd), scale);
+            o.w = __fmul_rn(__fdiv_rn(x.w - mean, sd), scale);
+            if (nz) {
+                o.x = __fadd_rn(o.x, __fmul_rn(g[k].x, noise_sv)); o.y = __fadd_rn(o.y, __fmul_rn(g[k].y, noise_sv));
+                o.z = __fadd_rn(o.z, __fmul_rn(g[k].z, noise_sv)); o.w = __fadd_rn(o.w, __fmul_rn(g[k].w, noise_sv));
+            }
+            __stcs(dst + di[k], o);
+        }
     }
 }
 
@@ -112,8 +158,8 @@ extern "C" int scd_augment_batch(const float* samples, const float* locs, const 
     if (!samples || !locs || !counts || !index || !flips || !jitter || !tiles || !out_locs || !out_counts)
         return fail(SCD_EINVAL, "scd_augment_batch: null pointer");
     if (n_samples <= 0) return fail(SCD_EINVAL, "scd_augment_batch: empty dataset");
-    augment_kernel<<<batch, AU_THREADS, 0, (cudaStream_t)stream>>>(samples, locs, counts, index, flips, jitter, noise,
-                                                                    noise_sv, jitter_sv, tiles, out_locs, out_counts);
+    augment_kernel<<<batch * AU_CL, AU_THREADS, 0, (cudaStream_t)stream>>>(samples, locs, counts, index, flips, jitter, noise,
+                                                                    noise_sv, jitter_sv, n_samples, tiles, out_locs, out_counts);
     SCD_LAUNCH_CHECK("augment_kernel");
     return SCD_OK;
 }

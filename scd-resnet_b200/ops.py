@@ -173,7 +173,8 @@ def augment_batch(samples, locs, counts, index, flips, jitter, noise=None, noise
 
     samples (N,512,512) f32, locs (N,30,8) f32, counts (N) i32 stay on the device; index (B) i64, flips (B,2) bool /
     u8, jitter (B) f32, noise (B,512,512) f32 or None are the batch's sample ids and random draws.
-    Returns (tiles (B,1,512,512) f32, out_locs (B,30,8) f32, out_counts (B) i32)."""
+    Returns (tiles (B,1,512,512) f32, out_locs (B,30,8) f32, out_counts (B) i32); out_counts[b] = -1 marks a sample
+    index outside the dataset."""
     samples = _req(samples, torch.float32, "samples")
     locs = _req(locs, torch.float32, "locs")
     counts = _req(counts, torch.int32, "counts")
@@ -187,8 +188,7 @@ def augment_batch(samples, locs, counts, index, flips, jitter, noise=None, noise
     n, b = samples.shape[0], index.shape[0]
     if tuple(samples.shape[1:]) != (512, 512) or tuple(locs.shape) != (n, MAXTAGLEN, 8) or counts.shape[0] != n:
         raise ScdError("augment_batch: dataset tensors must be (N,512,512), (N,30,8), (N)")
-    if b and (int(index.min()) < 0 or int(index.max()) >= n):
-        raise ScdError("augment_batch: sample index out of range")
+    # an index outside [0, N) is reported in-band (out_counts[b] = -1, tile b untouched): no host sync on this path
     dev = samples.device
     tiles = torch.empty(b, 1, 512, 512, dtype=torch.float32, device=dev)
     out_locs = torch.empty(b, MAXTAGLEN, 8, dtype=torch.float32, device=dev)

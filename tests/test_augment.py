@@ -66,8 +66,10 @@ def test_augment_kernel_matches_oracle(golden):
     z = torch.zeros(n, 2, dtype=torch.bool)
     t0, _, _ = S.ops.augment_batch(s.cuda(), l.cuda(), c.cuda(), torch.arange(n).cuda(), z.cuda(), torch.zeros(n).cuda(), None)
     assert abs(t0.double().mean().item()) < 1e-6 and abs(t0.double().var(unbiased=False).item() * 1.0 - 1.0) < 1e-5
-    with pytest.raises(S.ScdError):
-        S.ops.augment_batch(s.cuda(), l.cuda(), c.cuda(), torch.tensor([n]).cuda(), z[:1].cuda(), torch.zeros(1).cuda(), None)
+    # a sample id outside the dataset is reported in-band (no host sync on the data path): count -1, tile untouched
+    bad = S.ops.augment_batch(s.cuda(), l.cuda(), c.cuda(), torch.tensor([n, 1, -1]).cuda(), z[:3].cuda(),
+                              torch.zeros(3).cuda(), None)
+    assert bad[2].cpu().tolist() == [-1, int(c[1]), -1] and torch.equal(bad[0][1], t0[1])
 
 
 @pytest.mark.gpu
