@@ -293,10 +293,10 @@ int scd_stem_bn_relu_pool(const void* z0, const float* scale, const float* shift
                           void* a0, uint8_t* argmax, void* stream);
 int scd_stem_pool_bwd(const uint8_t* argmax, const void* da0, int batch, int hp, int wp, void* dy0, void* stream);
 
-/* Heads in training: scd_heads_fwd + hidden = ReLU(conv3x3 + b3) stored as (B,H,W,384) bf16;
+/* Heads in training: scd_heads_fwd_c (x has `cin` channels) + hidden = ReLU(conv3x3 + b3) stored as (B,H,W,384) bf16;
  * scd_heads_bwd: d_hidden = (w1^T d_out) * (hidden > 0), and the gradients of w1 (7,128), b1 (7), b3 (384). */
 int scd_heads_fwd_train(const void* x, const void* w3, const float* b3, const float* w1,
-                        const float* b1, int batch, int height, int width,
+                        const float* b1, int batch, int height, int width, int cin,
                         float* heat, float* regr, float* offset, void* hidden, void* stream);
 int scd_heads_bwd(const float* d_heat, const float* d_regr, const float* d_off, const void* hidden,
                   const float* w1, int batch, int height, int width, void* d_hidden, float* g_w1,
@@ -309,17 +309,17 @@ int scd_heads_bwd(const float* d_heat, const float* d_regr, const float* d_off, 
  *                           scd_conv_wgrad / scd_conv_igemm_dgrad with 128 channels), dh_objects (B*max_tags,256)
  *                           f32 = hidden gradient of the regr (0..127) and offset (128..255) heads per object,
  *                           and the gradients of w1 (7,128), b1 (7), b3 (384);
- *   scd_heads_wgrad_sparse  out[tap][co][ci] (9,256,256) f32 = gradient of w3 rows 128..383 (regr, offset heads),
- *                           x = the heads' input (B,H,W,256) bf16;
- *   scd_heads_dgrad_sparse  dx (B,H,W,256) bf16 += dh_objects . w3[128:384] around every object pixel
- *                           (w3 = the (384, 9*256) bf16 forward operand); call after the dense data gradient. */
+ *   scd_heads_wgrad_sparse  out[tap][co][ci] (9,256,cin) f32 = gradient of w3 rows 128..383 (regr, offset heads),
+ *                           x = the heads' input (B,H,W,cin) bf16 (cin = 256 for the full-width networks);
+ *   scd_heads_dgrad_sparse  dx (B,H,W,cin) bf16 += dh_objects . w3[128:384] around every object pixel
+ *                           (w3 = the (384, 9*cin) bf16 forward operand); call after the dense data gradient. */
 int scd_heads_bwd_sparse(const float* d_heat, const float* d_obj, const uint8_t* mask, const int64_t* idx,
                          const void* hidden, const float* w1, int batch, int height, int width, int max_tags,
                          void* d_hidden_heat, float* dh_objects, float* g_w1, float* g_b1, float* g_b3, void* stream);
 int scd_heads_wgrad_sparse(const void* x, const float* dh_objects, const uint8_t* mask, const int64_t* idx,
-                           int batch, int height, int width, int max_tags, float* out, void* stream);
+                           int batch, int height, int width, int max_tags, int cin, float* out, void* stream);
 int scd_heads_dgrad_sparse(const float* dh_objects, const uint8_t* mask, const int64_t* idx, const void* w3,
-                           int batch, int height, int width, int max_tags, void* dx, void* stream);
+                           int batch, int height, int width, int max_tags, int cin, void* dx, void* stream);
 
 /* One-shot all-reduce (sum) of a small fp64 vector over NVLink peer memory: the SyncBatchNorm statistics exchange
  * (models/networkFactory.py:133) without a NCCL launch per BatchNorm.  Every rank owns a symmetric buffer of

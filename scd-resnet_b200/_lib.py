@@ -56,11 +56,11 @@ PROTOTYPES = {
     "scd_stem_conv_train": (c_int, [c_void_p, c_void_p] + [c_int] * 3 + [c_void_p] * 3),
     "scd_stem_bn_relu_pool": (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p, c_void_p, c_void_p]),
     "scd_stem_pool_bwd": (c_int, [c_void_p] * 2 + [c_int] * 3 + [c_void_p, c_void_p]),
-    "scd_heads_fwd_train": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p] * 4 + [c_void_p]),
+    "scd_heads_fwd_train": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p] * 4 + [c_void_p]),
     "scd_heads_bwd": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p] * 4 + [c_void_p]),
     "scd_heads_bwd_sparse": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_void_p] * 5 + [c_void_p]),
-    "scd_heads_wgrad_sparse": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p, c_void_p]),
-    "scd_heads_dgrad_sparse": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p, c_void_p]),
+    "scd_heads_wgrad_sparse": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p, c_void_p]),
+    "scd_heads_dgrad_sparse": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p, c_void_p]),
     "scd_peer_allreduce_buffer_bytes": (c_size_t, [c_int, c_int]),
     "scd_peer_allreduce_f64": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, ctypes.c_uint, c_void_p]),
     "scd_adam_step": (c_int, [c_void_p] * 5 + [c_size_t, c_int] + [c_float] * 5 + [c_void_p]),

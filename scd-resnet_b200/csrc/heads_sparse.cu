@@ -142,12 +142,12 @@ __device__ __forceinline__ int hs_compact(const uint8_t* __restrict__ mask, int 
     return total;
 }
 
-// out[tap][co][ci] = sum_n dh[n][co] * x[pixel_n + off(tap)][ci]     (co, ci < 256; zero padding outside the map)
-// grid (4 ci tiles, 4 co tiles, 9 taps), 256 threads, each a 4 (co) x 4 (ci) register tile of the 64 x 64 CTA tile.
+// out[tap][co][ci] = sum_n dh[n][co] * x[pixel_n + off(tap)][ci]     (co < 256, ci < cin; zero padding outside the map)
+// grid (cin / 64 ci tiles, 4 co tiles, 9 taps), 256 threads, each a 4 (co) x 4 (ci) register tile of the 64 x 64 CTA tile.
 __global__ void __launch_bounds__(256)
 heads_wgrad_objects_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ dh,
                            const uint8_t* __restrict__ mask, const int64_t* __restrict__ idx, int n_obj, int max_tags,
-                           int height, int width, float* __restrict__ out)
+                           int height, int width, int cin, float* __restrict__ out)
 {
     __shared__ float sA[HS_CHUNK][64 + 4];      // dh chunk  [object][co]
     __shared__ float sB[HS_CHUNK][64 + 4];      // x chunk   [object][ci]
@@ -180,7 +180,7 @@ heads_wgrad_objects_kernel(const __nv_bfloat16* __restrict__ x, const float* __r
                     const int yy = p / width + dy, xx = p % width + dx;
                     if (yy >= 0 && yy < height && xx >= 0 && xx < width) {
                         const size_t q = (size_t)(n / max_tags) * hw + (size_t)yy * width + xx;
-                        hs_unpack8(__ldg(reinterpret_cast<const uint4*>(x + q * 256 + ci0 + e)), b);
+                        hs_unpack8(__ldg(reinterpret_cast<const uint4*>(x + q * cin + ci0 + e)), b);
                     }
                 }
 #pragma unroll
@@ -202,17 +202,17 @@ heads_wgrad_objects_kernel(const __nv_bfloat16* __restrict__ x, const float* __r
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-        *reinterpret_cast<float4*>(out + ((size_t)tap * 256 + co0 + tco + i) * 256 + ci0 + tci) =
+        *reinterpret_cast<float4*>(out + ((size_t)tap * 256 + co0 + tco + i) * cin + ci0 + tci) =
             make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
 }
 
-// dx[pixel_n + off(tap)][ci] += sum_co dh[n][co] * w3[128 + co][tap * 256 + ci]
-// grid (4 ci tiles, object blocks of 32, 9 taps), 256 threads: thread -> (object t / 8, 8 consecutive ci).
-// w3 (384, 9 * 256) bf16, K-major forward operand.  dx (B,H,W,256) bf16 already holds the dense part.
+// dx[pixel_n + off(tap)][ci] += sum_co dh[n][co] * w3[128 + co][tap * cin + ci]
+// grid (cin / 64 ci tiles, object blocks of 32, 9 taps), 256 threads: thread -> (object t / 8, 8 consecutive ci).
+// w3 (384, 9 * cin) bf16, K-major forward operand.  dx (B,H,W,cin) bf16 already holds the dense part.
 __global__ void __launch_bounds__(256)
 heads_dgrad_objects_kernel(const float* __restrict__ dh, const uint8_t* __restrict__ mask,
                            const int64_t* __restrict__ idx, const __nv_bfloat16* __restrict__ w3, int n_obj,
-                           int max_tags, int height, int width, __nv_bfloat16* __restrict__ dx)
+                           int max_tags, int height, int width, int cin, __nv_bfloat16* __restrict__ dx)
 {
     __shared__ float sA[HS_CHUNK][32 + 1];      // dh      [object][co chunk of 32]
     __shared__ float sW[32][64 + 4];            // weights [co chunk][ci]
@@ -234,7 +234,7 @@ heads_dgrad_objects_kernel(const float* __restrict__ dh, const uint8_t* __restri
             sA[o][cc] = v.x; sA[o][cc + 1] = v.y; sA[o][cc + 2] = v.z; sA[o][cc + 3] = v.w;
             // weight chunk: 32 co x 64 ci -> thread (co t / 8, 8 ci)
             float wv[8];
-            hs_unpack8(__ldg(reinterpret_cast<const uint4*>(w3 + (size_t)(128 + c0 + o) * 2304 + tap * 256 + ci0 + e)), wv);
+            hs_unpack8(__ldg(reinterpret_cast<const uint4*>(w3 + (size_t)(128 + c0 + o) * (9 * cin) + tap * cin + ci0 + e)), wv);
 #pragma unroll
             for (int k = 0; k < 8; ++k) sW[o][e + k] = wv[k];
         }
@@ -256,7 +256,7 @@ heads_dgrad_objects_kernel(const float* __restrict__ dh, const uint8_t* __restri
     const int yy = p / width + dy, xx = p % width + dxo;
     if (yy < 0 || yy >= height || xx < 0 || xx >= width) return;
     const size_t q = (size_t)(n / max_tags) * height * width + (size_t)yy * width + xx;
-    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(dx + q * 256 + ci0 + e);
+    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(dx + q * cin + ci0 + e);
 #pragma unroll
     for (int k = 0; k < 4; ++k) atomicAdd(dst + k, __floats2bfloat162_rn(acc[2 * k], acc[2 * k + 1]));
 }
@@ -290,26 +290,28 @@ extern "C" int scd_heads_bwd_sparse(const float* d_heat, const float* d_obj, con
 }
 
 extern "C" int scd_heads_wgrad_sparse(const void* x, const float* dh_objects, const uint8_t* mask, const int64_t* idx,
-                                      int batch, int height, int width, int max_tags, float* out, void* stream)
+                                      int batch, int height, int width, int max_tags, int cin, float* out, void* stream)
 {
     using namespace scd;
     if (!x || !dh_objects || !mask || !idx || !out) return fail(SCD_EINVAL, "scd_heads_wgrad_sparse: null pointer");
     if (batch <= 0 || max_tags <= 0) return fail(SCD_EINVAL, "scd_heads_wgrad_sparse: empty batch");
-    heads_wgrad_objects_kernel<<<dim3(4, 4, 9), 256, 0, (cudaStream_t)stream>>>(
-        static_cast<const __nv_bfloat16*>(x), dh_objects, mask, idx, batch * max_tags, max_tags, height, width, out);
+    if (cin < 64 || cin % 64) return fail(SCD_EINVAL, "scd_heads_wgrad_sparse: cin = %d", cin);
+    heads_wgrad_objects_kernel<<<dim3(cin / 64, 4, 9), 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const __nv_bfloat16*>(x), dh_objects, mask, idx, batch * max_tags, max_tags, height, width, cin, out);
     SCD_LAUNCH_CHECK("heads_wgrad_objects_kernel");
     return SCD_OK;
 }
 
 extern "C" int scd_heads_dgrad_sparse(const float* dh_objects, const uint8_t* mask, const int64_t* idx, const void* w3,
-                                      int batch, int height, int width, int max_tags, void* dx, void* stream)
+                                      int batch, int height, int width, int max_tags, int cin, void* dx, void* stream)
 {
     using namespace scd;
     if (!dh_objects || !mask || !idx || !w3 || !dx) return fail(SCD_EINVAL, "scd_heads_dgrad_sparse: null pointer");
     if (batch <= 0 || max_tags <= 0) return fail(SCD_EINVAL, "scd_heads_dgrad_sparse: empty batch");
+    if (cin < 64 || cin % 64) return fail(SCD_EINVAL, "scd_heads_dgrad_sparse: cin = %d", cin);
     const int n_obj = batch * max_tags;
-    heads_dgrad_objects_kernel<<<dim3(4, (n_obj + scd::HS_CHUNK - 1) / scd::HS_CHUNK, 9), 256, 0, (cudaStream_t)stream>>>(
-        dh_objects, mask, idx, static_cast<const __nv_bfloat16*>(w3), n_obj, max_tags, height, width,
+    heads_dgrad_objects_kernel<<<dim3(cin / 64, (n_obj + scd::HS_CHUNK - 1) / scd::HS_CHUNK, 9), 256, 0, (cudaStream_t)stream>>>(
+        dh_objects, mask, idx, static_cast<const __nv_bfloat16*>(w3), n_obj, max_tags, height, width, cin,
         static_cast<__nv_bfloat16*>(dx));
     SCD_LAUNCH_CHECK("heads_dgrad_objects_kernel");
     return SCD_OK;

@@ -688,9 +688,10 @@ extern "C" int scd_heads_fwd_c_f16(const void* x, const void* w3, const float* b
 }
 
 extern "C" int scd_heads_fwd_train(const void* x, const void* w3, const float* b3, const float* w1,
-                                   const float* b1, int batch, int height, int width,
+                                   const float* b1, int batch, int height, int width, int cin,
                                    float* heat, float* regr, float* offset, void* hidden, void* stream)
 {
     if (!hidden) return scd::fail(SCD_EINVAL, "scd_heads_fwd_train: hidden is null");
-    return heads_fwd(x, w3, b3, w1, b1, batch, height, width, heat, regr, offset, hidden, stream);
+    if (cin % 64 || cin < 64 || cin > 512) return scd::fail(SCD_EINVAL, "scd_heads_fwd_train: cin = %d", cin);
+    return heads_fwd(x, w3, b3, w1, b1, batch, height, width, heat, regr, offset, hidden, stream, false, cin);
 }

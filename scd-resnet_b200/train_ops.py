@@ -119,15 +119,15 @@ def stem_pool_bwd(argmax, da0):
 
 
 def heads_fwd_train(x, w3, b3, w1, b1):
-    b, h, w, _ = x.shape
+    b, h, w, cin = x.shape
     dev = x.device
     heat = torch.empty(b, 1, h, w, dtype=torch.float32, device=dev)
     regr = torch.empty(b, 4, h, w, dtype=torch.float32, device=dev)
     off = torch.empty(b, 2, h, w, dtype=torch.float32, device=dev)
     hidden = torch.empty(b, h, w, 384, dtype=torch.bfloat16, device=dev)
     with torch.cuda.device(dev):
-        check(lib.scd_heads_fwd_train(_ptr(x), _ptr(w3), _ptr(b3), _ptr(w1), _ptr(b1), b, h, w, _ptr(heat), _ptr(regr),
-                                      _ptr(off), _ptr(hidden), _stream()), "scd_heads_fwd_train")
+        check(lib.scd_heads_fwd_train(_ptr(x), _ptr(w3), _ptr(b3), _ptr(w1), _ptr(b1), b, h, w, cin, _ptr(heat),
+                                      _ptr(regr), _ptr(off), _ptr(hidden), _stream()), "scd_heads_fwd_train")
     return heat, regr, off, hidden
 
 
@@ -156,23 +156,23 @@ def heads_bwd_sparse(d_heat, d_obj, mask, idx, hidden, w1, g_w1, g_b1, g_b3):
 
 
 def heads_wgrad_sparse(x, dh, mask, idx, out):
-    """out (9,256,256) f32 [tap][co][ci] = gradient of the regr / offset heads' 3x3 weights."""
-    b, h, w, _ = x.shape
+    """out (9,256,cin) f32 [tap][co][ci] = gradient of the regr / offset heads' 3x3 weights."""
+    b, h, w, cin = x.shape
     if mask.dtype == torch.bool:
         mask = mask.contiguous().view(torch.uint8)
     with torch.cuda.device(x.device):
-        check(lib.scd_heads_wgrad_sparse(_ptr(x), _ptr(dh), _ptr(mask), _ptr(idx), b, h, w, mask.shape[1], _ptr(out),
-                                         _stream()), "scd_heads_wgrad_sparse")
+        check(lib.scd_heads_wgrad_sparse(_ptr(x), _ptr(dh), _ptr(mask), _ptr(idx), b, h, w, mask.shape[1], cin,
+                                         _ptr(out), _stream()), "scd_heads_wgrad_sparse")
 
 
 def heads_dgrad_sparse(dh, mask, idx, w3, dx):
-    """dx (B,H,W,256) bf16 += the regr / offset heads' contribution around every object pixel."""
-    b, h, w, _ = dx.shape
+    """dx (B,H,W,cin) bf16 += the regr / offset heads' contribution around every object pixel."""
+    b, h, w, cin = dx.shape
     if mask.dtype == torch.bool:
         mask = mask.contiguous().view(torch.uint8)
     with torch.cuda.device(dx.device):
-        check(lib.scd_heads_dgrad_sparse(_ptr(dh), _ptr(mask), _ptr(idx), _ptr(w3), b, h, w, mask.shape[1], _ptr(dx),
-                                         _stream()), "scd_heads_dgrad_sparse")
+        check(lib.scd_heads_dgrad_sparse(_ptr(dh), _ptr(mask), _ptr(idx), _ptr(w3), b, h, w, mask.shape[1], cin,
+                                         _ptr(dx), _stream()), "scd_heads_dgrad_sparse")
 
 
 def adam_step(params, exp_avg, exp_avg_sq, grads, gmap, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):

@@ -31,6 +31,13 @@ def _block_list(depth, dims):
     return out
 
 
+def _numel(shape):
+    n = 1
+    for d in shape:
+        n *= d
+    return n
+
+
 def _deconv_list(dims):
     out, cin = [], dims[4]
     for i in range(3):
@@ -53,28 +60,50 @@ class TrainEngine:
         if dev.type != "cuda":
             raise ScdError("TrainEngine needs the module on a CUDA device")
         self.dev = dev
-        depth, dims, _ = weights.arch_of(module.state_dict())
-        if list(dims) != list(weights.DEFAULT_DIMS) or module.heatmap[0].weight.shape[0] != 128:
-            raise ScdError("TrainEngine: training is built for the full-width networks (Res10 / 18 / 34, dims %r, 128-channel "
-                           "heads); the half / quarter-width plugins run inference only (got dims %r)"
-                           % (list(weights.DEFAULT_DIMS), list(dims)))
-        self.blocks, self.deconvs = _block_list(depth, dims), _deconv_list(dims)
-        # ---- flat parameter buffer; head 1x1 weights / biases grouped so the kernels see (7,128), (7), (384)
+        depth, dims, kd = weights.arch_of(module.state_dict())
+        self.depth, self.dims, self.kd = depth, list(dims), list(kd)       # kd: the widths the kernels run at (>= 64)
+        self.blocks, self.deconvs = _block_list(depth, kd), _deconv_list(kd)
+        # ---- flat parameter buffer; head 1x1 weights / biases grouped so the kernels see (7,128), (7), (384).
+        # A narrow network (half / quarter-width plugins) is trained zero-padded to the kernels' widths: per-channel
+        # vectors (BatchNorm affine, head biases) and the heads' 1x1 rows are ALLOCATED at the padded width and the
+        # module's parameter is a view of the leading part; conv weights stay in their own shape and are padded by the
+        # operand gather (structural zeros) / read back through the gradient map.  A padded channel has zero weights,
+        # gamma = beta = 0, hence activation 0 and gradient 0 everywhere, and Adam leaves exact zeros in place.
         order = [k for k in named if not (k.split(".")[0] in ("heatmap", "regr", "offset"))]
         order += [h + ".0.weight" for h, _, _ in _HEADS] + [h + ".0.bias" for h, _, _ in _HEADS]
         order += [h + ".2.weight" for h, _, _ in _HEADS] + [h + ".2.bias" for h, _, _ in _HEADS]
         assert sorted(order) == sorted(named)
+        self.alloc = {}                                   # key -> allocated shape inside P
+        bn_modules = {n: m for n, m in module.named_modules() if isinstance(m, torch.nn.BatchNorm2d)}
+        for k in order:
+            shape = tuple(named[k].shape)
+            prefix, leaf = k.rsplit(".", 1)
+            if prefix in bn_modules:
+                shape = (weights.pad_width(shape[0]),)
+            elif k.split(".")[0] in ("heatmap", "regr", "offset"):
+                if k.endswith(".0.bias"):
+                    shape = (128,)
+                elif k.endswith(".2.weight"):
+                    shape = (shape[0], 128)
+            self.alloc[k] = shape
         self.off, n = {}, 0
         for k in order:
             self.off[k] = n
-            n += named[k].numel()
+            n += _numel(self.alloc[k])
         self.n_params = n
-        self.P = torch.empty(n, dtype=torch.float32, device=dev)
+        self.P = torch.zeros(n, dtype=torch.float32, device=dev)
         for k in order:
             p = named[k]
-            view = self.P[self.off[k]:self.off[k] + p.numel()].view_as(p)
+            view = self._param_view(self.P, k, p.shape)
             view.copy_(p.data)
             p.data = view                                  # the module now lives in the flat buffer
+        for prefix, m in bn_modules.items():               # running statistics at the padded width, too
+            C, Cp = m.running_mean.shape[0], weights.pad_width(m.running_mean.shape[0])
+            if Cp != C:
+                rm, rv = torch.zeros(Cp, device=dev), torch.ones(Cp, device=dev)
+                rm[:C].copy_(m.running_mean)
+                rv[:C].copy_(m.running_var)
+                m.running_mean.data, m.running_var.data = rm[:C], rv[:C]
         self.M = torch.zeros_like(self.P)
         self.V = torch.zeros_like(self.P)
         self._build_layouts(named)
@@ -104,9 +133,11 @@ class TrainEngine:
             g_n += (floats + 63) // 64 * 64
             return self.g_off[key]
 
-        def pidx(key):                                    # 1-based indices of a parameter inside P
+        def pidx(key, padded=None):                       # 1-based indices of a parameter inside P, zero-padded to `padded`
             p = named[key]
-            return (torch.arange(p.numel(), dtype=torch.int64) + self.off[key] + 1).view(p.shape)
+            assert self.alloc[key] == tuple(p.shape)       # conv weights: allocated in their own shape
+            t = (torch.arange(p.numel(), dtype=torch.int64) + self.off[key] + 1).view(p.shape)
+            return t if padded is None else weights._pad(t, padded)
 
         def w_alloc(key, index_tensor):
             nonlocal w_n
@@ -116,56 +147,67 @@ class TrainEngine:
             wparts.append((self.wb_off[key][0], flat))
 
         def plain(key):
-            base = g_alloc(key, named[key].numel())
-            gmap[self.off[key]:self.off[key] + named[key].numel()] = base + torch.arange(named[key].numel())
+            n = _numel(self.alloc[key])
+            base = g_alloc(key, n)
+            gmap[self.off[key]:self.off[key] + n] = base + torch.arange(n)
 
         def conv(key, kind, cin, cout, fwd=True):
-            shape = tuple(named[key].shape)
+            """cin, cout: the (padded) widths the kernels run this conv at."""
+            real = tuple(named[key].shape)
+            padded = ((cin, cout) if kind == 3 else (cout, cin)) + real[2:]
             base = g_alloc(key, T.conv_wgrad_floats(kind, cin, cout))
-            gmap[self.off[key]:self.off[key] + named[key].numel()] = (base + weights.wgrad_index(shape, kind)).reshape(-1)
+            gi = weights.wgrad_index(padded, kind)[tuple(slice(0, d) for d in real)]
+            gmap[self.off[key]:self.off[key] + named[key].numel()] = (base + gi).reshape(-1)
             if fwd:
-                w_alloc(key + ":fwd", weights.layout_fwd(pidx(key), kind))
+                w_alloc(key + ":fwd", weights.layout_fwd(pidx(key, padded), kind))
+            return padded
 
         def bn(prefix):
             plain(prefix + ".weight")
             plain(prefix + ".bias")
 
         # stem
+        c0 = named["preprocess.0.weight"].shape[0]
         base = g_alloc("preprocess.0.weight", T.conv_wgrad_floats(4, 64, 64))
-        gmap[self.off["preprocess.0.weight"]:self.off["preprocess.0.weight"] + 64 * 49] = \
-            (base + weights.wgrad_index((64, 1, 7, 7), 4)).reshape(-1)
-        w_alloc("preprocess.0.weight:fwd", weights.layout_stem(pidx("preprocess.0.weight")))
+        gmap[self.off["preprocess.0.weight"]:self.off["preprocess.0.weight"] + c0 * 49] = \
+            (base + weights.wgrad_index((64, 1, 7, 7), 4)[:c0]).reshape(-1)
+        w_alloc("preprocess.0.weight:fwd", weights.layout_stem(pidx("preprocess.0.weight", (64, 1, 7, 7))))
         bn("preprocess.1")
         for p, cin, cout, stride in self.blocks:
-            conv(p + ".conv1.weight", 0 if stride == 1 else 1, cin, cout)
+            pad1 = conv(p + ".conv1.weight", 0 if stride == 1 else 1, cin, cout)
             bn(p + ".bn1")
-            conv(p + ".conv2.weight", 0, cout, cout)
+            pad2 = conv(p + ".conv2.weight", 0, cout, cout)
             bn(p + ".bn2")
-            w_alloc(p + ".conv2.weight:dgrad", weights.layout_dgrad(pidx(p + ".conv2.weight"), 0))
+            w_alloc(p + ".conv2.weight:dgrad", weights.layout_dgrad(pidx(p + ".conv2.weight", pad2), 0))
             if stride == 1:
-                w_alloc(p + ".conv1.weight:dgrad", weights.layout_dgrad(pidx(p + ".conv1.weight"), 0))
+                w_alloc(p + ".conv1.weight:dgrad", weights.layout_dgrad(pidx(p + ".conv1.weight", pad1), 0))
             else:
-                conv(p + ".downsample.0.weight", 2, cin, cout)
+                padd = conv(p + ".downsample.0.weight", 2, cin, cout)
                 bn(p + ".downsample.1")
                 w_alloc(p + ".conv1.weight:dgrad",
-                        weights.layout_dgrad(pidx(p + ".conv1.weight"), 1, pidx(p + ".downsample.0.weight")))
+                        weights.layout_dgrad(pidx(p + ".conv1.weight", pad1), 1, pidx(p + ".downsample.0.weight", padd)))
         for ck, bk, cin, cout in self.deconvs:
-            conv(ck + ".weight", 3, cin, cout)
+            padc = conv(ck + ".weight", 3, cin, cout)
             bn(bk)
-            w_alloc(ck + ".weight:dgrad", weights.layout_dgrad(pidx(ck + ".weight"), 3))
+            w_alloc(ck + ".weight:dgrad", weights.layout_dgrad(pidx(ck + ".weight", padc), 3))
         # heads: the three 3x3 convs run as one conv with 384 output channels in the forward pass.  Backward: the
         # heat head (dense gradient) goes through the tensor-core wgrad / dgrad with 128 channels; the regr and
         # offset heads have a hidden gradient at the object pixels only (csrc/heads_sparse.cu), their weight
         # gradient is laid out [tap][co][ci] with co = 0..127 regr, 128..255 offset.
-        w3_idx = torch.cat([pidx(h + ".0.weight") for h, _, _ in _HEADS], 0)          # (384,256,3,3) of P indices
-        base = g_alloc("heads.w3h", T.conv_wgrad_floats(0, 256, 128))
+        hc = self.kd[7]                                                                 # channels of the heads' input
+        hd = named["heatmap.0.weight"].shape[0]                                         # head width: 128, or 64 (h / q)
+        ci_real = named["heatmap.0.weight"].shape[1]
+        w3_idx = torch.cat([pidx(h + ".0.weight", (128, hc, 3, 3)) for h, _, _ in _HEADS], 0)   # (384,hc,3,3) of P indices
+        base = g_alloc("heads.w3h", T.conv_wgrad_floats(0, hc, 128))
         k = "heatmap.0.weight"
-        gmap[self.off[k]:self.off[k] + named[k].numel()] = (base + weights.wgrad_index((128, 256, 3, 3), 0)).reshape(-1)
-        base = g_alloc("heads.w3s", 9 * 256 * 256)
-        co, ci, r, s_ = torch.meshgrid(torch.arange(128), torch.arange(256), torch.arange(3), torch.arange(3), indexing="ij")
+        gmap[self.off[k]:self.off[k] + named[k].numel()] = \
+            (base + weights.wgrad_index((128, hc, 3, 3), 0)[:hd, :ci_real]).reshape(-1)
+        base = g_alloc("heads.w3s", 9 * 256 * hc)
+        co, ci, r, s_ = torch.meshgrid(torch.arange(hd), torch.arange(ci_real), torch.arange(3), torch.arange(3),
+                                       indexing="ij")
         for i, k in enumerate(("regr.0.weight", "offset.0.weight")):
             gmap[self.off[k]:self.off[k] + named[k].numel()] = \
-                (base + ((r * 3 + s_) * 256 + (co + 128 * i)) * 256 + ci).reshape(-1)
+                (base + ((r * 3 + s_) * 256 + (co + 128 * i)) * hc + ci).reshape(-1)
         w_alloc("heads.w3:fwd", weights.layout_fwd(w3_idx, 0))
         w_alloc("heads.w3h:dgrad", weights.layout_dgrad(w3_idx[:128], 0))
         b3 = g_alloc("heads.b3", 384)
@@ -183,6 +225,16 @@ class TrainEngine:
             wmap[o:o + flat.numel()] = flat
         self.wmap = wmap.to(torch.int32).to(self.dev)
         self.WB = torch.empty(w_n, dtype=torch.bfloat16, device=self.dev)
+
+    def _param_view(self, flat, key, shape):
+        """The view of parameter `key` (reference shape `shape`) inside a flat buffer laid out like P."""
+        a = self.alloc[key]
+        t = flat[self.off[key]:self.off[key] + _numel(a)].view(a)
+        if a == tuple(shape):
+            return t
+        if len(a) == 1:                                   # per-channel vector allocated at the padded width
+            return t[:shape[0]]
+        return t[:, :shape[1]].unsqueeze(-1).unsqueeze(-1)       # head 1x1 weight: rows of 128, (nj, hd, 1, 1) in the module
 
     def wb(self, key):
         o, shape = self.wb_off[key]
@@ -269,9 +321,10 @@ class TrainEngine:
         # ---- backward ----------------------------------------------------------------------------------
         d_hh, dh_obj = T.heads_bwd_sparse(d_heat, d_obj, mask, gidx, hidden, w1, self.g("heads.w1"), self.g("heads.b1"),
                                           self.g("heads.b3"))
-        T.conv_wgrad(0, e3, d_hh, 256, 128, self.g("heads.w3h"))
+        hc = self.kd[7]
+        T.conv_wgrad(0, e3, d_hh, hc, 128, self.g("heads.w3h"))
         T.heads_wgrad_sparse(e3, dh_obj, mask, gidx, self.g("heads.w3s"))
-        da = T.conv_dgrad(0, d_hh, self.wb("heads.w3h:dgrad"), self.zero_bias[:256], 256)
+        da = T.conv_dgrad(0, d_hh, self.wb("heads.w3h:dgrad"), self.zero_bias[:hc], hc)
         T.heads_dgrad_sparse(dh_obj, mask, gidx, self.wb("heads.w3:fwd"), da)
         for ck, bk, cin, cout, a_in, z, c, a_out in reversed(dtape):
             dz, _ = self._bn_bwd(da, None, z, c, bk, relu_from_z=True)       # conv -> BN -> ReLU, no residual
@@ -333,7 +386,7 @@ class TrainEngine:
     def grads_reference_layout(self):
         """{name: gradient tensor in the parameter's own layout} (diagnostics / interop; not on the hot path)."""
         g = self.G[self.gmap.long()]
-        return {k: g[self.off[k]:self.off[k] + p.numel()].view_as(p) for k, p in self.module.named_parameters()}
+        return {k: self._param_view(g, k, p.shape) for k, p in self.module.named_parameters()}
 
 
 def forward_train(module, x):
