@@ -39,7 +39,7 @@ for name in NAMES:
     ms = timed(step)
     rec = {"variant": name, "batch": B, "infer_decode_ms": round(ms, 4), "tiles_per_s": round(B / ms * 1e3, 1),
            "launches": det.launches_per_batch, "kernel_dims": det.kdims}
-    if p.modelParams["dims"][0] == 64:
+    if True:
         model.train()
         eng = TrainEngine(model)
         TB = 32
