@@ -390,7 +390,7 @@ def main():
                              "value": sps, "unit": "samples/s", "ms_per_step": train_ms / args.train_steps,
                              "steps": args.train_steps, "batch_per_gpu": args.train_batch,
                              "step": "render targets + fwd (batch-stat BN) + focal/L1 loss + bwd + Adam",
-                             "grad_sync": ("NCCL all-reduce of the flat fp32 gradient; BN statistics: "
+                             "grad_sync": ("NCCL all-reduce of the flat fp32 gradient in 3 ranges started during the backward pass; BN statistics: "
                                            + ("one-shot NVLink peer-memory all-reduce kernel" if eng.peer is not None
                                               else "NCCL all-reduce (%s)" % eng.peer_reason)) if world > 1 else "none",
                              "tflops": 147.5e9 * args.train_batch / (train_ms / args.train_steps * 1e-3) / 1e12,

@@ -104,6 +104,7 @@ class TrainEngine:
                 rm[:C].copy_(m.running_mean)
                 rv[:C].copy_(m.running_var)
                 m.running_mean.data, m.running_var.data = rm[:C], rv[:C]
+        self._pending, self._reduced_from = [], 0          # gradient all-reduces in flight / lowest G index covered
         self.M = torch.zeros_like(self.P)
         self.V = torch.zeros_like(self.P)
         self._build_layouts(named)
@@ -218,6 +219,7 @@ class TrainEngine:
             gmap[self.off[h + ".2.weight"]:self.off[h + ".2.weight"] + nj * 128] = w1 + j0 * 128 + torch.arange(nj * 128)
             gmap[self.off[h + ".2.bias"]:self.off[h + ".2.bias"] + nj] = b1 + j0 + torch.arange(nj)
         self.n_grads = g_n
+        self._reduced_from = g_n
         self.G = torch.zeros(g_n, dtype=torch.float32, device=self.dev)
         self.gmap = gmap.to(torch.int32).to(self.dev)
         wmap = torch.full((w_n,), -1, dtype=torch.int64)
@@ -281,6 +283,9 @@ class TrainEngine:
         (+ optionally the two device counters of ops.render_targets(with_npos=True)).
         Returns (losses f32[4] on the device, outputs dict); gradients land in self.G."""
         mod = self.module
+        for w in self._pending:                            # a backward pass that was not followed by optimizer_step
+            w.wait()
+        self._pending, self._reduced_from = [], self.n_grads
         self.G.zero_()
         tape = []
         # ---- forward -----------------------------------------------------------------------------------
@@ -330,6 +335,7 @@ class TrainEngine:
             dz, _ = self._bn_bwd(da, None, z, c, bk, relu_from_z=True)       # conv -> BN -> ReLU, no residual
             T.conv_wgrad(3, a_in, dz, cin, cout, self.g(ck + ".weight"))
             da = T.conv_dgrad(3, dz, self.wb(ck + ".weight:dgrad"), self.zero_bias[:cin], cin)
+        self._reduce_async(self.g_off[self.deconvs[0][0] + ".weight"], self.n_grads)          # deconvs + heads are final
         for p, cin, cout, stride, a_in, z1, a1, c1, z2, c2, zd, cd, a_out in reversed(tape):
             dz2, dy = self._bn_bwd(da, a_out, z2, c2, p + ".bn2", want_dy=True)
             T.conv_wgrad(0, a1, dz2, cout, cout, self.g(p + ".conv2.weight"))
@@ -343,6 +349,8 @@ class TrainEngine:
                 T.conv_wgrad(1, a_in, dz1, cin, cout, self.g(p + ".conv1.weight"))
                 T.conv_wgrad(2, a_in, dzd, cin, cout, self.g(p + ".downsample.0.weight"))
                 da = T.conv_dgrad(1, dz1, self.wb(p + ".conv1.weight:dgrad"), self.zero_bias[:cin], cin, dz2=dzd)
+            if p == "layer3.0":                                                               # layer3 + layer4 are final
+                self._reduce_async(self.g_off["layer3.0.conv1.weight"], self._reduced_from)
         dy0 = T.stem_pool_bwd(argmax0, da)
         dz0, _ = T.bn_backward(dy0, None, z0, ctx0, False, self.g("preprocess.1.weight"), self.g("preprocess.1.bias"),
                                all_reduce=self._allreduce_stats if self.world > 1 else None)
@@ -365,10 +373,22 @@ class TrainEngine:
         return None, {"stat": stat, "count": count, "sums": sums}
 
     # ------------------------------------------------------------------ optimiser
+    def _reduce_async(self, lo, hi):
+        """Start the gradient all-reduce of G[lo:hi] (a range whose weight gradients are final) while the backward pass
+        goes on: NCCL runs it on its own stream, ordered after what this stream has written so far."""
+        if self.world > 1 and hi > lo:
+            self._pending.append(torch.distributed.all_reduce(self.G[lo:hi], group=self.group, async_op=True))
+            self._reduced_from = min(self._reduced_from, lo)
+
     def optimizer_step(self):
-        """DDP semantics (ref: models/networkFactory.py:134): gradients are averaged over ranks, then Adam."""
+        """DDP semantics (ref: models/networkFactory.py:134): gradients are averaged over ranks, then Adam.
+        The deconv + heads range and the layer3-4 range were started during the backward pass (forward_backward); what is
+        left here is the stem .. layer2 range (12 % of the parameters)."""
         if self.world > 1:
-            torch.distributed.all_reduce(self.G, group=self.group)
+            self._reduce_async(0, min(self._reduced_from, self.n_grads))
+            for w in self._pending:
+                w.wait()                                   # this stream waits for the collectives, not the host
+            self._pending, self._reduced_from = [], self.n_grads
         self.step_count += 1
         T.adam_step(self.P, self.M, self.V, self.G, self.gmap, self.step_count, self.lr, self.betas, self.eps,
                     1.0 / self.world)
