@@ -24,170 +24,11 @@ constexpr int ST_MT = 3;                     // M tiles of 128 rows
 constexpr int ST_PS = ST_C + 3;              // 20x20 s2d pixels of input under the conv tile
 constexpr int ST_THREADS = 256;
 constexpr int ST_CO = 64;
-constexpr int ST_TMEM_COLS = 256;            // 3 x 64 accumulator columns, power of two
-
-// shared memory map (byte offsets from a 1024-aligned base)
-constexpr int ST_OFF_A = 0;                                   // 3 x 16 KB im2col tiles; later the conv tile
-constexpr int ST_OFF_B = ST_MT * 16384;                       // 8 KB weights (64 x 64 bf16, swizzled by TMA)
-constexpr int ST_OFF_PATCH = ST_OFF_B + 8192;                 // 20 x 20 x 4 bf16
-constexpr int ST_OFF_BAR = ST_OFF_PATCH + ST_PS * ST_PS * 8 + 64;   // +64: chunk reads run 8 B past the end
-constexpr int ST_SMEM = ST_OFF_BAR + 64 + 1024;
-
-template <bool F16>
-__global__ void __launch_bounds__(ST_THREADS, 2)
-stem_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ x,
-               const float* __restrict__ bias, int height, int width, __nv_bfloat16* __restrict__ y)
-{
-    using A16 = tc::Act<F16>;        // y is bf16 or fp16 (same size); the pointer type is nominal
-    extern __shared__ unsigned char smem_dyn[];
-    const uint32_t sbase = (tc::smem_u32(smem_dyn) + 1023u) & ~1023u;
-    unsigned char* sgen = smem_dyn + (sbase - tc::smem_u32(smem_dyn));
-    const uint32_t bar_w = sbase + ST_OFF_BAR, bar_mma = bar_w + 8, tmem_slot = bar_w + 16;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    const int hp = height / 4, wp = width / 4, hc = height / 2, wc = width / 2;
-    const int tiles_x = wp / ST_P;
-    const int b = blockIdx.y;
-    const int py0 = (blockIdx.x / tiles_x) * ST_P, px0 = (blockIdx.x % tiles_x) * ST_P;
-    const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;      // first conv row / col under the pool tile
-    const int Y0 = cy0 - 2, X0 = cx0 - 2;                // first s2d row / col under that (iy = 2Y + py)
-
-    if (tid == 0) {
-        tc::mbar_init(bar_w, 1);
-        tc::mbar_init(bar_mma, 1);
-        tc::fence_barrier_init();
-        tc::mbar_arrive_expect_tx(bar_w, 8192);
-        tc::tma_load_2d(&tmW, bar_w, sbase + ST_OFF_B, 0, 0);
-    }
-    if (warp == 1) tc::tmem_alloc<ST_TMEM_COLS>(tmem_slot);
-
-    // ---- stage the input patch as s2d bf16: patch[Y][X][py][px] -------------------------------
-    {
-        const float* xb = x + (size_t)b * height * width;
-        uint32_t* patch = reinterpret_cast<uint32_t*>(sgen + ST_OFF_PATCH);
-        for (int i = tid; i < 2 * ST_PS * ST_PS; i += ST_THREADS) {      // one (iy, X) pixel pair each
-            const int X = i % ST_PS, ry = i / ST_PS;                      // ry = 2*Ylocal + py
-            const int iy = 2 * Y0 + ry, ix = 2 * (X0 + X);
-            float2 v = make_float2(0.f, 0.f);                             // conv zero padding
-            if (iy >= 0 && iy < height && ix >= 0 && ix < width)
-                v = *reinterpret_cast<const float2*>(xb + (size_t)iy * width + ix);
-            patch[((ry >> 1) * ST_PS + X) * 2 + (ry & 1)] = A16::pack(v.x, v.y);
-        }
-        if (tid < 16) patch[ST_PS * ST_PS * 2 + tid] = 0u;               // slack read by the last chunk
-    }
-    __syncthreads();
-
-    // ---- im2col: A[row][k], k = (dy*4 + dx)*4 + py*2 + px, 128 B rows, 128-byte swizzle --------
-    {
-        const unsigned char* patch = sgen + ST_OFF_PATCH;
-        for (int it = tid; it < ST_MT * 128 * 8; it += ST_THREADS) {
-            const int j = it & 7, row = it >> 3;
-            const int pos = row < ST_NPOS ? row : ST_NPOS - 1;           // padded rows: any in-bounds source
-            const int r = pos / ST_C, c = pos % ST_C;
-            const int dy = j >> 1, dx0 = (j & 1) * 2;
-            const unsigned char* src = patch + ((r + dy) * ST_PS + c + dx0) * 8;
-            const uint2 lo = *reinterpret_cast<const uint2*>(src);
-            const uint2 hi = *reinterpret_cast<const uint2*>(src + 8);
-            uint4 v = make_uint4(lo.x, lo.y, hi.x, hi.y);
-            *reinterpret_cast<uint4*>(sgen + ST_OFF_A + row * 128 + ((j ^ (row & 7)) << 4)) = v;
-        }
-    }
-    // generic-proxy writes above must be visible to the tensor core (async proxy)
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<const uint32_t*>(sgen + ST_OFF_BAR + 16);
-
-    if (tid == 0) {
-        tc::mbar_wait(bar_w, 0);                                          // weights landed
-        tc::tc_fence_after();
-        constexpr uint32_t idesc = tc::umma_idesc_16(128, ST_CO, A16::kFmt);
-#pragma unroll
-        for (int m = 0; m < ST_MT; ++m)
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                tc::umma_bf16(tmem_base + m * ST_CO, tc::umma_desc_sw128(sbase + ST_OFF_A + m * 16384 + k * 32),
-                              tc::umma_desc_sw128(sbase + ST_OFF_B + k * 32), idesc, k ? 1u : 0u);
-        tc::umma_commit(bar_mma);
-    }
-    __syncwarp();
-    tc::mbar_wait(bar_mma, 0);                                            // all 12 MMAs retired: A is dead
-    tc::tc_fence_after();
-
-    // ---- epilogue: TMEM -> +bias, ReLU -> bf16 conv tile in smem (over the A tiles) ------------
-    // warp w reads TMEM lanes 32*(w%4)..; warps 0-3 take M tiles 0 and 2, warps 4-7 take M tile 1
-    {
-        const int q = warp & 3;
-        for (int m = (warp >> 2); m < ST_MT; m += 2) {
-            const int row = m * 128 + q * 32 + lane;
-            uint32_t r0[32], r1[32];
-            const uint32_t taddr = tmem_base + m * ST_CO + ((uint32_t)(q * 32) << 16);
-            tc::tmem_ld32(taddr, r0);
-            tc::tmem_ld32(taddr + 32, r1);
-            tc::tmem_ld_wait();
-            if (row < ST_NPOS) {
-                const int cy = cy0 + row / ST_C, cx = cx0 + row % ST_C;
-                // conv positions outside the map are max-pool padding; post-ReLU values are >= 0 so 0 == -inf
-                const bool valid = cy >= 0 && cy < hc && cx >= 0 && cx < wc;
-                unsigned char* dst = sgen + ST_OFF_A + row * 128;
-#pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                    uint32_t o[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int cidx = ch * 8 + 2 * i;
-                        const float a = __uint_as_float(cidx < 32 ? r0[cidx] : r1[cidx - 32]) + __ldg(bias + cidx);
-                        const float d = __uint_as_float(cidx < 32 ? r0[cidx + 1] : r1[cidx - 31]) + __ldg(bias + cidx + 1);
-                        o[i] = valid ? A16::pack(fmaxf(a, 0.f), fmaxf(d, 0.f)) : 0u;
-                    }
-                    *reinterpret_cast<uint4*>(dst + ((ch ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-                }
-            }
-        }
-    }
-    tc::tc_fence_before();
-    __syncthreads();
-
-    // ---- 3x3 s2 max pool, NHWC bf16 store: thread = (pool pixel, 16-channel quarter) -----------
-    {
-        const int quarter = tid & 3, pos = tid >> 2;                      // 64 pool pixels x 4 quarters
-        const int pyl = pos / ST_P, pxl = pos % ST_P;
-        uint32_t m[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) m[c] = 0u;                            // +0.0 in either format
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-                const int row = (2 * pyl + dy) * ST_C + 2 * pxl + dx;
-                const unsigned char* src = sgen + ST_OFF_A + row * 128;
-#pragma unroll
-                for (int hch = 0; hch < 2; ++hch) {
-                    const int ch = quarter * 2 + hch;
-                    const uint4 u = *reinterpret_cast<const uint4*>(src + ((ch ^ (row & 7)) << 4));
-                    const uint32_t h2[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) m[hch * 4 + c] = A16::max2(m[hch * 4 + c], h2[c]);
-                }
-            }
-        uint4* dst = reinterpret_cast<uint4*>(y + (((size_t)b * hp + py0 + pyl) * wp + px0 + pxl) * ST_CO + quarter * 16);
-        dst[0] = make_uint4(m[0], m[1], m[2], m[3]);
-        dst[1] = make_uint4(m[4], m[5], m[6], m[7]);
-    }
-    __syncthreads();
-    if (warp == 1) {
-        tc::tc_fence_after();
-        tc::tmem_dealloc<ST_TMEM_COLS>(tmem_base);
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
-// Persistent, warp-specialised version of the same computation (the one scd_stem_fwd launches).
-// stem_tc_kernel above runs one 8x8 pool tile per CTA as a chain of phases (stage patch -> im2col -> MMA ->
-// epilogue -> pool) separated by block barriers: 16 k CTAs of ~7 us each, tensor pipe 6 % busy, issue slots 18 %
-// (ncu, profiles/ncu_full_r01_b.json).  Here one CTA per SM walks its tiles with three roles running
-// concurrently on different tiles:
+// Persistent, warp-specialised kernel.  (Its predecessor ran one 8x8 pool tile per CTA as a chain of phases - stage
+// patch -> im2col -> MMA -> epilogue -> pool - separated by block barriers: 16 k CTAs of ~7 us each, tensor pipe 6 %
+// busy, 0.43 ms per 64 tiles.)  Here CTAs walk their tiles with three roles running concurrently on different tiles:
 //   warps 0-3  loaders   global patch (prefetched one tile ahead in registers) -> s2d patch in smem -> im2col A tile
 //   warp  4    MMA       12 x tcgen05.mma per tile into one of two TMEM accumulator stages
 //   warps 5-8  epilogue  TMEM -> +bias, ReLU -> 16-bit conv tile (over the consumed A tile) -> 3x3 s2 max pool -> HBM
