@@ -57,9 +57,9 @@ int scd_decode_topk(const float* heat, const float* regr, const float* offset,
                     float* scores, int64_t* idx, int64_t* ys, int64_t* xs,
                     float* off_out, float* regr_out, float* planes, void* stream);
 
-/* Same with an explicit kernel choice: impl 0 = by batch size (what scd_decode_topk does), 1 = one CTA per
- * image (lowest latency, for a few hundred images or fewer), 2 = one warp per image (highest throughput).
- * Both kernels produce identical results. */
+/* Same with an explicit kernel choice: impl 0 or 3 = what scd_decode_topk runs (one CTA per image, thresholds from
+ * histograms of the score bits, output position = rank by counting), 2 = one warp per image (streaming exact top-K:
+ * the kernel the default falls back on, inside the same launch, for flat or saturated maps).  Identical results. */
 int scd_decode_topk_impl(const float* heat, const float* regr, const float* offset,
                          int batch, int classes, int height, int width, int K,
                          float* scores, int64_t* idx, int64_t* ys, int64_t* xs,

@@ -4,7 +4,11 @@
 // calls (ref: models/backbones/utility.py:76-118).  HBM-bound: the heat map is read exactly
 // once (one coalesced 512 B request per row), regr/offset are touched at K points only.
 //
-// One WARP per image, no block-level barrier anywhere:
+// Two kernels with identical results.  The default is decode_hist_kernel (further down: one CTA per image, thresholds
+// from histograms of the score bits, rank-by-counting output).  It shares the arithmetic below and falls back, inside
+// the same launch, on the first kernel for maps its fixed buffers cannot hold:
+//
+// One WARP per image (dec_warp_image / decode_kernel), no block-level barrier anywhere:
 //
 //   * the peak test runs on the LOGITS.  fp32 sigmoid is monotone non-decreasing, so
 //     max3x3(sigmoid(x)) == sigmoid(max3x3(x)) and the reference's keep mask
@@ -31,11 +35,6 @@
 #include <math_constants.h>
 
 namespace scd {
-
-// decode_cta.cu: one CTA per image, lower latency per image, lower throughput
-int launch_decode_cta(const float* heat, const float* regr, const float* offset, int batch, int K,
-                      float* scores, int64_t* idx, int64_t* ys, int64_t* xs, float* off_out, float* regr_out,
-                      float* planes, cudaStream_t st);
 
 constexpr int DEC_HW = 128;
 constexpr int DEC_MAXK = 128;
@@ -192,20 +191,15 @@ __device__ __forceinline__ unsigned dec_prune(DecWarp& w, unsigned nbuf, int K)
     return out;
 }
 
-template <int WPC>
-__global__ void __launch_bounds__(WPC * 32)
-decode_kernel(const float* __restrict__ heat, const float* __restrict__ regr,
-              const float* __restrict__ offset, int batch, int K,
-              float* __restrict__ scores, int64_t* __restrict__ idx_out,
-              int64_t* __restrict__ ys, int64_t* __restrict__ xs,
-              float* __restrict__ off_out, float* __restrict__ regr_out,
-              float* __restrict__ planes)
+// One image, one warp: the whole decode (streaming exact top-K, sort, gathers, outputs).  No block-level barrier.
+__device__ __forceinline__ void dec_warp_image(DecWarp& w, const float* __restrict__ heat, const float* __restrict__ regr,
+                                               const float* __restrict__ offset, int batch, int b, int K,
+                                               float* __restrict__ scores, int64_t* __restrict__ idx_out,
+                                               int64_t* __restrict__ ys, int64_t* __restrict__ xs,
+                                               float* __restrict__ off_out, float* __restrict__ regr_out,
+                                               float* __restrict__ planes)
 {
-    __shared__ DecWarp sm[WPC];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * WPC + warp;
-    if (b >= batch) return;                                  // warps are independent: no block barrier below
-    DecWarp& w = sm[warp];
+    const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const float4* hp = reinterpret_cast<const float4*>(heat + (size_t)b * DEC_HW * DEC_HW) + lane;
     const float4 ninf = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
@@ -431,6 +425,370 @@ decode_kernel(const float* __restrict__ heat, const float* __restrict__ regr,
     }
 }
 
+template <int WPC>
+__global__ void __launch_bounds__(WPC * 32)
+decode_kernel(const float* __restrict__ heat, const float* __restrict__ regr,
+              const float* __restrict__ offset, int batch, int K,
+              float* __restrict__ scores, int64_t* __restrict__ idx_out,
+              int64_t* __restrict__ ys, int64_t* __restrict__ xs,
+              float* __restrict__ off_out, float* __restrict__ regr_out,
+              float* __restrict__ planes)
+{
+    __shared__ DecWarp sm[WPC];
+    const int warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * WPC + warp;
+    if (b >= batch) return;                                  // warps are independent: no block barrier
+    dec_warp_image(sm[warp], heat, regr, offset, batch, b, K, scores, idx_out, ys, xs, off_out, regr_out, planes);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA per image, 8 warps, no serial threshold chain: the default kernel.
+//
+// The warp-per-image kernel above is latency bound: one warp walks the image and every admission depends on the
+// running K-th score.  Here the threshold comes from HISTOGRAMS of the score bits, so all warps of the CTA scan
+// their rows independently:
+//   phase 0  every warp evaluates the first 4 of its 16 rows completely (3x3 screen in registers, survivors evaluated
+//            compacted against the rows staged in shared memory) -> candidate list + 256-bin histogram of the score
+//            bits (8 bins per octave) -> bin T1 that holds the K-th best of this quarter-image sample, a valid lower
+//            bound of the final K-th score, turned into a logit bound tau_x;
+//   phase 1  the other 12 rows: one compare per pixel against tau_x, flagged pixels are listed and evaluated
+//            compacted the same way, candidates in bins >= T1 join the list;
+//   select   histogram of the list -> bin T2 of the K-th best, second histogram of the next 8 score bits inside T2
+//            -> at most 256 survivors, all others provably rank below K;
+//   rank     every survivor counts the survivors with a larger key (score bits, then smaller index): that count IS
+//            its output position, so selection and sort are one step and the owner thread writes the result row.
+// Exact like the warp kernel (same candidate predicate, same (score desc, index asc) order).  Anything the fixed
+// buffers cannot hold (more than 2048 candidates, more than 256 survivors: flat or saturated maps) is handed, inside
+// the same launch, to warp 0 running the warp-per-image algorithm on this image.
+constexpr int DH_THREADS = 256;
+constexpr int DH_ROWS = DEC_HW / (DH_THREADS / 32);      // image rows per warp
+constexpr int DH_CTAS = 3;                                // resident CTAs per SM the kernel is sized for
+constexpr int DH_CAP = 2048;            // candidate list entries
+constexpr int DH_SURV = 256;            // survivors ranked by counting
+constexpr int DH_FLAG = 512;            // flagged pixels per warp per 4-row chunk
+
+struct alignas(16) DecCta {
+    uint2 list[DH_CAP];                         // (score bits, flat index)
+    float tile[DH_THREADS / 32][6][DEC_HW];     // per warp: the 4 rows of a group with one halo row above and below
+    unsigned short flag[DH_THREADS / 32][DH_FLAG];
+    unsigned hist[256], hist2[256];
+    unsigned long long surv[DH_SURV];           // (score bits << 32) | ~flat
+    unsigned n_list, n_surv, overflow, t_bin, t_sub, total_pos;
+    float tau_x;
+};
+union alignas(16) DecSmem {
+    DecCta c;
+    DecWarp w;
+    __device__ DecSmem() {}
+};
+
+__device__ __forceinline__ unsigned dh_bin(unsigned sbits) {           // monotone in the score: 8 bins per octave, 2^-32 .. 1
+    const int e = (int)(sbits >> 20) - (95 << 3);
+    return (unsigned)min(max(e, 0), 255);
+}
+__device__ __forceinline__ unsigned dh_bin_edge(unsigned b) { return b == 0u ? 0u : (((95u << 3) + b) << 20); }
+// second-level key, monotone in the score INSIDE one bin: the next 8 score bits; the two clamped end bins span several
+// values of the leading bits and get their own (coarser) monotone maps
+__device__ __forceinline__ unsigned dh_sub(unsigned sbits, unsigned bin) {
+    if (bin == 0u) return sbits >> 22;                                  // scores below 2^-32: 0 .. 190
+    if (bin == 255u) return min((sbits - 0x3F700000u) >> 13, 255u);     // 0.9375 .. 1.0: 0 .. 128
+    return (sbits >> 12) & 255u;
+}
+
+// keep mask of the reference (see dec_warp_image) for a pixel x with 3x3 maximum m, positive scores only
+__device__ __forceinline__ bool dh_candidate(float x, float m, unsigned& sbits) {
+    if (x == m || x > DEC_SAT || !(m - x >= collapse_bound(x))) {
+        const float sg = sigmoidf_ref(x);
+        sbits = __float_as_uint(sg);
+        return sbits > 0u && sbits <= 0x3F800000u && (x == m || sigmoidf_ref(m) == sg);
+    }
+    return false;
+}
+
+__device__ __forceinline__ void dh_push(DecCta& c, bool ok, unsigned sbits, unsigned flat, int lane) {
+    const unsigned bal = __ballot_sync(FULL, ok);
+    if (bal == 0u) return;
+    const int leader = __ffs(bal) - 1;
+    unsigned base = 0u;
+    if (lane == leader) base = atomicAdd(&c.n_list, (unsigned)__popc(bal));
+    base = __shfl_sync(FULL, base, leader);
+    if (ok) {
+        const unsigned pos = base + __popc(bal & ((1u << lane) - 1u));
+        if (pos < (unsigned)DH_CAP) c.list[pos] = make_uint2(sbits, flat);
+        else c.overflow = 1u;
+    }
+}
+
+// warp 0: the bin that holds the k-th largest entry of a 256-bin histogram and the number of entries in higher bins;
+// k > total -> bin 0, above = total - hist[0]
+__device__ __forceinline__ void dh_find_bin(const unsigned* hist, unsigned k, unsigned& bin_out, unsigned& above_out, unsigned& total_out)
+{
+    const int lane = threadIdx.x & 31;
+    const uint4 a = *reinterpret_cast<const uint4*>(&hist[8 * lane]);
+    const uint4 c = *reinterpret_cast<const uint4*>(&hist[8 * lane + 4]);
+    const unsigned t = a.x + a.y + a.z + a.w + c.x + c.y + c.z + c.w;
+    unsigned incl = t;                                                 // entries in bins >= 8 lane
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned n = __shfl_down_sync(FULL, incl, o);
+        if (lane + o < 32) incl += n;
+    }
+    const unsigned total = __shfl_sync(FULL, incl, 0);
+    const unsigned above = incl - t;
+    const bool mine = above < k && incl >= k;
+    unsigned bin = 0u, ab = 0u;
+    if (mine) {
+        const unsigned cnt[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+        unsigned acc = above;
+        bool found = false;
+#pragma unroll
+        for (int i = 7; i >= 0; --i) {
+            if (!found && acc + cnt[i] >= k) { bin = 8u * lane + i; ab = acc; found = true; }
+            acc += cnt[i];
+        }
+    }
+    const unsigned bm = __ballot_sync(FULL, mine);
+    if (bm == 0u) {                                                    // fewer than k entries in all
+        bin_out = 0u; above_out = total - hist[0]; total_out = total;
+        return;
+    }
+    const int src = __ffs(bm) - 1;
+    bin_out = __shfl_sync(FULL, bin, src);
+    above_out = __shfl_sync(FULL, ab, src);
+    total_out = total;
+}
+
+__device__ __forceinline__ void dec_write_row(int b, int batch, int K, int t, unsigned sbits, unsigned flat,
+                                              const float* __restrict__ regr, const float* __restrict__ offset,
+                                              float* __restrict__ scores, int64_t* __restrict__ idx_out,
+                                              int64_t* __restrict__ ys, int64_t* __restrict__ xs,
+                                              float* __restrict__ off_out, float* __restrict__ regr_out,
+                                              float* __restrict__ planes)
+{
+    const float* rp = regr + (size_t)b * 4 * DEC_HW * DEC_HW + flat;
+    const float* op = offset + (size_t)b * 2 * DEC_HW * DEC_HW + flat;
+    const float g0 = __ldg(rp), g1 = __ldg(rp + DEC_HW * DEC_HW), g2 = __ldg(rp + 2 * DEC_HW * DEC_HW),
+                g3 = __ldg(rp + 3 * DEC_HW * DEC_HW), g4 = __ldg(op), g5 = __ldg(op + DEC_HW * DEC_HW);
+    const float sc = __uint_as_float(sbits);
+    const int y = (int)(flat / DEC_HW), x = (int)(flat % DEC_HW);                     // utility.py:115-117
+    const size_t o = (size_t)b * K + t;
+    scores[o] = sc;
+    idx_out[o] = (int64_t)flat;
+    ys[o] = (int64_t)y;
+    xs[o] = (int64_t)x;
+    reinterpret_cast<float4*>(regr_out)[o] = make_float4(g0, g1, g2, g3);
+    reinterpret_cast<float2*>(off_out)[o] = make_float2(g4, g5);
+    if (planes != nullptr) {
+        const size_t ps = (size_t)batch * K;
+        planes[o] = sc;
+        planes[ps + o] = (float)flat;
+        planes[2 * ps + o] = (float)y;
+        planes[3 * ps + o] = (float)x;
+        planes[4 * ps + o] = g0; planes[5 * ps + o] = g1; planes[6 * ps + o] = g2; planes[7 * ps + o] = g3;
+        planes[8 * ps + o] = g4; planes[9 * ps + o] = g5;
+    }
+}
+
+__global__ void __launch_bounds__(DH_THREADS, DH_CTAS)
+decode_hist_kernel(const float* __restrict__ heat, const float* __restrict__ regr,
+                   const float* __restrict__ offset, int batch, int K,
+                   float* __restrict__ scores, int64_t* __restrict__ idx_out,
+                   int64_t* __restrict__ ys, int64_t* __restrict__ xs,
+                   float* __restrict__ off_out, float* __restrict__ regr_out,
+                   float* __restrict__ planes)
+{
+    extern __shared__ __align__(16) unsigned char dh_smem[];       // 52 KB: above the static limit
+    DecSmem& sm = *reinterpret_cast<DecSmem*>(dh_smem);
+    DecCta& c = sm.c;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const float* img = heat + (size_t)b * DEC_HW * DEC_HW;
+    const float4* hp = reinterpret_cast<const float4*>(img) + lane;
+    const float4 ninf = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+    for (int i = tid; i < 256; i += DH_THREADS) { c.hist[i] = 0u; c.hist2[i] = 0u; }
+    if (tid == 0) { c.n_list = 0u; c.n_surv = 0u; c.overflow = 0u; }
+    __syncthreads();
+
+    // ---- groups of 4 rows.  Group 0 of every warp (the sample): every pixel that passes the 3x3 screen is evaluated;
+    // later groups: only pixels above the logit bound of the sample's K-th best.  Either way the flagged pixels are
+    // listed and evaluated COMPACTED, 32 per step, against the rows staged in shared memory.
+    const int r0 = warp * DH_ROWS;
+    float tau_x = -CUDART_INF_F;
+    unsigned t1 = 0u;
+    float4 rv[6];
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+        const int row = r0 - 1 + u;
+        rv[u] = row >= 0 ? ld_stream(hp + row * (DEC_HW / 4)) : ninf;
+    }
+#pragma unroll 1
+    for (int g = 0; g < DH_ROWS / 4; ++g) {
+        const int ra = r0 + 4 * g;
+        unsigned mask = 0u;
+        if (g == 0) {
+            float4 hm_a = hmax3(rv[0], lane), hm_b = hmax3(rv[1], lane);
+#pragma unroll
+            for (int u = 1; u <= 4; ++u) {
+                const float4 hm_c = hmax3(rv[u + 1], lane);
+                const float xv[4] = {rv[u].x, rv[u].y, rv[u].z, rv[u].w};
+                const float mv[4] = {fmaxf(fmaxf(hm_a.x, hm_b.x), hm_c.x), fmaxf(fmaxf(hm_a.y, hm_b.y), hm_c.y),
+                                     fmaxf(fmaxf(hm_a.z, hm_b.z), hm_c.z), fmaxf(fmaxf(hm_a.w, hm_b.w), hm_c.w)};
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    mask |= (((xv[q] > DEC_SAT) | !(mv[q] - xv[q] >= collapse_bound(xv[q]))) ? 1u : 0u) << (4 * (u - 1) + q);
+                hm_a = hm_b; hm_b = hm_c;
+            }
+        } else {
+#pragma unroll
+            for (int u = 1; u <= 4; ++u)
+                mask |= ((rv[u].x > tau_x ? 1u : 0u) | (rv[u].y > tau_x ? 2u : 0u) | (rv[u].z > tau_x ? 4u : 0u) |
+                         (rv[u].w > tau_x ? 8u : 0u)) << (4 * (u - 1));
+        }
+        __syncwarp();                                            // the previous group's tile / list reads are done
+#pragma unroll
+        for (int u = 0; u < 6; ++u) *reinterpret_cast<float4*>(&c.tile[warp][u][lane * 4]) = rv[u];
+        if (g < DH_ROWS / 4 - 1) {                               // next group's rows: ra + 3 .. ra + 8
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+                const int row = ra + 3 + u;
+                rv[u] = row < DEC_HW ? ld_stream(hp + row * (DEC_HW / 4)) : ninf;
+            }
+        }
+        if (__any_sync(FULL, mask != 0u)) {
+            const unsigned n_mine = __popc(mask);
+            unsigned incl = n_mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const unsigned total = __shfl_sync(FULL, incl, 31);
+            {
+                unsigned pos = incl - n_mine;
+                for (unsigned m2 = mask; m2; m2 &= m2 - 1u) {
+                    const int bit = __ffs(m2) - 1;
+                    c.flag[warp][pos++] = (unsigned short)(((bit >> 2) << 7) | (lane * 4 + (bit & 3)));
+                }
+            }
+            __syncwarp();
+            for (unsigned j0 = 0; j0 < total; j0 += 32) {
+                const unsigned j = j0 + lane;
+                bool ok = false;
+                unsigned sbits = 0u, flat = 0u;
+                if (j < total) {
+                    const unsigned code = c.flag[warp][j];
+                    const int u = (int)(code >> 7), col = (int)(code & 127u);
+                    const int cl = col > 0 ? col - 1 : col, cr = col < DEC_HW - 1 ? col + 1 : col;   // -inf padding: repeat
+                    const float (*tl)[DEC_HW] = c.tile[warp];
+                    const float x = tl[u + 1][col];
+                    float m = fmaxf(fmaxf(tl[u][cl], tl[u][col]), tl[u][cr]);
+                    m = fmaxf(m, fmaxf(fmaxf(tl[u + 1][cl], x), tl[u + 1][cr]));
+                    m = fmaxf(m, fmaxf(fmaxf(tl[u + 2][cl], tl[u + 2][col]), tl[u + 2][cr]));
+                    flat = (unsigned)((ra + u) * DEC_HW + col);
+                    ok = dh_candidate(x, m, sbits) && dh_bin(sbits) >= t1;
+                    if (ok && g == 0) atomicAdd(&c.hist[dh_bin(sbits)], 1u);
+                }
+                dh_push(c, ok, sbits, flat, lane);
+            }
+        }
+        if (g == 0) {
+            __syncthreads();
+            if (warp == 0) {
+                unsigned bin, above, total;
+                dh_find_bin(c.hist, (unsigned)K, bin, above, total);
+                if (lane == 0) {
+                    c.t_bin = bin;
+                    c.tau_x = bin == 0u ? -CUDART_INF_F : logit_bound(dh_bin_edge(bin) - 1u);   // x <= tau_x: score below bin T1
+                }
+            }
+            __syncthreads();
+            tau_x = c.tau_x;
+            t1 = c.t_bin;
+        }
+    }
+    __syncthreads();
+    bool fallback = c.overflow != 0u || c.n_list > (unsigned)DH_CAP;
+    const unsigned n_list = fallback ? 0u : c.n_list;
+
+    // ---- select: bin of the K-th best, then the next 8 score bits inside that bin --------------------------------
+    for (int i = tid; i < 256; i += DH_THREADS) c.hist[i] = 0u;
+    __syncthreads();
+    for (unsigned i = tid; i < n_list; i += DH_THREADS) atomicAdd(&c.hist[dh_bin(c.list[i].x)], 1u);
+    __syncthreads();
+    if (warp == 0) {
+        unsigned bin, above, total;
+        dh_find_bin(c.hist, (unsigned)K, bin, above, total);
+        if (lane == 0) { c.t_bin = bin; c.n_surv = above; c.total_pos = total; }       // n_surv: entries above the bin, for now
+    }
+    __syncthreads();
+    const unsigned t2 = c.t_bin, above2 = c.n_surv, total_pos = c.total_pos;
+    for (unsigned i = tid; i < n_list; i += DH_THREADS) {
+        const unsigned sb = c.list[i].x;
+        if (dh_bin(sb) == t2) atomicAdd(&c.hist2[dh_sub(sb, t2)], 1u);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        unsigned sub = 0u, above_s = 0u, tot_s = 0u;
+        const unsigned need = total_pos >= (unsigned)K ? (unsigned)K - above2 : 0xFFFFFFFFu;   // how many of bin t2 are needed
+        dh_find_bin(c.hist2, need, sub, above_s, tot_s);
+        if (need == 0xFFFFFFFFu) sub = 0u;                         // fewer than K positive candidates: everything survives
+        // survivors: bin > t2, or bin == t2 and sub-bin >= sub
+        unsigned cnt = 0u;
+        for (unsigned sbin = sub + lane; sbin < 256u; sbin += 32u) cnt += c.hist2[sbin];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+        if (lane == 0) { c.t_sub = sub; c.overflow = (above2 + cnt > (unsigned)DH_SURV) ? 1u : 0u; c.n_surv = 0u; }
+    }
+    __syncthreads();
+    fallback = fallback || c.overflow != 0u;
+    if (fallback) {
+        // flat / saturated map: more candidates or ties than the fixed buffers hold.  Warp 0 decodes this image alone.
+        __syncthreads();
+        if (warp == 0) dec_warp_image(sm.w, heat, regr, offset, batch, b, K, scores, idx_out, ys, xs, off_out, regr_out, planes);
+        return;
+    }
+    const unsigned t_sub = c.t_sub;
+    for (unsigned i = tid; i < n_list; i += DH_THREADS) {
+        const uint2 e = c.list[i];
+        const unsigned bn = dh_bin(e.x);
+        if (bn > t2 || (bn == t2 && dh_sub(e.x, t2) >= t_sub)) {
+            const unsigned pos = atomicAdd(&c.n_surv, 1u);
+            c.surv[pos] = ((unsigned long long)e.x << 32) | (unsigned long long)(0xFFFFFFFFu - e.y);
+        }
+    }
+    __syncthreads();
+    const unsigned S = c.n_surv;
+
+    // ---- rank by counting = output position --------------------------------------------------------------------
+    for (unsigned t = tid; t < S; t += DH_THREADS) {
+        const unsigned long long key = c.surv[t];
+        unsigned rank = 0u;
+#pragma unroll 4
+        for (unsigned j = 0; j < S; ++j) rank += c.surv[j] > key ? 1u : 0u;
+        if (rank < (unsigned)K)
+            dec_write_row(b, batch, K, (int)rank, (unsigned)(key >> 32), 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull), regr,
+                          offset, scores, idx_out, ys, xs, off_out, regr_out, planes);
+    }
+    if (S < (unsigned)K && warp == 0) {
+        // fewer than K positive peaks: every other pixel scores 0; the K - S smallest flat indices outside the
+        // survivors fill the tail (they lie in [0, K)), in ascending order
+        const unsigned Z = (unsigned)K - S;
+        unsigned zseen = 0u;
+        for (unsigned j0 = 0; j0 < (unsigned)K; j0 += 32) {
+            const unsigned j = j0 + lane;
+            bool in = false;
+            for (unsigned i = 0; i < S; ++i) in |= (0xFFFFFFFFu - (unsigned)(c.surv[i] & 0xFFFFFFFFull)) == j;
+            const bool z = j < (unsigned)K && !in;
+            const unsigned bz = __ballot_sync(FULL, z);
+            const unsigned rank = zseen + __popc(bz & lt);
+            if (z && rank < Z)
+                dec_write_row(b, batch, K, (int)(S + rank), 0u, j, regr, offset, scores, idx_out, ys, xs, off_out, regr_out, planes);
+            zseen += __popc(bz);
+        }
+    }
+}
+
 // Exhaustive check, over every fp32 bit pattern, of the three properties decode_kernel relies on:
 //   counts[0]: sigmoid is monotone:            sigmoid(x) <= sigmoid(next float above x)
 //   counts[1]: the collapse screen is safe:    sigmoid(x + bound(x) / 2) > sigmoid(x)   whenever sigmoid(x) > 0
@@ -466,7 +824,8 @@ extern "C" int scd_selftest_decode_math(unsigned long long* counts3, void* strea
     return SCD_OK;
 }
 
-// impl: 0 = choose by batch size, 1 = CTA per image (decode_cta.cu), 2 = warp per image (this file)
+// impl: 0 or 3 = CTA per image with histogram thresholds (the default at every batch size), 2 = warp per image (the
+// streaming kernel that the default falls back on for flat / saturated maps; kept callable as a cross-check)
 extern "C" int scd_decode_topk_impl(const float* heat, const float* regr, const float* offset,
                                     int batch, int classes, int height, int width, int K,
                                     float* scores, int64_t* idx, int64_t* ys, int64_t* xs,
@@ -479,12 +838,22 @@ extern "C" int scd_decode_topk_impl(const float* heat, const float* regr, const 
     if (K < 1 || K > scd::DEC_MAXK) return scd::fail(SCD_EINVAL, "scd_decode_topk: K must be in [1,128] (got %d)", K);
     if (!heat || !regr || !offset || !scores || !idx || !ys || !xs || !off_out || !regr_out)
         return scd::fail(SCD_EINVAL, "scd_decode_topk: null pointer");
-    if (impl < 0 || impl > 2) return scd::fail(SCD_EINVAL, "scd_decode_topk_impl: impl must be 0, 1 or 2");
+    if (impl != 0 && impl != 2 && impl != 3) return scd::fail(SCD_EINVAL, "scd_decode_topk_impl: impl must be 0, 2 or 3");
     cudaStream_t st = (cudaStream_t)stream;
-    // Measured on B200: the CTA-per-image kernel takes ~37 us per wave of 296 images (2 CTAs / SM), the
-    // warp-per-image kernel 85 us (one image) to 127 us (2048 images): the latter wins from three waves on.
-    if (impl == 1 || (impl == 0 && batch <= 4 * scd::kNumSMs))
-        return scd::launch_decode_cta(heat, regr, offset, batch, K, scores, idx, ys, xs, off_out, regr_out, planes, st);
+    // Measured on B200 (tools/bench_decode_impls.py): the histogram kernel is faster than the warp-per-image kernel at
+    // every batch size: 18 vs 55 us at 64 images, 90 vs 107 us at 2048, 295 vs 359 us at 8192.
+    if (impl != 2) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            SCD_CUDA_CHECK(cudaFuncSetAttribute(scd::decode_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)sizeof(scd::DecSmem)));
+            attr_done = true;
+        }
+        scd::decode_hist_kernel<<<batch, scd::DH_THREADS, sizeof(scd::DecSmem), st>>>(heat, regr, offset, batch, K, scores, idx, ys, xs, off_out,
+                                                                   regr_out, planes);
+        SCD_LAUNCH_CHECK("decode_hist_kernel");
+        return SCD_OK;
+    }
     if (batch <= 2 * scd::kNumSMs)          // few images: one warp per CTA so that they spread over the SMs
         scd::decode_kernel<1><<<batch, 32, 0, st>>>(heat, regr, offset, batch, K, scores, idx, ys, xs, off_out,
                                                     regr_out, planes);

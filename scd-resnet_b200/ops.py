@@ -35,7 +35,7 @@ def decode_topk(heat, regr, offset, K=100, planes=False, impl=0):
 
     Returns (scores f32 (B,K), idx i64, ys i64, xs i64, offset (B,K,2), regr (B,K,4)) and, when
     `planes`, also the (10,B,K) f32 stack of trainer/wrappers/centerOffsetResidual.py:11-22.
-    impl: 0 = kernel chosen by batch size, 1 = CTA per image, 2 = warp per image (identical results).
+    impl: 0 / 3 = the default kernel (CTA per image, histogram thresholds), 2 = warp per image (identical results).
     """
     heat = _req(heat, torch.float32, "heatmap")
     regr = _req(regr, torch.float32, "regr")

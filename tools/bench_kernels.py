@@ -36,8 +36,11 @@ off = torch.randn(N, 2, 128, 128, device=dev, generator=g)
 ms = timeit(lambda: S.ops.decode_topk(heat, regr, off, K=100))
 out["decode"] = {"tiles": N, "ms": ms, "alg_bytes_per_tile": 73136, "gbs": 73136 * N / ms / 1e6, "frac": 73136 * N / ms / 1e6 / HBM}
 heat_real = torch.full((N, 1, 128, 128), -4.0, device=dev) + 0.05 * torch.randn(N, 1, 128, 128, device=dev, generator=g)
-ms = timeit(lambda: S.ops.decode_topk(heat, regr, off, K=100, impl=1))
-out["decode_cta_per_image"] = {"ms": ms, "frac": 73136 * N / ms / 1e6 / HBM}
+for impl in (2, 3):
+    ms = timeit(lambda: S.ops.decode_topk(heat, regr, off, K=100, impl=impl))
+    out["decode_impl%d" % impl] = {"ms": ms, "frac": 73136 * N / ms / 1e6 / HBM}
+    ms = timeit(lambda: S.ops.decode_topk(heat_real, regr, off, K=100, impl=impl))
+    out["decode_impl%d_flat_background" % impl] = {"ms": ms, "frac": 73136 * N / ms / 1e6 / HBM}
 for nb in (64, 256, 592, 1024):
     ms = timeit(lambda: S.ops.decode_topk(heat[:nb], regr[:nb], off[:nb], K=100))
     out["decode_b%d" % nb] = {"ms": ms}
