@@ -34,12 +34,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+// ... with a suspend-time hint: the thread sleeps in hardware until the phase completes or ~`ns` have passed, instead of
+// spinning.  (ncu, stem kernel: 39 % of all issued instructions were the spin loops of waiting warps.)
+__device__ __forceinline__ bool mbar_try_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(ns) : "memory");
+    return ok != 0;
+}
 // Bounded wait: a pipeline bug traps (launch failure reported to the host) instead of hanging
 // the GPU.  2^31 cycles is about one second.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
+    while (!mbar_try_wait_sleep(bar, parity, 20000u)) {
         if (clock64() - t0 > (1ll << 31)) {
             printf("scd_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
                    (int)blockIdx.x, (int)threadIdx.x, bar, parity);
