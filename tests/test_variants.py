@@ -164,3 +164,34 @@ def test_variant_training_step(name):
     model.eval()
     dec = model(O.make_tiles(1, seed=8).cuda(), decode=True)
     assert dec[0].shape == (1, 100) and bool(torch.isfinite(dec[0]).all())
+
+
+def test_native_plan_queries():
+    """Host-only entry points of the generic pass (no GPU needed): stage lists, blob layout and workspace size."""
+    from scd_resnet_b200 import ops
+    from scd_resnet_b200._lib import lib, ScdError
+    # depth 10 / default widths == the headline entry points
+    assert len(ops.resnet_conv_specs(10)) == 14 and len(ops.resnet_conv_specs(18)) == 22 and len(ops.resnet_conv_specs(34)) == 38
+    offs, sizes, total = ops.infer_weights_layout(10)
+    assert total == lib.scd_infer_weights_bytes() and len(offs) == 34
+    assert lib.scd_resnet_workspace_bytes(10, None, 64, 512, 512) == lib.scd_infer_workspace_bytes(64, 512, 512)
+    # stage order of a projection block: downsample, conv1 (stride 2), conv2; deconvs last
+    s18 = ops.resnet_conv_specs(18)
+    assert s18[:4] == [(0, 64, 64)] * 4 and s18[4:7] == [(2, 64, 128), (1, 64, 128), (0, 128, 128)]
+    assert s18[-3:] == [(3, 512, 256), (3, 256, 256), (3, 256, 256)]
+    # every blob entry is 256-byte aligned and sized as the packed tensors are
+    for depth, dims in ((18, None), (34, None), (10, [64, 64, 64, 128, 256, 128, 128, 128]), (10, [64, 64, 64, 64, 128, 64, 64, 64])):
+        specs = ops.resnet_conv_specs(depth, dims)
+        offs, sizes, total = ops.infer_weights_layout(depth, dims)
+        assert all(o % 256 == 0 for o in offs) and offs[-1] + sizes[-1] <= total
+        taps = {0: 9, 1: 9, 2: 1, 3: 16}
+        for i, (kind, cin, cout) in enumerate(specs):
+            assert sizes[2 + 2 * i] == cout * taps[kind] * cin * 2 and sizes[3 + 2 * i] == cout * 4
+        head_cin = (dims or [0] * 7 + [256])[7]
+        assert sizes[-4] == 384 * 9 * head_cin * 2 and sizes[-3:] == [384 * 4, 7 * 128 * 4, 7 * 4]
+    # unsupported architectures fail loudly, with a message
+    for depth, dims in ((50, None), (10, [64, 128, 128, 256, 512, 256, 256, 256]), (10, [32, 32, 64, 128, 256, 128, 128, 128]),
+                        (10, [64, 64, 128, 256, 1024, 256, 256, 256])):
+        with pytest.raises(ScdError):
+            ops.resnet_conv_specs(depth, dims)
+    assert lib.scd_resnet_num_convs(50, None) < 0 and lib.scd_resnet_weights_bytes(50, None) == 0
