@@ -22,7 +22,7 @@ namespace scd {
 
 constexpr int RT_HW = 128;        // HEATMAPSIZE, ref: scdx16p100.py:50
 constexpr int RT_MAXTAG = 30;     // MAXTAGLEN,   ref: scdx16p100.py:46
-constexpr int RT_THREADS = 256;   // one CTA per sample; the 64 KB heat map lives in shared memory
+constexpr int RT_THREADS = 384;   // one CTA per sample; the 64 KB heat map lives in shared memory
 
 struct RenderObj {
     int cx, cy, roi;
@@ -108,8 +108,9 @@ render_targets_kernel(const float* __restrict__ locs, const int32_t* __restrict_
         if (n_pos != nullptr && tid == 0 && n) atomicAdd(n_pos + 1, (unsigned)n);        // mask.sum() (drawn == masked)
         const int slot = __popc(m & ((1u << tid) - 1u));
         if (draw) objs[slot] = o;
-        // table offsets: (roi + 1)^2 entries each, in compacted order; objects that do not fit get -1
-        int need = draw ? (o.roi + 1) * (o.roi + 1) : 0;
+        // table offsets: (roi + 1)(roi + 2) / 2 entries each (g is symmetric in |dy|, |dx|), in compacted order; objects
+        // that do not fit get -1
+        int need = draw ? (o.roi + 1) * (o.roi + 2) / 2 : 0;
         int incl = need;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -161,17 +162,20 @@ render_targets_kernel(const float* __restrict__ locs, const int32_t* __restrict_
         }
         if (tid < n) { order[rank] = (unsigned char)tid; level_of[rank] = (unsigned char)level; }
     } else {
-        // ---- warps 1..7: Gaussian tables.  g depends on (|dy|, |dx|) only: (roi + 1)^2 exps per object instead
-        // of (2 roi + 1)^2, each bit-identical to what the per-pixel evaluation would give.
+        // ---- the other warps: Gaussian tables.  g depends on the unordered pair {|dy|, |dx|} only: (roi + 1)(roi + 2) / 2
+        // exps per object instead of (2 roi + 1)^2, each bit-identical to what the per-pixel evaluation would give
+        // (a * a + c * c is an exact integer either way round).  Entry (hi, lo), hi >= lo, sits at hi (hi + 1) / 2 + lo.
         const int nf = n_fit, total = n_tab;
         for (int i = tid - 32; i < total; i += RT_THREADS - 32) {
             int k = 0;                                   // last fitting object whose table starts at or before i
 #pragma unroll
             for (int step = 16; step > 0; step >>= 1)
                 if (k + step < nf && tab_off[k + step] <= i) k += step;
-            const int side = objs[k].roi + 1;
             const int e = i - tab_off[k];
-            const int a = e / side, c = e - a * side;
+            int a = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);                   // row of the triangle, fixed up below
+            while ((a + 1) * (a + 2) / 2 <= e) ++a;
+            while (a * (a + 1) / 2 > e) --a;
+            const int c = e - a * (a + 1) / 2;
             tab[i] = exp(__ddiv_rn(-(double)(a * a + c * c), objs[k].den));
         }
     }
@@ -190,14 +194,15 @@ render_targets_kernel(const float* __restrict__ locs, const int32_t* __restrict_
             for (int s2 = s0 + warp; s2 < s1; s2 += RT_THREADS / 32) {
                 const int k = order[s2];
                 const RenderObj o = objs[k];
-                const int off = tab_off[k], side = o.roi + 1;
+                const int off = tab_off[k];
                 const int xa = max(o.cx - o.roi, 0), xb = min(o.cx + o.roi, RT_HW - 1);  // :579-583 window clipping
                 const int ya = max(o.cy - o.roi, 0), yb = min(o.cy + o.roi, RT_HW - 1);
                 for (int yy = ya + ly; yy <= yb; yy += 2) {
                     const int dy = abs(yy - o.cy);
                     for (int xx = xa + lx; xx <= xb; xx += 16) {
                         const int dx = abs(xx - o.cx);
-                        const double g = off >= 0 ? tab[off + dy * side + dx]
+                        const int hi = max(dy, dx), lo = min(dy, dx);
+                        const double g = off >= 0 ? tab[off + hi * (hi + 1) / 2 + lo]
                                                   : exp(__ddiv_rn(-(double)(dx * dx + dy * dy), o.den));
                         float* hp = tile + yy * RT_HW + xx;
                         *hp = (float)__dadd_rn(g, (double)*hp);
