@@ -65,6 +65,7 @@ render_targets_kernel(const float* __restrict__ locs, const int32_t* __restrict_
     __shared__ int tab_off[RT_MAXTAG + 1];             // start of the object's table, -1: does not fit, compute directly
     __shared__ unsigned char order[RT_MAXTAG], level_of[RT_MAXTAG], lvl[32];   // draw order: overlap level, then list order
     __shared__ int n_draw, n_tab, n_fit;
+    __shared__ unsigned level_starts;
     __shared__ unsigned ones;
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
@@ -161,6 +162,11 @@ render_targets_kernel(const float* __restrict__ locs, const int32_t* __restrict_
             rank += (lj < level || (lj == level && j < tid)) ? 1 : 0;
         }
         if (tid < n) { order[rank] = (unsigned char)tid; level_of[rank] = (unsigned char)level; }
+        __syncwarp();
+        // bit r set: draw slot r starts a new level (every thread walks the levels from this mask, no scan of level_of)
+        const bool starts = tid < n && (tid == 0 || level_of[tid] != level_of[tid - 1]);
+        const unsigned sm_ = __ballot_sync(0xffffffffu, starts);
+        if (tid == 0) level_starts = sm_;
     } else {
         // ---- the other warps: Gaussian tables.  g depends on the unordered pair {|dy|, |dx|} only: (roi + 1)(roi + 2) / 2
         // exps per object instead of (2 roi + 1)^2, each bit-identical to what the per-pixel evaluation would give
@@ -186,11 +192,11 @@ render_targets_kernel(const float* __restrict__ locs, const int32_t* __restrict_
     {
         const int n = n_draw, warp = tid >> 5, lane = tid & 31;
         const int ly = lane >> 4, lx = lane & 15;
+        const unsigned starts = level_starts;
         int s0 = 0;
         while (s0 < n) {
-            const int lv = level_of[s0];
-            int s1 = s0 + 1;
-            while (s1 < n && level_of[s1] == lv) ++s1;
+            const unsigned later = s0 < 31 ? starts & ~((2u << s0) - 1u) : 0u;           // level starts after slot s0
+            const int s1 = later ? min(__ffs(later) - 1, n) : n;
             for (int s2 = s0 + warp; s2 < s1; s2 += RT_THREADS / 32) {
                 const int k = order[s2];
                 const RenderObj o = objs[k];
