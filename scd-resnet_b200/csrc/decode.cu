@@ -687,7 +687,7 @@ decode_hist_kernel(const float* __restrict__ heat, const float* __restrict__ reg
                     m = fmaxf(m, fmaxf(fmaxf(tl[u + 2][cl], tl[u + 2][col]), tl[u + 2][cr]));
                     flat = (unsigned)((ra + u) * DEC_HW + col);
                     ok = dh_candidate(x, m, sbits) && dh_bin(sbits) >= t1;
-                    if (ok && g == 0) atomicAdd(&c.hist[dh_bin(sbits)], 1u);
+                    if (ok) atomicAdd(&c.hist[dh_bin(sbits)], 1u);     // the histogram always covers the whole list
                 }
                 dh_push(c, ok, sbits, flat, lane);
             }
@@ -711,11 +711,8 @@ decode_hist_kernel(const float* __restrict__ heat, const float* __restrict__ reg
     bool fallback = c.overflow != 0u || c.n_list > (unsigned)DH_CAP;
     const unsigned n_list = fallback ? 0u : c.n_list;
 
-    // ---- select: bin of the K-th best, then the next 8 score bits inside that bin --------------------------------
-    for (int i = tid; i < 256; i += DH_THREADS) c.hist[i] = 0u;
-    __syncthreads();
-    for (unsigned i = tid; i < n_list; i += DH_THREADS) atomicAdd(&c.hist[dh_bin(c.list[i].x)], 1u);
-    __syncthreads();
+    // ---- select: bin of the K-th best (the histogram was kept up to date by every push), then the next 8 score bits
+    // inside that bin
     if (warp == 0) {
         unsigned bin, above, total;
         dh_find_bin(c.hist, (unsigned)K, bin, above, total);
