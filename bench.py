@@ -366,7 +366,10 @@ def main():
                        "l2": "3 rotating input batches (3x64 MB) + 1.4 GB activations per step > 126 MB L2"},
             "e2e": {"value": world * B * K / (e2e_ms * 1e-3), "unit": "tiles/s",
                     "h2d_bytes_per_step": B * 512 * 512 * 4, "d2h_bytes_per_step": 10 * B * 100 * 4,
-                    "api": "TileDetector.detect_host (pinned host tiles -> host detections, copies overlapped)"},
+                    "api": "TileDetector.detect_host (pinned host tiles -> host detections, copies overlapped)",
+                    "h2d_gb_per_s": round(B * 512 * 512 * 4 / (e2e_ms / K * 1e-3) / 1e9, 2),
+                    "note": "fp32 tiles are 1 MB each: when this falls below `value` the host -> device link of the box is "
+                            "the limit (the copies overlap the kernels), not the GPU"},
             "gpu_launches": 17 * K,
             "roofline": {"kernel": "igemm_kernel<384, EPI_HEADS> (fused heads)", "bound": "tensor",
                          "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
