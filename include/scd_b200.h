@@ -277,7 +277,8 @@ int scd_conv_igemm_dgrad(int kind, const void* dz, const void* dz2, const void* 
  * kind 0/1/2: a_in = layer input (B,hin,win,cin), dz = output gradient, out[(t*cin/64 + ci/64)][co][ci%64];
  * kind 3 (ConvTranspose): a_in = layer input (B,hin,win,cin), dz (B,2hin,2win,cout),
  *                         out[(t*cout/64 + co/64)][ci][co%64], t = kh*4 + kw;
- * kind 4 (stem): a_in = im2col operand col0 (B,hin,win,64), dz = dz0, out[0][co][k].
+ * kind 4 (stem): a_in = im2col operand col0 (B,hin,win,64), dz = dz0, out[0][co][k];
+ * kind 5 (3x3 s1, roles swapped: dz is the shifted operand; for Cin > Cout): out[(t*cout/64 + co/64)][ci][co%64].
  * `out` (fp32, scd_conv_wgrad_out_floats elements) must be zero on entry; partial tiles are accumulated. */
 size_t scd_conv_wgrad_out_floats(int kind, int cin, int cout);
 int scd_conv_wgrad(int kind, const void* a_in, const void* dz, int batch, int hin, int win,

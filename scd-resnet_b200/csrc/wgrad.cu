@@ -186,7 +186,7 @@ wgrad_kernel(const __grid_constant__ WgradParams p)
 extern "C" size_t scd_conv_wgrad_out_floats(int kind, int cin, int cout)
 {
     const int taps = (kind == 2 || kind == 4) ? 1 : (kind == 3 ? 16 : 9);
-    const int cs = kind == 3 ? cout : cin, cp = kind == 3 ? cin : cout;
+    const int cs = (kind == 3 || kind == 5) ? cout : cin, cp = (kind == 3 || kind == 5) ? cin : cout;
     const int chunks = taps * (cs / 64);
     return (size_t)((chunks + 1) / 2 * 2) * cp * 64;
 }
@@ -234,6 +234,14 @@ extern "C" int scd_conv_wgrad(int kind, const void* a_in, const void* dz, int ba
             p.tap_dx[kh * 4 + kw] = (int8_t)off_of[kw];
         }
         if ((rc = make_act_map(&p.tmP, a_in, batch, hin, win, cin, 1, 0, 0, WG_TH))) return rc;
+    } else if (kind == 5) {
+        // 3x3 s1 conv with the roles swapped: the output gradient is the shifted operand (by MINUS the tap offset) and the
+        // layer input is read in place: sum_p dz[p, co] x[p + t, ci] = sum_q dz[q - t, co] x[q, ci].  Same result as
+        // kind 0; pays when Cin > Cout (N = Cin per MMA instead of Cout: the heat head, 256 -> 128).
+        gh = hin; gw = win; p.n_taps = 9;
+        if ((rc = make_act_map(&p.tmS[0], dz, batch, hin, win, cout, 1, 0, 0, WG_TH))) return rc;
+        for (int r = 0; r < 3; ++r) for (int s = 0; s < 3; ++s) { p.tap_dy[r * 3 + s] = (int8_t)(1 - r); p.tap_dx[r * 3 + s] = (int8_t)(1 - s); }
+        if ((rc = make_act_map(&p.tmP, a_in, batch, hin, win, cin, 1, 0, 0, WG_TH))) return rc;
     } else if (kind == 4) {
         // plain pixel contraction, one tap, no shift: the stem (S = im2col operand col0, P = dz0)
         gh = hin; gw = win; p.n_taps = 1;
@@ -243,7 +251,7 @@ extern "C" int scd_conv_wgrad(int kind, const void* a_in, const void* dz, int ba
         return fail(SCD_EINVAL, "scd_conv_wgrad: unknown kind %d", kind);
     }
     if (gh % WG_TH || gw % TM_TW) return fail(SCD_EINVAL, "scd_conv_wgrad: grid %dx%d not a multiple of 4x16", gh, gw);
-    const int cs = kind == 3 ? cout : cin, cp = kind == 3 ? cin : cout;
+    const int cs = (kind == 3 || kind == 5) ? cout : cin, cp = (kind == 3 || kind == 5) ? cin : cout;
     p.cs_blocks = cs / 64;
     p.n_chunks = p.n_taps * p.cs_blocks;
     p.m_tiles = (p.n_chunks + 1) / 2;

@@ -199,10 +199,12 @@ class TrainEngine:
         hd = named["heatmap.0.weight"].shape[0]                                         # head width: 128, or 64 (h / q)
         ci_real = named["heatmap.0.weight"].shape[1]
         w3_idx = torch.cat([pidx(h + ".0.weight", (128, hc, 3, 3)) for h, _, _ in _HEADS], 0)   # (384,hc,3,3) of P indices
-        base = g_alloc("heads.w3h", T.conv_wgrad_floats(0, hc, 128))
+        # heat head weight gradient: wgrad kind 5 (dz shifted, N = the heads' input width) when that is wider than 128
+        self.heat_wgrad_kind = 5 if hc > 128 else 0
+        base = g_alloc("heads.w3h", T.conv_wgrad_floats(self.heat_wgrad_kind, hc, 128))
         k = "heatmap.0.weight"
         gmap[self.off[k]:self.off[k] + named[k].numel()] = \
-            (base + weights.wgrad_index((128, hc, 3, 3), 0)[:hd, :ci_real]).reshape(-1)
+            (base + weights.wgrad_index((128, hc, 3, 3), self.heat_wgrad_kind)[:hd, :ci_real]).reshape(-1)
         base = g_alloc("heads.w3s", 9 * 256 * hc)
         co, ci, r, s_ = torch.meshgrid(torch.arange(hd), torch.arange(ci_real), torch.arange(3), torch.arange(3),
                                        indexing="ij")
@@ -327,7 +329,7 @@ class TrainEngine:
         d_hh, dh_obj = T.heads_bwd_sparse(d_heat, d_obj, mask, gidx, hidden, w1, self.g("heads.w1"), self.g("heads.b1"),
                                           self.g("heads.b3"))
         hc = self.kd[7]
-        T.conv_wgrad(0, e3, d_hh, hc, 128, self.g("heads.w3h"))
+        T.conv_wgrad(self.heat_wgrad_kind, e3, d_hh, hc, 128, self.g("heads.w3h"))
         T.heads_wgrad_sparse(e3, dh_obj, mask, gidx, self.g("heads.w3s"))
         da = T.conv_dgrad(0, d_hh, self.wb("heads.w3h:dgrad"), self.zero_bias[:hc], hc)
         T.heads_dgrad_sparse(dh_obj, mask, gidx, self.wb("heads.w3:fwd"), da)

@@ -240,6 +240,10 @@ def wgrad_index(shape, kind):
         ci, co, kh, kw = torch.meshgrid(*[torch.arange(s) for s in shape], indexing="ij")
         t = kh * 4 + kw
         return ((t * (shape[1] // 64) + co // 64) * shape[0] + ci) * 64 + co % 64
+    if kind == 5:                                           # conv (Co,Ci,3,3), chunks over Co: out[(t, co/64)][ci][co%64]
+        co, ci, r, s = torch.meshgrid(*[torch.arange(s) for s in shape], indexing="ij")
+        t = r * 3 + s
+        return ((t * (shape[0] // 64) + co // 64) * shape[1] + ci) * 64 + co % 64
     co, ci, r, s = torch.meshgrid(*[torch.arange(s) for s in shape], indexing="ij")
     t = r * shape[3] + s
     return ((t * (shape[1] // 64) + ci // 64) * shape[0] + co) * 64 + ci % 64

@@ -123,7 +123,7 @@ def test_conv_dgrad(S, kind, ci, co, h):
 # ------------------------------------------------------------------------------ weight gradients
 @pytest.mark.parametrize("kind,ci,co,h,b", [(0, 64, 64, 32, 2), (0, 256, 384, 16, 2), (0, 512, 512, 16, 3),
                                             (1, 64, 128, 32, 2), (2, 128, 256, 32, 2), (3, 512, 256, 16, 2),
-                                            (3, 256, 256, 16, 1)])
+                                            (3, 256, 256, 16, 1), (5, 256, 128, 32, 2), (5, 128, 64, 16, 2)])
 def test_conv_wgrad(S, kind, ci, co, h, b):
     from scd_resnet_b200 import train_ops as T
     rng = np.random.default_rng(kind * 77 + ci + co)
@@ -136,7 +136,7 @@ def test_conv_wgrad(S, kind, ci, co, h, b):
         y = F.conv2d(x, w, stride=2)
     else:
         w = torch.zeros(co, ci, 3, 3, requires_grad=True)
-        y = F.conv2d(x, w, stride=1 if kind == 0 else 2, padding=1)
+        y = F.conv2d(x, w, stride=1 if kind in (0, 5) else 2, padding=1)      # kind 5: kind 0 with dz as the shifted operand
     dz = rnd(rng, *y.shape)
     y.backward(dz)
     out = torch.zeros(T.conv_wgrad_floats(kind, ci, co), device="cuda")
