@@ -5,7 +5,7 @@
  * The reference has no native boundary on this path: every entry point below replaces
  * a run of ATen library calls made from the reference's Python, cited per function
  * (paths relative to the upstream repository root).  The Python side of this repo
- * (scd-resnet_b200/) binds these with ctypes; INTEGRATION.md shows the stub a maintainer
+ * (scd_resnet_b200/) binds these with ctypes; INTEGRATION.md shows the stub a maintainer
  * of the reference would add.
  *
  * Conventions

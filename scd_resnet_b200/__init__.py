@@ -1,7 +1,7 @@
-"""Importable alias of the `scd-resnet_b200/` package (a hyphen cannot be imported)."""
-import os as _os
+"""scd-resnet_b200: the centerOffsetRes10 detection hot path of yang-z-03/scd-resnet on B200.
 
-_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "scd-resnet_b200")
-__path__ = [_real]
-with open(_os.path.join(_real, "__init__.py")) as _f:
-    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
+Hand-written sm_100a CUDA (libscd_b200.so, C ABI in include/scd_b200.h) behind the reference's
+own Python surface.  Import as `scd_resnet_b200`.
+"""
+from ._lib import lib, check, ScdError, LIB_PATH  # noqa: F401  (fails loudly if the library is missing)
+from . import ops, weights  # noqa: F401

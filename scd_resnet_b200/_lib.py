@@ -83,7 +83,7 @@ def _load():
     if not os.path.exists(LIB_PATH):
         raise ScdError(
             "libscd_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
-            "or `python scd-resnet_b200/build.py`. There is no CPU or PyTorch fallback." % LIB_PATH)
+            "or `python scd_resnet_b200/build.py`. There is no CPU or PyTorch fallback." % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported

@@ -3,7 +3,7 @@
 // the stem, the implicit-GEMM stages and the fused heads on one stream.  The stage list is built from the depth
 // (BasicBlock counts of ResNetSpec, ref: models/backbones/residuals.py:20-26 via centerNetOffset.py:152-155) and
 // the eight `dims` of ResNet.__init__ (residuals.py:195-201), rounded up by the host to the 64-channel k-block
-// (the half / quarter-width plugins run zero-padded, scd-resnet_b200/weights.py).
+// (the half / quarter-width plugins run zero-padded, scd_resnet_b200/weights.py).
 #include "common.cuh"
 
 namespace scd {

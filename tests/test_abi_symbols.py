@@ -45,7 +45,7 @@ def test_no_cpu_fallback():
 
 
 def test_product_never_imports_oracle():
-    pkg = os.path.join(ROOT, "scd-resnet_b200")
+    pkg = os.path.join(ROOT, "scd_resnet_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh")):
