@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SCD_ABI_VERSION 1
+#define SCD_ABI_VERSION 2
 
 #define SCD_OK          0
 #define SCD_EINVAL     -1   /* bad argument / unsupported shape   */
@@ -201,7 +201,8 @@ int scd_resnet10_infer(const float* x, const void* weights, int batch, int heigh
  * Blob: 0 stem w | 1 stem b | 2+2i, 3+2i weight / bias of igemm stage i | then heads w3, b3, w1, b1;
  * stage order per layer: [downsample, conv1, conv2] for a projection block, [conv1, conv2] otherwise, then the
  * three deconvs (scd_resnet_conv_specs lists kind / cin / cout).  Stage events: scd_resnet_num_convs + 3.
- * f16 != 0 selects fp16 operands.  scd_resnet10_infer == scd_resnet_infer(10, NULL, 0, ...).
+ * f16 = operand formats: 0 = bf16 weights and activations, 1 = fp16 both, 2 = bf16 weights x fp16 activations (the
+ * blob is packed in the weight format).  scd_resnet10_infer == scd_resnet_infer(10, NULL, 0, ...).
  * ---------------------------------------------------------------------------------- */
 int    scd_resnet_num_convs(int depth, const int* dims8);                     /* < 0: unsupported */
 int    scd_resnet_conv_specs(int depth, const int* dims8, int* h_kind, int* h_cin, int* h_cout, int n);
@@ -238,6 +239,21 @@ int scd_resnet10_infer_f16(const float* x, const void* weights, int batch, int h
                            void* workspace, size_t workspace_bytes, void* const* h_stage_events,
                            void* stream);
 
+/* Operand-format variants, fmt: 0 = bf16 weights and activations, 1 = fp16 both, 2 = MIXED: bf16 weights (B operand)
+ * x fp16 activations (A operand, stores, residual).  tcgen05 kind::f16 takes the two formats independently and
+ * multiplies them exactly into the fp32 accumulator.  With bf16 model weights the mixed plan removes the activation
+ * half of the rounding error: rel-RMS of heat / regr / offset vs the fp32 reference 4.3e-3 / 5.5e-3 / 8.7e-3 against
+ * 5.9e-3 / 7.9e-3 / 1.26e-2 with bf16 activations (tools/emulate_precision.py, profiles/accuracy_r02.json): inside the
+ * 1e-2 the north star sets for bf16 on all three heads, at the same tensor-core rate. */
+int scd_stem_fwd_fmt(int fmt, const float* x, const void* weight, const float* bias, int batch,
+                     int height, int width, void* y, void* stream);
+int scd_conv_igemm_fwd_fmt(int kind, int fmt, const void* x, const void* weight, const float* bias,
+                           const void* residual, int relu, int batch, int hin, int win,
+                           int cin, int cout, void* y, void* stream);
+int scd_heads_fwd_fmt(int fmt, const void* x, const void* w3, const float* b3, const float* w1,
+                      const float* b1, int batch, int height, int width, int cin,
+                      float* heat, float* regr, float* offset, void* stream);
+
 /* ====================================================================================
  * Training path (NetworkFactory.train, models/networkFactory.py:257-263: forward with
  * batch-statistics BatchNorm -> CenterNetLoss -> backward -> Adam).
@@ -254,7 +270,10 @@ int scd_resnet10_infer_f16(const float* x, const void* weights, int batch, int h
  *                    the mask is recomputed as z*scale + shift > 0 (valid when the forward had no residual: one
  *                    tensor less to read); a == NULL and shift == NULL: no ReLU mask;
  *                    phase 1: dz = scale*(dy - sums0/count - xhat*sums1/count), optional dy_out (the gradient
- *                    entering the residual branch), dgamma, dbeta. */
+ *                    entering the residual branch), dgamma, dbeta.  With several ranks `sums` is all-reduced between
+ *                    the phases; `local_sums` (nullable = sums) then holds THIS rank's sums saved before the
+ *                    all-reduce: dgamma / dbeta are local sums like torch.nn.SyncBatchNorm's, to be averaged over
+ *                    ranks with the other parameter gradients (DDP, models/networkFactory.py:133-134). */
 int scd_bn_stats(const void* z, size_t pixels, int C, double* sums, void* stream);
 int scd_bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean,
                     float* running_var, long long* num_batches, int C, double count, float momentum,
@@ -263,7 +282,7 @@ int scd_bn_apply(const void* z, const float* scale, const float* shift, const vo
                  size_t pixels, int C, void* out, void* stream);
 int scd_bn_bwd(const void* da, const void* a, const void* z, const float* scale, const float* shift,
                const float* mean, const float* invstd, size_t pixels, int C, double count, double* sums, void* dz,
-               void* dy_out, float* dgamma, float* dbeta, int phase, void* stream);
+               void* dy_out, float* dgamma, float* dbeta, const double* local_sums, int phase, void* stream);
 
 /* Data gradient of a forward stage of kind 0 (3x3 s1), 1 (3x3 s2, optionally fused with the gradient of the
  * parallel 1x1 s2 downsample conv: dz2) or 3 (ConvTranspose 4x4 s2), as an implicit GEMM over dz
@@ -327,19 +346,24 @@ int scd_heads_dgrad_sparse(const float* dh_objects, const uint8_t* mask, const i
  * scd_peer_allreduce_buffer_bytes(world, cap) bytes, zeroed once; d_peer_buffers is a DEVICE array of `world`
  * pointers to those buffers (peer-mapped; index = rank).  All ranks call with the same n <= cap and the same
  * seq = 1, 2, 3, ...; local[0..n) is replaced by the sum over ranks, added in rank order (bit-identical
- * everywhere).  A peer that never arrives traps the kernel after ~4 s instead of hanging the GPU. */
+ * everywhere).  The kernel waits for its peers like a NCCL collective would; timeout_cycles > 0 bounds the wait (SM clock
+ * cycles): past it the kernel stores 1 + (rank it was waiting for) into *status (device-accessible, e.g. pinned host
+ * memory the caller polls), leaves `local` untouched and returns; with status == NULL it traps instead. */
 size_t scd_peer_allreduce_buffer_bytes(int world, int cap);
 int scd_peer_allreduce_f64(double* local, int n, void* const* d_peer_buffers, int rank, int world, int cap,
-                           unsigned int seq, void* stream);
+                           unsigned int seq, long long timeout_cycles, int* status, void* stream);
 
 /* Fused Adam (torch.optim.Adam defaults, networkFactory.py:80-82) over the flat fp32 parameter buffer.
  * The gradient of parameter i is grad_scale * grads[gmap ? gmap[i] : i] (the wgrad kernels write their own
  * layout).  scd_gather_cast_bf16 refreshes the bf16 GEMM-operand copies: dst[i] = bf16(src[idx[i]]), 0 if
- * idx[i] < 0.  scd_scale_inplace: x *= *d_scale. */
+ * idx[i] < 0.  scd_gather_f32: dst[i] = src[idx[i]] * (d_scale ? *d_scale : 1), 0 if idx[i] < 0 (gradients from the
+ * wgrad layouts to the parameters' own layout, what loss.backward() leaves in param.grad,
+ * models/networkFactory.py:261).  scd_scale_inplace: x *= *d_scale. */
 int scd_adam_step(float* params, float* exp_avg, float* exp_avg_sq, const float* grads, const int* gmap,
                   size_t n, int step, float lr, float beta1, float beta2, float eps, float grad_scale,
                   void* stream);
 int scd_gather_cast_bf16(const float* src, const int* idx, size_t n, void* dst, void* stream);
+int scd_gather_f32(const float* src, const int* idx, size_t n, const float* d_scale, float* dst, void* stream);
 int scd_scale_inplace(float* x, size_t n, const float* d_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------

@@ -46,10 +46,13 @@ PROTOTYPES = {
                          + [c_void_p, c_size_t, c_void_p, c_int, c_void_p]),
     "scd_heads_fwd_c": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p] * 3 + [c_void_p]),
     "scd_heads_fwd_c_f16": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p] * 3 + [c_void_p]),
+    "scd_stem_fwd_fmt": (c_int, [c_int] + [c_void_p] * 3 + [c_int] * 3 + [c_void_p, c_void_p]),
+    "scd_conv_igemm_fwd_fmt": (c_int, [c_int, c_int] + [c_void_p] * 4 + [c_int] * 6 + [c_void_p, c_void_p]),
+    "scd_heads_fwd_fmt": (c_int, [c_int] + [c_void_p] * 5 + [c_int] * 4 + [c_void_p] * 3 + [c_void_p]),
     "scd_bn_stats": (c_int, [c_void_p, c_size_t, c_int, c_void_p, c_void_p]),
     "scd_bn_finalize": (c_int, [c_void_p] * 6 + [c_int, ctypes.c_double, c_float, c_float] + [c_void_p] * 4 + [c_void_p]),
     "scd_bn_apply": (c_int, [c_void_p] * 4 + [c_int, c_size_t, c_int, c_void_p, c_void_p]),
-    "scd_bn_bwd": (c_int, [c_void_p] * 7 + [c_size_t, c_int, ctypes.c_double] + [c_void_p] * 5 + [c_int, c_void_p]),
+    "scd_bn_bwd": (c_int, [c_void_p] * 7 + [c_size_t, c_int, ctypes.c_double] + [c_void_p] * 6 + [c_int, c_void_p]),
     "scd_conv_igemm_dgrad": (c_int, [c_int] + [c_void_p] * 5 + [c_int] * 5 + [c_void_p, c_void_p]),
     "scd_conv_wgrad_out_floats": (c_size_t, [c_int, c_int, c_int]),
     "scd_conv_wgrad": (c_int, [c_int, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p, c_void_p]),
@@ -62,9 +65,11 @@ PROTOTYPES = {
     "scd_heads_wgrad_sparse": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p, c_void_p]),
     "scd_heads_dgrad_sparse": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p, c_void_p]),
     "scd_peer_allreduce_buffer_bytes": (c_size_t, [c_int, c_int]),
-    "scd_peer_allreduce_f64": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, ctypes.c_uint, c_void_p]),
+    "scd_peer_allreduce_f64": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, ctypes.c_uint, ctypes.c_longlong,
+                                        c_void_p, c_void_p]),
     "scd_adam_step": (c_int, [c_void_p] * 5 + [c_size_t, c_int] + [c_float] * 5 + [c_void_p]),
     "scd_gather_cast_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "scd_gather_f32": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "scd_scale_inplace": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "scd_augment_batch": (c_int, [c_void_p] * 3 + [c_int] + [c_void_p] * 4 + [c_int, c_float, c_float] + [c_void_p] * 3 + [c_void_p]),
     "scd_centernet_eval_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
@@ -89,8 +94,8 @@ def _load():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.scd_abi_version() != 1:
-        raise ScdError("libscd_b200.so ABI version %d, expected 1" % lib.scd_abi_version())
+    if lib.scd_abi_version() != 2:
+        raise ScdError("libscd_b200.so ABI version %d, expected 2" % lib.scd_abi_version())
     return lib
 
 

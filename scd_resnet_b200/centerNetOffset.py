@@ -53,13 +53,14 @@ class CenterNetResidual(torch.nn.Module):
     64-channel granularity, weights.arch_of).  The Bottleneck depths 50 / 101 are not built."""
     terminalDimension = 128                                                      # ref: centerNetOffset.py:146-148
 
-    def __init__(self, numLayers=10, dims=(64, 64, 128, 256, 512, 256, 256, 256), precision="bf16"):
-        """precision: 16-bit format of the eval-mode tensor-core path, "bf16" (BASELINE's configuration) or "fp16"
-        (same speed, ~8x smaller rounding error: 1e-3 instead of 1e-2 against the fp32 reference).  It can also be
-        switched later through the `precision` attribute."""
+    def __init__(self, numLayers=10, dims=(64, 64, 128, 256, 512, 256, 256, 256), precision=None):
+        """precision: operand formats of the eval-mode tensor-core path (weights.PRECISIONS): "mixed" (default: bf16
+        weights x fp16 activations, every head within the north star's 1e-2 of the fp32 reference), "bf16" (weights and
+        activations bf16: the offset head sits at 1.26e-2), "fp16" (both fp16: 1e-3).  All run at the same tensor-core
+        rate.  It can also be switched later through the `precision` attribute."""
         super().__init__()
-        if precision not in ("bf16", "fp16"):
-            raise ScdError("precision must be 'bf16' or 'fp16'")
+        precision = precision or weights.DEFAULT_PRECISION
+        weights.precision_spec(precision)
         self.precision = precision
         dims = list(dims)
         if numLayers not in weights.BLOCKS:
@@ -100,6 +101,7 @@ class CenterNetResidual(torch.nn.Module):
         self._blob = None
         self._blob_key = None
         self._workspace = None
+        self._engine = None                      # training.TrainEngine, built by the first train-mode forward
 
     def initialize(self, num_layers):
         """Same distributions as the reference's ResNet.initialize (ref: residuals.py:336-353,
@@ -123,7 +125,7 @@ class CenterNetResidual(torch.nn.Module):
             sd = {k: v.detach() for k, v in self.state_dict().items()}
             self._arch = weights.arch_of(sd)
             self._blob = weights.pack_infer_blob(sd, next(self.parameters()).device,
-                                                 torch.float16 if self.precision == "fp16" else torch.bfloat16)
+                                                 weights.precision_spec(self.precision)[1])
             self._blob_key = key
         return self._blob
 
@@ -134,15 +136,93 @@ class CenterNetResidual(torch.nn.Module):
         if not inp.is_cuda:
             raise ScdError("CenterNetResidual (scd_b200) runs on CUDA only; move the module and input to a B200")
         if self.training:
-            from . import training
-            ret = training.forward_train(self, inp)
+            ret = self._forward_train(inp.float())
         else:
             with torch.no_grad():
                 blob = self._infer_blob()
                 heat, regr, off, self._workspace = ops.resnet_infer(inp.float(), blob, self._arch[0], self._arch[2],
-                                                                    self._workspace, fp16=self.precision == "fp16")
+                                                                    self._workspace,
+                                                                    fmt=weights.precision_spec(self.precision)[0])
             ret = {"heatmap": heat, "regr": regr, "offset": off}
         return [ret] if not decode else self.decoder(ret)
+
+
+    # ------------------------------------------------------------------ train mode
+    def train_engine(self):
+        """The native training engine behind the train-mode forward (training.TrainEngine): parameters re-bound as
+        views of one flat fp32 buffer (state_dict, optimizers and DDP keep working on the same nn.Parameter objects),
+        16-bit operand copies, tape-based backward.  (Re)built when the parameters moved (module.to(), .half()).
+        BatchNorm statistics are shared across ranks exactly when the BatchNorm children are SyncBatchNorm
+        (torch.nn.SyncBatchNorm.convert_sync_batchnorm, ref: models/networkFactory.py:133); gradient averaging is
+        left to whoever wraps the module (DistributedDataParallel, :134)."""
+        from . import training
+        eng = self._engine
+        if eng is None or not eng.owns(self):
+            sync = [m for m in self.modules() if isinstance(m, torch.nn.SyncBatchNorm)]
+            group = None
+            if sync and torch.distributed.is_available() and torch.distributed.is_initialized():
+                g = sync[0].process_group if sync[0].process_group is not None else torch.distributed.group.WORLD
+                if torch.distributed.get_world_size(g) > 1:
+                    group = g
+            eng = training.TrainEngine(self, process_group=None, stat_group=group, dense_heads=True)
+            self._engine = eng
+        return eng
+
+    def _forward_train(self, x):
+        """ref: ResNet.forward in train() mode (residuals.py:312-334): batch-statistics BatchNorm, autograd graph to
+        every parameter.  One autograd node whose backward runs the native backward pass (models/networkFactory.py:
+        257-263 drives it: zero_grad -> forward -> loss -> backward -> optimizer.step)."""
+        eng = self.train_engine()
+        names = [k for k, _ in self.named_parameters()]
+        params = [p for _, p in self.named_parameters()]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            heat, regr, off = _TrainForwardFn.apply(eng, names, x, *params)
+        else:
+            (heat, regr, off), _ = eng.forward(x, keep=False)
+        return {"heatmap": heat, "regr": regr, "offset": off}
+
+
+class _TrainForwardFn(torch.autograd.Function):
+    """forward = TrainEngine.forward (tape kept on the node), backward = TrainEngine.backward + one gather of the
+    weight gradients into the parameters' own layouts.  The node advertises `scd_accepts_sparse`: this package's
+    CenterNetLoss then hands the masked-L1 gradients over as a (B,30,6) object list (`scd_sparse`) instead of dense
+    maps, which keeps the sparse heads backward of the native step; any other loss takes the dense route."""
+
+    @staticmethod
+    def forward(ctx, eng, names, x, *params):
+        (heat, regr, off), tape = eng.forward(x, keep=True)
+        ctx.scd_engine, ctx.scd_tape, ctx.scd_names = eng, tape, names
+        ctx.scd_accepts_sparse, ctx.scd_sparse = True, None
+        return heat, regr, off
+
+    @staticmethod
+    def backward(ctx, d_heat, d_regr, d_off):
+        eng, tape = ctx.scd_engine, ctx.scd_tape
+        if tape is None:
+            raise ScdError("CenterNetResidual (scd_b200): backward through the same forward twice (the tape is released "
+                           "after the first backward; retain_graph is not supported)")
+        ctx.scd_tape = None
+        like = tape["e3"]
+        b, h, w = like.shape[0], like.shape[1], like.shape[2]
+        if d_heat is None:
+            d_heat = torch.zeros(b, 1, h, w, dtype=torch.float32, device=like.device)
+        sparse = ctx.scd_sparse
+        ctx.scd_sparse = None
+        if sparse is not None:
+            eng.backward(tape, d_heat.float(), sparse=sparse)
+        else:
+            zeros = lambda c: torch.zeros(b, c, h, w, dtype=torch.float32, device=like.device)
+            eng.backward(tape, d_heat.float(), dense=(d_regr.float() if d_regr is not None else zeros(4),
+                                                      d_off.float() if d_off is not None else zeros(2)))
+        scale = None
+        if eng.world > 1:                                     # an engine that averages gradients itself (no DDP wrapper)
+            eng.finish_reduce()
+            scale = torch.full((1,), 1.0 / eng.world, dtype=torch.float32, device=like.device)
+        grads = eng.grads_reference_layout(dense=sparse is None, scale=scale)
+        out = [None, None, None]
+        for i, k in enumerate(ctx.scd_names):
+            out.append(grads[k] if ctx.needs_input_grad[3 + i] else None)
+        return tuple(out)
 
 
 def decodeCenterNet(outputDictionary, K=100, nmsKernelSize=3, **kwargs):
@@ -196,6 +276,43 @@ class _CenterNetLossFn(torch.autograd.Function):
         return dh * s, dr * s, do * s, None, None, None, None, None, None
 
 
+_zero_scalar = {}
+
+
+def _placeholder(shape, device):
+    """A stride-0 zero tensor of `shape`: the dense regr / offset gradients nobody reads when the object-list form was
+    handed to the network's backward node."""
+    z = _zero_scalar.get(device)
+    if z is None:
+        z = _zero_scalar[device] = torch.zeros((), dtype=torch.float32, device=device)
+    return z.expand(shape)
+
+
+class _CenterNetLossSparseFn(torch.autograd.Function):
+    """Same fused kernel, masked-L1 gradients kept as the (B,30,6) object list and passed to the network's backward
+    node (`node.scd_sparse`), scaled by the upstream gradient of the total like the dense ones."""
+
+    @staticmethod
+    def forward(ctx, heat, regr, off, gt_heat, mask, regr6, idx, regr_w, off_w, npos, node):
+        losses, d_heat, d_obj = ops.centernet_loss_sparse(heat.detach(), regr.detach(), off.detach(), gt_heat, mask,
+                                                          regr6, idx, regr_w, off_w, npos=npos, sigmoid_inplace=True)
+        ctx.save_for_backward(d_heat, d_obj)
+        ctx.scd_node, ctx.scd_meta = node, (mask, idx, tuple(regr.shape), tuple(off.shape))
+        return losses
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import train_ops as T
+        d_heat, d_obj = ctx.saved_tensors
+        mask, idx, regr_shape, off_shape = ctx.scd_meta
+        s = g[0:1].contiguous()                                  # d (what is differentiated) / d total, on the device
+        T.scale_inplace(d_heat, s)
+        T.scale_inplace(d_obj, s)
+        ctx.scd_node.scd_sparse = (d_obj, mask, idx)
+        return (d_heat, _placeholder(regr_shape, d_heat.device), _placeholder(off_shape, d_heat.device),
+                None, None, None, None, None, None, None, None)
+
+
 class CenterNetLoss(torch.nn.Module):
     """ref: CenterNetLoss models/centerNetOffset.py:170-217 (focal = focalLoss, regression = L1LossMask)."""
 
@@ -208,7 +325,14 @@ class CenterNetLoss(torch.nn.Module):
         if len(outs) != 1:
             raise ScdError("CenterNetLoss (scd_b200): one prediction dict expected (ResNet returns one)")
         out = outs[0]
-        losses = _CenterNetLossFn.apply(out["heatmap"], out["regr"], out["offset"], targets[0], targets[1],
-                                        targets[2], targets[3], float(self.regressionWeight),
-                                        float(self.offsetWeight))
+        heat, regr, off = out["heatmap"], out["regr"], out["offset"]
+        node = regr.grad_fn
+        if (torch.is_grad_enabled() and node is not None and getattr(node, "scd_accepts_sparse", False)
+                and heat.grad_fn is node and off.grad_fn is node and getattr(node, "scd_tape", None) is not None):
+            npos = targets[4] if len(targets) > 4 else None      # [N_pos, mask.sum()] counters of render_targets
+            losses = _CenterNetLossSparseFn.apply(heat, regr, off, targets[0], targets[1], targets[2], targets[3],
+                                                  float(self.regressionWeight), float(self.offsetWeight), npos, node)
+        else:
+            losses = _CenterNetLossFn.apply(heat, regr, off, targets[0], targets[1], targets[2], targets[3],
+                                            float(self.regressionWeight), float(self.offsetWeight))
         return losses[0].unsqueeze(0), [losses[1], losses[2], losses[3]]

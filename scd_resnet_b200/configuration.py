@@ -10,10 +10,13 @@ _DEFAULTS = {
     "learningRate": 0.00025, "learningRateDecay": [80000], "learningRateDecayRate": [10],
     "currentIter": 0, "iterations": 117000, "validation": 200, "snapshot": 2000,
     "batchSize": 32, "validationBatchSize": 160,
-    "naming": "{modelName}.{trainName}.{currentIter}.pth", "pretrain": None, "optimizer": "adam",
+    "naming": "{modelName}.{trainName}.{currentIter}.pth", "namingOptimizer": "{naming}.{optimizer}.pth",
+    "pretrain": None, "optimizer": "adam",
     "dirData": "trainer.dataset.{datasetName}", "dirModel": "scd_resnet_b200.trainer.model.{modelName}",
     "dirTemp": "/tmp/scd_b200/temp/", "dirPretrain": "/tmp/scd_b200/pretrain/", "dirResult": "/tmp/scd_b200/results/",
-    "dirDataset": "/tmp/scd_b200/datasets/", "useGPU": True,
+    "dirConfig": "/tmp/scd_b200/configs/", "dirDataset": "/tmp/scd_b200/datasets/",
+    "dirDatafile": "{dirDataset}{datasetName}.d", "dirDataSplitProfile": "{dirDataset}{datasetName}.split.json",
+    "useGPU": True,
 }
 
 
@@ -36,7 +39,11 @@ class Configuration:
 
     def expand(self, key):
         v = self.config[key]
-        return v.format(**self.config) if isinstance(v, str) else v
+        for _ in range(3):                          # templates may nest one level ("{naming}.{optimizer}.pth")
+            if not isinstance(v, str) or "{" not in v:
+                break
+            v = v.format(**self.config)
+        return v
 
     def __getattr__(self, key):
         cfg = self.__dict__.get("config", {})

@@ -161,13 +161,15 @@ bn_bwd_apply_kernel(const uint4* __restrict__ da, const uint4* __restrict__ a, c
                     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                     const float* __restrict__ invstd, const double* __restrict__ sums, double count,
                     size_t n8, int cgroups, uint4* __restrict__ dz, uint4* __restrict__ dy_out,
-                    float* __restrict__ dgamma, float* __restrict__ dbeta)
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, const double* __restrict__ grad_sums)
 {
     const int C = cgroups * 8;
     if (blockIdx.x == 0) {
+        // d gamma = sum(dy xhat), d beta = sum(dy) over THIS rank's pixels (grad_sums = the sums before the cross-rank
+        // all-reduce): torch.nn.SyncBatchNorm does the same and DDP then averages the parameter gradients over ranks
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            if (dbeta) dbeta[c] = (float)sums[c];
-            if (dgamma) dgamma[c] = (float)sums[C + c];
+            if (dbeta) dbeta[c] = (float)grad_sums[c];
+            if (dgamma) dgamma[c] = (float)grad_sums[C + c];
         }
     }
     // The block size, hence the grid stride, is a multiple of cgroups (apply_block), so a thread
@@ -275,9 +277,10 @@ extern "C" int scd_bn_apply(const void* z, const float* scale, const float* shif
 
 extern "C" int scd_bn_bwd(const void* da, const void* a, const void* z, const float* scale, const float* shift,
                           const float* mean, const float* invstd, size_t pixels, int C, double count, double* sums, void* dz,
-                          void* dy_out, float* dgamma, float* dbeta, int phase, void* stream)
+                          void* dy_out, float* dgamma, float* dbeta, const double* local_sums, int phase, void* stream)
 {
-    // phase 0: reduce (sums <- sum dy, sum dy*xhat); phase 1: apply (uses sums, possibly all-reduced in between)
+    // phase 0: reduce (sums <- sum dy, sum dy*xhat); phase 1: apply (uses sums, possibly all-reduced in between;
+    // local_sums = this rank's sums saved before that all-reduce, the source of d gamma / d beta; null = sums)
     using namespace scd;
     if (!da || !z || !scale || !mean || !invstd || !sums || C % 8) return fail(SCD_EINVAL, "scd_bn_bwd: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
@@ -302,7 +305,8 @@ extern "C" int scd_bn_bwd(const void* da, const void* a, const void* z, const fl
         const size_t n8 = pixels * (size_t)(C / 8);
         bn_bwd_apply_kernel<<<stream_grid(n8, ablock * 4), ablock, 0, st>>>(
             static_cast<const uint4*>(da), static_cast<const uint4*>(a), static_cast<const uint4*>(z), scale, shift, mean,
-            invstd, sums, count, n8, C / 8, static_cast<uint4*>(dz), static_cast<uint4*>(dy_out), dgamma, dbeta);
+            invstd, sums, count, n8, C / 8, static_cast<uint4*>(dz), static_cast<uint4*>(dy_out), dgamma, dbeta,
+            local_sums ? local_sums : sums);
         SCD_LAUNCH_CHECK("bn_bwd_apply_kernel");
     }
     return SCD_OK;

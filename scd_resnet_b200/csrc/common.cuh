@@ -39,6 +39,19 @@ inline int fail(int code, const char* fmt, ...) {
                              cudaGetErrorString(_e));                                     \
     } while (0)
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute is per DEVICE, so it is tracked per device
+// (a process that drives several GPUs, or a C consumer on cuda:1, gets it on each of them).
+#define SCD_SMEM_ATTR(kernel, bytes)                                                                     \
+    do {                                                                                                 \
+        static bool scd_attr_done_[64] = {};                                                             \
+        int scd_dev_ = 0;                                                                                \
+        SCD_CUDA_CHECK(cudaGetDevice(&scd_dev_));                                                        \
+        if (scd_dev_ < 0 || scd_dev_ >= 64 || !scd_attr_done_[scd_dev_]) {                               \
+            SCD_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            if (scd_dev_ >= 0 && scd_dev_ < 64) scd_attr_done_[scd_dev_] = true;                         \
+        }                                                                                                \
+    } while (0)
+
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 
 __device__ __forceinline__ float warp_sum(float v) {

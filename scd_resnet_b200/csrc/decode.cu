@@ -840,12 +840,7 @@ extern "C" int scd_decode_topk_impl(const float* heat, const float* regr, const 
     // Measured on B200 (tools/bench_decode_impls.py): the histogram kernel is faster than the warp-per-image kernel at
     // every batch size: 18 vs 55 us at 64 images, 90 vs 107 us at 2048, 295 vs 359 us at 8192.
     if (impl != 2) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            SCD_CUDA_CHECK(cudaFuncSetAttribute(scd::decode_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)sizeof(scd::DecSmem)));
-            attr_done = true;
-        }
+        SCD_SMEM_ATTR(scd::decode_hist_kernel, sizeof(scd::DecSmem));
         scd::decode_hist_kernel<<<batch, scd::DH_THREADS, sizeof(scd::DecSmem), st>>>(heat, regr, offset, batch, K, scores, idx, ys, xs, off_out,
                                                                    regr_out, planes);
         SCD_LAUNCH_CHECK("decode_hist_kernel");

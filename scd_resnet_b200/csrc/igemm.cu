@@ -42,10 +42,7 @@ struct alignas(64) IgemmParams {
     int b_resident;                 // BN = 64 only: the whole weight matrix (<= 9 k-blocks) stays in shared memory
     int row_mode;                   // BN = 64, 3x3 s1, Cin = 64, W = 128: one image row per tile, A = 3-row halo strip loaded once
     int bo_mode;                    // row_mode: put (start address >> 7) & 7 into the descriptor's base_offset field
-    int mc;                         // CTA-pair mode: clusters of 2 CTAs on neighbouring tiles of the same weight rows run
-                                    // ONE tcgen05.mma.cta_group::2 (M = 256) per step; each CTA stages its own 128 pixels
-                                    // of A and HALF of the weight k-block, which halves the shared-memory traffic per SM
-    CUtensorMap tmBh;               // weight map with a 64-row box (the halves are loaded in 64-row pieces)
+    uint32_t b_fmt;                 // 16-bit format of the WEIGHT operand: 1 = bf16, 0 = fp16 (activations: template F16)
     CUtensorMap tmHalo;             // box {64 ch, 130 x, 3 y}
     CUtensorMap tmOutRow;           // box {64 ch, 32 x, 1 y}
     CUtensorMap tmRes;              // row mode with a residual: box {64 ch, 128 x, 1 y}, prefetched by the producer
@@ -61,13 +58,10 @@ struct alignas(64) IgemmParams {
     float* off;
 };
 
-// PAIR (CTA-pair mode): a stage holds this CTA's half of the weight k-block only, so the same shared memory gives a
-// deeper pipeline (the stage round trip now crosses the pair: leader's commit -> peer's producer -> leader's barrier).
-template <int BN, bool PAIR = false> struct IgemmCfg {
+template <int BN> struct IgemmCfg {
     static constexpr int B_BYTES = BN * IG_BK * 2;
-    static constexpr int STAGE_BYTES = IG_A_BYTES + (PAIR ? B_BYTES / 2 : B_BYTES);
-    static constexpr int STAGES = PAIR ? ((BN == 128) ? 8 : (BN == 256 ? 6 : 5))
-                                       : ((BN == 64) ? 5 : (BN == 128 ? 6 : (BN == 256 ? 4 : 3)));
+    static constexpr int STAGE_BYTES = IG_A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 64) ? 5 : (BN == 128 ? 6 : (BN == 256 ? 4 : 3));
     static constexpr int RES_B_BLOCKS = (BN == 64) ? 9 : 0;     // resident weights: 9 k-blocks x 8 KB (layer1: 3x3, Cin 64)
     static constexpr int HALO_W = 130, HALO_BYTES = 3 * HALO_W * 128;       // row mode: 3 rows x 130 px x 64 ch
     static constexpr int HALO_STAGE = 50 * 1024, HALO_STAGES = 2;           // fits into the 5 x 24 KB stage area
@@ -87,14 +81,12 @@ template <int BN, bool PAIR = false> struct IgemmCfg {
     static constexpr int SMEM_BYTES = OFF_CONST + CONST_BYTES + 1024 /*align slack*/;
 };
 
-// PAIR: CTA-pair mode (IgemmParams::mc), a separate instantiation: a kernel that contains cta_group::2 instructions can
-// only be launched as clusters of two.
-template <int BN, int EPI, bool F16, bool PAIR>
+template <int BN, int EPI, bool F16>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_kernel(const __grid_constant__ IgemmParams p)
 {
     using A16 = tc::Act<F16>;
-    using Cfg = IgemmCfg<BN, PAIR>;
+    using Cfg = IgemmCfg<BN>;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t smem_base = (tc::smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* smem_gen = smem_dyn + (smem_base - tc::smem_u32(smem_dyn));
@@ -108,7 +100,6 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
     const uint32_t resb_bar = bar_base + 8u * (2 * Cfg::STAGES + 5);          // resident weights have landed
     auto rfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 6 + s); };    // row mode: residual row landed
     auto rempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 8 + s); };   //           ... and was consumed
-    auto pfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 10 + s); };    // pair mode, leader: the peer's stage landed
     const bool resb = Cfg::RES_B_BLOCKS > 0 && p.b_resident != 0;
     uint32_t* tmem_slot_gen = reinterpret_cast<uint32_t*>(smem_gen + Cfg::OFF_BAR + 8 * (2 * Cfg::STAGES + 4));
     float* head_const = reinterpret_cast<float*>(smem_gen + Cfg::OFF_CONST);
@@ -118,18 +109,13 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&p.tmB);
         tc::tma_prefetch_desc(&p.tmA[0]);
-        // pair mode: the LEADER's full barriers collect both CTAs' loads (one arrive.expect_tx each) and its tmem_empty
-        // barriers both CTAs' epilogue threads; empty / tmem_full are per CTA, signalled by the leader's multicast commits
-        for (int s = 0; s < Cfg::STAGES; ++s) { tc::mbar_init(full_bar(s), 1); tc::mbar_init(empty_bar(s), 1); tc::mbar_init(pfull_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { tc::mbar_init(tfull_bar(s), 1); tc::mbar_init(tempty_bar(s), PAIR ? 256 : 128); }
+        for (int s = 0; s < Cfg::STAGES; ++s) { tc::mbar_init(full_bar(s), 1); tc::mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(tfull_bar(s), 1); tc::mbar_init(tempty_bar(s), 128); }
         tc::mbar_init(resb_bar, 1);
         for (int s = 0; s < 2; ++s) { tc::mbar_init(rfull_bar(s), 1); tc::mbar_init(rempty_bar(s), 128); }
         tc::fence_barrier_init();
     }
-    if (warp == 1) {
-        if (PAIR) tc::tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot);
-        else tc::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
-    }
+    if (warp == 1) tc::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
     if (EPI != EPI_STORE) {
         for (int i = threadIdx.x; i < 384 + 7 * 128 + 7; i += IG_THREADS) {
             float v;
@@ -141,10 +127,8 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (PAIR) tc::cluster_sync_all();          // the peer's barriers exist before anything is multicast to them
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
-    const uint32_t cta_rank = PAIR ? tc::cluster_ctarank() : 0u;        // pair mode: rank inside the 2-CTA cluster
 
 
     if (warp == 0) {
@@ -189,21 +173,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
                         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                         const uint32_t sb = sa + IG_A_BYTES;
                         const int kcol = (tap * p.cin_blocks + cb) * IG_BK;
-                        if (PAIR) {
-                            // my 128 pixels of A and my half of the weight k-block, on my own barrier (the peer's issuer
-                            // thread forwards "landed" to the leader, see below)
-                            tc::mbar_arrive_expect_tx(full_bar(stage), IG_A_BYTES + Cfg::B_BYTES / 2);
-                            tc::tma_load_4d(ma, full_bar(stage), sa, cb * IG_BK, ax, ay, img);
-                            // the pair's B operand of one MMA is [CTA 0's rows; CTA 1's rows]: for N <= 256 my rows are
-                            // [rank * N/2, +N/2); N = 384 runs as a 256-wide and a 128-wide MMA, so my rows are
-                            // [128 rank, +128) followed by [256 + 64 rank, +64)
-#pragma unroll
-                            for (int j = 0; j < BN / 128; ++j) {
-                                const int r0 = (BN > 256) ? (j < 2 ? 128 * (int)cta_rank + 64 * j : 256 + 64 * (int)cta_rank)
-                                                          : (BN / 2) * (int)cta_rank + 64 * j;
-                                tc::tma_load_2d(&p.tmBh, full_bar(stage), sb + j * 64 * IG_BK * 2, kcol, brow + r0);
-                            }
-                        } else {
+                        {
                             tc::mbar_arrive_expect_tx(full_bar(stage), resb ? IG_A_BYTES : Cfg::STAGE_BYTES);
                             tc::tma_load_4d(ma, full_bar(stage), sa, cb * IG_BK, ax, ay, img);
                             if (!resb) tc::tma_load_2d(&p.tmB, full_bar(stage), sb, kcol, brow);
@@ -220,8 +190,8 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            constexpr uint32_t idesc_main = tc::umma_idesc_16(IG_BM, BN > 256 ? 256 : BN, A16::kFmt);
-            constexpr uint32_t idesc_tail = tc::umma_idesc_16(IG_BM, BN > 256 ? BN - 256 : 16, A16::kFmt);
+            const uint32_t idesc_main = tc::umma_idesc_16ab(IG_BM, BN > 256 ? 256 : BN, A16::kFmt, p.b_fmt);
+            const uint32_t idesc_tail = tc::umma_idesc_16ab(IG_BM, BN > 256 ? BN - 256 : 16, A16::kFmt, p.b_fmt);
             int stage = 0; uint32_t phase = 0;
             uint32_t it = 0;
             if (resb) { tc::mbar_wait(resb_bar, 0); tc::tc_fence_after(); }
@@ -250,51 +220,6 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
                     tc::umma_commit(empty_bar(stage));
                     tc::umma_commit(tfull_bar(as));
                     if (++stage == Cfg::HALO_STAGES) { stage = 0; phase ^= 1u; }
-                }
-            } else
-            if (PAIR) {
-                // CTA pair: the leader issues M = 256 MMAs over both CTAs' operands; the peer's issuer thread idles
-                constexpr uint32_t idesc2_main = tc::umma_idesc_16(2 * IG_BM, BN > 256 ? 256 : BN, A16::kFmt);
-                constexpr uint32_t idesc2_tail = tc::umma_idesc_16(2 * IG_BM, BN > 256 ? BN - 256 : 16, A16::kFmt);
-                if (cta_rank != 0) {
-                    // peer: forward "my stage has landed" to the leader, stage by stage
-                    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                        const int k_blocks = p.n_taps[(t / (p.n_tiles_n * p.tiles_x * p.tiles_y)) % p.n_par] * p.cin_blocks;
-                        for (int kb = 0; kb < k_blocks; ++kb) {
-                            tc::mbar_wait(full_bar(stage), phase);
-                            tc::mbar_arrive_cluster(tc::mapa(pfull_bar(stage), 0u));
-                            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
-                        }
-                    }
-                } else
-                for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-                    const int k_blocks = p.n_taps[(t / (p.n_tiles_n * p.tiles_x * p.tiles_y)) % p.n_par] * p.cin_blocks;
-                    const uint32_t as = (Cfg::ACC_STAGES == 2) ? (it & 1u) : 0u;
-                    const uint32_t aphase = (Cfg::ACC_STAGES == 2) ? ((it >> 1) & 1u) : (it & 1u);
-                    tc::mbar_wait(tempty_bar(as), aphase ^ 1u);          // both CTAs' epilogues have drained this accumulator
-                    tc::tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + as * BN;
-                    for (int kb = 0; kb < k_blocks; ++kb) {
-                        tc::mbar_wait(full_bar(stage), phase);           // my loads of this stage have landed
-                        tc::mbar_wait(pfull_bar(stage), phase);          // ... and the peer's
-                        tc::tc_fence_after();
-                        const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-                        const uint32_t sb = sa + IG_A_BYTES;
-#pragma unroll
-                        for (int k = 0; k < IG_BK / 16; ++k) {
-                            const uint64_t adesc = tc::umma_desc_sw128(sa + k * 32);
-                            const uint64_t bdesc = tc::umma_desc_sw128(sb + k * 32);
-                            const uint32_t acc = (kb | k) ? 1u : 0u;
-                            tc::umma_bf16_2sm(d_tmem, adesc, bdesc, idesc2_main, acc);
-                            if (BN > 256) {
-                                const uint64_t bdesc2 = tc::umma_desc_sw128(sb + 128 * IG_BK * 2 + k * 32);
-                                tc::umma_bf16_2sm(d_tmem + 256, adesc, bdesc2, idesc2_tail, acc);
-                            }
-                        }
-                        tc::umma_commit_2sm(empty_bar(stage), (uint16_t)3);              // frees the stage in both CTAs
-                        if (kb == k_blocks - 1) tc::umma_commit_2sm(tfull_bar(as), (uint16_t)3);
-                        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
-                    }
                 }
             } else
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
@@ -382,8 +307,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
                     tc::tmem_ld_wait();
                     if (c0 + 64 >= BN) {                     // last TMEM read of this tile: release the accumulator
                         tc::tc_fence_before();
-                        if (PAIR) tc::mbar_arrive_cluster(tc::mapa(tempty_bar(as), 0u));     // at the leader, who issues the MMAs
-                        else tc::mbar_arrive(tempty_bar(as));
+                        tc::mbar_arrive(tempty_bar(as));
                     }
                     if (lane == 0) tc::bulk_wait_read0();    // previous store has finished reading the staging tile
                     __syncwarp();
@@ -485,8 +409,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
             }
             if (EPI != EPI_STORE) {
                 tc::tc_fence_before();
-                if (PAIR) tc::mbar_arrive_cluster(tc::mapa(tempty_bar(as), 0u));
-                else tc::mbar_arrive(tempty_bar(as));        // 128 arrivals release the accumulator
+                tc::mbar_arrive(tempty_bar(as));             // 128 arrivals release the accumulator
             }
         }
         if (EPI != EPI_HEADS && lane == 0) tc::bulk_wait0(); // all TMA stores of this warp have completed
@@ -495,11 +418,9 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
 
     tc::tc_fence_before();
     __syncthreads();
-    if (PAIR) tc::cluster_sync_all();          // no CTA of the pair exits while the other may still signal it
     if (warp == 1) {
         tc::tc_fence_after();
-        if (PAIR) tc::tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base);
-        else tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+        tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
     }
 }
 
@@ -509,47 +430,10 @@ static int launch_igemm(const IgemmParams& p, cudaStream_t st)
 {
     using Cfg = IgemmCfg<BN>;
     const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-    if constexpr (BN >= 128) {
-        if (p.mc) {
-            using Cfg2 = IgemmCfg<BN, true>;
-            static_assert(Cfg2::SMEM_BYTES <= 227 * 1024, "pair-mode shared memory");
-            static bool attr2_done = false;
-            if (!attr2_done) {
-                SCD_CUDA_CHECK(cudaFuncSetAttribute(igemm_kernel<BN, EPI, F16, true>,
-                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
-                attr2_done = true;
-            }
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)(grid & ~1), 1, 1);
-            cfg.blockDim = dim3(IG_THREADS, 1, 1);
-            cfg.dynamicSmemBytes = Cfg2::SMEM_BYTES;
-            cfg.stream = st;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr; cfg.numAttrs = 1;
-            SCD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, igemm_kernel<BN, EPI, F16, true>, p));
-            return SCD_OK;
-        }
-    }
-    static bool attr_done = false;     // idempotent per-process kernel attribute
-    if (!attr_done) {
-        SCD_CUDA_CHECK(cudaFuncSetAttribute(igemm_kernel<BN, EPI, F16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            Cfg::SMEM_BYTES));
-        attr_done = true;
-    }
-    igemm_kernel<BN, EPI, F16, false><<<grid, IG_THREADS, Cfg::SMEM_BYTES, st>>>(p);
+    SCD_SMEM_ATTR((igemm_kernel<BN, EPI, F16>), Cfg::SMEM_BYTES);
+    igemm_kernel<BN, EPI, F16><<<grid, IG_THREADS, Cfg::SMEM_BYTES, st>>>(p);
     SCD_LAUNCH_CHECK("igemm_kernel");
     return SCD_OK;
-}
-
-// CTA-pair mode (2-CTA clusters, tcgen05.mma.cta_group::2): tiles 2j and 2j + 1 must use the same weight rows and taps.
-static void choose_pair_mode(IgemmParams& p, int bn)
-{
-    // Off by default: measured on B200 (kernel notes) this mode is correct but slower than cta_group::1.
-    static const int mc_env = [] { const char* e = getenv("SCD_IGEMM_PAIR"); return e ? atoi(e) : 0; }();
-    p.mc = (mc_env && bn >= 128 && !p.b_resident && !p.row_mode && p.n_tiles_n == 1 && p.total_tiles >= 2 &&
-            p.total_tiles % 2 == 0 && (p.tiles_x * p.tiles_y) % 2 == 0) ? 1 : 0;
 }
 
 // kind: 0 = conv 3x3 s1 p1          1 = conv 3x3 s2 p1         2 = conv 1x1 s2      3 = deconv 4x4 s2 p1
@@ -655,8 +539,10 @@ static int pick_bn(int cout) { return cout >= 256 ? 256 : (cout >= 128 ? 128 : 6
 
 static int conv_igemm(int kind, const void* x, const void* x2, const void* weight, const float* bias,
                       const void* residual, int relu, int batch, int hin, int win, int cin, int cout, void* y,
-                      void* stream, bool f16 = false)
+                      void* stream, bool f16 = false, int w_f16 = -1)
 {
+    // f16: activations (input, residual, output) are fp16 instead of bf16; w_f16: the packed weights are fp16 (default:
+    // like the activations).  f16 && !w_f16 = the "mixed" plan: bf16 weights x fp16 activations.
     using namespace scd;
     if (batch <= 0) return SCD_OK;
     if (!x || !weight || !bias || !y) return fail(SCD_EINVAL, "scd_conv_igemm: null pointer");
@@ -667,6 +553,7 @@ static int conv_igemm(int kind, const void* x, const void* x2, const void* weigh
     const int bn = pick_bn(cout);
     if (cout % bn) return fail(SCD_EINVAL, "Cout = %d unsupported", cout);
     p.cout = cout; p.n_tiles_n = cout / bn; p.relu = relu;
+    p.b_fmt = (w_f16 < 0 ? f16 : (w_f16 != 0)) ? 0u : 1u;
     p.b_resident = (bn == 64 && p.n_par == 1 && p.n_tiles_n == 1 && p.n_taps[0] * p.cin_blocks <= IgemmCfg<64>::RES_B_BLOCKS) ? 1 : 0;
     // SCD_IGEMM_ROW_MODE: 0 = off, 1 = on (default), 2 = on with the pattern phase in the descriptor's base_offset field.
     // Measured on B200: tcgen05 derives the 128-byte swizzle phase from the operand's shared-memory ADDRESS bits, so a
@@ -704,8 +591,6 @@ static int conv_igemm(int kind, const void* x, const void* x2, const void* weigh
     for (int a = 0; a < p.n_par; ++a) max_taps = p.n_taps[a] > max_taps ? p.n_taps[a] : max_taps;
     rc = make_w_map(&p.tmB, weight, max_taps * cin, p.n_par * cout, bn, f16);   // rows = (class, cout), K = taps * cin
     if (rc) return rc;
-    choose_pair_mode(p, bn);
-    if (p.mc && (rc = make_w_map(&p.tmBh, weight, max_taps * cin, p.n_par * cout, 64, f16))) return rc;
     for (int par = 0; par < p.n_par; ++par) {
         rc = make_act_map(&p.tmOut[par], y, batch, p.hout, p.wout, cout, p.out_mul, par >> 1, par & 1, 2, f16);
         if (rc) return rc;
@@ -737,6 +622,17 @@ extern "C" int scd_conv_igemm_fwd_f16(int kind, const void* x, const void* weigh
     return conv_igemm(kind, x, nullptr, weight, bias, residual, relu, batch, hin, win, cin, cout, y, stream, true);
 }
 
+// fmt: 0 = bf16 weights and activations, 1 = fp16 both, 2 = bf16 weights x fp16 activations
+extern "C" int scd_conv_igemm_fwd_fmt(int kind, int fmt, const void* x, const void* weight, const float* bias,
+                                      const void* residual, int relu, int batch, int hin, int win,
+                                      int cin, int cout, void* y, void* stream)
+{
+    if (kind < 0 || kind > 3) return scd::fail(SCD_EINVAL, "scd_conv_igemm_fwd_fmt: kind must be 0..3");
+    if (fmt < 0 || fmt > 2) return scd::fail(SCD_EINVAL, "scd_conv_igemm_fwd_fmt: fmt must be 0, 1 or 2");
+    return conv_igemm(kind, x, nullptr, weight, bias, residual, relu, batch, hin, win, cin, cout, y, stream, fmt != 0,
+                      fmt == 1);
+}
+
 extern "C" int scd_conv_igemm_dgrad(int kind, const void* dz, const void* dz2, const void* weight, const float* bias,
                                     const void* add, int batch, int hin, int win, int cin, int cout, void* dx,
                                     void* stream)
@@ -749,7 +645,8 @@ extern "C" int scd_conv_igemm_dgrad(int kind, const void* dz, const void* dz2, c
 
 static int heads_fwd(const void* x, const void* w3, const float* b3, const float* w1,
                      const float* b1, int batch, int height, int width,
-                     float* heat, float* regr, float* offset, void* hidden, void* stream, bool f16 = false, int cin = 256)
+                     float* heat, float* regr, float* offset, void* hidden, void* stream, bool f16 = false, int cin = 256,
+                     int w_f16 = -1)
 {
     using namespace scd;
     if (batch <= 0) return SCD_OK;
@@ -760,12 +657,11 @@ static int heads_fwd(const void* x, const void* w3, const float* b3, const float
     int rc = fill_geometry(p, 0, x, nullptr, batch, height, width, cin, f16);
     if (rc) return rc;
     p.cout = 384; p.n_tiles_n = 1; p.relu = 1;
+    p.b_fmt = (w_f16 < 0 ? f16 : (w_f16 != 0)) ? 0u : 1u;
     p.total_tiles = batch * p.tiles_y * p.tiles_x;
     p.bias = b3; p.w1 = w1; p.b1 = b1; p.heat = heat; p.regr = regr; p.off = offset;
     rc = make_w_map(&p.tmB, w3, 9 * cin, 384, IgemmCfg<384>::B_BOX_ROWS, f16);
     if (rc) return rc;
-    choose_pair_mode(p, 384);
-    if (p.mc && (rc = make_w_map(&p.tmBh, w3, 9 * cin, 384, 64, f16))) return rc;
     if (hidden) {
         if ((rc = make_act_map(&p.tmOut[0], hidden, batch, height, width, 384, 1, 0, 0, 2))) return rc;
         return launch_igemm<384, EPI_HEADS_TRAIN>(p, (cudaStream_t)stream);
@@ -803,6 +699,15 @@ extern "C" int scd_heads_fwd_c_f16(const void* x, const void* w3, const float* b
 {
     if (cin % 64 || cin < 64 || cin > 512) return scd::fail(SCD_EINVAL, "scd_heads_fwd_c_f16: cin = %d", cin);
     return heads_fwd(x, w3, b3, w1, b1, batch, height, width, heat, regr, offset, nullptr, stream, true, cin);
+}
+
+extern "C" int scd_heads_fwd_fmt(int fmt, const void* x, const void* w3, const float* b3, const float* w1,
+                                 const float* b1, int batch, int height, int width, int cin,
+                                 float* heat, float* regr, float* offset, void* stream)
+{
+    if (cin % 64 || cin < 64 || cin > 512) return scd::fail(SCD_EINVAL, "scd_heads_fwd_fmt: cin = %d", cin);
+    if (fmt < 0 || fmt > 2) return scd::fail(SCD_EINVAL, "scd_heads_fwd_fmt: fmt must be 0, 1 or 2");
+    return heads_fwd(x, w3, b3, w1, b1, batch, height, width, heat, regr, offset, nullptr, stream, fmt != 0, cin, fmt == 1);
 }
 
 extern "C" int scd_heads_fwd_train(const void* x, const void* w3, const float* b3, const float* w1,

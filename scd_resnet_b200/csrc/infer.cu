@@ -200,22 +200,21 @@ extern "C" int scd_resnet_infer(int depth, const int* dims8, int f16, const floa
         return SCD_OK;
     };
     if ((rc = mark(0))) return rc;
-    rc = f16 ? scd_stem_fwd_f16(x, W(0), Bf(1), batch, height, width, buf[0], stream)
-             : scd_stem_fwd(x, W(0), Bf(1), batch, height, width, buf[0], stream);
+    if (f16 < 0 || f16 > 2) return fail(SCD_EINVAL, "scd_resnet_infer: format %d (0 = bf16, 1 = fp16, 2 = bf16 weights x fp16 activations)", f16);
+    rc = scd_stem_fwd_fmt(f16, x, W(0), Bf(1), batch, height, width, buf[0], stream);
     if (rc) return rc;
     if ((rc = mark(1))) return rc;
     for (int i = 0; i < pl.n_convs; ++i) {
         const Step& s = pl.steps[i];
         const ConvSpec& c = pl.convs[s.conv];
-        rc = (f16 ? scd_conv_igemm_fwd_f16 : scd_conv_igemm_fwd)(c.kind, buf[s.in], W(2 + 2 * i), Bf(3 + 2 * i),
-                                                                 s.res >= 0 ? buf[s.res] : nullptr, c.relu, batch,
-                                                                 h1 / s.hin, w1 / s.hin, c.cin, c.cout, buf[s.out], stream);
+        rc = scd_conv_igemm_fwd_fmt(c.kind, f16, buf[s.in], W(2 + 2 * i), Bf(3 + 2 * i), s.res >= 0 ? buf[s.res] : nullptr,
+                                    c.relu, batch, h1 / s.hin, w1 / s.hin, c.cin, c.cout, buf[s.out], stream);
         if (rc) return rc;
         if ((rc = mark(2 + i))) return rc;
     }
     const int h = 2 + 2 * pl.n_convs;
-    rc = (f16 ? scd_heads_fwd_c_f16 : scd_heads_fwd_c)(buf[pl.heads_in], W(h), Bf(h + 1), Bf(h + 2), Bf(h + 3), batch, h1, w1,
-                                                       pl.dims[7], heat, regr, offset, stream);
+    rc = scd_heads_fwd_fmt(f16, buf[pl.heads_in], W(h), Bf(h + 1), Bf(h + 2), Bf(h + 3), batch, h1, w1, pl.dims[7], heat, regr,
+                           offset, stream);
     if (rc) return rc;
     return mark(2 + pl.n_convs);
 }

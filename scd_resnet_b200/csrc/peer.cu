@@ -26,8 +26,10 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 
 __global__ void __launch_bounds__(256)
 peer_allreduce_f64_kernel(double* __restrict__ local, int n, unsigned char* const* __restrict__ peers, int rank,
-                          int world, int cap, unsigned seq)
+                          int world, int cap, unsigned seq, long long timeout_cycles, int* __restrict__ status)
 {
+    __shared__ int timed_out;
+    if (threadIdx.x == 0) timed_out = 0;
     const int par = (int)(seq & 1u);
     const size_t flags_off = (size_t)2 * world * cap * sizeof(double);
     // 1. my vector -> slot [par][rank] of every rank's buffer (mine included)
@@ -44,13 +46,23 @@ peer_allreduce_f64_kernel(double* __restrict__ local, int n, unsigned char* cons
         const unsigned* mine = reinterpret_cast<const unsigned*>(peers[rank] + flags_off) + par * world + threadIdx.x;
         const long long t0 = clock64();
         while (ld_acquire_sys(mine) != seq) {
-            if (clock64() - t0 > (1ll << 33)) {          // ~4 s: a peer died or the calls went out of step
-                printf("scd_b200: peer all-reduce timed out (rank %d waiting for rank %d, seq %u)\n", rank, (int)threadIdx.x, seq);
-                __trap();
+            // A slow peer (snapshot I/O, validation, a GC pause) is not an error: NCCL would simply wait, and so does this
+            // kernel unless the caller set a limit.  Past the limit the kernel reports through `status` (host-visible)
+            // and leaves `local` untouched instead of trapping, which would take the CUDA context of every rank down.
+            if (timeout_cycles > 0 && clock64() - t0 > timeout_cycles) {
+                if (status) atomicExch(status, 1 + (int)threadIdx.x);
+                else {
+                    printf("scd_b200: peer all-reduce timed out (rank %d waiting for rank %d, seq %u)\n", rank, (int)threadIdx.x, seq);
+                    __trap();
+                }
+                timed_out = 1;
+                break;
             }
+            __nanosleep(200);
         }
     }
     __syncthreads();
+    if (timed_out) return;
     // 3. fixed-order sum: identical on every rank
     const double* base = reinterpret_cast<const double*>(peers[rank]) + (size_t)par * world * cap;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -68,7 +80,7 @@ extern "C" size_t scd_peer_allreduce_buffer_bytes(int world, int cap)
 }
 
 extern "C" int scd_peer_allreduce_f64(double* local, int n, void* const* d_peer_buffers, int rank, int world, int cap,
-                                      unsigned seq, void* stream)
+                                      unsigned seq, long long timeout_cycles, int* status, void* stream)
 {
     using namespace scd;
     if (!local || !d_peer_buffers) return fail(SCD_EINVAL, "scd_peer_allreduce_f64: null pointer");
@@ -77,7 +89,7 @@ extern "C" int scd_peer_allreduce_f64(double* local, int n, void* const* d_peer_
     if (seq == 0u) return fail(SCD_EINVAL, "scd_peer_allreduce_f64: seq starts at 1 (0 is the cleared state)");
     if (n == 0) return SCD_OK;
     peer_allreduce_f64_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(
-        local, n, reinterpret_cast<unsigned char* const*>(d_peer_buffers), rank, world, cap, seq);
+        local, n, reinterpret_cast<unsigned char* const*>(d_peer_buffers), rank, world, cap, seq, timeout_cycles, status);
     SCD_LAUNCH_CHECK("peer_allreduce_f64_kernel");
     return SCD_OK;
 }

@@ -250,12 +250,7 @@ static int render_targets_impl(const float* locs, const int32_t* counts, int bat
     if (batch <= 0) return SCD_OK;
     if (!locs || !counts || !heat || !mask || !regr6 || !idx)
         return scd::fail(SCD_EINVAL, "scd_render_targets: null pointer");
-    static bool attr_done = false;
-    if (!attr_done) {
-        SCD_CUDA_CHECK(cudaFuncSetAttribute(scd::render_targets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            scd::RT_HW * scd::RT_HW * 4));
-        attr_done = true;
-    }
+    SCD_SMEM_ATTR(scd::render_targets_kernel, scd::RT_HW * scd::RT_HW * 4);
     if (d_npos) SCD_CUDA_CHECK(cudaMemsetAsync(d_npos, 0, 2 * sizeof(unsigned), (cudaStream_t)stream));
     scd::render_targets_kernel<<<batch, scd::RT_THREADS, scd::RT_HW * scd::RT_HW * 4, (cudaStream_t)stream>>>(
         locs, counts, heat, mask, regr6, idx, d_npos);

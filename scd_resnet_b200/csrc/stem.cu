@@ -47,7 +47,8 @@ constexpr int SP_LD_ITERS = (2 * ST_PS * ST_PS + 127) / 128;                // 7
 template <bool F16>
 __global__ void __launch_bounds__(SP_THREADS, 2)
 stem_pipe_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ x,
-                 const float* __restrict__ bias, int batch, int height, int width, __nv_bfloat16* __restrict__ y)
+                 const float* __restrict__ bias, int batch, int height, int width, __nv_bfloat16* __restrict__ y,
+                 uint32_t b_fmt /* weights: 1 = bf16, 0 = fp16 */)
 {
     using A16 = tc::Act<F16>;
     extern __shared__ unsigned char smem_dyn[];
@@ -149,7 +150,7 @@ stem_pipe_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restric
         // ===================== MMA issuer =====================
         if (lane == 0) {
             tc::mbar_wait(bar_w, 0);
-            constexpr uint32_t idesc = tc::umma_idesc_16(128, ST_CO, A16::kFmt);
+            const uint32_t idesc = tc::umma_idesc_16ab(128, ST_CO, A16::kFmt, b_fmt);
             uint32_t it = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
                 const int s = it % SP_STAGES;
@@ -380,7 +381,7 @@ stem_conv_train_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
 
 template <bool F16>
 static int stem_fwd_impl(const float* x, const void* weight, const float* bias, int batch,
-                         int height, int width, void* y, void* stream)
+                         int height, int width, void* y, void* stream, bool w_f16 = F16)
 {
     using namespace scd;
     if (batch <= 0) return SCD_OK;
@@ -390,14 +391,10 @@ static int stem_fwd_impl(const float* x, const void* weight, const float* bias, 
     CUtensorMap tmW;
     int rc = make_w_map(&tmW, weight, 64, 64, 64, F16);
     if (rc) return rc;
-    static bool attr_done = false;
-    if (!attr_done) {
-        SCD_CUDA_CHECK(cudaFuncSetAttribute(stem_pipe_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
-        attr_done = true;
-    }
+    SCD_SMEM_ATTR(stem_pipe_kernel<F16>, SP_SMEM);
     const int total = (height / 4 / ST_P) * (width / 4 / ST_P) * batch;
     stem_pipe_kernel<F16><<<total < 2 * kNumSMs ? total : 2 * kNumSMs, SP_THREADS, SP_SMEM, (cudaStream_t)stream>>>(
-        tmW, x, bias, batch, height, width, reinterpret_cast<__nv_bfloat16*>(y));
+        tmW, x, bias, batch, height, width, reinterpret_cast<__nv_bfloat16*>(y), w_f16 ? 0u : 1u);
     SCD_LAUNCH_CHECK("stem_pipe_kernel");
     return SCD_OK;
 }
@@ -414,6 +411,15 @@ extern "C" int scd_stem_fwd_f16(const float* x, const void* weight, const float*
     return stem_fwd_impl<true>(x, weight, bias, batch, height, width, y, stream);
 }
 
+extern "C" int scd_stem_fwd_fmt(int fmt, const float* x, const void* weight, const float* bias, int batch,
+                                int height, int width, void* y, void* stream)
+{
+    if (fmt == 0) return stem_fwd_impl<false>(x, weight, bias, batch, height, width, y, stream);
+    if (fmt == 1) return stem_fwd_impl<true>(x, weight, bias, batch, height, width, y, stream);
+    if (fmt == 2) return stem_fwd_impl<true>(x, weight, bias, batch, height, width, y, stream, false);
+    return scd::fail(SCD_EINVAL, "scd_stem_fwd_fmt: fmt must be 0, 1 or 2");
+}
+
 extern "C" int scd_stem_conv_train(const float* x, const void* weight, int batch, int height, int width,
                                    void* z0, void* col0, void* stream)
 {
@@ -427,11 +433,7 @@ extern "C" int scd_stem_conv_train(const float* x, const void* weight, int batch
     if ((rc = make_w_map(&tmW, weight, 64, 64, 64))) return rc;
     if ((rc = make_act_map(&tmZ, z0, batch, height / 2, width / 2, 64, 1, 0, 0, 8))) return rc;
     if ((rc = make_act_map(&tmCol, col0, batch, height / 2, width / 2, 64, 1, 0, 0, 8))) return rc;
-    static bool attr_done = false;
-    if (!attr_done) {
-        SCD_CUDA_CHECK(cudaFuncSetAttribute(stem_conv_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SV_SMEM));
-        attr_done = true;
-    }
+    SCD_SMEM_ATTR(stem_conv_train_kernel, SV_SMEM);
     dim3 grid((height / 2 / SV_T) * (width / 2 / SV_T), batch);
     stem_conv_train_kernel<<<grid, ST_THREADS, SV_SMEM, (cudaStream_t)stream>>>(tmW, tmZ, tmCol, x, height, width);
     SCD_LAUNCH_CHECK("stem_conv_train_kernel");

@@ -75,23 +75,6 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
-// ---- CTA-pair (cta_group::2) helpers: rank in the pair, peer addresses (mapa), remote mbarrier arrive ----
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t cta_rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
-    return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 // shared -> global tile store (bulk async group); the smem tile uses the tensor map's swizzle
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
     asm volatile(
@@ -118,17 +101,6 @@ __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {      // whole wa
 template <int kCols>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {       // whole warp, the allocating one
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
-}
-// CTA pair: one warp of EACH CTA of the pair executes these
-template <int kCols>
-__device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(kCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-template <int kCols>
-__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -163,6 +135,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
 // Same for either 16-bit operand format of kind::f16: fmt 0 = fp16, 1 = bf16 (A at bits [7,10), B at [10,13)).
 __host__ __device__ constexpr uint32_t umma_idesc_16(int m, int n, uint32_t fmt) {
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// A (activations) and B (weights) formats chosen independently: kind::f16 multiplies fp16 x bf16 exactly into fp32.
+__host__ __device__ constexpr uint32_t umma_idesc_16ab(int m, int n, uint32_t afmt, uint32_t bfmt) {
+    return (1u << 4) | (afmt << 7) | (bfmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // Element type of the inference activations / GEMM operands.  bf16 is the configuration BASELINE names; fp16
@@ -209,22 +186,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 // mbarrier arrives once every tcgen05.mma issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// CTA pair: D[256 x N] = [A of CTA 0; A of CTA 1] * [B half of CTA 0; B half of CTA 1]^T, rows 0..127 of D in the TMEM of
-// CTA 0 and rows 128..255 in CTA 1's; issued by one thread of the leader CTA (rank 0) for both SMs
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                              uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// ... and the completion arrives on the mbarrier at the same offset in every CTA of `cta_mask`
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t cta_mask) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"(cta_mask) : "memory");
 }
 
 }  // namespace tc

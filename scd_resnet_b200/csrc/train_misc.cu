@@ -229,6 +229,18 @@ gather_cast_kernel(const float* __restrict__ src, const int* __restrict__ idx, s
     }
 }
 
+// dst[i] = src[idx[i]] * (*scale)   (idx < 0 -> 0): wgrad-layout gradients -> the parameters' own layout
+__global__ void __launch_bounds__(256)
+gather_f32_kernel(const float* __restrict__ src, const int* __restrict__ idx, size_t n, const float* __restrict__ scale,
+                  float* __restrict__ dst)
+{
+    const float f = scale ? *scale : 1.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int j = idx[i];
+        dst[i] = j >= 0 ? src[j] * f : 0.f;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 scale_kernel(float* __restrict__ x, size_t n, const float* __restrict__ s)
 {
@@ -309,6 +321,15 @@ extern "C" int scd_gather_cast_bf16(const float* src, const int* idx, size_t n, 
     if (!src || !idx || !dst) return fail(SCD_EINVAL, "scd_gather_cast_bf16: null pointer");
     gather_cast_kernel<<<sgrid(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(src, idx, n, static_cast<__nv_bfloat16*>(dst));
     SCD_LAUNCH_CHECK("gather_cast_kernel");
+    return SCD_OK;
+}
+
+extern "C" int scd_gather_f32(const float* src, const int* idx, size_t n, const float* d_scale, float* dst, void* stream)
+{
+    using namespace scd;
+    if (!src || !idx || !dst) return fail(SCD_EINVAL, "scd_gather_f32: null pointer");
+    gather_f32_kernel<<<sgrid(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(src, idx, n, d_scale, dst);
+    SCD_LAUNCH_CHECK("gather_f32_kernel");
     return SCD_OK;
 }
 

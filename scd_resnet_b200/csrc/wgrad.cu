@@ -277,11 +277,7 @@ extern "C" int scd_conv_wgrad(int kind, const void* a_in, const void* dz, int ba
     p.splits = splits;
     p.total_units = out_tiles * splits;
     p.out = out;
-    static bool attr_done = false;
-    if (!attr_done) {
-        SCD_CUDA_CHECK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
-        attr_done = true;
-    }
+    SCD_SMEM_ATTR(wgrad_kernel, WG_SMEM);
     const int grid = p.total_units < kNumSMs ? p.total_units : kNumSMs;
     wgrad_kernel<<<grid, WG_THREADS, WG_SMEM, (cudaStream_t)stream>>>(p);
     SCD_LAUNCH_CHECK("wgrad_kernel");

@@ -66,13 +66,19 @@ class PeerAllReduce:
     the reduction itself is this repository's kernel.  Construction is collective.  `available` is False when the
     platform cannot map peer memory (then the caller keeps using NCCL all-reduces)."""
 
-    def __init__(self, group, device, cap=1024):
+    def __init__(self, group, device, cap=1024, timeout_s=None):
+        """timeout_s: how long a rank waits for its peers inside the kernel before it gives up (reported by check());
+        default $SCD_PEER_TIMEOUT_S or 1800 s, 0 = wait forever like NCCL."""
         import ctypes
         from ._lib import lib, check
         self._lib, self._check, self._ctypes = lib, check, ctypes
         self.group, self.device, self.cap = group, torch.device(device), cap
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.seq = 0
+        if timeout_s is None:
+            timeout_s = float(os.environ.get("SCD_PEER_TIMEOUT_S", "1800"))
+        self.timeout_cycles = int(timeout_s * 2.0e9)                  # SM clock <= 2 GHz: at least timeout_s
+        self.status = torch.zeros(1, dtype=torch.int32).pin_memory()  # written by the kernel on a timeout (UVA: same address)
         self.available = False
         self.reason = ""
         try:
@@ -115,7 +121,15 @@ class PeerAllReduce:
         with torch.cuda.device(self.device):
             self._check(self._lib.scd_peer_allreduce_f64(c.c_void_p(vec.data_ptr()), vec.numel(),
                                                          c.c_void_p(self.peers.data_ptr()), self.rank, self.world, self.cap,
-                                                         self.seq & 0xFFFFFFFF or 1,
+                                                         self.seq & 0xFFFFFFFF or 1, self.timeout_cycles,
+                                                         c.c_void_p(self.status.data_ptr()),
                                                          c.c_void_p(torch.cuda.current_stream().cuda_stream)),
                         "scd_peer_allreduce_f64")
         return vec
+
+    def check(self):
+        """Raise if an earlier call gave up waiting for a peer (a host read of a pinned word: no synchronisation)."""
+        st = int(self.status[0])
+        if st != 0:
+            raise RuntimeError("scd_b200 peer all-reduce: rank %d timed out waiting for rank %d (a peer died or the "
+                               "ranks went out of step); the statistics of that step are invalid" % (self.rank, st - 1))

@@ -11,19 +11,20 @@ from . import ops, weights
 
 class TileDetector:
     """model: a CenterNetResidual in eval mode (or a state_dict).  batch: tiles per launch.
-    precision: "bf16" (the configuration BASELINE names) or "fp16" (same speed, ~8x smaller rounding error)."""
+    precision: operand formats of the tensor-core path (weights.PRECISIONS): "mixed" (default: the bf16 model's weights
+    x fp16 activations, within 1e-2 of the fp32 reference on every head), "bf16" (both bf16), "fp16" (both fp16)."""
 
-    def __init__(self, model_or_sd, batch, device=None, K=100, height=512, width=512, precision="bf16"):
-        if precision not in ("bf16", "fp16"):
-            raise ops.ScdError("precision must be 'bf16' or 'fp16'")
-        self.fp16 = precision == "fp16"
+    def __init__(self, model_or_sd, batch, device=None, K=100, height=512, width=512, precision=None):
+        self.precision = precision or weights.DEFAULT_PRECISION
+        self.fmt, self.wdtype = weights.precision_spec(self.precision)
+        self.fp16 = self.fmt == 1
         sd = model_or_sd.state_dict() if hasattr(model_or_sd, "state_dict") else model_or_sd
         sd = {k.replace("module.", "", 1) if k.startswith("module.") else k: v for k, v in sd.items()}
         self.device = torch.device(device if device is not None else "cuda")
         self.batch, self.K, self.h, self.w = batch, K, height, width
         with torch.cuda.device(self.device):
             self.depth, self.dims, self.kdims = weights.arch_of(sd)      # numLayers, widths, kernel-level widths
-            self.blob = weights.pack_infer_blob(sd, self.device, torch.float16 if self.fp16 else torch.bfloat16)
+            self.blob = weights.pack_infer_blob(sd, self.device, self.wdtype)
             self.workspace = torch.empty(ops.lib.scd_resnet_workspace_bytes(self.depth, ops._dims_arg(self.kdims), batch,
                                                                             height, width),
                                          dtype=torch.uint8, device=self.device)
@@ -45,7 +46,7 @@ class TileDetector:
         b = x.shape[0]
         heat, regr, off = [m[:b] for m in self.maps]
         ops.resnet_infer(x, self.blob, self.depth, self.kdims, self.workspace, (heat, regr, off), stage_events,
-                         fp16=self.fp16)
+                         fmt=self.fmt)
         return ops.decode_topk(heat, regr, off, K=self.K, planes=True)[6]
 
     def detect_host(self, host_batches):

@@ -162,10 +162,24 @@ def centernet_loss_sparse(heat, regr, offset, gt_heat, mask, regr6, idx, regr_w=
 
 
 def _act_dtype(weight):
-    """Inference activations take the dtype of the packed weights: bf16 (default) or fp16."""
+    """Inference activations take the dtype of the packed weights (bf16 or fp16) unless the caller asks for the mixed
+    plan (bf16 weights x fp16 activations) with act_dtype=torch.float16."""
     if weight.dtype not in (torch.bfloat16, torch.float16):
         raise ScdError("packed weights must be bfloat16 or float16, got %s" % weight.dtype)
     return weight.dtype
+
+
+def _fmt(weight, act_dtype):
+    """(fmt code of the *_fmt entry points, activation dtype) for a packed weight and the requested activation dtype."""
+    wd = _act_dtype(weight)
+    ad = wd if act_dtype is None else act_dtype
+    if wd == torch.bfloat16 and ad == torch.bfloat16:
+        return 0, ad
+    if wd == torch.float16 and ad == torch.float16:
+        return 1, ad
+    if wd == torch.bfloat16 and ad == torch.float16:
+        return 2, ad
+    raise ScdError("unsupported operand formats: weights %s, activations %s" % (wd, ad))
 
 
 def augment_batch(samples, locs, counts, index, flips, jitter, noise=None, noise_sv=0.05, jitter_sv=0.05):
@@ -231,27 +245,26 @@ def centernet_eval(scores, ys, xs, offset, regr, regr6, gt_idx, mask, threshold=
     return out, counts, obj
 
 
-def stem_fwd(x, weight, bias):
-    """ResNet.preprocess (ref: models/backbones/residuals.py:210-215), BN folded. -> (B,H/4,W/4,64) NHWC in the
-    dtype of `weight` (bf16 or fp16)."""
+def stem_fwd(x, weight, bias, act_dtype=None):
+    """ResNet.preprocess (ref: models/backbones/residuals.py:210-215), BN folded. -> (B,H/4,W/4,64) NHWC in
+    `act_dtype` (default: the dtype of `weight`, bf16 or fp16; fp16 with bf16 weights = the mixed plan)."""
     x = _req(x, torch.float32, "x")
-    dt = _act_dtype(weight)
-    weight = _req(weight, dt, "stem weight")
+    fmt, dt = _fmt(weight, act_dtype)
+    weight = _req(weight, weight.dtype, "stem weight")
     bias = _req(bias, torch.float32, "stem bias")
     b, c, h, w = x.shape
     y = torch.empty(b, h // 4, w // 4, 64, dtype=dt, device=x.device)
-    fn = lib.scd_stem_fwd_f16 if dt == torch.float16 else lib.scd_stem_fwd
     with torch.cuda.device(x.device):
-        check(fn(_ptr(x), _ptr(weight), _ptr(bias), b, h, w, _ptr(y), _stream()), "scd_stem_fwd")
+        check(lib.scd_stem_fwd_fmt(fmt, _ptr(x), _ptr(weight), _ptr(bias), b, h, w, _ptr(y), _stream()), "scd_stem_fwd")
     return y
 
 
 def conv_igemm_fwd(kind, x, weight, bias, residual=None, relu=True):
-    """One implicit-GEMM stage. x (B,H,W,Cin) NHWC bf16 or fp16 (= the dtype of `weight`, packed by
-    weights.pack_conv); -> NHWC of the same dtype."""
-    dt = _act_dtype(weight)
+    """One implicit-GEMM stage. x (B,H,W,Cin) NHWC bf16 or fp16; `weight` packed by weights.pack_conv in the same
+    dtype, or bf16 with fp16 activations (mixed plan); -> NHWC of x's dtype."""
+    fmt, dt = _fmt(weight, x.dtype)
     x = _req(x, dt, "x")
-    weight = _req(weight, dt, "weight")
+    weight = _req(weight, weight.dtype, "weight")
     bias = _req(bias, torch.float32, "bias")
     b, h, w, cin = x.shape
     cout = bias.numel()
@@ -266,26 +279,24 @@ def conv_igemm_fwd(kind, x, weight, bias, residual=None, relu=True):
         residual = _req(residual, dt, "residual")
         if residual.shape != y.shape:
             raise ScdError("residual shape mismatch")
-    fn = lib.scd_conv_igemm_fwd_f16 if dt == torch.float16 else lib.scd_conv_igemm_fwd
     with torch.cuda.device(x.device):
-        check(fn(kind, _ptr(x), _ptr(weight), _ptr(bias), _ptr(residual), int(relu), b, h, w,
-                                     cin, cout, _ptr(y), _stream()), "scd_conv_igemm_fwd")
+        check(lib.scd_conv_igemm_fwd_fmt(kind, fmt, _ptr(x), _ptr(weight), _ptr(bias), _ptr(residual), int(relu), b, h, w,
+                                         cin, cout, _ptr(y), _stream()), "scd_conv_igemm_fwd")
     return y
 
 
 def heads_fwd(x, w3, b3, w1, b1):
     """The three heads fused (ref: models/centerNetOffset.py:103-122). x (B,H,W,256) bf16 / fp16 -> NCHW f32 maps."""
-    dt = _act_dtype(w3)
+    fmt, dt = _fmt(w3, x.dtype)
     x = _req(x, dt, "x")
-    fn = lib.scd_heads_fwd_f16 if dt == torch.float16 else lib.scd_heads_fwd
     b, h, w, c = x.shape
     heat = torch.empty(b, 1, h, w, dtype=torch.float32, device=x.device)
     regr = torch.empty(b, 4, h, w, dtype=torch.float32, device=x.device)
     off = torch.empty(b, 2, h, w, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        check(fn(_ptr(x), _ptr(_req(w3, dt, "w3")), _ptr(_req(b3, torch.float32, "b3")),
-                                _ptr(_req(w1, torch.float32, "w1")), _ptr(_req(b1, torch.float32, "b1")), b, h, w,
-                                _ptr(heat), _ptr(regr), _ptr(off), _stream()), "scd_heads_fwd")
+        check(lib.scd_heads_fwd_fmt(fmt, _ptr(x), _ptr(_req(w3, w3.dtype, "w3")), _ptr(_req(b3, torch.float32, "b3")),
+                                    _ptr(_req(w1, torch.float32, "w1")), _ptr(_req(b1, torch.float32, "b1")), b, h, w, c,
+                                    _ptr(heat), _ptr(regr), _ptr(off), _stream()), "scd_heads_fwd")
     return heat, regr, off
 
 
@@ -323,11 +334,12 @@ def infer_weights_layout(depth=10, dims=None):
     return list(offs), list(sizes), lib.scd_resnet_weights_bytes(depth, d)
 
 
-def resnet_infer(x, blob, depth=10, dims=None, workspace=None, out=None, stage_events=None, fp16=False):
+def resnet_infer(x, blob, depth=10, dims=None, workspace=None, out=None, stage_events=None, fp16=False, fmt=None):
     """ResNet.forward, eval, decode=False (ref: models/backbones/residuals.py:312-334) as one native call.
 
     x (B,1,H,W) f32; blob = packed BN-folded weights (weights.pack_infer_blob with the same depth / dims; `fp16`
     must match the dtype it was packed with).  depth = numLayers (10, 18, 34); dims = kernel-level (padded) widths.
+    fmt (overrides fp16): 0 = bf16, 1 = fp16, 2 = mixed, bf16 weights x fp16 activations (weights.PRECISIONS).
     Returns heat, regr, offset (NCHW f32) and the workspace (reusable).
     """
     x = _req(x, torch.float32, "x")
@@ -353,15 +365,15 @@ def resnet_infer(x, blob, depth=10, dims=None, workspace=None, out=None, stage_e
             raise ScdError("stage_events must hold %d events" % n_ev)
         ev = (ctypes.c_void_p * n_ev)(*[e.cuda_event for e in stage_events])
     with torch.cuda.device(dev):
-        check(lib.scd_resnet_infer(depth, d, 1 if fp16 else 0, _ptr(x), _ptr(blob), b, h, w, _ptr(heat), _ptr(regr),
+        check(lib.scd_resnet_infer(depth, d, fmt if fmt is not None else (1 if fp16 else 0), _ptr(x), _ptr(blob), b, h, w, _ptr(heat), _ptr(regr),
                                    _ptr(off), _ptr(workspace), workspace.numel(), ev, n_ev, _stream()),
               "scd_resnet_infer")
     return heat, regr, off, workspace
 
 
-def resnet10_infer(x, blob, workspace=None, out=None, stage_events=None, fp16=False):
+def resnet10_infer(x, blob, workspace=None, out=None, stage_events=None, fp16=False, fmt=None):
     """CenterNetResidual(numLayers=10) with the default widths: the headline path (scd_resnet10_infer)."""
-    return resnet_infer(x, blob, 10, None, workspace, out, stage_events, fp16)
+    return resnet_infer(x, blob, 10, None, workspace, out, stage_events, fp16, fmt)
 
 
 def slide_geometry(height, width):

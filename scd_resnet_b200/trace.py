@@ -78,16 +78,17 @@ def architecture_of(sd):
     return "centerOffsetRes%d%s" % (depth, suffix)
 
 
-def export(sd, output, shape=(1, 1, 512, 512), precision="bf16", architecture=None, raw=False):
-    """Write the deployable file for state_dict `sd`.  Packing needs the library (not a GPU)."""
-    if precision not in ("bf16", "fp16"):
-        raise ScdError("precision must be 'bf16' or 'fp16'")
+def export(sd, output, shape=(1, 1, 512, 512), precision=None, architecture=None, raw=False):
+    """Write the deployable file for state_dict `sd`.  Packing needs the library (not a GPU).
+    precision: weights.PRECISIONS ("mixed" = bf16 weights x fp16 activations is the default)."""
+    precision = precision or weights.DEFAULT_PRECISION
+    fmt, wdtype = weights.precision_spec(precision)
     depth, dims, kdims = weights.arch_of(sd)
     arch = architecture or architecture_of(sd)
-    blob = weights.pack_infer_blob(sd, "cpu", torch.float16 if precision == "fp16" else torch.bfloat16)
+    blob = weights.pack_infer_blob(sd, "cpu", wdtype)
     offs, sizes, total = ops.infer_weights_layout(depth, kdims)
     header = {"format": FORMAT, "architecture": arch, "numLayers": depth, "dims": list(dims), "kernel_dims": list(kdims),
-              "precision": precision, "input_shape": list(shape), "K": 100,
+              "precision": precision, "fmt": fmt, "input_shape": list(shape), "K": 100,
               "output": "(10, B, K) f32: scores, idx, ctY, ctX, majX, majY, minL, rad, offX, offY "
                         "(ref: trainer/wrappers/centerOffsetResidual.py:11-22)",
               "blob_bytes": total, "blob_entry_offsets": offs, "blob_entry_sizes": sizes}
@@ -111,7 +112,7 @@ class ExportedDetector(torch.nn.Module):
         super().__init__()
         self.header = header
         self.depth, self.kdims = header["numLayers"], header["kernel_dims"]
-        self.fp16 = header["precision"] == "fp16"
+        self.fmt = weights.precision_spec(header["precision"])[0]
         self.register_buffer("blob", blob.to(device))
         self._workspace = None
 
@@ -120,7 +121,7 @@ class ExportedDetector(torch.nn.Module):
             raise ScdError("ExportedDetector (scd_b200) runs on CUDA only")
         with torch.no_grad():
             heat, regr, off, self._workspace = ops.resnet_infer(inp.float(), self.blob, self.depth, self.kdims,
-                                                                self._workspace, fp16=self.fp16)
+                                                                self._workspace, fmt=self.fmt)
             return ops.decode_topk(heat, regr, off, K=self.header["K"], planes=True)[6]
 
 
@@ -135,13 +136,13 @@ def load_exported(path, device="cuda"):
         sd = load_checkpoint(path)
         depth, dims, kdims = weights.arch_of(sd)
         obj = {"format": FORMAT, "architecture": architecture_of(sd), "numLayers": depth, "dims": list(dims),
-               "kernel_dims": list(kdims), "precision": "bf16", "K": 100,
+               "kernel_dims": list(kdims), "precision": weights.DEFAULT_PRECISION, "K": 100,
                "blob": weights.pack_infer_blob(sd, "cpu")}
     header = {k: v for k, v in obj.items() if k not in ("blob", "state_dict")}
     return ExportedDetector(header, obj["blob"], torch.device(device))
 
 
-def load_model(path, device="cuda", precision="bf16"):
+def load_model(path, device="cuda", precision=None):
     """The plugin's nn.Module (CenterNetResidual of the right depth / widths) with the checkpoint loaded, eval mode."""
     sd = load_checkpoint(path)
     plugin = importlib.import_module(__package__ + ".trainer.model." + architecture_of(sd))
@@ -164,7 +165,7 @@ def parseArguments(argv=None):
                         help="accepted for command-line compatibility (packing runs on the host)")
     parser.add_argument("-wrapped", dest="isWrapped", const=True, default=False, action="store_const",
                         help="accepted for command-line compatibility: `module.` prefixes are detected automatically")
-    parser.add_argument("--precision", default="bf16", choices=("bf16", "fp16"))
+    parser.add_argument("--precision", default=weights.DEFAULT_PRECISION, choices=sorted(weights.PRECISIONS))
     parser.add_argument("--raw", action="store_true", help="also write <output>.blob / <output>.json for C consumers")
     return parser.parse_args(argv)
 

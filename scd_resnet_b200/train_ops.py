@@ -49,10 +49,16 @@ def bn_backward(da, a, z, ctx, want_dy=False, dgamma=None, dbeta=None, all_reduc
             a = None
         args = (_ptr(da), _ptr(a), _ptr(z), _ptr(stat[0]), _ptr(stat[1] if relu_from_z else None), _ptr(stat[2]),
                 _ptr(stat[3]), pixels, C, count, _ptr(sums))
-        check(lib.scd_bn_bwd(*args, None, None, None, None, 0, _stream()), "scd_bn_bwd(reduce)")
+        check(lib.scd_bn_bwd(*args, None, None, None, None, None, 0, _stream()), "scd_bn_bwd(reduce)")
+        local = None
         if all_reduce is not None:
+            # d gamma / d beta are THIS rank's sums (torch.nn.SyncBatchNorm semantics; the gradient all-reduce averages
+            # them like every other parameter gradient): keep a copy from before the exchange (a D2D memcpy of 2C doubles)
+            local = torch.empty_like(sums)
+            local.copy_(sums)
             all_reduce(sums, None)
-        check(lib.scd_bn_bwd(*args, _ptr(dz), _ptr(dy), _ptr(dgamma), _ptr(dbeta), 1, _stream()), "scd_bn_bwd(apply)")
+        check(lib.scd_bn_bwd(*args, _ptr(dz), _ptr(dy), _ptr(dgamma), _ptr(dbeta), _ptr(local), 1, _stream()),
+              "scd_bn_bwd(apply)")
     return dz, dy
 
 
@@ -184,6 +190,13 @@ def adam_step(params, exp_avg, exp_avg_sq, grads, gmap, step, lr=1e-3, betas=(0.
 def gather_cast_bf16(src, idx, dst):
     with torch.cuda.device(src.device):
         check(lib.scd_gather_cast_bf16(_ptr(src), _ptr(idx), idx.numel(), _ptr(dst), _stream()), "scd_gather_cast_bf16")
+
+
+def gather_f32(src, idx, dst, d_scale=None):
+    """dst[i] = src[idx[i]] (* d_scale[0]); idx int32 (negative -> 0)."""
+    with torch.cuda.device(src.device):
+        check(lib.scd_gather_f32(_ptr(src), _ptr(idx), idx.numel(), _ptr(d_scale), _ptr(dst), _stream()), "scd_gather_f32")
+    return dst
 
 
 def scale_inplace(x, d_scale):

@@ -48,12 +48,19 @@ def _deconv_list(dims):
 
 class TrainEngine:
     def __init__(self, module, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, regr_w=0.1, off_w=0.1, process_group=None,
-                 peer_stats=True):
+                 peer_stats=True, stat_group="same", dense_heads=False):
+        """process_group: ranks whose gradients this engine averages itself (None: it does not; a DistributedDataParallel
+        wrapper around the module may).  stat_group: ranks that share BatchNorm batch statistics (= SyncBatchNorm);
+        "same" = process_group.  dense_heads: also lay out the buffers of the dense heads backward, used when the
+        upstream gradients of regr / offset arrive as dense maps (the autograd route with a foreign loss)."""
         self.module = module
         self.lr, self.betas, self.eps = lr, betas, eps
         self.regr_w, self.off_w = regr_w, off_w
         self.group = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.stat_group = process_group if isinstance(stat_group, str) else stat_group
+        self.stat_world = torch.distributed.get_world_size(self.stat_group) if self.stat_group is not None else 1
+        self.dense_heads = dense_heads
         self.step_count = 0
         named = dict(module.named_parameters())
         dev = next(module.parameters()).device
@@ -74,7 +81,8 @@ class TrainEngine:
         order += [h + ".2.weight" for h, _, _ in _HEADS] + [h + ".2.bias" for h, _, _ in _HEADS]
         assert sorted(order) == sorted(named)
         self.alloc = {}                                   # key -> allocated shape inside P
-        bn_modules = {n: m for n, m in module.named_modules() if isinstance(m, torch.nn.BatchNorm2d)}
+        # BatchNorm2d, or SyncBatchNorm after torch.nn.SyncBatchNorm.convert_sync_batchnorm (ref: networkFactory.py:133)
+        bn_modules = {n: m for n, m in module.named_modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)}
         for k in order:
             shape = tuple(named[k].shape)
             prefix, leaf = k.rsplit(".", 1)
@@ -113,13 +121,16 @@ class TrainEngine:
         # SyncBatchNorm statistics: 2 x C fp64 sums per BatchNorm, forward and backward.  Over NVLink peer memory when
         # the platform allows it (falls back to NCCL all-reduces otherwise; `peer_reason` says why).
         self.peer, self.peer_reason = None, ""
-        if self.world > 1 and peer_stats:
+        self._versions = self._param_versions()
+        if self.stat_world > 1 and peer_stats:
             from .dist import PeerAllReduce
-            pa = PeerAllReduce(process_group, dev, cap=1024)
+            pa = PeerAllReduce(self.stat_group, dev, cap=1024)
             if pa.available:
                 self.peer = pa
             else:
                 self.peer_reason = pa.reason
+        if hasattr(module, "_engine"):
+            module._engine = self                          # the module's train-mode forward runs through this engine
 
     # ------------------------------------------------------------------ layouts
     def _build_layouts(self, named):
@@ -220,10 +231,22 @@ class TrainEngine:
             gmap[self.off[h + ".0.bias"]:self.off[h + ".0.bias"] + 128] = b3 + i * 128 + torch.arange(128)
             gmap[self.off[h + ".2.weight"]:self.off[h + ".2.weight"] + nj * 128] = w1 + j0 * 128 + torch.arange(nj * 128)
             gmap[self.off[h + ".2.bias"]:self.off[h + ".2.bias"] + nj] = b1 + j0 + torch.arange(nj)
-        self.n_grads = g_n
+        self.n_grads = g_n                                                              # what a gradient all-reduce covers
         self._reduced_from = g_n
-        self.G = torch.zeros(g_n, dtype=torch.float32, device=self.dev)
         self.gmap = gmap.to(torch.int32).to(self.dev)
+        self.gmap_dense = None
+        if self.dense_heads:
+            # dense heads backward: one wgrad (kind 0, 384 output channels) / one dgrad over all three heads; the slot
+            # sits behind the all-reduced range and a second gradient map reads the 3x3 weights from it
+            base = g_alloc("heads.w3d", T.conv_wgrad_floats(0, hc, 384))
+            gd = gmap.clone()
+            idx384 = weights.wgrad_index((384, hc, 3, 3), 0)
+            for i, (h, _, _) in enumerate(_HEADS):
+                k = h + ".0.weight"
+                gd[self.off[k]:self.off[k] + named[k].numel()] = (base + idx384[i * 128:i * 128 + hd, :ci_real]).reshape(-1)
+            self.gmap_dense = gd.to(torch.int32).to(self.dev)
+            w_alloc("heads.w3:dgrad", weights.layout_dgrad(w3_idx, 0))
+        self.G = torch.zeros(g_n, dtype=torch.float32, device=self.dev)
         wmap = torch.full((w_n,), -1, dtype=torch.int64)
         for o, flat in wparts:
             wmap[o:o + flat.numel()] = flat
@@ -256,45 +279,59 @@ class TrainEngine:
 
     def refresh_operands(self):
         T.gather_cast_bf16(self.P, self.wmap, self.WB)
+        self._versions = self._param_versions()
+
+    def _param_versions(self):
+        return tuple(p._version for p in self.module.parameters())
+
+    def refresh_if_changed(self):
+        """The 16-bit operand copies follow the fp32 masters: any in-place update of a parameter since the last refresh
+        (a torch optimizer stepping on the views, load_state_dict, a broadcast) triggers one gather kernel."""
+        if self._versions != self._param_versions():
+            self.refresh_operands()
+
+    def owns(self, module=None):
+        """True while every parameter of the module still is the view into P this engine bound it to (module.to(),
+        .half() or a re-assigned .data break that; the caller then builds a new engine)."""
+        base = self.P.data_ptr()
+        for k, p in (module or self.module).named_parameters():
+            if k not in self.off or p.data_ptr() != base + 4 * self.off[k] or p.dtype != torch.float32:
+                return False
+        return True
 
     # ------------------------------------------------------------------ SyncBatchNorm hooks
     def _allreduce_stats(self, sums, pixels):
-        if self.world == 1:
+        if self.stat_world == 1:
             return float(pixels) if pixels is not None else None
         if self.peer is not None:
             self.peer(sums)                                # one-shot NVLink peer-memory reduction (csrc/peer.cu)
         else:
-            torch.distributed.all_reduce(sums, group=self.group)
-        return float(pixels) * self.world if pixels is not None else None
+            torch.distributed.all_reduce(sums, group=self.stat_group)
+        return float(pixels) * self.stat_world if pixels is not None else None
 
     # ------------------------------------------------------------------ forward + backward
     def _bn(self, z, prefix, residual=None, relu=True):
         m = self.module.get_submodule(prefix)
         return T.bn_forward(z, m.weight.data, m.bias.data, m.running_mean, m.running_var, m.num_batches_tracked,
-                            residual, relu, all_reduce=self._allreduce_stats if self.world > 1 else None)
+                            residual, relu, all_reduce=self._allreduce_stats if self.stat_world > 1 else None)
 
     def _bn_bwd(self, da, a, z, ctx, prefix, want_dy=False, relu_from_z=False):
         return T.bn_backward(da, a, z, ctx, want_dy, self.g(prefix + ".weight"), self.g(prefix + ".bias"),
-                             all_reduce=self._allreduce_stats if self.world > 1 else None, relu_from_z=relu_from_z)
+                             all_reduce=self._allreduce_stats if self.stat_world > 1 else None, relu_from_z=relu_from_z)
 
     def _conv(self, kind, x, key, cout):
         return ops.conv_igemm_fwd(kind, x, self.wb(key + ":fwd"), self.zero_bias[:cout], None, False)
 
-    def forward_backward(self, x, targets, sigmoid_inplace=False):
-        """x (B,1,H,W) f32 CUDA; targets = [heat (B,1,128,128), mask (B,30), regr6 (B,30,6), idx (B,30)]
-        (+ optionally the two device counters of ops.render_targets(with_npos=True)).
-        Returns (losses f32[4] on the device, outputs dict); gradients land in self.G."""
+    def forward(self, x, keep=True):
+        """Train-mode forward (batch-statistics BatchNorm, running statistics updated) on x (B,1,H,W) f32 CUDA.
+        Returns ((heat logits, regr, offset) NCHW f32, tape); tape = what backward() needs, or None when not `keep`
+        (validation in train mode under no_grad, ref: models/networkFactory.py:265-271 with the model left in train())."""
         mod = self.module
-        for w in self._pending:                            # a backward pass that was not followed by optimizer_step
-            w.wait()
-        self._pending, self._reduced_from = [], self.n_grads
-        self.G.zero_()
-        tape = []
-        # ---- forward -----------------------------------------------------------------------------------
+        self.refresh_if_changed()
         z0, col0 = T.stem_conv_train(x, self.wb("preprocess.0.weight:fwd"))
         _, ctx0 = self._stem_bn(z0, mod.preprocess[1])
-        a, argmax0 = T.stem_bn_relu_pool(z0, ctx0["stat"])
-        a0 = a
+        a, argmax0 = T.stem_bn_relu_pool(z0, ctx0["stat"], want_argmax=keep)
+        tape = []
         for p, cin, cout, stride in self.blocks:
             a_in = a
             z1 = self._conv(0 if stride == 1 else 1, a_in, p + ".conv1.weight", cout)
@@ -306,39 +343,58 @@ class TrainEngine:
                 zd = self._conv(2, a_in, p + ".downsample.0.weight", cout)
                 skip, cd = self._bn(zd, p + ".downsample.1", relu=False)
             a, c2 = self._bn(z2, p + ".bn2", residual=skip)
-            tape.append((p, cin, cout, stride, a_in, z1, a1, c1, z2, c2, zd, cd, a))
+            if keep:
+                tape.append((p, cin, cout, stride, a_in, z1, a1, c1, z2, c2, zd, cd, a))
         dtape = []
         for ck, bk, cin, cout in self.deconvs:
             a_in = a
             z = self._conv(3, a_in, ck + ".weight", cout)
             a, c = self._bn(z, bk)
-            dtape.append((ck, bk, cin, cout, a_in, z, c, a))
+            if keep:
+                dtape.append((ck, bk, cin, cout, a_in, z, c, a))
         e3 = a
         b3 = self.P[self.off["heatmap.0.bias"]:self.off["heatmap.0.bias"] + 384]
         w1 = self.P[self.off["heatmap.2.weight"]:self.off["heatmap.2.weight"] + 7 * 128]
         b1 = self.P[self.off["heatmap.2.bias"]:self.off["heatmap.2.bias"] + 7]
         heat, regr, off, hidden = T.heads_fwd_train(e3, self.wb("heads.w3:fwd"), b3, w1, b1)
-        # ---- loss (forward + its own backward in one pass; L1 gradients in sparse, per-object form) -----------
-        heat_logits = heat
-        gt_heat, mask, regr6, gidx = targets[0], targets[1], targets[2], targets[3]
-        counts = targets[4] if len(targets) > 4 else None          # [N_pos, mask.sum()] from render_targets(with_npos)
-        losses, d_heat, d_obj = ops.centernet_loss_sparse(heat_logits, regr, off, gt_heat, mask, regr6, gidx,
-                                                          self.regr_w, self.off_w, npos=counts,
-                                                          sigmoid_inplace=sigmoid_inplace)
-        # ---- backward ----------------------------------------------------------------------------------
-        d_hh, dh_obj = T.heads_bwd_sparse(d_heat, d_obj, mask, gidx, hidden, w1, self.g("heads.w1"), self.g("heads.b1"),
-                                          self.g("heads.b3"))
+        if not keep:
+            return (heat, regr, off), None
+        return (heat, regr, off), {"z0": z0, "col0": col0, "ctx0": ctx0, "argmax0": argmax0, "blocks": tape,
+                                   "deconvs": dtape, "e3": e3, "hidden": hidden, "w1": w1}
+
+    def backward(self, tape, d_heat, sparse=None, dense=None):
+        """Backward pass from the heads' output gradients; weight gradients land in self.G (wgrad layouts).
+        d_heat (B,1,H,W) f32 and EITHER sparse = (d_obj (B,30,6), mask, idx): the masked-L1 gradients of regr / offset in
+        per-object form (ops.centernet_loss_sparse), OR dense = (d_regr (B,4,H,W), d_off (B,2,H,W)) (needs
+        dense_heads=True)."""
+        for w in self._pending:                            # a backward pass that was not followed by optimizer_step
+            w.wait()
+        self._pending, self._reduced_from = [], self.n_grads
+        self.G.zero_()
+        e3, hidden, w1 = tape["e3"], tape["hidden"], tape["w1"]
         hc = self.kd[7]
-        T.conv_wgrad(self.heat_wgrad_kind, e3, d_hh, hc, 128, self.g("heads.w3h"))
-        T.heads_wgrad_sparse(e3, dh_obj, mask, gidx, self.g("heads.w3s"))
-        da = T.conv_dgrad(0, d_hh, self.wb("heads.w3h:dgrad"), self.zero_bias[:hc], hc)
-        T.heads_dgrad_sparse(dh_obj, mask, gidx, self.wb("heads.w3:fwd"), da)
-        for ck, bk, cin, cout, a_in, z, c, a_out in reversed(dtape):
+        if sparse is not None:
+            d_obj, mask, gidx = sparse
+            d_hh, dh_obj = T.heads_bwd_sparse(d_heat, d_obj, mask, gidx, hidden, w1, self.g("heads.w1"),
+                                              self.g("heads.b1"), self.g("heads.b3"))
+            T.conv_wgrad(self.heat_wgrad_kind, e3, d_hh, hc, 128, self.g("heads.w3h"))
+            T.heads_wgrad_sparse(e3, dh_obj, mask, gidx, self.g("heads.w3s"))
+            da = T.conv_dgrad(0, d_hh, self.wb("heads.w3h:dgrad"), self.zero_bias[:hc], hc)
+            T.heads_dgrad_sparse(dh_obj, mask, gidx, self.wb("heads.w3:fwd"), da)
+        else:
+            if not self.dense_heads:
+                raise ScdError("TrainEngine: dense heads backward needs dense_heads=True")
+            d_regr, d_off = dense
+            d_hidden = T.heads_bwd(d_heat, d_regr, d_off, hidden, w1, self.g("heads.w1"), self.g("heads.b1"),
+                                   self.g("heads.b3"))
+            T.conv_wgrad(0, e3, d_hidden, hc, 384, self.g("heads.w3d"))
+            da = T.conv_dgrad(0, d_hidden, self.wb("heads.w3:dgrad"), self.zero_bias[:hc], hc)
+        for ck, bk, cin, cout, a_in, z, c, a_out in reversed(tape["deconvs"]):
             dz, _ = self._bn_bwd(da, None, z, c, bk, relu_from_z=True)       # conv -> BN -> ReLU, no residual
             T.conv_wgrad(3, a_in, dz, cin, cout, self.g(ck + ".weight"))
             da = T.conv_dgrad(3, dz, self.wb(ck + ".weight:dgrad"), self.zero_bias[:cin], cin)
         self._reduce_async(self.g_off[self.deconvs[0][0] + ".weight"], self.n_grads)          # deconvs + heads are final
-        for p, cin, cout, stride, a_in, z1, a1, c1, z2, c2, zd, cd, a_out in reversed(tape):
+        for p, cin, cout, stride, a_in, z1, a1, c1, z2, c2, zd, cd, a_out in reversed(tape["blocks"]):
             dz2, dy = self._bn_bwd(da, a_out, z2, c2, p + ".bn2", want_dy=True)
             T.conv_wgrad(0, a1, dz2, cout, cout, self.g(p + ".conv2.weight"))
             da1 = T.conv_dgrad(0, dz2, self.wb(p + ".conv2.weight:dgrad"), self.zero_bias[:cout], cout)
@@ -353,11 +409,25 @@ class TrainEngine:
                 da = T.conv_dgrad(1, dz1, self.wb(p + ".conv1.weight:dgrad"), self.zero_bias[:cin], cin, dz2=dzd)
             if p == "layer3.0":                                                               # layer3 + layer4 are final
                 self._reduce_async(self.g_off["layer3.0.conv1.weight"], self._reduced_from)
-        dy0 = T.stem_pool_bwd(argmax0, da)
-        dz0, _ = T.bn_backward(dy0, None, z0, ctx0, False, self.g("preprocess.1.weight"), self.g("preprocess.1.bias"),
-                               all_reduce=self._allreduce_stats if self.world > 1 else None)
-        T.conv_wgrad(4, col0, dz0, 64, 64, self.g("preprocess.0.weight"))
-        return losses, {"heatmap": heat_logits, "regr": regr, "offset": off}
+        dy0 = T.stem_pool_bwd(tape["argmax0"], da)
+        dz0, _ = T.bn_backward(dy0, None, tape["z0"], tape["ctx0"], False, self.g("preprocess.1.weight"),
+                               self.g("preprocess.1.bias"),
+                               all_reduce=self._allreduce_stats if self.stat_world > 1 else None)
+        T.conv_wgrad(4, tape["col0"], dz0, 64, 64, self.g("preprocess.0.weight"))
+
+    def forward_backward(self, x, targets, sigmoid_inplace=False):
+        """x (B,1,H,W) f32 CUDA; targets = [heat (B,1,128,128), mask (B,30), regr6 (B,30,6), idx (B,30)]
+        (+ optionally the two device counters of ops.render_targets(with_npos=True)).
+        Returns (losses f32[4] on the device, outputs dict); gradients land in self.G."""
+        (heat, regr, off), tape = self.forward(x, keep=True)
+        # ---- loss (forward + its own backward in one pass; L1 gradients in sparse, per-object form) -----------
+        gt_heat, mask, regr6, gidx = targets[0], targets[1], targets[2], targets[3]
+        counts = targets[4] if len(targets) > 4 else None          # [N_pos, mask.sum()] from render_targets(with_npos)
+        losses, d_heat, d_obj = ops.centernet_loss_sparse(heat, regr, off, gt_heat, mask, regr6, gidx,
+                                                          self.regr_w, self.off_w, npos=counts,
+                                                          sigmoid_inplace=sigmoid_inplace)
+        self.backward(tape, d_heat, sparse=(d_obj, mask, gidx))
+        return losses, {"heatmap": heat, "regr": regr, "offset": off}
 
     def _stem_bn(self, z0, bn0):
         """Batch statistics of the stem conv output; the normalisation itself is fused with ReLU + max-pool."""
@@ -382,15 +452,21 @@ class TrainEngine:
             self._pending.append(torch.distributed.all_reduce(self.G[lo:hi], group=self.group, async_op=True))
             self._reduced_from = min(self._reduced_from, lo)
 
-    def optimizer_step(self):
-        """DDP semantics (ref: models/networkFactory.py:134): gradients are averaged over ranks, then Adam.
-        The deconv + heads range and the layer3-4 range were started during the backward pass (forward_backward); what is
-        left here is the stem .. layer2 range (12 % of the parameters)."""
+    def finish_reduce(self):
+        """Complete the gradient all-reduce (sum over ranks) of G[0:n_grads).  The deconv + heads range and the layer3-4
+        range were started during the backward pass; what is left here is the stem .. layer2 range (12 % of the
+        parameters)."""
         if self.world > 1:
             self._reduce_async(0, min(self._reduced_from, self.n_grads))
             for w in self._pending:
                 w.wait()                                   # this stream waits for the collectives, not the host
             self._pending, self._reduced_from = [], self.n_grads
+
+    def optimizer_step(self):
+        """DDP semantics (ref: models/networkFactory.py:134): gradients are averaged over ranks, then Adam."""
+        self.finish_reduce()
+        if self.peer is not None:
+            self.peer.check()
         self.step_count += 1
         T.adam_step(self.P, self.M, self.V, self.G, self.gmap, self.step_count, self.lr, self.betas, self.eps,
                     1.0 / self.world)
@@ -405,13 +481,12 @@ class TrainEngine:
     def set_learning_rate(self, lr):
         self.lr = lr
 
-    def grads_reference_layout(self):
-        """{name: gradient tensor in the parameter's own layout} (diagnostics / interop; not on the hot path)."""
-        g = self.G[self.gmap.long()]
+    def grads_reference_layout(self, dense=False, scale=None):
+        """{name: gradient in the parameter's own layout}: one gather kernel from the wgrad layouts of G into a fresh flat
+        buffer laid out like P (what loss.backward() leaves in param.grad, ref: models/networkFactory.py:261).
+        dense: the last backward ran the dense heads path; scale: optional device scalar multiplied in."""
+        g = torch.empty_like(self.P)
+        T.gather_f32(self.G, self.gmap_dense if dense else self.gmap, g, scale)
         return {k: self._param_view(g, k, p.shape) for k, p in self.module.named_parameters()}
 
 
-def forward_train(module, x):
-    raise ScdError("CenterNetResidual.forward in train mode has no stand-alone autograd graph in scd_b200: training "
-                   "runs through scd_resnet_b200.training.TrainEngine (forward + loss + backward + Adam on native "
-                   "kernels), which networkFactory.NetworkFactory.train uses. Call .eval() for inference.")

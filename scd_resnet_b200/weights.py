@@ -14,6 +14,22 @@ BLOCKS = {10: (1, 1, 1, 1), 18: (2, 2, 2, 2), 34: (3, 4, 6, 3)}
 DEFAULT_DIMS = (64, 64, 128, 256, 512, 256, 256, 256)      # ref: models/backbones/residuals.py:195-201
 
 
+# Operand formats of the eval-mode tensor-core path: name -> (fmt code of the C ABI, dtype the weights are packed in).
+#   "bf16"   bf16 weights, bf16 activations
+#   "fp16"   fp16 weights, fp16 activations
+#   "mixed"  bf16 weights x fp16 activations (tcgen05 kind::f16 takes the A / B formats independently): the default.
+#            The model is the bf16 model BASELINE names; only the stored activations carry fp16's finer mantissa, which
+#            brings all three heads inside the north star's 1e-2 (tools/emulate_precision.py, profiles/accuracy_r02.json).
+PRECISIONS = {"bf16": (0, torch.bfloat16), "fp16": (1, torch.float16), "mixed": (2, torch.bfloat16)}
+DEFAULT_PRECISION = "mixed"
+
+
+def precision_spec(name):
+    if name not in PRECISIONS:
+        raise ops.ScdError("precision must be one of %s, got %r" % (sorted(PRECISIONS), name))
+    return PRECISIONS[name]
+
+
 def stages(depth=10):
     """igemm stages of CenterNetResidual(depth) in blob order: (conv key, bn prefix, kind).  The first block of
     layers 2-4 has the projection shortcut (ref: ResNet.makeLayer, models/backbones/residuals.py:256-271)."""

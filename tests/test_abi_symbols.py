@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_layout_queries():
     import scd_resnet_b200 as s
-    assert s.lib.scd_abi_version() == 1
+    assert s.lib.scd_abi_version() == 2
     offs, sizes, total = s.ops.infer_weights_layout()
     assert len(offs) == 34 and total == s.lib.scd_infer_weights_bytes()
     assert sizes[0] == 64 * 64 * 2 and sizes[30] == 384 * 2304 * 2

@@ -303,12 +303,15 @@ def test_slide_tiles_opencv_fixup_width(S):
 
 
 # ------------------------------------------------------------------------------ stem
-@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
-def test_stem(S, dt):
+@pytest.mark.parametrize("dt,adt", [(torch.bfloat16, None), (torch.float16, None), (torch.bfloat16, torch.float16)])
+def test_stem(S, dt, adt):
+    """dt: weight format; adt: activation format (None = dt; bf16 weights + fp16 activations = the mixed plan)."""
     sd = O.make_state_dict(1234)
     f = S.weights.fold(sd, dt)
     x = O.make_tiles(2, seed=3)
-    y = S.ops.stem_fwd(dev(x), dev(f["stem_w"]), dev(f["stem_b"])).float().cpu().permute(0, 3, 1, 2)
+    y = S.ops.stem_fwd(dev(x), dev(f["stem_w"]), dev(f["stem_b"]), act_dtype=adt)
+    assert y.dtype == (adt or dt)
+    y = y.float().cpu().permute(0, 3, 1, 2)
     t = F.conv2d(x, sd["preprocess.0.weight"], None, stride=2, padding=3)
     t = F.relu(F.batch_norm(t, sd["preprocess.1.running_mean"], sd["preprocess.1.running_var"],
                             sd["preprocess.1.weight"], sd["preprocess.1.bias"], False, 0.1, 1e-5))
@@ -326,17 +329,20 @@ def _bf16(t):
     return t.to(torch.bfloat16).float()
 
 
-def _conv_case(S, kind, b, h, w, cin, cout, residual, relu, seed, dt=torch.bfloat16):
-    _bf16 = lambda t: t.to(dt).float()                       # operands rounded to the kernel's own 16-bit format
+def _conv_case(S, kind, b, h, w, cin, cout, residual, relu, seed, dt=torch.bfloat16, wdt=None):
+    """dt: activation format; wdt: weight format (None = dt).  dt fp16 + wdt bf16 = the mixed plan."""
+    wdt = wdt or dt
+    _bf16 = lambda t: t.to(dt).float()                       # operands rounded to the kernel's own 16-bit formats
+    _wr = lambda t: t.to(wdt).float()
     rng = np.random.default_rng(seed)
     x = _bf16(torch.from_numpy(rng.standard_normal((b, cin, h, w)).astype(np.float32)))
     bias = torch.from_numpy(rng.standard_normal(cout).astype(np.float32))
     if kind == 3:
-        wt = _bf16(torch.from_numpy((rng.standard_normal((cin, cout, 4, 4)) / np.sqrt(4 * cin)).astype(np.float32)))
+        wt = _wr(torch.from_numpy((rng.standard_normal((cin, cout, 4, 4)) / np.sqrt(4 * cin)).astype(np.float32)))
         ref = F.conv_transpose2d(x, wt, bias, stride=2, padding=1)
     else:
         k = 1 if kind == 2 else 3
-        wt = _bf16(torch.from_numpy((rng.standard_normal((cout, cin, k, k)) / np.sqrt(k * k * cin)).astype(np.float32)))
+        wt = _wr(torch.from_numpy((rng.standard_normal((cout, cin, k, k)) / np.sqrt(k * k * cin)).astype(np.float32)))
         ref = F.conv2d(x, wt, bias, stride=1 if kind == 0 else 2, padding=0 if kind == 2 else 1)
     res = None
     if residual:
@@ -346,7 +352,7 @@ def _conv_case(S, kind, b, h, w, cin, cout, residual, relu, seed, dt=torch.bfloa
         ref = F.relu(ref)
     xg = dev(x.permute(0, 2, 3, 1).contiguous().to(dt))
     rg = dev(res.permute(0, 2, 3, 1).contiguous().to(dt)) if residual else None
-    y = S.ops.conv_igemm_fwd(kind, xg, dev(S.weights.pack_conv(wt, kind, None, dt)), dev(bias), rg, relu)
+    y = S.ops.conv_igemm_fwd(kind, xg, dev(S.weights.pack_conv(wt, kind, None, wdt)), dev(bias), rg, relu)
     torch.cuda.synchronize()
     assert y.dtype == dt
     y = y.float().cpu().permute(0, 3, 1, 2)
@@ -381,6 +387,15 @@ def test_conv_igemm_fp16(S, case):
     _conv_case(S, *case, seed=hash(case) % 1000, dt=torch.float16)
 
 
+@pytest.mark.parametrize("case", [(0, 1, 128, 128, 64, 64, True, True), (0, 3, 16, 16, 512, 512, True, True),
+                                  (1, 2, 128, 128, 64, 128, False, True), (2, 2, 32, 32, 256, 512, False, False),
+                                  (3, 1, 64, 64, 256, 256, False, True)])
+def test_conv_igemm_mixed(S, case):
+    """bf16 weights x fp16 activations: tcgen05 kind::f16 with different A / B formats; products are exact in fp32, so
+    against the same rounded operands only the fp16 output rounding remains."""
+    _conv_case(S, *case, seed=hash(case) % 1000, dt=torch.float16, wdt=torch.bfloat16)
+
+
 def test_conv_igemm_fp16_saturates(S):
     """fp16 stores clamp to +-65504 instead of producing inf."""
     x = torch.full((1, 8, 16, 64), 200.0, dtype=torch.float16, device="cuda")
@@ -390,42 +405,64 @@ def test_conv_igemm_fp16_saturates(S):
     assert torch.isfinite(y.float()).all() and float(y.float().max()) == 65504.0
 
 
-@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
-def test_heads(S, dt):
-    _bf16 = lambda t: t.to(dt).float()
+@pytest.mark.parametrize("dt,adt", [(torch.bfloat16, None), (torch.float16, None), (torch.bfloat16, torch.float16)])
+def test_heads(S, dt, adt):
+    adt = adt or dt
+    _bf16 = lambda t: t.to(adt).float()
+    _wr = lambda t: t.to(dt).float()
     rng = np.random.default_rng(31)
     sd = O.make_state_dict(1234)
     f = S.weights.fold(sd, dt)
     x = _bf16(torch.from_numpy(np.abs(rng.standard_normal((2, 256, 128, 128))).astype(np.float32)))
-    heat, regr, off = S.ops.heads_fwd(dev(x.permute(0, 2, 3, 1).contiguous().to(dt)),
+    heat, regr, off = S.ops.heads_fwd(dev(x.permute(0, 2, 3, 1).contiguous().to(adt)),
                                       dev(f["head_w3"]), dev(f["head_b3"]), dev(f["head_w1"]), dev(f["head_b1"]))
     for name, got in (("heatmap", heat), ("regr", regr), ("offset", off)):
-        hmid = F.relu(F.conv2d(x, _bf16(sd[name + ".0.weight"]), sd[name + ".0.bias"], padding=1))
+        hmid = F.relu(F.conv2d(x, _wr(sd[name + ".0.weight"]), sd[name + ".0.bias"], padding=1))
         ref = F.conv2d(hmid, sd[name + ".2.weight"], sd[name + ".2.bias"])
         assert relmax(got, ref) < 1e-2, name
         assert ((got.cpu() - ref).abs() <= 0.01 * ref.abs() + 0.02 * ref.abs().max()).all()
 
 
 # ------------------------------------------------------------------------------ whole network
-def test_infer_vs_oracle(S, golden):
-    """heatmap / regr / offset of the bf16 tensor-core path vs the fp32 oracle: 1e-2 rel (north star)."""
-    sd = O.make_state_dict(1234)
-    x = O.make_tiles(2, seed=0)
-    blob = S.weights.pack_infer_blob(sd, "cuda")
-    heat, regr, off, _ = S.ops.resnet10_infer(dev(x), blob)
+def _rel_rms(got, ref):
+    return ((got.cpu() - ref).double().pow(2).mean().sqrt() / ref.double().pow(2).mean().sqrt()).item()
+
+
+@pytest.mark.parametrize("seed", [1234, 77])
+def test_infer_vs_oracle(S, golden, seed):
+    """The DEFAULT inference path (the one bench.py times): bf16 weights x fp16 activations.  heatmap / regr / offset
+    within the north star's 1e-2 (bf16) of the fp32 oracle, all three heads.  Measured 4.3e-3 / 5.5e-3 / 8.7e-3
+    (profiles/accuracy_r02.json; tools/emulate_precision.py predicts the same on the CPU)."""
+    assert S.weights.DEFAULT_PRECISION == "mixed"
+    fmt, wdt = S.weights.precision_spec(S.weights.DEFAULT_PRECISION)
+    sd = O.make_state_dict(seed)
+    x = O.make_tiles(2, seed=seed % 5)
+    blob = S.weights.pack_infer_blob(sd, "cuda", wdt)
+    heat, regr, off, _ = S.ops.resnet10_infer(dev(x), blob, fmt=fmt)
     with torch.no_grad():
         ref = O.resnet10_forward(sd, x)[0]
     for name, got in (("heatmap", heat), ("regr", regr), ("offset", off)):
         r = ref[name]
-        e = (got.cpu() - r).abs()
-        rms = (e.double().pow(2).mean().sqrt() / r.double().pow(2).mean().sqrt()).item()
-        # bf16 operands through 16 layers.  Measured (tools/accuracy_report.py, profiles/accuracy_r01.json):
-        # heat 5.9e-3, regr 7.7e-3, offset 1.25e-2 rel-RMS; torch's own bf16 autocast (cuDNN) on the same
-        # weights: 7.9e-3 / 1.1e-2 / 1.7e-2.  The north-star 1e-2 is asserted where bf16 reaches it.
-        assert rms < (1e-2 if name != "offset" else 1.5e-2), (name, rms)
-        assert e.max() <= 2e-2 * r.abs().max(), (name, e.max().item(), r.abs().max().item())
-    g = golden("model_eval")
-    assert relmax(heat[:, :, ::4, ::4], torch.from_numpy(g["heat_sub"])) < 3e-2
+        rms = _rel_rms(got, r)
+        assert rms < 1e-2, (name, rms)
+        assert (got.cpu() - r).abs().max() <= 2e-2 * r.abs().max(), name
+    if seed == 1234:
+        g = golden("model_eval")
+        assert relmax(heat[:, :, ::4, ::4], torch.from_numpy(g["heat_sub"])) < 3e-2
+
+
+def test_infer_pure_bf16_mode(S):
+    """precision="bf16" (bf16 weights AND bf16 activations) stays available but is not the default: 16 layers of bf16
+    activation rounding put heat / regr at 5.9e-3 / 7.9e-3 and the offset head at 1.26e-2, outside the 1e-2 bar
+    (profiles/accuracy_r01.json; torch's own bf16 autocast through cuDNN: 7.9e-3 / 1.1e-2 / 1.7e-2).  This test pins
+    those figures so that the mode cannot drift further; the 1e-2 gate is test_infer_vs_oracle."""
+    sd = O.make_state_dict(1234)
+    x = O.make_tiles(2, seed=0)
+    heat, regr, off, _ = S.ops.resnet10_infer(dev(x), S.weights.pack_infer_blob(sd, "cuda"), fmt=0)
+    with torch.no_grad():
+        ref = O.resnet10_forward(sd, x)[0]
+    assert _rel_rms(heat, ref["heatmap"]) < 1e-2 and _rel_rms(regr, ref["regr"]) < 1e-2
+    assert 1e-2 < _rel_rms(off, ref["offset"]) < 1.4e-2
 
 
 def test_infer_fp16_vs_oracle(S, golden):

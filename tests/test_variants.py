@@ -49,7 +49,7 @@ def test_unsupported_variants_fail_loudly():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("precision", ["mixed", "bf16", "fp16"])
 @pytest.mark.parametrize("name", ["centerOffsetRes18", "centerOffsetRes34", "centerOffsetRes10h", "centerOffsetRes10q",
                                   "centerOffsetRes18h", "centerOffsetRes34h"])
 def test_variant_forward_vs_oracle(golden, name, precision):
@@ -65,7 +65,8 @@ def test_variant_forward_vs_oracle(golden, name, precision):
         ref = O.resnet_forward(sd, x)[0]
     g = golden("variants")
     # bf16 through up to 36 conv layers: rel-RMS bound grows with depth (Res10 measures 0.6-1.3e-2); fp16 stays at 1e-3
-    tol = {"bf16": 1.5e-2 if depth == 10 else 3e-2, "fp16": 4e-3}[precision]
+    # "mixed" (the default: bf16 weights x fp16 activations) removes the activation half of that rounding
+    tol = {"bf16": 1.5e-2 if depth == 10 else 3e-2, "mixed": 1e-2 if depth == 10 else 2.2e-2, "fp16": 4e-3}[precision]
     for key, short in (("heatmap", "heat"), ("regr", "regr"), ("offset", "off")):
         r, got = ref[key], out[key].cpu()
         assert got.shape == r.shape
