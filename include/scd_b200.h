@@ -239,6 +239,14 @@ int scd_resnet10_infer_f16(const float* x, const void* weights, int batch, int h
                            void* workspace, size_t workspace_bytes, void* const* h_stage_events,
                            void* stream);
 
+/* Diagnostic: one tcgen05.mma chain (M = 128, N = n_cols, K = 16 per step, kind::f16) over a caller-supplied shared-memory
+ * image (copied to a 1024 B aligned buffer) with caller-supplied operand descriptors (start-address field relative to
+ * that buffer) and instruction descriptor; step k adds k * a_step / k * b_step to the descriptors.  out (128, n_cols)
+ * f32.  Pins the operand layouts the kernels rely on (tools/probe_umma_desc.py); not on the hot path. */
+int scd_probe_umma(const void* image, int image_bytes, unsigned long long adesc, unsigned long long bdesc,
+                   unsigned int idesc, int n_cols, int k_steps, unsigned long long a_step, unsigned long long b_step,
+                   float* out, void* stream);
+
 /* Operand-format variants, fmt: 0 = bf16 weights and activations, 1 = fp16 both, 2 = MIXED: bf16 weights (B operand)
  * x fp16 activations (A operand, stores, residual).  tcgen05 kind::f16 takes the two formats independently and
  * multiplies them exactly into the fp32 accumulator.  With bf16 model weights the mixed plan removes the activation

@@ -49,6 +49,8 @@ PROTOTYPES = {
     "scd_stem_fwd_fmt": (c_int, [c_int] + [c_void_p] * 3 + [c_int] * 3 + [c_void_p, c_void_p]),
     "scd_conv_igemm_fwd_fmt": (c_int, [c_int, c_int] + [c_void_p] * 4 + [c_int] * 6 + [c_void_p, c_void_p]),
     "scd_heads_fwd_fmt": (c_int, [c_int] + [c_void_p] * 5 + [c_int] * 4 + [c_void_p] * 3 + [c_void_p]),
+    "scd_probe_umma": (c_int, [c_void_p, c_int, ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.c_uint, c_int, c_int,
+                                ctypes.c_ulonglong, ctypes.c_ulonglong, c_void_p, c_void_p]),
     "scd_bn_stats": (c_int, [c_void_p, c_size_t, c_int, c_void_p, c_void_p]),
     "scd_bn_finalize": (c_int, [c_void_p] * 6 + [c_int, ctypes.c_double, c_float, c_float] + [c_void_p] * 4 + [c_void_p]),
     "scd_bn_apply": (c_int, [c_void_p] * 4 + [c_int, c_size_t, c_int, c_void_p, c_void_p]),

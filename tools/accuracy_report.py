@@ -22,8 +22,10 @@ x = O.make_tiles(2, seed=0)
 with torch.no_grad():
     ref = O.resnet10_forward(sd, x)[0]
 blob = S.weights.pack_infer_blob(sd, "cuda")
-heat, regr, off, _ = S.ops.resnet10_infer(x.cuda(), blob)
+heat, regr, off, _ = S.ops.resnet10_infer(x.cuda(), blob, fmt=0)
 rep = {"ours_bf16_vs_fp32_oracle": {k: metrics(v, ref[k]) for k, v in (("heatmap", heat), ("regr", regr), ("offset", off))}}
+hm, rm, om, _ = S.ops.resnet10_infer(x.cuda(), blob, fmt=2)
+rep["ours_mixed_bf16w_fp16a_vs_fp32_oracle"] = {k: metrics(v, ref[k]) for k, v in (("heatmap", hm), ("regr", rm), ("offset", om))}
 blob16 = S.weights.pack_infer_blob(sd, "cuda", torch.float16)
 h16, r16, o16, _ = S.ops.resnet10_infer(x.cuda(), blob16, fp16=True)
 rep["ours_fp16_vs_fp32_oracle"] = {k: metrics(v, ref[k]) for k, v in (("heatmap", h16), ("regr", r16), ("offset", o16))}
@@ -38,5 +40,6 @@ rep["torch_cuda_fp32_vs_fp32_oracle"] = {k: metrics(g32[k], ref[k]) for k in ref
 rep["torch_cuda_bf16_autocast_vs_fp32_oracle"] = {k: metrics(g16[k].float(), ref[k]) for k in ref}
 # probabilities (what decode and the loss consume)
 rep["ours_sigmoid_heat"] = metrics(torch.sigmoid(heat), torch.sigmoid(ref["heatmap"]))
+rep["ours_mixed_sigmoid_heat"] = metrics(torch.sigmoid(hm), torch.sigmoid(ref["heatmap"]))
 rep["ours_fp16_sigmoid_heat"] = metrics(torch.sigmoid(h16), torch.sigmoid(ref["heatmap"]))
 print(json.dumps(rep, indent=1))
