@@ -201,8 +201,8 @@ int scd_resnet10_infer(const float* x, const void* weights, int batch, int heigh
  * Blob: 0 stem w | 1 stem b | 2+2i, 3+2i weight / bias of igemm stage i | then heads w3, b3, w1, b1;
  * stage order per layer: [downsample, conv1, conv2] for a projection block, [conv1, conv2] otherwise, then the
  * three deconvs (scd_resnet_conv_specs lists kind / cin / cout).  Stage events: scd_resnet_num_convs + 3.
- * f16 = operand formats: 0 = bf16 weights and activations, 1 = fp16 both, 2 = bf16 weights x fp16 activations (the
- * blob is packed in the weight format).  scd_resnet10_infer == scd_resnet_infer(10, NULL, 0, ...).
+ * f16 = operand format: 0 = bf16, 1 = fp16 (the blob's 16-bit entries are in that format).
+ * scd_resnet10_infer == scd_resnet_infer(10, NULL, 0, ...).
  * ---------------------------------------------------------------------------------- */
 int    scd_resnet_num_convs(int depth, const int* dims8);                     /* < 0: unsupported */
 int    scd_resnet_conv_specs(int depth, const int* dims8, int* h_kind, int* h_cin, int* h_cout, int n);
@@ -247,12 +247,13 @@ int scd_probe_umma(const void* image, int image_bytes, unsigned long long adesc,
                    unsigned int idesc, int n_cols, int k_steps, unsigned long long a_step, unsigned long long b_step,
                    float* out, void* stream);
 
-/* Operand-format variants, fmt: 0 = bf16 weights and activations, 1 = fp16 both, 2 = MIXED: bf16 weights (B operand)
- * x fp16 activations (A operand, stores, residual).  tcgen05 kind::f16 takes the two formats independently and
- * multiplies them exactly into the fp32 accumulator.  With bf16 model weights the mixed plan removes the activation
- * half of the rounding error: rel-RMS of heat / regr / offset vs the fp32 reference 4.3e-3 / 5.5e-3 / 8.7e-3 against
- * 5.9e-3 / 7.9e-3 / 1.26e-2 with bf16 activations (tools/emulate_precision.py, profiles/accuracy_r02.json): inside the
- * 1e-2 the north star sets for bf16 on all three heads, at the same tensor-core rate. */
+/* One entry point per op for both operand formats, fmt: 0 = bf16, 1 = fp16 (weights, activations, stores, residual).
+ * tcgen05 kind::f16 needs the same format for A and B: A = fp16 with B = bf16 in one instruction descriptor faults
+ * (illegal instruction on sm_100a, measured).  The default precision plan of the Python layer ("mixed") therefore keeps
+ * the MODEL in bf16 and the ACTIVATIONS in fp16 by storing the bf16-rounded weights in fp16 containers (exact for
+ * |w| >= 2^-16) and running fmt = 1: rel-RMS of heat / regr / offset vs the fp32 reference 4.3e-3 / 5.5e-3 / 8.7e-3
+ * against 5.9e-3 / 7.9e-3 / 1.26e-2 with bf16 activations (tools/emulate_precision.py, profiles/accuracy_r02.json):
+ * inside the 1e-2 the north star sets for bf16 on all three heads, at the same tensor-core rate. */
 int scd_stem_fwd_fmt(int fmt, const float* x, const void* weight, const float* bias, int batch,
                      int height, int width, void* y, void* stream);
 int scd_conv_igemm_fwd_fmt(int kind, int fmt, const void* x, const void* weight, const float* bias,
@@ -427,6 +428,37 @@ int scd_slide_tiles(const float* gray, int height, int width, int tile_begin, in
 /* Same for a uint8 grey image (the rounded grey values of test.py:31 are integers in [0, 255]). */
 int scd_slide_tiles_u8(const uint8_t* gray, int height, int width, int tile_begin, int tile_end,
                        float* tiles, void* stream);
+
+/* The same from a COLUMN STRIP of the slide: `strip` holds slide columns [col0, col0 + ncols) of every row, `pitch`
+ * elements per row (float32, or uint8 when is_u8).  With several ranks each one owns a contiguous range of the x-major
+ * tile list, i.e. a few tile columns, and uploads only the columns those read (scd_slide_column_span lists them for one
+ * tile column, reflect pad and the 3200-wide fix-up included): the whole slide is no longer copied to every GPU. */
+int scd_slide_tiles_strip(const void* strip, int is_u8, int height, int width, int col0, int ncols, int pitch,
+                          int tile_begin, int tile_end, float* tiles, void* stream);
+int scd_slide_column_span(int height, int width, int tile_column, int* h_lo_hi);
+
+/* grayscale (test.py:21-33): gray = numpy.round(0.1140 r + 0.5870 g + 0.2989 b) on the first three of `channels` uint8
+ * channels per pixel, fp64 products and sums in that order, round half to even; bit exact.  rgb: rows x cols pixels,
+ * in_pitch_bytes between rows; writes uint8 and / or float32 (either may be NULL) with out_pitch_elems between rows. */
+int scd_grayscale_u8(const uint8_t* rgb, int rows, int cols, int channels, size_t in_pitch_bytes,
+                     uint8_t* gray_u8, float* gray_f32, size_t out_pitch_elems, void* stream);
+
+/* normalize (datasets/argumentations.py:39-44, applied per tile in fp64 by test.py:89) for a batch of uint8 tiles
+ * (n, 512, 512) -> float32: what TileDetector.detect_host runs on tiles that arrive as grey bytes (a quarter of the
+ * host -> device traffic of float32 tiles). */
+int scd_tiles_normalize_u8(const uint8_t* tiles_u8, int n_tiles, float* tiles, void* stream);
+
+/* Detection merge of the whole-slide flow (test.py:103-140) for one batch of tiles: planes (10, n_tiles, K) f32 = the
+ * Wrapper stack of tiles [tile_begin, tile_begin + n_tiles) of a (height, width) slide.  Keeps score > threshold and
+ * APPENDS rows [int(x), int(y), ratio] (fp64; x = int(tx*384 - padLR + ctX*4 + offX), ratio = (rad*4 - minL*4) /
+ * (2*minL*4)) behind *d_count in tile order then rank order: calls on one stream in tile order reproduce the reference's
+ * host loop.  Rows past `cap` are dropped (the count still advances).  n_tiles <= 4096 per call. */
+int scd_slide_merge(const float* planes, int n_tiles, int K, int tile_begin, int height, int width,
+                    float threshold, double* rows, int cap, int* d_count, void* stream);
+
+/* cudaMemcpy2DAsync host -> device (the strip upload above; pinned host memory makes it asynchronous). */
+int scd_copy2d_h2d(void* dst, size_t dst_pitch_bytes, const void* src, size_t src_pitch_bytes, size_t width_bytes,
+                   size_t rows, void* stream);
 
 #ifdef __cplusplus
 }

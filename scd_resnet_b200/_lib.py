@@ -79,6 +79,12 @@ PROTOTYPES = {
     "scd_slide_geometry": (c_int, [c_int, c_int, c_void_p]),
     "scd_slide_tiles": (c_int, [c_void_p] + [c_int] * 4 + [c_void_p, c_void_p]),
     "scd_slide_tiles_u8": (c_int, [c_void_p] + [c_int] * 4 + [c_void_p, c_void_p]),
+    "scd_slide_tiles_strip": (c_int, [c_void_p] + [c_int] * 8 + [c_void_p, c_void_p]),
+    "scd_slide_column_span": (c_int, [c_int, c_int, c_int, c_void_p]),
+    "scd_grayscale_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "scd_tiles_normalize_u8": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "scd_slide_merge": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_void_p]),
+    "scd_copy2d_h2d": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p]),
 }
 
 

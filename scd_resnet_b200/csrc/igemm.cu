@@ -42,7 +42,6 @@ struct alignas(64) IgemmParams {
     int b_resident;                 // BN = 64 only: the whole weight matrix (<= 9 k-blocks) stays in shared memory
     int row_mode;                   // BN = 64, 3x3 s1, Cin = 64, W = 128: one image row per tile, A = 3-row halo strip loaded once
     int bo_mode;                    // row_mode: put (start address >> 7) & 7 into the descriptor's base_offset field
-    uint32_t b_fmt;                 // 16-bit format of the WEIGHT operand: 1 = bf16, 0 = fp16 (activations: template F16)
     CUtensorMap tmHalo;             // box {64 ch, 130 x, 3 y}
     CUtensorMap tmOutRow;           // box {64 ch, 32 x, 1 y}
     CUtensorMap tmRes;              // row mode with a residual: box {64 ch, 128 x, 1 y}, prefetched by the producer
@@ -190,8 +189,8 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            const uint32_t idesc_main = tc::umma_idesc_16ab(IG_BM, BN > 256 ? 256 : BN, A16::kFmt, p.b_fmt);
-            const uint32_t idesc_tail = tc::umma_idesc_16ab(IG_BM, BN > 256 ? BN - 256 : 16, A16::kFmt, p.b_fmt);
+            constexpr uint32_t idesc_main = tc::umma_idesc_16(IG_BM, BN > 256 ? 256 : BN, A16::kFmt);
+            constexpr uint32_t idesc_tail = tc::umma_idesc_16(IG_BM, BN > 256 ? BN - 256 : 16, A16::kFmt);
             int stage = 0; uint32_t phase = 0;
             uint32_t it = 0;
             if (resb) { tc::mbar_wait(resb_bar, 0); tc::tc_fence_after(); }
@@ -539,10 +538,8 @@ static int pick_bn(int cout) { return cout >= 256 ? 256 : (cout >= 128 ? 128 : 6
 
 static int conv_igemm(int kind, const void* x, const void* x2, const void* weight, const float* bias,
                       const void* residual, int relu, int batch, int hin, int win, int cin, int cout, void* y,
-                      void* stream, bool f16 = false, int w_f16 = -1)
+                      void* stream, bool f16 = false)
 {
-    // f16: activations (input, residual, output) are fp16 instead of bf16; w_f16: the packed weights are fp16 (default:
-    // like the activations).  f16 && !w_f16 = the "mixed" plan: bf16 weights x fp16 activations.
     using namespace scd;
     if (batch <= 0) return SCD_OK;
     if (!x || !weight || !bias || !y) return fail(SCD_EINVAL, "scd_conv_igemm: null pointer");
@@ -553,7 +550,6 @@ static int conv_igemm(int kind, const void* x, const void* x2, const void* weigh
     const int bn = pick_bn(cout);
     if (cout % bn) return fail(SCD_EINVAL, "Cout = %d unsupported", cout);
     p.cout = cout; p.n_tiles_n = cout / bn; p.relu = relu;
-    p.b_fmt = (w_f16 < 0 ? f16 : (w_f16 != 0)) ? 0u : 1u;
     p.b_resident = (bn == 64 && p.n_par == 1 && p.n_tiles_n == 1 && p.n_taps[0] * p.cin_blocks <= IgemmCfg<64>::RES_B_BLOCKS) ? 1 : 0;
     // SCD_IGEMM_ROW_MODE: 0 = off, 1 = on (default), 2 = on with the pattern phase in the descriptor's base_offset field.
     // Measured on B200: tcgen05 derives the 128-byte swizzle phase from the operand's shared-memory ADDRESS bits, so a
@@ -622,15 +618,16 @@ extern "C" int scd_conv_igemm_fwd_f16(int kind, const void* x, const void* weigh
     return conv_igemm(kind, x, nullptr, weight, bias, residual, relu, batch, hin, win, cin, cout, y, stream, true);
 }
 
-// fmt: 0 = bf16 weights and activations, 1 = fp16 both, 2 = bf16 weights x fp16 activations
+// fmt: 0 = bf16 operands and activations, 1 = fp16.  (tcgen05 kind::f16 wants ONE format for A and B: an instruction
+// descriptor with A = fp16 and B = bf16 raises an illegal-instruction fault on sm_100a, measured; the "mixed" precision
+// plan therefore stores the bf16-rounded weights in fp16 containers, weights.py.)
 extern "C" int scd_conv_igemm_fwd_fmt(int kind, int fmt, const void* x, const void* weight, const float* bias,
                                       const void* residual, int relu, int batch, int hin, int win,
                                       int cin, int cout, void* y, void* stream)
 {
     if (kind < 0 || kind > 3) return scd::fail(SCD_EINVAL, "scd_conv_igemm_fwd_fmt: kind must be 0..3");
-    if (fmt < 0 || fmt > 2) return scd::fail(SCD_EINVAL, "scd_conv_igemm_fwd_fmt: fmt must be 0, 1 or 2");
-    return conv_igemm(kind, x, nullptr, weight, bias, residual, relu, batch, hin, win, cin, cout, y, stream, fmt != 0,
-                      fmt == 1);
+    if (fmt < 0 || fmt > 1) return scd::fail(SCD_EINVAL, "scd_conv_igemm_fwd_fmt: fmt must be 0 (bf16) or 1 (fp16)");
+    return conv_igemm(kind, x, nullptr, weight, bias, residual, relu, batch, hin, win, cin, cout, y, stream, fmt != 0);
 }
 
 extern "C" int scd_conv_igemm_dgrad(int kind, const void* dz, const void* dz2, const void* weight, const float* bias,
@@ -645,8 +642,7 @@ extern "C" int scd_conv_igemm_dgrad(int kind, const void* dz, const void* dz2, c
 
 static int heads_fwd(const void* x, const void* w3, const float* b3, const float* w1,
                      const float* b1, int batch, int height, int width,
-                     float* heat, float* regr, float* offset, void* hidden, void* stream, bool f16 = false, int cin = 256,
-                     int w_f16 = -1)
+                     float* heat, float* regr, float* offset, void* hidden, void* stream, bool f16 = false, int cin = 256)
 {
     using namespace scd;
     if (batch <= 0) return SCD_OK;
@@ -657,7 +653,6 @@ static int heads_fwd(const void* x, const void* w3, const float* b3, const float
     int rc = fill_geometry(p, 0, x, nullptr, batch, height, width, cin, f16);
     if (rc) return rc;
     p.cout = 384; p.n_tiles_n = 1; p.relu = 1;
-    p.b_fmt = (w_f16 < 0 ? f16 : (w_f16 != 0)) ? 0u : 1u;
     p.total_tiles = batch * p.tiles_y * p.tiles_x;
     p.bias = b3; p.w1 = w1; p.b1 = b1; p.heat = heat; p.regr = regr; p.off = offset;
     rc = make_w_map(&p.tmB, w3, 9 * cin, 384, IgemmCfg<384>::B_BOX_ROWS, f16);
@@ -706,8 +701,8 @@ extern "C" int scd_heads_fwd_fmt(int fmt, const void* x, const void* w3, const f
                                  float* heat, float* regr, float* offset, void* stream)
 {
     if (cin % 64 || cin < 64 || cin > 512) return scd::fail(SCD_EINVAL, "scd_heads_fwd_fmt: cin = %d", cin);
-    if (fmt < 0 || fmt > 2) return scd::fail(SCD_EINVAL, "scd_heads_fwd_fmt: fmt must be 0, 1 or 2");
-    return heads_fwd(x, w3, b3, w1, b1, batch, height, width, heat, regr, offset, nullptr, stream, fmt != 0, cin, fmt == 1);
+    if (fmt < 0 || fmt > 1) return scd::fail(SCD_EINVAL, "scd_heads_fwd_fmt: fmt must be 0 (bf16) or 1 (fp16)");
+    return heads_fwd(x, w3, b3, w1, b1, batch, height, width, heat, regr, offset, nullptr, stream, fmt != 0, cin);
 }
 
 extern "C" int scd_heads_fwd_train(const void* x, const void* w3, const float* b3, const float* w1,

@@ -200,7 +200,7 @@ extern "C" int scd_resnet_infer(int depth, const int* dims8, int f16, const floa
         return SCD_OK;
     };
     if ((rc = mark(0))) return rc;
-    if (f16 < 0 || f16 > 2) return fail(SCD_EINVAL, "scd_resnet_infer: format %d (0 = bf16, 1 = fp16, 2 = bf16 weights x fp16 activations)", f16);
+    if (f16 < 0 || f16 > 1) return fail(SCD_EINVAL, "scd_resnet_infer: format %d (0 = bf16, 1 = fp16)", f16);
     rc = scd_stem_fwd_fmt(f16, x, W(0), Bf(1), batch, height, width, buf[0], stream);
     if (rc) return rc;
     if ((rc = mark(1))) return rc;

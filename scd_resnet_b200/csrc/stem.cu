@@ -47,8 +47,7 @@ constexpr int SP_LD_ITERS = (2 * ST_PS * ST_PS + 127) / 128;                // 7
 template <bool F16>
 __global__ void __launch_bounds__(SP_THREADS, 2)
 stem_pipe_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ x,
-                 const float* __restrict__ bias, int batch, int height, int width, __nv_bfloat16* __restrict__ y,
-                 uint32_t b_fmt /* weights: 1 = bf16, 0 = fp16 */)
+                 const float* __restrict__ bias, int batch, int height, int width, __nv_bfloat16* __restrict__ y)
 {
     using A16 = tc::Act<F16>;
     extern __shared__ unsigned char smem_dyn[];
@@ -150,7 +149,7 @@ stem_pipe_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restric
         // ===================== MMA issuer =====================
         if (lane == 0) {
             tc::mbar_wait(bar_w, 0);
-            const uint32_t idesc = tc::umma_idesc_16ab(128, ST_CO, A16::kFmt, b_fmt);
+            constexpr uint32_t idesc = tc::umma_idesc_16(128, ST_CO, A16::kFmt);
             uint32_t it = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
                 const int s = it % SP_STAGES;
@@ -381,7 +380,7 @@ stem_conv_train_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
 
 template <bool F16>
 static int stem_fwd_impl(const float* x, const void* weight, const float* bias, int batch,
-                         int height, int width, void* y, void* stream, bool w_f16 = F16)
+                         int height, int width, void* y, void* stream)
 {
     using namespace scd;
     if (batch <= 0) return SCD_OK;
@@ -394,7 +393,7 @@ static int stem_fwd_impl(const float* x, const void* weight, const float* bias, 
     SCD_SMEM_ATTR(stem_pipe_kernel<F16>, SP_SMEM);
     const int total = (height / 4 / ST_P) * (width / 4 / ST_P) * batch;
     stem_pipe_kernel<F16><<<total < 2 * kNumSMs ? total : 2 * kNumSMs, SP_THREADS, SP_SMEM, (cudaStream_t)stream>>>(
-        tmW, x, bias, batch, height, width, reinterpret_cast<__nv_bfloat16*>(y), w_f16 ? 0u : 1u);
+        tmW, x, bias, batch, height, width, reinterpret_cast<__nv_bfloat16*>(y));
     SCD_LAUNCH_CHECK("stem_pipe_kernel");
     return SCD_OK;
 }
@@ -416,8 +415,7 @@ extern "C" int scd_stem_fwd_fmt(int fmt, const float* x, const void* weight, con
 {
     if (fmt == 0) return stem_fwd_impl<false>(x, weight, bias, batch, height, width, y, stream);
     if (fmt == 1) return stem_fwd_impl<true>(x, weight, bias, batch, height, width, y, stream);
-    if (fmt == 2) return stem_fwd_impl<true>(x, weight, bias, batch, height, width, y, stream, false);
-    return scd::fail(SCD_EINVAL, "scd_stem_fwd_fmt: fmt must be 0, 1 or 2");
+    return scd::fail(SCD_EINVAL, "scd_stem_fwd_fmt: fmt must be 0 (bf16) or 1 (fp16)");
 }
 
 extern "C" int scd_stem_conv_train(const float* x, const void* weight, int batch, int height, int width,

@@ -137,11 +137,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_16(int m, int n, uint32_t fmt)
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// A (activations) and B (weights) formats chosen independently: kind::f16 multiplies fp16 x bf16 exactly into fp32.
-__host__ __device__ constexpr uint32_t umma_idesc_16ab(int m, int n, uint32_t afmt, uint32_t bfmt) {
-    return (1u << 4) | (afmt << 7) | (bfmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-
+// (A = fp16 with B = bf16 in one descriptor is NOT accepted by sm_100a: illegal-instruction fault, measured in round 2.)
 // Element type of the inference activations / GEMM operands.  bf16 is the configuration BASELINE names; fp16
 // runs at the same tensor-core rate with an 8x finer mantissa (the network's values are O(1..100): BatchNorm is
 // folded and the tiles are normalised) and saturates at +-65504 instead of producing inf.

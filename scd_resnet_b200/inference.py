@@ -38,6 +38,7 @@ class TileDetector:
             self.in_ready = [torch.cuda.Event() for _ in range(2)]
             self.in_free = [torch.cuda.Event() for _ in range(2)]
             self.out_ready = [torch.cuda.Event() for _ in range(2)]
+            self.dev_in_u8 = None                                    # grey-byte tiles: allocated on first use
             self._host_ring = None
         self.launches_per_batch = len(ops.resnet_conv_specs(self.depth, self.kdims)) + 3     # stem + igemms + heads + decode
 
@@ -50,10 +51,17 @@ class TileDetector:
         return ops.decode_topk(heat, regr, off, K=self.K, planes=True)[6]
 
     def detect_host(self, host_batches):
-        """host_batches: list of pinned (B,1,H,W) f32 host tensors.  Returns a list of (10,B,K) host tensors.
+        """host_batches: list of pinned (B,1,H,W) host tensors, float32 (normalised tiles, what the network consumes) or
+        uint8 (grey values as the slide holds them: a quarter of the bytes over the host link; the per-tile fp64
+        normalisation of test.py:89 then runs on the device, scd_tiles_normalize_u8).  Returns a list of (10,B,K) host
+        tensors.
 
         Copies run on copy_stream, kernels on compute_stream, two buffers each way."""
         n = len(host_batches)
+        if any(hb.dtype == torch.uint8 for hb in host_batches) and self.dev_in_u8 is None:
+            with torch.cuda.device(self.device):
+                self.dev_in_u8 = [torch.empty(self.batch, 1, self.h, self.w, dtype=torch.uint8, device=self.device)
+                                  for _ in range(2)]
         if self._host_ring is None or self._host_ring.shape[0] < n:
             self._host_ring = torch.empty(n, 10, self.batch, self.K, pin_memory=True)
         results = []
@@ -67,10 +75,13 @@ class TileDetector:
                 with torch.cuda.stream(self.copy_stream):
                     if i >= 2:
                         self.copy_stream.wait_event(self.in_free[s])      # batch i-2 has consumed this buffer
-                    self.dev_in[s][:b].copy_(hb, non_blocking=True)
+                    u8 = hb.dtype == torch.uint8
+                    (self.dev_in_u8 if u8 else self.dev_in)[s][:b].copy_(hb, non_blocking=True)
                     self.in_ready[s].record(self.copy_stream)
                 with torch.cuda.stream(self.compute_stream):
                     self.compute_stream.wait_event(self.in_ready[s])
+                    if u8:
+                        ops.tiles_normalize_u8(self.dev_in_u8[s][:b], out=self.dev_in[s])
                     planes = self.detect_device(self.dev_in[s][:b])
                     self.in_free[s].record(self.compute_stream)
                     self.out_ready[s].record(self.compute_stream)

@@ -170,16 +170,15 @@ def _act_dtype(weight):
 
 
 def _fmt(weight, act_dtype):
-    """(fmt code of the *_fmt entry points, activation dtype) for a packed weight and the requested activation dtype."""
+    """(fmt code of the *_fmt entry points, activation dtype) for a packed weight and the requested activation dtype.
+    The tensor core wants one format for both operands (kind::f16 faults on fp16 x bf16); the "mixed" precision plan
+    packs its bf16-rounded weights as fp16 (weights.to_operand)."""
     wd = _act_dtype(weight)
     ad = wd if act_dtype is None else act_dtype
-    if wd == torch.bfloat16 and ad == torch.bfloat16:
-        return 0, ad
-    if wd == torch.float16 and ad == torch.float16:
-        return 1, ad
-    if wd == torch.bfloat16 and ad == torch.float16:
-        return 2, ad
-    raise ScdError("unsupported operand formats: weights %s, activations %s" % (wd, ad))
+    if wd != ad:
+        raise ScdError("weights (%s) and activations (%s) must share one 16-bit format; for bf16 weights with fp16 "
+                       "activations pack the weights with precision 'mixed'" % (wd, ad))
+    return (0 if wd == torch.bfloat16 else 1), ad
 
 
 def augment_batch(samples, locs, counts, index, flips, jitter, noise=None, noise_sv=0.05, jitter_sv=0.05):
@@ -339,7 +338,7 @@ def resnet_infer(x, blob, depth=10, dims=None, workspace=None, out=None, stage_e
 
     x (B,1,H,W) f32; blob = packed BN-folded weights (weights.pack_infer_blob with the same depth / dims; `fp16`
     must match the dtype it was packed with).  depth = numLayers (10, 18, 34); dims = kernel-level (padded) widths.
-    fmt (overrides fp16): 0 = bf16, 1 = fp16, 2 = mixed, bf16 weights x fp16 activations (weights.PRECISIONS).
+    fmt (overrides fp16): 0 = bf16, 1 = fp16 (weights.PRECISIONS; the "mixed" plan runs fmt 1 on bf16-rounded weights).
     Returns heat, regr, offset (NCHW f32) and the workspace (reusable).
     """
     x = _req(x, torch.float32, "x")
@@ -399,3 +398,80 @@ def slide_tiles(gray, tile_begin=0, tile_end=None):
     with torch.cuda.device(gray.device):
         check(fn(_ptr(gray), h, w, tile_begin, tile_end, _ptr(tiles), _stream()), "scd_slide_tiles")
     return tiles
+
+
+def slide_column_span(height, width, tile_column):
+    """Slide columns [lo, hi) the tiles of one tile column read (reflect pad and 3200-wide fix-up included)."""
+    v = (ctypes.c_int * 2)()
+    check(lib.scd_slide_column_span(height, width, tile_column, v), "scd_slide_column_span")
+    return v[0], v[1]
+
+
+def slide_tiles_strip(strip, height, width, col0, tile_begin, tile_end, out=None):
+    """slide_tiles from a column strip: strip (height, ncols) CUDA tensor (uint8 or float32, rows may be padded: the row
+    stride is taken from the tensor) holding slide columns [col0, col0 + ncols)."""
+    if strip.dtype not in (torch.uint8, torch.float32) or not strip.is_cuda or strip.dim() != 2 or strip.stride(1) != 1:
+        raise ScdError("strip must be a 2-D CUDA tensor of uint8 or float32 with unit column stride")
+    if strip.shape[0] != height:
+        raise ScdError("strip must hold every row of the slide")
+    n = tile_end - tile_begin
+    if out is None:
+        out = torch.empty(n, 1, 512, 512, dtype=torch.float32, device=strip.device)
+    with torch.cuda.device(strip.device):
+        check(lib.scd_slide_tiles_strip(_ptr(strip), int(strip.dtype == torch.uint8), height, width, col0, strip.shape[1],
+                                        strip.stride(0), tile_begin, tile_end, _ptr(out), _stream()), "scd_slide_tiles_strip")
+    return out[:n]
+
+
+def grayscale(rgb, out_dtype=torch.uint8, out=None):
+    """ref: test.py:21-33 on the device: rgb (H,W,C>=3) uint8 CUDA -> (H,W) rounded grey values, uint8 or float32.
+    rgb may be a column slice of a larger image (row stride taken from the tensor); `out`: a (H,W) CUDA tensor or
+    column slice to write into."""
+    if not isinstance(rgb, torch.Tensor) or not rgb.is_cuda or rgb.dtype != torch.uint8:
+        raise ScdError("rgb must be a uint8 CUDA tensor")
+    if rgb.dim() != 3 or rgb.shape[2] < 3 or rgb.stride(2) != 1 or rgb.stride(1) != rgb.shape[2]:
+        raise ScdError("rgb must be (H,W,C) with at least three channels, channels innermost")
+    h, w, c = rgb.shape
+    if out is None:
+        if out_dtype not in (torch.uint8, torch.float32):
+            raise ScdError("out_dtype must be torch.uint8 or torch.float32")
+        out = torch.empty(h, w, dtype=out_dtype, device=rgb.device)
+    if out.shape != (h, w) or out.stride(1) != 1 or out.dtype not in (torch.uint8, torch.float32):
+        raise ScdError("out must be (H,W) uint8 / float32 with unit column stride")
+    g8, gf = (out, None) if out.dtype == torch.uint8 else (None, out)
+    with torch.cuda.device(rgb.device):
+        check(lib.scd_grayscale_u8(_ptr(rgb), h, w, c, rgb.stride(0), _ptr(g8), _ptr(gf), out.stride(0), _stream()),
+              "scd_grayscale_u8")
+    return out
+
+
+def tiles_normalize_u8(tiles_u8, out=None):
+    """normalize (ref: datasets/argumentations.py:39-44 as test.py:89 applies it) of (B,1,512,512) uint8 tiles -> f32."""
+    tiles_u8 = _req(tiles_u8, torch.uint8, "tiles")
+    b = tiles_u8.shape[0]
+    if tuple(tiles_u8.shape[-2:]) != (512, 512) or tiles_u8.numel() != b * 512 * 512:
+        raise ScdError("tiles must be (B,1,512,512) uint8")
+    if out is None:
+        out = torch.empty(b, 1, 512, 512, dtype=torch.float32, device=tiles_u8.device)
+    with torch.cuda.device(tiles_u8.device):
+        check(lib.scd_tiles_normalize_u8(_ptr(tiles_u8), b, _ptr(out), _stream()), "scd_tiles_normalize_u8")
+    return out[:b]
+
+
+def slide_merge(planes, tile_begin, height, width, rows, count, threshold=0.3):
+    """Append the detections of one batch (planes (10,b,K) f32, tiles tile_begin ..) to rows (cap,3) f64 / count (1) i32."""
+    planes = _req(planes, torch.float32, "planes")
+    with torch.cuda.device(planes.device):
+        check(lib.scd_slide_merge(_ptr(planes), planes.shape[1], planes.shape[2], tile_begin, height, width, threshold,
+                                  _ptr(rows), rows.shape[0], _ptr(count), _stream()), "scd_slide_merge")
+
+
+def copy2d_h2d(dst, src, stream=None):
+    """dst (rows, cols) CUDA view <- src (rows, cols) host view, both with unit column stride (cudaMemcpy2DAsync)."""
+    if dst.shape != src.shape or dst.dtype != src.dtype or dst.stride(1) != 1 or src.stride(1) != 1:
+        raise ScdError("copy2d_h2d: 2-D views of equal shape / dtype with unit column stride expected")
+    es = dst.element_size()
+    st = ctypes.c_void_p(stream.cuda_stream) if stream is not None else _stream()
+    with torch.cuda.device(dst.device):
+        check(lib.scd_copy2d_h2d(_ptr(dst), dst.stride(0) * es, _ptr(src), src.stride(0) * es, dst.shape[1] * es,
+                                 dst.shape[0], st), "scd_copy2d_h2d")

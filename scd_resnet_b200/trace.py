@@ -137,7 +137,7 @@ def load_exported(path, device="cuda"):
         depth, dims, kdims = weights.arch_of(sd)
         obj = {"format": FORMAT, "architecture": architecture_of(sd), "numLayers": depth, "dims": list(dims),
                "kernel_dims": list(kdims), "precision": weights.DEFAULT_PRECISION, "K": 100,
-               "blob": weights.pack_infer_blob(sd, "cpu")}
+               "blob": weights.pack_infer_blob(sd, "cpu", weights.precision_spec(weights.DEFAULT_PRECISION)[1])}
     header = {k: v for k, v in obj.items() if k not in ("blob", "state_dict")}
     return ExportedDetector(header, obj["blob"], torch.device(device))
 

@@ -303,21 +303,24 @@ def test_slide_tiles_opencv_fixup_width(S):
 
 
 # ------------------------------------------------------------------------------ stem
-@pytest.mark.parametrize("dt,adt", [(torch.bfloat16, None), (torch.float16, None), (torch.bfloat16, torch.float16)])
-def test_stem(S, dt, adt):
-    """dt: weight format; adt: activation format (None = dt; bf16 weights + fp16 activations = the mixed plan)."""
+@pytest.mark.parametrize("plan", ["bf16", "fp16", "mixed"])
+def test_stem(S, plan):
+    """plan: weights.PRECISIONS ("mixed" = bf16-rounded weights in fp16 containers, fp16 activations)."""
     sd = O.make_state_dict(1234)
-    f = S.weights.fold(sd, dt)
+    fmt, wdt = S.weights.precision_spec(plan)
+    dt = torch.bfloat16 if fmt == 0 else torch.float16
+    f = S.weights.fold(sd, wdt)
+    assert f["stem_w"].dtype == dt
     x = O.make_tiles(2, seed=3)
-    y = S.ops.stem_fwd(dev(x), dev(f["stem_w"]), dev(f["stem_b"]), act_dtype=adt)
-    assert y.dtype == (adt or dt)
+    y = S.ops.stem_fwd(dev(x), dev(f["stem_w"]), dev(f["stem_b"]))
+    assert y.dtype == dt
     y = y.float().cpu().permute(0, 3, 1, 2)
     t = F.conv2d(x, sd["preprocess.0.weight"], None, stride=2, padding=3)
     t = F.relu(F.batch_norm(t, sd["preprocess.1.running_mean"], sd["preprocess.1.running_var"],
                             sd["preprocess.1.weight"], sd["preprocess.1.bias"], False, 0.1, 1e-5))
     t = F.max_pool2d(t, 3, 2, 1)
     assert y.shape == t.shape
-    tol = 1.0 if dt == torch.bfloat16 else 0.15              # fp16: 8x finer mantissa
+    tol = {"bf16": 1.0, "fp16": 0.15, "mixed": 0.7}[plan]    # fp16: 8x finer mantissa; mixed: the bf16 weights remain
     assert relmax(y, t) < 1e-2 * tol                         # bf16 operands and output: 1e-2 rel (north star)
     assert ((y - t).double().pow(2).mean().sqrt() / t.double().pow(2).mean().sqrt()) < 5e-3 * tol
     # pool padding / image borders: exact zeros stay zeros, shapes of the border rows are right
@@ -352,7 +355,10 @@ def _conv_case(S, kind, b, h, w, cin, cout, residual, relu, seed, dt=torch.bfloa
         ref = F.relu(ref)
     xg = dev(x.permute(0, 2, 3, 1).contiguous().to(dt))
     rg = dev(res.permute(0, 2, 3, 1).contiguous().to(dt)) if residual else None
-    y = S.ops.conv_igemm_fwd(kind, xg, dev(S.weights.pack_conv(wt, kind, None, wdt)), dev(bias), rg, relu)
+    pack_dt = S.weights.PRECISIONS["mixed"][1] if (dt == torch.float16 and wdt == torch.bfloat16) else wdt
+    wp = S.weights.pack_conv(wt, kind, None, pack_dt)        # mixed: bf16-rounded values in fp16 containers (exact here)
+    assert wp.dtype == dt
+    y = S.ops.conv_igemm_fwd(kind, xg, dev(wp), dev(bias), rg, relu)
     torch.cuda.synchronize()
     assert y.dtype == dt
     y = y.float().cpu().permute(0, 3, 1, 2)
@@ -391,8 +397,8 @@ def test_conv_igemm_fp16(S, case):
                                   (1, 2, 128, 128, 64, 128, False, True), (2, 2, 32, 32, 256, 512, False, False),
                                   (3, 1, 64, 64, 256, 256, False, True)])
 def test_conv_igemm_mixed(S, case):
-    """bf16 weights x fp16 activations: tcgen05 kind::f16 with different A / B formats; products are exact in fp32, so
-    against the same rounded operands only the fp16 output rounding remains."""
+    """The mixed plan: bf16-rounded weights in fp16 containers x fp16 activations (kind::f16 faults on fp16 x bf16 in one
+    instruction); products are exact in fp32, so against the same rounded operands only the fp16 output rounding remains."""
     _conv_case(S, *case, seed=hash(case) % 1000, dt=torch.float16, wdt=torch.bfloat16)
 
 
@@ -405,14 +411,16 @@ def test_conv_igemm_fp16_saturates(S):
     assert torch.isfinite(y.float()).all() and float(y.float().max()) == 65504.0
 
 
-@pytest.mark.parametrize("dt,adt", [(torch.bfloat16, None), (torch.float16, None), (torch.bfloat16, torch.float16)])
-def test_heads(S, dt, adt):
-    adt = adt or dt
+@pytest.mark.parametrize("plan", ["bf16", "fp16", "mixed"])
+def test_heads(S, plan):
+    fmt, wdt = S.weights.precision_spec(plan)
+    adt = torch.bfloat16 if fmt == 0 else torch.float16
+    dt = torch.bfloat16 if plan != "fp16" else torch.float16      # the format the weight VALUES are rounded to
     _bf16 = lambda t: t.to(adt).float()
     _wr = lambda t: t.to(dt).float()
     rng = np.random.default_rng(31)
     sd = O.make_state_dict(1234)
-    f = S.weights.fold(sd, dt)
+    f = S.weights.fold(sd, wdt)
     x = _bf16(torch.from_numpy(np.abs(rng.standard_normal((2, 256, 128, 128))).astype(np.float32)))
     heat, regr, off = S.ops.heads_fwd(dev(x.permute(0, 2, 3, 1).contiguous().to(adt)),
                                       dev(f["head_w3"]), dev(f["head_b3"]), dev(f["head_w1"]), dev(f["head_b1"]))

@@ -53,7 +53,8 @@ def test_checkpoint_formats_and_export(tmp_path, variant):
     header = trace.main([out, "-a", name, "-m", p2, "-s", "1 1 512 512", "-wrapped", "--raw"])
     assert header["architecture"] == name and header["numLayers"] == depth and header["dims"] == list(dims)
     payload = torch.load(out, map_location="cpu", weights_only=True)
-    blob = weights.pack_infer_blob(sd, "cpu")
+    blob = weights.pack_infer_blob(sd, "cpu", weights.precision_spec(weights.DEFAULT_PRECISION)[1])
+    assert header["precision"] == "mixed" and blob.dtype == torch.uint8
     assert torch.equal(payload["blob"], blob) and payload["blob_bytes"] == blob.numel()
     assert all(torch.equal(payload["state_dict"][k], sd[k]) for k in sd)
     raw = np.fromfile(out + ".blob", dtype=np.uint8)

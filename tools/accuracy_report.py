@@ -24,7 +24,8 @@ with torch.no_grad():
 blob = S.weights.pack_infer_blob(sd, "cuda")
 heat, regr, off, _ = S.ops.resnet10_infer(x.cuda(), blob, fmt=0)
 rep = {"ours_bf16_vs_fp32_oracle": {k: metrics(v, ref[k]) for k, v in (("heatmap", heat), ("regr", regr), ("offset", off))}}
-hm, rm, om, _ = S.ops.resnet10_infer(x.cuda(), blob, fmt=2)
+mfmt, mdt = S.weights.precision_spec("mixed")
+hm, rm, om, _ = S.ops.resnet10_infer(x.cuda(), S.weights.pack_infer_blob(sd, "cuda", mdt), fmt=mfmt)
 rep["ours_mixed_bf16w_fp16a_vs_fp32_oracle"] = {k: metrics(v, ref[k]) for k, v in (("heatmap", hm), ("regr", rm), ("offset", om))}
 blob16 = S.weights.pack_infer_blob(sd, "cuda", torch.float16)
 h16, r16, o16, _ = S.ops.resnet10_infer(x.cuda(), blob16, fp16=True)

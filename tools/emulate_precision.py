@@ -37,7 +37,7 @@ def forward(sd, x, plan):
     """plan(stage_name) -> (weight format, output activation format)."""
     w, b = fold(sd, "preprocess.0", "preprocess.1")
     wf, af = plan("stem")
-    t = F.relu(F.conv2d(rnd(x, "fp32"), rnd(w, wf), b, stride=2, padding=3))
+    t = F.relu(F.conv2d(rnd(x, af), rnd(w, wf), b, stride=2, padding=3))      # the tile enters the MMA in the activation format
     t = rnd(F.max_pool2d(t, 3, 2, 1), af)
     for li in range(1, 5):
         p = "layer%d.0" % li
