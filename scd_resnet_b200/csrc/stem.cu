@@ -12,6 +12,7 @@
 // built in shared memory with 2 x LDS.64 + 1 x STS.128 per chunk (128-byte swizzle applied by
 // hand), and 289 conv outputs x 64 channels take 12 tcgen05.mma (M=128, N=64, K=16) into TMEM.
 // The CUDA-core version of this stage cost 1.34 ms per 64-tile batch (32 % of the step).
+#include <cstdlib>
 #include "tc.cuh"
 #include "tmap.cuh"
 
@@ -250,6 +251,260 @@ stem_pipe_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// Row kernel (round 2): the A operand is read IN PLACE from the space-to-depth patch, no im2col copy, and the 3x3 s2
+// max pool happens in registers.
+//
+//   * K-major operand WITHOUT swizzle (cute/atom/mma_traits_sm100.hpp: ((8,m),(T,2)):((1T,SBO),(1,LBO)) in 16 B units):
+//     the 8 rows of a core matrix sit 16 B apart, the second K chunk LBO further, the next 8 rows SBO further.  Measured
+//     with scd_probe_umma (tools/probe_umma_desc.py): any 16 B-granular start address, LBO = 16 B (overlapping core
+//     matrices) and mixing with a 128 B-swizzled B operand all behave as that formula says.
+//   * One 16 B entry = two neighbouring s2d pixels = half the K = 16 values of one tap row dy.  For every s2d row two
+//     arrays are staged: P0[j] = (pix 2j, 2j+1), P1[j] = (pix 2j+1, 2j+2).  Conv column cx = 2 px + d (the three columns
+//     under pooled pixel px) reads (pix cx-2, cx-1 | cx, cx+1) = two CONSECUTIVE entries of P0 (d = 0) or P1 (d = -1,
+//     +1), and consecutive pooled pixels px are consecutive entries: an M tile of 128 pooled pixels of one row is the
+//     descriptor {start = array + entry offset, rows 16 B apart, LBO = 16 B, SBO = 128 B}; the four tap rows dy are
+//     four MMAs (K = 16 each) on four s2d rows.  Nothing is copied, 4.2 KB of shared memory per s2d row.
+//   * A pooled row py needs conv rows 2py-1, 2py, 2py+1, each at d = -1, 0, +1: nine conv tiles whose TMEM lane i is
+//     the SAME pooled pixel, so the pool is a per-thread max over accumulators.  Row 2py+1 is also row 2(py+1)-1: its
+//     max is carried in registers to the next pooled row, leaving six tiles = 24 MMAs (N = 64) per 128 pooled pixels.
+//     bias + ReLU commute with the max and run once per pooled value.
+//   * CTA = 3 loader warps (fp32 rows -> 16-bit entries, two new s2d rows per pooled row into a ring of eight), one MMA
+//     warp, eight epilogue warps (TMEM lane quarter x channel half); the even-row and odd-row tile groups use two
+//     192-column TMEM buffers, so the tensor core runs one group ahead of the epilogue.  One CTA per SM, each walks a
+//     contiguous range of (image, pooled row) units.
+constexpr int SR_THREADS = 384;                            // 3 loader warps, 1 MMA warp, 8 epilogue warps (12 warps: 168 registers)
+constexpr int SR_LOADERS = 96;
+constexpr int SR_ENT = 132;                                // 16 B entries per array: pooled px 0..127 use entries 0..129
+constexpr int SR_ARR = SR_ENT * 16;
+constexpr int SR_ROW = 2 * SR_ARR;                         // P0 | P1 of one s2d row
+constexpr int SR_SLOTS = 8;                                // ring of s2d rows, slot = (Y + 8) & 7
+constexpr int SR_OFF_ROWS = 8192;                          // behind the 64 x 64 weight tile
+constexpr int SR_OFF_BAR = SR_OFF_ROWS + SR_SLOTS * SR_ROW;
+constexpr int SR_SMEM = SR_OFF_BAR + 256 + 256 + 1024;     // barriers | bias | align slack
+constexpr int SR_EBUF = 0, SR_OBUF = 192;                  // TMEM columns of the two tile groups (3 tiles x 64)
+
+// K-major, no swizzle: rows 16 B apart inside a core matrix, LBO = 16 B to the second K chunk, SBO = 128 B to the next 8 rows
+__device__ __forceinline__ uint64_t stem_adesc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(16u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+}
+
+template <bool F16>
+__global__ void __launch_bounds__(SR_THREADS, 1)
+stem_row_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ x, const float* __restrict__ bias,
+                int batch, int height, int width, __nv_bfloat16* __restrict__ y)
+{
+    using A16 = tc::Act<F16>;
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t sbase = (tc::smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* sgen = smem_dyn + (sbase - tc::smem_u32(smem_dyn));
+    const uint32_t bar0 = sbase + SR_OFF_BAR;
+    auto full = [&](int b) { return bar0 + 8u * b; };                       // loaders -> MMA        (96 arrivals)
+    auto done = [&](int b) { return bar0 + 8u * (2 + b); };                 // MMA -> loaders        (tcgen05.commit)
+    const uint32_t e_full = bar0 + 8u * 4, e_empty = bar0 + 8u * 5, o_full = bar0 + 8u * 6, o_empty = bar0 + 8u * 7;
+    const uint32_t bar_w = bar0 + 8u * 8, tmem_slot = bar0 + 8u * 9;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    const int hp = height / 4, wp = width / 4, hc = height / 2;
+    const int nseg = wp / 128;
+    const int total = batch * nseg * hp;                                    // units, pooled row fastest
+    const int g0 = (int)((long long)total * blockIdx.x / gridDim.x), g1 = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
+
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) { tc::mbar_init(full(b), SR_LOADERS); tc::mbar_init(done(b), 1); }
+        tc::mbar_init(e_full, 1); tc::mbar_init(e_empty, 256);
+        tc::mbar_init(o_full, 1); tc::mbar_init(o_empty, 256);
+        tc::mbar_init(bar_w, 1);
+        tc::fence_barrier_init();
+        tc::mbar_arrive_expect_tx(bar_w, 8192);
+        tc::tma_load_2d(&tmW, bar_w, sbase, 0, 0);
+    }
+    if (warp == 3) tc::tmem_alloc<512>(tmem_slot);
+    float* bias_s = reinterpret_cast<float*>(sgen + SR_OFF_BAR + 256);
+    if (tid < ST_CO) bias_s[tid] = bias[tid];
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<const uint32_t*>(sgen + SR_OFF_BAR + 8 * 9);
+
+    if (warp < 3) {
+        // ===================== loaders =====================
+        // s2d rows [Y, Y + n) of image `img`, pooled columns [px0, px0 + 128): entry je covers image columns
+        // 4 px0 - 8 + 4 je .. + 5 of image rows 2Y, 2Y + 1 (zeros outside the image = the conv padding)
+        auto load_rows = [&](int img, int px0, int Y, int n) {
+            const float* xb = x + (size_t)img * height * width;
+            for (int t = tid; t < n * SR_ENT; t += SR_LOADERS) {
+                const int r = t / SR_ENT, je = t - r * SR_ENT;
+                const int Yr = Y + r;
+                unsigned char* dst = sgen + SR_OFF_ROWS + ((Yr + 8) & 7) * SR_ROW + je * 16;
+                uint4 p0 = make_uint4(0u, 0u, 0u, 0u), p1 = p0;
+                if (Yr >= 0 && Yr < hc) {
+                    const int c = 4 * px0 - 8 + 4 * je;
+                    const float* r0 = xb + (size_t)(2 * Yr) * width;
+                    const float* r1 = r0 + width;
+                    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+                    float2 f0 = make_float2(0.f, 0.f), f1 = f0;
+                    if (c >= 0 && c < width) {
+                        a0 = __ldg(reinterpret_cast<const float4*>(r0 + c));
+                        a1 = __ldg(reinterpret_cast<const float4*>(r1 + c));
+                    }
+                    if (c + 4 >= 0 && c + 4 < width) {
+                        f0 = __ldg(reinterpret_cast<const float2*>(r0 + c + 4));
+                        f1 = __ldg(reinterpret_cast<const float2*>(r1 + c + 4));
+                    }
+                    const uint32_t A0 = A16::pack(a0.x, a0.y), A1 = A16::pack(a1.x, a1.y);      // pixel c / 2
+                    const uint32_t B0 = A16::pack(a0.z, a0.w), B1 = A16::pack(a1.z, a1.w);      // pixel c / 2 + 1
+                    const uint32_t C0 = A16::pack(f0.x, f0.y), C1 = A16::pack(f1.x, f1.y);      // pixel c / 2 + 2
+                    p0 = make_uint4(A0, A1, B0, B1);
+                    p1 = make_uint4(B0, B1, C0, C1);
+                }
+                *reinterpret_cast<uint4*>(dst) = p0;
+                *reinterpret_cast<uint4*>(dst + SR_ARR) = p1;
+            }
+        };
+        int j = 0;                                                           // job counter (PRE and FULL jobs)
+        auto wait_done = [&](int job) { if (job >= 0) tc::mbar_wait(done(job & 1), (uint32_t)((job >> 1) & 1)); };
+        for (int g = g0; g < g1; ++g) {
+            const int is = g / hp, py = g - is * hp;
+            const int img = is / nseg, px0 = (is - img * nseg) * 128;
+            if (g == g0 && py > 0) {
+                // PRE job: the odd conv row above this CTA's first pooled row (its max is the first carry)
+                load_rows(img, px0, 2 * py - 3, 4);
+                tc::fence_proxy_async();
+                tc::mbar_arrive(full(j & 1));
+                ++j;
+            }
+            // a ring slot is rewritten two jobs after it was last read; a new image breaks the row sequence: drain
+            wait_done(j - 2);
+            if (py == 0) { wait_done(j - 1); load_rows(img, px0, -2, 3); }
+            load_rows(img, px0, 2 * py + 1, 2);
+            tc::fence_proxy_async();
+            tc::mbar_arrive(full(j & 1));
+            ++j;
+        }
+    } else if (warp == 3) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            tc::mbar_wait(bar_w, 0);
+            constexpr uint32_t idesc = tc::umma_idesc_16(128, ST_CO, A16::kFmt);
+            const uint32_t rows = sbase + SR_OFF_ROWS;
+            // one group = the three conv tiles (d = 0, -1, +1) of conv row cy into TMEM columns buf .. buf + 192
+            auto issue_group = [&](int cy, uint32_t buf) {
+#pragma unroll
+                for (int ti = 0; ti < 3; ++ti) {
+                    const uint32_t aoff = ti == 0 ? 16u : (ti == 1 ? (uint32_t)SR_ARR : (uint32_t)SR_ARR + 16u);
+#pragma unroll
+                    for (int dy = 0; dy < 4; ++dy) {
+                        const uint32_t a = rows + (uint32_t)(((cy - 2 + dy) + 8) & 7) * SR_ROW + aoff;
+                        tc::umma_bf16(tmem_base + buf + ti * ST_CO, stem_adesc(a), tc::umma_desc_sw128(sbase + dy * 32), idesc,
+                                      dy ? 1u : 0u);
+                    }
+                }
+            };
+            int j = 0;
+            uint32_t nE = 0, nO = 0;
+            for (int g = g0; g < g1; ++g) {
+                const int py = g % hp;
+                if (g == g0 && py > 0) {
+                    tc::mbar_wait(full(j & 1), (uint32_t)((j >> 1) & 1));
+                    tc::mbar_wait(o_empty, (nO & 1u) ^ 1u);
+                    tc::tc_fence_after();
+                    issue_group(2 * py - 1, SR_OBUF);
+                    tc::umma_commit(o_full); ++nO;
+                    tc::umma_commit(done(j & 1));
+                    ++j;
+                }
+                tc::mbar_wait(full(j & 1), (uint32_t)((j >> 1) & 1));
+                tc::mbar_wait(e_empty, (nE & 1u) ^ 1u);
+                tc::tc_fence_after();
+                issue_group(2 * py, SR_EBUF);
+                tc::umma_commit(e_full); ++nE;
+                tc::mbar_wait(o_empty, (nO & 1u) ^ 1u);
+                tc::tc_fence_after();
+                issue_group(2 * py + 1, SR_OBUF);
+                tc::umma_commit(o_full); ++nO;
+                tc::umma_commit(done(j & 1));
+                ++j;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue: max over the conv tiles, carry of the odd row, bias + ReLU, store =====================
+        const int q = warp & 3, hsel = (warp - 4) >> 2;                     // TMEM lane quarter, channel half
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const float NEG = -3.0e38f;
+        float carry[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) carry[i] = NEG;
+        // max over the three tiles of a group; the d = -1 tile of pooled column 0 is conv column -1: pool padding
+        auto group_max = [&](uint32_t buf, bool left_ok, float (&m)[32]) {
+            uint32_t r[32];
+            const uint32_t t0 = tmem_base + buf + hsel * 32 + lane_off;
+            tc::tmem_ld32(t0, r);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m[i] = __uint_as_float(r[i]);
+            tc::tmem_ld32(t0 + 2 * ST_CO, r);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m[i] = fmaxf(m[i], __uint_as_float(r[i]));
+            tc::tmem_ld32(t0 + ST_CO, r);
+            tc::tmem_ld_wait();
+            if (left_ok) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) m[i] = fmaxf(m[i], __uint_as_float(r[i]));
+            }
+        };
+        uint32_t nE = 0, nO = 0;
+        for (int g = g0; g < g1; ++g) {
+            const int is = g / hp, py = g - is * hp;
+            const int img = is / nseg, seg = is - img * nseg;
+            const int px = seg * 128 + q * 32 + lane;
+            const bool left_ok = px > 0;
+            if (py == 0) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) carry[i] = NEG;                // conv row -1: pool padding
+            }
+            if (g == g0 && py > 0) {
+                tc::mbar_wait(o_full, nO & 1u);
+                tc::tc_fence_after();
+                group_max(SR_OBUF, left_ok, carry);
+                tc::tc_fence_before();
+                tc::mbar_arrive(o_empty); ++nO;
+            }
+            float m[32], o[32];
+            tc::mbar_wait(e_full, nE & 1u);
+            tc::tc_fence_after();
+            group_max(SR_EBUF, left_ok, m);
+            tc::tc_fence_before();
+            tc::mbar_arrive(e_empty); ++nE;
+            tc::mbar_wait(o_full, nO & 1u);
+            tc::tc_fence_after();
+            group_max(SR_OBUF, left_ok, o);
+            tc::tc_fence_before();
+            tc::mbar_arrive(o_empty); ++nO;
+            uint32_t packed[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float v0 = fmaxf(fmaxf(fmaxf(m[2 * i], o[2 * i]), carry[2 * i]) + bias_s[hsel * 32 + 2 * i], 0.f);
+                const float v1 = fmaxf(fmaxf(fmaxf(m[2 * i + 1], o[2 * i + 1]), carry[2 * i + 1]) + bias_s[hsel * 32 + 2 * i + 1], 0.f);
+                packed[i] = A16::pack(v0, v1);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) carry[i] = o[i];
+            uint4* dst = reinterpret_cast<uint4*>(y + (((size_t)img * hp + py) * wp + px) * ST_CO + hsel * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 3) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Training variant: raw conv output z0 (B, H/2, W/2, 64) bf16 NHWC (BatchNorm needs batch statistics
 // before the ReLU / pool), plus the im2col operand itself, col0 (B, H/2, W/2, 64) bf16, so that the stem's
 // weight gradient is a plain pixel-contraction GEMM (wgrad.cu kind 4) with no second im2col pass.
@@ -390,6 +645,16 @@ static int stem_fwd_impl(const float* x, const void* weight, const float* bias, 
     CUtensorMap tmW;
     int rc = make_w_map(&tmW, weight, 64, 64, 64, F16);
     if (rc) return rc;
+    // SCD_STEM_IMPL: 1 (default) = row kernel (operand read in place, pool in registers), 0 = the round-1 tile kernel
+    static const int impl = [] { const char* e = getenv("SCD_STEM_IMPL"); return e ? atoi(e) : 1; }();
+    if (impl == 1 && width % 512 == 0) {
+        SCD_SMEM_ATTR(stem_row_kernel<F16>, SR_SMEM);
+        const int units = batch * (width / 512) * (height / 4);
+        stem_row_kernel<F16><<<units < kNumSMs ? units : kNumSMs, SR_THREADS, SR_SMEM, (cudaStream_t)stream>>>(
+            tmW, x, bias, batch, height, width, reinterpret_cast<__nv_bfloat16*>(y));
+        SCD_LAUNCH_CHECK("stem_row_kernel");
+        return SCD_OK;
+    }
     SCD_SMEM_ATTR(stem_pipe_kernel<F16>, SP_SMEM);
     const int total = (height / 4 / ST_P) * (width / 4 / ST_P) * batch;
     stem_pipe_kernel<F16><<<total < 2 * kNumSMs ? total : 2 * kNumSMs, SP_THREADS, SP_SMEM, (cudaStream_t)stream>>>(

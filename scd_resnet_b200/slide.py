@@ -29,9 +29,11 @@ def merge_detections(planes, height, width, threshold=0.3):
     Returns an (n, 3) float64 array of [x, y, ratio] rows in the reference's order."""
     clip_h, clip_v, _, _, pad_tb, pad_lr = ops.slide_geometry(height, width)
     step = INPUTSIZE - 2 * PADDINGSIZE
-    p = planes.double().numpy() if isinstance(planes, torch.Tensor) else np.asarray(planes, np.float64)
+    p32 = planes.float().numpy() if isinstance(planes, torch.Tensor) else np.asarray(planes, np.float32)
+    p = p32.astype(np.float64)
     sc, cy, cx, minl, rad, offx, offy = p[0], p[2], p[3], p[6], p[7], p[8], p[9]
-    t_idx, k_idx = np.nonzero(sc > threshold)                  # row-major: tile order, then rank inside the tile
+    # the reference compares the float32 scores with the Python scalar in float32 (`ctScores[item] > 0.3`, test.py:104)
+    t_idx, k_idx = np.nonzero(p32[0] > np.float32(threshold))   # row-major: tile order, then rank inside the tile
     tx, ty = t_idx // clip_v, t_idx % clip_v                   # x-major then y (test.py:114-116)
     dminl = minl[t_idx, k_idx] * 4
     halo = rad[t_idx, k_idx] * 4

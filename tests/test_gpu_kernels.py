@@ -327,6 +327,51 @@ def test_stem(S, plan):
     assert torch.equal(y == 0, t == 0) or ((y == 0) != (t == 0)).float().mean() < 1e-3
 
 
+@pytest.mark.parametrize("shape", [(1, 256, 1024), (3, 768, 512), (5, 64, 512), (1, 512, 1536)])
+def test_stem_shapes(S, shape):
+    """Row kernel geometry: several 128-pixel segments per row, heights that are not 512, CTA ranges that start in the
+    middle of an image (the carried odd conv row is recomputed), image borders in both directions."""
+    b, h, w = shape
+    sd = O.make_state_dict(1234)
+    fmt, wdt = S.weights.precision_spec("fp16")
+    f = S.weights.fold(sd, wdt)
+    rng = np.random.default_rng(h + w)
+    x = torch.from_numpy(rng.standard_normal((b, 1, h, w)).astype(np.float32))
+    y = S.ops.stem_fwd(dev(x), dev(f["stem_w"]), dev(f["stem_b"])).float().cpu().permute(0, 3, 1, 2)
+    t = F.conv2d(x, sd["preprocess.0.weight"], None, stride=2, padding=3)
+    t = F.relu(F.batch_norm(t, sd["preprocess.1.running_mean"], sd["preprocess.1.running_var"],
+                            sd["preprocess.1.weight"], sd["preprocess.1.bias"], False, 0.1, 1e-5))
+    t = F.max_pool2d(t, 3, 2, 1)
+    assert y.shape == t.shape
+    assert relmax(y, t) < 2e-3
+    # borders separately: first / last pooled row and column
+    for sl in (np.s_[:, :, 0], np.s_[:, :, -1], np.s_[:, :, :, 0], np.s_[:, :, :, -1]):
+        assert relmax(y[sl], t[sl]) < 2e-3
+
+
+def test_stem_row_kernel_equals_tile_kernel(S):
+    """The round-1 tile kernel (SCD_STEM_IMPL=0, hand-built im2col) and the row kernel (operand read in place) compute
+    the same sums of the same products: outputs agree to the last bit or to one rounding of the 16-bit store."""
+    import subprocess, sys, os
+    code = ("import torch, numpy as np, scd_resnet_b200 as S\n"
+            "from oracle import centernet_cpu as O\n"
+            "sd = O.make_state_dict(1234); f = S.weights.fold(sd, torch.bfloat16)\n"
+            "x = O.make_tiles(2, seed=3).cuda()\n"
+            "y = S.ops.stem_fwd(x, f['stem_w'].cuda(), f['stem_b'].cuda())\n"
+            "torch.save(y.cpu(), '%s')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for impl in ("0", "1"):
+        path = "/tmp/scd_stem_impl%s.pt" % impl
+        env = dict(os.environ, SCD_STEM_IMPL=impl)
+        r = subprocess.run([sys.executable, "-c", code % path], cwd=root, env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(torch.load(path).float())
+    d = (outs[0] - outs[1]).abs()
+    assert (d <= 2.0 ** -7 * outs[0].abs() + 1e-6).all()          # one bf16 ulp: the accumulation order inside the MMA differs
+    assert (d > 0).float().mean() < 0.05
+
+
 # ------------------------------------------------------------------------------ implicit GEMM convs
 def _bf16(t):
     return t.to(torch.bfloat16).float()
@@ -444,7 +489,7 @@ def test_infer_vs_oracle(S, golden, seed):
     assert S.weights.DEFAULT_PRECISION == "mixed"
     fmt, wdt = S.weights.precision_spec(S.weights.DEFAULT_PRECISION)
     sd = O.make_state_dict(seed)
-    x = O.make_tiles(2, seed=seed % 5)
+    x = O.make_tiles(2, seed=0 if seed == 1234 else 4)
     blob = S.weights.pack_infer_blob(sd, "cuda", wdt)
     heat, regr, off, _ = S.ops.resnet10_infer(dev(x), blob, fmt=fmt)
     with torch.no_grad():
