@@ -88,6 +88,20 @@ slide_tiles_kernel(const T* __restrict__ gray, int height, int width, SlideGeom 
     }
     const double sd = sqrt(block_sum_f64(ss, sh) / n);         // sqrt(mean(square(t - mean)))
     float* out = tiles + (size_t)blockIdx.x * SL_TILE * SL_TILE;
+    if (sizeof(T) == 1) {
+        // grey bytes take 256 values: the fp64 subtract / divide / round-to-fp32 runs once per VALUE (a table in
+        // shared memory), not once per pixel: same bits, and the pass stops being bound by fp64 division
+        __shared__ float lut[256];
+        if (tid < 256) lut[tid] = (float)(((double)tid - mean) / sd);
+        __syncthreads();
+        for (int r = rbase; r < SL_TILE; r += SL_THREADS / 128) {
+            const T* row = gray + (size_t)reflect(oy + r, height) * pitch;
+            float4 o;
+            o.x = lut[(int)row[sx[0]]]; o.y = lut[(int)row[sx[1]]]; o.z = lut[(int)row[sx[2]]]; o.w = lut[(int)row[sx[3]]];
+            reinterpret_cast<float4*>(out + (size_t)r * SL_TILE)[tid & 127] = o;
+        }
+        return;
+    }
     for (int r = rbase; r < SL_TILE; r += SL_THREADS / 128) {
         const T* row = gray + (size_t)reflect(oy + r, height) * pitch;
         float4 o;
@@ -164,11 +178,13 @@ tiles_normalize_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ t
         ss += a * a; ss += b * b; ss += c * c; ss += d * d;
     }
     const double sd = sqrt(block_sum_f64(ss, sh) / n);
+    __shared__ float lut[256];                                 // one fp64 divide per grey VALUE, not per pixel (same bits)
+    if (threadIdx.x < 256) lut[threadIdx.x] = (float)(((double)threadIdx.x - mean) / sd);
+    __syncthreads();
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
         float4 o;
-        o.x = (float)(((double)v[k].x - mean) / sd); o.y = (float)(((double)v[k].y - mean) / sd);
-        o.z = (float)(((double)v[k].z - mean) / sd); o.w = (float)(((double)v[k].w - mean) / sd);
+        o.x = lut[v[k].x]; o.y = lut[v[k].y]; o.z = lut[v[k].z]; o.w = lut[v[k].w];
         out[threadIdx.x + k * SL_THREADS] = o;
     }
 }

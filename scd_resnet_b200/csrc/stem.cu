@@ -277,7 +277,8 @@ constexpr int SR_LOADERS = 96;
 constexpr int SR_ENT = 132;                                // 16 B entries per array: pooled px 0..127 use entries 0..129
 constexpr int SR_ARR = SR_ENT * 16;
 constexpr int SR_ROW = 2 * SR_ARR;                         // P0 | P1 of one s2d row
-constexpr int SR_SLOTS = 8;                                // ring of s2d rows, slot = (Y + 8) & 7
+constexpr int SR_SLOTS = 16;                               // ring of s2d rows, slot = (Y + 16) & 15: the loaders run up to
+constexpr int SR_AHEAD = 6;                                //   six jobs ahead of the tensor core (global latency hidden)
 constexpr int SR_OFF_ROWS = 8192;                          // behind the 64 x 64 weight tile
 constexpr int SR_OFF_BAR = SR_OFF_ROWS + SR_SLOTS * SR_ROW;
 constexpr int SR_SMEM = SR_OFF_BAR + 256 + 256 + 1024;     // barriers | bias | align slack
@@ -298,10 +299,10 @@ stem_row_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict
     const uint32_t sbase = (tc::smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* sgen = smem_dyn + (sbase - tc::smem_u32(smem_dyn));
     const uint32_t bar0 = sbase + SR_OFF_BAR;
-    auto full = [&](int b) { return bar0 + 8u * b; };                       // loaders -> MMA        (96 arrivals)
-    auto done = [&](int b) { return bar0 + 8u * (2 + b); };                 // MMA -> loaders        (tcgen05.commit)
-    const uint32_t e_full = bar0 + 8u * 4, e_empty = bar0 + 8u * 5, o_full = bar0 + 8u * 6, o_empty = bar0 + 8u * 7;
-    const uint32_t bar_w = bar0 + 8u * 8, tmem_slot = bar0 + 8u * 9;
+    auto full = [&](int j) { return bar0 + 8u * (j & 7); };                 // loaders -> MMA, job j (96 arrivals)
+    auto done = [&](int j) { return bar0 + 8u * (8 + (j & 7)); };           // MMA -> loaders, job j (tcgen05.commit)
+    const uint32_t e_full = bar0 + 8u * 16, e_empty = bar0 + 8u * 17, o_full = bar0 + 8u * 18, o_empty = bar0 + 8u * 19;
+    const uint32_t bar_w = bar0 + 8u * 20, tmem_slot = bar0 + 8u * 21;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     const int hp = height / 4, wp = width / 4, hc = height / 2;
@@ -310,7 +311,7 @@ stem_row_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict
     const int g0 = (int)((long long)total * blockIdx.x / gridDim.x), g1 = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
 
     if (tid == 0) {
-        for (int b = 0; b < 2; ++b) { tc::mbar_init(full(b), SR_LOADERS); tc::mbar_init(done(b), 1); }
+        for (int b = 0; b < 8; ++b) { tc::mbar_init(full(b), SR_LOADERS); tc::mbar_init(done(b), 1); }
         tc::mbar_init(e_full, 1); tc::mbar_init(e_empty, 256);
         tc::mbar_init(o_full, 1); tc::mbar_init(o_empty, 256);
         tc::mbar_init(bar_w, 1);
@@ -324,7 +325,7 @@ stem_row_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<const uint32_t*>(sgen + SR_OFF_BAR + 8 * 9);
+    const uint32_t tmem_base = *reinterpret_cast<const uint32_t*>(sgen + SR_OFF_BAR + 8 * 21);
 
     if (warp < 3) {
         // ===================== loaders =====================
@@ -332,37 +333,47 @@ stem_row_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict
         // 4 px0 - 8 + 4 je .. + 5 of image rows 2Y, 2Y + 1 (zeros outside the image = the conv padding)
         auto load_rows = [&](int img, int px0, int Y, int n) {
             const float* xb = x + (size_t)img * height * width;
-            for (int t = tid; t < n * SR_ENT; t += SR_LOADERS) {
-                const int r = t / SR_ENT, je = t - r * SR_ENT;
-                const int Yr = Y + r;
-                unsigned char* dst = sgen + SR_OFF_ROWS + ((Yr + 8) & 7) * SR_ROW + je * 16;
-                uint4 p0 = make_uint4(0u, 0u, 0u, 0u), p1 = p0;
-                if (Yr >= 0 && Yr < hc) {
-                    const int c = 4 * px0 - 8 + 4 * je;
-                    const float* r0 = xb + (size_t)(2 * Yr) * width;
-                    const float* r1 = r0 + width;
-                    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-                    float2 f0 = make_float2(0.f, 0.f), f1 = f0;
-                    if (c >= 0 && c < width) {
-                        a0 = __ldg(reinterpret_cast<const float4*>(r0 + c));
-                        a1 = __ldg(reinterpret_cast<const float4*>(r1 + c));
+            // two rows per pass; a thread owns entries tid and tid + 96 of both: all global loads of the pass are issued
+            // before the first conversion (one exposed latency per pass instead of one per entry)
+            for (int rr = 0; rr < n; rr += 2) {
+                float4 a0[4], a1[4];
+                float2 f0[4], f1[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = rr + (u >> 1), je = tid + (u & 1) * SR_LOADERS;
+                    const int Yr = Y + r;
+                    a0[u] = make_float4(0.f, 0.f, 0.f, 0.f); a1[u] = a0[u];
+                    f0[u] = make_float2(0.f, 0.f); f1[u] = f0[u];
+                    if (r < n && je < SR_ENT && Yr >= 0 && Yr < hc) {
+                        const int c = 4 * px0 - 8 + 4 * je;
+                        const float* r0 = xb + (size_t)(2 * Yr) * width;
+                        const float* r1 = r0 + width;
+                        if (c >= 0 && c < width) {
+                            a0[u] = __ldg(reinterpret_cast<const float4*>(r0 + c));
+                            a1[u] = __ldg(reinterpret_cast<const float4*>(r1 + c));
+                        }
+                        if (c + 4 >= 0 && c + 4 < width) {
+                            f0[u] = __ldg(reinterpret_cast<const float2*>(r0 + c + 4));
+                            f1[u] = __ldg(reinterpret_cast<const float2*>(r1 + c + 4));
+                        }
                     }
-                    if (c + 4 >= 0 && c + 4 < width) {
-                        f0 = __ldg(reinterpret_cast<const float2*>(r0 + c + 4));
-                        f1 = __ldg(reinterpret_cast<const float2*>(r1 + c + 4));
-                    }
-                    const uint32_t A0 = A16::pack(a0.x, a0.y), A1 = A16::pack(a1.x, a1.y);      // pixel c / 2
-                    const uint32_t B0 = A16::pack(a0.z, a0.w), B1 = A16::pack(a1.z, a1.w);      // pixel c / 2 + 1
-                    const uint32_t C0 = A16::pack(f0.x, f0.y), C1 = A16::pack(f1.x, f1.y);      // pixel c / 2 + 2
-                    p0 = make_uint4(A0, A1, B0, B1);
-                    p1 = make_uint4(B0, B1, C0, C1);
                 }
-                *reinterpret_cast<uint4*>(dst) = p0;
-                *reinterpret_cast<uint4*>(dst + SR_ARR) = p1;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = rr + (u >> 1), je = tid + (u & 1) * SR_LOADERS;
+                    if (r < n && je < SR_ENT) {
+                        unsigned char* dst = sgen + SR_OFF_ROWS + ((Y + r + SR_SLOTS) & (SR_SLOTS - 1)) * SR_ROW + je * 16;
+                        const uint32_t A0 = A16::pack(a0[u].x, a0[u].y), A1 = A16::pack(a1[u].x, a1[u].y);      // pixel c / 2
+                        const uint32_t B0 = A16::pack(a0[u].z, a0[u].w), B1 = A16::pack(a1[u].z, a1[u].w);      // pixel c / 2 + 1
+                        const uint32_t C0 = A16::pack(f0[u].x, f0[u].y), C1 = A16::pack(f1[u].x, f1[u].y);      // pixel c / 2 + 2
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(A0, A1, B0, B1);
+                        *reinterpret_cast<uint4*>(dst + SR_ARR) = make_uint4(B0, B1, C0, C1);
+                    }
+                }
             }
         };
         int j = 0;                                                           // job counter (PRE and FULL jobs)
-        auto wait_done = [&](int job) { if (job >= 0) tc::mbar_wait(done(job & 1), (uint32_t)((job >> 1) & 1)); };
+        auto wait_done = [&](int job) { if (job >= 0) tc::mbar_wait(done(job), (uint32_t)((job >> 3) & 1)); };
         for (int g = g0; g < g1; ++g) {
             const int is = g / hp, py = g - is * hp;
             const int img = is / nseg, px0 = (is - img * nseg) * 128;
@@ -370,15 +381,16 @@ stem_row_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict
                 // PRE job: the odd conv row above this CTA's first pooled row (its max is the first carry)
                 load_rows(img, px0, 2 * py - 3, 4);
                 tc::fence_proxy_async();
-                tc::mbar_arrive(full(j & 1));
+                tc::mbar_arrive(full(j));
                 ++j;
             }
-            // a ring slot is rewritten two jobs after it was last read; a new image breaks the row sequence: drain
-            wait_done(j - 2);
+            // ring of 16 rows: the two rows of job j alias rows last read by job j - 6; a new image breaks the row
+            // sequence: drain
+            wait_done(j - SR_AHEAD);
             if (py == 0) { wait_done(j - 1); load_rows(img, px0, -2, 3); }
             load_rows(img, px0, 2 * py + 1, 2);
             tc::fence_proxy_async();
-            tc::mbar_arrive(full(j & 1));
+            tc::mbar_arrive(full(j));
             ++j;
         }
     } else if (warp == 3) {
@@ -394,7 +406,7 @@ stem_row_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict
                     const uint32_t aoff = ti == 0 ? 16u : (ti == 1 ? (uint32_t)SR_ARR : (uint32_t)SR_ARR + 16u);
 #pragma unroll
                     for (int dy = 0; dy < 4; ++dy) {
-                        const uint32_t a = rows + (uint32_t)(((cy - 2 + dy) + 8) & 7) * SR_ROW + aoff;
+                        const uint32_t a = rows + (uint32_t)(((cy - 2 + dy) + SR_SLOTS) & (SR_SLOTS - 1)) * SR_ROW + aoff;
                         tc::umma_bf16(tmem_base + buf + ti * ST_CO, stem_adesc(a), tc::umma_desc_sw128(sbase + dy * 32), idesc,
                                       dy ? 1u : 0u);
                     }
@@ -405,15 +417,15 @@ stem_row_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict
             for (int g = g0; g < g1; ++g) {
                 const int py = g % hp;
                 if (g == g0 && py > 0) {
-                    tc::mbar_wait(full(j & 1), (uint32_t)((j >> 1) & 1));
+                    tc::mbar_wait(full(j), (uint32_t)((j >> 3) & 1));
                     tc::mbar_wait(o_empty, (nO & 1u) ^ 1u);
                     tc::tc_fence_after();
                     issue_group(2 * py - 1, SR_OBUF);
                     tc::umma_commit(o_full); ++nO;
-                    tc::umma_commit(done(j & 1));
+                    tc::umma_commit(done(j));
                     ++j;
                 }
-                tc::mbar_wait(full(j & 1), (uint32_t)((j >> 1) & 1));
+                tc::mbar_wait(full(j), (uint32_t)((j >> 3) & 1));
                 tc::mbar_wait(e_empty, (nE & 1u) ^ 1u);
                 tc::tc_fence_after();
                 issue_group(2 * py, SR_EBUF);
@@ -422,7 +434,7 @@ stem_row_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict
                 tc::tc_fence_after();
                 issue_group(2 * py + 1, SR_OBUF);
                 tc::umma_commit(o_full); ++nO;
-                tc::umma_commit(done(j & 1));
+                tc::umma_commit(done(j));
                 ++j;
             }
         }

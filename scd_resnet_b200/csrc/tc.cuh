@@ -158,8 +158,11 @@ template <> struct Act<false> {
 template <> struct Act<true> {
     static constexpr uint32_t kFmt = 0u;
     __device__ static __forceinline__ uint32_t pack(float a, float b) {
-        const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
-        return *reinterpret_cast<const uint32_t*>(&h);
+        // one F2FP.SATFINITE: round to nearest even, +-inf / overflow -> +-65504 (the explicit fminf / fmaxf pair it
+        // replaces made the fp16 instantiations 3 % slower than bf16)
+        uint32_t r;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+        return r;
     }
     __device__ static __forceinline__ float lo(uint32_t u) { return __low2float(*reinterpret_cast<const __half2*>(&u)); }
     __device__ static __forceinline__ float hi(uint32_t u) { return __high2float(*reinterpret_cast<const __half2*>(&u)); }

@@ -6,7 +6,7 @@ from scd_resnet_b200 import ops, synthetic, weights
 from oracle import centernet_cpu as O
 
 sd = O.make_state_dict(1234)
-f = weights.fold(sd)
+f = weights.fold(sd, weights.precision_spec(weights.DEFAULT_PRECISION)[1])      # the timed plan: fp16 containers
 x = synthetic.make_tiles(64, seed=0).cuda()
 w, b = f["stem_w"].cuda(), f["stem_b"].cuda()
 for _ in range(3):
