@@ -284,6 +284,21 @@ int scd_heads_fwd_fmt(int fmt, const void* x, const void* w3, const float* b3, c
  *                    all-reduce: dgamma / dbeta are local sums like torch.nn.SyncBatchNorm's, to be averaged over
  *                    ranks with the other parameter gradients (DDP, models/networkFactory.py:133-134). */
 int scd_bn_stats(const void* z, size_t pixels, int C, double* sums, void* stream);
+/* Fused forms (one launch where the calls above take three or four): the LAST CTA of the reduction, which sees every
+ * partial sum, (i) keeps a copy of this rank's sums [backward: the source of dgamma / dbeta], (ii) exchanges the sums
+ * with the other ranks through the peer buffers of scd_peer_allreduce_f64 (d_peer_buffers == NULL or world <= 1: no
+ * exchange; same seq / timeout / status contract) = SyncBatchNorm without a collective launch, and (iii) [forward] does
+ * what scd_bn_finalize does.  sums_ws: 2C doubles + one 8-byte counter cell (cleared by the call).  `count` = elements
+ * per channel over all ranks. */
+int scd_bn_stats_finalize(const void* z, size_t pixels, int C, double* sums_ws, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, long long* num_batches, double count,
+                          float momentum, float eps, float* scale, float* shift, float* mean, float* invstd,
+                          void* const* d_peer_buffers, int rank, int world, int cap, unsigned int seq,
+                          long long timeout_cycles, int* status, void* stream);
+int scd_bn_bwd_reduce(const void* da, const void* a, const void* z, const float* scale, const float* shift,
+                      const float* mean, const float* invstd, size_t pixels, int C, double* sums_ws,
+                      double* local_sums, void* const* d_peer_buffers, int rank, int world, int cap,
+                      unsigned int seq, long long timeout_cycles, int* status, void* stream);
 int scd_bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean,
                     float* running_var, long long* num_batches, int C, double count, float momentum,
                     float eps, float* scale, float* shift, float* mean, float* invstd, void* stream);

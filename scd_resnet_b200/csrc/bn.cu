@@ -11,11 +11,32 @@
 //   bn_apply      z, scale, shift, res?  -> a = [relu](z*scale + shift [+ res])     (bf16)
 //   bn_bwd_reduce da, a?, z              -> sum(dy), sum(dy * xhat)                 (fp64), dy = da * (a > 0)
 //   bn_bwd_apply  da, a?, z, sums        -> dz = scale*(dy - mean(dy) - xhat*mean(dy*xhat)) (bf16) [, dy]
-#include "common.cuh"
+#include "peer.cuh"
 
 namespace scd {
 
 constexpr int BN_THREADS = 256;
+
+// What the LAST CTA of a reduction does once every CTA's partial sums are in `sums` (no extra launch between the
+// reduction and its consumer): keep a copy of this rank's sums (the source of d gamma / d beta in the backward pass),
+// exchange the sums with the other ranks over NVLink peer memory (= SyncBatchNorm), and, in the forward pass, turn them
+// into the normalisation coefficients and move the running statistics (= the old bn_finalize launch).
+struct BnTail {
+    unsigned* counter;               // CTAs finished so far; lives behind the sums and is cleared with them; null: no tail
+    double* local_copy;              // nullable
+    PeerArgs peer;
+    const float* gamma;              // null: no finalize (backward reduction)
+    const float* beta;
+    float* running_mean;
+    float* running_var;
+    long long* num_batches;
+    double count;                    // elements per channel over ALL ranks
+    float momentum, eps;
+    float* scale;
+    float* shift;
+    float* mean_out;
+    float* invstd_out;
+};
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -44,7 +65,7 @@ __global__ void __launch_bounds__(384, 3)
 bn_reduce_kernel(const uint4* __restrict__ z, const uint4* __restrict__ da, const uint4* __restrict__ a,
                  const float* __restrict__ mean, const float* __restrict__ invstd,
                  const float* __restrict__ scale, const float* __restrict__ shift,    // ReLU mask from z when a == NULL
-                 size_t pixels, int cgroups, double* __restrict__ sums /* [2][C] */)
+                 size_t pixels, int cgroups, double* __restrict__ sums /* [2][C] */, const BnTail tail)
 {
     extern __shared__ float red[];                       // [2][blockDim.x][8]
     const int g = threadIdx.x % cgroups;                 // channel group of 8
@@ -97,6 +118,38 @@ bn_reduce_kernel(const uint4* __restrict__ z, const uint4* __restrict__ da, cons
         double t = 0.0;
         for (int l = 0; l < lanes; ++l) t += (double)base[(size_t)(l * cgroups + ch / 8) * 8 + (ch & 7)];
         atomicAdd(sums + which * C + ch, t);
+    }
+    if (tail.counter == nullptr) return;
+    // ---- tail: the last CTA to get here sees every partial sum (atomics are performed at L2; fence + counter order them)
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(tail.counter, 1u) == gridDim.x - 1u) ? 1 : 0;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (tail.local_copy)
+        for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) tail.local_copy[c] = __ldcg(sums + c);
+    if (tail.peer.world > 1 && tail.peer.peers != nullptr) {
+        if (!peer_allreduce_block(sums, 2 * C, tail.peer)) return;
+    }
+    if (tail.gamma == nullptr) return;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        if (c == 0 && tail.num_batches) *tail.num_batches += 1;
+        const double m = __ldcg(sums + c) / tail.count;
+        double var = __ldcg(sums + C + c) / tail.count - m * m;      // biased (what normalises the batch)
+        if (var < 0.0) var = 0.0;
+        const float inv = (float)(1.0 / sqrt(var + (double)tail.eps));
+        const float sc = tail.gamma[c] * inv;
+        tail.scale[c] = sc;
+        tail.shift[c] = tail.beta[c] - (float)m * sc;
+        tail.mean_out[c] = (float)m;
+        tail.invstd_out[c] = inv;
+        if (tail.running_mean) {
+            const double unbiased = tail.count > 1.0 ? var * tail.count / (tail.count - 1.0) : var;
+            tail.running_mean[c] = (1.f - tail.momentum) * tail.running_mean[c] + tail.momentum * (float)m;
+            tail.running_var[c] = (1.f - tail.momentum) * tail.running_var[c] + tail.momentum * (float)unbiased;
+        }
     }
 }
 
@@ -242,8 +295,76 @@ extern "C" int scd_bn_stats(const void* z, size_t pixels, int C, double* sums, v
     const int lanes = block / (C / 8);
     const int grid = stream_grid(pixels, lanes * 16);
     bn_reduce_kernel<0><<<grid, block, (size_t)2 * block * 8 * sizeof(float), (cudaStream_t)stream>>>(
-        static_cast<const uint4*>(z), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, pixels, C / 8, sums);
+        static_cast<const uint4*>(z), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, pixels, C / 8, sums, BnTail{});
     SCD_LAUNCH_CHECK("bn_reduce_kernel<0>");
+    return SCD_OK;
+}
+
+static int peer_args(scd::PeerArgs& pa, void* const* d_peer_buffers, int rank, int world, int cap, unsigned seq,
+                     long long timeout_cycles, int* status, int n, const char* who)
+{
+    pa = scd::PeerArgs{nullptr, 0, 1, 0, 0u, 0, nullptr};
+    if (!d_peer_buffers || world <= 1) return SCD_OK;
+    if (world > 64 || rank < 0 || rank >= world) return scd::fail(SCD_EINVAL, "%s: bad rank / world", who);
+    if (n > cap) return scd::fail(SCD_EINVAL, "%s: %d statistics exceed the peer slot capacity %d", who, n, cap);
+    if (seq == 0u) return scd::fail(SCD_EINVAL, "%s: seq starts at 1", who);
+    pa = scd::PeerArgs{reinterpret_cast<unsigned char* const*>(d_peer_buffers), rank, world, cap, seq, timeout_cycles, status};
+    return SCD_OK;
+}
+
+// bn_stats + (peer exchange) + bn_finalize in ONE launch.  sums_ws: 2C doubles followed by one 8-byte counter cell.
+extern "C" int scd_bn_stats_finalize(const void* z, size_t pixels, int C, double* sums_ws, const float* gamma,
+                                     const float* beta, float* running_mean, float* running_var, long long* num_batches,
+                                     double count, float momentum, float eps, float* scale, float* shift, float* mean,
+                                     float* invstd, void* const* d_peer_buffers, int rank, int world, int cap,
+                                     unsigned seq, long long timeout_cycles, int* status, void* stream)
+{
+    using namespace scd;
+    if (!z || !sums_ws || !gamma || !beta || !scale || !shift || !mean || !invstd || C % 8)
+        return fail(SCD_EINVAL, "scd_bn_stats_finalize: bad arguments");
+    const int block = reduce_block(C);
+    if (!block) return fail(SCD_EINVAL, "scd_bn_stats_finalize: unsupported channel count %d", C);
+    BnTail t = {};
+    int rc = peer_args(t.peer, d_peer_buffers, rank, world, cap, seq, timeout_cycles, status, 2 * C, "scd_bn_stats_finalize");
+    if (rc) return rc;
+    t.counter = reinterpret_cast<unsigned*>(sums_ws + 2 * C);
+    t.gamma = gamma; t.beta = beta; t.running_mean = running_mean; t.running_var = running_var; t.num_batches = num_batches;
+    t.count = count; t.momentum = momentum; t.eps = eps; t.scale = scale; t.shift = shift; t.mean_out = mean; t.invstd_out = invstd;
+    SCD_CUDA_CHECK(cudaMemsetAsync(sums_ws, 0, sizeof(double) * (2 * C + 1), (cudaStream_t)stream));
+    const int lanes = block / (C / 8);
+    bn_reduce_kernel<0><<<stream_grid(pixels, lanes * 16), block, (size_t)2 * block * 8 * sizeof(float), (cudaStream_t)stream>>>(
+        static_cast<const uint4*>(z), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, pixels, C / 8, sums_ws, t);
+    SCD_LAUNCH_CHECK("bn_reduce_kernel<0> (+finalize)");
+    return SCD_OK;
+}
+
+// Backward reduction (phase 0 of scd_bn_bwd) + copy of the local sums + (peer exchange) in ONE launch.
+extern "C" int scd_bn_bwd_reduce(const void* da, const void* a, const void* z, const float* scale, const float* shift,
+                                 const float* mean, const float* invstd, size_t pixels, int C, double* sums_ws,
+                                 double* local_sums, void* const* d_peer_buffers, int rank, int world, int cap,
+                                 unsigned seq, long long timeout_cycles, int* status, void* stream)
+{
+    using namespace scd;
+    if (!da || !z || !scale || !mean || !invstd || !sums_ws || C % 8) return fail(SCD_EINVAL, "scd_bn_bwd_reduce: bad arguments");
+    const int block = reduce_block(C);
+    if (!block) return fail(SCD_EINVAL, "scd_bn_bwd_reduce: unsupported channel count %d", C);
+    BnTail t = {};
+    int rc = peer_args(t.peer, d_peer_buffers, rank, world, cap, seq, timeout_cycles, status, 2 * C, "scd_bn_bwd_reduce");
+    if (rc) return rc;
+    t.counter = reinterpret_cast<unsigned*>(sums_ws + 2 * C);
+    t.local_copy = local_sums;
+    cudaStream_t st = (cudaStream_t)stream;
+    SCD_CUDA_CHECK(cudaMemsetAsync(sums_ws, 0, sizeof(double) * (2 * C + 1), st));
+    const int lanes = block / (C / 8);
+    const size_t smem = (size_t)2 * block * 8 * sizeof(float);
+    if (a == nullptr && shift != nullptr)
+        bn_reduce_kernel<2><<<stream_grid(pixels, lanes * 16), block, smem, st>>>(
+            static_cast<const uint4*>(z), static_cast<const uint4*>(da), nullptr, mean, invstd, scale, shift, pixels, C / 8, sums_ws, t);
+    else
+        bn_reduce_kernel<1><<<stream_grid(pixels, lanes * 16), block, smem, st>>>(
+            static_cast<const uint4*>(z), static_cast<const uint4*>(da), static_cast<const uint4*>(a), mean, invstd, scale, shift,
+            pixels, C / 8, sums_ws, t);
+    SCD_LAUNCH_CHECK("bn_reduce_kernel (backward, + exchange)");
     return SCD_OK;
 }
 
@@ -292,11 +413,11 @@ extern "C" int scd_bn_bwd(const void* da, const void* a, const void* z, const fl
         if (a == nullptr && shift != nullptr)
             bn_reduce_kernel<2><<<stream_grid(pixels, lanes * 16), block, (size_t)2 * block * 8 * sizeof(float), st>>>(
                 static_cast<const uint4*>(z), static_cast<const uint4*>(da), nullptr, mean, invstd, scale, shift, pixels,
-                C / 8, sums);
+                C / 8, sums, BnTail{});
         else
             bn_reduce_kernel<1><<<stream_grid(pixels, lanes * 16), block, (size_t)2 * block * 8 * sizeof(float), st>>>(
                 static_cast<const uint4*>(z), static_cast<const uint4*>(da), static_cast<const uint4*>(a), mean, invstd,
-                scale, shift, pixels, C / 8, sums);
+                scale, shift, pixels, C / 8, sums, BnTail{});
         SCD_LAUNCH_CHECK("bn_reduce_kernel<1>");
     } else {
         if (!dz) return fail(SCD_EINVAL, "scd_bn_bwd: dz is null");

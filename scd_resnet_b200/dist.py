@@ -127,6 +127,14 @@ class PeerAllReduce:
                         "scd_peer_allreduce_f64")
         return vec
 
+    def next_args(self):
+        """(peers, rank, world, cap, seq, timeout, status) for a kernel that runs the exchange itself (the BatchNorm
+        reductions, csrc/bn.cu); advances the sequence number exactly like a call would."""
+        c = self._ctypes
+        self.seq += 1
+        return (c.c_void_p(self.peers.data_ptr()), self.rank, self.world, self.cap, self.seq & 0xFFFFFFFF or 1,
+                self.timeout_cycles, c.c_void_p(self.status.data_ptr()))
+
     def check(self):
         """Raise if an earlier call gave up waiting for a peer (a host read of a pinned word: no synchronisation)."""
         st = int(self.status[0])

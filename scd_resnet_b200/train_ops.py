@@ -9,24 +9,35 @@ from .ops import _ptr, _stream, _req
 BN_EPS, BN_MOMENTUM = 1e-5, 0.1     # ref: torch BatchNorm2d default eps; models/backbones/residuals.py:30
 
 
+_NO_PEER = (None, 0, 1, 0, 0, 0, None)
+
+
 def bn_forward(z, gamma, beta, running_mean=None, running_var=None, num_batches=None, residual=None, relu=True,
-               out=None, all_reduce=None):
+               out=None, all_reduce=None, peer=None, world=1):
     """Train-mode BN (+residual)(+ReLU) on z (B,H,W,C) bf16 NHWC.  Returns (a, ctx); ctx is what the backward
-    needs.  `all_reduce(t)` (optional) sums the fp64 statistics across ranks = SyncBatchNorm."""
+    needs.  Statistics shared over `world` ranks (= SyncBatchNorm): `peer` (dist.PeerAllReduce) runs the exchange inside
+    the statistics kernel (2 launches per BatchNorm: statistics + exchange + finalize, apply); without it
+    `all_reduce(sums, pixels) -> count` (NCCL) sits between separate statistics / finalize launches."""
     z = _req(z, torch.bfloat16, "z")
     C = z.shape[-1]
     pixels = z.numel() // C
     dev = z.device
-    sums = torch.empty(2 * C, dtype=torch.float64, device=dev)
+    sums = torch.empty(2 * C + 1, dtype=torch.float64, device=dev)      # + the counter cell of the fused kernels
     stat = torch.empty(4, C, dtype=torch.float32, device=dev)          # scale, shift, mean, invstd
     with torch.cuda.device(dev):
-        check(lib.scd_bn_stats(_ptr(z), pixels, C, _ptr(sums), _stream()), "scd_bn_stats")
-        count = float(pixels)
-        if all_reduce is not None:
-            count = all_reduce(sums, pixels)
-        check(lib.scd_bn_finalize(_ptr(sums), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
-                                  _ptr(num_batches), C, count, BN_MOMENTUM, BN_EPS, _ptr(stat[0]), _ptr(stat[1]),
-                                  _ptr(stat[2]), _ptr(stat[3]), _stream()), "scd_bn_finalize")
+        if world == 1 or peer is not None:
+            count = float(pixels) * world
+            pa = peer.next_args() if (peer is not None and world > 1) else _NO_PEER
+            check(lib.scd_bn_stats_finalize(_ptr(z), pixels, C, _ptr(sums), _ptr(gamma), _ptr(beta), _ptr(running_mean),
+                                            _ptr(running_var), _ptr(num_batches), count, BN_MOMENTUM, BN_EPS, _ptr(stat[0]),
+                                            _ptr(stat[1]), _ptr(stat[2]), _ptr(stat[3]), *pa, _stream()),
+                  "scd_bn_stats_finalize")
+        else:
+            check(lib.scd_bn_stats(_ptr(z), pixels, C, _ptr(sums), _stream()), "scd_bn_stats")
+            count = all_reduce(sums[:2 * C], pixels)
+            check(lib.scd_bn_finalize(_ptr(sums), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
+                                      _ptr(num_batches), C, count, BN_MOMENTUM, BN_EPS, _ptr(stat[0]), _ptr(stat[1]),
+                                      _ptr(stat[2]), _ptr(stat[3]), _stream()), "scd_bn_finalize")
         if out is None:
             out = torch.empty_like(z)
         check(lib.scd_bn_apply(_ptr(z), _ptr(stat[0]), _ptr(stat[1]), _ptr(residual), int(relu), pixels, C, _ptr(out),
@@ -34,9 +45,12 @@ def bn_forward(z, gamma, beta, running_mean=None, running_var=None, num_batches=
     return out, {"stat": stat, "count": count, "sums": sums}
 
 
-def bn_backward(da, a, z, ctx, want_dy=False, dgamma=None, dbeta=None, all_reduce=None, relu_from_z=False):
+def bn_backward(da, a, z, ctx, want_dy=False, dgamma=None, dbeta=None, all_reduce=None, relu_from_z=False, peer=None,
+                world=1):
     """Backward of bn_forward.  a = the post-ReLU output (ReLU mask) or None; relu_from_z: there was a ReLU and no
-    residual, so the mask is recomputed from z instead of reading a.  Returns (dz, dy or None)."""
+    residual, so the mask is recomputed from z instead of reading a.  Returns (dz, dy or None).
+    d gamma / d beta are THIS rank's sums (torch.nn.SyncBatchNorm semantics; the gradient all-reduce averages them like
+    every other parameter gradient): a copy from before the exchange feeds them."""
     C = z.shape[-1]
     pixels = z.numel() // C
     dev = z.device
@@ -47,16 +61,24 @@ def bn_backward(da, a, z, ctx, want_dy=False, dgamma=None, dbeta=None, all_reduc
     with torch.cuda.device(dev):
         if relu_from_z:
             a = None
-        args = (_ptr(da), _ptr(a), _ptr(z), _ptr(stat[0]), _ptr(stat[1] if relu_from_z else None), _ptr(stat[2]),
-                _ptr(stat[3]), pixels, C, count, _ptr(sums))
-        check(lib.scd_bn_bwd(*args, None, None, None, None, None, 0, _stream()), "scd_bn_bwd(reduce)")
+        shift = stat[1] if relu_from_z else None
         local = None
-        if all_reduce is not None:
-            # d gamma / d beta are THIS rank's sums (torch.nn.SyncBatchNorm semantics; the gradient all-reduce averages
-            # them like every other parameter gradient): keep a copy from before the exchange (a D2D memcpy of 2C doubles)
-            local = torch.empty_like(sums)
-            local.copy_(sums)
-            all_reduce(sums, None)
+        if world == 1 or peer is not None:
+            pa = _NO_PEER
+            if peer is not None and world > 1:
+                pa = peer.next_args()
+                local = torch.empty(2 * C, dtype=torch.float64, device=dev)
+            check(lib.scd_bn_bwd_reduce(_ptr(da), _ptr(a), _ptr(z), _ptr(stat[0]), _ptr(shift), _ptr(stat[2]), _ptr(stat[3]),
+                                        pixels, C, _ptr(sums), _ptr(local), *pa, _stream()), "scd_bn_bwd_reduce")
+        else:
+            args0 = (_ptr(da), _ptr(a), _ptr(z), _ptr(stat[0]), _ptr(shift), _ptr(stat[2]), _ptr(stat[3]), pixels, C, count,
+                     _ptr(sums))
+            check(lib.scd_bn_bwd(*args0, None, None, None, None, None, 0, _stream()), "scd_bn_bwd(reduce)")
+            local = torch.empty(2 * C, dtype=torch.float64, device=dev)
+            local.copy_(sums[:2 * C])
+            all_reduce(sums[:2 * C], None)
+        args = (_ptr(da), _ptr(a), _ptr(z), _ptr(stat[0]), _ptr(shift), _ptr(stat[2]), _ptr(stat[3]), pixels, C, count,
+                _ptr(sums))
         check(lib.scd_bn_bwd(*args, _ptr(dz), _ptr(dy), _ptr(dgamma), _ptr(dbeta), _ptr(local), 1, _stream()),
               "scd_bn_bwd(apply)")
     return dz, dy

@@ -301,23 +301,26 @@ class TrainEngine:
 
     # ------------------------------------------------------------------ SyncBatchNorm hooks
     def _allreduce_stats(self, sums, pixels):
+        """NCCL route of the statistics exchange (used when peer memory is unavailable; with it, the exchange runs inside
+        the BatchNorm reduction kernels, csrc/bn.cu)."""
         if self.stat_world == 1:
             return float(pixels) if pixels is not None else None
-        if self.peer is not None:
-            self.peer(sums)                                # one-shot NVLink peer-memory reduction (csrc/peer.cu)
-        else:
-            torch.distributed.all_reduce(sums, group=self.stat_group)
+        torch.distributed.all_reduce(sums, group=self.stat_group)
         return float(pixels) * self.stat_world if pixels is not None else None
+
+    def _sync_kw(self):
+        return {"all_reduce": self._allreduce_stats if (self.stat_world > 1 and self.peer is None) else None,
+                "peer": self.peer, "world": self.stat_world}
 
     # ------------------------------------------------------------------ forward + backward
     def _bn(self, z, prefix, residual=None, relu=True):
         m = self.module.get_submodule(prefix)
         return T.bn_forward(z, m.weight.data, m.bias.data, m.running_mean, m.running_var, m.num_batches_tracked,
-                            residual, relu, all_reduce=self._allreduce_stats if self.stat_world > 1 else None)
+                            residual, relu, **self._sync_kw())
 
     def _bn_bwd(self, da, a, z, ctx, prefix, want_dy=False, relu_from_z=False):
         return T.bn_backward(da, a, z, ctx, want_dy, self.g(prefix + ".weight"), self.g(prefix + ".bias"),
-                             all_reduce=self._allreduce_stats if self.stat_world > 1 else None, relu_from_z=relu_from_z)
+                             relu_from_z=relu_from_z, **self._sync_kw())
 
     def _conv(self, kind, x, key, cout):
         return ops.conv_igemm_fwd(kind, x, self.wb(key + ":fwd"), self.zero_bias[:cout], None, False)
@@ -411,8 +414,7 @@ class TrainEngine:
                 self._reduce_async(self.g_off["layer3.0.conv1.weight"], self._reduced_from)
         dy0 = T.stem_pool_bwd(tape["argmax0"], da)
         dz0, _ = T.bn_backward(dy0, None, tape["z0"], tape["ctx0"], False, self.g("preprocess.1.weight"),
-                               self.g("preprocess.1.bias"),
-                               all_reduce=self._allreduce_stats if self.stat_world > 1 else None)
+                               self.g("preprocess.1.bias"), **self._sync_kw())
         T.conv_wgrad(4, tape["col0"], dz0, 64, 64, self.g("preprocess.0.weight"))
 
     def forward_backward(self, x, targets, sigmoid_inplace=False):
@@ -433,15 +435,21 @@ class TrainEngine:
         """Batch statistics of the stem conv output; the normalisation itself is fused with ReLU + max-pool."""
         C = 64
         pixels = z0.numel() // C
-        sums = torch.empty(2 * C, dtype=torch.float64, device=self.dev)
+        sums = torch.empty(2 * C + 1, dtype=torch.float64, device=self.dev)
         stat = torch.empty(4, C, dtype=torch.float32, device=self.dev)
-        ops.check(ops.lib.scd_bn_stats(ops._ptr(z0), pixels, C, ops._ptr(sums), ops._stream()), "scd_bn_stats")
-        count = self._allreduce_stats(sums, pixels)
-        ops.check(ops.lib.scd_bn_finalize(ops._ptr(sums), ops._ptr(bn0.weight.data), ops._ptr(bn0.bias.data),
-                                          ops._ptr(bn0.running_mean), ops._ptr(bn0.running_var),
-                                          ops._ptr(bn0.num_batches_tracked), C, count, T.BN_MOMENTUM, T.BN_EPS,
-                                          ops._ptr(stat[0]), ops._ptr(stat[1]), ops._ptr(stat[2]), ops._ptr(stat[3]),
-                                          ops._stream()), "scd_bn_finalize")
+        outs = (ops._ptr(stat[0]), ops._ptr(stat[1]), ops._ptr(stat[2]), ops._ptr(stat[3]))
+        bnp = (ops._ptr(bn0.weight.data), ops._ptr(bn0.bias.data), ops._ptr(bn0.running_mean), ops._ptr(bn0.running_var),
+               ops._ptr(bn0.num_batches_tracked))
+        if self.stat_world == 1 or self.peer is not None:
+            count = float(pixels) * self.stat_world
+            pa = self.peer.next_args() if (self.peer is not None and self.stat_world > 1) else T._NO_PEER
+            ops.check(ops.lib.scd_bn_stats_finalize(ops._ptr(z0), pixels, C, ops._ptr(sums), *bnp, count, T.BN_MOMENTUM,
+                                                    T.BN_EPS, *outs, *pa, ops._stream()), "scd_bn_stats_finalize")
+        else:
+            ops.check(ops.lib.scd_bn_stats(ops._ptr(z0), pixels, C, ops._ptr(sums), ops._stream()), "scd_bn_stats")
+            count = self._allreduce_stats(sums[:2 * C], pixels)
+            ops.check(ops.lib.scd_bn_finalize(ops._ptr(sums), *bnp, C, count, T.BN_MOMENTUM, T.BN_EPS, *outs, ops._stream()),
+                      "scd_bn_finalize")
         return None, {"stat": stat, "count": count, "sums": sums}
 
     # ------------------------------------------------------------------ optimiser
