@@ -269,11 +269,12 @@ stem_pipe_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restric
 //     max is carried in registers to the next pooled row, leaving six tiles = 24 MMAs (N = 64) per 128 pooled pixels.
 //     bias + ReLU commute with the max and run once per pooled value.
 //   * CTA = 3 loader warps (fp32 rows -> 16-bit entries, two new s2d rows per pooled row into a ring of sixteen), one MMA
-//     warp, sixteen epilogue warps (TMEM lane quarter x 16-channel quarter: the epilogue is the instruction-bound role); the even-row and odd-row tile groups use two
+//     warp, eight epilogue warps (TMEM lane quarter x channel half: the epilogue is the instruction-bound role); the even-row and odd-row tile groups use two
 //     192-column TMEM buffers, so the tensor core runs one group ahead of the epilogue.  One CTA per SM, each walks a
 //     contiguous range of (image, pooled row) units.
-constexpr int SR_THREADS = 640;                            // 3 loader warps, 1 MMA warp, 16 epilogue warps (96 registers each)
-constexpr int SR_EPI = 512;                                // epilogue threads: TMEM lane quarter x 16-channel quarter
+constexpr int SR_THREADS = 384;                            // 3 loader warps, 1 MMA warp, 8 epilogue warps (12 warps: 168 registers)
+constexpr int SR_EPI = 256;                                // epilogue threads: TMEM lane quarter x channel half
+                                                           // (16 warps of 16 channels at 96 registers measured SLOWER: 0.146 vs 0.124 ms)
 constexpr int SR_LOADERS = 96;
 constexpr int SR_ENT = 132;                                // 16 B entries per array: pooled px 0..127 use entries 0..129
 constexpr int SR_ARR = SR_ENT * 16;
@@ -442,24 +443,26 @@ stem_row_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict
         __syncwarp();
     } else {
         // ===================== epilogue: max over the conv tiles, carry of the odd row, bias + ReLU, store =====================
-        const int q = warp & 3, cq = (warp - 4) >> 2;                       // TMEM lane quarter, 16-channel quarter
+        const int q = warp & 3, hsel = (warp - 4) >> 2;                     // TMEM lane quarter, channel half
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         const float NEG = -3.0e38f;
-        float carry[16];
+        float carry[32];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) carry[i] = NEG;
+        for (int i = 0; i < 32; ++i) carry[i] = NEG;
         // m <- max(m, the three tiles of a group); the d = -1 tile of pooled column 0 is conv column -1: pool padding
-        auto group_max = [&](uint32_t buf, bool left_ok, float (&m)[16]) {
-            uint32_t r0[16], r1[16], r2[16];
-            const uint32_t t0 = tmem_base + buf + cq * 16 + lane_off;
-            tc::tmem_ld16(t0, r0);
-            tc::tmem_ld16(t0 + 2 * ST_CO, r2);
-            tc::tmem_ld16(t0 + ST_CO, r1);
+        auto group_max = [&](uint32_t buf, bool left_ok, float (&m)[32]) {
+            uint32_t r0[32], r2[32];
+            const uint32_t t0 = tmem_base + buf + hsel * 32 + lane_off;
+            tc::tmem_ld32(t0, r0);
+            tc::tmem_ld32(t0 + 2 * ST_CO, r2);
             tc::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float l = left_ok ? __uint_as_float(r1[i]) : NEG;
-                m[i] = fmaxf(fmaxf(m[i], __uint_as_float(r0[i])), fmaxf(__uint_as_float(r2[i]), l));
+            for (int i = 0; i < 32; ++i) m[i] = fmaxf(fmaxf(m[i], __uint_as_float(r0[i])), __uint_as_float(r2[i]));     // FMNMX3
+            tc::tmem_ld32(t0 + ST_CO, r0);
+            tc::tmem_ld_wait();
+            if (left_ok) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) m[i] = fmaxf(m[i], __uint_as_float(r0[i]));
             }
         };
         uint32_t nE = 0, nO = 0;
@@ -470,7 +473,7 @@ stem_row_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict
             const bool left_ok = px > 0;
             if (py == 0) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) carry[i] = NEG;                // conv row -1: pool padding
+                for (int i = 0; i < 32; ++i) carry[i] = NEG;                // conv row -1: pool padding
             }
             if (g == g0 && py > 0) {
                 tc::mbar_wait(o_full, nO & 1u);
@@ -479,34 +482,34 @@ stem_row_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict
                 tc::tc_fence_before();
                 tc::mbar_arrive(o_empty); ++nO;
             }
-            float m[16], o[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) m[i] = carry[i];
+            // `carry` holds the odd conv row above; the even row's tiles are folded into it, then the odd row below
+            // becomes both the third operand and the next unit's carry
             tc::mbar_wait(e_full, nE & 1u);
             tc::tc_fence_after();
-            group_max(SR_EBUF, left_ok, m);                                  // even conv row (and the carried odd row above)
+            group_max(SR_EBUF, left_ok, carry);
             tc::tc_fence_before();
             tc::mbar_arrive(e_empty); ++nE;
+            float o[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = NEG;
             tc::mbar_wait(o_full, nO & 1u);
             tc::tc_fence_after();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = NEG;
-            group_max(SR_OBUF, left_ok, o);                                  // odd conv row below: also the next unit's carry
+            group_max(SR_OBUF, left_ok, o);
             tc::tc_fence_before();
             tc::mbar_arrive(o_empty); ++nO;
-            uint32_t packed[8];
-            const float4* bq = reinterpret_cast<const float4*>(bias_s + cq * 16);
+            uint32_t packed[16];
+            const float4* bq = reinterpret_cast<const float4*>(bias_s + hsel * 32);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 8; ++i) {
                 const float4 b4 = bq[i];
-                packed[2 * i] = A16::pack_relu(fmaxf(m[4 * i], o[4 * i]) + b4.x, fmaxf(m[4 * i + 1], o[4 * i + 1]) + b4.y);
-                packed[2 * i + 1] = A16::pack_relu(fmaxf(m[4 * i + 2], o[4 * i + 2]) + b4.z, fmaxf(m[4 * i + 3], o[4 * i + 3]) + b4.w);
+                packed[2 * i] = A16::pack_relu(fmaxf(carry[4 * i], o[4 * i]) + b4.x, fmaxf(carry[4 * i + 1], o[4 * i + 1]) + b4.y);
+                packed[2 * i + 1] = A16::pack_relu(fmaxf(carry[4 * i + 2], o[4 * i + 2]) + b4.z, fmaxf(carry[4 * i + 3], o[4 * i + 3]) + b4.w);
             }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) carry[i] = o[i];
-            uint4* dst = reinterpret_cast<uint4*>(y + (((size_t)img * hp + py) * wp + px) * ST_CO + cq * 16);
-            dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            for (int i = 0; i < 32; ++i) carry[i] = o[i];
+            uint4* dst = reinterpret_cast<uint4*>(y + (((size_t)img * hp + py) * wp + px) * ST_CO + hsel * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
             if (++py == hp) { py = 0; ++is; }
         }
     }

@@ -10,6 +10,7 @@ BN_EPS, BN_MOMENTUM = 1e-5, 0.1     # ref: torch BatchNorm2d default eps; models
 
 
 _NO_PEER = (None, 0, 1, 0, 0, 0, None)
+_BN_FUSED = __import__("os").environ.get("SCD_BN_FUSED", "1") != "0"      # 0: separate statistics / finalize launches (A/B)
 
 
 def bn_forward(z, gamma, beta, running_mean=None, running_var=None, num_batches=None, residual=None, relu=True,
@@ -25,7 +26,7 @@ def bn_forward(z, gamma, beta, running_mean=None, running_var=None, num_batches=
     sums = torch.empty(2 * C + 1, dtype=torch.float64, device=dev)      # + the counter cell of the fused kernels
     stat = torch.empty(4, C, dtype=torch.float32, device=dev)          # scale, shift, mean, invstd
     with torch.cuda.device(dev):
-        if world == 1 or peer is not None:
+        if _BN_FUSED and (world == 1 or peer is not None):
             count = float(pixels) * world
             pa = peer.next_args() if (peer is not None and world > 1) else _NO_PEER
             check(lib.scd_bn_stats_finalize(_ptr(z), pixels, C, _ptr(sums), _ptr(gamma), _ptr(beta), _ptr(running_mean),
@@ -34,7 +35,9 @@ def bn_forward(z, gamma, beta, running_mean=None, running_var=None, num_batches=
                   "scd_bn_stats_finalize")
         else:
             check(lib.scd_bn_stats(_ptr(z), pixels, C, _ptr(sums), _stream()), "scd_bn_stats")
-            count = all_reduce(sums[:2 * C], pixels)
+            count = float(pixels)
+            if world > 1:
+                count = all_reduce(sums[:2 * C], pixels) if all_reduce is not None else (peer(sums[:2 * C]), float(pixels) * world)[1]
             check(lib.scd_bn_finalize(_ptr(sums), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
                                       _ptr(num_batches), C, count, BN_MOMENTUM, BN_EPS, _ptr(stat[0]), _ptr(stat[1]),
                                       _ptr(stat[2]), _ptr(stat[3]), _stream()), "scd_bn_finalize")
@@ -63,7 +66,7 @@ def bn_backward(da, a, z, ctx, want_dy=False, dgamma=None, dbeta=None, all_reduc
             a = None
         shift = stat[1] if relu_from_z else None
         local = None
-        if world == 1 or peer is not None:
+        if _BN_FUSED and (world == 1 or peer is not None):
             pa = _NO_PEER
             if peer is not None and world > 1:
                 pa = peer.next_args()
@@ -74,9 +77,13 @@ def bn_backward(da, a, z, ctx, want_dy=False, dgamma=None, dbeta=None, all_reduc
             args0 = (_ptr(da), _ptr(a), _ptr(z), _ptr(stat[0]), _ptr(shift), _ptr(stat[2]), _ptr(stat[3]), pixels, C, count,
                      _ptr(sums))
             check(lib.scd_bn_bwd(*args0, None, None, None, None, None, 0, _stream()), "scd_bn_bwd(reduce)")
-            local = torch.empty(2 * C, dtype=torch.float64, device=dev)
-            local.copy_(sums[:2 * C])
-            all_reduce(sums[:2 * C], None)
+            if world > 1:
+                local = torch.empty(2 * C, dtype=torch.float64, device=dev)
+                local.copy_(sums[:2 * C])
+                if all_reduce is not None:
+                    all_reduce(sums[:2 * C], None)
+                else:
+                    peer(sums[:2 * C])
         args = (_ptr(da), _ptr(a), _ptr(z), _ptr(stat[0]), _ptr(shift), _ptr(stat[2]), _ptr(stat[3]), pixels, C, count,
                 _ptr(sums))
         check(lib.scd_bn_bwd(*args, _ptr(dz), _ptr(dy), _ptr(dgamma), _ptr(dbeta), _ptr(local), 1, _stream()),
