@@ -416,6 +416,14 @@ int scd_augment_batch(const float* samples, const float* locs, const int32_t* co
                       const int64_t* index, const uint8_t* flips, const float* jitter, const float* noise,
                       int batch, float noise_sv, float jitter_sv,
                       float* tiles, float* out_locs, int32_t* out_counts, void* stream);
+/* The same with the random draws made inside the kernel: Philox4x32-10 keyed by `seed`, counter = (output position,
+ * sample, `offset`; advance offset by one per call) gives the flip decisions (numpy.random.uniform() > 0.5,
+ * scdx16p100.py:424,431), the jitter Gaussian (argumentations.py:64) and the noise field (:57) by Box-Muller.  No RNG
+ * kernels and no noise tensor in HBM: 2 MB per sample.  draws_out (B,3) f32, nullable: [flip x, flip y, jitter draw]. */
+int scd_augment_batch_philox(const float* samples, const float* locs, const int32_t* counts, int n_samples,
+                             const int64_t* index, int batch, float noise_sv, float jitter_sv,
+                             unsigned long long seed, unsigned long long offset, float* tiles, float* out_locs,
+                             int32_t* out_counts, float* draws_out, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Detection metrics of the validation loop.  Replaces centerNetEvaluation

@@ -81,6 +81,8 @@ PROTOTYPES = {
     "scd_gather_f32": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "scd_scale_inplace": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "scd_augment_batch": (c_int, [c_void_p] * 3 + [c_int] + [c_void_p] * 4 + [c_int, c_float, c_float] + [c_void_p] * 3 + [c_void_p]),
+    "scd_augment_batch_philox": (c_int, [c_void_p] * 3 + [c_int, c_void_p, c_int, c_float, c_float, ctypes.c_ulonglong,
+                                          ctypes.c_ulonglong] + [c_void_p] * 4 + [c_void_p]),
     "scd_centernet_eval_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "scd_centernet_eval": (c_int, [c_void_p] * 8 + [c_int] * 4 + [c_float] + [c_void_p] * 3 + [c_void_p, c_size_t, c_void_p]),
     "scd_slide_geometry": (c_int, [c_int, c_int, c_void_p]),

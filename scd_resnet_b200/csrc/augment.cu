@@ -48,6 +48,28 @@ __device__ __forceinline__ double au_cluster_sum(double v, double* slots, unsign
     return t;
 }
 
+// Philox4x32-10 (Salmon et al., SC'11; the generator behind torch.randn on CUDA): counter-based, so every output element
+// draws its noise from (seed, call offset, sample, position) with no state and no noise tensor in HBM.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float u01(unsigned x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }   // (0, 1)
+// four N(0,1) values from four 32-bit words (Box-Muller, two pairs)
+__device__ __forceinline__ float4 normal4(uint4 r) {
+    const float r0 = sqrtf(-2.f * __logf(u01(r.x))), r1 = sqrtf(-2.f * __logf(u01(r.z)));
+    float s0, c0, s1, c1;
+    __sincosf(6.283185307179586f * u01(r.y), &s0, &c0);
+    __sincosf(6.283185307179586f * u01(r.w), &s1, &c1);
+    return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+}
+
 // samples (N,512,512) f32, locs (N,30,8) f32, counts (N) i32: the resident dataset.  index (B) i64: the samples of
 // this batch.  flips (B,2) u8: [flip x (dim 2), flip y (dim 1)].  jitter (B) f32: the N(0,1) draw of varianceJitter.
 // noise (B,512,512) f32 N(0,1) draws (nullable: no noise).  -> tiles (B,1,512,512) f32, out_locs (B,30,8), out_counts (B).
@@ -55,11 +77,15 @@ __device__ __forceinline__ double au_cluster_sum(double v, double* slots, unsign
 // One cluster of 8 CTAs per sample.  Each CTA keeps its 64 source rows (128 KB) in REGISTERS, 8 float4 per thread, so
 // the tile is read from HBM exactly once; the two statistics (mean, then the variance about that mean, as the
 // reference computes them) are reduced over the cluster through distributed shared memory.
+// PHILOX: flips, jitter and noise are drawn inside the kernel from (seed, offset) instead of being read (flips / jitter /
+// noise pointers unused); draws_out (B,3) f32, nullable, receives [flip x, flip y, jitter draw] of every sample.
+template <bool PHILOX>
 __global__ void __cluster_dims__(AU_CL, 1, 1) __launch_bounds__(AU_THREADS)
 augment_kernel(const float* __restrict__ samples, const float* __restrict__ locs, const int32_t* __restrict__ counts,
                const int64_t* __restrict__ index, const uint8_t* __restrict__ flips, const float* __restrict__ jitter,
                const float* __restrict__ noise, float noise_sv, float jitter_sv, int n_samples,
-               float* __restrict__ tiles, float* __restrict__ out_locs, int32_t* __restrict__ out_counts)
+               float* __restrict__ tiles, float* __restrict__ out_locs, int32_t* __restrict__ out_counts,
+               unsigned long long seed, unsigned long long offset, float* __restrict__ draws_out)
 {
     __shared__ double sh[AU_THREADS / 32];
     __shared__ double slots[2][AU_CL];
@@ -71,7 +97,21 @@ augment_kernel(const float* __restrict__ samples, const float* __restrict__ locs
         return;
     }
     const size_t src_i = (size_t)raw_i;
-    const bool fx = flips[2 * b] != 0, fy = flips[2 * b + 1] != 0;
+    bool fx, fy;
+    float jit;
+    const uint2 pkey = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+    if (PHILOX) {
+        // per-sample draws: counter word 0 = 0xFFFFFFFF is never a pixel position
+        const uint4 r = philox4x32_10(make_uint4(0xFFFFFFFFu, (unsigned)b, (unsigned)offset, (unsigned)(offset >> 32)), pkey);
+        fx = u01(r.x) > 0.5f; fy = u01(r.y) > 0.5f;            // numpy.random.uniform() > 0.5, scdx16p100.py:424,431
+        jit = normal4(r).z;                                   // torch.randn(1), argumentations.py:64
+        if (draws_out != nullptr && rank == 0 && tid == 0) {
+            draws_out[3 * b] = fx ? 1.f : 0.f; draws_out[3 * b + 1] = fy ? 1.f : 0.f; draws_out[3 * b + 2] = jit;
+        }
+    } else {
+        fx = flips[2 * b] != 0; fy = flips[2 * b + 1] != 0;
+        jit = jitter[b];
+    }
     constexpr int N4 = AU_S * AU_S / 4;
     const int base = rank * (N4 / AU_CL);                    // this CTA's float4 range of the SOURCE tile
     const float4* src = reinterpret_cast<const float4*>(samples + src_i * AU_S * AU_S) + base;
@@ -114,7 +154,7 @@ augment_kernel(const float* __restrict__ samples, const float* __restrict__ locs
     const double q_tile = au_cluster_sum(au_block_sum(q, sh), slots[1], rank);
     const float var = (float)(q_tile / (double)(AU_S * AU_S));                         // mean(square(t - mean))
     const float sd = sqrtf(var);
-    const float scale = 1.f + jitter_sv * jitter[b];                                  // varianceJitter
+    const float scale = 1.f + jitter_sv * jit;                                        // varianceJitter
     float4* dst = reinterpret_cast<float4*>(tiles + (size_t)b * AU_S * AU_S);
     const float4* nz = noise ? reinterpret_cast<const float4*>(noise + (size_t)b * AU_S * AU_S) : nullptr;
 #pragma unroll
@@ -126,7 +166,8 @@ augment_kernel(const float* __restrict__ samples, const float* __restrict__ locs
             const int sp = base + (h + k) * AU_THREADS + tid;
             const int y = sp / (AU_S / 4), x4 = sp % (AU_S / 4);
             di[k] = (fy ? AU_S - 1 - y : y) * (AU_S / 4) + (fx ? AU_S / 4 - 1 - x4 : x4);
-            if (nz) g[k] = ld_stream(nz + di[k]);
+            if (PHILOX) g[k] = normal4(philox4x32_10(make_uint4((unsigned)di[k], (unsigned)b, (unsigned)offset, (unsigned)(offset >> 32)), pkey));
+            else if (nz) g[k] = ld_stream(nz + di[k]);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -137,7 +178,7 @@ augment_kernel(const float* __restrict__ samples, const float* __restrict__ locs
             o.y = __fmul_rn(__fdiv_rn(x.y - mean, sd), scale);
             o.z = __fmul_rn(__fdiv_rn(x.z - mean, sd), scale);
             o.w = __fmul_rn(__fdiv_rn(x.w - mean, sd), scale);
-            if (nz) {
+            if (PHILOX || nz) {
                 o.x = __fadd_rn(o.x, __fmul_rn(g[k].x, noise_sv)); o.y = __fadd_rn(o.y, __fmul_rn(g[k].y, noise_sv));
                 o.z = __fadd_rn(o.z, __fmul_rn(g[k].z, noise_sv)); o.w = __fadd_rn(o.w, __fmul_rn(g[k].w, noise_sv));
             }
@@ -158,8 +199,30 @@ extern "C" int scd_augment_batch(const float* samples, const float* locs, const 
     if (!samples || !locs || !counts || !index || !flips || !jitter || !tiles || !out_locs || !out_counts)
         return fail(SCD_EINVAL, "scd_augment_batch: null pointer");
     if (n_samples <= 0) return fail(SCD_EINVAL, "scd_augment_batch: empty dataset");
-    augment_kernel<<<batch * AU_CL, AU_THREADS, 0, (cudaStream_t)stream>>>(samples, locs, counts, index, flips, jitter, noise,
-                                                                    noise_sv, jitter_sv, n_samples, tiles, out_locs, out_counts);
+    augment_kernel<false><<<batch * AU_CL, AU_THREADS, 0, (cudaStream_t)stream>>>(samples, locs, counts, index, flips, jitter, noise,
+                                                                           noise_sv, jitter_sv, n_samples, tiles, out_locs,
+                                                                           out_counts, 0ull, 0ull, nullptr);
     SCD_LAUNCH_CHECK("augment_kernel");
+    return SCD_OK;
+}
+
+// The same with the random draws made INSIDE the kernel (Philox4x32-10 keyed by `seed`, counter = (position, sample,
+// `offset`)): flip decisions (p = 0.5 each), the jitter Gaussian and the noise field.  No RNG kernels, no noise tensor:
+// 2 MB per sample instead of 3 (+1 to write the noise).  Advance `offset` by one per call.  draws_out (B,3) f32, nullable:
+// [flip x, flip y, jitter draw] per sample (for logging / replay).
+extern "C" int scd_augment_batch_philox(const float* samples, const float* locs, const int32_t* counts, int n_samples,
+                                        const int64_t* index, int batch, float noise_sv, float jitter_sv,
+                                        unsigned long long seed, unsigned long long offset, float* tiles, float* out_locs,
+                                        int32_t* out_counts, float* draws_out, void* stream)
+{
+    using namespace scd;
+    if (batch <= 0) return SCD_OK;
+    if (!samples || !locs || !counts || !index || !tiles || !out_locs || !out_counts)
+        return fail(SCD_EINVAL, "scd_augment_batch_philox: null pointer");
+    if (n_samples <= 0) return fail(SCD_EINVAL, "scd_augment_batch_philox: empty dataset");
+    augment_kernel<true><<<batch * AU_CL, AU_THREADS, 0, (cudaStream_t)stream>>>(samples, locs, counts, index, nullptr, nullptr,
+                                                                          nullptr, noise_sv, jitter_sv, n_samples, tiles,
+                                                                          out_locs, out_counts, seed, offset, draws_out);
+    SCD_LAUNCH_CHECK("augment_kernel<philox>");
     return SCD_OK;
 }

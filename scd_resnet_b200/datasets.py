@@ -68,7 +68,7 @@ class DeviceSCD:
         self.batch, self.noise_sv, self.jitter_sv = batch, noise_sv, jitter_sv
         self.rank, self.world = rank, world
         self.gen = torch.Generator(device=self.device).manual_seed(seed)          # permutations: same stream on every rank
-        self.aug_gen = torch.Generator(device=self.device).manual_seed(seed * 1000003 + 7919 * rank + 1)   # draws: per rank
+        self.aug_seed, self.aug_calls = seed * 1000003 + 7919 * rank + 1, 0                        # draws: per rank
         self.n = n
         held = torch.zeros(n, dtype=torch.bool)
         if validation is not None:
@@ -99,12 +99,10 @@ class DeviceSCD:
 
     def draw(self, index):
         """One augmented batch for the given sample ids (device i64 tensor)."""
-        b = index.shape[0]
-        flips = torch.rand(b, 2, device=self.device, generator=self.aug_gen) > 0.5
-        jitter = torch.randn(b, device=self.device, generator=self.aug_gen)
-        noise = torch.randn(b, 512, 512, device=self.device, generator=self.aug_gen)
-        tiles, locs, counts = ops.augment_batch(self.samples, self.locs, self.counts, index, flips, jitter, noise,
-                                                self.noise_sv, self.jitter_sv)
+        # flips, jitter and noise are drawn inside the augmentation kernel (Philox keyed per rank, one offset per batch)
+        self.aug_calls += 1
+        tiles, locs, counts = ops.augment_batch_philox(self.samples, self.locs, self.counts, index, self.aug_seed,
+                                                       self.aug_calls, self.noise_sv, self.jitter_sv)
         ys = ops.render_targets(locs, counts, with_npos=True)
         return {"xs": [tiles], "ys": list(ys)}
 

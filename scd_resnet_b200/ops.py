@@ -224,6 +224,30 @@ def augment_batch(samples, locs, counts, index, flips, jitter, noise=None, noise
     return tiles, out_locs, out_counts
 
 
+def augment_batch_philox(samples, locs, counts, index, seed, offset, noise_sv=0.05, jitter_sv=0.05, want_draws=False):
+    """augment_batch with the flips, the jitter Gaussian and the noise field drawn inside the kernel (Philox4x32-10 keyed
+    by `seed`, counter = (position, sample, `offset`)): no RNG kernels, no noise tensor.  Returns (tiles, out_locs,
+    out_counts[, draws (B,3) = flip x, flip y, jitter draw])."""
+    samples = _req(samples, torch.float32, "samples")
+    locs = _req(locs, torch.float32, "locs")
+    counts = _req(counts, torch.int32, "counts")
+    index = _req(index, torch.int64, "index")
+    n, b = samples.shape[0], index.shape[0]
+    if tuple(samples.shape[1:]) != (512, 512) or tuple(locs.shape) != (n, MAXTAGLEN, 8) or counts.shape[0] != n:
+        raise ScdError("augment_batch_philox: dataset tensors must be (N,512,512), (N,30,8), (N)")
+    dev = samples.device
+    tiles = torch.empty(b, 1, 512, 512, dtype=torch.float32, device=dev)
+    out_locs = torch.empty(b, MAXTAGLEN, 8, dtype=torch.float32, device=dev)
+    out_counts = torch.empty(b, dtype=torch.int32, device=dev)
+    draws = torch.empty(b, 3, dtype=torch.float32, device=dev) if want_draws else None
+    with torch.cuda.device(dev):
+        check(lib.scd_augment_batch_philox(_ptr(samples), _ptr(locs), _ptr(counts), n, _ptr(index), b, noise_sv, jitter_sv,
+                                           int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset) & 0xFFFFFFFFFFFFFFFF, _ptr(tiles),
+                                           _ptr(out_locs), _ptr(out_counts), _ptr(draws), _stream()),
+              "scd_augment_batch_philox")
+    return (tiles, out_locs, out_counts, draws) if want_draws else (tiles, out_locs, out_counts)
+
+
 def centernet_eval(scores, ys, xs, offset, regr, regr6, gt_idx, mask, threshold=0.3):
     """Pair metrics of centerNetEvaluation (ref: models/centerNetOffset.py:253-353) in one native call.
 

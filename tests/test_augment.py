@@ -97,3 +97,29 @@ def test_device_dataset_and_archive(tmp_path):
             assert abs(b["xs"][0].mean().item()) < 0.05                # normalised (+ noise, jitter)
         runs.append(torch.cat([b["xs"][0] for b in out]))
     assert torch.equal(runs[0], runs[1])                               # same seed, same batches
+
+
+@pytest.mark.gpu
+def test_augment_philox_draws():
+    """scd_augment_batch_philox: the draws made inside the kernel.  With the reported flips / jitter replayed through the
+    input-driven kernel (noise off) the difference IS the noise field: N(0, noise_sv^2), independent between samples and
+    calls, reproducible for the same (seed, offset); flips are fair coins."""
+    import scd_resnet_b200 as S
+    s, l, c = O.make_dataset(6, seed=8)
+    sg, lg, cg = s.cuda(), l.cuda(), c.cuda()
+    index = torch.arange(64, device="cuda") % 6
+    t1, l1, c1, d1 = S.ops.augment_batch_philox(sg, lg, cg, index, seed=123, offset=1, want_draws=True)
+    t1b, *_ = S.ops.augment_batch_philox(sg, lg, cg, index, seed=123, offset=1)
+    t2, _, _, d2 = S.ops.augment_batch_philox(sg, lg, cg, index, seed=123, offset=2, want_draws=True)
+    assert torch.equal(t1, t1b) and not torch.equal(t1, t2)
+    flips = d1[:, :2] > 0.5
+    base, lb, cb = S.ops.augment_batch(sg, lg, cg, index, flips, d1[:, 2].contiguous(), None)
+    assert torch.equal(lb, l1) and torch.equal(cb, c1)                       # same flips, same object fix-ups
+    noise = ((t1 - base) / 0.05).double().cpu().reshape(64, -1)
+    assert abs(noise.mean().item()) < 2e-3 and abs(noise.var().item() - 1.0) < 5e-3
+    assert abs((noise ** 4).mean().item() - 3.0) < 0.05                      # Gaussian kurtosis
+    assert abs((noise[0] * noise[6]).mean().item()) < 1e-2                    # same source sample, different batch slot
+    assert abs((noise[:, :-1] * noise[:, 1:]).mean().item()) < 2e-3          # neighbouring pixels
+    both = torch.cat([d1, d2])
+    assert 0.25 < both[:, 0].mean().item() < 0.75 and 0.25 < both[:, 1].mean().item() < 0.75
+    assert abs(both[:, 2].mean().item()) < 0.4 and 0.5 < both[:, 2].std().item() < 1.5
