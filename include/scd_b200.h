@@ -90,15 +90,6 @@ int scd_render_targets_npos(const float* locs, const int32_t* counts, int batch,
                             float* heat, uint8_t* mask, float* regr6, int64_t* idx,
                             unsigned int* d_counts, void* stream);
 
-/* Two-kernel form, the one the Python layer uses (d_counts nullable): a PREP kernel at full occupancy does the work
- * that has nothing to stream (fp64 radius, overlap levels, Gaussian tables) for the whole batch and leaves a record per
- * sample in `workspace` (scd_render_workspace_bytes); the DRAW kernel (one CTA per sample, map in shared memory) only
- * streams.  Outputs identical to scd_render_targets[_npos], bit for bit. */
-size_t scd_render_workspace_bytes(int batch);
-int scd_render_targets_ws(const float* locs, const int32_t* counts, int batch, float* heat, uint8_t* mask,
-                          float* regr6, int64_t* idx, unsigned int* d_counts, void* workspace,
-                          size_t workspace_bytes, void* stream);
-
 /* ------------------------------------------------------------------------------------
  * CenterNetLoss forward + backward in one pass.  Replaces CenterNetLoss.forward
  * (models/centerNetOffset.py:182-217) = clampSigmoid (utility.py:120-122) + focalLoss

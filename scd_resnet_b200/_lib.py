@@ -19,8 +19,6 @@ PROTOTYPES = {
     "scd_selftest_decode_math": (c_int, [c_void_p, c_void_p]),
     "scd_render_targets": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 4 + [c_void_p]),
     "scd_render_targets_npos": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 5 + [c_void_p]),
-    "scd_render_workspace_bytes": (c_size_t, [c_int]),
-    "scd_render_targets_ws": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 5 + [c_void_p, c_size_t, c_void_p]),
     "scd_centernet_loss_sparse": (c_int, [c_void_p] * 8 + [c_int] * 4 + [c_float, c_float] + [c_void_p] * 4
                                   + [c_void_p, c_size_t, c_void_p]),
     "scd_centernet_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

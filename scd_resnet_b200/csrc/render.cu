@@ -242,245 +242,7 @@ render_targets_kernel(const float* __restrict__ locs, const int32_t* __restrict_
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Two-kernel form (round 2).  The single kernel above spends most of its 13 us per CTA in latency chains that have
-// nothing to stream: the fp64 radius (3 sqrt, 8 divides) on one warp, the overlap-level relaxation, up to 1024 fp64
-// exps, each followed by a block barrier, while the 64 KB tile sits idle in shared memory (3 CTAs per SM, 0.35 of the
-// HBM roofline).  Here a PREP kernel does that work for the whole batch at full occupancy (256 threads per sample, no
-// tile) and leaves a 9 KB record per sample in a workspace; the DRAW kernel only streams: load the record, clear the
-// tile, draw level by level, clamp and store.  Same arithmetic, same order of additions per pixel: bit-identical output.
-// ---------------------------------------------------------------------------------------------------------------
-struct alignas(16) RenderPrep {
-    double tab[RT_TAB];                          // Gaussian tables of the objects that fit (fp64)
-    RenderObj objs[RT_MAXTAG];                   // drawn objects, list order
-    int tab_off[RT_MAXTAG + 2];                  // table start per object, -1: evaluate directly
-    unsigned char order[32], level_of[32];       // draw order: overlap level, then list order
-    int n_draw, n_tab, n_fit;
-    unsigned level_starts;
-};
-constexpr int RT_PREP_HEAD = (int)(sizeof(RenderPrep) - sizeof(double) * RT_TAB);       // everything behind the tables
-constexpr int RP_THREADS = 256;
-
-__global__ void __launch_bounds__(RP_THREADS)
-render_prep_kernel(const float* __restrict__ locs, const int32_t* __restrict__ counts, uint8_t* __restrict__ mask,
-                   float* __restrict__ regr6, int64_t* __restrict__ idx, unsigned* __restrict__ n_pos,
-                   RenderPrep* __restrict__ ws)
-{
-    __shared__ RenderPrep P;
-    __shared__ unsigned char lvl[32];
-    const int b = blockIdx.x;
-    const int tid = threadIdx.x;
-    int count = counts[b];
-    count = count < 0 ? 0 : (count > RT_MAXTAG ? RT_MAXTAG : count);
-    int my_n = 0;
-    unsigned conf = 0u;
-    if (tid < 32) {
-        bool draw = false;
-        RenderObj o = {0, 0, 0, 1.0};
-        if (tid < RT_MAXTAG) {
-            const float* l = locs + ((size_t)b * RT_MAXTAG + tid) * 8;
-            const bool live = tid < count;
-            const float fx = live ? truncf(l[0]) : 0.f;          // loc[0] = int(loc[0]), :515-516
-            const float fy = live ? truncf(l[1]) : 0.f;
-            const bool inside = live && fx >= 0.f && fx < (float)RT_HW && fy >= 0.f && fy < (float)RT_HW;
-            mask[(size_t)b * RT_MAXTAG + tid] = inside ? 1 : 0;                          // :330-336
-            idx[(size_t)b * RT_MAXTAG + tid] = inside ? (int64_t)((int)fy * RT_HW + (int)fx) : 0;  // :338-344
-            float* r = regr6 + ((size_t)b * RT_MAXTAG + tid) * 6;                        // :346-351
-#pragma unroll
-            for (int c = 0; c < 6; ++c) r[c] = live ? l[2 + c] : 0.f;
-            if (inside) {
-                const float sq = __fadd_rn(__fmul_rn(l[4], l[4]), __fmul_rn(l[5], l[5]));
-                const double w = __dmul_rn(2.0, __dsqrt_rn((double)sq));
-                const double h = __dmul_rn(2.0, (double)l[6]);
-                const double radius = center_threshold_radius(w, h, 0.5);                // THRESHOLDIOU
-                const double sigma = __ddiv_rn(radius, 3.0);                             // :589
-                o.cx = (int)fx; o.cy = (int)fy;
-                o.roi = (int)ceil(__dmul_rn(radius, 2.0));                               // :576
-                o.den = __dmul_rn(__dmul_rn(2.0, sigma), sigma);                         // utility.py:15
-                draw = true;
-            }
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, draw);
-        const int n = __popc(m);
-        if (n_pos != nullptr && tid == 0 && n) atomicAdd(n_pos + 1, (unsigned)n);        // mask.sum() (drawn == masked)
-        const int slot = __popc(m & ((1u << tid) - 1u));
-        if (draw) P.objs[slot] = o;
-        int need = draw ? (o.roi + 1) * (o.roi + 2) / 2 : 0;
-        int incl = need;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (tid >= d) incl += v;
-        }
-        const bool fits = incl <= RT_TAB;
-        if (draw) P.tab_off[slot] = fits ? incl - need : -1;
-        const unsigned fm = __ballot_sync(0xffffffffu, draw && fits);
-        const int last = 31 - __clz(fm | 1u);
-        const int used = __shfl_sync(0xffffffffu, incl, last);
-        if (tid == 0) { P.n_draw = n; P.n_tab = fm ? used : 0; P.n_fit = __popc(fm); }
-        my_n = n;
-    }
-    __syncthreads();
-    if (tid < 32) {
-        const int n = my_n;
-        RenderObj me = {0, 0, 0, 1.0};
-        if (tid < n) me = P.objs[tid];
-        const int xa = me.cx - me.roi, xb = me.cx + me.roi, ya = me.cy - me.roi, yb = me.cy + me.roi;
-        for (int j = 0; j < n; ++j) {
-            const RenderObj oj = P.objs[j];
-            const bool ov = j < tid && tid < n && !(oj.cx + oj.roi < xa || oj.cx - oj.roi > xb ||
-                                                     oj.cy + oj.roi < ya || oj.cy - oj.roi > yb);
-            conf |= (ov ? 1u : 0u) << j;
-        }
-        int level = 1;
-        lvl[tid] = 1;
-        __syncwarp();
-        for (int round = 0; round < RT_MAXTAG; ++round) {
-            int nl = 1;
-            for (unsigned c = conf; c; c &= c - 1u) nl = max(nl, (int)lvl[__ffs(c) - 1] + 1);
-            const bool changed = nl != level;
-            level = nl;
-            __syncwarp();
-            lvl[tid] = (unsigned char)level;
-            __syncwarp();
-            if (!__any_sync(0xffffffffu, changed)) break;
-        }
-        int rank = 0;
-        for (int j = 0; j < n; ++j) {
-            const int lj = lvl[j];
-            rank += (lj < level || (lj == level && j < tid)) ? 1 : 0;
-        }
-        if (tid < n) { P.order[rank] = (unsigned char)tid; P.level_of[rank] = (unsigned char)level; }
-        __syncwarp();
-        const bool starts = tid < n && (tid == 0 || P.level_of[tid] != P.level_of[tid - 1]);
-        const unsigned sm_ = __ballot_sync(0xffffffffu, starts);
-        if (tid == 0) P.level_starts = sm_;
-    } else {
-        const int nf = P.n_fit, total = P.n_tab;
-        for (int i = tid - 32; i < total; i += RP_THREADS - 32) {
-            int k = 0;
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1)
-                if (k + step < nf && P.tab_off[k + step] <= i) k += step;
-            const int e = i - P.tab_off[k];
-            int a = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
-            while ((a + 1) * (a + 2) / 2 <= e) ++a;
-            while (a * (a + 1) / 2 > e) --a;
-            const int c = e - a * (a + 1) / 2;
-            P.tab[i] = exp(__ddiv_rn(-(double)(a * a + c * c), P.objs[k].den));
-        }
-    }
-    __syncthreads();
-    // record -> workspace: the head, then the used part of the tables
-    RenderPrep* out = ws + b;
-    const uint4* src_h = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(&P) + sizeof(double) * RT_TAB);
-    uint4* dst_h = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(out) + sizeof(double) * RT_TAB);
-    for (int i = tid; i < RT_PREP_HEAD / 16; i += RP_THREADS) dst_h[i] = src_h[i];
-    const int n2 = (P.n_tab + 1) / 2;
-    for (int i = tid; i < n2; i += RP_THREADS) reinterpret_cast<uint4*>(out->tab)[i] = reinterpret_cast<const uint4*>(P.tab)[i];
-}
-
-__global__ void __launch_bounds__(RT_THREADS)
-render_draw_kernel(const RenderPrep* __restrict__ ws, float* __restrict__ heat, unsigned* __restrict__ n_pos)
-{
-    extern __shared__ float tile[];                    // [128][128] fp32
-    __shared__ RenderPrep P;
-    __shared__ unsigned ones;
-    const int b = blockIdx.x;
-    const int tid = threadIdx.x;
-    const RenderPrep* in = ws + b;
-    {
-        const uint4* src_h = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(in) + sizeof(double) * RT_TAB);
-        uint4* dst_h = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(&P) + sizeof(double) * RT_TAB);
-        for (int i = tid; i < RT_PREP_HEAD / 16; i += RT_THREADS) dst_h[i] = __ldg(src_h + i);
-    }
-    for (int i = tid; i < RT_HW * RT_HW / 4; i += RT_THREADS)
-        reinterpret_cast<float4*>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tid == 0) ones = 0u;
-    __syncthreads();
-    {
-        const int n2 = (P.n_tab + 1) / 2;
-        for (int i = tid; i < n2; i += RT_THREADS) reinterpret_cast<uint4*>(P.tab)[i] = __ldg(reinterpret_cast<const uint4*>(in->tab) + i);
-    }
-    __syncthreads();
-    {
-        const int n = P.n_draw, warp = tid >> 5, lane = tid & 31;
-        const int ly = lane >> 4, lx = lane & 15;
-        const unsigned starts = P.level_starts;
-        int s0 = 0;
-        while (s0 < n) {
-            const unsigned later = s0 < 31 ? starts & ~((2u << s0) - 1u) : 0u;           // level starts after slot s0
-            const int s1 = later ? min(__ffs(later) - 1, n) : n;
-            for (int s2 = s0 + warp; s2 < s1; s2 += RT_THREADS / 32) {
-                const int k = P.order[s2];
-                const RenderObj o = P.objs[k];
-                const int off = P.tab_off[k];
-                const int xa = max(o.cx - o.roi, 0), xb = min(o.cx + o.roi, RT_HW - 1);  // :579-583 window clipping
-                const int ya = max(o.cy - o.roi, 0), yb = min(o.cy + o.roi, RT_HW - 1);
-                for (int yy = ya + ly; yy <= yb; yy += 2) {
-                    const int dy = abs(yy - o.cy);
-                    for (int xx = xa + lx; xx <= xb; xx += 16) {
-                        const int dx = abs(xx - o.cx);
-                        const int hi = max(dy, dx), lo = min(dy, dx);
-                        const double g = off >= 0 ? P.tab[off + hi * (hi + 1) / 2 + lo]
-                                                  : exp(__ddiv_rn(-(double)(dx * dx + dy * dy), o.den));
-                        float* hp = tile + yy * RT_HW + xx;
-                        *hp = (float)__dadd_rn(g, (double)*hp);
-                    }
-                }
-            }
-            s0 = s1;
-            __syncthreads();
-        }
-    }
-    float4* dst = reinterpret_cast<float4*>(heat + (size_t)b * RT_HW * RT_HW);
-    int c1 = 0;
-#pragma unroll 4
-    for (int i = tid; i < RT_HW * RT_HW / 4; i += RT_THREADS) {
-        float4 v = reinterpret_cast<const float4*>(tile)[i];
-        const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
-        if (mx >= 1.f) {                                                                 // rare: object centres
-            v.x = fminf(v.x, 1.f); v.y = fminf(v.y, 1.f);                                // heat[heat > 1] = 1
-            v.z = fminf(v.z, 1.f); v.w = fminf(v.w, 1.f);
-            c1 += (v.x == 1.f) + (v.y == 1.f) + (v.z == 1.f) + (v.w == 1.f);
-        }
-        __stcs(dst + i, v);
-    }
-    if (n_pos != nullptr) {
-        c1 = warp_sum(c1);
-        if ((tid & 31) == 0 && c1) atomicAdd(&ones, (unsigned)c1);
-        __syncthreads();
-        if (tid == 0 && ones) atomicAdd(n_pos, ones);
-    }
-}
-
 }  // namespace scd
-
-extern "C" size_t scd_render_workspace_bytes(int batch)
-{
-    return batch > 0 ? (size_t)batch * sizeof(scd::RenderPrep) + 16 : 0;
-}
-
-// Two-kernel form of scd_render_targets[_npos] (d_counts nullable): same outputs, bit for bit.
-extern "C" int scd_render_targets_ws(const float* locs, const int32_t* counts, int batch, float* heat, uint8_t* mask,
-                                     float* regr6, int64_t* idx, unsigned* d_counts, void* workspace,
-                                     size_t workspace_bytes, void* stream)
-{
-    using namespace scd;
-    if (batch <= 0) return SCD_OK;
-    if (!locs || !counts || !heat || !mask || !regr6 || !idx || !workspace)
-        return fail(SCD_EINVAL, "scd_render_targets_ws: null pointer");
-    if (workspace_bytes < scd_render_workspace_bytes(batch)) return fail(SCD_EWORKSPACE, "scd_render_targets_ws: workspace too small");
-    RenderPrep* ws = reinterpret_cast<RenderPrep*>(((uintptr_t)workspace + 15) & ~(uintptr_t)15);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (d_counts) SCD_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, 2 * sizeof(unsigned), st));
-    render_prep_kernel<<<batch, RP_THREADS, 0, st>>>(locs, counts, mask, regr6, idx, d_counts, ws);
-    SCD_LAUNCH_CHECK("render_prep_kernel");
-    SCD_SMEM_ATTR(render_draw_kernel, RT_HW * RT_HW * 4);
-    render_draw_kernel<<<batch, RT_THREADS, RT_HW * RT_HW * 4, st>>>(ws, heat, d_counts);
-    SCD_LAUNCH_CHECK("render_draw_kernel");
-    return SCD_OK;
-}
 
 static int render_targets_impl(const float* locs, const int32_t* counts, int batch, float* heat, uint8_t* mask,
                                float* regr6, int64_t* idx, unsigned* d_npos, void* stream)

@@ -57,9 +57,6 @@ def decode_topk(heat, regr, offset, K=100, planes=False, impl=0):
     return out + (pl,) if planes else out
 
 
-_RENDER_TWO_KERNELS = __import__("os").environ.get("SCD_RENDER_IMPL", "1") != "0"      # 0: the single-kernel form
-
-
 def render_targets(locs, counts, with_npos=False):
     """Gaussian target rendering + batch contract (ref: datasets/scds/scdx16p100.py:328-356,514-536,575-591).
 
@@ -78,14 +75,6 @@ def render_targets(locs, counts, with_npos=False):
     regr6 = torch.empty(b, MAXTAGLEN, 6, dtype=torch.float32, device=dev)
     idx = torch.empty(b, MAXTAGLEN, dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
-        if _RENDER_TWO_KERNELS and b > 0:
-            # prep kernel (fp64 radius / levels / tables at full occupancy) + streaming draw kernel: same bits
-            nbytes = lib.scd_render_workspace_bytes(b)
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            npos = torch.empty(2, dtype=torch.int32, device=dev) if with_npos else None
-            check(lib.scd_render_targets_ws(_ptr(locs), _ptr(counts), b, _ptr(heat), _ptr(mask), _ptr(regr6), _ptr(idx),
-                                            _ptr(npos), _ptr(ws), nbytes, _stream()), "scd_render_targets_ws")
-            return (heat, mask, regr6, idx, npos) if with_npos else (heat, mask, regr6, idx)
         if with_npos:
             npos = torch.empty(2, dtype=torch.int32, device=dev)
             check(lib.scd_render_targets_npos(_ptr(locs), _ptr(counts), b, _ptr(heat), _ptr(mask), _ptr(regr6),
