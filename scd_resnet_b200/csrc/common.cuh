@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
+#include <utility>
 
 #include "../../include/scd_b200.h"
 
@@ -51,6 +53,31 @@ inline int fail(int code, const char* fmt, ...) {
             if (scd_dev_ >= 0 && scd_dev_ < 64) scd_attr_done_[scd_dev_] = true;                         \
         }                                                                                                \
     } while (0)
+
+// Programmatic dependent launch (PDL) along the inference chain (stem -> 14 igemm stages -> heads -> decode): every kernel
+// lets its successor be scheduled as soon as SM resources free up (launch_dependents at the top) and only waits for its
+// predecessor's results where it first touches memory (pdl_wait, after its own prologue: barrier init, TMEM allocation,
+// descriptor prefetch).  The launch latency and the prologue of kernel N+1 overlap the tail of kernel N.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+    static const int on = [] { const char* e = getenv("SCD_PDL"); return e ? atoi(e) : 1; }();
+    return on != 0;
+}
+
+// kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-stream-serialization attribute when PDL is on
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 

@@ -598,6 +598,8 @@ decode_hist_kernel(const float* __restrict__ heat, const float* __restrict__ reg
                    float* __restrict__ planes)
 {
     extern __shared__ __align__(16) unsigned char dh_smem[];       // 52 KB: above the static limit
+    pdl_launch_dependents();                                       // the next batch's stem may be scheduled behind this grid
+    pdl_wait();                                                    // the maps come from the heads kernel
     DecSmem& sm = *reinterpret_cast<DecSmem*>(dh_smem);
     DecCta& c = sm.c;
     const int b = blockIdx.x;
@@ -841,8 +843,8 @@ extern "C" int scd_decode_topk_impl(const float* heat, const float* regr, const 
     // every batch size: 18 vs 55 us at 64 images, 90 vs 107 us at 2048, 295 vs 359 us at 8192.
     if (impl != 2) {
         SCD_SMEM_ATTR(scd::decode_hist_kernel, sizeof(scd::DecSmem));
-        scd::decode_hist_kernel<<<batch, scd::DH_THREADS, sizeof(scd::DecSmem), st>>>(heat, regr, offset, batch, K, scores, idx, ys, xs, off_out,
-                                                                   regr_out, planes);
+        SCD_CUDA_CHECK(scd::launch_pdl(scd::decode_hist_kernel, dim3(batch), dim3(scd::DH_THREADS), sizeof(scd::DecSmem), st, heat, regr,
+                                       offset, batch, K, scores, idx, ys, xs, off_out, regr_out, planes));
         SCD_LAUNCH_CHECK("decode_hist_kernel");
         return SCD_OK;
     }

@@ -104,6 +104,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
     float* head_const = reinterpret_cast<float*>(smem_gen + Cfg::OFF_CONST);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&p.tmB);
@@ -115,6 +116,9 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    // Barriers, TMEM and the descriptor prefetch above do not depend on any earlier kernel; everything below may read what
+    // the previous kernel (or a parameter update before it) wrote.
+    pdl_wait();
     if (EPI != EPI_STORE) {
         for (int i = threadIdx.x; i < 384 + 7 * 128 + 7; i += IG_THREADS) {
             float v;
@@ -430,7 +434,7 @@ static int launch_igemm(const IgemmParams& p, cudaStream_t st)
     using Cfg = IgemmCfg<BN>;
     const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
     SCD_SMEM_ATTR((igemm_kernel<BN, EPI, F16>), Cfg::SMEM_BYTES);
-    igemm_kernel<BN, EPI, F16><<<grid, IG_THREADS, Cfg::SMEM_BYTES, st>>>(p);
+    SCD_CUDA_CHECK(launch_pdl(igemm_kernel<BN, EPI, F16>, dim3(grid), dim3(IG_THREADS), Cfg::SMEM_BYTES, st, p));
     SCD_LAUNCH_CHECK("igemm_kernel");
     return SCD_OK;
 }

@@ -310,6 +310,7 @@ stem_row_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict
     const int hp = height / 4, wp = width / 4, hc = height / 2;
     const int nseg = wp / 128;
     const int total = batch * nseg * hp;                                    // units, pooled row fastest
+    pdl_launch_dependents();
     const int g0 = (int)((long long)total * blockIdx.x / gridDim.x), g1 = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
 
     if (tid == 0) {
@@ -318,10 +319,14 @@ stem_row_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict
         tc::mbar_init(o_full, 1); tc::mbar_init(o_empty, SR_EPI);
         tc::mbar_init(bar_w, 1);
         tc::fence_barrier_init();
+    }
+    if (warp == 3) tc::tmem_alloc<512>(tmem_slot);
+    pdl_wait();                                 // nothing above depends on earlier kernels; the weights, the tiles and the
+                                                // output buffer's previous readers below do
+    if (tid == 0) {
         tc::mbar_arrive_expect_tx(bar_w, 8192);
         tc::tma_load_2d(&tmW, bar_w, sbase, 0, 0);
     }
-    if (warp == 3) tc::tmem_alloc<512>(tmem_slot);
     float* bias_s = reinterpret_cast<float*>(sgen + SR_OFF_BAR + 256);
     if (tid < ST_CO) bias_s[tid] = bias[tid];
     tc::tc_fence_before();
@@ -667,8 +672,8 @@ static int stem_fwd_impl(const float* x, const void* weight, const float* bias, 
     if (impl == 1 && width % 512 == 0) {
         SCD_SMEM_ATTR(stem_row_kernel<F16>, SR_SMEM);
         const int units = batch * (width / 512) * (height / 4);
-        stem_row_kernel<F16><<<units < kNumSMs ? units : kNumSMs, SR_THREADS, SR_SMEM, (cudaStream_t)stream>>>(
-            tmW, x, bias, batch, height, width, reinterpret_cast<__nv_bfloat16*>(y));
+        SCD_CUDA_CHECK(launch_pdl(stem_row_kernel<F16>, dim3(units < kNumSMs ? units : kNumSMs), dim3(SR_THREADS), SR_SMEM,
+                                  (cudaStream_t)stream, tmW, x, bias, batch, height, width, reinterpret_cast<__nv_bfloat16*>(y)));
         SCD_LAUNCH_CHECK("stem_row_kernel");
         return SCD_OK;
     }
