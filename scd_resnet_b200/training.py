@@ -414,8 +414,11 @@ class TrainEngine:
                 T.conv_wgrad(1, a_in, dz1, cin, cout, self.g(p + ".conv1.weight"))
                 T.conv_wgrad(2, a_in, dzd, cin, cout, self.g(p + ".downsample.0.weight"))
                 da = T.conv_dgrad(1, dz1, self.wb(p + ".conv1.weight:dgrad"), self.zero_bias[:cin], cin, dz2=dzd)
-            if p == "layer3.0":                                                               # layer3 + layer4 are final
-                self._reduce_async(self.g_off["layer3.0.conv1.weight"], self._reduced_from)
+            # Everything from this block's first gradient upwards is final: start its all-reduce now, on NCCL's stream,
+            # while the backward pass goes on below (layer3 + layer4 together, then layer2, then layer1; only the stem's
+            # 3 K gradients are left for optimizer_step).
+            if p in ("layer3.0", "layer2.0", "layer1.0"):
+                self._reduce_async(self.g_off[p + ".conv1.weight"], self._reduced_from)
         dy0 = T.stem_pool_bwd(tape["argmax0"], da)
         dz0, _ = T.bn_backward(dy0, None, tape["z0"], tape["ctx0"], False, self.g("preprocess.1.weight"),
                                self.g("preprocess.1.bias"), **self._sync_kw())

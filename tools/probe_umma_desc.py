@@ -93,5 +93,47 @@ def main():
     json.dump(res, open(out, "w"), indent=1)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--mn" not in sys.argv:
     main()
+
+
+def mn_major_probe():
+    """MN-major operands with the 128-byte swizzle read as WINDOWS of a pixel strip (wgrad strip mode): the operand start
+    is a whole number of 128 B pixel rows into a strip written the way TMA writes it (16 B chunk c of row r at chunk
+    c ^ (r & 7), keyed on the ADDRESS bits), the two 64-channel halves of the M = 128 tile are two different windows
+    (LBO = their distance), the K = 16 pixels are two 8-row groups 1024 B apart."""
+    rng = np.random.default_rng(1)
+    npx = 160                                               # pixel rows of 64 channels (128 B)
+    vals = rng.integers(-4, 5, size=(2, npx, 64)).astype(np.float16)          # [A strip, B strip][pixel][channel]
+    img16 = np.zeros(IMG // 2, np.float16)
+    for which, base in ((0, A_OFF), (1, B_OFF)):
+        for r in range(npx):
+            for c in range(8):
+                off = base + r * 128 + ((c ^ (r & 7)) << 4)
+                img16[off // 2: off // 2 + 8] = vals[which, r, c * 8:(c + 1) * 8]
+    res = []
+    for p0, p1, q0 in ((0, 8, 0), (1, 19, 0), (3, 22, 5), (18, 37, 2), (37, 38, 9)):
+        a_start, lbo = A_OFF + p0 * 128, (p1 - p0) * 128
+        ad = (a_start >> 4) | ((lbo >> 4) << 16) | ((1024 >> 4) << 32) | (1 << 46) | (2 << 61)
+        b_start = B_OFF + q0 * 128
+        bd = (b_start >> 4) | ((8192 >> 4) << 16) | ((1024 >> 4) << 32) | (1 << 46) | (2 << 61)
+        idesc_mn = idesc(128, 64) | (1 << 15) | (1 << 16)
+        img = torch.from_numpy(img16.view(np.uint8)).cuda()
+        out = torch.empty(128, 64, dtype=torch.float32, device="cuda")
+        S.check(S.lib.scd_probe_umma(ctypes.c_void_p(img.data_ptr()), img.numel(), ad, bd, idesc_mn, 64, 1, 0, 0,
+                                     ctypes.c_void_p(out.data_ptr()),
+                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "scd_probe_umma")
+        torch.cuda.synchronize()
+        got = out.cpu().numpy().astype(np.float64)
+        A = np.concatenate([vals[0, p0:p0 + 16].astype(np.float64), vals[0, p1:p1 + 16].astype(np.float64)], axis=1)   # (16 px, 128 ch)
+        B = vals[1, q0:q0 + 16].astype(np.float64)                                                                       # (16 px, 64 ch)
+        exp = A.T @ B
+        row = {"case": "MN-major window", "p0": p0, "p1": p1, "q0": q0, "match": bool(np.array_equal(got, exp)),
+               "max_abs_diff": float(np.abs(got - exp).max())}
+        res.append(row)
+        print(json.dumps(row))
+    return res
+
+
+if __name__ == "__main__" and "--mn" in sys.argv:
+    mn_major_probe()
