@@ -273,6 +273,23 @@ wgrad_strip_kernel(const __grid_constant__ WgradStripParams p)
                 const int t0 = tg * p.taps_per_group;
                 const int ntap = min(p.taps_per_group, p.n_taps - t0);
                 const int nchunks = ntap * p.cs_blocks, mtiles = (nchunks + 1) / 2;
+                // per M tile of this unit: window offset of its lower half and the distance to the other half (the issuing
+                // thread is the only one working here: everything that does not change with the k-tile is hoisted, a
+                // first version that recomputed these inside the loop spent 2-3 k cycles per k-tile on index arithmetic)
+                int lo_off[8];
+                uint64_t a_hi[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    lo_off[i] = 0; a_hi[i] = 0;
+                    if (i < mtiles) {
+                        const int j0 = 2 * i, j1 = (2 * i + 1 < nchunks) ? 2 * i + 1 : -1;
+                        const int o0 = ws_chunk_off(p, t0, j0);
+                        const int o1 = j1 >= 0 ? ws_chunk_off(p, t0, j1) : o0 + 128;       // padded half: any in-strip window
+                        lo_off[i] = min(o0, o1);
+                        a_hi[i] = umma_desc_mn_sw128(0u, (uint32_t)abs(o1 - o0));
+                    }
+                }
+                const uint64_t b_hi = umma_desc_mn_sw128(0u, WG_CHUNK_BYTES);
                 tc::mbar_wait(tempty_bar, (it & 1u) ^ 1u);
                 tc::tc_fence_after();
                 uint32_t first = 1;
@@ -281,15 +298,15 @@ wgrad_strip_kernel(const __grid_constant__ WgradStripParams p)
                     tc::tc_fence_after();
                     const uint32_t sa = smem_base + stage * p.stage_bytes;
                     const uint32_t sb = sa + s_bytes;
-                    for (int i = 0; i < mtiles; ++i) {
-                        const int j0 = 2 * i, j1 = (2 * i + 1 < nchunks) ? 2 * i + 1 : -1;
-                        const int o0 = ws_chunk_off(p, t0, j0);
-                        const int o1 = j1 >= 0 ? ws_chunk_off(p, t0, j1) : o0 + 128;       // padded half: any in-strip window
-                        const int lo = min(o0, o1), dist = abs(o1 - o0);
 #pragma unroll
-                        for (int k = 0; k < WG_KPIX / 16; ++k)
-                            tc::umma_bf16(tmem_base + i * bn, umma_desc_mn_sw128(sa + lo + k * WS_W * 128, (uint32_t)dist),
-                                          umma_desc_mn_sw128(sb + k * 2048, WG_CHUNK_BYTES), idesc, (first && k == 0) ? 0u : 1u);
+                    for (int i = 0; i < 8; ++i) {
+                        if (i < mtiles) {
+#pragma unroll
+                            for (int k = 0; k < WG_KPIX / 16; ++k)
+                                tc::umma_bf16(tmem_base + i * bn,
+                                              a_hi[i] | (uint64_t)(((sa + lo_off[i] + k * WS_W * 128) & 0x3FFFFu) >> 4),
+                                              b_hi | (uint64_t)(((sb + k * 2048) & 0x3FFFFu) >> 4), idesc, (first && k == 0) ? 0u : 1u);
+                        }
                     }
                     first = 0;
                     tc::umma_commit(empty_bar(stage));
