@@ -51,12 +51,17 @@ def heads_traffic():
             with open(p) as f:
                 rows = json.load(f)
             rows = rows["kernels"] if isinstance(rows, dict) and "kernels" in rows else rows
+
+            def nbytes(v):              # tools/ncu_summary.py keeps ncu's "<value> <unit>" strings
+                num, unit = (str(v).split() + ["byte"])[:2]
+                return float(num) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+
             for r in rows:
-                if "igemm_kernel<384" in r.get("name", "") or "igemm_kernel<(int)384" in r.get("name", ""):
-                    rd = r.get("dram_read_bytes", r.get("dram__bytes_read.sum"))
-                    wr = r.get("dram_write_bytes", r.get("dram__bytes_write.sum"))
+                kn = r.get("kernel", r.get("name", ""))
+                if "igemm_kernel<384" in kn or "igemm_kernel<(int)384" in kn:
+                    rd, wr = r.get("dram__bytes_read.sum"), r.get("dram__bytes_write.sum")
                     if rd is not None and wr is not None:
-                        return int(float(rd) + float(wr)), "profiles/" + name
+                        return int(nbytes(rd) + nbytes(wr)), "profiles/" + name
         except Exception:
             continue
     return None, None

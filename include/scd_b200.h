@@ -295,20 +295,6 @@ int scd_bn_stats_finalize(const void* z, size_t pixels, int C, double* sums_ws, 
                           float momentum, float eps, float* scale, float* shift, float* mean, float* invstd,
                           void* const* d_peer_buffers, int rank, int world, int cap, unsigned int seq,
                           long long timeout_cycles, int* status, void* stream);
-/* Whole BatchNorm forward / backward in ONE launch each: the reduction above, then a grid-wide barrier (the last CTA
- * raises a flag once exchange and finalize are done; the grid is sized with the occupancy API so that all of its CTAs are
- * resident), then every CTA normalises the pixels it has just reduced.  The separate launches are latency bound for the
- * small layers (18-22 us each on 4-17 MB tensors that sit in L2).  Same arguments and masking rules as scd_bn_stats_finalize
- * + scd_bn_apply and as scd_bn_bwd; dgamma / dbeta are this rank's sums. */
-int scd_bn_fwd_fused(const void* z, size_t pixels, int C, double* sums_ws, const float* gamma, const float* beta,
-                     float* running_mean, float* running_var, long long* num_batches, double count,
-                     float momentum, float eps, float* scale, float* shift, float* mean, float* invstd,
-                     const void* residual, int relu, void* out, void* const* d_peer_buffers, int rank, int world,
-                     int cap, unsigned int seq, long long timeout_cycles, int* status, void* stream);
-int scd_bn_bwd_fused(const void* da, const void* a, const void* z, const float* scale, const float* shift,
-                     const float* mean, const float* invstd, size_t pixels, int C, double count, double* sums_ws,
-                     void* dz, void* dy_out, float* dgamma, float* dbeta, void* const* d_peer_buffers, int rank,
-                     int world, int cap, unsigned int seq, long long timeout_cycles, int* status, void* stream);
 int scd_bn_bwd_reduce(const void* da, const void* a, const void* z, const float* scale, const float* shift,
                       const float* mean, const float* invstd, size_t pixels, int C, double* sums_ws,
                       double* local_sums, void* const* d_peer_buffers, int rank, int world, int cap,

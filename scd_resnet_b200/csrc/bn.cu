@@ -36,27 +36,7 @@ struct BnTail {
     float* shift;
     float* mean_out;
     float* invstd_out;
-    // ---- second phase in the SAME launch (FUSED instantiations): once the tail is done the last CTA raises `release`
-    // and every CTA normalises the pixels it has just reduced (they are still in its L1 / in L2).  All CTAs of the grid
-    // must be resident at once: the host sizes the grid with the occupancy API.
-    unsigned* release;               // behind the counter; null: no second phase
-    const uint4* residual;           // forward: optional residual, ReLU flag, output
-    int relu;
-    uint4* out;
-    uint4* dz;                       // backward: dz, optional dy (the gradient entering the residual branch), d gamma / d beta
-    uint4* dy_out;
-    float* dgamma;
-    float* dbeta;
 };
-
-__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -80,8 +60,8 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
 // Threads are laid out so that thread t always handles channel group (t % (C/8)); a CTA strides over
 // pixels.  Requires BN_THREADS % (C/8) == 0, true for C in {64,128,256,384(no!),512}: 384/8 = 48 does not
 // divide 256, so the launch picks a block size that is a multiple of C/8.
-template <int MODE, bool FUSED = false>   // 0: stats of z   1: backward sums (mask from a, or none)   2: backward sums, ReLU mask recomputed from z
-__global__ void __launch_bounds__(384, FUSED ? 2 : 3)
+template <int MODE>   // 0: stats of z   1: backward sums (mask from a, or none)   2: backward sums, ReLU mask recomputed from z
+__global__ void __launch_bounds__(384, 3)
 bn_reduce_kernel(const uint4* __restrict__ z, const uint4* __restrict__ da, const uint4* __restrict__ a,
                  const float* __restrict__ mean, const float* __restrict__ invstd,
                  const float* __restrict__ scale, const float* __restrict__ shift,    // ReLU mask from z when a == NULL
@@ -146,107 +126,6 @@ bn_reduce_kernel(const uint4* __restrict__ z, const uint4* __restrict__ da, cons
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(tail.counter, 1u) == gridDim.x - 1u) ? 1 : 0;
     __syncthreads();
-    if (FUSED) {
-        // ---------------- one launch: reduce -> (exchange, finalize by the last CTA) -> grid barrier -> normalise -------------
-        if (is_last) {
-            __threadfence();
-            bool ok = true;
-            if (MODE != 0 && (tail.dgamma || tail.dbeta))          // THIS rank's sums, before the exchange
-                for (int c = threadIdx.x; c < C; c += blockDim.x) {
-                    if (tail.dbeta) tail.dbeta[c] = (float)__ldcg(sums + c);
-                    if (tail.dgamma) tail.dgamma[c] = (float)__ldcg(sums + C + c);
-                }
-            if (tail.peer.world > 1 && tail.peer.peers != nullptr) ok = peer_allreduce_block(sums, 2 * C, tail.peer);
-            if (MODE == 0 && ok) {
-                for (int c = threadIdx.x; c < C; c += blockDim.x) {
-                    if (c == 0 && tail.num_batches) *tail.num_batches += 1;
-                    const double m = __ldcg(sums + c) / tail.count;
-                    double var = __ldcg(sums + C + c) / tail.count - m * m;
-                    if (var < 0.0) var = 0.0;
-                    const float inv = (float)(1.0 / sqrt(var + (double)tail.eps));
-                    const float sc = tail.gamma[c] * inv;
-                    tail.scale[c] = sc;
-                    tail.shift[c] = tail.beta[c] - (float)m * sc;
-                    tail.mean_out[c] = (float)m;
-                    tail.invstd_out[c] = inv;
-                    if (tail.running_mean) {
-                        const double unbiased = tail.count > 1.0 ? var * tail.count / (tail.count - 1.0) : var;
-                        tail.running_mean[c] = (1.f - tail.momentum) * tail.running_mean[c] + tail.momentum * (float)m;
-                        tail.running_var[c] = (1.f - tail.momentum) * tail.running_var[c] + tail.momentum * (float)unbiased;
-                    }
-                }
-            }
-            __threadfence();
-            __syncthreads();
-            if (threadIdx.x == 0) st_release_gpu(tail.release, ok ? 1u : 2u);
-        } else if (threadIdx.x == 0) {
-            const long long t0 = clock64();
-            while (ld_acquire_gpu(tail.release) == 0u) {
-                __nanosleep(64);
-                if (tail.peer.world <= 1 && clock64() - t0 > (1ll << 32)) {      // ~2 s alone on the GPU: the grid was not co-resident
-                    printf("scd_b200: BatchNorm grid barrier timed out (block %d of %d)\n", (int)blockIdx.x, (int)gridDim.x);
-                    __trap();
-                }
-            }
-        }
-        __syncthreads();
-        if (ld_acquire_gpu(tail.release) != 1u) return;             // the exchange gave up (status word set): nothing to apply
-        if (MODE == 0) {
-            float sc[8], sh[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { sc[i] = __ldcg(tail.scale + g * 8 + i); sh[i] = __ldcg(tail.shift + g * 8 + i); }
-            for (size_t p = (size_t)blockIdx.x * lanes + pl; p < pixels; p += (size_t)gridDim.x * lanes) {
-                float zf[8], o[8];
-                unpack8(__ldg(z + p * cgroups + g), zf);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = fmaf(zf[i], sc[i], sh[i]);
-                if (tail.residual) {
-                    float rf[8];
-                    unpack8(ld_stream_u4(tail.residual + p * cgroups + g), rf);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) o[i] += rf[i];
-                }
-                if (tail.relu) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
-                }
-                tail.out[p * cgroups + g] = pack8(o);
-            }
-        } else {
-            // dz = A dy + B z + D per channel (bn_bwd_apply_kernel), sums possibly summed over ranks
-            const float inv_n = (float)(1.0 / tail.count);
-            float cA[8], cB[8], cD[8], cS[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int c = g * 8 + i;
-                const float m1 = (float)__ldcg(sums + c) * inv_n, m2 = (float)__ldcg(sums + C + c) * inv_n;
-                const float scl = scale[c], isd = invstd[c], mu_ = mean[c];
-                cS[i] = (MODE == 2) ? shift[c] : 0.f;
-                cA[i] = scl;
-                cB[i] = -scl * m2 * isd;
-                cD[i] = scl * (m2 * isd * mu_ - m1);
-            }
-            for (size_t p = (size_t)blockIdx.x * lanes + pl; p < pixels; p += (size_t)gridDim.x * lanes) {
-                float df[8], zf[8], o[8];
-                unpack8(__ldg(da + p * cgroups + g), df);
-                unpack8(__ldg(z + p * cgroups + g), zf);
-                if (MODE == 2) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) df[i] = fmaf(zf[i], cA[i], cS[i]) > 0.f ? df[i] : 0.f;
-                } else if (a != nullptr) {
-                    float af[8];
-                    unpack8(__ldg(a + p * cgroups + g), af);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) df[i] = af[i] > 0.f ? df[i] : 0.f;
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = fmaf(cA[i], df[i], fmaf(cB[i], zf[i], cD[i]));
-                tail.dz[p * cgroups + g] = pack8(o);
-                if (tail.dy_out) tail.dy_out[p * cgroups + g] = pack8(df);
-            }
-        }
-        return;
-    }
     if (!is_last) return;
     __threadfence();
     if (tail.local_copy)
@@ -486,91 +365,6 @@ extern "C" int scd_bn_bwd_reduce(const void* da, const void* a, const void* z, c
             static_cast<const uint4*>(z), static_cast<const uint4*>(da), static_cast<const uint4*>(a), mean, invstd, scale, shift,
             pixels, C / 8, sums_ws, t);
     SCD_LAUNCH_CHECK("bn_reduce_kernel (backward, + exchange)");
-    return SCD_OK;
-}
-
-// Largest grid whose CTAs are all resident at once (the fused kernels synchronise across the grid).
-template <typename K>
-static int resident_grid(K kernel, int block, size_t smem, size_t want)
-{
-    int per_sm = 0, dev = 0, sms = scd::kNumSMs;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1) return 0;
-    const size_t cap = (size_t)per_sm * sms;
-    return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
-}
-
-// Whole train-mode BatchNorm forward in ONE launch: statistics -> (peer exchange) -> finalize -> grid barrier -> apply
-// (+ residual, + ReLU).  The small layers' separate statistics / apply launches were latency bound (18-22 us each for
-// 4-17 MB tensors that live in L2); here the second phase re-reads what the CTA has just reduced.
-extern "C" int scd_bn_fwd_fused(const void* z, size_t pixels, int C, double* sums_ws, const float* gamma, const float* beta,
-                                float* running_mean, float* running_var, long long* num_batches, double count,
-                                float momentum, float eps, float* scale, float* shift, float* mean, float* invstd,
-                                const void* residual, int relu, void* out, void* const* d_peer_buffers, int rank, int world,
-                                int cap, unsigned seq, long long timeout_cycles, int* status, void* stream)
-{
-    using namespace scd;
-    if (!z || !sums_ws || !gamma || !beta || !scale || !shift || !mean || !invstd || !out || C % 8)
-        return fail(SCD_EINVAL, "scd_bn_fwd_fused: bad arguments");
-    const int block = reduce_block(C);
-    if (!block) return fail(SCD_EINVAL, "scd_bn_fwd_fused: unsupported channel count %d", C);
-    BnTail t = {};
-    int rc = peer_args(t.peer, d_peer_buffers, rank, world, cap, seq, timeout_cycles, status, 2 * C, "scd_bn_fwd_fused");
-    if (rc) return rc;
-    t.counter = reinterpret_cast<unsigned*>(sums_ws + 2 * C);
-    t.release = t.counter + 1;
-    t.gamma = gamma; t.beta = beta; t.running_mean = running_mean; t.running_var = running_var; t.num_batches = num_batches;
-    t.count = count; t.momentum = momentum; t.eps = eps; t.scale = scale; t.shift = shift; t.mean_out = mean; t.invstd_out = invstd;
-    t.residual = static_cast<const uint4*>(residual); t.relu = relu; t.out = static_cast<uint4*>(out);
-    const int lanes = block / (C / 8);
-    const size_t smem = (size_t)2 * block * 8 * sizeof(float);
-    const int grid = resident_grid(bn_reduce_kernel<0, true>, block, smem, (pixels + (size_t)lanes * 16 - 1) / ((size_t)lanes * 16));
-    if (grid < 1) return fail(SCD_ECUDA, "scd_bn_fwd_fused: occupancy query failed");
-    SCD_CUDA_CHECK(cudaMemsetAsync(sums_ws, 0, sizeof(double) * (2 * C + 1), (cudaStream_t)stream));
-    bn_reduce_kernel<0, true><<<grid, block, smem, (cudaStream_t)stream>>>(
-        static_cast<const uint4*>(z), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, pixels, C / 8, sums_ws, t);
-    SCD_LAUNCH_CHECK("bn_reduce_kernel<0, fused>");
-    return SCD_OK;
-}
-
-// Whole BatchNorm backward in ONE launch: sums -> d gamma / d beta from the local sums -> (peer exchange) -> grid barrier
-// -> dz (and dy).  Masking as scd_bn_bwd: a != NULL: dy = da * (a > 0); a == NULL, shift != NULL: mask recomputed from z;
-// both NULL: no ReLU.
-extern "C" int scd_bn_bwd_fused(const void* da, const void* a, const void* z, const float* scale, const float* shift,
-                                const float* mean, const float* invstd, size_t pixels, int C, double count, double* sums_ws,
-                                void* dz, void* dy_out, float* dgamma, float* dbeta, void* const* d_peer_buffers, int rank,
-                                int world, int cap, unsigned seq, long long timeout_cycles, int* status, void* stream)
-{
-    using namespace scd;
-    if (!da || !z || !scale || !mean || !invstd || !sums_ws || !dz || C % 8) return fail(SCD_EINVAL, "scd_bn_bwd_fused: bad arguments");
-    const int block = reduce_block(C);
-    if (!block) return fail(SCD_EINVAL, "scd_bn_bwd_fused: unsupported channel count %d", C);
-    BnTail t = {};
-    int rc = peer_args(t.peer, d_peer_buffers, rank, world, cap, seq, timeout_cycles, status, 2 * C, "scd_bn_bwd_fused");
-    if (rc) return rc;
-    t.counter = reinterpret_cast<unsigned*>(sums_ws + 2 * C);
-    t.release = t.counter + 1;
-    t.count = count;
-    t.dz = static_cast<uint4*>(dz); t.dy_out = static_cast<uint4*>(dy_out); t.dgamma = dgamma; t.dbeta = dbeta;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int lanes = block / (C / 8);
-    const size_t smem = (size_t)2 * block * 8 * sizeof(float);
-    const size_t want = (pixels + (size_t)lanes * 16 - 1) / ((size_t)lanes * 16);
-    SCD_CUDA_CHECK(cudaMemsetAsync(sums_ws, 0, sizeof(double) * (2 * C + 1), st));
-    if (a == nullptr && shift != nullptr) {
-        const int grid = resident_grid(bn_reduce_kernel<2, true>, block, smem, want);
-        if (grid < 1) return fail(SCD_ECUDA, "scd_bn_bwd_fused: occupancy query failed");
-        bn_reduce_kernel<2, true><<<grid, block, smem, st>>>(
-            static_cast<const uint4*>(z), static_cast<const uint4*>(da), nullptr, mean, invstd, scale, shift, pixels, C / 8, sums_ws, t);
-    } else {
-        const int grid = resident_grid(bn_reduce_kernel<1, true>, block, smem, want);
-        if (grid < 1) return fail(SCD_ECUDA, "scd_bn_bwd_fused: occupancy query failed");
-        bn_reduce_kernel<1, true><<<grid, block, smem, st>>>(
-            static_cast<const uint4*>(z), static_cast<const uint4*>(da), static_cast<const uint4*>(a), mean, invstd, scale, shift,
-            pixels, C / 8, sums_ws, t);
-    }
-    SCD_LAUNCH_CHECK("bn_reduce_kernel (backward, fused)");
     return SCD_OK;
 }
 

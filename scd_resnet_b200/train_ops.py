@@ -11,7 +11,6 @@ BN_EPS, BN_MOMENTUM = 1e-5, 0.1     # ref: torch BatchNorm2d default eps; models
 
 _NO_PEER = (None, 0, 1, 0, 0, 0, None)
 _BN_FUSED = __import__("os").environ.get("SCD_BN_FUSED", "1") != "0"      # 0: separate statistics / finalize launches (A/B)
-_BN_ONE = __import__("os").environ.get("SCD_BN_ONE_LAUNCH", "1") != "0"   # 1: reduce + grid barrier + apply in one launch
 
 
 def bn_forward(z, gamma, beta, running_mean=None, running_var=None, num_batches=None, residual=None, relu=True,
@@ -27,16 +26,6 @@ def bn_forward(z, gamma, beta, running_mean=None, running_var=None, num_batches=
     sums = torch.empty(2 * C + 1, dtype=torch.float64, device=dev)      # + the counter cell of the fused kernels
     stat = torch.empty(4, C, dtype=torch.float32, device=dev)          # scale, shift, mean, invstd
     with torch.cuda.device(dev):
-        if _BN_FUSED and _BN_ONE and (world == 1 or peer is not None):
-            count = float(pixels) * world
-            pa = peer.next_args() if (peer is not None and world > 1) else _NO_PEER
-            if out is None:
-                out = torch.empty_like(z)
-            check(lib.scd_bn_fwd_fused(_ptr(z), pixels, C, _ptr(sums), _ptr(gamma), _ptr(beta), _ptr(running_mean),
-                                       _ptr(running_var), _ptr(num_batches), count, BN_MOMENTUM, BN_EPS, _ptr(stat[0]),
-                                       _ptr(stat[1]), _ptr(stat[2]), _ptr(stat[3]), _ptr(residual), int(relu), _ptr(out),
-                                       *pa, _stream()), "scd_bn_fwd_fused")
-            return out, {"stat": stat, "count": count, "sums": sums}
         if _BN_FUSED and (world == 1 or peer is not None):
             count = float(pixels) * world
             pa = peer.next_args() if (peer is not None and world > 1) else _NO_PEER
@@ -77,12 +66,6 @@ def bn_backward(da, a, z, ctx, want_dy=False, dgamma=None, dbeta=None, all_reduc
             a = None
         shift = stat[1] if relu_from_z else None
         local = None
-        if _BN_FUSED and _BN_ONE and (world == 1 or peer is not None):
-            pa = peer.next_args() if (peer is not None and world > 1) else _NO_PEER
-            check(lib.scd_bn_bwd_fused(_ptr(da), _ptr(a), _ptr(z), _ptr(stat[0]), _ptr(shift), _ptr(stat[2]), _ptr(stat[3]),
-                                       pixels, C, count, _ptr(sums), _ptr(dz), _ptr(dy), _ptr(dgamma), _ptr(dbeta), *pa,
-                                       _stream()), "scd_bn_bwd_fused")
-            return dz, dy
         if _BN_FUSED and (world == 1 or peer is not None):
             pa = _NO_PEER
             if peer is not None and world > 1:
