@@ -10,7 +10,14 @@ BN_EPS, BN_MOMENTUM = 1e-5, 0.1     # ref: torch BatchNorm2d default eps; models
 
 
 _NO_PEER = (None, 0, 1, 0, 0, 0, None)
-_BN_FUSED = __import__("os").environ.get("SCD_BN_FUSED", "1") != "0"      # 0: separate statistics / finalize launches (A/B)
+# Last-CTA tail of the BatchNorm reductions (local copy, peer exchange, finalize in the reduction kernel itself):
+# "auto" = with several ranks only.  On one GPU it is neutral to slightly slower than the separate finalize launch
+# (6.60 / 6.64 vs 6.55 / 6.59 ms per step); with several ranks it removes a launch on either side of the exchange.
+_BN_FUSED_ENV = __import__("os").environ.get("SCD_BN_FUSED", "auto")
+
+
+def _bn_fused(world):
+    return world > 1 if _BN_FUSED_ENV == "auto" else _BN_FUSED_ENV != "0"
 
 
 def bn_forward(z, gamma, beta, running_mean=None, running_var=None, num_batches=None, residual=None, relu=True,
@@ -26,7 +33,7 @@ def bn_forward(z, gamma, beta, running_mean=None, running_var=None, num_batches=
     sums = torch.empty(2 * C + 1, dtype=torch.float64, device=dev)      # + the counter cell of the fused kernels
     stat = torch.empty(4, C, dtype=torch.float32, device=dev)          # scale, shift, mean, invstd
     with torch.cuda.device(dev):
-        if _BN_FUSED and (world == 1 or peer is not None):
+        if _bn_fused(world) and (world == 1 or peer is not None):
             count = float(pixels) * world
             pa = peer.next_args() if (peer is not None and world > 1) else _NO_PEER
             check(lib.scd_bn_stats_finalize(_ptr(z), pixels, C, _ptr(sums), _ptr(gamma), _ptr(beta), _ptr(running_mean),
@@ -66,7 +73,7 @@ def bn_backward(da, a, z, ctx, want_dy=False, dgamma=None, dbeta=None, all_reduc
             a = None
         shift = stat[1] if relu_from_z else None
         local = None
-        if _BN_FUSED and (world == 1 or peer is not None):
+        if _bn_fused(world) and (world == 1 or peer is not None):
             pa = _NO_PEER
             if peer is not None and world > 1:
                 pa = peer.next_args()

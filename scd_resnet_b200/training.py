@@ -312,7 +312,7 @@ class TrainEngine:
         return float(pixels) * self.stat_world if pixels is not None else None
 
     def _sync_kw(self):
-        fused = T._BN_FUSED and self.peer is not None
+        fused = T._bn_fused(self.stat_world) and self.peer is not None
         return {"all_reduce": self._allreduce_stats if (self.stat_world > 1 and not fused) else None,
                 "peer": self.peer if fused else None, "world": self.stat_world}
 
@@ -447,7 +447,7 @@ class TrainEngine:
         outs = (ops._ptr(stat[0]), ops._ptr(stat[1]), ops._ptr(stat[2]), ops._ptr(stat[3]))
         bnp = (ops._ptr(bn0.weight.data), ops._ptr(bn0.bias.data), ops._ptr(bn0.running_mean), ops._ptr(bn0.running_var),
                ops._ptr(bn0.num_batches_tracked))
-        if T._BN_FUSED and (self.stat_world == 1 or self.peer is not None):
+        if T._bn_fused(self.stat_world) and (self.stat_world == 1 or self.peer is not None):
             count = float(pixels) * self.stat_world
             pa = self.peer.next_args() if (self.peer is not None and self.stat_world > 1) else T._NO_PEER
             ops.check(ops.lib.scd_bn_stats_finalize(ops._ptr(z0), pixels, C, ops._ptr(sums), *bnp, count, T.BN_MOMENTUM,

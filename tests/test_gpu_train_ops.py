@@ -41,10 +41,14 @@ def rnd(rng, *shape, s=1.0):
 
 
 # ------------------------------------------------------------------------------ batch norm
+@pytest.mark.parametrize("fused", ["0", "1"])
 @pytest.mark.parametrize("C,relu,res", [(64, True, False), (128, True, True), (256, False, False), (384, True, False),
                                         (512, True, True)])
-def test_bn_forward_backward(S, C, relu, res):
+def test_bn_forward_backward(S, C, relu, res, fused, monkeypatch):
+    """fused = 1: the last CTA of the reduction kernels finalizes (and, with several ranks, exchanges) in place
+    (scd_bn_stats_finalize / scd_bn_bwd_reduce); 0: separate statistics / finalize launches.  Same results."""
     from scd_resnet_b200 import train_ops as T
+    monkeypatch.setattr(T, "_BN_FUSED_ENV", fused)
     rng = np.random.default_rng(C)
     z = bf(rnd(rng, 3, C, 16, 16, s=2.0) + 0.5)
     r = rnd(rng, 3, C, 16, 16) if res else None
