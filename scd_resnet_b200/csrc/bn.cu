@@ -11,32 +11,11 @@
 //   bn_apply      z, scale, shift, res?  -> a = [relu](z*scale + shift [+ res])     (bf16)
 //   bn_bwd_reduce da, a?, z              -> sum(dy), sum(dy * xhat)                 (fp64), dy = da * (a > 0)
 //   bn_bwd_apply  da, a?, z, sums        -> dz = scale*(dy - mean(dy) - xhat*mean(dy*xhat)) (bf16) [, dy]
-#include "peer.cuh"
+#include "bn_tail.cuh"
 
 namespace scd {
 
 constexpr int BN_THREADS = 256;
-
-// What the LAST CTA of a reduction does once every CTA's partial sums are in `sums` (no extra launch between the
-// reduction and its consumer): keep a copy of this rank's sums (the source of d gamma / d beta in the backward pass),
-// exchange the sums with the other ranks over NVLink peer memory (= SyncBatchNorm), and, in the forward pass, turn them
-// into the normalisation coefficients and move the running statistics (= the old bn_finalize launch).
-struct BnTail {
-    unsigned* counter;               // CTAs finished so far; lives behind the sums and is cleared with them; null: no tail
-    double* local_copy;              // nullable
-    PeerArgs peer;
-    const float* gamma;              // null: no finalize (backward reduction)
-    const float* beta;
-    float* running_mean;
-    float* running_var;
-    long long* num_batches;
-    double count;                    // elements per channel over ALL ranks
-    float momentum, eps;
-    float* scale;
-    float* shift;
-    float* mean_out;
-    float* invstd_out;
-};
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -127,30 +106,7 @@ bn_reduce_kernel(const uint4* __restrict__ z, const uint4* __restrict__ da, cons
     if (threadIdx.x == 0) is_last = (atomicAdd(tail.counter, 1u) == gridDim.x - 1u) ? 1 : 0;
     __syncthreads();
     if (!is_last) return;
-    __threadfence();
-    if (tail.local_copy)
-        for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) tail.local_copy[c] = __ldcg(sums + c);
-    if (tail.peer.world > 1 && tail.peer.peers != nullptr) {
-        if (!peer_allreduce_block(sums, 2 * C, tail.peer)) return;
-    }
-    if (tail.gamma == nullptr) return;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        if (c == 0 && tail.num_batches) *tail.num_batches += 1;
-        const double m = __ldcg(sums + c) / tail.count;
-        double var = __ldcg(sums + C + c) / tail.count - m * m;      // biased (what normalises the batch)
-        if (var < 0.0) var = 0.0;
-        const float inv = (float)(1.0 / sqrt(var + (double)tail.eps));
-        const float sc = tail.gamma[c] * inv;
-        tail.scale[c] = sc;
-        tail.shift[c] = tail.beta[c] - (float)m * sc;
-        tail.mean_out[c] = (float)m;
-        tail.invstd_out[c] = inv;
-        if (tail.running_mean) {
-            const double unbiased = tail.count > 1.0 ? var * tail.count / (tail.count - 1.0) : var;
-            tail.running_mean[c] = (1.f - tail.momentum) * tail.running_mean[c] + tail.momentum * (float)m;
-            tail.running_var[c] = (1.f - tail.momentum) * tail.running_var[c] + tail.momentum * (float)unbiased;
-        }
-    }
+    bn_tail_run(tail, sums, C);
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
