@@ -40,7 +40,7 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
 // pixels.  Requires BN_THREADS % (C/8) == 0, true for C in {64,128,256,384(no!),512}: 384/8 = 48 does not
 // divide 256, so the launch picks a block size that is a multiple of C/8.
 template <int MODE>   // 0: stats of z   1: backward sums (mask from a, or none)   2: backward sums, ReLU mask recomputed from z
-__global__ void __launch_bounds__(384, 3)
+__global__ void __launch_bounds__(384, 2)
 bn_reduce_kernel(const uint4* __restrict__ z, const uint4* __restrict__ da, const uint4* __restrict__ a,
                  const float* __restrict__ mean, const float* __restrict__ invstd,
                  const float* __restrict__ scale, const float* __restrict__ shift,    // ReLU mask from z when a == NULL
@@ -50,40 +50,64 @@ bn_reduce_kernel(const uint4* __restrict__ z, const uint4* __restrict__ da, cons
     const int g = threadIdx.x % cgroups;                 // channel group of 8
     const int lanes = blockDim.x / cgroups;              // pixel lanes per CTA
     const int pl = threadIdx.x / cgroups;
-    float s0[8], s1[8], mu[8], is[8];
+    // U pixel rows per thread and trip, all loads issued before the first use: 768 threads x U x 16 B per operand in
+    // flight per SM (a read-only stream needs ~32 KB per SM to cover the HBM latency at full rate).
+    constexpr int U = (MODE == 1) ? 2 : 4;
+    float s0[8], s1[8], is[8], nmi[8];                   // xhat = z * invstd - mean * invstd
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s0[i] = 0.f; s1[i] = 0.f; mu[i] = 0.f; is[i] = 1.f; }
+    for (int i = 0; i < 8; ++i) { s0[i] = 0.f; s1[i] = 0.f; is[i] = 1.f; nmi[i] = 0.f; }
     float sc[MODE == 2 ? 8 : 1], sh[MODE == 2 ? 8 : 1];
-    constexpr bool zmask = MODE == 2;
     if (MODE >= 1) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { mu[i] = mean[g * 8 + i]; is[i] = invstd[g * 8 + i]; }
+        for (int i = 0; i < 8; ++i) { is[i] = invstd[g * 8 + i]; nmi[i] = -mean[g * 8 + i] * is[i]; }
     }
     if (MODE == 2) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) { sc[i] = scale[g * 8 + i]; sh[i] = shift[g * 8 + i]; }
     }
-    for (size_t p = (size_t)blockIdx.x * lanes + pl; p < pixels; p += (size_t)gridDim.x * lanes) {
+    auto accumulate = [&](const uint4& zr, const uint4& dr, const uint4& ar, bool has_a) {
         float zf[8];
-        unpack8(__ldg(z + p * cgroups + g), zf);
+        unpack8(zr, zf);
         if (MODE == 0) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) { s0[i] += zf[i]; s1[i] = fmaf(zf[i], zf[i], s1[i]); }
         } else {
             float df[8];
-            unpack8(__ldg(da + p * cgroups + g), df);
-            if (zmask) {                    // a = relu(z * scale + shift): the same fma as the forward, same sign
+            unpack8(dr, df);
+            if (MODE == 2) {                // a = relu(z * scale + shift): the same fma as the forward, same sign
 #pragma unroll
                 for (int i = 0; i < 8; ++i) df[i] = fmaf(zf[i], sc[MODE == 2 ? i : 0], sh[MODE == 2 ? i : 0]) > 0.f ? df[i] : 0.f;
-            } else if (a != nullptr) {
+            } else if (has_a) {
                 float af[8];
-                unpack8(__ldg(a + p * cgroups + g), af);
+                unpack8(ar, af);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) df[i] = af[i] > 0.f ? df[i] : 0.f;
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { s0[i] += df[i]; s1[i] = fmaf(df[i], (zf[i] - mu[i]) * is[i], s1[i]); }
+            for (int i = 0; i < 8; ++i) { s0[i] += df[i]; s1[i] = fmaf(df[i], fmaf(zf[i], is[i], nmi[i]), s1[i]); }
         }
+    };
+    const size_t stride = (size_t)gridDim.x * lanes;
+    const bool has_a = MODE == 1 && a != nullptr;
+    size_t p = (size_t)blockIdx.x * lanes + pl;
+    for (; p + (U - 1) * stride < pixels; p += U * stride) {
+        uint4 zr[U], dr[U], ar[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t at = (p + u * stride) * cgroups + g;
+            zr[u] = ld_stream_u4(z + at);
+            if (MODE >= 1) dr[u] = ld_stream_u4(da + at);
+            if (has_a) ar[u] = ld_stream_u4(a + at);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) accumulate(zr[u], dr[u], ar[u], has_a);
+    }
+    for (; p < pixels; p += stride) {
+        const size_t at = p * cgroups + g;
+        uint4 zr = ld_stream_u4(z + at), dr = zr, ar = zr;
+        if (MODE >= 1) dr = ld_stream_u4(da + at);
+        if (has_a) ar = ld_stream_u4(a + at);
+        accumulate(zr, dr, ar, has_a);
     }
     float* r0 = red + (size_t)threadIdx.x * 8;
     float* r1 = red + (size_t)(blockDim.x + threadIdx.x) * 8;
@@ -218,12 +242,23 @@ bn_bwd_apply_kernel(const uint4* __restrict__ da, const uint4* __restrict__ a, c
     }
 }
 
-static inline int stream_grid(size_t items, int per_block) {
+// CTAs of a streaming pass: `per_block` items each, at most 8 per SM.  Small tensors (layer3 / layer4 / the first
+// deconv) would get fewer CTAs than SMs and run as one long chain of dependent load latencies per thread: below two
+// CTAs per SM the work is cut finer, down to `min_per_block` items per CTA.
+static inline int stream_grid(size_t items, int per_block, int min_per_block, int max_per_sm = 8) {
     size_t want = (items + per_block - 1) / per_block;
-    const size_t cap = (size_t)kNumSMs * 8;
+    const size_t two_waves = (size_t)kNumSMs * 2, cap = (size_t)kNumSMs * max_per_sm;
+    if (want < two_waves) {
+        const size_t finest = (items + min_per_block - 1) / min_per_block;
+        want = finest < two_waves ? finest : two_waves;
+    }
     if (want > cap) want = cap;
     return (int)(want < 1 ? 1 : want);
 }
+
+// The reductions end with 2 C fp64 atomics per CTA onto 2 C / 16 cache lines, and same-line atomics serialise in L2:
+// exactly the CTAs that are resident at once (2 per SM at 384 threads), not four waves of them.
+constexpr int BN_REDUCE_PER_SM = 2;
 
 static int apply_block(int C) {             // largest multiple of C/8 and of 32 that is <= BN_THREADS
     const int cg = C / 8;
@@ -249,7 +284,7 @@ extern "C" int scd_bn_stats(const void* z, size_t pixels, int C, double* sums, v
     if (!block) return fail(SCD_EINVAL, "scd_bn_stats: unsupported channel count %d", C);
     SCD_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, (cudaStream_t)stream));
     const int lanes = block / (C / 8);
-    const int grid = stream_grid(pixels, lanes * 16);
+    const int grid = stream_grid(pixels, lanes * 16, lanes * 4, BN_REDUCE_PER_SM);
     bn_reduce_kernel<0><<<grid, block, (size_t)2 * block * 8 * sizeof(float), (cudaStream_t)stream>>>(
         static_cast<const uint4*>(z), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, pixels, C / 8, sums, BnTail{});
     SCD_LAUNCH_CHECK("bn_reduce_kernel<0>");
@@ -288,7 +323,7 @@ extern "C" int scd_bn_stats_finalize(const void* z, size_t pixels, int C, double
     t.count = count; t.momentum = momentum; t.eps = eps; t.scale = scale; t.shift = shift; t.mean_out = mean; t.invstd_out = invstd;
     SCD_CUDA_CHECK(cudaMemsetAsync(sums_ws, 0, sizeof(double) * (2 * C + 1), (cudaStream_t)stream));
     const int lanes = block / (C / 8);
-    bn_reduce_kernel<0><<<stream_grid(pixels, lanes * 16), block, (size_t)2 * block * 8 * sizeof(float), (cudaStream_t)stream>>>(
+    bn_reduce_kernel<0><<<stream_grid(pixels, lanes * 16, lanes * 4, BN_REDUCE_PER_SM), block, (size_t)2 * block * 8 * sizeof(float), (cudaStream_t)stream>>>(
         static_cast<const uint4*>(z), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, pixels, C / 8, sums_ws, t);
     SCD_LAUNCH_CHECK("bn_reduce_kernel<0> (+finalize)");
     return SCD_OK;
@@ -314,10 +349,10 @@ extern "C" int scd_bn_bwd_reduce(const void* da, const void* a, const void* z, c
     const int lanes = block / (C / 8);
     const size_t smem = (size_t)2 * block * 8 * sizeof(float);
     if (a == nullptr && shift != nullptr)
-        bn_reduce_kernel<2><<<stream_grid(pixels, lanes * 16), block, smem, st>>>(
+        bn_reduce_kernel<2><<<stream_grid(pixels, lanes * 16, lanes * 4, BN_REDUCE_PER_SM), block, smem, st>>>(
             static_cast<const uint4*>(z), static_cast<const uint4*>(da), nullptr, mean, invstd, scale, shift, pixels, C / 8, sums_ws, t);
     else
-        bn_reduce_kernel<1><<<stream_grid(pixels, lanes * 16), block, smem, st>>>(
+        bn_reduce_kernel<1><<<stream_grid(pixels, lanes * 16, lanes * 4, BN_REDUCE_PER_SM), block, smem, st>>>(
             static_cast<const uint4*>(z), static_cast<const uint4*>(da), static_cast<const uint4*>(a), mean, invstd, scale, shift,
             pixels, C / 8, sums_ws, t);
     SCD_LAUNCH_CHECK("bn_reduce_kernel (backward, + exchange)");
@@ -345,7 +380,7 @@ extern "C" int scd_bn_apply(const void* z, const float* scale, const float* shif
     const int block = apply_block(C);
     if (!block) return fail(SCD_EINVAL, "scd_bn_apply: unsupported channel count %d", C);
     const size_t n8 = pixels * (size_t)(C / 8);
-    bn_apply_kernel<<<stream_grid(n8, block * 4), block, 0, (cudaStream_t)stream>>>(
+    bn_apply_kernel<<<stream_grid(n8, block * 4, block), block, 0, (cudaStream_t)stream>>>(
         static_cast<const uint4*>(z), scale, shift, static_cast<const uint4*>(residual), relu, n8, C / 8,
         static_cast<uint4*>(out));
     SCD_LAUNCH_CHECK("bn_apply_kernel");
@@ -367,11 +402,11 @@ extern "C" int scd_bn_bwd(const void* da, const void* a, const void* z, const fl
         SCD_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
         const int lanes = block / (C / 8);
         if (a == nullptr && shift != nullptr)
-            bn_reduce_kernel<2><<<stream_grid(pixels, lanes * 16), block, (size_t)2 * block * 8 * sizeof(float), st>>>(
+            bn_reduce_kernel<2><<<stream_grid(pixels, lanes * 16, lanes * 4, BN_REDUCE_PER_SM), block, (size_t)2 * block * 8 * sizeof(float), st>>>(
                 static_cast<const uint4*>(z), static_cast<const uint4*>(da), nullptr, mean, invstd, scale, shift, pixels,
                 C / 8, sums, BnTail{});
         else
-            bn_reduce_kernel<1><<<stream_grid(pixels, lanes * 16), block, (size_t)2 * block * 8 * sizeof(float), st>>>(
+            bn_reduce_kernel<1><<<stream_grid(pixels, lanes * 16, lanes * 4, BN_REDUCE_PER_SM), block, (size_t)2 * block * 8 * sizeof(float), st>>>(
                 static_cast<const uint4*>(z), static_cast<const uint4*>(da), static_cast<const uint4*>(a), mean, invstd,
                 scale, shift, pixels, C / 8, sums, BnTail{});
         SCD_LAUNCH_CHECK("bn_reduce_kernel<1>");
@@ -380,7 +415,7 @@ extern "C" int scd_bn_bwd(const void* da, const void* a, const void* z, const fl
         const int ablock = apply_block(C);
         if (!ablock) return fail(SCD_EINVAL, "scd_bn_bwd: unsupported channel count %d", C);
         const size_t n8 = pixels * (size_t)(C / 8);
-        bn_bwd_apply_kernel<<<stream_grid(n8, ablock * 4), ablock, 0, st>>>(
+        bn_bwd_apply_kernel<<<stream_grid(n8, ablock * 4, ablock), ablock, 0, st>>>(
             static_cast<const uint4*>(da), static_cast<const uint4*>(a), static_cast<const uint4*>(z), scale, shift, mean,
             invstd, sums, count, n8, C / 8, static_cast<uint4*>(dz), static_cast<uint4*>(dy_out), dgamma, dbeta,
             local_sums ? local_sums : sums);

@@ -47,10 +47,9 @@ heads_bwd_heat_kernel(const float* __restrict__ d_heat, const uint4* __restrict_
     float w[8], acc_b3[8], acc_w[8], acc_b1 = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) { w[k] = __ldg(w1 + g * 8 + k); acc_b3[k] = 0.f; acc_w[k] = 0.f; }
-    for (size_t p = (size_t)blockIdx.x * 16 + pl; p < pixels; p += (size_t)gridDim.x * 16) {
-        const float d = __ldg(d_heat + p);
+    auto one = [&](size_t p, float d, const uint4& hraw) {
         float hf[8], o[8];
-        hs_unpack8(__ldg(hidden + p * 48 + g), hf);
+        hs_unpack8(hraw, hf);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             o[k] = hf[k] > 0.f ? d * w[k] : 0.f;                // ReLU mask of the hidden activation
@@ -59,7 +58,19 @@ heads_bwd_heat_kernel(const float* __restrict__ d_heat, const uint4* __restrict_
         }
         if (g == 0) acc_b1 += d;
         d_hidden_heat[p * 16 + g] = hs_pack8(o);
+    };
+    // four pixels per trip, loads first: 2048 threads x 4 x 16 B in flight per SM
+    const size_t stride = (size_t)gridDim.x * 16;
+    size_t p = (size_t)blockIdx.x * 16 + pl;
+    for (; p + 3 * stride < pixels; p += 4 * stride) {
+        float d[4];
+        uint4 h[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { d[u] = __ldg(d_heat + p + u * stride); h[u] = __ldg(hidden + (p + u * stride) * 48 + g); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) one(p + u * stride, d[u], h[u]);
     }
+    for (; p < pixels; p += stride) one(p, __ldg(d_heat + p), __ldg(hidden + p * 48 + g));
     if (g == 0) s_db1[pl] = acc_b1;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {                               // c = 0: d b3, c = 1: d w1 row 0
@@ -143,7 +154,11 @@ __device__ __forceinline__ int hs_compact(const uint8_t* __restrict__ mask, int 
 }
 
 // out[tap][co][ci] = sum_n dh[n][co] * x[pixel_n + off(tap)][ci]     (co < 256, ci < cin; zero padding outside the map)
-// grid (cin / 64 ci tiles, 4 co tiles, 9 taps), 256 threads, each a 4 (co) x 4 (ci) register tile of the 64 x 64 CTA tile.
+// grid (cin / 64 ci tiles, 4 co tiles x HW_SPLITS object ranges, 9 taps), 256 threads, each a 4 (co) x 4 (ci) register
+// tile of the 64 x 64 CTA tile.  Every chunk of 32 objects is a chain of two dependent global loads (idx, then the
+// pixel row): with one CTA per output tile the kernel was that chain 30 times over (38 us); the object ranges run it
+// in parallel and accumulate into the zeroed `out` with 16-byte reductions.
+constexpr int HW_SPLITS = 8;
 __global__ void __launch_bounds__(256)
 heads_wgrad_objects_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ dh,
                            const uint8_t* __restrict__ mask, const int64_t* __restrict__ idx, int n_obj, int max_tags,
@@ -153,7 +168,9 @@ heads_wgrad_objects_kernel(const __nv_bfloat16* __restrict__ x, const float* __r
     __shared__ float sB[HS_CHUNK][64 + 4];      // x chunk   [object][ci]
     __shared__ int list[256];
     __shared__ int warp_cnt[8];
-    const int ci0 = blockIdx.x * 64, co0 = blockIdx.y * 64, tap = blockIdx.z;
+    const int ci0 = blockIdx.x * 64, co0 = (blockIdx.y & 3) * 64, tap = blockIdx.z;
+    const int per = (n_obj + HW_SPLITS - 1) / HW_SPLITS;
+    const int n_lo = (blockIdx.y >> 2) * per, n_hi = min(n_obj, n_lo + per);
     const int dy = tap / 3 - 1, dx = tap % 3 - 1;
     const int t = threadIdx.x, tco = (t >> 4) * 4, tci = (t & 15) * 4;
     const size_t hw = (size_t)height * width;
@@ -162,8 +179,10 @@ heads_wgrad_objects_kernel(const __nv_bfloat16* __restrict__ x, const float* __r
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int n0 = 0; n0 < n_obj; n0 += 256) {
-        const int na = hs_compact(mask, n0, n_obj, list, warp_cnt);
+    bool any = false;
+    for (int n0 = n_lo; n0 < n_hi; n0 += 256) {
+        const int na = hs_compact(mask, n0, n_hi, list, warp_cnt);
+        any |= na > 0;
         for (int c0 = 0; c0 < na; c0 += HS_CHUNK) {
             // load: 32 objects x 64 floats each side; thread -> (object t / 8, 8 consecutive elements)
             {
@@ -200,65 +219,112 @@ heads_wgrad_objects_kernel(const __nv_bfloat16* __restrict__ x, const float* __r
             __syncthreads();
         }
     }
+    if (!any) return;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-        *reinterpret_cast<float4*>(out + ((size_t)tap * 256 + co0 + tco + i) * cin + ci0 + tci) =
-            make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};"
+                     ::"l"(out + ((size_t)tap * 256 + co0 + tco + i) * cin + ci0 + tci),
+                       "f"(acc[i][0]), "f"(acc[i][1]), "f"(acc[i][2]), "f"(acc[i][3]) : "memory");
 }
 
 // dx[pixel_n + off(tap)][ci] += sum_co dh[n][co] * w3[128 + co][tap * cin + ci]
-// grid (cin / 64 ci tiles, object blocks of 32, 9 taps), 256 threads: thread -> (object t / 8, 8 consecutive ci).
-// w3 (384, 9 * cin) bf16, K-major forward operand.  dx (B,H,W,cin) bf16 already holds the dense part.
-__global__ void __launch_bounds__(256)
+// grid (cin / 64 ci tiles, object blocks of 64, 9 taps), 128 threads: thread -> (4 consecutive objects, 8 consecutive
+// ci), i.e. 32 accumulators fed by three 16-byte shared-memory reads per co (the first version, one object x 8 ci per
+// thread, moved 36 B of shared memory per 8 FMAs and was bound by that: 158 us).  The next co chunk's global loads are
+// issued before the current chunk's FMAs.  w3 (384, 9 * cin) bf16, K-major forward operand.  dx (B,H,W,cin) bf16 already
+// holds the dense part.
+constexpr int HD_OBJ = 64, HD_CO = 32, HD_THREADS = 128;
+
+__global__ void __launch_bounds__(HD_THREADS)
 heads_dgrad_objects_kernel(const float* __restrict__ dh, const uint8_t* __restrict__ mask,
                            const int64_t* __restrict__ idx, const __nv_bfloat16* __restrict__ w3, int n_obj,
                            int max_tags, int height, int width, int cin, __nv_bfloat16* __restrict__ dx)
 {
-    __shared__ float sA[HS_CHUNK][32 + 1];      // dh      [object][co chunk of 32]
-    __shared__ float sW[32][64 + 4];            // weights [co chunk][ci]
-    const int ci0 = blockIdx.x * 64, n0 = blockIdx.y * HS_CHUNK, tap = blockIdx.z;
+    __shared__ __align__(16) float sA[HD_CO][HD_OBJ + 4];     // dh      [co][object]
+    __shared__ __align__(16) float sW[HD_CO][64 + 4];         // weights [co][ci]
+    const int ci0 = blockIdx.x * 64, n0 = blockIdx.y * HD_OBJ, tap = blockIdx.z;
     const int dy = tap / 3 - 1, dxo = tap % 3 - 1;
-    const int t = threadIdx.x, o = t >> 3, e = (t & 7) * 8;
-    const int n = n0 + o;
-    const bool live = n < n_obj && mask[n] != 0;
-    // any live object in this block?  (block-uniform early exit)
-    if (__syncthreads_or(live ? 1 : 0) == 0) return;
-    float acc[8];
+    const int t = threadIdx.x, og = (t >> 3) * 4, e = (t & 7) * 8;
+    // loader roles: dh chunk = 64 objects x 32 co = 512 float4 (4 per thread), weights = 32 co x 64 ci = 256 uint4 (2)
+    int l_obj[4], l_cc[4];
+    bool l_live[4];
+    bool any = false;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    for (int c0 = 0; c0 < 256; c0 += 32) {
-        {   // dh chunk: 32 objects x 32 co -> thread (object t / 8, 4 co)
-            const int cc = (t & 7) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live) v = __ldg(reinterpret_cast<const float4*>(dh + (size_t)n * 256 + c0 + cc));
-            sA[o][cc] = v.x; sA[o][cc + 1] = v.y; sA[o][cc + 2] = v.z; sA[o][cc + 3] = v.w;
-            // weight chunk: 32 co x 64 ci -> thread (co t / 8, 8 ci)
+    for (int r = 0; r < 4; ++r) {
+        const int q = t + HD_THREADS * r;
+        l_obj[r] = q >> 3; l_cc[r] = (q & 7) * 4;
+        const int n = n0 + l_obj[r];
+        l_live[r] = n < n_obj && mask[n] != 0;
+        any |= l_live[r];
+    }
+    if (__syncthreads_or(any ? 1 : 0) == 0) return;           // no live object in this block
+    float4 ra[4];
+    uint4 rw[2];
+    auto fetch = [&](int c0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            ra[r] = l_live[r] ? __ldg(reinterpret_cast<const float4*>(dh + (size_t)(n0 + l_obj[r]) * 256 + c0 + l_cc[r]))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int q = t + HD_THREADS * r;
+            rw[r] = __ldg(reinterpret_cast<const uint4*>(w3 + (size_t)(128 + c0 + (q >> 3)) * (9 * cin) + tap * cin + ci0 + (q & 7) * 8));
+        }
+    };
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[i][k] = 0.f;
+    fetch(0);
+    for (int c0 = 0; c0 < 256; c0 += HD_CO) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            sA[l_cc[r] + 0][l_obj[r]] = ra[r].x; sA[l_cc[r] + 1][l_obj[r]] = ra[r].y;
+            sA[l_cc[r] + 2][l_obj[r]] = ra[r].z; sA[l_cc[r] + 3][l_obj[r]] = ra[r].w;
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int q = t + HD_THREADS * r;
             float wv[8];
-            hs_unpack8(__ldg(reinterpret_cast<const uint4*>(w3 + (size_t)(128 + c0 + o) * (9 * cin) + tap * cin + ci0 + e)), wv);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) sW[o][e + k] = wv[k];
+            hs_unpack8(rw[r], wv);
+            *reinterpret_cast<float4*>(&sW[q >> 3][(q & 7) * 8]) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+            *reinterpret_cast<float4*>(&sW[q >> 3][(q & 7) * 8 + 4]) = make_float4(wv[4], wv[5], wv[6], wv[7]);
         }
         __syncthreads();
+        if (c0 + HD_CO < 256) fetch(c0 + HD_CO);
 #pragma unroll 8
-        for (int c = 0; c < 32; ++c) {
-            const float a = sA[o][c];
+        for (int c = 0; c < HD_CO; ++c) {
+            const float4 av = *reinterpret_cast<const float4*>(&sA[c][og]);
             const float4 w0 = *reinterpret_cast<const float4*>(&sW[c][e]);
             const float4 w1v = *reinterpret_cast<const float4*>(&sW[c][e + 4]);
-            acc[0] = fmaf(a, w0.x, acc[0]); acc[1] = fmaf(a, w0.y, acc[1]);
-            acc[2] = fmaf(a, w0.z, acc[2]); acc[3] = fmaf(a, w0.w, acc[3]);
-            acc[4] = fmaf(a, w1v.x, acc[4]); acc[5] = fmaf(a, w1v.y, acc[5]);
-            acc[6] = fmaf(a, w1v.z, acc[6]); acc[7] = fmaf(a, w1v.w, acc[7]);
+            const float a[4] = {av.x, av.y, av.z, av.w};
+            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1v.x, w1v.y, w1v.z, w1v.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[i][k] = fmaf(a[i], w[k], acc[i][k]);
         }
         __syncthreads();
     }
-    if (!live) return;
-    const int p = (int)idx[n];
-    const int yy = p / width + dy, xx = p % width + dxo;
-    if (yy < 0 || yy >= height || xx < 0 || xx >= width) return;
-    const size_t q = (size_t)(n / max_tags) * height * width + (size_t)yy * width + xx;
-    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(dx + q * cin + ci0 + e);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) atomicAdd(dst + k, __floats2bfloat162_rn(acc[2 * k], acc[2 * k + 1]));
+    for (int i = 0; i < 4; ++i) {
+        const int n = n0 + og + i;
+        if (n >= n_obj || mask[n] == 0) continue;
+        const int p = (int)idx[n];
+        const int yy = p / width + dy, xx = p % width + dxo;
+        if (yy < 0 || yy >= height || xx < 0 || xx >= width) continue;
+        const size_t q = (size_t)(n / max_tags) * height * width + (size_t)yy * width + xx;
+        // one 16-byte reduction (REDG.ADD.BF16x8) per object instead of four bf16x2 atomics
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(acc[i][2 * k], acc[i][2 * k + 1]);
+            v[k] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        asm volatile("red.global.v4.bf16x2.add.noftz [%0], {%1, %2, %3, %4};"
+                     ::"l"(dx + q * cin + ci0 + e), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+    }
 }
 
 }  // namespace scd
@@ -277,8 +343,10 @@ extern "C" int scd_heads_bwd_sparse(const float* d_heat, const float* d_obj, con
     SCD_CUDA_CHECK(cudaMemsetAsync(g_b1, 0, 7 * sizeof(float), st));
     SCD_CUDA_CHECK(cudaMemsetAsync(g_b3, 0, 384 * sizeof(float), st));
     const size_t pixels = (size_t)batch * height * width;
+    // one wave of resident CTAs (4 per SM at 64 registers): every CTA ends with 257 atomics onto the same nine cache
+    // lines, which serialise in L2 -- eight CTAs per SM spent more time there than streaming
     size_t grid = (pixels + 16 * 8 - 1) / (16 * 8);
-    if (grid > (size_t)kNumSMs * 8) grid = (size_t)kNumSMs * 8;
+    if (grid > (size_t)kNumSMs * 4) grid = (size_t)kNumSMs * 4;
     heads_bwd_heat_kernel<<<(int)grid, 256, 0, st>>>(d_heat, static_cast<const uint4*>(hidden), w1, pixels,
                                                      static_cast<uint4*>(d_hidden_heat), g_w1, g_b1, g_b3);
     const int n_obj = batch * max_tags;
@@ -296,7 +364,8 @@ extern "C" int scd_heads_wgrad_sparse(const void* x, const float* dh_objects, co
     if (!x || !dh_objects || !mask || !idx || !out) return fail(SCD_EINVAL, "scd_heads_wgrad_sparse: null pointer");
     if (batch <= 0 || max_tags <= 0) return fail(SCD_EINVAL, "scd_heads_wgrad_sparse: empty batch");
     if (cin < 64 || cin % 64) return fail(SCD_EINVAL, "scd_heads_wgrad_sparse: cin = %d", cin);
-    heads_wgrad_objects_kernel<<<dim3(cin / 64, 4, 9), 256, 0, (cudaStream_t)stream>>>(
+    SCD_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * 9 * 256 * (size_t)cin, (cudaStream_t)stream));
+    heads_wgrad_objects_kernel<<<dim3(cin / 64, 4 * scd::HW_SPLITS, 9), 256, 0, (cudaStream_t)stream>>>(
         static_cast<const __nv_bfloat16*>(x), dh_objects, mask, idx, batch * max_tags, max_tags, height, width, cin, out);
     SCD_LAUNCH_CHECK("heads_wgrad_objects_kernel");
     return SCD_OK;
@@ -310,7 +379,7 @@ extern "C" int scd_heads_dgrad_sparse(const float* dh_objects, const uint8_t* ma
     if (batch <= 0 || max_tags <= 0) return fail(SCD_EINVAL, "scd_heads_dgrad_sparse: empty batch");
     if (cin < 64 || cin % 64) return fail(SCD_EINVAL, "scd_heads_dgrad_sparse: cin = %d", cin);
     const int n_obj = batch * max_tags;
-    heads_dgrad_objects_kernel<<<dim3(cin / 64, (n_obj + scd::HS_CHUNK - 1) / scd::HS_CHUNK, 9), 256, 0, (cudaStream_t)stream>>>(
+    heads_dgrad_objects_kernel<<<dim3(cin / 64, (n_obj + scd::HD_OBJ - 1) / scd::HD_OBJ, 9), scd::HD_THREADS, 0, (cudaStream_t)stream>>>(
         dh_objects, mask, idx, static_cast<const __nv_bfloat16*>(w3), n_obj, max_tags, height, width, cin,
         static_cast<__nv_bfloat16*>(dx));
     SCD_LAUNCH_CHECK("heads_dgrad_objects_kernel");

@@ -33,30 +33,42 @@ stem_bn_relu_pool_kernel(const uint4* __restrict__ z0, const float* __restrict__
 {
     const size_t total = (size_t)batch * hp * wp * 8;
     const int hc = 2 * hp, wc = 2 * wp;
+    // the grid stride is a multiple of 8: a thread keeps its channel group
+    const int g = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) & 7);
+    float sc[8], sh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sc[k] = __ldg(scale + g * 8 + k); sh[k] = __ldg(shift + g * 8 + k); }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int g = (int)(i & 7);
-        size_t r = i >> 3;
-        const int px = (int)(r % wp); r /= wp;
-        const int py = (int)(r % hp);
-        const int b = (int)(r / hp);
-        float sc[8], sh[8], m[8];
+        const unsigned r0 = (unsigned)(i >> 3);                   // pooled pixel index (< 2^32)
+        const int px = (int)(r0 % (unsigned)wp);
+        const unsigned r1 = r0 / (unsigned)wp;
+        const int py = (int)(r1 % (unsigned)hp);
+        const int b = (int)(r1 / (unsigned)hp);
+        // all nine window loads are issued before the first use (clamped addresses, validity kept aside): one load in
+        // flight per thread left this kernel at 2.4 TB/s
+        uint4 raw[9];
+        bool ok[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            const int cy = 2 * py + j / 3 - 1, cx = 2 * px + j % 3 - 1;
+            ok[j] = cy >= 0 && cy < hc && cx >= 0 && cx < wc;     // -inf padding; relu output >= 0
+            const int yy = min(max(cy, 0), hc - 1), xx = min(max(cx, 0), wc - 1);
+            raw[j] = __ldg(z0 + (((size_t)b * hc + yy) * wc + xx) * 8 + g);
+        }
+        float m[8];
         unsigned code[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { sc[k] = __ldg(scale + g * 8 + k); sh[k] = __ldg(shift + g * 8 + k); m[k] = 0.f; code[k] = 9u; }
+        for (int k = 0; k < 8; ++k) { m[k] = 0.f; code[k] = 9u; }
 #pragma unroll
-        for (int dy = -1; dy <= 1; ++dy)
+        for (int j = 0; j < 9; ++j) {
+            float zf[8];
+            unpack8f(raw[j], zf);
 #pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                const int cy = 2 * py + dy, cx = 2 * px + dx;
-                if (cy < 0 || cy >= hc || cx < 0 || cx >= wc) continue;      // -inf padding; relu output >= 0
-                float zf[8];
-                unpack8f(__ldg(z0 + (((size_t)b * hc + cy) * wc + cx) * 8 + g), zf);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float v = fmaf(zf[k], sc[k], sh[k]);
-                    if (v > m[k]) { m[k] = v; code[k] = (unsigned)((dy + 1) * 3 + dx + 1); }   // strict: first maximum wins
-                }
+            for (int k = 0; k < 8; ++k) {
+                const float v = fmaf(zf[k], sc[k], sh[k]);
+                if (ok[j] && v > m[k]) { m[k] = v; code[k] = (unsigned)j; }      // strict: first maximum wins
             }
+        }
         a0[i] = pack8f(m);
         if (argmax != nullptr)
             argmax[i] = make_uint2(code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24),
@@ -220,10 +232,21 @@ adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
     }
 }
 
+// thread = 8 consecutive outputs: two 16-byte index loads, eight gathers in flight, one 16-byte store (one output per
+// thread and trip was a chain of two dependent loads per 2-byte store: 70 us for the 17 M operand elements)
 __global__ void __launch_bounds__(256)
 gather_cast_kernel(const float* __restrict__ src, const int* __restrict__ idx, size_t n, __nv_bfloat16* __restrict__ dst)
 {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n8 = n >> 3;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const int4 j0 = __ldg(reinterpret_cast<const int4*>(idx) + 2 * i), j1 = __ldg(reinterpret_cast<const int4*>(idx) + 2 * i + 1);
+        const int j[8] = {j0.x, j0.y, j0.z, j0.w, j1.x, j1.y, j1.z, j1.w};
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = j[k] >= 0 ? src[j[k]] : 0.f;
+        reinterpret_cast<uint4*>(dst)[i] = pack8f(v);
+    }
+    for (size_t i = (n8 << 3) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int j = idx[i];
         dst[i] = __float2bfloat16_rn(j >= 0 ? src[j] : 0.f);
     }
@@ -319,7 +342,9 @@ extern "C" int scd_gather_cast_bf16(const float* src, const int* idx, size_t n, 
 {
     using namespace scd;
     if (!src || !idx || !dst) return fail(SCD_EINVAL, "scd_gather_cast_bf16: null pointer");
-    gather_cast_kernel<<<sgrid(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(src, idx, n, static_cast<__nv_bfloat16*>(dst));
+    if ((reinterpret_cast<uintptr_t>(idx) | reinterpret_cast<uintptr_t>(dst)) & 15)
+        return fail(SCD_EINVAL, "scd_gather_cast_bf16: idx and dst must be 16-byte aligned");
+    gather_cast_kernel<<<sgrid(n / 8 + 1, 256 * 2), 256, 0, (cudaStream_t)stream>>>(src, idx, n, static_cast<__nv_bfloat16*>(dst));
     SCD_LAUNCH_CHECK("gather_cast_kernel");
     return SCD_OK;
 }

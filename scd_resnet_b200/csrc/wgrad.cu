@@ -26,10 +26,18 @@ constexpr int WG_THREADS = 192;
 constexpr int WG_KPIX = 64;                    // pixels per k-tile: 4 rows x 16 cols
 constexpr int WG_TH = 4;
 constexpr int WG_CHUNK_BYTES = WG_KPIX * 128;  // 8 KB: 64 pixel rows x 64 channels bf16
-constexpr int WG_STAGES = 4;
-constexpr int WG_STAGE_BYTES = 6 * WG_CHUNK_BYTES;      // 2 S chunks + up to 4 P chunks
-constexpr int WG_OFF_BAR = WG_STAGES * WG_STAGE_BYTES;
-constexpr int WG_SMEM = WG_OFF_BAR + 256 + 1024;
+// MT = M sub-tiles of 128 rows (two S chunks each) a unit accumulates.  MT = 1: two 256-column accumulators, the
+// epilogue of a unit overlaps the next unit's MMAs.  MT = 2: one accumulator set of 2 x 256 columns; the P tile of a
+// k-tile is loaded once for 256 output rows, i.e. 64 KB instead of 96 KB of shared-memory fill per 256 x 256 x 64 MACs
+// (the generic kernel is bound by that fill, not by the tensor pipe: profiles/ncu_wgrad_r02.json, 46 % tensor active).
+template <int MT> struct WgCfg {
+    static constexpr int STAGES = MT == 1 ? 4 : 3;
+    static constexpr int STAGE_BYTES = (2 * MT + 4) * WG_CHUNK_BYTES;      // 2 MT S chunks + up to 4 P chunks
+    static constexpr int OFF_BAR = STAGES * STAGE_BYTES;
+    static constexpr int SMEM = OFF_BAR + 256 + 1024;
+    static constexpr int ACC = MT == 1 ? 2 : 1;                            // accumulator stages in TMEM
+};
+constexpr int WG_STAGES = 4;                                               // barrier slot layout (>= any STAGES)
 
 struct alignas(64) WgradParams {
     CUtensorMap tmS[4];
@@ -47,9 +55,12 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
            ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+template <int MT>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_kernel(const __grid_constant__ WgradParams p)
 {
+    using Cfg = WgCfg<MT>;
+    constexpr int WG_OFF_BAR = Cfg::OFF_BAR, WG_STAGE_BYTES = Cfg::STAGE_BYTES, STAGES = Cfg::STAGES, ACC = Cfg::ACC;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t smem_base = (tc::smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* smem_gen = smem_dyn + (smem_base - tc::smem_u32(smem_dyn));
@@ -62,7 +73,7 @@ wgrad_kernel(const __grid_constant__ WgradParams p)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < WG_STAGES; ++s) { tc::mbar_init(full_bar(s), 1); tc::mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(full_bar(s), 1); tc::mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < 2; ++s) { tc::mbar_init(tfull_bar(s), 1); tc::mbar_init(tempty_bar(s), 128); }
         tc::fence_barrier_init();
     }
@@ -79,31 +90,34 @@ wgrad_kernel(const __grid_constant__ WgradParams p)
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            const uint32_t bytes = (uint32_t)(2 + p.bn_chunks) * WG_CHUNK_BYTES;
+            const uint32_t bytes = (uint32_t)(2 * MT + p.bn_chunks) * WG_CHUNK_BYTES;
             for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
                 const int split = u % p.splits;
                 const int rest = u / p.splits;
                 const int nt = rest % p.n_tiles, mt = rest / p.n_tiles;
-                int c0 = 2 * mt, c1 = 2 * mt + 1;
-                if (c1 >= p.n_chunks) c1 = p.n_chunks - 1;          // padded chunk: any valid source
-                const int tap0 = c0 / p.cs_blocks, csb0 = c0 % p.cs_blocks;
-                const int tap1 = c1 / p.cs_blocks, csb1 = c1 % p.cs_blocks;
+                int tap[2 * MT], csb[2 * MT];
+#pragma unroll
+                for (int j = 0; j < 2 * MT; ++j) {
+                    int c = 2 * MT * mt + j;
+                    if (c >= p.n_chunks) c = p.n_chunks - 1;        // padded chunk: any valid source
+                    tap[j] = c / p.cs_blocks; csb[j] = c % p.cs_blocks;
+                }
                 for (int kt = split; kt < k_tiles; kt += p.splits) {
                     const int img = kt / tiles_per_img;
                     const int r = kt % tiles_per_img;
                     const int ty = r / p.tiles_x, tx = r % p.tiles_x;
                     tc::mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = smem_base + stage * WG_STAGE_BYTES;
-                    const uint32_t sb = sa + 2 * WG_CHUNK_BYTES;
+                    const uint32_t sb = sa + 2 * MT * WG_CHUNK_BYTES;
                     tc::mbar_arrive_expect_tx(full_bar(stage), bytes);
-                    tc::tma_load_4d(&p.tmS[p.tap_map[tap0]], full_bar(stage), sa, csb0 * 64,
-                                    tx * TM_TW + p.tap_dx[tap0], ty * WG_TH + p.tap_dy[tap0], img);
-                    tc::tma_load_4d(&p.tmS[p.tap_map[tap1]], full_bar(stage), sa + WG_CHUNK_BYTES, csb1 * 64,
-                                    tx * TM_TW + p.tap_dx[tap1], ty * WG_TH + p.tap_dy[tap1], img);
+#pragma unroll
+                    for (int j = 0; j < 2 * MT; ++j)
+                        tc::tma_load_4d(&p.tmS[p.tap_map[tap[j]]], full_bar(stage), sa + j * WG_CHUNK_BYTES, csb[j] * 64,
+                                        tx * TM_TW + p.tap_dx[tap[j]], ty * WG_TH + p.tap_dy[tap[j]], img);
                     for (int i = 0; i < p.bn_chunks; ++i)
                         tc::tma_load_4d(&p.tmP, full_bar(stage), sb + i * WG_CHUNK_BYTES,
                                         (nt * p.bn_chunks + i) * 64, tx * TM_TW, ty * WG_TH, img);
-                    if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -115,7 +129,7 @@ wgrad_kernel(const __grid_constant__ WgradParams p)
             int stage = 0; uint32_t phase = 0, it = 0;
             for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
                 const int split = u % p.splits;
-                const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+                const uint32_t as = it % ACC, aphase = (it / ACC) & 1u;
                 tc::mbar_wait(tempty_bar(as), aphase ^ 1u);
                 tc::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * 256;
@@ -124,15 +138,17 @@ wgrad_kernel(const __grid_constant__ WgradParams p)
                     tc::mbar_wait(full_bar(stage), phase);
                     tc::tc_fence_after();
                     const uint32_t sa = smem_base + stage * WG_STAGE_BYTES;
-                    const uint32_t sb = sa + 2 * WG_CHUNK_BYTES;
+                    const uint32_t sb = sa + 2 * MT * WG_CHUNK_BYTES;
 #pragma unroll
                     for (int k = 0; k < WG_KPIX / 16; ++k) {
-                        tc::umma_bf16(d_tmem, umma_desc_mn_sw128(sa + k * 2048, WG_CHUNK_BYTES),
-                                      umma_desc_mn_sw128(sb + k * 2048, WG_CHUNK_BYTES), idesc, (first && k == 0) ? 0u : 1u);
+#pragma unroll
+                        for (int j = 0; j < MT; ++j)
+                            tc::umma_bf16(d_tmem + j * 256, umma_desc_mn_sw128(sa + j * 2 * WG_CHUNK_BYTES + k * 2048, WG_CHUNK_BYTES),
+                                          umma_desc_mn_sw128(sb + k * 2048, WG_CHUNK_BYTES), idesc, (first && k == 0) ? 0u : 1u);
                     }
                     first = 0;
                     tc::umma_commit(empty_bar(stage));
-                    if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
                 tc::umma_commit(tfull_bar(as));
             }
@@ -145,24 +161,27 @@ wgrad_kernel(const __grid_constant__ WgradParams p)
         for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
             const int rest = u / p.splits;
             const int nt = rest % p.n_tiles, mt = rest / p.n_tiles;
-            const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+            const uint32_t as = it % ACC, aphase = (it / ACC) & 1u;
             tc::mbar_wait(tfull_bar(as), aphase);
             tc::tc_fence_after();
-            const uint32_t taddr = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
-            const int chunk = 2 * mt + (row >> 6);
-            // out[chunk][cp][64]: the 32 lanes of a warp hit 32 consecutive floats per column
-            float* obase = p.out + ((size_t)chunk * p.cp + (size_t)nt * bn) * 64 + (row & 63);
-            const bool live = chunk < p.n_chunks;
 #pragma unroll 1
-            for (int c0 = 0; c0 < bn; c0 += 32) {
-                uint32_t r[32];
-                tc::tmem_ld32(taddr + c0, r);
-                tc::tmem_ld_wait();
-                if (live) {
+            for (int j = 0; j < MT; ++j) {
+                const uint32_t taddr = tmem_base + as * 256 + j * 256 + ((uint32_t)(q * 32) << 16);
+                const int chunk = 2 * (MT * mt + j) + (row >> 6);
+                // out[chunk][cp][64]: the 32 lanes of a warp hit 32 consecutive floats per column
+                float* obase = p.out + ((size_t)chunk * p.cp + (size_t)nt * bn) * 64 + (row & 63);
+                const bool live = chunk < p.n_chunks;
+#pragma unroll 1
+                for (int c0 = 0; c0 < bn; c0 += 32) {
+                    uint32_t r[32];
+                    tc::tmem_ld32(taddr + c0, r);
+                    tc::tmem_ld_wait();
+                    if (live) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(obase + (size_t)(c0 + i) * 64),
-                                     "f"(__uint_as_float(r[i])) : "memory");
+                        for (int i = 0; i < 32; ++i)
+                            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(obase + (size_t)(c0 + i) * 64),
+                                         "f"(__uint_as_float(r[i])) : "memory");
+                    }
                 }
             }
             tc::tc_fence_before();
@@ -495,7 +514,10 @@ extern "C" int scd_conv_wgrad(int kind, const void* a_in, const void* dz, int ba
     }
     p.cs_blocks = cs / 64;
     p.n_chunks = p.n_taps * p.cs_blocks;
-    p.m_tiles = (p.n_chunks + 1) / 2;
+    // 256-row units when at least two full sub-tiles exist (SCD_WGRAD_MT=1 / 2 forces either)
+    static const int mt_env = [] { const char* e = getenv("SCD_WGRAD_MT"); return e ? atoi(e) : 0; }();
+    const int MT = mt_env ? (mt_env >= 2 ? 2 : 1) : (p.n_chunks >= 4 ? 2 : 1);
+    p.m_tiles = (p.n_chunks + 2 * MT - 1) / (2 * MT);
     p.cp = cp;
     p.bn_chunks = cp % 256 == 0 ? 4 : (cp % 192 == 0 ? 3 : (cp % 128 == 0 ? 2 : 1));
     p.n_tiles = cp / (p.bn_chunks * 64);
@@ -518,9 +540,14 @@ extern "C" int scd_conv_wgrad(int kind, const void* a_in, const void* dz, int ba
     p.splits = splits;
     p.total_units = out_tiles * splits;
     p.out = out;
-    SCD_SMEM_ATTR(wgrad_kernel, WG_SMEM);
     const int grid = p.total_units < kNumSMs ? p.total_units : kNumSMs;
-    wgrad_kernel<<<grid, WG_THREADS, WG_SMEM, (cudaStream_t)stream>>>(p);
+    if (MT == 2) {
+        SCD_SMEM_ATTR(wgrad_kernel<2>, WgCfg<2>::SMEM);
+        wgrad_kernel<2><<<grid, WG_THREADS, WgCfg<2>::SMEM, (cudaStream_t)stream>>>(p);
+    } else {
+        SCD_SMEM_ATTR(wgrad_kernel<1>, WgCfg<1>::SMEM);
+        wgrad_kernel<1><<<grid, WG_THREADS, WgCfg<1>::SMEM, (cudaStream_t)stream>>>(p);
+    }
     SCD_LAUNCH_CHECK("wgrad_kernel");
     return SCD_OK;
 }
