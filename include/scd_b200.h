@@ -295,6 +295,20 @@ int scd_bn_stats_finalize(const void* z, size_t pixels, int C, double* sums_ws, 
                           float momentum, float eps, float* scale, float* shift, float* mean, float* invstd,
                           void* const* d_peer_buffers, int rank, int world, int cap, unsigned int seq,
                           long long timeout_cycles, int* status, void* stream);
+/* Training forward of one conv stage (kinds 0..3, no bias, no ReLU) AND the BatchNorm statistics of its output in one
+ * launch: the store epilogue of the implicit GEMM accumulates Sum y / Sum y^2 per channel (of the bf16 values it stores,
+ * as a separate pass over y would see them) per CTA in shared memory, then fp64 atomics; replaces scd_conv_igemm_fwd +
+ * scd_bn_stats.  With gamma != NULL the last CTA also does what the last CTA of scd_bn_stats_finalize does (exchange
+ * over ranks, finalize); with gamma == NULL only sums_ws is produced (finish with scd_bn_finalize).  sums_ws: 2 cout
+ * doubles + one 8-byte counter cell (cleared by the call).  cout <= 512.
+ * Replaces: Conv2d / ConvTranspose2d followed by the batch statistics of BatchNorm2d.forward in training,
+ * /root/reference/models/backbones/residuals.py:100-120, 298-307. */
+int scd_conv_igemm_fwd_bn(int kind, const void* x, const void* weight, const float* zero_bias, int batch, int hin, int win,
+                          int cin, int cout, void* y, double* sums_ws, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, long long* num_batches, double count, float momentum,
+                          float eps, float* scale, float* shift, float* mean, float* invstd,
+                          void* const* d_peer_buffers, int rank, int world, int cap, unsigned int seq,
+                          long long timeout_cycles, int* status, void* stream);
 int scd_bn_bwd_reduce(const void* da, const void* a, const void* z, const float* scale, const float* shift,
                       const float* mean, const float* invstd, size_t pixels, int C, double* sums_ws,
                       double* local_sums, void* const* d_peer_buffers, int rank, int world, int cap,

@@ -291,18 +291,6 @@ extern "C" int scd_bn_stats(const void* z, size_t pixels, int C, double* sums, v
     return SCD_OK;
 }
 
-static int peer_args(scd::PeerArgs& pa, void* const* d_peer_buffers, int rank, int world, int cap, unsigned seq,
-                     long long timeout_cycles, int* status, int n, const char* who)
-{
-    pa = scd::PeerArgs{nullptr, 0, 1, 0, 0u, 0, nullptr};
-    if (!d_peer_buffers || world <= 1) return SCD_OK;
-    if (world > 64 || rank < 0 || rank >= world) return scd::fail(SCD_EINVAL, "%s: bad rank / world", who);
-    if (n > cap) return scd::fail(SCD_EINVAL, "%s: %d statistics exceed the peer slot capacity %d", who, n, cap);
-    if (seq == 0u) return scd::fail(SCD_EINVAL, "%s: seq starts at 1", who);
-    pa = scd::PeerArgs{reinterpret_cast<unsigned char* const*>(d_peer_buffers), rank, world, cap, seq, timeout_cycles, status};
-    return SCD_OK;
-}
-
 // bn_stats + (peer exchange) + bn_finalize in ONE launch.  sums_ws: 2C doubles followed by one 8-byte counter cell.
 extern "C" int scd_bn_stats_finalize(const void* z, size_t pixels, int C, double* sums_ws, const float* gamma,
                                      const float* beta, float* running_mean, float* running_var, long long* num_batches,
@@ -316,7 +304,7 @@ extern "C" int scd_bn_stats_finalize(const void* z, size_t pixels, int C, double
     const int block = reduce_block(C);
     if (!block) return fail(SCD_EINVAL, "scd_bn_stats_finalize: unsupported channel count %d", C);
     BnTail t = {};
-    int rc = peer_args(t.peer, d_peer_buffers, rank, world, cap, seq, timeout_cycles, status, 2 * C, "scd_bn_stats_finalize");
+    int rc = scd::peer_args(t.peer, d_peer_buffers, rank, world, cap, seq, timeout_cycles, status, 2 * C, "scd_bn_stats_finalize");
     if (rc) return rc;
     t.counter = reinterpret_cast<unsigned*>(sums_ws + 2 * C);
     t.gamma = gamma; t.beta = beta; t.running_mean = running_mean; t.running_var = running_var; t.num_batches = num_batches;
@@ -340,7 +328,7 @@ extern "C" int scd_bn_bwd_reduce(const void* da, const void* a, const void* z, c
     const int block = reduce_block(C);
     if (!block) return fail(SCD_EINVAL, "scd_bn_bwd_reduce: unsupported channel count %d", C);
     BnTail t = {};
-    int rc = peer_args(t.peer, d_peer_buffers, rank, world, cap, seq, timeout_cycles, status, 2 * C, "scd_bn_bwd_reduce");
+    int rc = scd::peer_args(t.peer, d_peer_buffers, rank, world, cap, seq, timeout_cycles, status, 2 * C, "scd_bn_bwd_reduce");
     if (rc) return rc;
     t.counter = reinterpret_cast<unsigned*>(sums_ws + 2 * C);
     t.local_copy = local_sums;

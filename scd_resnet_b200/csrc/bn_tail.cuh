@@ -55,4 +55,17 @@ __device__ __forceinline__ void bn_tail_run(const BnTail& tail, double* sums, in
     }
 }
 
+// Host side: the peer-exchange arguments of a tail (world <= 1 or no buffers: no exchange).
+inline int peer_args(PeerArgs& pa, void* const* d_peer_buffers, int rank, int world, int cap, unsigned seq,
+                     long long timeout_cycles, int* status, int n, const char* who)
+{
+    pa = PeerArgs{nullptr, 0, 1, 0, 0u, 0, nullptr};
+    if (!d_peer_buffers || world <= 1) return SCD_OK;
+    if (world > 64 || rank < 0 || rank >= world) return fail(SCD_EINVAL, "%s: bad rank / world", who);
+    if (n > cap) return fail(SCD_EINVAL, "%s: %d statistics exceed the peer slot capacity %d", who, n, cap);
+    if (seq == 0u) return fail(SCD_EINVAL, "%s: seq starts at 1", who);
+    pa = PeerArgs{reinterpret_cast<unsigned char* const*>(d_peer_buffers), rank, world, cap, seq, timeout_cycles, status};
+    return SCD_OK;
+}
+
 }  // namespace scd

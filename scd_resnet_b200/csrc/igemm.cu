@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include "tc.cuh"
 #include "tmap.cuh"
+#include "bn_tail.cuh"
 
 namespace scd {
 
@@ -55,6 +56,11 @@ struct alignas(64) IgemmParams {
     float* heat;
     float* regr;
     float* off;
+    // EPI_STORE, training: per-channel Sum y / Sum y^2 of what this launch stores (the BatchNorm statistics of the conv
+    // output), accumulated per CTA in shared memory, then fp64 atomics into bn_sums [2][cout]; the last CTA runs the
+    // reduction's tail (exchange over ranks, finalize) when bn_tail.counter is set.  null: off.
+    double* bn_sums;
+    BnTail bn_tail;
 };
 
 template <int BN> struct IgemmCfg {
@@ -77,7 +83,9 @@ template <int BN> struct IgemmCfg {
     static constexpr int OFF_BAR = OFF_STG + 4 * 4096;
     static constexpr int OFF_CONST = OFF_BAR + 512;
     static constexpr int CONST_BYTES = (BN > 256) ? (384 + 7 * 128 + 8) * 4 : 4 * BN * 4;
-    static constexpr int SMEM_BYTES = OFF_CONST + CONST_BYTES + 1024 /*align slack*/;
+    static constexpr int OFF_STATS = OFF_CONST + CONST_BYTES;               // EPI_STORE: [4 epilogue warps][2][BN] floats
+    static constexpr int STATS_FLOATS = (BN > 256) ? 0 : 8 * BN;
+    static constexpr int SMEM_BYTES = OFF_STATS + STATS_FLOATS * 4 + 1024 /*align slack*/;
 };
 
 template <int BN, int EPI, bool F16>
@@ -102,6 +110,9 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
     const bool resb = Cfg::RES_B_BLOCKS > 0 && p.b_resident != 0;
     uint32_t* tmem_slot_gen = reinterpret_cast<uint32_t*>(smem_gen + Cfg::OFF_BAR + 8 * (2 * Cfg::STAGES + 4));
     float* head_const = reinterpret_cast<float*>(smem_gen + Cfg::OFF_CONST);
+    float* s_stats = reinterpret_cast<float*>(smem_gen + Cfg::OFF_STATS);
+    const bool stats = EPI == EPI_STORE && p.bn_sums != nullptr;
+    __shared__ int s_stats_nt;                              // channel range the epilogue warps' sums belong to at the end
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_launch_dependents();
@@ -119,6 +130,8 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
     // Barriers, TMEM and the descriptor prefetch above do not depend on any earlier kernel; everything below may read what
     // the previous kernel (or a parameter update before it) wrote.
     pdl_wait();
+    if (stats)
+        for (int i = threadIdx.x; i < Cfg::STATS_FLOATS; i += IG_THREADS) s_stats[i] = 0.f;
     if (EPI != EPI_STORE) {
         for (int i = threadIdx.x; i < 384 + 7 * 128 + 7; i += IG_THREADS) {
             float v;
@@ -260,6 +273,8 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
         const int q = warp & 3;
         const int row = q * 32 + lane;                      // pixel inside the 8x16 patch
         const int ly = row >> 4, lx = row & 15;
+        float* my_stats = s_stats + q * 2 * BN;             // [2][BN]: Sum y, Sum y^2 of the channel range stats_nt
+        int stats_nt = -1;
         uint32_t it = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
             const int nt = t % p.n_tiles_n;
@@ -278,6 +293,16 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
             const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
 
             if (EPI == EPI_STORE) {
+                if (stats && nt != stats_nt) {               // another channel range: hand this warp's sums over first
+                    if (stats_nt >= 0) {
+                        for (int c = lane; c < 2 * BN; c += 32) {
+                            atomicAdd(p.bn_sums + (c / BN) * p.cout + stats_nt * BN + (c % BN), (double)my_stats[c]);
+                            my_stats[c] = 0.f;
+                        }
+                        __syncwarp();
+                    }
+                    stats_nt = nt;
+                }
                 // TMEM -> regs -> (+bias, +residual, ReLU) -> bf16 -> swizzled smem tile -> TMA store.
                 // Each warp owns 2 rows of the 8x16 pixel patch = one {64 ch, 16 x, 2 y} box per 64 channels.
                 unsigned char* stg_gen = smem_gen + Cfg::OFF_STG + q * 4096;
@@ -342,6 +367,22 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
                     if (lane == 0) {
                         tc::tma_store_4d(mo, stg, nt * BN + c0, gx, gy, img);
                         tc::bulk_commit();
+                    }
+                    if (stats) {
+                        // transposed read of the staged tile: lane -> channels c0 + 2 lane, + 1 of this warp's 32 pixels
+                        // (word (lane & 3) of chunk lane >> 2; the swizzle makes the 32 lanes hit 32 banks)
+                        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+                        for (int r = 0; r < 32; ++r) {
+                            const uint32_t w = *reinterpret_cast<const uint32_t*>(
+                                stg_gen + r * 128 + ((((uint32_t)lane >> 2) ^ (uint32_t)(r & 7)) << 4) + (lane & 3) * 4);
+                            const float a = A16::lo(w), b = A16::hi(w);
+                            s0 += a; q0 = fmaf(a, a, q0);
+                            s1 += b; q1 = fmaf(b, b, q1);
+                        }
+                        // this lane is the only writer of its four slots: plain adds, a fixed order per CTA
+                        float* st = my_stats + c0 + 2 * lane;
+                        st[0] += s0; st[1] += s1; st[BN] += q0; st[BN + 1] += q1;
                     }
                 }
             } else {
@@ -417,6 +458,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
         }
         if (EPI != EPI_HEADS && lane == 0) tc::bulk_wait0(); // all TMA stores of this warp have completed
         __syncwarp();
+        if (stats && q == 0 && lane == 0) s_stats_nt = stats_nt;
     }
 
     tc::tc_fence_before();
@@ -424,6 +466,22 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
     if (warp == 1) {
         tc::tc_fence_after();
         tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
+    if (stats) {
+        const int nt = s_stats_nt;
+        if (nt >= 0) {
+            for (int c = threadIdx.x; c < 2 * BN; c += IG_THREADS) {      // the four warps' slices in a fixed order
+                const float v = ((s_stats[c] + s_stats[2 * BN + c]) + s_stats[4 * BN + c]) + s_stats[6 * BN + c];
+                atomicAdd(p.bn_sums + (c / BN) * p.cout + nt * BN + (c % BN), (double)v);
+            }
+        }
+        if (p.bn_tail.counter == nullptr) return;
+        __shared__ int is_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) is_last = (atomicAdd(p.bn_tail.counter, 1u) == gridDim.x - 1u) ? 1 : 0;
+        __syncthreads();
+        if (is_last) bn_tail_run(p.bn_tail, p.bn_sums, p.cout);
     }
 }
 
@@ -540,9 +598,11 @@ static int pick_bn(int cout) { return cout >= 256 ? 256 : (cout >= 128 ? 128 : 6
 
 }  // namespace scd
 
+struct IgemmBnStats { double* sums; scd::BnTail tail; };
+
 static int conv_igemm(int kind, const void* x, const void* x2, const void* weight, const float* bias,
                       const void* residual, int relu, int batch, int hin, int win, int cin, int cout, void* y,
-                      void* stream, bool f16 = false)
+                      void* stream, bool f16 = false, const IgemmBnStats* bn_stats = nullptr)
 {
     using namespace scd;
     if (batch <= 0) return SCD_OK;
@@ -587,6 +647,7 @@ static int conv_igemm(int kind, const void* x, const void* x2, const void* weigh
     }
     p.total_tiles = batch * p.n_par * p.tiles_y * p.tiles_x * p.n_tiles_n;
     p.bias = bias; p.residual = static_cast<const __nv_bfloat16*>(residual); p.out = static_cast<__nv_bfloat16*>(y);
+    if (bn_stats) { p.bn_sums = bn_stats->sums; p.bn_tail = bn_stats->tail; }
     int max_taps = 0;
     for (int a = 0; a < p.n_par; ++a) max_taps = p.n_taps[a] > max_taps ? p.n_taps[a] : max_taps;
     rc = make_w_map(&p.tmB, weight, max_taps * cin, p.n_par * cout, bn, f16);   // rows = (class, cout), K = taps * cin
@@ -620,6 +681,36 @@ extern "C" int scd_conv_igemm_fwd_f16(int kind, const void* x, const void* weigh
 {
     if (kind < 0 || kind > 3) return scd::fail(SCD_EINVAL, "scd_conv_igemm_fwd_f16: kind must be 0..3");
     return conv_igemm(kind, x, nullptr, weight, bias, residual, relu, batch, hin, win, cin, cout, y, stream, true);
+}
+
+// Training forward: the conv (no bias, no ReLU) AND the BatchNorm statistics of its output in one launch (replaces
+// scd_conv_igemm_fwd + scd_bn_stats [+ scd_bn_finalize]; the statistics are those of the bf16 values that were stored,
+// like a separate pass over y would see).  sums_ws: 2 cout doubles + one 8-byte counter cell, cleared here.  With gamma
+// != NULL the last CTA also exchanges the sums over `world` ranks and finalizes, exactly like scd_bn_stats_finalize;
+// with gamma == NULL only the sums are produced (finish with scd_bn_finalize).
+extern "C" int scd_conv_igemm_fwd_bn(int kind, const void* x, const void* weight, const float* zero_bias, int batch,
+                                     int hin, int win, int cin, int cout, void* y, double* sums_ws, const float* gamma,
+                                     const float* beta, float* running_mean, float* running_var, long long* num_batches,
+                                     double count, float momentum, float eps, float* scale, float* shift, float* mean,
+                                     float* invstd, void* const* d_peer_buffers, int rank, int world, int cap,
+                                     unsigned seq, long long timeout_cycles, int* status, void* stream)
+{
+    using namespace scd;
+    if (kind < 0 || kind > 3) return fail(SCD_EINVAL, "scd_conv_igemm_fwd_bn: kind must be 0..3");
+    if (!sums_ws || cout > 512) return fail(SCD_EINVAL, "scd_conv_igemm_fwd_bn: bad arguments");
+    IgemmBnStats bs = {};
+    bs.sums = sums_ws;
+    if (gamma) {
+        if (!beta || !scale || !shift || !mean || !invstd) return fail(SCD_EINVAL, "scd_conv_igemm_fwd_bn: null pointer");
+        int rc = peer_args(bs.tail.peer, d_peer_buffers, rank, world, cap, seq, timeout_cycles, status, 2 * cout, "scd_conv_igemm_fwd_bn");
+        if (rc) return rc;
+        BnTail& t = bs.tail;
+        t.counter = reinterpret_cast<unsigned*>(sums_ws + 2 * cout);
+        t.gamma = gamma; t.beta = beta; t.running_mean = running_mean; t.running_var = running_var; t.num_batches = num_batches;
+        t.count = count; t.momentum = momentum; t.eps = eps; t.scale = scale; t.shift = shift; t.mean_out = mean; t.invstd_out = invstd;
+    }
+    SCD_CUDA_CHECK(cudaMemsetAsync(sums_ws, 0, sizeof(double) * (2 * cout + 1), (cudaStream_t)stream));
+    return conv_igemm(kind, x, nullptr, weight, zero_bias, nullptr, 0, batch, hin, win, cin, cout, y, stream, false, &bs);
 }
 
 // fmt: 0 = bf16 operands and activations, 1 = fp16.  (tcgen05 kind::f16 wants ONE format for A and B: an instruction

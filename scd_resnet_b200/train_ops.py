@@ -20,6 +20,26 @@ def _bn_fused(world):
     return world > 1 if _BN_FUSED_ENV == "auto" else _BN_FUSED_ENV != "0"
 
 
+def _bn_apply(z, stat, residual, relu, out):
+    C = z.shape[-1]
+    if out is None:
+        out = torch.empty_like(z)
+    check(lib.scd_bn_apply(_ptr(z), _ptr(stat[0]), _ptr(stat[1]), _ptr(residual), int(relu), z.numel() // C, C, _ptr(out),
+                           _stream()), "scd_bn_apply")
+    return out
+
+
+def _bn_finish_sums(sums, C, pixels, stat, gamma, beta, running_mean, running_var, num_batches, all_reduce, peer, world):
+    """Separate exchange + finalize launches behind a reduction that only produced this rank's sums."""
+    count = float(pixels)
+    if world > 1:
+        count = all_reduce(sums[:2 * C], pixels) if all_reduce is not None else (peer(sums[:2 * C]), float(pixels) * world)[1]
+    check(lib.scd_bn_finalize(_ptr(sums), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
+                              _ptr(num_batches), C, count, BN_MOMENTUM, BN_EPS, _ptr(stat[0]), _ptr(stat[1]),
+                              _ptr(stat[2]), _ptr(stat[3]), _stream()), "scd_bn_finalize")
+    return count
+
+
 def bn_forward(z, gamma, beta, running_mean=None, running_var=None, num_batches=None, residual=None, relu=True,
                out=None, all_reduce=None, peer=None, world=1):
     """Train-mode BN (+residual)(+ReLU) on z (B,H,W,C) bf16 NHWC.  Returns (a, ctx); ctx is what the backward
@@ -42,17 +62,37 @@ def bn_forward(z, gamma, beta, running_mean=None, running_var=None, num_batches=
                   "scd_bn_stats_finalize")
         else:
             check(lib.scd_bn_stats(_ptr(z), pixels, C, _ptr(sums), _stream()), "scd_bn_stats")
-            count = float(pixels)
-            if world > 1:
-                count = all_reduce(sums[:2 * C], pixels) if all_reduce is not None else (peer(sums[:2 * C]), float(pixels) * world)[1]
-            check(lib.scd_bn_finalize(_ptr(sums), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
-                                      _ptr(num_batches), C, count, BN_MOMENTUM, BN_EPS, _ptr(stat[0]), _ptr(stat[1]),
-                                      _ptr(stat[2]), _ptr(stat[3]), _stream()), "scd_bn_finalize")
-        if out is None:
-            out = torch.empty_like(z)
-        check(lib.scd_bn_apply(_ptr(z), _ptr(stat[0]), _ptr(stat[1]), _ptr(residual), int(relu), pixels, C, _ptr(out),
-                               _stream()), "scd_bn_apply")
+            count = _bn_finish_sums(sums, C, pixels, stat, gamma, beta, running_mean, running_var, num_batches, all_reduce,
+                                    peer, world)
+        out = _bn_apply(z, stat, residual, relu, out)
     return out, {"stat": stat, "count": count, "sums": sums}
+
+
+def conv_bn_forward(kind, x, weight, zero_bias, cout, gamma, beta, running_mean=None, running_var=None, num_batches=None,
+                    residual=None, relu=True, all_reduce=None, peer=None, world=1):
+    """z = conv(x) and a = BN(z) (+residual)(+ReLU) with the batch statistics accumulated by the conv's store epilogue
+    (scd_conv_igemm_fwd_bn): no separate pass over z for the statistics.  Returns (z, a, ctx) like _conv + bn_forward."""
+    x = _req(x, torch.bfloat16, "x")
+    b, h, w, cin = x.shape
+    ho, wo = (h, w) if kind == 0 else ((h // 2, w // 2) if kind in (1, 2) else (2 * h, 2 * w))
+    dev = x.device
+    z = torch.empty(b, ho, wo, cout, dtype=torch.bfloat16, device=dev)
+    pixels = b * ho * wo
+    sums = torch.empty(2 * cout + 1, dtype=torch.float64, device=dev)
+    stat = torch.empty(4, cout, dtype=torch.float32, device=dev)
+    fused_tail = _bn_fused(world) and (world == 1 or peer is not None)
+    with torch.cuda.device(dev):
+        count = float(pixels) * world
+        pa = peer.next_args() if (fused_tail and peer is not None and world > 1) else _NO_PEER
+        g = (gamma, beta, running_mean, running_var, num_batches) if fused_tail else (None,) * 5
+        check(lib.scd_conv_igemm_fwd_bn(kind, _ptr(x), _ptr(weight), _ptr(zero_bias), b, h, w, cin, cout, _ptr(z), _ptr(sums),
+                                        *[_ptr(t) for t in g], count, BN_MOMENTUM, BN_EPS, _ptr(stat[0]), _ptr(stat[1]),
+                                        _ptr(stat[2]), _ptr(stat[3]), *pa, _stream()), "scd_conv_igemm_fwd_bn")
+        if not fused_tail:
+            count = _bn_finish_sums(sums, cout, pixels, stat, gamma, beta, running_mean, running_var, num_batches,
+                                    all_reduce, peer, world)
+        a = _bn_apply(z, stat, residual, relu, None)
+    return z, a, {"stat": stat, "count": count, "sums": sums}
 
 
 def bn_backward(da, a, z, ctx, want_dy=False, dgamma=None, dbeta=None, all_reduce=None, relu_from_z=False, peer=None,

@@ -18,6 +18,8 @@ from . import train_ops as T
 from ._lib import ScdError
 
 _HEADS = (("heatmap", 0, 1), ("regr", 1, 4), ("offset", 5, 2))
+# BatchNorm batch statistics from the conv's store epilogue (scd_conv_igemm_fwd_bn); "0" = separate statistics pass
+_CONV_BN_STATS = __import__("os").environ.get("SCD_CONV_BN_STATS", "1") != "0"
 
 
 def _block_list(depth, dims):
@@ -329,6 +331,18 @@ class TrainEngine:
     def _conv(self, kind, x, key, cout):
         return ops.conv_igemm_fwd(kind, x, self.wb(key + ":fwd"), self.zero_bias[:cout], None, False)
 
+    def _conv_bn(self, kind, x, key, cout, prefix, residual=None, relu=True):
+        """conv -> train-mode BN (+residual)(+ReLU) -> (z, a, ctx).  The 3x3 / 4x4 stages accumulate the batch statistics
+        in the conv's own store epilogue; the 1x1 downsample (one k-block per tile, epilogue-bound already) keeps the
+        separate statistics pass.  SCD_CONV_BN_STATS=0 restores the separate pass everywhere."""
+        if kind == 2 or not _CONV_BN_STATS:
+            z = self._conv(kind, x, key, cout)
+            a, ctx = self._bn(z, prefix, residual=residual, relu=relu)
+            return z, a, ctx
+        m = self.module.get_submodule(prefix)
+        return T.conv_bn_forward(kind, x, self.wb(key + ":fwd"), self.zero_bias[:cout], cout, m.weight.data, m.bias.data,
+                                 m.running_mean, m.running_var, m.num_batches_tracked, residual, relu, **self._sync_kw())
+
     def forward(self, x, keep=True):
         """Train-mode forward (batch-statistics BatchNorm, running statistics updated) on x (B,1,H,W) f32 CUDA.
         Returns ((heat logits, regr, offset) NCHW f32, tape); tape = what backward() needs, or None when not `keep`
@@ -341,22 +355,18 @@ class TrainEngine:
         tape = []
         for p, cin, cout, stride in self.blocks:
             a_in = a
-            z1 = self._conv(0 if stride == 1 else 1, a_in, p + ".conv1.weight", cout)
-            a1, c1 = self._bn(z1, p + ".bn1")
-            z2 = self._conv(0, a1, p + ".conv2.weight", cout)
+            z1, a1, c1 = self._conv_bn(0 if stride == 1 else 1, a_in, p + ".conv1.weight", cout, p + ".bn1")
             if stride == 1:
                 skip, zd, cd = a_in, None, None
             else:
-                zd = self._conv(2, a_in, p + ".downsample.0.weight", cout)
-                skip, cd = self._bn(zd, p + ".downsample.1", relu=False)
-            a, c2 = self._bn(z2, p + ".bn2", residual=skip)
+                zd, skip, cd = self._conv_bn(2, a_in, p + ".downsample.0.weight", cout, p + ".downsample.1", relu=False)
+            z2, a, c2 = self._conv_bn(0, a1, p + ".conv2.weight", cout, p + ".bn2", residual=skip)
             if keep:
                 tape.append((p, cin, cout, stride, a_in, z1, a1, c1, z2, c2, zd, cd, a))
         dtape = []
         for ck, bk, cin, cout in self.deconvs:
             a_in = a
-            z = self._conv(3, a_in, ck + ".weight", cout)
-            a, c = self._bn(z, bk)
+            z, a, c = self._conv_bn(3, a_in, ck + ".weight", cout, bk)
             if keep:
                 dtape.append((ck, bk, cin, cout, a_in, z, c, a))
         e3 = a

@@ -84,6 +84,40 @@ def test_bn_forward_backward(S, C, relu, res, fused, monkeypatch):
         close(dz2, dz, 1e-2); close(dg2, dg, 1e-6); close(db2, db, 1e-6)
 
 
+@pytest.mark.parametrize("fused", ["0", "1"])
+@pytest.mark.parametrize("kind,ci,co,h,b", [(0, 64, 64, 128, 2), (1, 64, 128, 64, 2), (0, 128, 128, 32, 3), (0, 256, 512, 16, 2),
+                                            (3, 512, 256, 16, 2), (2, 128, 256, 32, 2)])
+def test_conv_bn_forward_equals_conv_then_bn(S, kind, ci, co, h, b, fused, monkeypatch):
+    """scd_conv_igemm_fwd_bn (statistics from the conv's store epilogue; (0, 64, 64, 128) is the row-mode kernel) against
+    scd_conv_igemm_fwd followed by the separate statistics pass: the same z bit for bit, the same statistics up to the
+    summation order, the same running statistics."""
+    from scd_resnet_b200 import train_ops as T
+    monkeypatch.setattr(T, "_BN_FUSED_ENV", fused)
+    rng = np.random.default_rng(kind * 31 + ci + co)
+    x = nhwc(rnd(rng, b, ci, h, h))
+    taps = {0: 9, 1: 9, 2: 1, 3: 16}[kind]
+    shape = (ci, co, 4, 4) if kind == 3 else (co, ci, 1, 1) if kind == 2 else (co, ci, 3, 3)
+    w = rnd(rng, *shape, s=1.0 / np.sqrt(taps * ci / (4 if kind == 3 else 1)))
+    wb = S.weights.pack_conv(w, kind).to(torch.bfloat16).cuda()
+    zero = torch.zeros(co, device="cuda")
+    gamma = torch.from_numpy(rng.uniform(0.5, 1.5, co).astype(np.float32)).cuda()
+    beta = torch.from_numpy((0.2 * rng.standard_normal(co)).astype(np.float32)).cuda()
+    z_ref = S.ops.conv_igemm_fwd(kind, x, wb, zero, None, False)
+    res = (torch.randn_like(z_ref.float()) * 0.5).to(torch.bfloat16) if kind == 0 else None
+    rm0, rv0, nb0 = torch.zeros(co, device="cuda"), torch.ones(co, device="cuda"), torch.zeros((), dtype=torch.int64, device="cuda")
+    a_ref, ctx_ref = T.bn_forward(z_ref, gamma, beta, rm0, rv0, nb0, res, True)
+    rm1, rv1, nb1 = torch.zeros(co, device="cuda"), torch.ones(co, device="cuda"), torch.zeros((), dtype=torch.int64, device="cuda")
+    z, a, ctx = T.conv_bn_forward(kind, x, wb, zero, co, gamma, beta, rm1, rv1, nb1, res, True)
+    assert torch.equal(z, z_ref)
+    assert ctx["count"] == ctx_ref["count"]
+    close(ctx["sums"][:2 * co], ctx_ref["sums"][:2 * co], 1e-5)
+    close(ctx["stat"], ctx_ref["stat"], 1e-4)
+    close(rm1, rm0, 1e-4); close(rv1, rv0, 1e-4)
+    assert int(nb1) == 1
+    assert (a != a_ref).float().mean() < 1e-3            # a rare bf16 rounding flip from the summation order
+    close(a, a_ref, 1e-2)
+
+
 # ------------------------------------------------------------------------------ data gradients
 @pytest.mark.parametrize("kind,ci,co,h", [(0, 64, 64, 32), (0, 128, 256, 16), (0, 256, 384, 16), (1, 64, 128, 32),
                                           (1, 256, 512, 32), (3, 512, 256, 16), (3, 256, 256, 32)])
