@@ -274,7 +274,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
         const int row = q * 32 + lane;                      // pixel inside the 8x16 patch
         const int ly = row >> 4, lx = row & 15;
         float* my_stats = s_stats + q * 2 * BN;             // [2][BN]: Sum y, Sum y^2 of the channel range stats_nt
-        int stats_nt = -1;
+        int stats_nt = -1, bias_nt = -1;
         uint32_t it = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
             const int nt = t % p.n_tiles_n;
@@ -308,9 +308,12 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
                 unsigned char* stg_gen = smem_gen + Cfg::OFF_STG + q * 4096;
                 const uint32_t stg = smem_base + Cfg::OFF_STG + q * 4096;
                 float* bias_s = head_const + q * BN;
-                __syncwarp();
-                for (int i = lane; i < BN; i += 32) bias_s[i] = __ldg(p.bias + nt * BN + i);
-                __syncwarp();
+                if (nt != bias_nt) {                         // this warp's bias copy: reloaded only when the channel range changes
+                    __syncwarp();
+                    for (int i = lane; i < BN; i += 32) bias_s[i] = __ldg(p.bias + nt * BN + i);
+                    __syncwarp();
+                    bias_nt = nt;
+                }
                 const size_t pix = ((size_t)img * p.hout + oy) * p.wout + ox;
                 const __nv_bfloat16* rptr = p.residual ? p.residual + pix * p.cout + nt * BN : nullptr;
                 const CUtensorMap* mo = rowm ? &p.tmOutRow : &p.tmOut[par];

@@ -66,6 +66,12 @@ class TileDetector:
             self._host_ring = torch.empty(n, 10, self.batch, self.K, pin_memory=True)
         results = []
         with torch.cuda.device(self.device):
+            # The buffers (and the weights) were allocated / written on the caller's stream: the side streams start behind
+            # it.  (Without this the first call after construction could overlap the tail of the weight packing, and a
+            # freshly allocated buffer could alias a block whose last use on the caller's stream was still running.)
+            cur = torch.cuda.current_stream(self.device)
+            for side in (self.copy_stream, self.compute_stream, self.d2h_stream):
+                side.wait_stream(cur)
             self.t_first = torch.cuda.Event(enable_timing=True)
             self.t_last = torch.cuda.Event(enable_timing=True)
             self.t_first.record(self.copy_stream)             # device-side bracket of the whole call
