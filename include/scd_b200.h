@@ -350,6 +350,18 @@ int scd_stem_conv_train(const float* x, const void* weight, int batch, int heigh
 int scd_stem_bn_relu_pool(const void* z0, const float* scale, const float* shift, int batch, int hp, int wp,
                           void* a0, uint8_t* argmax, void* stream);
 int scd_stem_pool_bwd(const uint8_t* argmax, const void* da0, int batch, int hp, int wp, void* dy0, void* stream);
+/* The stem's pool backward and BatchNorm backward without materialising dy0: both passes rebuild dy from the pool record
+ * next to their read of z0 (replaces scd_stem_pool_bwd + scd_bn_bwd on the (B,H/2,W/2,64) tensors).
+ *   phase 0: sums_ws[0..127] <- sum dy, sum dy xhat of this rank's pixels; with tail != 0 the last CTA also copies them
+ *            to local_sums (nullable) and exchanges them over `world` ranks through the peer buffers (as
+ *            scd_bn_bwd_reduce does; sums_ws then holds 128 doubles + one 8-byte counter cell);
+ *   phase 1: dz0 (B,H/2,W/2,64) bf16 from the sums (all-reduced in between when tail == 0 and world > 1), d gamma /
+ *            d beta from local_sums (NULL: sums_ws).  `count` = elements per channel over all ranks. */
+int scd_stem_bn_pool_bwd(const uint8_t* argmax, const void* da0, const void* z0, const float* scale, const float* mean,
+                         const float* invstd, int batch, int hp, int wp, double count, double* sums_ws, double* local_sums,
+                         int tail, void* const* d_peer_buffers, int rank, int world, int cap, unsigned int seq,
+                         long long timeout_cycles, int* status, int phase, void* dz0, float* dgamma, float* dbeta,
+                         void* stream);
 
 /* Heads in training: scd_heads_fwd_c (x has `cin` channels) + hidden = ReLU(conv3x3 + b3) stored as (B,H,W,384) bf16;
  * scd_heads_bwd: d_hidden = (w1^T d_out) * (hidden > 0), and the gradients of w1 (7,128), b1 (7), b3 (384). */

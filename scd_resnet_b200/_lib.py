@@ -58,6 +58,9 @@ PROTOTYPES = {
     "scd_conv_igemm_fwd_bn": (c_int, [c_int] + [c_void_p] * 3 + [c_int] * 5 + [c_void_p, c_void_p] + [c_void_p] * 5
                               + [ctypes.c_double, c_float, c_float] + [c_void_p] * 4
                               + [c_void_p, c_int, c_int, c_int, ctypes.c_uint, ctypes.c_longlong, c_void_p, c_void_p]),
+    "scd_stem_bn_pool_bwd": (c_int, [c_void_p] * 6 + [c_int] * 3 + [ctypes.c_double, c_void_p, c_void_p, c_int]
+                             + [c_void_p, c_int, c_int, c_int, ctypes.c_uint, ctypes.c_longlong, c_void_p]
+                             + [c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "scd_bn_bwd_reduce": (c_int, [c_void_p] * 7 + [c_size_t, c_int, c_void_p, c_void_p]
                           + [c_void_p, c_int, c_int, c_int, ctypes.c_uint, ctypes.c_longlong, c_void_p, c_void_p]),
     "scd_bn_finalize": (c_int, [c_void_p] * 6 + [c_int, ctypes.c_double, c_float, c_float] + [c_void_p] * 4 + [c_void_p]),

@@ -7,6 +7,7 @@
 //   gather_cast            bf16 GEMM-operand copies of the fp32 master weights
 //   scale_inplace          x *= s (upstream-gradient scaling of the fused loss gradients)
 #include "common.cuh"
+#include "bn_tail.cuh"
 
 namespace scd {
 
@@ -80,6 +81,60 @@ stem_bn_relu_pool_kernel(const uint4* __restrict__ z0, const float* __restrict__
 // whose recorded argmax is this position; the ReLU mask is part of the record (code 9).  The block (2a..2a+1,
 // 2b..2b+1) lies in the windows (a..a+1, b..b+1): four window reads (8 B of codes + 16 B of gradient each) serve
 // four outputs.  Window position codes: dy * 3 + dx with (dy, dx) = conv - (2 * window - 1).
+struct PoolBwdItem { int g, b0, a0; size_t img; };
+
+__device__ __forceinline__ PoolBwdItem pool_bwd_item(size_t i, int hp, int wp) {
+    PoolBwdItem it;
+    it.g = (int)(i & 7);
+    const unsigned r0 = (unsigned)(i >> 3);
+    it.b0 = (int)(r0 % (unsigned)wp);
+    const unsigned r1 = r0 / (unsigned)wp;
+    it.a0 = (int)(r1 % (unsigned)hp);
+    it.img = r1 / (unsigned)hp;
+    return it;
+}
+
+// dy[ry][rx][8] of the 2 x 2 conv block of `it`
+__device__ __forceinline__ void pool_bwd_block(const uint2* __restrict__ argmax, const uint4* __restrict__ da0,
+                                               const PoolBwdItem& it, int hp, int wp, float (&out)[2][2][8])
+{
+    uint2 code[2][2];
+    float df[2][2][8];
+#pragma unroll
+    for (int wy = 0; wy < 2; ++wy)
+#pragma unroll
+        for (int wx = 0; wx < 2; ++wx) {
+            const bool in = it.a0 + wy < hp && it.b0 + wx < wp;
+            code[wy][wx] = make_uint2(0x09090909u, 0x09090909u);
+            uint4 d = make_uint4(0u, 0u, 0u, 0u);
+            if (in) {
+                const size_t w = ((it.img * hp + it.a0 + wy) * wp + it.b0 + wx) * 8 + it.g;
+                code[wy][wx] = __ldg(argmax + w);
+                d = __ldg(da0 + w);
+            }
+            unpack8f(d, df[wy][wx]);
+        }
+    // out(ry, rx), ry, rx in {0, 1}: windows (wy <= ry, wx <= rx); code = (ry + 1 - 2 wy) * 3 + (rx + 1 - 2 wx)
+#pragma unroll
+    for (int ry = 0; ry < 2; ++ry)
+#pragma unroll
+        for (int rx = 0; rx < 2; ++rx) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) out[ry][rx][k] = 0.f;
+#pragma unroll
+            for (int wy = 0; wy <= ry; ++wy)
+#pragma unroll
+                for (int wx = 0; wx <= rx; ++wx) {
+                    const unsigned want = (unsigned)((ry + 1 - 2 * wy) * 3 + (rx + 1 - 2 * wx));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        out[ry][rx][k] += ((code[wy][wx].x >> (8 * k)) & 0xFFu) == want ? df[wy][wx][k] : 0.f;
+                        out[ry][rx][4 + k] += ((code[wy][wx].y >> (8 * k)) & 0xFFu) == want ? df[wy][wx][4 + k] : 0.f;
+                    }
+                }
+        }
+}
+
 __global__ void __launch_bounds__(256)
 stem_pool_bwd_kernel(const uint2* __restrict__ argmax, const uint4* __restrict__ da0, int batch, int hp, int wp,
                      uint4* __restrict__ dy0)
@@ -87,49 +142,97 @@ stem_pool_bwd_kernel(const uint2* __restrict__ argmax, const uint4* __restrict__
     const int wc = 2 * wp;
     const size_t total = (size_t)batch * hp * wp * 8;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int g = (int)(i & 7);
-        size_t r = i >> 3;
-        const int b0 = (int)(r % wp); r /= wp;
-        const int a0 = (int)(r % hp);
-        const size_t img = r / hp;
-        uint2 code[2][2];
-        float df[2][2][8];
+        const PoolBwdItem it = pool_bwd_item(i, hp, wp);
+        float out[2][2][8];
+        pool_bwd_block(argmax, da0, it, hp, wp, out);
 #pragma unroll
-        for (int wy = 0; wy < 2; ++wy)
+        for (int ry = 0; ry < 2; ++ry)
 #pragma unroll
-            for (int wx = 0; wx < 2; ++wx) {
-                const bool in = a0 + wy < hp && b0 + wx < wp;
-                code[wy][wx] = make_uint2(0x09090909u, 0x09090909u);
-                uint4 d = make_uint4(0u, 0u, 0u, 0u);
-                if (in) {
-                    const size_t w = ((img * hp + a0 + wy) * wp + b0 + wx) * 8 + g;
-                    code[wy][wx] = __ldg(argmax + w);
-                    d = __ldg(da0 + w);
-                }
-                unpack8f(d, df[wy][wx]);
-            }
-        // out(ry, rx), ry, rx in {0, 1}: windows (wy <= ry, wx <= rx); code = (ry + 1 - 2 wy) * 3 + (rx + 1 - 2 wx)
+            for (int rx = 0; rx < 2; ++rx)
+                __stcs(dy0 + ((it.img * 2 * hp + 2 * it.a0 + ry) * wc + 2 * it.b0 + rx) * 8 + it.g, pack8f(out[ry][rx]));
+    }
+}
+
+// The stem's pool backward and BatchNorm backward in one pair of passes, without materialising dy0 (B,256,256,64): both
+// passes rebuild dy from the pool record (8 B of codes + 16 B of gradient per pooled element) next to their read of z0.
+//   REDUCE: sums[0..63] += dy, sums[64..127] += dy * xhat (fp64 atomics, one wave of CTAs), then the BatchNorm tail
+//           (copy of the local sums, exchange over ranks);  APPLY: dz0 = A dy + B z0 + D like bn_bwd_apply_kernel.
+// Replaces stem_pool_bwd + bn_reduce<1> + bn_bwd_apply on 268 MB tensors (batch 32): 1.0 GB of traffic instead of 1.9 GB.
+template <bool APPLY>
+__global__ void __launch_bounds__(256)
+stem_bn_pool_bwd_kernel(const uint2* __restrict__ argmax, const uint4* __restrict__ da0, const uint4* __restrict__ z0,
+                        const float* __restrict__ scale, const float* __restrict__ mean, const float* __restrict__ invstd,
+                        int batch, int hp, int wp, double count, double* __restrict__ sums, const double* __restrict__ grad_sums,
+                        uint4* __restrict__ dz0, float* __restrict__ dgamma, float* __restrict__ dbeta, const BnTail tail)
+{
+    __shared__ float red[2][256][8 + 1];
+    const int wc = 2 * wp;
+    const size_t total = (size_t)batch * hp * wp * 8;
+    const int g = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) & 7);      // grid stride = multiple of 8
+    float is[8], nmi[8], cA[8], cB[8], cD[8], s0[8], s1[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = g * 8 + k;
+        is[k] = __ldg(invstd + c); nmi[k] = -__ldg(mean + c) * is[k];
+        s0[k] = 0.f; s1[k] = 0.f;
+        if (APPLY) {
+            const float inv_n = (float)(1.0 / count);
+            const float m1 = (float)sums[c] * inv_n, m2 = (float)sums[64 + c] * inv_n, sc = __ldg(scale + c);
+            cA[k] = sc; cB[k] = -sc * m2 * is[k]; cD[k] = sc * (m2 * is[k] * __ldg(mean + c) - m1);
+        }
+    }
+    if (APPLY && blockIdx.x == 0 && threadIdx.x < 64) {
+        // d gamma / d beta from THIS rank's sums (torch.nn.SyncBatchNorm semantics), as in bn_bwd_apply_kernel
+        if (dbeta) dbeta[threadIdx.x] = (float)grad_sums[threadIdx.x];
+        if (dgamma) dgamma[threadIdx.x] = (float)grad_sums[64 + threadIdx.x];
+    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const PoolBwdItem it = pool_bwd_item(i, hp, wp);
+        uint4 zr[2][2];
+#pragma unroll
+        for (int ry = 0; ry < 2; ++ry)
+#pragma unroll
+            for (int rx = 0; rx < 2; ++rx)
+                zr[ry][rx] = __ldg(z0 + ((it.img * 2 * hp + 2 * it.a0 + ry) * wc + 2 * it.b0 + rx) * 8 + it.g);
+        float dy[2][2][8];
+        pool_bwd_block(argmax, da0, it, hp, wp, dy);
 #pragma unroll
         for (int ry = 0; ry < 2; ++ry)
 #pragma unroll
             for (int rx = 0; rx < 2; ++rx) {
-                float out[8];
+                float zf[8];
+                unpack8f(zr[ry][rx], zf);
+                if (APPLY) {
+                    float o[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) out[k] = 0.f;
+                    for (int k = 0; k < 8; ++k) o[k] = fmaf(cA[k], dy[ry][rx][k], fmaf(cB[k], zf[k], cD[k]));
+                    __stcs(dz0 + ((it.img * 2 * hp + 2 * it.a0 + ry) * wc + 2 * it.b0 + rx) * 8 + it.g, pack8f(o));
+                } else {
 #pragma unroll
-                for (int wy = 0; wy <= ry; ++wy)
-#pragma unroll
-                    for (int wx = 0; wx <= rx; ++wx) {
-                        const unsigned want = (unsigned)((ry + 1 - 2 * wy) * 3 + (rx + 1 - 2 * wx));
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            out[k] += ((code[wy][wx].x >> (8 * k)) & 0xFFu) == want ? df[wy][wx][k] : 0.f;
-                            out[4 + k] += ((code[wy][wx].y >> (8 * k)) & 0xFFu) == want ? df[wy][wx][4 + k] : 0.f;
-                        }
+                    for (int k = 0; k < 8; ++k) {
+                        s0[k] += dy[ry][rx][k];
+                        s1[k] = fmaf(dy[ry][rx][k], fmaf(zf[k], is[k], nmi[k]), s1[k]);
                     }
-                __stcs(dy0 + ((img * 2 * hp + 2 * a0 + ry) * wc + 2 * b0 + rx) * 8 + g, pack8f(out));
+                }
             }
     }
+    if (APPLY) return;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { red[0][threadIdx.x][k] = s0[k]; red[1][threadIdx.x][k] = s1[k]; }
+    __syncthreads();
+    if (threadIdx.x < 128) {                              // thread -> (which, channel); its group's threads are t = g (mod 8)
+        const int which = threadIdx.x >> 6, ch = threadIdx.x & 63, cg = ch >> 3, k = ch & 7;
+        double t = 0.0;
+        for (int l = 0; l < 32; ++l) t += (double)red[which][l * 8 + cg][k];     // blockDim is a multiple of 8: g = threadIdx & 7
+        atomicAdd(sums + which * 64 + ch, t);
+    }
+    if (tail.counter == nullptr) return;
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(tail.counter, 1u) == gridDim.x - 1u) ? 1 : 0;
+    __syncthreads();
+    if (is_last) bn_tail_run(tail, sums, 64);
 }
 
 // heads backward through Conv1x1 and the hidden ReLU.  block = 8 pixels x 48 channel groups (8 channels each).
@@ -302,6 +405,47 @@ extern "C" int scd_stem_pool_bwd(const uint8_t* argmax, const void* da0, int bat
     stem_pool_bwd_kernel<<<sgrid(total, 256), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const uint2*>(argmax), static_cast<const uint4*>(da0), batch, hp, wp, static_cast<uint4*>(dy0));
     SCD_LAUNCH_CHECK("stem_pool_bwd_kernel");
+    return SCD_OK;
+}
+
+// phase 0: sums_ws[0..127] <- sum dy, sum dy xhat over this rank's pixels (+ with `tail`: the last CTA copies them to
+// local_sums and exchanges them over the ranks like scd_bn_bwd_reduce; sums_ws then holds 128 doubles + a counter cell);
+// phase 1: dz0 from the (possibly all-reduced) sums, d gamma / d beta from local_sums (null: sums_ws).
+extern "C" int scd_stem_bn_pool_bwd(const uint8_t* argmax, const void* da0, const void* z0, const float* scale,
+                                    const float* mean, const float* invstd, int batch, int hp, int wp, double count,
+                                    double* sums_ws, double* local_sums, int tail, void* const* d_peer_buffers, int rank,
+                                    int world, int cap, unsigned seq, long long timeout_cycles, int* status, int phase,
+                                    void* dz0, float* dgamma, float* dbeta, void* stream)
+{
+    using namespace scd;
+    if (!argmax || !da0 || !z0 || !scale || !mean || !invstd || !sums_ws) return fail(SCD_EINVAL, "scd_stem_bn_pool_bwd: null pointer");
+    if (batch <= 0) return SCD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t total = (size_t)batch * hp * wp * 8;
+    size_t grid = (total + 255) / 256;
+    if (phase == 0) {
+        BnTail t = {};
+        if (tail) {
+            int rc = peer_args(t.peer, d_peer_buffers, rank, world, cap, seq, timeout_cycles, status, 128, "scd_stem_bn_pool_bwd");
+            if (rc) return rc;
+            t.counter = reinterpret_cast<unsigned*>(sums_ws + 128);
+            t.local_copy = local_sums;
+        }
+        SCD_CUDA_CHECK(cudaMemsetAsync(sums_ws, 0, sizeof(double) * (128 + (tail ? 1 : 0)), st));
+        if (grid > (size_t)kNumSMs * 2) grid = (size_t)kNumSMs * 2;          // the resident wave: every CTA ends with 128 fp64 atomics
+        stem_bn_pool_bwd_kernel<false><<<(int)grid, 256, 0, st>>>(
+            reinterpret_cast<const uint2*>(argmax), static_cast<const uint4*>(da0), static_cast<const uint4*>(z0), scale, mean,
+            invstd, batch, hp, wp, count, sums_ws, nullptr, nullptr, nullptr, nullptr, t);
+        SCD_LAUNCH_CHECK("stem_bn_pool_bwd_kernel<reduce>");
+    } else {
+        if (!dz0) return fail(SCD_EINVAL, "scd_stem_bn_pool_bwd: dz0 is null");
+        if (grid > (size_t)kNumSMs * 8) grid = (size_t)kNumSMs * 8;
+        stem_bn_pool_bwd_kernel<true><<<(int)grid, 256, 0, st>>>(
+            reinterpret_cast<const uint2*>(argmax), static_cast<const uint4*>(da0), static_cast<const uint4*>(z0), scale, mean,
+            invstd, batch, hp, wp, count, sums_ws, local_sums ? local_sums : sums_ws, static_cast<uint4*>(dz0), dgamma, dbeta,
+            BnTail{});
+        SCD_LAUNCH_CHECK("stem_bn_pool_bwd_kernel<apply>");
+    }
     return SCD_OK;
 }
 

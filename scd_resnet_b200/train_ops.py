@@ -200,6 +200,37 @@ def stem_pool_bwd(argmax, da0):
     return dy0
 
 
+def stem_bn_pool_backward(argmax, da0, z0, ctx, dgamma=None, dbeta=None, all_reduce=None, peer=None, world=1):
+    """dz0 = backward of maxpool3x3s2(relu(bn(z0))) for the gradient da0 of the pooled map, without the intermediate dy0
+    (scd_stem_bn_pool_bwd): stem_pool_bwd + bn_backward in two passes over z0 instead of three over dy0 and two over z0.
+    d gamma / d beta and the exchange over ranks as in bn_backward."""
+    b, hp, wp, _ = argmax.shape
+    dev = da0.device
+    stat, count, sums = ctx["stat"], ctx["count"], ctx["sums"]
+    dz0 = torch.empty_like(z0)
+    local = None
+    with torch.cuda.device(dev):
+        head = (_ptr(argmax), _ptr(da0), _ptr(z0), _ptr(stat[0]), _ptr(stat[2]), _ptr(stat[3]), b, hp, wp, count, _ptr(sums))
+        if _bn_fused(world) and (world == 1 or peer is not None):
+            pa = _NO_PEER
+            if peer is not None and world > 1:
+                pa = peer.next_args()
+                local = torch.empty(128, dtype=torch.float64, device=dev)
+            check(lib.scd_stem_bn_pool_bwd(*head, _ptr(local), 1, *pa, 0, None, None, None, _stream()), "scd_stem_bn_pool_bwd(reduce)")
+        else:
+            check(lib.scd_stem_bn_pool_bwd(*head, None, 0, *_NO_PEER, 0, None, None, None, _stream()), "scd_stem_bn_pool_bwd(reduce)")
+            if world > 1:
+                local = torch.empty(128, dtype=torch.float64, device=dev)
+                local.copy_(sums[:128])
+                if all_reduce is not None:
+                    all_reduce(sums[:128], None)
+                else:
+                    peer(sums[:128])
+        check(lib.scd_stem_bn_pool_bwd(*head, _ptr(local), 0, *_NO_PEER, 1, _ptr(dz0), _ptr(dgamma), _ptr(dbeta), _stream()),
+              "scd_stem_bn_pool_bwd(apply)")
+    return dz0
+
+
 def heads_fwd_train(x, w3, b3, w1, b1):
     b, h, w, cin = x.shape
     dev = x.device

@@ -20,6 +20,8 @@ from ._lib import ScdError
 _HEADS = (("heatmap", 0, 1), ("regr", 1, 4), ("offset", 5, 2))
 # BatchNorm batch statistics from the conv's store epilogue (scd_conv_igemm_fwd_bn); "0" = separate statistics pass
 _CONV_BN_STATS = __import__("os").environ.get("SCD_CONV_BN_STATS", "1") != "0"
+# the stem's pool backward + BatchNorm backward without the intermediate dy0 (scd_stem_bn_pool_bwd); "0" = separate kernels
+_STEM_BWD_FUSED = __import__("os").environ.get("SCD_STEM_BWD_FUSED", "1") != "0"
 
 
 def _block_list(depth, dims):
@@ -429,9 +431,13 @@ class TrainEngine:
             # 3 K gradients are left for optimizer_step).
             if p in ("layer3.0", "layer2.0", "layer1.0"):
                 self._reduce_async(self.g_off[p + ".conv1.weight"], self._reduced_from)
-        dy0 = T.stem_pool_bwd(tape["argmax0"], da)
-        dz0, _ = T.bn_backward(dy0, None, tape["z0"], tape["ctx0"], False, self.g("preprocess.1.weight"),
-                               self.g("preprocess.1.bias"), **self._sync_kw())
+        if _STEM_BWD_FUSED:
+            dz0 = T.stem_bn_pool_backward(tape["argmax0"], da, tape["z0"], tape["ctx0"], self.g("preprocess.1.weight"),
+                                          self.g("preprocess.1.bias"), **self._sync_kw())
+        else:
+            dy0 = T.stem_pool_bwd(tape["argmax0"], da)
+            dz0, _ = T.bn_backward(dy0, None, tape["z0"], tape["ctx0"], False, self.g("preprocess.1.weight"),
+                                   self.g("preprocess.1.bias"), **self._sync_kw())
         T.conv_wgrad(4, tape["col0"], dz0, 64, 64, self.g("preprocess.0.weight"))
 
     def forward_backward(self, x, targets, sigmoid_inplace=False):

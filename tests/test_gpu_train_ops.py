@@ -206,8 +206,20 @@ def test_stem_train(S):
     close(nchw(a0), y.detach())
     assert int(argmax.max()) <= 9
     dy0 = T.stem_pool_bwd(argmax, nhwc(da0))
-    dz0, _ = T.bn_backward(dy0, None, z0, ctx)
+    dg, db = torch.empty(64, device="cuda"), torch.empty(64, device="cuda")
+    dz0, _ = T.bn_backward(dy0, None, z0, ctx, dgamma=dg, dbeta=db)
     close(nchw(dz0), zt.grad)
+    # the fused form (no dy0 in memory, dy kept in fp32): same gradient, same d gamma / d beta
+    for fused in ("0", "1"):
+        T._BN_FUSED_ENV, keep = fused, T._BN_FUSED_ENV
+        try:
+            dg2, db2 = torch.empty(64, device="cuda"), torch.empty(64, device="cuda")
+            dz0f = T.stem_bn_pool_backward(argmax, nhwc(da0), z0, ctx, dg2, db2)
+        finally:
+            T._BN_FUSED_ENV = keep
+        close(nchw(dz0f), zt.grad)
+        close(dz0f, dz0, 1e-2)
+        close(dg2, dg, 1e-2); close(db2, db, 1e-2)
     # weight gradient from the im2col operand written by the forward
     dz = rnd(rng, *z.shape)
     z.backward(dz)
