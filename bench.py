@@ -7,7 +7,7 @@ A step = one pass of the hot path over one batch of 64 synthetic 512x512 tiles o
 stem -> 14 tcgen05 implicit-GEMM stages -> fused heads -> decode (17 kernel launches).
 Prints ONE JSON line (rank 0).  `value` = tiles/s over all GPUs with inputs resident in HBM;
 `e2e` = the same through TileDetector.detect_host with pinned HOST tiles (H2D + D2H inside the timed
-region); `roofline` = the dominant kernel (fused heads igemm) against the measured bf16 peak;
+region), timed for both input forms (grey bytes / float32 tiles), the faster one on this box as the headline; `roofline` = the dominant kernel (fused heads igemm) against the measured bf16 peak;
 `cpu_baseline` = the CPU oracle (a port of the reference's PyTorch path) on this box's host cores.
 `--impl reference` times that CPU path alone.
 """
@@ -32,6 +32,28 @@ WORKLOAD = "configs[1]: centerOffsetRes10 batched inference+decode, batch 64 of 
 # tcgen05 kind::f16 (weights.PRECISIONS["mixed"]: all three heads within the north star's 1e-2 of the fp32 reference;
 # the pure-bf16 and pure-fp16 plans are timed next to it)
 DTYPE = "bf16 weights x fp16 activations, fp32 accumulate"
+
+
+def e2e_entry(world, B, K, u8_ms, f32_ms):
+    """The end-to-end line: both input forms of TileDetector.detect_host are timed (grey bytes normalised on the device, a
+    quarter of the bytes over the host link; float32 tiles normalised on the host, what the reference's test.py uploads);
+    the headline is the faster one on this box, the other is reported beside it."""
+    forms = {
+        "grey_bytes": {"value": world * B * K / (u8_ms * 1e-3), "h2d_bytes_per_step": B * 512 * 512,
+                       "h2d_gb_per_s": round(B * 512 * 512 / (u8_ms / K * 1e-3) / 1e9, 2),
+                       "note": "uint8 tiles as the slide holds them; the per-tile fp64 normalisation (test.py:89) runs on the "
+                               "device (scd_tiles_normalize_u8, +0.05 ms per 64 tiles)"},
+        "float32_tiles": {"value": world * B * K / (f32_ms * 1e-3), "h2d_bytes_per_step": B * 512 * 512 * 4,
+                          "h2d_gb_per_s": round(B * 512 * 512 * 4 / (f32_ms / K * 1e-3) / 1e9, 2),
+                          "note": "tiles normalised on the host arrive as float32, 1 MB each (the reference's own form): needs "
+                                  ">= 24 GB/s of host link per GPU to stay compute bound"},
+    }
+    best = max(forms, key=lambda k: forms[k]["value"])
+    return {"value": forms[best]["value"], "unit": "tiles/s", "h2d_bytes_per_step": forms[best]["h2d_bytes_per_step"],
+            "d2h_bytes_per_step": 10 * B * 100 * 4, "form": best,
+            "api": "TileDetector.detect_host (pinned host tiles -> [per-tile normalise on the device] -> inference + decode -> "
+                   "host detections; copies overlapped with the kernels on three streams)",
+            "grey_bytes": forms["grey_bytes"], "float32_tiles": forms["float32_tiles"]}
 
 
 def workload_config(batch):
@@ -542,15 +564,7 @@ def main():
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
             "config": workload_config(B),
-            "e2e": {"value": world * B * K / (e2e_ms * 1e-3), "unit": "tiles/s",
-                    "h2d_bytes_per_step": B * 512 * 512, "d2h_bytes_per_step": 10 * B * 100 * 4,
-                    "api": "TileDetector.detect_host (pinned host tiles as grey bytes -> per-tile normalise on the device -> "
-                           "inference + decode -> host detections; copies overlapped with the kernels on three streams)",
-                    "h2d_gb_per_s": round(B * 512 * 512 / (e2e_ms / K * 1e-3) / 1e9, 2),
-                    "float32_tiles": {"value": world * B * K / (e2e_f32_ms * 1e-3), "h2d_bytes_per_step": B * 512 * 512 * 4,
-                                      "h2d_gb_per_s": round(B * 512 * 512 * 4 / (e2e_f32_ms / K * 1e-3) / 1e9, 2),
-                                      "note": "tiles normalised on the host arrive as float32, 1 MB each: this form is bound by "
-                                              "the host -> device link of the box"}},
+            "e2e": e2e_entry(world, B, K, e2e_ms, e2e_f32_ms),
             "gpu_launches": 17 * K,
             "roofline": {"kernel": "igemm_kernel<384, EPI_HEADS> (fused heads)", "bound": "tensor",
                          "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,

@@ -140,14 +140,20 @@ def test_analyse_slide_rgb_host_device_and_no_planes(S):
 
 
 def test_detect_host_grey_bytes_equal_normalised_floats(S):
+    """Grey bytes normalised on the device inside detect_host = the same tiles normalised beforehand: the device
+    normalisation matches the oracle's fp64 normalize to an ulp, and fed with bit-identical floats both routes give
+    bit-identical planes.  (Comparing against HOST-normalised floats end to end is not a stable check: an ulp in one input
+    pixel reorders near-tied peaks of these noise tiles, and the fp64 reductions of the host normalisation are not
+    run-to-run reproducible.)"""
     det = _detector(S, batch=4)
     rng = np.random.default_rng(17)
     u8 = [torch.from_numpy(rng.integers(0, 256, size=(4, 1, 512, 512), dtype=np.uint8)).pin_memory() for _ in range(3)]
-    f32 = [torch.stack([O.normalize(t[i].double()).float() for i in range(4)]).pin_memory() for t in u8]
+    dev_norm = [S.ops.tiles_normalize_u8(t.cuda()).cpu() for t in u8]
+    for t, dn in zip(u8, dev_norm):
+        ref = torch.stack([O.normalize(t[i].double()).float() for i in range(4)])
+        assert (dn - ref).abs().max() <= 2.5e-7 * max(1.0, float(ref.abs().max()))
     a = [p.clone() for p in det.detect_host(u8)]
-    b = [p.clone() for p in det.detect_host(f32)]
+    b = [p.clone() for p in det.detect_host([dn.pin_memory() for dn in dev_norm])]
     for pa, pb in zip(a, b):
         assert pa.shape == (10, 4, 100)
-        # the normalised tiles agree to an ulp (fp64 on both sides), the network is deterministic: same peaks
-        assert torch.equal(pa[1], pb[1]) or (pa[1] != pb[1]).float().mean() < 0.02
-        assert (pa[0] - pb[0]).abs().max() < 1e-3
+        assert torch.equal(pa, pb)
