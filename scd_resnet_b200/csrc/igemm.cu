@@ -40,6 +40,7 @@ struct alignas(64) IgemmParams {
     CUtensorMap tmOut[4];           // output views (one per output parity for the deconv), box {64 ch, 16 x, 2 y}
     int n_taps[4], cin_blocks, tiles_x, tiles_y, n_par, n_tiles_n, batch, total_tiles;
     int cout, out_mul, hout, wout, relu;
+    int mt;                         // M sub-tiles (128 pixels each, neighbours in x) per unit: 1, or 2 for BN = 128 (see IgemmCfg)
     int b_resident;                 // BN = 64 only: the whole weight matrix (<= 9 k-blocks) stays in shared memory
     int row_mode;                   // BN = 64, 3x3 s1, Cin = 64, W = 128: one image row per tile, A = 3-row halo strip loaded once
     int bo_mode;                    // row_mode: put (start address >> 7) & 7 into the descriptor's base_offset field
@@ -63,15 +64,20 @@ struct alignas(64) IgemmParams {
     BnTail bn_tail;
 };
 
-template <int BN> struct IgemmCfg {
+// MT = 2 (BN = 128 only): a unit is TWO neighbouring 128-pixel tiles that share every B k-block: 16 + 16 KB of A and 16 KB
+// of B per two MMA groups instead of 16 + 16 KB per one.  The BN = 128 stages are bound by shared-memory fill (35-38 %
+// tensor-pipe active at 32 KB per 128 x 128 x 64 MMA group, profiles/ncu_full_r02.json); two 128-column accumulators per
+// stage still double-buffer in 512 TMEM columns.
+template <int BN, int MT = 1> struct IgemmCfg {
     static constexpr int B_BYTES = BN * IG_BK * 2;
-    static constexpr int STAGE_BYTES = IG_A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 64) ? 5 : (BN == 128 ? 6 : (BN == 256 ? 4 : 3));
+    static constexpr int STAGE_BYTES = MT * IG_A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 64) ? 5 : (BN == 128 ? (MT == 2 ? 4 : 6) : (BN == 256 ? 4 : 3));
     static constexpr int RES_B_BLOCKS = (BN == 64) ? 9 : 0;     // resident weights: 9 k-blocks x 8 KB (layer1: 3x3, Cin 64)
     static constexpr int HALO_W = 130, HALO_BYTES = 3 * HALO_W * 128;       // row mode: 3 rows x 130 px x 64 ch
     static constexpr int HALO_STAGE = 50 * 1024, HALO_STAGES = 2;           // fits into the 5 x 24 KB stage area
-    static constexpr int ACC_STAGES = (2 * BN <= 512) ? 2 : 1;
-    static constexpr int TMEM_COLS = (BN * ACC_STAGES <= 128) ? 128 : (BN * ACC_STAGES <= 256 ? 256 : 512);
+    static constexpr int ACC_STAGES = (2 * BN * MT <= 512) ? 2 : 1;
+    static constexpr int TMEM_COLS = (BN * MT * ACC_STAGES <= 128) ? 128 : (BN * MT * ACC_STAGES <= 256 ? 256 : 512);
+    static_assert(MT == 1 || BN == 128, "two sub-tiles per unit: BN = 128 only");
     static constexpr int B_BOX_ROWS = (BN > 256) ? BN / 2 : BN;
     // [pipeline stages][4 x 4 KB store staging][barriers 256 B][per-warp bias copies | head constants]
     static constexpr int RES_STAGE = IG_BM * 128;                           // row mode: residual row, 16 KB, 2 stages
@@ -88,12 +94,13 @@ template <int BN> struct IgemmCfg {
     static constexpr int SMEM_BYTES = OFF_STATS + STATS_FLOATS * 4 + 1024 /*align slack*/;
 };
 
-template <int BN, int EPI, bool F16>
+template <int BN, int EPI, bool F16, int MT = 1>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_kernel(const __grid_constant__ IgemmParams p)
 {
     using A16 = tc::Act<F16>;
-    using Cfg = IgemmCfg<BN>;
+    using Cfg = IgemmCfg<BN, MT>;
+    const int n_units = p.total_tiles / MT, utiles_x = p.tiles_x / MT;      // units of MT tiles, neighbours in x
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t smem_base = (tc::smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* smem_gen = smem_dyn + (smem_base - tc::smem_u32(smem_dyn));
@@ -172,10 +179,10 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
                     if (++stage == Cfg::HALO_STAGES) { stage = 0; phase ^= 1u; }
                 }
             } else
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            for (int t = blockIdx.x; t < n_units; t += gridDim.x) {
                 const int nt = t % p.n_tiles_n;
                 int m = t / p.n_tiles_n;
-                const int tx = m % p.tiles_x; m /= p.tiles_x;
+                const int tx = (m % utiles_x) * MT; m /= utiles_x;
                 const int ty = m % p.tiles_y; m /= p.tiles_y;
                 const int par = m % p.n_par;
                 const int img = m / p.n_par;
@@ -187,11 +194,13 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
                     for (int cb = 0; cb < p.cin_blocks; ++cb) {
                         tc::mbar_wait(empty_bar(stage), phase ^ 1u);
                         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-                        const uint32_t sb = sa + IG_A_BYTES;
+                        const uint32_t sb = sa + MT * IG_A_BYTES;
                         const int kcol = (tap * p.cin_blocks + cb) * IG_BK;
                         {
-                            tc::mbar_arrive_expect_tx(full_bar(stage), resb ? IG_A_BYTES : Cfg::STAGE_BYTES);
-                            tc::tma_load_4d(ma, full_bar(stage), sa, cb * IG_BK, ax, ay, img);
+                            tc::mbar_arrive_expect_tx(full_bar(stage), resb ? MT * IG_A_BYTES : Cfg::STAGE_BYTES);
+#pragma unroll
+                            for (int j = 0; j < MT; ++j)
+                                tc::tma_load_4d(ma, full_bar(stage), sa + j * IG_A_BYTES, cb * IG_BK, ax + j * IG_TW, ay, img);
                             if (!resb) tc::tma_load_2d(&p.tmB, full_bar(stage), sb, kcol, brow);
                             if (BN > 256)
                                 tc::tma_load_2d(&p.tmB, full_bar(stage), sb + Cfg::B_BOX_ROWS * IG_BK * 2, kcol,
@@ -238,24 +247,26 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
                     if (++stage == Cfg::HALO_STAGES) { stage = 0; phase ^= 1u; }
                 }
             } else
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-                const int k_blocks = p.n_taps[(t / (p.n_tiles_n * p.tiles_x * p.tiles_y)) % p.n_par] * p.cin_blocks;
+            for (int t = blockIdx.x; t < n_units; t += gridDim.x, ++it) {
+                const int k_blocks = p.n_taps[(t / (p.n_tiles_n * utiles_x * p.tiles_y)) % p.n_par] * p.cin_blocks;
                 const uint32_t as = (Cfg::ACC_STAGES == 2) ? (it & 1u) : 0u;
                 const uint32_t aphase = (Cfg::ACC_STAGES == 2) ? ((it >> 1) & 1u) : (it & 1u);
                 tc::mbar_wait(tempty_bar(as), aphase ^ 1u);
                 tc::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BN;
+                const uint32_t d_tmem = tmem_base + as * BN * MT;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     tc::mbar_wait(full_bar(stage), phase);
                     tc::tc_fence_after();
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-                    const uint32_t sb = resb ? smem_base + Cfg::OFF_RESB + kb * Cfg::B_BYTES : sa + IG_A_BYTES;
+                    const uint32_t sb = resb ? smem_base + Cfg::OFF_RESB + kb * Cfg::B_BYTES : sa + MT * IG_A_BYTES;
 #pragma unroll
                     for (int k = 0; k < IG_BK / 16; ++k) {
                         const uint64_t adesc = tc::umma_desc_sw128(sa + k * 32);
                         const uint64_t bdesc = tc::umma_desc_sw128(sb + k * 32);
                         const uint32_t acc = (kb | k) ? 1u : 0u;
                         tc::umma_bf16(d_tmem, adesc, bdesc, idesc_main, acc);
+                        if (MT == 2)                         // the neighbouring tile against the same B k-block
+                            tc::umma_bf16(d_tmem + BN, tc::umma_desc_sw128(sa + IG_A_BYTES + k * 32), bdesc, idesc_main, acc);
                         if (BN > 256) {
                             const uint64_t bdesc2 = tc::umma_desc_sw128(sb + 256 * IG_BK * 2 + k * 32);
                             tc::umma_bf16(d_tmem + 256, adesc, bdesc2, idesc_tail, acc);
@@ -276,21 +287,21 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
         float* my_stats = s_stats + q * 2 * BN;             // [2][BN]: Sum y, Sum y^2 of the channel range stats_nt
         int stats_nt = -1, bias_nt = -1;
         uint32_t it = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        for (int t = blockIdx.x; t < n_units; t += gridDim.x, ++it) {
             const int nt = t % p.n_tiles_n;
             int m = t / p.n_tiles_n;
-            const int tx = m % p.tiles_x; m /= p.tiles_x;
+            int tx = (m % utiles_x) * MT; m /= utiles_x;         // first tile of the unit
             const int ty = m % p.tiles_y; m /= p.tiles_y;
             const int par = m % p.n_par;
             const int img = m / p.n_par;
             const bool rowm = Cfg::RES_B_BLOCKS > 0 && p.row_mode;                   // tile = image row ty, pixel x = TMEM lane
             const int oy = rowm ? ty : (ty * IG_TH + ly) * p.out_mul + (par >> 1);
-            const int ox = rowm ? row : (tx * IG_TW + lx) * p.out_mul + (par & 1);
+            int ox = rowm ? row : (tx * IG_TW + lx) * p.out_mul + (par & 1);
             const uint32_t as = (Cfg::ACC_STAGES == 2) ? (it & 1u) : 0u;
             const uint32_t aphase = (Cfg::ACC_STAGES == 2) ? ((it >> 1) & 1u) : (it & 1u);
             tc::mbar_wait(tfull_bar(as), aphase);
             tc::tc_fence_after();
-            const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+            uint32_t taddr = tmem_base + as * BN * MT + ((uint32_t)(q * 32) << 16);
 
             if (EPI == EPI_STORE) {
                 if (stats && nt != stats_nt) {               // another channel range: hand this warp's sums over first
@@ -314,9 +325,12 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
                     __syncwarp();
                     bias_nt = nt;
                 }
+                const CUtensorMap* mo = rowm ? &p.tmOutRow : &p.tmOut[par];
+#pragma unroll 1
+                for (int j = 0; j < MT; ++j) {               // the tiles of the unit, one after the other
+                if (j > 0) { tx += 1; ox += IG_TW * p.out_mul; taddr += BN; }
                 const size_t pix = ((size_t)img * p.hout + oy) * p.wout + ox;
                 const __nv_bfloat16* rptr = p.residual ? p.residual + pix * p.cout + nt * BN : nullptr;
-                const CUtensorMap* mo = rowm ? &p.tmOutRow : &p.tmOut[par];
                 const int gx = rowm ? 32 * q : tx * IG_TW, gy = rowm ? ty : ty * IG_TH + 2 * q;
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 64) {
@@ -336,7 +350,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
                     tc::tmem_ld32(taddr + c0, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
                     tc::tmem_ld32(taddr + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
                     tc::tmem_ld_wait();
-                    if (c0 + 64 >= BN) {                     // last TMEM read of this tile: release the accumulator
+                    if (c0 + 64 >= BN && j == MT - 1) {      // last TMEM read of this unit: release the accumulator
                         tc::tc_fence_before();
                         tc::mbar_arrive(tempty_bar(as));
                     }
@@ -388,6 +402,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
                         st[0] += s0; st[1] += s1; st[BN] += q0; st[BN + 1] += q1;
                     }
                 }
+                }                                            // j: tiles of the unit
             } else {
                 // heads: hidden = ReLU(acc + b3); out_j = b1_j + sum_c hidden[head(j), c] * w1[j, c]
                 const float* b3 = head_const;
@@ -489,13 +504,14 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
 }
 
 // ---------------------------------------------------------------------------- host side
-template <int BN, int EPI, bool F16 = false>
+template <int BN, int EPI, bool F16 = false, int MT = 1>
 static int launch_igemm(const IgemmParams& p, cudaStream_t st)
 {
-    using Cfg = IgemmCfg<BN>;
-    const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-    SCD_SMEM_ATTR((igemm_kernel<BN, EPI, F16>), Cfg::SMEM_BYTES);
-    SCD_CUDA_CHECK(launch_pdl(igemm_kernel<BN, EPI, F16>, dim3(grid), dim3(IG_THREADS), Cfg::SMEM_BYTES, st, p));
+    using Cfg = IgemmCfg<BN, MT>;
+    const int units = p.total_tiles / MT;
+    const int grid = units < kNumSMs ? units : kNumSMs;
+    SCD_SMEM_ATTR((igemm_kernel<BN, EPI, F16, MT>), Cfg::SMEM_BYTES);
+    SCD_CUDA_CHECK(launch_pdl(igemm_kernel<BN, EPI, F16, MT>, dim3(grid), dim3(IG_THREADS), Cfg::SMEM_BYTES, st, p));
     SCD_LAUNCH_CHECK("igemm_kernel");
     return SCD_OK;
 }
@@ -660,13 +676,16 @@ static int conv_igemm(int kind, const void* x, const void* x2, const void* weigh
         if (rc) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    // BN = 128: units of two neighbouring tiles when the tile grid allows it (SCD_IGEMM_MT=1 keeps single tiles)
+    static const int mt_env = [] { const char* e = getenv("SCD_IGEMM_MT"); return e ? atoi(e) : 2; }();
+    p.mt = (bn == 128 && mt_env >= 2 && p.tiles_x % 2 == 0) ? 2 : 1;
     if (f16) {
         if (bn == 256) return launch_igemm<256, EPI_STORE, true>(p, st);
-        if (bn == 128) return launch_igemm<128, EPI_STORE, true>(p, st);
+        if (bn == 128) return p.mt == 2 ? launch_igemm<128, EPI_STORE, true, 2>(p, st) : launch_igemm<128, EPI_STORE, true>(p, st);
         return launch_igemm<64, EPI_STORE, true>(p, st);
     }
     if (bn == 256) return launch_igemm<256, EPI_STORE>(p, st);
-    if (bn == 128) return launch_igemm<128, EPI_STORE>(p, st);
+    if (bn == 128) return p.mt == 2 ? launch_igemm<128, EPI_STORE, false, 2>(p, st) : launch_igemm<128, EPI_STORE>(p, st);
     return launch_igemm<64, EPI_STORE>(p, st);
 }
 
