@@ -302,15 +302,19 @@ def main():
     # the host, 4x the bytes over the host link) is timed as well.
     def e2e_run(host):
         det.detect_host([host[i % 3] for i in range(3)])
-        barrier()
-        t0 = time.perf_counter()
-        det.detect_host([host[i % 3] for i in range(K)])
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        # device-side bracket: first upload enqueued -> last download finished (events on the copy streams); the
-        # host wall clock around the same call is reported too and the slower of the two is used
-        dev_ms = det.t_first.elapsed_time(det.t_last)
-        barrier()
-        return max(dev_ms, wall_ms)
+        best = None
+        for _ in range(2):                      # two passes of K steps, the better one: a host hiccup (page faults of the
+            barrier()                           # freshly pinned buffers, another rank's setup) is not the pipeline's rate
+            t0 = time.perf_counter()
+            det.detect_host([host[i % 3] for i in range(K)])
+            wall_ms = (time.perf_counter() - t0) * 1e3
+            # device-side bracket: first upload enqueued -> last download finished (events on the copy streams); the
+            # host wall clock around the same call is taken too and the slower of the two is used
+            dev_ms = det.t_first.elapsed_time(det.t_last)
+            barrier()
+            ms = max(dev_ms, wall_ms)
+            best = ms if best is None else min(best, ms)
+        return best
 
     gh = torch.Generator().manual_seed(11 + rank)
     host_u8 = [torch.randint(0, 256, (B, 1, 512, 512), dtype=torch.uint8, generator=gh).pin_memory() for _ in range(3)]
