@@ -380,7 +380,8 @@ int scd_heads_bwd(const float* d_heat, const float* d_regr, const float* d_off, 
  *                           f32 = hidden gradient of the regr (0..127) and offset (128..255) heads per object,
  *                           and the gradients of w1 (7,128), b1 (7), b3 (384);
  *   scd_heads_wgrad_sparse  out[tap][co][ci] (9,256,cin) f32 = gradient of w3 rows 128..383 (regr, offset heads),
- *                           x = the heads' input (B,H,W,cin) bf16 (cin = 256 for the full-width networks);
+ *                           x = the heads' input (B,H,W,cin) bf16 (cin = 256 for the full-width networks); `out` is
+ *                           cleared by the call (the object ranges accumulate into it with 16-byte reductions);
  *   scd_heads_dgrad_sparse  dx (B,H,W,cin) bf16 += dh_objects . w3[128:384] around every object pixel
  *                           (w3 = the (384, 9*cin) bf16 forward operand); call after the dense data gradient. */
 int scd_heads_bwd_sparse(const float* d_heat, const float* d_obj, const uint8_t* mask, const int64_t* idx,
