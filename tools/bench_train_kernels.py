@@ -72,6 +72,17 @@ def main():
     out = torch.zeros(9, 256, 256, device=dev)
     res["heads_sparse_us"] = {"dgrad_objects": timed(lambda: T.heads_dgrad_sparse(dh, mask, idx, w3, dx)),
                               "wgrad_objects": timed(lambda: T.heads_wgrad_sparse(x, dh, mask, idx, out))}
+    # the stem's backward: pool backward + BatchNorm backward, fused (no dy0) and as separate kernels
+    z0 = act(256, 64)
+    gamma, beta = torch.ones(64, device=dev), torch.zeros(64, device=dev)
+    _, ctx0 = T.bn_forward(z0, gamma, beta)
+    a0, argmax = T.stem_bn_relu_pool(z0, ctx0["stat"])
+    da0 = act(128, 64)
+    def separate():
+        dy0 = T.stem_pool_bwd(argmax, da0)
+        T.bn_backward(dy0, None, z0, ctx0)
+    res["stem_backward_us"] = {"fused": timed(lambda: T.stem_bn_pool_backward(argmax, da0, z0, ctx0)), "separate": timed(separate),
+                               "pool_forward": timed(lambda: T.stem_bn_relu_pool(z0, ctx0["stat"]))}
     print(json.dumps(res))
     if "--out" in sys.argv:
         json.dump(res, open(sys.argv[sys.argv.index("--out") + 1], "w"), indent=1)
