@@ -13,9 +13,10 @@
 // 64-channel blocks sit 8 KB apart (descriptor LBO), 8-pixel groups 1 KB apart (SBO).  The tap shift
 // and the conv zero padding are again just TMA coordinates.
 //
-// M tile = two (tap, 64-channel) chunks of S, N tile = up to 256 channels of P, the pixel range of a
-// work unit is one of `splits` interleaved slices (split-K); partial tiles are accumulated into the fp32
-// gradient buffer with coalesced red.global.add.  Same warp roles as igemm.cu.
+// M sub-tile = two (tap, 64-channel) chunks of S (a unit accumulates one or two of them against the same P tile, see
+// WgCfg), N tile = up to 256 channels of P, the pixel range of a work unit is one of `splits` interleaved slices
+// (split-K); partial tiles are accumulated into the fp32 gradient buffer with coalesced red.global.add.  Same warp
+// roles as igemm.cu.
 #include <cstdlib>
 #include "tc.cuh"
 #include "tmap.cuh"
