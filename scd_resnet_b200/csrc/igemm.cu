@@ -354,8 +354,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
                         tc::tc_fence_before();
                         tc::mbar_arrive(tempty_bar(as));
                     }
-                    if (lane == 0) tc::bulk_wait_read0();    // previous store has finished reading the staging tile
-                    __syncwarp();
+                    uint4 ov[8];                             // the packed tile row of this lane: all math before the wait below
 #pragma unroll
                     for (int ch = 0; ch < 8; ++ch) {
                         const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c0 + ch * 8);
@@ -374,11 +373,14 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
 #pragma unroll
                             for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
                         }
-                        uint4 o;
-                        o.x = A16::pack(v[0], v[1]); o.y = A16::pack(v[2], v[3]);
-                        o.z = A16::pack(v[4], v[5]); o.w = A16::pack(v[6], v[7]);
-                        *reinterpret_cast<uint4*>(stg_gen + lane * 128 + ((ch ^ (lane & 7)) << 4)) = o;
+                        ov[ch].x = A16::pack(v[0], v[1]); ov[ch].y = A16::pack(v[2], v[3]);
+                        ov[ch].z = A16::pack(v[4], v[5]); ov[ch].w = A16::pack(v[6], v[7]);
                     }
+                    if (lane == 0) tc::bulk_wait_read0();    // previous store has finished reading the staging tile
+                    __syncwarp();
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch)
+                        *reinterpret_cast<uint4*>(stg_gen + lane * 128 + ((ch ^ (lane & 7)) << 4)) = ov[ch];
                     tc::fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
