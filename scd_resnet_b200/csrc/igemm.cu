@@ -341,6 +341,10 @@ igemm_kernel(const __grid_constant__ IgemmParams p)
                         const unsigned char* rsm = smem_gen + Cfg::OFF_ROWRES + rs * Cfg::RES_STAGE + row * 128;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) resv[i] = *reinterpret_cast<const uint4*>(rsm + ((i ^ (row & 7)) << 4));
+                        // the reads above are generic-proxy, the producer's next TMA load into this stage is async-proxy:
+                        // order them before the release (without the fence the LAST warp to arrive saw the tail of its
+                        // row overwritten by the load for the tile after next: a rare, timing-dependent wrong residual)
+                        tc::fence_proxy_async();
                         tc::mbar_arrive(rempty_bar(rs));
                     } else if (rptr) {
 #pragma unroll

@@ -51,6 +51,17 @@ def main():
             else:
                 bad += int(any(not torch.equal(a, b) for a, b in zip(got, ref)))
         out[name] = {"runs": reps // 4, "differ": bad}
+    # three batches in flight, repeated: planes AND the whole activation workspace of the last batch
+    ref, bad = None, 0
+    for _ in range(reps // 2):
+        got = [p.clone() for p in det.detect_host(u8)]
+        torch.cuda.synchronize()
+        ws = det.workspace.clone()
+        if ref is None:
+            ref = (got, ws)
+        else:
+            bad += int(not torch.equal(ws, ref[1]) or any(not torch.equal(a, b) for a, b in zip(got, ref[0])))
+    out["detect_host_u8_workspace"] = {"runs": reps // 2, "differ": bad}
     print(json.dumps(out))
 
 
